@@ -1,0 +1,38 @@
+"""Copies the reference's own golden fixtures for the raster hot path into tests/golden/.
+
+Run in the build container (where /root/reference exists).  The copied files are test FIXTURES
+(golden PNGs the reference's tests compare against, SURVEY.md section 4, and the tiger SVG input of
+BASELINE config 2), not reference source code.  /root/reference does not exist on the GPU box,
+so tests and bench.py read only the copies committed here.
+"""
+import os
+import shutil
+import sys
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+PATHS = """pathStroke1 pathStroke2 pathStroke3 pathBlackRectangle pathBlackRectangleZ pathYellowRectangle
+pathRedRectangle pathBottomArc pathHeart pathRotatedArc pathInvertedCornerArc pathCornerArc pixelScale
+boxRound boxBevel boxMiter ButtCap RoundCap SquareCap dashes selfclosing rectExcludeMask rectExcludeMaskAA
+rectMask rectMaskAA rectMaskStroke opacityFill opacityStroke pathStroke1Big path1pxCover path0pxCover
+polygon3 polygon4 polygon5 polygon6 polygon7 polygon8 pathSwish miterLimit_10deg_2.00num
+miterLimit_145deg_2.00num miterLimit_155deg_2.00num miterLimit_165deg_2.00num miterLimit_165deg_10.00num
+miterLimit_145deg_3.32num miterLimit_145deg_3.33num""".split()
+
+FILES = [(f"tests/paths/{n}.png", f"paths_{n}.png") for n in PATHS] + [
+    ("tests/images/imageblur20.png", "images_imageblur20.png"),
+    ("tests/images/imageblur20oob.png", "images_imageblur20oob.png"),
+    ("tests/contexts/blendmode_1.png", "contexts_blendmode_1.png"),
+    ("examples/heart.png", "examples_heart.png"),
+    ("examples/shadow.png", "examples_shadow.png"),
+    ("examples/masking.png", "examples_masking.png"),
+    ("examples/blur.png", "examples_blur.png"),
+    ("examples/data/trees.png", "examples_data_trees.png"),
+    ("examples/data/tiger.svg", "tiger.svg"),
+    ("tests/fileformats/svg/masters/Ghostscript_Tiger.png", "svg_masters_Ghostscript_Tiger.png"),
+] + [(f"tests/images/maskClearsOnDraw{i}.png", f"images_maskClearsOnDraw{i}.png") for i in range(5)]
+
+for src, dst in FILES:
+    shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
+    print(dst)

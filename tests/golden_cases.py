@@ -1,0 +1,378 @@
+"""The reference's own golden-image test cases for the raster hot path, restated as data.
+
+Each case mirrors a block of /root/reference/tests/test_paths.nim, test_images.nim,
+test_contexts.nim, test_images_draw.nim or an examples/*.nim program (cited per case) and renders
+through a *backend* — the CPU oracle (tests/_oracle.py) or the CUDA C ABI (tests/_gpu_backend.py)
+— so the same table pins the oracle against the goldens and the GPU against the oracle.
+
+Backend protocol (numpy uint8 [h, w, 4] premultiplied RGBX images):
+    fill_segments(img, segs, rgbx, rule, mode)   in place
+    blend_rect(dst, src, px, py, mode)           in place
+    blur(img, lut, radius, oob_rgbx)             in place
+    shadow(img, ox, oy, spread, lut, radius, rgbx) -> new image
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+
+from pixie_b200 import host
+from pixie_b200.common import (ExcludeMaskBlend, ExclusionBlend, MaskBlend, NormalBlend, OverwriteBlend,
+                               parseHtmlColor, rgbx as pack_rgbx)
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# --------------------------------------------------------------------------- colour plumbing
+def color_to_rgbx(r, g, b, a, opacity=1.0):
+    """paint.color (chroma Color, float32) -> color.a *= opacity -> asRgbx() (paths.nim:2110-2112,1603)."""
+    f = np.float32
+    a = f(a) * f(opacity)
+
+    def q(v):
+        return int(math.floor(float(f(v) * f(255)) + 0.5))
+
+    r8, g8, b8, a8 = q(r), q(g), q(b), q(a)
+    if a8 != 255:
+        r8, g8, b8 = (r8 * a8 + 127) // 255, (g8 * a8 + 127) // 255, (b8 * a8 + 127) // 255
+    return pack_rgbx(r8, g8, b8, a8)
+
+
+def rgba8(r, g, b, a, opacity=1.0):
+    f = np.float32
+    return color_to_rgbx(f(r) / f(255), f(g) / f(255), f(b) / f(255), f(a) / f(255), opacity)
+
+
+def html(s, opacity=1.0):
+    return rgba8(*parseHtmlColor(s), opacity=opacity)
+
+
+def new_image(w, h, fill_rgbx=None):
+    img = np.zeros((h, w, 4), np.uint8)
+    if fill_rgbx is not None:
+        img.view(np.uint32)[...] = fill_rgbx
+    return img
+
+
+WHITE = pack_rgbx(255, 255, 255, 255)
+
+
+def fillPath(be, img, path, rgbx, transform=None, rule=host.NonZero, blend=NormalBlend):
+    """fillPath, solid paint branch (paths.nim:2106-2113)."""
+    if (rgbx >> 24) == 0 and blend != OverwriteBlend:
+        return
+    segs = host.fill_segments(path, transform)
+    be.fill_segments(img, segs, rgbx, rule, blend)
+
+
+def strokePath(be, img, path, rgbx, transform=None, strokeWidth=1.0, lineCap=host.ButtCap,
+               lineJoin=host.MiterJoin, miterLimit=host.defaultMiterLimit, dashes=(), blend=NormalBlend):
+    """strokePath, solid paint branch (paths.nim:2161-2176): always NonZero."""
+    if (rgbx >> 24) == 0 and blend != OverwriteBlend:
+        return
+    segs = host.stroke_segments(path, transform, strokeWidth, lineCap, lineJoin, miterLimit, dashes)
+    be.fill_segments(img, segs, rgbx, host.NonZero, blend)
+
+
+# --------------------------------------------------------------------------- cases
+CASES = {}
+
+
+def case(golden):
+    def deco(fn):
+        CASES[golden] = fn
+        return fn
+    return deco
+
+
+def _simple_stroke(golden, w, h, path, rgba, sw):
+    @case(golden)
+    def _f(be):
+        img = new_image(w, h)
+        strokePath(be, img, path, rgba8(*rgba), strokeWidth=sw)
+        return img
+
+
+def _simple_fill(golden, w, h, path, rgbx_, bg=None):
+    @case(golden)
+    def _f(be):
+        img = new_image(w, h, bg)
+        fillPath(be, img, path, rgbx_)
+        return img
+
+
+# tests/test_paths.nim:51-74, 608-614
+_simple_stroke("paths_pathStroke1.png", 100, 100, "M 10 10 L 90 90", (255, 0, 0, 255), 10)
+_simple_stroke("paths_pathStroke2.png", 100, 100, "M 10 10 L 50 60 90 90", (255, 0, 0, 255), 10)
+_simple_stroke("paths_pathStroke3.png", 100, 100, "M 15 10 L 30 90 60 30 90 90", (255, 255, 0, 255), 10)
+_simple_stroke("paths_pathStroke1Big.png", 100, 100, "M0 0 L200 200", (255, 0, 0, 255), 10)
+# tests/test_paths.nim:76-156
+_simple_fill("paths_pathBlackRectangle.png", 100, 100, "M 10 10 H 90 V 90 H 10 L 10 10", rgba8(0, 0, 0, 255))
+_simple_fill("paths_pathBlackRectangleZ.png", 100, 100, "M 10 10 H 90 V 90 H 10 Z", rgba8(0, 0, 0, 255))
+_simple_fill("paths_pathYellowRectangle.png", 100, 100, "M 10 10 H 90 V 90 H 10 L 10 10", rgba8(255, 255, 0, 255))
+_simple_fill("paths_pathBottomArc.png", 100, 100, "M30 60 A 20 20 0 0 0 90 60 L 30 60", html("#FC427B"))
+_simple_fill("paths_pathHeart.png", 100, 100, """
+      M 10,30
+      A 20,20 0,0,1 50,30
+      A 20,20 0,0,1 90,30
+      Q 90,60 50,90
+      Q 10,60 10,30 z
+    """, html("#FC427B"))
+_simple_fill("paths_pathRotatedArc.png", 100, 100, "M 20 50 A 20 10 45 1 1 80 50 L 20 50", html("#FC427B"))
+_simple_fill("paths_pathInvertedCornerArc.png", 100, 100, "M 0 50 A 50 50 0 0 0 50 0 L 50 50 L 0 50", html("#FC427B"))
+_simple_fill("paths_pathCornerArc.png", 100, 100, "M 0 50 A 50 50 0 0 1 50 0 L 50 50 L 0 50", html("#FC427B"))
+# tests/test_paths.nim:616-630
+_simple_fill("paths_path1pxCover.png", 100, 100, "M99 99 L999 99 L999 100 L99 100 Z", rgba8(255, 0, 0, 255))
+_simple_fill("paths_path0pxCover.png", 100, 100, "M100 100 L999 100 L999 101 L100 101 Z", rgba8(255, 0, 0, 255))
+# tests/test_paths.nim:315-322, 701-710
+_simple_fill("paths_selfclosing.png", 60, 60, "M0 0 L0 0 L60 0 L60 60 L0 60", rgba8(127, 127, 127, 255), WHITE)
+_simple_fill("paths_pathSwish.png", 100, 100, "M 40 40 L 40 80 L 80 80 L 80 40 C 80 -20 40 100 40 40",
+             rgba8(0, 0, 0, 255), WHITE)
+# examples/heart.nim
+_simple_fill("examples_heart.png", 200, 200, """
+    M 20 60
+    A 40 40 90 0 1 100 60
+    A 40 40 90 0 1 180 60
+    Q 180 120 100 180
+    Q 20 120 20 60
+    z
+  """, html("#FC427B"), WHITE)
+
+
+@case("paths_pathRedRectangle.png")  # tests/test_paths.nim:101-111
+def _red_rect(be):
+    p = host.newPath()
+    p.moveTo(10, 10)
+    p.lineTo(10, 90)
+    p.lineTo(90, 90)
+    p.lineTo(90, 10)
+    p.lineTo(10, 10)
+    img = new_image(100, 100)
+    fillPath(be, img, p, rgba8(255, 0, 0, 255))
+    return img
+
+
+@case("paths_pixelScale.png")  # tests/test_paths.nim:175-185
+def _pixel_scale(be):
+    img = new_image(200, 200, WHITE)
+    p = host.parsePath("M1 0.5C1 0.776142 0.776142 1 0.5 1C0.223858 1 0 0.776142 0 0.5C0 0.223858 0.223858 0 0.5 0"
+                       "C0.776142 0 1 0.223858 1 0.5Z")
+    fillPath(be, img, p, rgba8(255, 0, 0, 255), host.scale(200, 200))
+    strokePath(be, img, p, rgba8(0, 255, 0, 255), host.scale(200, 200), strokeWidth=0.01)
+    return img
+
+
+def _box(golden, path, cap, join):  # tests/test_paths.nim:187-257
+    @case(golden)
+    def _f(be):
+        img = new_image(60, 60, WHITE)
+        strokePath(be, img, path, rgba8(0, 0, 0, 255), host.translate(10, 10), 10, cap, join)
+        return img
+
+
+_box("paths_boxRound.png", "M 3 3 L 20 3 L 20 20 L 3 20 Z", host.RoundCap, host.RoundJoin)
+_box("paths_boxBevel.png", "M 3 3 L 20 3 L 20 20 L 3 20 Z", host.RoundCap, host.BevelJoin)
+_box("paths_boxMiter.png", "M 3 3 L 20 3 L 20 20 L 3 20 Z", host.RoundCap, host.MiterJoin)
+_box("paths_ButtCap.png", "M 3 3 L 20 3 L 20 20 L 3 20", host.ButtCap, host.BevelJoin)
+_box("paths_RoundCap.png", "M 3 3 L 20 3 L 20 20 L 3 20", host.RoundCap, host.BevelJoin)
+_box("paths_SquareCap.png", "M 3 3 L 20 3 L 20 20 L 3 20", host.SquareCap, host.BevelJoin)
+
+
+@case("paths_dashes.png")  # tests/test_paths.nim:259-291
+def _dashes(be):
+    img = new_image(60, 120, WHITE)
+    path = host.parsePath("M 0 0 L 50 0")
+    for ty, d in [(5, ()), (25, (2, 2)), (45, (4, 4)), (65, (2, 4, 6, 2)), (85, (1,)),
+                  (105, (1, 2, 3, 4, 5, 6, 7, 8, 9))]:
+        strokePath(be, img, path, rgba8(0, 0, 0, 255), host.translate(5, ty), 10, host.ButtCap, host.BevelJoin,
+                   dashes=d)
+    return img
+
+
+def _miter(angle, limit):  # tests/test_paths.nim:293-313
+    name = f"paths_miterLimit_{int(angle)}deg_{limit:0.2f}num.png"
+
+    @case(name)
+    def _f(be):
+        img = new_image(60, 60, WHITE)
+        p = host.newPath()
+        p.moveTo(-20, 0)
+        p.lineTo(0, 0)
+        th = float(np.float32(angle) * np.float32(math.pi / 180)) + math.pi / 2   # degToRad (f32) + PI/2 (f64)
+        p.lineTo(math.sin(th) * 20, math.cos(th) * 20)
+        strokePath(be, img, p, rgba8(0, 0, 0, 255), host.translate(30, 30), 8, host.ButtCap, host.MiterJoin,
+                   miterLimit=limit)
+        return img
+
+
+for _a, _l in [(10, 2), (145, 2), (155, 2), (165, 2), (165, 10), (145, 3.32), (145, 3.33)]:
+    _miter(_a, _l)
+
+
+def _rect_mask(golden, p1, p2, mode, stroke=False):  # tests/test_paths.nim:362-446
+    @case(golden)
+    def _f(be):
+        img = new_image(100, 100)
+        fillPath(be, img, p1, pack_rgbx(255, 0, 0, 255))
+        green = color_to_rgbx(0, 1, 0, 1)
+        if stroke:
+            strokePath(be, img, p2, green, strokeWidth=10, blend=mode)
+        else:
+            fillPath(be, img, p2, green, blend=mode)
+        return img
+
+
+_rect_mask("paths_rectExcludeMask.png", "M 10 10 H 60 V 60 H 10 z", "M 30 30 H 80 V 80 H 30 z", ExcludeMaskBlend)
+_rect_mask("paths_rectExcludeMaskAA.png", "M 10.1 10.1 H 60.1 V 60.1 H 10.1 z", "M 30.1 30.1 H 80.1 V 80.1 H 30.1 z",
+           ExcludeMaskBlend)
+_rect_mask("paths_rectMask.png", "M 10 10 H 60 V 60 H 10 z", "M 30 30 H 80 V 80 H 30 z", MaskBlend)
+_rect_mask("paths_rectMaskAA.png", "M 10.1 10.1 H 60.1 V 60.1 H 10.1 z", "M 30.1 30.1 H 80.1 V 80.1 H 30.1 z", MaskBlend)
+_rect_mask("paths_rectMaskStroke.png", "M 10 10 H 60 V 60 H 10 z", "M 30 30 H 50 V 50 H 30 z", MaskBlend, stroke=True)
+
+
+@case("paths_opacityFill.png")  # tests/test_paths.nim:582-593
+def _opacity_fill(be):
+    p = host.newPath()
+    p.circle(50, 50, 30)
+    img = new_image(100, 100)
+    fillPath(be, img, p, color_to_rgbx(1, 0, 1, 1, opacity=0.5))
+    return img
+
+
+@case("paths_opacityStroke.png")  # tests/test_paths.nim:595-606
+def _opacity_stroke(be):
+    p = host.newPath()
+    p.circle(50, 50, 30)
+    img = new_image(100, 100)
+    strokePath(be, img, p, color_to_rgbx(1, 0, 1, 1, opacity=0.5), strokeWidth=10)
+    return img
+
+
+def _polygon(i):  # tests/test_paths.nim:650-657
+    @case(f"paths_polygon{i}.png")
+    def _f(be):
+        p = host.newPath()
+        p.polygon(50, 50, 30, i)
+        img = new_image(100, 100)
+        fillPath(be, img, p, color_to_rgbx(1, 1, 1, 1))
+        return img
+
+
+for _i in range(3, 9):
+    _polygon(_i)
+
+
+@case("contexts_blendmode_1.png")  # tests/test_contexts.nim:525-537 (ctx.fillRect -> path.rect -> fillPath)
+def _blendmode_1(be):
+    img = new_image(300, 150, WHITE)
+    p = host.newPath()
+    p.rect(10, 10, 100, 100)
+    fillPath(be, img, p, color_to_rgbx(0, 0, 1, 1), blend=ExclusionBlend)
+    return img
+
+
+def _blur_case(golden, oob):  # tests/test_images.nim:126-140
+    @case(golden)
+    def _f(be):
+        img = new_image(100, 100, pack_rgbx(0, 0, 0, 255))
+        p = host.newPath()
+        p.rect(25, 25, 50, 50)
+        fillPath(be, img, p, rgba8(255, 255, 255, 255))
+        be.blur(img, host.gaussianKernel(20), 20, oob)
+        return img
+
+
+_blur_case("images_imageblur20.png", 0)
+_blur_case("images_imageblur20oob.png", pack_rgbx(0, 0, 0, 255))
+
+
+def _mask_clears(i, tx, ty):  # tests/test_images_draw.nim:309-331
+    @case(f"images_maskClearsOnDraw{i}.png")
+    def _f(be):
+        p = host.newPath()
+        p.rect(10, 10, 80, 80)
+        mask = new_image(100, 100)
+        fillPath(be, mask, p, color_to_rgbx(1, 1, 1, 1))
+        a = new_image(100, 100, color_to_rgbx(0, 0, 1, 1))
+        be.blend_rect(a, mask, tx, ty, MaskBlend)
+        return a
+
+
+for _i, (_tx, _ty) in enumerate([(0, 0), (50, -50), (50, 50), (-50, 50), (-50, -50)]):
+    _mask_clears(_i, _tx, _ty)
+
+
+@case("examples_shadow.png")  # examples/shadow.nim
+def _shadow(be):
+    img = new_image(200, 200, WHITE)
+    p = host.newPath()
+    p.polygon(100, 100, 70, 8)
+    poly = new_image(200, 200)
+    fillPath(be, poly, p, rgba8(255, 255, 255, 255))
+    sh = be.shadow(poly, 2, 2, 2, host.gaussianKernel(10), 10, rgba8(0, 0, 0, 200))
+    be.blend_rect(img, sh, 0, 0, NormalBlend)
+    be.blend_rect(img, poly, 0, 0, NormalBlend)
+    return img
+
+
+HEART = """
+    M 20 60
+    A 40 40 90 0 1 100 60
+    A 40 40 90 0 1 180 60
+    Q 180 120 100 180
+    Q 20 120 20 60
+    z
+  """
+
+
+@case("examples_masking.png")  # examples/masking.nim (ctx.strokeSegment = strokePath of moveTo/lineTo, contexts.nim:709-715)
+def _masking(be):
+    image = new_image(200, 200, WHITE)
+    lines = new_image(200, 200, html("#FC427B"))
+    mask = new_image(200, 200)
+    for (ax, ay, bx, by) in [(25, 25, 175, 175), (25, 175, 175, 25)]:
+        p = host.newPath()
+        p.moveTo(ax, ay)
+        p.lineTo(bx, by)
+        strokePath(be, lines, p, html("#F8D1DD"), strokeWidth=30)
+    fillPath(be, mask, HEART, color_to_rgbx(1, 1, 1, 1))
+    be.blend_rect(lines, mask, 0, 0, MaskBlend)
+    be.blend_rect(image, lines, 0, 0, NormalBlend)
+    return image
+
+
+@case("examples_blur.png")  # examples/blur.nim
+def _blur_example(be):
+    trees = load_golden("examples_data_trees.png")
+    blur = trees.copy()
+    image = new_image(200, 200, WHITE)
+    p = host.newPath()
+    p.polygon(100, 100, 70, 6)
+    mask = new_image(200, 200)
+    fillPath(be, mask, p, color_to_rgbx(1, 1, 1, 1))
+    be.blur(blur, host.gaussianKernel(20), 20, 0)
+    be.blend_rect(blur, mask, 0, 0, MaskBlend)
+    be.blend_rect(image, trees, 0, 0, NormalBlend)
+    be.blend_rect(image, blur, 0, 0, NormalBlend)
+    return image
+
+
+# --------------------------------------------------------------------------- helpers
+def load_golden(name):
+    """PNG (straight RGBA) -> premultiplied RGBX with (c*a+127) div 255 (png.nim:652-660)."""
+    from PIL import Image
+
+    g = np.array(Image.open(os.path.join(GOLDEN_DIR, name)).convert("RGBA"))
+    a = g[..., 3:4].astype(np.uint32)
+    rgb = (g[..., :3].astype(np.uint32) * a + 127) // 255
+    return np.ascontiguousarray(np.concatenate([rgb, a], axis=-1).astype(np.uint8))
+
+
+def compare(a, b):
+    """-> (mismatching pixels, max |delta| per channel)."""
+    if a.shape != b.shape:
+        return a.shape[0] * a.shape[1], 255
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    return int((d.max(axis=-1) > 0).sum()), int(d.max())
