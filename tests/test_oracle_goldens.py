@@ -21,4 +21,4 @@ def test_scalar_semantics_within_one_lsb(name):
     out = gc.CASES[name](OracleBackend(sem=1))
     mism, mx = gc.compare(out, gc.load_golden(name))
     assert mx <= 1, f"{name}: scalar semantics differ by {mx} LSB"
-    assert mism <= 0.02 * out.shape[0] * out.shape[1]
+    assert mism <= 0.05 * out.shape[0] * out.shape[1]
