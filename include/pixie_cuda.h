@@ -1,0 +1,146 @@
+/*
+ * pixie_cuda.h — C ABI of pixie_cuda.so, the B200 (sm_100a) raster hot path behind Pixie's
+ * public procs.  This is the drop-in boundary: a Nim shim ({.importc, dynlib: "pixie_cuda.so".},
+ * see INTEGRATION.md and pixie_b200/nim/pixie_cuda.nim) replaces the BODIES of the procs cited
+ * below and calls these entry points; signatures of the public procs do not change.
+ *
+ * Conventions
+ *   - every function returns 0 on success; 1 = the condition under which the reference raises
+ *     PixieError (src/pixie/common.nim:4) — the shim does
+ *     `raise newException(PixieError, $pixie_cuda_last_error())`; 2 = CUDA runtime error (sticky,
+ *     message verbatim).  There is NO CPU fallback.
+ *   - images are premultiplied-alpha RGBX, 4 bytes/pixel, row-major, index = width*y + x
+ *     (common.nim:34-37,56-57).  A8 images (1 byte/pixel) exist only as coverage masks.
+ *   - enums are passed as int: ord(BlendMode) per common.nim:6-29 (Normal=0 .. Luminosity=15,
+ *     Mask=16, Overwrite=17, SubtractMask=18, ExcludeMask=19); WindingRule NonZero=0, EvenOdd=1
+ *     (paths.nim:5-8).
+ *   - colours are packed ColorRGBX: r | g<<8 | b<<16 | a<<24, already premultiplied
+ *     (what color.asRgbx() yields at paths.nim:1603).
+ *   - the library never keeps a host pointer after a call returns.  Device work is issued on one
+ *     stream (pixie_cuda_set_stream) in call order = the reference's sequential semantics; only
+ *     *_download, *_host and pixie_cuda_sync block the host.
+ *   - numerics: bit-exact with the reference's x86 row kernels applied to every pixel
+ *     (src/pixie/simd/sse2.nim:6-46,510-524); float32 geometry without FMA.
+ */
+#ifndef PIXIE_CUDA_H
+#define PIXIE_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint64_t pixie_image_t;   /* opaque handle; 0 is never valid */
+typedef uint64_t pixie_cmdlist_t; /* opaque handle of a device-resident fill command list */
+
+/* ---- runtime ------------------------------------------------------------------------- */
+int pixie_cuda_init(int device);               /* select device, create the stream; idempotent */
+const char* pixie_cuda_last_error(void);       /* bindings/bindings.nim:3-10 takeError analogue */
+int pixie_cuda_set_stream(void* cuda_stream);  /* cudaStream_t to issue on (NULL = library stream) */
+int pixie_cuda_sync(void);                     /* wait for everything issued so far */
+int pixie_cuda_device_count(int* out);
+
+/* ---- images: newImage / copy / fill (common.nim:39-54, pixie.nim:120-131) -------------- */
+int pixie_cuda_image_create(int width, int height, pixie_image_t* out);       /* RGBX, zeroed */
+int pixie_cuda_image_create_layers(int width, int height, int layers, pixie_image_t* out);
+                                      /* `layers` independent RGBX canvases in one allocation */
+int pixie_cuda_image_create_a8(int width, int height, pixie_image_t* out);    /* coverage plane */
+int pixie_cuda_image_wrap(void* device_ptr, int width, int height, int layers, int bytes_per_pixel,
+                          pixie_image_t* out); /* borrow caller-owned device memory (not freed) */
+int pixie_cuda_image_destroy(pixie_image_t image);
+int pixie_cuda_image_info(pixie_image_t image, int* width, int* height, int* layers, int* bytes_per_pixel,
+                          void** device_ptr);
+int pixie_cuda_image_upload(pixie_image_t image, const uint8_t* host_pixels);  /* all layers */
+int pixie_cuda_image_download(pixie_image_t image, uint8_t* host_pixels);      /* all layers; blocks */
+int pixie_cuda_image_upload_async(pixie_image_t image, const uint8_t* pinned_host_pixels);
+int pixie_cuda_image_download_async(pixie_image_t image, uint8_t* pinned_host_pixels);
+int pixie_cuda_image_download_rows(pixie_image_t image, int layer, int y0, int y1, uint8_t* host_rows);
+int pixie_cuda_image_fill(pixie_image_t image, uint32_t rgbx);                 /* image.fill(color) */
+int pixie_cuda_image_copy(pixie_image_t dst, pixie_image_t src);               /* same shape */
+/* sum over pixels of (pixel_u32 * (index|1)) mod 2^64 — device-side checksum for batch tests */
+int pixie_cuda_image_checksum(pixie_image_t image, uint64_t* out);
+
+/* ---- fillShapes (paths.nim:1593-1912) ------------------------------------------------------
+ * Replaces the body of the private proc fillShapes() called by fillPath (:2112) and strokePath
+ * (:2175) from the point where shapesToSegments (:1604) has produced the segment list:
+ *   seg_xyxy  n x 4 float32 {at.x, at.y, to.x, to.y}, y quantised to 1/256, at.y < to.y, no
+ *             horizontals (exactly the output of shapesToSegments :1059-1090)
+ *   winding   n int16 (+1 / -1)
+ * Device kernels: partition/bin (partitionSegments :1168-1262), per-scanline mode decision +
+ * trapezoid / 5-sample coverage (:1631-1908, computeCoverage :1350-1431) fused with the blend
+ * (fillCoverage / fillHits :1479-1591, blends.nim).
+ * Returns 1 with "Path int overflow detected" where the reference raises it (:1618-1619). */
+int pixie_cuda_fill_segments(pixie_image_t image, const float* seg_xyxy, const int16_t* winding, int n,
+                             uint32_t rgbx, int winding_rule, int blend_mode);
+
+/* Ordered command list: fill k uses segments [seg_offsets[k], seg_offsets[k+1]) and goes to layer
+ * layer_of_fill[k] (NULL = layer 0; must be non-decreasing).  Fills of one layer are applied in
+ * list order (svg.nim:563-604 newImage(svg), fonts.nim:566-596); layers are independent.
+ * covered_px (optional, may be NULL) receives the number of pixels touched with non-zero coverage
+ * summed over fills — the work unit of the Mpixel/s metric (blocks the host when non-NULL). */
+int pixie_cuda_fill_batch(pixie_image_t image, int num_fills, const int32_t* layer_of_fill,
+                          const float* seg_xyxy, const int16_t* winding, const int32_t* seg_offsets,
+                          const uint32_t* rgbx, const uint8_t* winding_rule, const uint8_t* blend_mode,
+                          uint64_t* covered_px);
+
+/* Same, split so the inputs can stay resident in HBM: create uploads segments + per-fill headers
+ * for canvases of (width, height, layers); run rasterises them into `image`. */
+int pixie_cuda_cmdlist_create(int width, int height, int layers, int num_fills, const int32_t* layer_of_fill,
+                              const float* seg_xyxy, const int16_t* winding, const int32_t* seg_offsets,
+                              const uint32_t* rgbx, const uint8_t* winding_rule, const uint8_t* blend_mode,
+                              pixie_cmdlist_t* out);
+int pixie_cuda_cmdlist_run(pixie_cmdlist_t list, pixie_image_t image, uint64_t* covered_px);
+int pixie_cuda_cmdlist_info(pixie_cmdlist_t list, int64_t* num_segments, int64_t* num_partitions,
+                            int64_t* num_entries, int64_t* launches_per_run);
+int pixie_cuda_cmdlist_destroy(pixie_cmdlist_t list);
+
+/* ---- draw -> blendRect (images.nim:636-678 -> :468-529) -------------------------------------
+ * Integer-translate fast path of draw(): dst <- blend(dst, src at (px, py)), all 20 modes
+ * (blends.nim blender() :275-299); MaskBlend clears dst outside the drawn rect (:499-520) and the
+ * whole image when src lies outside (:473-476). */
+int pixie_cuda_blend_rect(pixie_image_t dst, pixie_image_t src, int px, int py, int blend_mode);
+/* Fused form of the non-solid paint composite (paths.nim:2141-2142):
+ *   fill.draw(mask, MaskBlend); image.draw(fill, blendMode)
+ * = dst <- blend(dst, floor(src * mask.a / 255)) in one pass.  mask is an RGBX image (alpha used)
+ * or an A8 coverage plane of src's size; src itself is left unchanged. */
+int pixie_cuda_blend_rect_masked(pixie_image_t dst, pixie_image_t src, pixie_image_t mask, int px, int py,
+                                 int blend_mode);
+int pixie_cuda_apply_opacity(pixie_image_t image, float opacity);              /* images.nim:261-277 */
+
+/* ---- blur / spread / shadow (images.nim:304-365, :700-758, :760-776) ------------------------
+ * lut = gaussianKernel(radius) (internal.nim:17-34), 2*radius+1 uint16 taps, computed by the
+ * caller.  radius < 0 -> 1 "Cannot apply negative blur" (:311-312); radius == 0 is a no-op. */
+int pixie_cuda_blur(pixie_image_t image, const uint16_t* lut, int radius, uint32_t out_of_bounds_rgbx);
+/* Row-band form used when one canvas is split across GPUs: computes the blur of the whole image
+ * but writes only rows [y0, y1); the other rows (the halo received from the neighbours) are left
+ * unchanged.  With `radius` halo rows above and below, rows [y0, y1) equal the global blur. */
+int pixie_cuda_blur_rows(pixie_image_t image, const uint16_t* lut, int radius, uint32_t out_of_bounds_rgbx,
+                         int y0, int y1);
+int pixie_cuda_spread(pixie_image_t image, int spread);
+/* dst <- shadow(src, offset, spread, blur, color); offset must be integral (a fractional offset
+ * goes through drawSmooth in the reference, which is not on this path -> returns 1). */
+int pixie_cuda_shadow(pixie_image_t src, pixie_image_t dst, float offset_x, float offset_y, int spread,
+                      const uint16_t* lut, int radius, uint32_t rgbx);
+
+/* ---- strict drop-in variants: host pixels in, host pixels out (upload -> run -> download) ---- */
+int pixie_cuda_fill_segments_host(uint8_t* pixels, int width, int height, const float* seg_xyxy,
+                                  const int16_t* winding, int n, uint32_t rgbx, int winding_rule, int blend_mode);
+int pixie_cuda_blend_rect_host(uint8_t* dst_pixels, int dst_width, int dst_height, const uint8_t* src_pixels,
+                               int src_width, int src_height, int px, int py, int blend_mode);
+int pixie_cuda_blur_host(uint8_t* pixels, int width, int height, const uint16_t* lut, int radius,
+                         uint32_t out_of_bounds_rgbx);
+int pixie_cuda_shadow_host(const uint8_t* src_pixels, uint8_t* dst_pixels, int width, int height, float offset_x,
+                           float offset_y, int spread, const uint16_t* lut, int radius, uint32_t rgbx);
+
+/* ---- instrumentation ----------------------------------------------------------------------- */
+/* number of kernels this library has launched since init (bench.py's gpu_launches) */
+int pixie_cuda_launch_count(uint64_t* out);
+/* CUDA-event timing on the library's stream: begin/end bracket, elapsed in milliseconds */
+int pixie_cuda_timer_begin(void);
+int pixie_cuda_timer_end(float* elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,319 @@
+// K5/K6 — separable Gaussian blur, alpha spread, drop shadow
+// (treeform/pixie src/pixie/images.nim: blur :304-365, spread :700-758, shadow :760-776).
+//
+// Exact integer arithmetic as the reference: per pass  out = (sum_i c[x+i] * lut[i]) div 256 div 255
+// in uint32 (wraps like the reference's uint32 for abnormal LUTs), 8-bit re-quantisation between
+// the two passes, constant-colour padding outside the image.
+//
+// Data flow: two kernels (X then Y) through one scratch plane.  r=32 is ALU-bound on CUDA cores
+// (65 taps x 4 channels x 2 passes per pixel), not HBM-bound, so the extra 8 B/px of the
+// intermediate plane costs nothing; each CTA stages a (64 + 2r) x 32 tile in shared memory
+// (lane = line, so every shared-memory access is conflict-free), each warp keeps a sliding window
+// of 8 unpacked pixels in registers and produces 8 outputs per line: 32 IMAD per tap against
+// 1 LDS + 4 PRMT.
+#include "common.cuh"
+
+namespace pixie {
+
+constexpr int kT = 8;           // outputs per thread along the blur axis
+constexpr int kWarps = 8;       // warps per CTA
+constexpr int kOutA = kT * kWarps;  // outputs per CTA along the blur axis (64)
+constexpr int kPitch = 33;      // tile pitch in words (32 lanes + 1 pad: conflict-free transposes)
+constexpr int kMaxTiledRadius = 700;
+
+struct ConvArgs {
+  const px_t* src;
+  px_t* dst;
+  int w, h;          // image size
+  int ntaps_pad;     // taps rounded up to a multiple of kT (extra taps are zero)
+  int radius;
+  uint32_t oob;
+  int y0, y1;        // output row range (rows outside are not written)
+  int sy0, sy1;      // rows of src that hold valid data for the vertical pass / rows to produce in X pass
+};
+
+PXD void unpack4(px_t p, uint32_t (&c)[4]) {
+  c[0] = __byte_perm(p, 0, 0x4440);
+  c[1] = __byte_perm(p, 0, 0x4441);
+  c[2] = __byte_perm(p, 0, 0x4442);
+  c[3] = __byte_perm(p, 0, 0x4443);
+}
+PXD px_t quantize4(const uint32_t (&a)[4]) {  // images.nim:332-338: v div 256 div 255
+  return mk(a[0] / 65280u, a[1] / 65280u, a[2] / 65280u, a[3] / 65280u);
+}
+
+// VERTICAL = false: blur along x (lane = row);  true: blur along y (lane = column).
+template <bool VERTICAL>
+__global__ void __launch_bounds__(kWarps * 32) conv_tiled(const ConvArgs a, const uint16_t* __restrict__ lut_g) {
+  extern __shared__ uint32_t smem[];
+  const int a_ext = kOutA + a.ntaps_pad + kT;  // tile extent along the blur axis
+  uint32_t* lut = smem;                        // ntaps_pad words
+  uint32_t* tile = smem + a.ntaps_pad;         // a_ext * kPitch words
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ntaps = 2 * a.radius + 1;
+
+  for (int i = tid; i < a.ntaps_pad; i += blockDim.x) lut[i] = i < ntaps ? (uint32_t)lut_g[i] : 0u;
+
+  // tile origin: a0 along the blur axis (first output), l0 along the line axis
+  const int a0 = blockIdx.x * kOutA + (VERTICAL ? a.y0 : 0);
+  const int l0 = blockIdx.y * 32 + (VERTICAL ? 0 : a.sy0);
+  const int a_len = VERTICAL ? a.h : a.w;      // image extent along the blur axis
+  const int l_len = VERTICAL ? a.w : a.sy1;    // exclusive bound along the line axis
+
+  if (VERTICAL) {
+    for (int idx = tid; idx < a_ext * 32; idx += blockDim.x) {
+      const int ln = idx & 31, aa = idx >> 5;
+      const int y = a0 - a.radius + aa, x = l0 + ln;
+      px_t v = a.oob;
+      if (y >= 0 && y < a_len && x < l_len) v = a.src[(size_t)a.w * y + x];
+      tile[aa * kPitch + ln] = v;
+    }
+  } else {
+    for (int idx = tid; idx < a_ext * 32; idx += blockDim.x) {
+      const int aa = idx % a_ext, ln = idx / a_ext;
+      const int x = a0 - a.radius + aa, y = l0 + ln;
+      px_t v = a.oob;
+      if (x >= 0 && x < a_len && y < l_len) v = a.src[(size_t)a.w * y + x];
+      tile[aa * kPitch + ln] = v;
+    }
+  }
+  __syncthreads();
+
+  uint32_t acc[kT][4];
+#pragma unroll
+  for (int t = 0; t < kT; t++) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0u;
+  uint32_t win[kT][4];
+  const uint32_t* col = tile + (warp * kT) * kPitch + lane;
+#pragma unroll
+  for (int j = 0; j < kT; j++) unpack4(col[j * kPitch], win[j]);
+
+  for (int i0 = 0; i0 < a.ntaps_pad; i0 += kT) {
+    const uint4 ka = *reinterpret_cast<const uint4*>(lut + i0);
+    const uint4 kb = *reinterpret_cast<const uint4*>(lut + i0 + 4);
+    const uint32_t k[kT] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+    for (int u = 0; u < kT; u++) {
+#pragma unroll
+      for (int t = 0; t < kT; t++) {
+        const int s = (u + t) % kT;
+        acc[t][0] += k[u] * win[s][0];
+        acc[t][1] += k[u] * win[s][1];
+        acc[t][2] += k[u] * win[s][2];
+        acc[t][3] += k[u] * win[s][3];
+      }
+      unpack4(col[(i0 + u + kT) * kPitch], win[u]);
+    }
+  }
+
+  if (VERTICAL) {
+    const int x = l0 + lane;
+    if (x < a.w) {
+#pragma unroll
+      for (int t = 0; t < kT; t++) {
+        const int y = a0 + warp * kT + t;
+        if (y < a.y1) a.dst[(size_t)a.w * y + x] = quantize4(acc[t]);
+      }
+    }
+  } else {
+    __syncthreads();  // everyone is done reading the input tile; reuse it to transpose the outputs
+#pragma unroll
+    for (int t = 0; t < kT; t++) tile[(warp * kT + t) * kPitch + lane] = quantize4(acc[t]);
+    __syncthreads();
+    for (int idx = tid; idx < kOutA * 32; idx += blockDim.x) {
+      const int aa = idx % kOutA, ln = idx / kOutA;
+      const int x = a0 + aa, y = l0 + ln;
+      if (x < a.w && y < a.sy1) a.dst[(size_t)a.w * y + x] = tile[aa * kPitch + ln];
+    }
+  }
+}
+
+// Any-radius fallback (radius > kMaxTiledRadius): one thread per output pixel.
+template <bool VERTICAL>
+__global__ void __launch_bounds__(256) conv_naive(const ConvArgs a, const uint16_t* __restrict__ lut) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = (VERTICAL ? a.y0 : a.sy0) + blockIdx.y;
+  if (x >= a.w || y >= (VERTICAL ? a.y1 : a.sy1)) return;
+  uint32_t acc[4] = {0u, 0u, 0u, 0u};
+  for (int i = -a.radius; i <= a.radius; i++) {
+    const int xx = VERTICAL ? x : x + i, yy = VERTICAL ? y + i : y;
+    px_t v = a.oob;
+    if (xx >= 0 && xx < a.w && yy >= 0 && yy < a.h) v = a.src[(size_t)a.w * yy + xx];
+    const uint32_t k = lut[i + a.radius];
+    acc[0] += k * pR(v); acc[1] += k * pG(v); acc[2] += k * pB(v); acc[3] += k * pA(v);
+  }
+  a.dst[(size_t)a.w * y + x] = quantize4(acc);
+}
+
+static int blur_impl(Image* im, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1) {
+  Runtime& r = rt();
+  if (radius == 0) return 0;
+  if (radius < 0) return fail_pixie("Cannot apply negative blur");  // images.nim:311-312
+  if (im->bpp != 4 || im->layers != 1) return fail_pixie("blur needs a single-layer RGBX image");
+  if (y0 < 0) y0 = 0;
+  if (y1 > im->h) y1 = im->h;
+  if (y0 >= y1) return 0;
+  const int ntaps = 2 * radius + 1;
+  void *tmp, *lut_d, *pin;
+  if (int rc = get_scratch(0, im->bytes(), &tmp)) return rc;
+  if (int rc = get_scratch(1, (size_t)ntaps * 2, &lut_d)) return rc;
+  if (int rc = get_pinned((size_t)ntaps * 2, &pin)) return rc;
+  PX_CUDA(cudaStreamSynchronize(r.stream));  // the pinned staging buffer is reused between calls
+  memcpy(pin, lut_host, (size_t)ntaps * 2);
+  PX_CUDA(cudaMemcpyAsync(lut_d, pin, (size_t)ntaps * 2, cudaMemcpyHostToDevice, r.stream));
+
+  ConvArgs a;
+  a.w = im->w; a.h = im->h; a.radius = radius; a.oob = oob;
+  a.ntaps_pad = (ntaps + kT - 1) / kT * kT;
+  a.y0 = y0; a.y1 = y1;
+  a.sy0 = std::max(0, y0 - radius);       // X pass only needs the rows the Y pass will read
+  a.sy1 = std::min(im->h, y1 + radius);
+  const size_t smem = ((size_t)a.ntaps_pad + (size_t)(kOutA + a.ntaps_pad + kT) * kPitch) * 4;
+
+  if (radius <= kMaxTiledRadius) {
+    static size_t configured[2] = {0, 0};
+    if (smem > 48 * 1024) {
+      if (configured[0] < smem) {
+        PX_CUDA(cudaFuncSetAttribute(conv_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[0] = smem;
+      }
+      if (configured[1] < smem) {
+        PX_CUDA(cudaFuncSetAttribute(conv_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[1] = smem;
+      }
+    }
+    // X pass: image -> tmp
+    a.src = (const px_t*)im->data; a.dst = (px_t*)tmp;
+    dim3 gx((im->w + kOutA - 1) / kOutA, (a.sy1 - a.sy0 + 31) / 32);
+    conv_tiled<false><<<gx, kWarps * 32, smem, r.stream>>>(a, (const uint16_t*)lut_d);
+    PX_LAUNCHED();
+    // Y pass: tmp -> image rows [y0, y1)
+    a.src = (const px_t*)tmp; a.dst = (px_t*)im->data;
+    dim3 gy((y1 - y0 + kOutA - 1) / kOutA, (im->w + 31) / 32);
+    conv_tiled<true><<<gy, kWarps * 32, smem, r.stream>>>(a, (const uint16_t*)lut_d);
+    PX_LAUNCHED();
+  } else {
+    a.src = (const px_t*)im->data; a.dst = (px_t*)tmp;
+    dim3 gx((im->w + 255) / 256, a.sy1 - a.sy0);
+    conv_naive<false><<<gx, 256, 0, r.stream>>>(a, (const uint16_t*)lut_d);
+    PX_LAUNCHED();
+    a.src = (const px_t*)tmp; a.dst = (px_t*)im->data;
+    dim3 gy((im->w + 255) / 256, y1 - y0);
+    conv_naive<true><<<gy, 256, 0, r.stream>>>(a, (const uint16_t*)lut_d);
+    PX_LAUNCHED();
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- spread (images.nim:700-758)
+// Separable max (spread > 0) / min (< 0) filter of alpha with a window clamped at the borders.
+template <bool GROW>
+__global__ void __launch_bounds__(256) spread_x(const px_t* __restrict__ src, uint8_t* __restrict__ tmp, int w, int h, int s) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const px_t* row = src + (size_t)w * y;
+  const int lo = max(x - s, 0), hi = min(x + s, w - 1);
+  uint32_t v = GROW ? 0u : 255u;
+  for (int xx = lo; xx <= hi; xx++) {
+    const uint32_t al = row[xx] >> 24;
+    v = GROW ? max(v, al) : min(v, al);
+  }
+  tmp[(size_t)w * y + x] = (uint8_t)v;
+}
+template <bool GROW>
+__global__ void __launch_bounds__(256) spread_y(const uint8_t* __restrict__ tmp, px_t* __restrict__ dst, int w, int h, int s) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const int lo = max(y - s, 0), hi = min(y + s, h - 1);
+  uint32_t v = GROW ? 0u : 255u;
+  for (int yy = lo; yy <= hi; yy++) {
+    const uint32_t al = tmp[(size_t)w * yy + x];
+    v = GROW ? max(v, al) : min(v, al);
+  }
+  dst[(size_t)w * y + x] = v << 24;  // rgbx(0, 0, 0, value)
+}
+
+static int spread_impl(Image* im, int spread) {
+  Runtime& r = rt();
+  if (spread == 0) return 0;
+  if (im->bpp != 4 || im->layers != 1) return fail_pixie("spread needs a single-layer RGBX image");
+  void* tmp;
+  if (int rc = get_scratch(0, (size_t)im->w * im->h, &tmp)) return rc;
+  dim3 grid((im->w + 255) / 256, im->h);
+  const int s = spread > 0 ? spread : -spread;
+  if (spread > 0) {
+    spread_x<true><<<grid, 256, 0, r.stream>>>((const px_t*)im->data, (uint8_t*)tmp, im->w, im->h, s);
+    PX_LAUNCHED();
+    spread_y<true><<<grid, 256, 0, r.stream>>>((const uint8_t*)tmp, (px_t*)im->data, im->w, im->h, s);
+    PX_LAUNCHED();
+  } else {
+    spread_x<false><<<grid, 256, 0, r.stream>>>((const px_t*)im->data, (uint8_t*)tmp, im->w, im->h, s);
+    PX_LAUNCHED();
+    spread_y<false><<<grid, 256, 0, r.stream>>>((const uint8_t*)tmp, (px_t*)im->data, im->w, im->h, s);
+    PX_LAUNCHED();
+  }
+  return 0;
+}
+
+// shadow's last step (images.nim:774-776): result.fill(color); result.draw(mask, MaskBlend)
+__global__ void __launch_bounds__(256) shadow_composite(px_t* __restrict__ p, size_t n, px_t color) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = line_mask(color, p[i]);
+}
+
+}  // namespace pixie
+
+using namespace pixie;
+
+extern "C" {
+
+int pixie_cuda_blur(pixie_image_t h, const uint16_t* lut, int radius, uint32_t oob) {
+  if (int rc = ensure_init()) return rc;
+  Image* im = find_image(h);
+  if (!im) return 1;
+  return blur_impl(im, lut, radius, oob, 0, im->h);
+}
+
+int pixie_cuda_blur_rows(pixie_image_t h, const uint16_t* lut, int radius, uint32_t oob, int y0, int y1) {
+  if (int rc = ensure_init()) return rc;
+  Image* im = find_image(h);
+  if (!im) return 1;
+  return blur_impl(im, lut, radius, oob, y0, y1);
+}
+
+int pixie_cuda_spread(pixie_image_t h, int spread) {
+  if (int rc = ensure_init()) return rc;
+  Image* im = find_image(h);
+  if (!im) return 1;
+  return spread_impl(im, spread);
+}
+
+int pixie_cuda_shadow(pixie_image_t srch, pixie_image_t dsth, float ox, float oy, int spread, const uint16_t* lut,
+                      int radius, uint32_t rgbx) {
+  if (int rc = ensure_init()) return rc;
+  Image* s = find_image(srch);
+  Image* d = find_image(dsth);
+  if (!s || !d) return 1;
+  if (s->w != d->w || s->h != d->h || s->bpp != 4 || d->bpp != 4 || s->layers != 1 || d->layers != 1)
+    return fail_pixie("shadow: src and dst must be single-layer RGBX images of the same size");
+  if (s->data == d->data) return fail_pixie("shadow: src and dst must be different images");
+  if (ox != truncf(ox) || oy != truncf(oy))
+    return fail_pixie("shadow: fractional offsets go through drawSmooth, which is not on this path");
+  // mask = copy / offset copy (images.nim:764-769), built directly in dst
+  if (ox == 0 && oy == 0) {
+    if (int rc = pixie_cuda_image_copy(dsth, srch)) return rc;
+  } else {
+    if (int rc = pixie_cuda_image_fill(dsth, 0u)) return rc;
+    if (int rc = pixie_cuda_blend_rect(dsth, srch, (int)ox, (int)oy, OverwriteBlend)) return rc;
+  }
+  if (int rc = spread_impl(d, spread)) return rc;
+  if (int rc = blur_impl(d, lut, radius, 0u, 0, d->h)) return rc;
+  Runtime& r = rt();
+  const size_t n = (size_t)d->w * d->h;
+  int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)r.num_sms * 16);
+  shadow_composite<<<blocks, 256, 0, r.stream>>>((px_t*)d->data, n, rgbx);
+  PX_LAUNCHED();
+  return 0;
+}
+
+}  // extern "C"

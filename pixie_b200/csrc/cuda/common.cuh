@@ -1,0 +1,327 @@
+// Shared runtime state + device helpers of pixie_cuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "pixie_cuda.h"
+
+namespace pixie {
+
+// ------------------------------------------------------------------ host runtime
+struct Image {
+  uint8_t* data = nullptr;
+  int w = 0, h = 0, layers = 1, bpp = 4;
+  bool owned = true;
+  size_t bytes() const { return (size_t)w * h * layers * bpp; }
+  size_t layer_bytes() const { return (size_t)w * h * bpp; }
+};
+
+struct Runtime {
+  bool inited = false;
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  std::unordered_map<uint64_t, Image> images;
+  uint64_t next_handle = 1;
+  uint64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // scratch buffers that grow on demand (stream-ordered reuse)
+  void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_bytes[4] = {0, 0, 0, 0};
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+};
+
+Runtime& rt();
+void set_error(const std::string& msg);
+int fail_pixie(const std::string& msg);            // returns 1
+int fail_cuda(cudaError_t e, const char* what);    // returns 2
+int ensure_init();
+Image* find_image(uint64_t h);
+int get_scratch(int slot, size_t bytes, void** out);
+int get_pinned(size_t bytes, void** out);
+
+#define PX_CUDA(call)                                  \
+  do {                                                 \
+    cudaError_t _e = (call);                           \
+    if (_e != cudaSuccess) return pixie::fail_cuda(_e, #call); \
+  } while (0)
+
+#define PX_LAUNCHED()                                  \
+  do {                                                 \
+    pixie::rt().launches++;                            \
+    cudaError_t _e = cudaGetLastError();               \
+    if (_e != cudaSuccess) return pixie::fail_cuda(_e, "kernel launch"); \
+  } while (0)
+
+enum BlendMode {
+  NormalBlend = 0, DarkenBlend, MultiplyBlend, ColorBurnBlend, LightenBlend, ScreenBlend,
+  ColorDodgeBlend, OverlayBlend, SoftLightBlend, HardLightBlend, DifferenceBlend, ExclusionBlend,
+  HueBlend, SaturationBlend, ColorBlend, LuminosityBlend, MaskBlend, OverwriteBlend,
+  SubtractMaskBlend, ExcludeMaskBlend, NumBlendModes
+};  // common.nim:6-29
+
+// ------------------------------------------------------------------ device pixel helpers
+typedef uint32_t px_t;  // r | g<<8 | b<<16 | a<<24
+#define PXD __device__ __forceinline__
+
+PXD uint32_t pR(px_t p) { return p & 255u; }
+PXD uint32_t pG(px_t p) { return (p >> 8) & 255u; }
+PXD uint32_t pB(px_t p) { return (p >> 16) & 255u; }
+PXD uint32_t pA(px_t p) { return p >> 24; }
+PXD px_t mk(uint32_t r, uint32_t g, uint32_t b, uint32_t a) {
+  return (r & 255u) | ((g & 255u) << 8) | ((b & 255u) << 16) | (a << 24);
+}
+
+// two 16-bit lanes holding values <= 65025: floor(x / 255) per lane = (x + 1 + (x >> 8)) >> 8
+PXD uint32_t div255x2(uint32_t x) {
+  uint32_t t = x + 0x00010001u + ((x >> 8) & 0x00FF00FFu);
+  return (t >> 8) & 0x00FF00FFu;
+}
+// floor(p * k / 255) on all four channels (k in 0..255)
+PXD px_t mul_div255(px_t p, uint32_t k) {
+  uint32_t rb = (p & 0x00FF00FFu) * k;
+  uint32_t ga = ((p >> 8) & 0x00FF00FFu) * k;
+  return div255x2(rb) | (div255x2(ga) << 8);
+}
+// byte-wise wrapping add (mm_add_epi8)
+PXD px_t add_bytes(px_t a, px_t b) {
+  uint32_t lo = (a & 0x00FF00FFu) + (b & 0x00FF00FFu);
+  uint32_t hi = ((a >> 8) & 0x00FF00FFu) + ((b >> 8) & 0x00FF00FFu);
+  return (lo & 0x00FF00FFu) | ((hi & 0x00FF00FFu) << 8);
+}
+
+// The x86 row-kernel bodies (sse2.nim:13-46): used wherever the reference calls blendLine*.
+PXD px_t line_normal(px_t b, px_t s) { return add_bytes(s, mul_div255(b, 255u - pA(s))); }
+PXD px_t line_mask(px_t b, px_t s) { return mul_div255(b, pA(s)); }
+// applyCoverage (sse2.nim:510-524): floor(c * cov / 255)
+PXD px_t mul_cov_floor(px_t c, uint32_t cov) { return mul_div255(c, cov); }
+// ColorRGBX * uint8 (common.nim:79-90): rounding form, used by the generic modes (paths.nim:1519-1526)
+PXD px_t mul_cov_round(px_t c, uint32_t cov) {
+  if (cov == 0) return 0;
+  if (cov == 255) return c;
+  return mk((pR(c) * cov + 127u) / 255u, (pG(c) * cov + 127u) / 255u, (pB(c) * cov + 127u) / 255u,
+            (pA(c) * cov + 127u) / 255u);
+}
+// applyOpacity(M128, area) (sse2.nim:6-11): cvtps_epi32 (round half even) + unsigned saturation
+PXD uint32_t cvt_sat(float v) {
+  float r = rintf(v);
+  if (!(r > 0.0f)) return 0u;
+  if (r > 255.0f) return 255u;
+  return (uint32_t)r;
+}
+PXD px_t mul_area(px_t c, float area) {
+  return mk(cvt_sat((float)pR(c) * area), cvt_sat((float)pG(c) * area), cvt_sat((float)pB(c) * area),
+            cvt_sat((float)pA(c) * area));
+}
+
+// ------------------------------------------------------------------ blends.nim (scalar forms, blender())
+PXD uint32_t blend_alpha(uint32_t ba, uint32_t sa) { return (sa + (ba * (255u - sa)) / 255u) & 255u; }  // :41-43
+PXD uint32_t screen_(uint32_t b, uint32_t s) { return ((b + s) - (b * s) / 255u) & 255u; }             // :45-46
+PXD uint32_t hard_light(uint32_t bc, uint32_t ba, uint32_t sc, uint32_t sa) {                          // :48-58
+  if (sc * 2u <= sa) return ((2u * sc * bc + (sc * (255u - ba)) + (bc * (255u - sa))) / 255u) & 255u;
+  return screen_(bc, sc);
+}
+PXD px_t blend_normal(px_t b, px_t s) {  // :60-70
+  if (pA(b) == 0u || pA(s) == 255u) return s;
+  if (pA(s) == 0u) return b;
+  return line_normal(b, s);
+}
+PXD uint32_t straight_(uint32_t c, uint32_t a) {  // internal.nim:68-74 stand-in for chroma rgba()
+  if (a == 0u) return 0u;
+  float multiplier = 255.0f / (float)a;
+  float v = roundf((float)c * multiplier);
+  return v > 255.0f ? 255u : (uint32_t)v;
+}
+PXD px_t to_straight(px_t p) {
+  uint32_t a = pA(p);
+  return mk(straight_(pR(p), a), straight_(pG(p), a), straight_(pB(p), a), a);
+}
+PXD px_t to_premul(px_t p) {  // chroma rgbx(ColorRGBA)
+  uint32_t a = pA(p);
+  if (a == 255u) return p;
+  return mk((pR(p) * a + 127u) / 255u, (pG(p) * a + 127u) / 255u, (pB(p) * a + 127u) / 255u, a);
+}
+PXD px_t alpha_fix(px_t backdrop, px_t source, px_t mixed) {  // blends.nim:18-39
+  uint32_t sa = pA(source), ba = pA(backdrop);
+  uint32_t t0 = sa * (255u - ba), t1 = sa * ba, t2 = (255u - sa) * ba;
+  uint32_t r = t0 * pR(source) + t1 * pR(mixed) + t2 * pR(backdrop);
+  uint32_t g = t0 * pG(source) + t1 * pG(mixed) + t2 * pG(backdrop);
+  uint32_t b = t0 * pB(source) + t1 * pB(mixed) + t2 * pB(backdrop);
+  uint32_t a = sa + ba * (255u - sa) / 255u;
+  if (a == 0u) return 0u;
+  return mk(r / a / 255u, g / a / 255u, b / a / 255u, a);
+}
+
+struct Col {
+  float r, g, b, a;
+};
+PXD Col to_color(px_t p) {
+  px_t s = to_straight(p);
+  Col c = {(float)pR(s) / 255.0f, (float)pG(s) / 255.0f, (float)pB(s) / 255.0f, (float)pA(s) / 255.0f};
+  return c;
+}
+PXD uint32_t f2u8(float v) {
+  float x = roundf(v * 255.0f);
+  if (!(x > 0.0f)) return 0u;
+  if (x > 255.0f) return 255u;
+  return (uint32_t)x;
+}
+PXD px_t from_color(Col c) { return to_premul(mk(f2u8(c.r), f2u8(c.g), f2u8(c.b), f2u8(c.a))); }
+PXD float min3f(float a, float b, float c) { return fminf(a, fminf(b, c)); }
+PXD float max3f(float a, float b, float c) { return fmaxf(a, fmaxf(b, c)); }
+PXD float lum(Col c) { return 0.3f * c.r + 0.59f * c.g + 0.11f * c.b; }
+PXD Col clip_color(Col c) {
+  float L = lum(c), n = min3f(c.r, c.g, c.b), x = max3f(c.r, c.g, c.b);
+  if (n < 0) {
+    c.r = L + (((c.r - L) * L) / (L - n));
+    c.g = L + (((c.g - L) * L) / (L - n));
+    c.b = L + (((c.b - L) * L) / (L - n));
+  }
+  if (x > 1) {
+    c.r = L + (((c.r - L) * (1 - L)) / (x - L));
+    c.g = L + (((c.g - L) * (1 - L)) / (x - L));
+    c.b = L + (((c.b - L) * (1 - L)) / (x - L));
+  }
+  return c;
+}
+PXD Col set_lum(Col c, float l) {
+  float d = l - lum(c);
+  c.r += d;
+  c.g += d;
+  c.b += d;
+  return clip_color(c);
+}
+PXD float sat(Col c) { return max3f(c.r, c.g, c.b) - min3f(c.r, c.g, c.b); }
+PXD Col set_sat(Col c, float s) {
+  float satC = sat(c);
+  Col r = {0.f, 0.f, 0.f, c.a};
+  if (satC > 0) {
+    float mn = min3f(c.r, c.g, c.b);
+    r.r = (c.r - mn) * s / satC;
+    r.g = (c.g - mn) * s / satC;
+    r.b = (c.b - mn) * s / satC;
+  }
+  return r;
+}
+PXD Col alpha_fix_f(Col cb, Col cs, Col mixed) {
+  Col r;
+  r.a = cs.a + cb.a * (1.0f - cs.a);
+  if (r.a == 0) {
+    r.r = r.g = r.b = 0.f;
+    return r;
+  }
+  float t0 = cs.a * (1 - cb.a), t1 = cs.a * cb.a, t2 = (1 - cs.a) * cb.a;
+  r.r = (t0 * cs.r + t1 * mixed.r + t2 * cb.r) / r.a;
+  r.g = (t0 * cs.g + t1 * mixed.g + t2 * cb.g) / r.a;
+  r.b = (t0 * cs.b + t1 * mixed.b + t2 * cb.b) / r.a;
+  return r;
+}
+
+// blender(MODE)(backdrop, source), blends.nim:275-299 — MODE is a compile-time constant
+template <int MODE>
+PXD px_t blend_px(px_t b, px_t s) {
+  if (MODE == NormalBlend) return blend_normal(b, s);
+  if (MODE == OverwriteBlend) return s;
+  if (MODE == MaskBlend) return mul_div255(b, pA(s));
+  const uint32_t ba = pA(b), sa = pA(s);
+  if (MODE == SubtractMaskBlend) {
+    uint32_t a = (ba * (255u - sa)) / 255u;
+    return (mul_div255(b, a) & 0x00FFFFFFu) | (a << 24);
+  }
+  if (MODE == ExcludeMaskBlend) {
+    uint32_t a = max(ba, sa) - min(ba, sa);
+    return (mul_div255(s, a) & 0x00FFFFFFu) | (a << 24);
+  }
+  if (MODE == ColorBurnBlend || MODE == ColorDodgeBlend) {
+    px_t bd = to_straight(b), sr = to_straight(s);
+    uint32_t o[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      uint32_t bc = (bd >> (8 * c)) & 255u, sc = (sr >> (8 * c)) & 255u;
+      if (MODE == ColorBurnBlend) {
+        if (bc == 255u) o[c] = 255u;
+        else if (sc == 0u) o[c] = 0u;
+        else o[c] = 255u - (min(255u, (255u * (255u - bc)) / sc) & 255u);
+      } else {
+        if (bc == 0u) o[c] = 0u;
+        else if (sc == 255u) o[c] = 255u;
+        else o[c] = min(255u, (255u * bc) / (255u - sc));
+      }
+    }
+    return to_premul(alpha_fix(bd, sr, mk(o[0], o[1], o[2], 0u)));
+  }
+  if (MODE == SoftLightBlend || MODE == HueBlend || MODE == SaturationBlend || MODE == ColorBlend ||
+      MODE == LuminosityBlend) {
+    Col cb = to_color(b), cs = to_color(s), m = {0.f, 0.f, 0.f, 0.f};
+    if (MODE == SoftLightBlend) {
+      m.r = (1 - 2 * cs.r) * (cb.r * cb.r) + 2 * cs.r * cb.r;
+      m.g = (1 - 2 * cs.g) * (cb.g * cb.g) + 2 * cs.g * cb.g;
+      m.b = (1 - 2 * cs.b) * (cb.b * cb.b) + 2 * cs.b * cb.b;
+    } else if (MODE == HueBlend) {
+      m = set_lum(set_sat(cs, sat(cb)), lum(cb));
+    } else if (MODE == SaturationBlend) {
+      m = set_lum(set_sat(cb, sat(cs)), lum(cb));
+    } else if (MODE == ColorBlend) {
+      m = set_lum(cs, lum(cb));
+    } else {
+      m = set_lum(cb, lum(cs));
+    }
+    return from_color(alpha_fix_f(cb, cs, m));
+  }
+  // separable integer modes: per channel f(bc, ba, sc, sa), alpha = blendAlpha
+  uint32_t o[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    uint32_t bc = (b >> (8 * c)) & 255u, sc = (s >> (8 * c)) & 255u;
+    uint32_t v = 0;
+    if (MODE == DarkenBlend) v = min(bc + ((255u - ba) * sc) / 255u, sc + ((255u - sa) * bc) / 255u);
+    else if (MODE == LightenBlend) v = max(bc + ((255u - ba) * sc) / 255u, sc + ((255u - sa) * bc) / 255u);
+    else if (MODE == MultiplyBlend) v = ((255u - ba) * sc + (255u - sa) * bc + bc * sc) / 255u;
+    else if (MODE == ScreenBlend) v = screen_(bc, sc);
+    else if (MODE == OverlayBlend) v = hard_light(sc, sa, bc, ba);
+    else if (MODE == HardLightBlend) v = hard_light(bc, ba, sc, sa);
+    else if (MODE == DifferenceBlend) v = (bc + sc) - 2u * (min(bc * sa, sc * ba) / 255u);
+    else if (MODE == ExclusionBlend) {
+      int32_t t = (int32_t)(bc + sc) - (int32_t)((2u * bc * sc) / 255u);
+      v = (uint32_t)(t < 0 ? 0 : t);
+    }
+    o[c] = v;
+  }
+  return mk(o[0], o[1], o[2], blend_alpha(ba, sa));
+}
+
+// run-time mode -> compile-time dispatch (mode is warp-uniform at every call site)
+#define PX_DISPATCH_MODE(mode, EXPR)                                                          \
+  switch (mode) {                                                                             \
+    case 0: { constexpr int MODE = 0; EXPR; } break;                                          \
+    case 1: { constexpr int MODE = 1; EXPR; } break;                                          \
+    case 2: { constexpr int MODE = 2; EXPR; } break;                                          \
+    case 3: { constexpr int MODE = 3; EXPR; } break;                                          \
+    case 4: { constexpr int MODE = 4; EXPR; } break;                                          \
+    case 5: { constexpr int MODE = 5; EXPR; } break;                                          \
+    case 6: { constexpr int MODE = 6; EXPR; } break;                                          \
+    case 7: { constexpr int MODE = 7; EXPR; } break;                                          \
+    case 8: { constexpr int MODE = 8; EXPR; } break;                                          \
+    case 9: { constexpr int MODE = 9; EXPR; } break;                                          \
+    case 10: { constexpr int MODE = 10; EXPR; } break;                                        \
+    case 11: { constexpr int MODE = 11; EXPR; } break;                                        \
+    case 12: { constexpr int MODE = 12; EXPR; } break;                                        \
+    case 13: { constexpr int MODE = 13; EXPR; } break;                                        \
+    case 14: { constexpr int MODE = 14; EXPR; } break;                                        \
+    case 15: { constexpr int MODE = 15; EXPR; } break;                                        \
+    case 16: { constexpr int MODE = 16; EXPR; } break;                                        \
+    case 17: { constexpr int MODE = 17; EXPR; } break;                                        \
+    case 18: { constexpr int MODE = 18; EXPR; } break;                                        \
+    default: { constexpr int MODE = 19; EXPR; } break;                                        \
+  }
+
+}  // namespace pixie

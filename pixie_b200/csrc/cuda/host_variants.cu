@@ -1,0 +1,58 @@
+// Strict drop-in variants of the C ABI: host pixels in, host pixels out (upload -> run -> download),
+// for callers whose Image.data is a host seq (treeform/pixie src/pixie/common.nim:34-37).
+#include "common.cuh"
+
+using namespace pixie;
+
+namespace {
+struct TmpImage {
+  pixie_image_t h = 0;
+  ~TmpImage() {
+    if (h) pixie_cuda_image_destroy(h);
+  }
+};
+}  // namespace
+
+extern "C" {
+
+int pixie_cuda_fill_segments_host(uint8_t* pixels, int w, int h, const float* seg, const int16_t* wind, int n,
+                                  uint32_t rgbx, int rule, int mode) {
+  TmpImage im;
+  if (int rc = pixie_cuda_image_create(w, h, &im.h)) return rc;
+  if (int rc = pixie_cuda_image_upload(im.h, pixels)) return rc;
+  if (int rc = pixie_cuda_fill_segments(im.h, seg, wind, n, rgbx, rule, mode)) return rc;
+  return pixie_cuda_image_download(im.h, pixels);
+}
+
+int pixie_cuda_blend_rect_host(uint8_t* dst, int dw, int dh, const uint8_t* src, int sw, int sh, int px, int py,
+                               int mode) {
+  TmpImage d, s;
+  if (int rc = pixie_cuda_image_create(dw, dh, &d.h)) return rc;
+  if (int rc = pixie_cuda_image_create(sw, sh, &s.h)) return rc;
+  if (int rc = pixie_cuda_image_upload(d.h, dst)) return rc;
+  if (int rc = pixie_cuda_image_upload(s.h, src)) return rc;
+  if (int rc = pixie_cuda_blend_rect(d.h, s.h, px, py, mode)) return rc;
+  return pixie_cuda_image_download(d.h, dst);
+}
+
+int pixie_cuda_blur_host(uint8_t* pixels, int w, int h, const uint16_t* lut, int radius, uint32_t oob) {
+  if (radius == 0) return 0;
+  if (radius < 0) return fail_pixie("Cannot apply negative blur");
+  TmpImage im;
+  if (int rc = pixie_cuda_image_create(w, h, &im.h)) return rc;
+  if (int rc = pixie_cuda_image_upload(im.h, pixels)) return rc;
+  if (int rc = pixie_cuda_blur(im.h, lut, radius, oob)) return rc;
+  return pixie_cuda_image_download(im.h, pixels);
+}
+
+int pixie_cuda_shadow_host(const uint8_t* src, uint8_t* dst, int w, int h, float ox, float oy, int spread,
+                           const uint16_t* lut, int radius, uint32_t rgbx) {
+  TmpImage s, d;
+  if (int rc = pixie_cuda_image_create(w, h, &s.h)) return rc;
+  if (int rc = pixie_cuda_image_create(w, h, &d.h)) return rc;
+  if (int rc = pixie_cuda_image_upload(s.h, src)) return rc;
+  if (int rc = pixie_cuda_shadow(s.h, d.h, ox, oy, spread, lut, radius, rgbx)) return rc;
+  return pixie_cuda_image_download(d.h, dst);
+}
+
+}  // extern "C"

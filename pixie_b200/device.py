@@ -1,0 +1,311 @@
+"""ctypes binding of pixie_cuda.so — the C ABI declared in include/pixie_cuda.h.
+
+There is no CPU fallback: loading fails loudly when the CUDA library is missing, and every call
+returns the library's status, raised here as PixieError (the analogue of the Nim shim's
+``raise newException(PixieError, $pixie_cuda_last_error())``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from .common import PixieError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "pixie_cuda.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pixie_cuda.h")
+
+_lib = None
+
+vp, i32, u32, u64, f32 = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_float
+P = C.POINTER
+
+_SIGNATURES = {
+    "pixie_cuda_init": [i32],
+    "pixie_cuda_set_stream": [vp],
+    "pixie_cuda_sync": [],
+    "pixie_cuda_device_count": [P(i32)],
+    "pixie_cuda_image_create": [i32, i32, P(u64)],
+    "pixie_cuda_image_create_layers": [i32, i32, i32, P(u64)],
+    "pixie_cuda_image_create_a8": [i32, i32, P(u64)],
+    "pixie_cuda_image_wrap": [vp, i32, i32, i32, i32, P(u64)],
+    "pixie_cuda_image_destroy": [u64],
+    "pixie_cuda_image_info": [u64, P(i32), P(i32), P(i32), P(i32), P(vp)],
+    "pixie_cuda_image_upload": [u64, vp],
+    "pixie_cuda_image_download": [u64, vp],
+    "pixie_cuda_image_upload_async": [u64, vp],
+    "pixie_cuda_image_download_async": [u64, vp],
+    "pixie_cuda_image_download_rows": [u64, i32, i32, i32, vp],
+    "pixie_cuda_image_fill": [u64, u32],
+    "pixie_cuda_image_copy": [u64, u64],
+    "pixie_cuda_image_checksum": [u64, P(u64)],
+    "pixie_cuda_fill_segments": [u64, vp, vp, i32, u32, i32, i32],
+    "pixie_cuda_fill_batch": [u64, i32, vp, vp, vp, vp, vp, vp, vp, P(u64)],
+    "pixie_cuda_cmdlist_create": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, P(u64)],
+    "pixie_cuda_cmdlist_run": [u64, u64, P(u64)],
+    "pixie_cuda_cmdlist_info": [u64, P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64)],
+    "pixie_cuda_cmdlist_destroy": [u64],
+    "pixie_cuda_blend_rect": [u64, u64, i32, i32, i32],
+    "pixie_cuda_blend_rect_masked": [u64, u64, u64, i32, i32, i32],
+    "pixie_cuda_apply_opacity": [u64, f32],
+    "pixie_cuda_blur": [u64, vp, i32, u32],
+    "pixie_cuda_blur_rows": [u64, vp, i32, u32, i32, i32],
+    "pixie_cuda_spread": [u64, i32],
+    "pixie_cuda_shadow": [u64, u64, f32, f32, i32, vp, i32, u32],
+    "pixie_cuda_fill_segments_host": [vp, i32, i32, vp, vp, i32, u32, i32, i32],
+    "pixie_cuda_blend_rect_host": [vp, i32, i32, vp, i32, i32, i32, i32, i32],
+    "pixie_cuda_blur_host": [vp, i32, i32, vp, i32, u32],
+    "pixie_cuda_shadow_host": [vp, vp, i32, i32, f32, f32, i32, vp, i32, u32],
+    "pixie_cuda_launch_count": [P(u64)],
+    "pixie_cuda_timer_begin": [],
+    "pixie_cuda_timer_end": [P(f32)],
+}
+
+
+def declared_symbols():
+    """Every function name include/pixie_cuda.h declares."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pixie_cuda_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib():
+    """Load pixie_cuda.so (fails loudly if absent) and bind every symbol the header declares."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "pixie_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name in declared_symbols():
+            fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+            if name == "pixie_cuda_last_error":
+                fn.restype = C.c_char_p
+                fn.argtypes = []
+            else:
+                fn.restype = i32
+                fn.argtypes = _SIGNATURES[name]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise PixieError(lib().pixie_cuda_last_error().decode())
+
+
+def init(device: int = 0):
+    check(lib().pixie_cuda_init(device))
+
+
+def sync():
+    check(lib().pixie_cuda_sync())
+
+
+def set_stream(cuda_stream_ptr):
+    check(lib().pixie_cuda_set_stream(cuda_stream_ptr))
+
+
+def launch_count() -> int:
+    v = u64(0)
+    check(lib().pixie_cuda_launch_count(C.byref(v)))
+    return v.value
+
+
+def device_count() -> int:
+    v = i32(0)
+    rc = lib().pixie_cuda_device_count(C.byref(v))
+    return v.value if rc == 0 else 0
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+class DeviceImage:
+    """A device-resident canvas (RGBX, optionally several independent layers) or A8 coverage plane."""
+
+    def __init__(self, width, height, layers=1, a8=False, _handle=None, _owner=None):
+        self.width, self.height, self.layers, self.a8 = width, height, layers, a8
+        self._owner = _owner
+        if _handle is not None:
+            self.handle = _handle
+            return
+        h = u64(0)
+        if a8:
+            check(lib().pixie_cuda_image_create_a8(width, height, C.byref(h)))
+        elif layers == 1:
+            check(lib().pixie_cuda_image_create(width, height, C.byref(h)))
+        else:
+            check(lib().pixie_cuda_image_create_layers(width, height, layers, C.byref(h)))
+        self.handle = h.value
+
+    @classmethod
+    def wrap(cls, device_ptr, width, height, layers=1, bytes_per_pixel=4, owner=None):
+        h = u64(0)
+        check(lib().pixie_cuda_image_wrap(device_ptr, width, height, layers, bytes_per_pixel, C.byref(h)))
+        return cls(width, height, layers, bytes_per_pixel == 1, _handle=h.value, _owner=owner)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", 0):
+                lib().pixie_cuda_image_destroy(self.handle)
+                self.handle = 0
+        except Exception:
+            pass
+
+    @property
+    def shape(self):
+        base = (self.height, self.width) if self.a8 else (self.height, self.width, 4)
+        return base if self.layers == 1 else (self.layers,) + base
+
+    def upload(self, pixels: np.ndarray):
+        a = np.ascontiguousarray(pixels, dtype=np.uint8)
+        assert a.size == int(np.prod(self.shape)), (a.shape, self.shape)
+        check(lib().pixie_cuda_image_upload(self.handle, a.ctypes.data))
+        return self
+
+    def download(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.shape, np.uint8)
+        check(lib().pixie_cuda_image_download(self.handle, out.ctypes.data))
+        return out
+
+    def download_rows(self, y0, y1, layer=0):
+        out = np.empty((y1 - y0, self.width) + (() if self.a8 else (4,)), np.uint8)
+        check(lib().pixie_cuda_image_download_rows(self.handle, layer, y0, y1, out.ctypes.data))
+        return out
+
+    def fill(self, rgbx: int):
+        check(lib().pixie_cuda_image_fill(self.handle, rgbx))
+
+    def copy_from(self, other: "DeviceImage"):
+        check(lib().pixie_cuda_image_copy(self.handle, other.handle))
+
+    def checksum(self) -> int:
+        v = u64(0)
+        check(lib().pixie_cuda_image_checksum(self.handle, C.byref(v)))
+        return v.value
+
+    def device_ptr(self) -> int:
+        p = vp()
+        check(lib().pixie_cuda_image_info(self.handle, None, None, None, None, C.byref(p)))
+        return p.value
+
+
+class FillBatch:
+    """Host-side ordered fill command list in the layout pixie_cuda_fill_batch takes."""
+
+    def __init__(self):
+        self._segs, self._wind = [], []
+        self.seg_offsets = [0]
+        self.rgbx, self.rule, self.mode, self.layer = [], [], [], []
+
+    def add(self, segs, rgbx, rule, mode, layer=0):
+        self._segs.append(segs.xyxy)
+        self._wind.append(segs.winding)
+        self.seg_offsets.append(self.seg_offsets[-1] + len(segs))
+        self.rgbx.append(rgbx)
+        self.rule.append(rule)
+        self.mode.append(mode)
+        self.layer.append(layer)
+
+    def __len__(self):
+        return len(self.rgbx)
+
+    def arrays(self):
+        xy = np.ascontiguousarray(np.concatenate(self._segs, axis=0) if self._segs else np.zeros((0, 4)), np.float32)
+        wd = np.ascontiguousarray(np.concatenate(self._wind) if self._wind else np.zeros((0,)), np.int16)
+        return dict(
+            xyxy=xy, winding=wd, seg_offsets=np.asarray(self.seg_offsets, np.int32),
+            rgbx=np.asarray(self.rgbx, np.uint32), rule=np.asarray(self.rule, np.uint8),
+            mode=np.asarray(self.mode, np.uint8), layer=np.asarray(self.layer, np.int32))
+
+
+def fill_segments(image: DeviceImage, segs, rgbx, rule, mode):
+    check(lib().pixie_cuda_fill_segments(image.handle, _ptr(segs.xyxy), _ptr(segs.winding), len(segs), rgbx, rule, mode))
+
+
+def fill_batch(image: DeviceImage, arrays: dict, count_covered=False):
+    cov = u64(0)
+    check(lib().pixie_cuda_fill_batch(
+        image.handle, len(arrays["rgbx"]), _ptr(arrays["layer"]), _ptr(arrays["xyxy"]), _ptr(arrays["winding"]),
+        _ptr(arrays["seg_offsets"]), _ptr(arrays["rgbx"]), _ptr(arrays["rule"]), _ptr(arrays["mode"]),
+        C.byref(cov) if count_covered else None))
+    return cov.value
+
+
+class CmdList:
+    """Device-resident command list (segments + fill headers in HBM)."""
+
+    def __init__(self, width, height, layers, arrays: dict):
+        h = u64(0)
+        check(lib().pixie_cuda_cmdlist_create(
+            width, height, layers, len(arrays["rgbx"]), _ptr(arrays["layer"]), _ptr(arrays["xyxy"]),
+            _ptr(arrays["winding"]), _ptr(arrays["seg_offsets"]), _ptr(arrays["rgbx"]), _ptr(arrays["rule"]),
+            _ptr(arrays["mode"]), C.byref(h)))
+        self.handle = h.value
+
+    def run(self, image: DeviceImage, count_covered=False):
+        cov = u64(0)
+        check(lib().pixie_cuda_cmdlist_run(self.handle, image.handle, C.byref(cov) if count_covered else None))
+        return cov.value
+
+    def info(self):
+        a, b, c, d = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        check(lib().pixie_cuda_cmdlist_info(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(segments=a.value, partitions=b.value, entries=c.value, launches_per_run=d.value)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", 0):
+                lib().pixie_cuda_cmdlist_destroy(self.handle)
+                self.handle = 0
+        except Exception:
+            pass
+
+
+def blend_rect(dst: DeviceImage, src: DeviceImage, px, py, mode):
+    check(lib().pixie_cuda_blend_rect(dst.handle, src.handle, px, py, mode))
+
+
+def blend_rect_masked(dst: DeviceImage, src: DeviceImage, mask: DeviceImage, px, py, mode):
+    check(lib().pixie_cuda_blend_rect_masked(dst.handle, src.handle, mask.handle, px, py, mode))
+
+
+def apply_opacity(image: DeviceImage, opacity):
+    check(lib().pixie_cuda_apply_opacity(image.handle, opacity))
+
+
+def blur(image: DeviceImage, lut, radius, oob=0):
+    lut = np.ascontiguousarray(lut, np.uint16)
+    check(lib().pixie_cuda_blur(image.handle, lut.ctypes.data, radius, oob))
+
+
+def blur_rows(image: DeviceImage, lut, radius, oob, y0, y1):
+    lut = np.ascontiguousarray(lut, np.uint16)
+    check(lib().pixie_cuda_blur_rows(image.handle, lut.ctypes.data, radius, oob, y0, y1))
+
+
+def spread(image: DeviceImage, amount):
+    check(lib().pixie_cuda_spread(image.handle, amount))
+
+
+def shadow(src: DeviceImage, dst: DeviceImage, ox, oy, spread_, lut, radius, rgbx):
+    lut = np.ascontiguousarray(lut, np.uint16)
+    check(lib().pixie_cuda_shadow(src.handle, dst.handle, ox, oy, spread_, lut.ctypes.data, radius, rgbx))
+
+
+def timer_begin():
+    check(lib().pixie_cuda_timer_begin())
+
+
+def timer_end() -> float:
+    v = f32(0)
+    check(lib().pixie_cuda_timer_end(C.byref(v)))
+    return v.value
