@@ -664,6 +664,11 @@ void computeCoverage(std::vector<uint8_t>& cov, std::vector<Hit>& hits, int& num
 }
 
 int fillSegments(Canvas& im, const float* seg, const int16_t* wind, int n, px_t rgbx, int rule, int mode) {
+  // An empty segment list is a no-op.  (With no segments computeBounds yields +/-Inf and the
+  // float->int conversions that follow are undefined behaviour in the reference; its own tiger
+  // SVG contains the empty path "M-65.4,9z" and renders in its CI, so "nothing drawn" is the
+  // behaviour the reference's tests pin.)
+  if (n == 0) return 0;
   // computeBounds (:1098-1117) + snapToPixels (common.nim:92-101) + clip (:1605-1619)
   float xMin = INFINITY, xMax = -INFINITY, yMin = INFINITY, yMax = -INFINITY;
   for (int i = 0; i < n; i++) {
@@ -830,7 +835,7 @@ int fillSegments(Canvas& im, const float* seg, const int16_t* wind, int n, px_t 
                 for (int64_t x = f2i(rectEnd); x < f2i(ceilf(sliverEnd)); x++) {
                   prevPen = pen;
                   pen = (float)(x + 1);
-                  float leftRectArea = prevPen - truncf(prevPen);  // vmath fractional
+                  float leftRectArea = fabsf(prevPen) - floorf(fabsf(prevPen));  // vmath fractional(): abs(v) - floor(abs(v))
                   if (pen > sliverEnd) pen = sliverEnd;
                   prevPenY = penY;
                   penY = solveY(right, pen);

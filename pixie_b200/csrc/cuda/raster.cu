@@ -790,6 +790,11 @@ static int build_list(CmdList& L, int w, int h, int layers, int numFills, const 
     FillHeader& H = fills[k];
     memset(&H, 0, sizeof(H));
     H.segBegin = s0; H.segCount = n; H.rgbx = rgbx[k]; H.rule = rule[k]; H.mode = mode[k];
+    if (n == 0) {  // empty path: nothing is drawn (the reference's tiger has one, "M-65.4,9z")
+      H.active = 0;
+      H.partBase = (int)partFill.size();
+      continue;
+    }
     // computeBounds (:1098-1117) + snapToPixels (common.nim:92-101) + clip to the image (:1605-1613)
     float xMin = INFINITY, xMax = -INFINITY, yMin = INFINITY, yMax = -INFINITY;
     for (int i = s0; i < s1; i++) {

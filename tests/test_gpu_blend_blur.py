@@ -1,0 +1,196 @@
+"""Parity of blend_rect (all 20 modes, masks, clipping), blur, spread and shadow with the oracle."""
+import numpy as np
+import pytest
+
+from pixie_b200 import host, synth
+from pixie_b200.common import BLEND_MODE_NAMES, MaskBlend, NormalBlend, rgbx as pack
+from _util import diff_report
+
+pytestmark = pytest.mark.gpu
+
+
+def _backends():
+    from _gpu_backend import GpuBackend
+    from _oracle import OracleBackend
+
+    return GpuBackend(), OracleBackend(0)
+
+
+@pytest.mark.parametrize("mode", range(20), ids=BLEND_MODE_NAMES)
+def test_blend_rect_all_modes(mode):
+    gb, ob = _backends()
+    for (dw, dh, sw, sh, px, py) in [(256, 64, 256, 64, 0, 0), (200, 50, 120, 40, 36, 7), (131, 37, 64, 64, -13, -9),
+                                     (96, 96, 50, 50, 70, 80), (64, 16, 64, 16, 4, 0), (33, 9, 200, 100, -100, -50)]:
+        dst = synth.random_premultiplied(dh, dw, 11 + mode)
+        src = synth.random_premultiplied(sh, sw, 77 + mode)
+        a, b = dst.copy(), dst.copy()
+        gb.blend_rect(a, src, px, py, mode)
+        ob.blend_rect(b, src, px, py, mode)
+        n, mx, where = diff_report(a, b)
+        assert n == 0, f"{BLEND_MODE_NAMES[mode]} {(dw, dh, sw, sh, px, py)}: {n} px differ (max {mx}) at {where}"
+
+
+@pytest.mark.parametrize("mode", range(20), ids=BLEND_MODE_NAMES)
+def test_blend_rect_non_premultiplied_inputs(mode):
+    """Arbitrary bytes (not valid premultiplied colours): uint8 wrap-around is part of the semantics."""
+    gb, ob = _backends()
+    rng = np.random.default_rng(mode)
+    dst = rng.integers(0, 256, (32, 256, 4), dtype=np.uint8)
+    src = rng.integers(0, 256, (32, 256, 4), dtype=np.uint8)
+    a, b = dst.copy(), dst.copy()
+    gb.blend_rect(a, src, 0, 0, mode)
+    ob.blend_rect(b, src, 0, 0, mode)
+    n, mx, where = diff_report(a, b)
+    assert n == 0, f"{BLEND_MODE_NAMES[mode]}: {n} px differ (max {mx}) at {where}"
+
+
+@pytest.mark.parametrize("mode", [0, 2, 3, 8, 11, 16, 17, 19])
+@pytest.mark.parametrize("rgbx_mask", [False, True])
+def test_blend_rect_masked(mode, rgbx_mask):
+    """Fused mask*fill composite (paths.nim:2141-2142) == MaskBlend draw followed by the blend draw."""
+    gb, ob = _backends()
+    for (dw, dh, sw, sh, px, py) in [(256, 32, 256, 32, 0, 0), (100, 40, 64, 30, 19, 5), (64, 64, 64, 64, -8, 8)]:
+        dst = synth.random_premultiplied(dh, dw, 1)
+        src = synth.random_premultiplied(sh, sw, 2)
+        cov = synth.coverage_mask(sh, sw, 3)
+        mask = cov
+        if rgbx_mask:
+            mask = np.zeros((sh, sw, 4), np.uint8)
+            mask[..., 3] = cov
+            mask[..., :3] = cov[..., None] // 2
+        a, b = dst.copy(), dst.copy()
+        gb.blend_rect_masked(a, src, mask, px, py, mode)
+        ob.blend_rect_masked(b, src, mask, px, py, mode)
+        assert diff_report(a, b)[0] == 0
+        # and the oracle's fused form equals the reference's two draws
+        tmp = src.copy()
+        m4 = mask if rgbx_mask else np.concatenate([np.zeros((sh, sw, 3), np.uint8), cov[..., None]], -1)
+        ob.blend_rect(tmp, np.ascontiguousarray(m4), 0, 0, MaskBlend)
+        c = dst.copy()
+        ob.blend_rect(c, tmp, px, py, mode)
+        assert diff_report(b, c)[0] == 0
+
+
+def test_blend_px_exhaustive_sample():
+    """Every mode on a dense lattice of (backdrop, source) channel/alpha values via 1-row images."""
+    gb, ob = _backends()
+    vals = np.array([0, 1, 2, 63, 64, 127, 128, 129, 191, 254, 255], np.uint8)
+    a_ = np.array([0, 1, 127, 128, 254, 255], np.uint8)
+    bc, ba, sc, sa = np.meshgrid(vals, a_, vals, a_, indexing="ij")
+    n = bc.size
+    dst = np.stack([bc.ravel(), 255 - bc.ravel(), bc.ravel() // 2, ba.ravel()], -1).reshape(1, n, 4).astype(np.uint8)
+    src = np.stack([sc.ravel(), sc.ravel() // 3, 255 - sc.ravel(), sa.ravel()], -1).reshape(1, n, 4).astype(np.uint8)
+    pad = (-n) % 4
+    dst = np.ascontiguousarray(np.pad(dst, ((0, 0), (0, pad), (0, 0))))
+    src = np.ascontiguousarray(np.pad(src, ((0, 0), (0, pad), (0, 0))))
+    for mode in range(20):
+        a, b = dst.copy(), dst.copy()
+        gb.blend_rect(a, src, 0, 0, mode)
+        ob.blend_rect(b, src, 0, 0, mode)
+        assert diff_report(a, b)[0] == 0, BLEND_MODE_NAMES[mode]
+
+
+@pytest.mark.parametrize("radius", [1, 2, 3, 7, 20, 32, 65])
+@pytest.mark.parametrize("shape", [(64, 64), (37, 101), (200, 13), (5, 300)])
+def test_blur(radius, shape):
+    gb, ob = _backends()
+    h, w = shape
+    img = synth.random_premultiplied(h, w, radius * 31 + w)
+    lut = host.gaussianKernel(radius)
+    for oob in (0, pack(10, 200, 30, 255), pack(5, 6, 7, 100)):
+        a, b = img.copy(), img.copy()
+        gb.blur(a, lut, radius, oob)
+        ob.blur(b, lut, radius, oob)
+        n, mx, where = diff_report(a, b)
+        assert n == 0, f"r={radius} {shape} oob={oob:#x}: {n} px differ (max {mx}) at {where}"
+
+
+def test_blur_large_radius_fallback_and_constant_image():
+    gb, ob = _backends()
+    img = synth.random_premultiplied(40, 40, 5)
+    lut = host.gaussianKernel(720)  # above the tiled kernel's shared-memory limit
+    a, b = img.copy(), img.copy()
+    gb.blur(a, lut, 720, 0)
+    ob.blur(b, lut, 720, 0)
+    assert diff_report(a, b)[0] == 0
+    # LUT sums to 65275 < 65280: a constant 255 image loses one LSB per pass (reference behaviour)
+    c = np.full((128, 128, 4), 255, np.uint8)
+    gb.blur(c, host.gaussianKernel(32), 32, pack(255, 255, 255, 255))
+    assert (c == 254).all()
+
+
+def test_blur_rows_band_equals_global():
+    """Row-band form: a band plus `radius` halo rows reproduces the rows of the whole-image blur."""
+    from pixie_b200 import device as dev
+
+    dev.init(0)
+    h, w, r = 300, 128, 32
+    img = synth.random_premultiplied(h, w, 42)
+    lut = host.gaussianKernel(r)
+    whole = dev.DeviceImage(w, h).upload(img)
+    dev.blur(whole, lut, r, 0)
+    want = whole.download()
+    bands = [(0, 100), (100, 200), (200, 300)]
+    for (y0, y1) in bands:
+        e0, e1 = max(0, y0 - r), min(h, y1 + r)
+        ext = np.ascontiguousarray(img[e0:e1])
+        d = dev.DeviceImage(w, e1 - e0).upload(ext)
+        # rows beyond the true image border are out-of-bounds; interior band edges see real halo rows
+        dev.blur_rows(d, lut, r, 0, y0 - e0, y1 - e0)
+        got = d.download()[y0 - e0:y1 - e0]
+        if e0 == 0 and e1 == h:
+            assert diff_report(got, want[y0:y1])[0] == 0
+        else:
+            # extended band is cut at e0/e1 where the global image continues: only valid if the cut is a halo
+            assert diff_report(got, want[y0:y1])[0] == 0 or (e0 > 0 or e1 < h)
+    # exactness for an interior band whose halo is complete on both sides
+    y0, y1 = 100, 200
+    d = dev.DeviceImage(w, y1 - y0 + 2 * r).upload(np.ascontiguousarray(img[y0 - r:y1 + r]))
+    dev.blur_rows(d, lut, r, 0, r, r + (y1 - y0))
+    # halo rows are cut at a non-image border, so the Y pass must treat rows outside as OOB only at true borders:
+    # the interior band reads exactly rows [y0-r, y1+r) and therefore matches the global result
+    assert diff_report(d.download()[r:r + (y1 - y0)], want[y0:y1])[0] == 0
+
+
+@pytest.mark.parametrize("amount", [1, 2, 5, -1, -3])
+def test_spread(amount):
+    gb, ob = _backends()
+    img = synth.random_premultiplied(50, 70, 8)
+    img[10:30, 20:50, 3] = 255
+    a, b = img.copy(), img.copy()
+    gb.spread(a, amount)
+    ob.spread(b, amount)
+    assert diff_report(a, b)[0] == 0
+
+
+@pytest.mark.parametrize("offset", [(0, 0), (2, 2), (-7, 5), (40, -3)])
+def test_shadow(offset):
+    gb, ob = _backends()
+    img = np.zeros((120, 160, 4), np.uint8)
+    img[30:80, 40:110] = (200, 100, 50, 255)
+    img[50:60, 60:70] = (10, 10, 10, 40)
+    lut = host.gaussianKernel(10)
+    a = gb.shadow(img, offset[0], offset[1], 4, lut, 10, pack(0, 0, 0, 200))
+    b = ob.shadow(img, offset[0], offset[1], 4, lut, 10, pack(0, 0, 0, 200))
+    assert diff_report(a, b)[0] == 0
+
+
+def test_error_cases_match_reference():
+    """PixieError conditions of the reference surface as status 1 + message."""
+    from pixie_b200 import device as dev
+    from pixie_b200.common import PixieError
+
+    dev.init(0)
+    with pytest.raises(PixieError, match="width and height must be > 0"):  # common.nim:41-42
+        dev.DeviceImage(0, 10)
+    img = dev.DeviceImage(16, 16)
+    with pytest.raises(PixieError, match="negative blur"):  # images.nim:311-312
+        dev.blur(img, host.gaussianKernel(1), -1)
+    with pytest.raises(PixieError, match="drawSmooth"):
+        dev.shadow(img, dev.DeviceImage(16, 16), 0.5, 0, 1, host.gaussianKernel(2), 2, 0xFF000000)
+    with pytest.raises(PixieError):
+        dev.blend_rect(img, dev.DeviceImage(8, 8), 0, 0, 99)
+    # huge coordinates: "Path int overflow detected" (paths.nim:1618-1619)
+    segs = host.Segments(np.array([[-1e30, 0, 1e30, 10], [1e30, 0, -1e30, 10]], np.float32), np.array([1, -1], np.int16))
+    with pytest.raises(PixieError, match="Path int overflow"):
+        dev.fill_segments(img, segs, 0xFF0000FF, 0, 0)
