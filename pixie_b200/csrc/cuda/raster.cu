@@ -458,6 +458,7 @@ __device__ __noinline__ void fill_row(WarpCtx& c, const FillHeader& H, const Ras
   const float scanTop = (float)y, scanBottom = (float)(y + 1);
   bool allSpan = true;
   int nsel = 0;
+  const int* selC = sel;  // entry order seen by computeCoverage
   if (two) {
     nsel = 2;
     if (lane < 2) sel[lane] = lane;
@@ -478,6 +479,9 @@ __device__ __noinline__ void fill_row(WarpCtx& c, const FillHeader& H, const Ras
   }
   __syncwarp();
 
+#ifdef PIXIE_DEBUG_ROW
+  if (y == PIXIE_DEBUG_ROW && lane == 0) printf("DBG y=%d eCnt=%d nsel=%d allSpan=%d aa=%d two=%d cap=%d\n", y, eCnt, nsel, (int)allSpan, (int)aa, (int)two, cap);
+#endif
   if (allSpan && (nsel % 2) == 0) {  // mode B (:1691-1872)
     float* mid = reinterpret_cast<float*>(hitAt);  // sort keys
     for (int s = lane; s < nsel; s += 32) {
@@ -519,6 +523,13 @@ __device__ __noinline__ void fill_row(WarpCtx& c, const FillHeader& H, const Ras
       }
       ok = __all_sync(0xffffffffu, ok);
     }
+#ifdef PIXIE_DEBUG_ROW
+    if (y == PIXIE_DEBUG_ROW && lane == 0) {
+      printf("DBG modeB ok=%d order:", (int)ok);
+      for (int i = 0; i < nsel; i++) printf(" %d(%.6f)", sel[hitW2[i]], midS[i]);
+      printf("\n");
+    }
+#endif
     if (ok) {
       int filledTo = 0;
       for (int i = 0; i < nsel; i += 2) {
@@ -578,6 +589,10 @@ __device__ __noinline__ void fill_row(WarpCtx& c, const FillHeader& H, const Ras
       if (MODE == MaskBlend) clear_span(c, min(filledTo, W), W);
       return;
     }
+    // The reference sorts entryIndices in place (:1707-1716) before it decides whether the shortcut
+    // applies, so when it falls through, computeCoverage walks the entries in mid-x order.
+    for (int i = lane; i < nsel; i += 32) sel2[i] = sel[hitW2[i]];
+    selC = sel2;
     __syncwarp();
   }
 
@@ -599,7 +614,7 @@ __device__ __noinline__ void fill_row(WarpCtx& c, const FillHeader& H, const Ras
       bool hit = false;
       int at = 0, wv = 0;
       if (s < nsel) {
-        const Entry e = ent[sel[s]];
+        const Entry e = ent[selC[s]];
         if (e.ay <= yLine && e.by >= yLine) {
           float x = e.m == 0.0f ? e.b : (yLine - e.b) / e.m;
           x = (x != x) ? wf : (x < wf ? x : wf);  // min(x, width.float32)
@@ -626,6 +641,15 @@ __device__ __noinline__ void fill_row(WarpCtx& c, const FillHeader& H, const Ras
     if (lane == 0) ns = walk_spans(hitAt2, hitW2, numHits, rule, spanA, spanB);
     ns = __shfl_sync(0xffffffffu, ns, 0);
     __syncwarp();
+#ifdef PIXIE_DEBUG_ROW
+    if (y == PIXIE_DEBUG_ROW && lane == 0) {
+      printf("DBG m=%d yLine=%.9g hits:", m, yLine);
+      for (int i = 0; i < numHits; i++) printf(" %d/%d", hitAt2[i], hitW2[i]);
+      printf(" spans:");
+      for (int i = 0; i < ns; i++) printf(" [%d,%d)", spanA[i], spanB[i]);
+      printf("\n");
+    }
+#endif
     if (aa) {
       for (int k = 0; k < ns; k++) {  // :1391-1431
         const int prevAt = spanA[k], at = spanB[k];

@@ -115,8 +115,10 @@ def test_blur_large_radius_fallback_and_constant_image():
     assert diff_report(a, b)[0] == 0
     # LUT sums to 65275 < 65280: a constant 255 image loses one LSB per pass (reference behaviour)
     c = np.full((128, 128, 4), 255, np.uint8)
+    d = c.copy()
     gb.blur(c, host.gaussianKernel(32), 32, pack(255, 255, 255, 255))
-    assert (c == 254).all()
+    ob.blur(d, host.gaussianKernel(32), 32, pack(255, 255, 255, 255))
+    assert diff_report(c, d)[0] == 0 and c.max() < 255
 
 
 def test_blur_rows_band_equals_global():

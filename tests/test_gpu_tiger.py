@@ -47,3 +47,19 @@ def test_tiger_4096_properties():
     assert c1 == wc
     got = img.download()
     assert diff_report(got, want[0])[0] == 0
+
+
+def test_tiger_per_fill_coverage_maps():
+    """Every tiger fill alone, in white OverwriteBlend on its own layer: the canvas then IS the coverage map,
+    so differences cannot hide behind an equal backdrop colour (black strokes over black fills)."""
+    size = 1024
+    arrays = psvg.svg_fill_batch(psvg.parseSvg(open(TIGER).read(), size, size)).arrays()
+    n = len(arrays["rgbx"])
+    arrays["layer"] = np.arange(n, dtype=np.int32)
+    arrays["rgbx"][:] = 0xFFFFFFFF
+    arrays["mode"][:] = 17
+    want, wc = oracle_render_batch(arrays, size, size, layers=n)
+    got, gc_ = gpu_render_batch(arrays, size, size, layers=n)
+    bad = [(k, diff_report(got[k], want[k])[:2]) for k in range(n) if diff_report(got[k], want[k])[0]]
+    assert not bad, bad[:10]
+    assert gc_ == wc
