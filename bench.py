@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the raster hot path on B200.
+
+Workload at every N: BASELINE.json configs[1] — the Ghostscript tiger (tests/golden/tiger.svg, the
+reference's examples/data/tiger.svg fixture) through parseSvg(data, 4096, 4096) semantics: 227
+fills + 78 strokes in document order (90 079 segments), first fill OverwriteBlend, the rest
+NormalBlend, into a fresh transparent 4096x4096 RGBX canvas.  One *step* = clear the canvas + one
+pass of the ordered command list (partition kernel + fused scanline kernel).  N>1 = one process
+per GPU (torchrun), each rank renders its own canvas (independent images, no data-path collective),
+scaling "weak".
+
+metric  = Mpixels/s filled+blended: sum over fills of pixels touched with non-zero coverage
+          (35.8 Mpx per tiger at 4096^2, counted by the kernel and equal to the oracle's count) / time.
+value   = inputs (segments + fill headers) already resident in HBM, CUDA-event timed.
+e2e     = through the C-ABI entry point with HOST buffers: pixie_cuda_fill_batch(host segments) +
+          pixie_cuda_image_download_async to pinned memory, wall clock, H2D/D2H inside the timed region.
+L2 is flushed between timed iterations (256 MiB device write); canvas = 64 MiB < 126 MB L2.
+
+`--impl reference` times the reference's CPU path restated by the oracle (oracle/, kind "port": the
+Nim reference cannot be built in this image) on the host cores, same metric / config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mpixels/s filled+blended (tiger SVG 4096^2)"
+UNIT = "Mpixel/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tiger_arrays(size):
+    from pixie_b200 import svg as psvg
+
+    with open(os.path.join(ROOT, "tests", "golden", "tiger.svg")) as f:
+        data = f.read()
+    return psvg.svg_fill_batch(psvg.parseSvg(data, size, size)).arrays()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_tiger(arrays, size, repeats):
+    """The oracle (CPU restatement of the reference) rendering the same command list, one thread
+    (fills of one canvas are order-dependent and the reference is single-threaded)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _util import oracle_render_batch
+
+    oracle_render_batch(arrays, size, size)  # warm-up (page faults, library load)
+    times, covered = [], 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        _, covered = oracle_render_batch(arrays, size, size)
+        times.append(time.perf_counter() - t0)
+    return covered, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import __graft_entry__ as g
+
+    g.build_cpu()
+    arrays = tiger_arrays(args.size)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _util import oracle_render_batch
+
+    for _ in range(args.warmup):
+        oracle_render_batch(arrays, args.size, args.size)
+    times, covered = [], 0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        _, covered = oracle_render_batch(arrays, args.size, args.size)
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    val = covered / (ms * 1e-3) / 1e6
+    out = {
+        "impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "tests/golden/tiger.svg (reference fixture)",
+        "config": workload_config(args.size, arrays),
+        "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{args.steps} full tiger renders at {args.size}^2 (whole workload, 1 thread: "
+                                   "fills are order-dependent and the reference is single-threaded)"},
+        "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def workload_config(size, arrays):
+    return {"workload": f"tiger.svg at {size}x{size}: {len(arrays['rgbx'])} ordered fills, "
+                        f"{int(arrays['seg_offsets'][-1])} segments, first OverwriteBlend then NormalBlend",
+            "canvas": f"{size}x{size} RGBX premultiplied", "l2": "flushed between timed iterations (256 MiB write)",
+            "partition": "independent canvas per GPU"}
+
+
+def extras_single_gpu(dev, peak):
+    """BASELINE configs 3 and 4 on one GPU: blend 8192^2 and blur r=32 / shadow 16384^2 (GB/s vs HBM)."""
+    from pixie_b200 import host, synth
+    from pixie_b200.common import BLEND_MODE_NAMES
+
+    out = {}
+    # ---- C3: all 20 modes, 8192^2 dst/src + A8 coverage mask (13 B/px; Overwrite 9 B/px)
+    n = 8192
+    tile = synth.random_premultiplied(512, n, 0x5EED)
+    dst0 = dev.DeviceImage(n, n).upload(np.tile(tile, (n // 512, 1, 1)))
+    src = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 0x5EED + 1), (n // 512, 1, 1)))
+    mask = dev.DeviceImage(n, n, a8=True).upload(np.tile(synth.coverage_mask(512, n, 0x5EED + 2), (n // 512, 1)))
+    dst = dev.DeviceImage(n, n)
+    blends = {}
+    for mode in range(20):
+        ms = []
+        for it in range(4):
+            dst.copy_from(dst0)  # also evicts src/mask lines: 3 x 256 MiB planes >> L2
+            dev.blend_rect_masked(dst, src, mask, 0, 0, mode)
+            t = dev.profile_read(dev.PROF_BLEND)
+            if it:
+                ms.append(t)
+        t = statistics.median(ms)
+        nbytes = n * n * (9 if mode == 17 else 13)
+        blends[BLEND_MODE_NAMES[mode]] = {"ms": round(t, 4), "GB/s": round(nbytes / t / 1e6, 1),
+                                          "frac_hbm": round(nbytes / t / 1e6 / peak, 3)}
+    out["blend_8192_masked"] = {"bytes_per_px": "13 (dst r+w, src r, 1-B coverage); Overwrite 9", "modes": blends}
+    del dst0, src, mask, dst
+    # ---- C4: blur r=32 on 16384^2 (8 B/px algorithmic) + shadow
+    n = 16384
+    img = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 0xB10B), (n // 512, 1, 1)))
+    lut = host.gaussianKernel(32)
+    ms, msx, msy = [], [], []
+    for it in range(3):
+        dev.timer_begin()
+        dev.blur(img, lut, 32, 0)
+        t = dev.timer_end()
+        if it:
+            ms.append(t)
+            msx.append(dev.profile_read(dev.PROF_BLUR_X))
+            msy.append(dev.profile_read(dev.PROF_BLUR_Y))
+    t = statistics.median(ms)
+    out["blur_r32_16384"] = {"ms": round(t, 3), "x_pass_ms": round(statistics.median(msx), 3),
+                             "y_pass_ms": round(statistics.median(msy), 3),
+                             "GB/s": round(n * n * 8 / t / 1e6, 1), "frac_hbm": round(n * n * 8 / t / 1e6 / peak, 3),
+                             "bytes_per_px": 8, "Gtaps_per_s": round(n * n * 4 * 2 * 65 / t / 1e6, 1),
+                             "bound": "ALU (65 taps x 4 ch x 2 passes per px), not HBM"}
+    dstimg = dev.DeviceImage(n, n)
+    ms = []
+    for it in range(2):
+        dev.timer_begin()
+        dev.shadow(img, dstimg, 8, 8, 4, lut, 32, 0xC8000000)
+        ms.append(dev.timer_end())
+    out["shadow_16384"] = {"ms": round(ms[-1], 3), "GB/s": round(n * n * 8 / ms[-1] / 1e6, 1)}
+    return out
+
+
+def run_ours(args):
+    import __graft_entry__ as g
+    from pixie_b200 import device as dev
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+
+        torch.cuda.set_device(local_rank)
+        dist_.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_
+    if not os.path.exists(dev.LIB_PATH):
+        g.build()
+    dev.init(local_rank)
+    dev.set_profiling(True)
+    peak, peak_src = load_peaks()
+    size = args.size
+    arrays = tiger_arrays(size)
+    nseg = int(arrays["seg_offsets"][-1])
+
+    def barrier():
+        dev.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        import torch
+
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    img = dev.DeviceImage(size, size)
+    flush = dev.DeviceImage(8192, 8192)  # 256 MiB > 126 MB L2
+    cl = dev.CmdList(size, size, 1, arrays)
+    covered = cl.run(img, count_covered=True)
+    info = cl.info()
+    pinned = dev.PinnedBuffer(size * size * 4)
+
+    def l2_flush(i):
+        flush.fill(0x01020304 + i)
+
+    # ---- device-resident timing (value)
+    for i in range(args.warmup):
+        l2_flush(i)
+        img.fill(0)
+        cl.run(img)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step_ms, part_ms, rast_ms = [], [], []
+    launches0 = dev.launch_count()
+    launches_timed = 0
+    barrier()
+    for i in range(args.steps):
+        l2_flush(i)
+        dev.sync()
+        l0 = dev.launch_count()
+        dev.timer_begin()
+        img.fill(0)
+        cl.run(img)
+        step_ms.append(dev.timer_end())
+        launches_timed += dev.launch_count() - l0
+        part_ms.append(dev.profile_read(dev.PROF_PARTITION))
+        rast_ms.append(dev.profile_read(dev.PROF_RASTER))
+    barrier()
+    total_ms = max_over_ranks(sum(step_ms))
+    ms_per_step = total_ms / args.steps
+    value = world * covered / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with host buffers
+    for i in range(min(args.warmup, 3)):
+        img.fill(0)
+        dev.fill_batch(img, arrays)
+        dev.download_async(img, pinned)
+        dev.sync()
+    e2e_s = []
+    barrier()
+    for i in range(args.steps):
+        l2_flush(i)
+        dev.sync()
+        t0 = time.perf_counter()
+        img.fill(0)
+        dev.fill_batch(img, arrays)      # host segments -> H2D -> partition + raster kernels
+        dev.download_async(img, pinned)  # canvas -> pinned host memory
+        dev.sync()
+        e2e_s.append(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop()
+    e2e_total = max_over_ranks(sum(e2e_s))
+    e2e_value = world * covered / (e2e_total / args.steps) / 1e6
+    h2d = nseg * 18 + len(arrays["rgbx"]) * 56 + (info["partitions"] * 2 + 1) * 4
+    d2h = size * size * 4
+    checksum_ok = int(pinned.array[:size * size * 4].view(np.uint32).sum(dtype=np.uint64)) != 0
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (raster_kernel), algorithmic bytes per SURVEY.md 8(d)
+    alg_bytes = 8 * covered + 18 * nseg
+    rast = statistics.mean(rast_ms)
+    part = statistics.mean(part_ms)
+    achieved = alg_bytes / (rast * 1e-3) / 1e9
+    roofline = {"kernel": "raster_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(rast, 4),
+                "partition_kernel_ms": round(part, 4), "share_of_step": round(rast / statistics.mean(step_ms), 3),
+                "note": "305 order-dependent fills: latency/occupancy-bound, not bandwidth-bound (SURVEY.md 7.1)"}
+
+    cpu = None
+    extras = None
+    if world == 1:
+        g.build_cpu()
+        reps = max(3, min(40, int(args.cpu_seconds / 0.35)))
+        ccov, times = cpu_tiger(arrays, size, reps)
+        cval = ccov / statistics.mean(times) / 1e6
+        cpu = {"value": round(cval, 3), "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{reps} full tiger renders at {size}^2 with the oracle (same workload, 1 thread: fills of a "
+                         "canvas are order-dependent; the reference is single-threaded)",
+               "covered_px_equal_to_gpu": bool(ccov == covered)}
+        if not args.no_extras:
+            try:
+                extras = extras_single_gpu(dev, peak)
+            except Exception as e:  # extras never block the headline line
+                extras = {"error": repr(e)}
+
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "tests/golden/tiger.svg (reference fixture); synthetic for extras",
+        "config": workload_config(size, arrays), "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": round(1e3 * e2e_total / args.steps, 4), "result_nonzero": checksum_ok},
+        "gpu_launches": int(launches_timed),
+        "covered_px_per_step": int(covered), "cmdlist": info,
+        "roofline": roofline, "cpu_baseline": cpu,
+    }
+    if extras is not None:
+        out["extras"] = extras
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

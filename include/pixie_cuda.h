@@ -25,6 +25,7 @@
 #ifndef PIXIE_CUDA_H
 #define PIXIE_CUDA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -133,9 +134,18 @@ int pixie_cuda_blur_host(uint8_t* pixels, int width, int height, const uint16_t*
 int pixie_cuda_shadow_host(const uint8_t* src_pixels, uint8_t* dst_pixels, int width, int height, float offset_x,
                            float offset_y, int spread, const uint16_t* lut, int radius, uint32_t rgbx);
 
+/* page-locked host staging memory for the *_async copies */
+int pixie_cuda_host_alloc(size_t bytes, void** out);
+int pixie_cuda_host_free(void* ptr);
+
 /* ---- instrumentation ----------------------------------------------------------------------- */
 /* number of kernels this library has launched since init (bench.py's gpu_launches) */
 int pixie_cuda_launch_count(uint64_t* out);
+/* per-kernel CUDA-event timing on the library's stream.  Slots: 0 partition kernel, 1 raster kernel,
+ * 2 blur X pass, 3 blur Y pass, 4 blend_rect kernel, 5 spread kernels.  profile_read waits for the
+ * slot's last launch and returns its duration in milliseconds. */
+int pixie_cuda_set_profiling(int enabled);
+int pixie_cuda_profile_read(int slot, float* elapsed_ms);
 /* CUDA-event timing on the library's stream: begin/end bracket, elapsed in milliseconds */
 int pixie_cuda_timer_begin(void);
 int pixie_cuda_timer_end(float* elapsed_ms);

@@ -148,6 +148,7 @@ static int launch_rect(const RectArgs& a) {
     int max_gy = (rows + 3) / 4;
     if (gy > max_gy) gy = max_gy;
     grid.y = gy;
+    ProfScope ps(kProfBlend);
     blend_rect_vec4<MODE, MASK><<<grid, 256, 0, r.stream>>>(a);
   } else {
     dim3 grid((a.xe - a.xs + 255) / 256, 1);

@@ -184,12 +184,18 @@ static int blur_impl(Image* im, const uint16_t* lut_host, int radius, uint32_t o
     // X pass: image -> tmp
     a.src = (const px_t*)im->data; a.dst = (px_t*)tmp;
     dim3 gx((im->w + kOutA - 1) / kOutA, (a.sy1 - a.sy0 + 31) / 32);
-    conv_tiled<false><<<gx, kWarps * 32, smem, r.stream>>>(a, (const uint16_t*)lut_d);
+    {
+      ProfScope ps(kProfBlurX);
+      conv_tiled<false><<<gx, kWarps * 32, smem, r.stream>>>(a, (const uint16_t*)lut_d);
+    }
     PX_LAUNCHED();
     // Y pass: tmp -> image rows [y0, y1)
     a.src = (const px_t*)tmp; a.dst = (px_t*)im->data;
     dim3 gy((y1 - y0 + kOutA - 1) / kOutA, (im->w + 31) / 32);
-    conv_tiled<true><<<gy, kWarps * 32, smem, r.stream>>>(a, (const uint16_t*)lut_d);
+    {
+      ProfScope ps(kProfBlurY);
+      conv_tiled<true><<<gy, kWarps * 32, smem, r.stream>>>(a, (const uint16_t*)lut_d);
+    }
     PX_LAUNCHED();
   } else {
     a.src = (const px_t*)im->data; a.dst = (px_t*)tmp;

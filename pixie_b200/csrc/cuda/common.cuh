@@ -38,6 +38,16 @@ struct Runtime {
   size_t scratch_bytes[4] = {0, 0, 0, 0};
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
+  // per-kernel CUDA-event timing (pixie_cuda_set_profiling): slot -> (begin, end) of the last launch
+  bool profiling = false;
+  cudaEvent_t prof[8][2] = {};
+};
+
+enum ProfSlot { kProfPartition = 0, kProfRaster = 1, kProfBlurX = 2, kProfBlurY = 3, kProfBlend = 4, kProfSpread = 5 };
+struct ProfScope {  // brackets one kernel launch with events on the library stream when profiling is on
+  int slot;
+  explicit ProfScope(int s);
+  ~ProfScope();
 };
 
 Runtime& rt();

@@ -946,8 +946,11 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px) {
   if (L.numParts > 0) {
     const int warps = (int)std::min<int64_t>(L.numParts, (int64_t)r.num_sms * 32);
     const int blocks = (warps + 7) / 8;
-    partition_kernel<<<blocks, 256, 0, r.stream>>>(L.fills, L.partFill, L.entryOff, L.segs, L.wind, L.entries, L.flags,
-                                                   (int)L.numParts);
+    {
+      ProfScope ps(kProfPartition);
+      partition_kernel<<<blocks, 256, 0, r.stream>>>(L.fills, L.partFill, L.entryOff, L.segs, L.wind, L.entries,
+                                                     L.flags, (int)L.numParts);
+    }
     PX_LAUNCHED();
   }
   RasterArgs A;
@@ -962,7 +965,10 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px) {
     PX_CUDA(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes));
     configured = L.smemBytes;
   }
-  raster_kernel<<<L.rasterBlocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
+  {
+    ProfScope ps(kProfRaster);
+    raster_kernel<<<L.rasterBlocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
+  }
   PX_LAUNCHED();
   if (covered_px) {
     unsigned long long host[2];

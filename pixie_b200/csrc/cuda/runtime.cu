@@ -25,6 +25,15 @@ int fail_cuda(cudaError_t e, const char* what) {
   return 2;
 }
 
+ProfScope::ProfScope(int s) : slot(s) {
+  Runtime& r = rt();
+  if (r.profiling) cudaEventRecord(r.prof[slot][0], r.stream);
+}
+ProfScope::~ProfScope() {
+  Runtime& r = rt();
+  if (r.profiling) cudaEventRecord(r.prof[slot][1], r.stream);
+}
+
 int ensure_init() {
   Runtime& r = rt();
   if (r.inited) return 0;
@@ -294,6 +303,33 @@ int pixie_cuda_image_checksum(pixie_image_t h, uint64_t* out) {
   PX_LAUNCHED();
   PX_CUDA(cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, r.stream));
   PX_CUDA(cudaStreamSynchronize(r.stream));
+  return 0;
+}
+
+int pixie_cuda_host_alloc(size_t bytes, void** out) {
+  if (int rc = ensure_init()) return rc;
+  PX_CUDA(cudaMallocHost(out, bytes));
+  return 0;
+}
+int pixie_cuda_host_free(void* p) {
+  PX_CUDA(cudaFreeHost(p));
+  return 0;
+}
+
+int pixie_cuda_set_profiling(int enabled) {
+  if (int rc = ensure_init()) return rc;
+  Runtime& r = rt();
+  if (enabled && !r.prof[0][0])
+    for (int i = 0; i < 8; i++)
+      for (int j = 0; j < 2; j++) PX_CUDA(cudaEventCreate(&r.prof[i][j]));
+  r.profiling = enabled != 0;
+  return 0;
+}
+int pixie_cuda_profile_read(int slot, float* ms) {
+  Runtime& r = rt();
+  if (slot < 0 || slot >= 8 || !r.prof[0][0]) return fail_pixie("profiling slot out of range or profiling never enabled");
+  PX_CUDA(cudaEventSynchronize(r.prof[slot][1]));
+  PX_CUDA(cudaEventElapsedTime(ms, r.prof[slot][0], r.prof[slot][1]));
   return 0;
 }
 

@@ -59,6 +59,10 @@ _SIGNATURES = {
     "pixie_cuda_blend_rect_host": [vp, i32, i32, vp, i32, i32, i32, i32, i32],
     "pixie_cuda_blur_host": [vp, i32, i32, vp, i32, u32],
     "pixie_cuda_shadow_host": [vp, vp, i32, i32, f32, f32, i32, vp, i32, u32],
+    "pixie_cuda_host_alloc": [C.c_size_t, P(vp)],
+    "pixie_cuda_host_free": [vp],
+    "pixie_cuda_set_profiling": [i32],
+    "pixie_cuda_profile_read": [i32, P(f32)],
     "pixie_cuda_launch_count": [P(u64)],
     "pixie_cuda_timer_begin": [],
     "pixie_cuda_timer_end": [P(f32)],
@@ -299,6 +303,46 @@ def spread(image: DeviceImage, amount):
 def shadow(src: DeviceImage, dst: DeviceImage, ox, oy, spread_, lut, radius, rgbx):
     lut = np.ascontiguousarray(lut, np.uint16)
     check(lib().pixie_cuda_shadow(src.handle, dst.handle, ox, oy, spread_, lut.ctypes.data, radius, rgbx))
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a numpy uint8 array (for upload_async / download_async)."""
+
+    def __init__(self, nbytes: int):
+        p = vp()
+        check(lib().pixie_cuda_host_alloc(nbytes, C.byref(p)))
+        self.ptr = p.value
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, P(C.c_uint8)), (nbytes,))
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None):
+                self.array = None
+                lib().pixie_cuda_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def download_async(image: DeviceImage, pinned: PinnedBuffer):
+    check(lib().pixie_cuda_image_download_async(image.handle, pinned.ptr))
+
+
+def upload_async(image: DeviceImage, pinned: PinnedBuffer):
+    check(lib().pixie_cuda_image_upload_async(image.handle, pinned.ptr))
+
+
+PROF_PARTITION, PROF_RASTER, PROF_BLUR_X, PROF_BLUR_Y, PROF_BLEND, PROF_SPREAD = range(6)
+
+
+def set_profiling(enabled: bool):
+    check(lib().pixie_cuda_set_profiling(1 if enabled else 0))
+
+
+def profile_read(slot: int) -> float:
+    v = f32(0)
+    check(lib().pixie_cuda_profile_read(slot, C.byref(v)))
+    return v.value
 
 
 def timer_begin():
