@@ -156,10 +156,10 @@ static int blur_impl(Image* im, const uint16_t* lut_host, int radius, uint32_t o
   void *tmp, *lut_d, *pin;
   if (int rc = get_scratch(0, im->bytes(), &tmp)) return rc;
   if (int rc = get_scratch(1, (size_t)ntaps * 2, &lut_d)) return rc;
-  if (int rc = get_pinned((size_t)ntaps * 2, &pin)) return rc;
-  PX_CUDA(cudaStreamSynchronize(r.stream));  // the pinned staging buffer is reused between calls
+  if (int rc = staging_acquire((size_t)ntaps * 2, &pin)) return rc;
   memcpy(pin, lut_host, (size_t)ntaps * 2);
   PX_CUDA(cudaMemcpyAsync(lut_d, pin, (size_t)ntaps * 2, cudaMemcpyHostToDevice, r.stream));
+  if (int rc = staging_release()) return rc;
 
   ConvArgs a;
   a.w = im->w; a.h = im->h; a.radius = radius; a.oob = oob;

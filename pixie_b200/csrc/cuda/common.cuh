@@ -38,6 +38,8 @@ struct Runtime {
   size_t scratch_bytes[4] = {0, 0, 0, 0};
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
+  cudaEvent_t staging_done = nullptr;  // recorded after the H2D copy that reads `pinned`
+  bool staging_busy = false;
   // per-kernel CUDA-event timing (pixie_cuda_set_profiling): slot -> (begin, end) of the last launch
   bool profiling = false;
   cudaEvent_t prof[8][2] = {};
@@ -58,6 +60,8 @@ int ensure_init();
 Image* find_image(uint64_t h);
 int get_scratch(int slot, size_t bytes, void** out);
 int get_pinned(size_t bytes, void** out);
+int staging_acquire(size_t bytes, void** out);  // pinned staging, safe to overwrite on return
+int staging_release();                          // call right after enqueuing the copy that reads it
 
 #define PX_CUDA(call)                                  \
   do {                                                 \

@@ -57,7 +57,9 @@ struct CmdList {
   uint32_t* scratch = nullptr;  // per-warp spill area when a band has more entries than fit in smem
   unsigned long long* counters = nullptr;  // [0] row ticket, [1] covered px
   int rasterBlocks = 0, warpsPerBlock = 0, scratchWords = 0, covBytes = 0, smemCap = 0;
-  size_t smemBytes = 0;
+  size_t smemBytes = 0, h2dBytes = 0;
+  uint8_t* block = nullptr;  // single device allocation (or a slice of the library arena) holding all of the above
+  bool owned = false;
 };
 
 static std::unordered_map<uint64_t, CmdList> g_lists;
@@ -775,23 +777,14 @@ static inline uint32_t f2u_host(float f) {  // matches __float2uint_rz (saturati
   return (uint32_t)f;
 }
 
-template <typename T>
-static int upload(T** dptr, const std::vector<T>& v, cudaStream_t st) {
-  *dptr = nullptr;
-  if (v.empty()) return 0;
-  PX_CUDA(cudaMalloc(dptr, v.size() * sizeof(T)));
-  PX_CUDA(cudaMemcpyAsync(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
-  return 0;
-}
-
 static void free_list(CmdList& L) {
-  cudaFree(L.segs); cudaFree(L.wind); cudaFree(L.fills); cudaFree(L.partFill); cudaFree(L.entryOff);
-  cudaFree(L.layerFillBegin); cudaFree(L.entries); cudaFree(L.flags); cudaFree(L.scratch); cudaFree(L.counters);
+  if (L.owned && L.block) cudaFree(L.block);
+  L.block = nullptr;
 }
 
-static int build_list(CmdList& L, int w, int h, int layers, int numFills, const int32_t* layerOf, const float* seg,
-                      const int16_t* wind, const int32_t* segOff, const uint32_t* rgbx, const uint8_t* rule,
-                      const uint8_t* mode) {
+static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numFills, const int32_t* layerOf,
+                      const float* seg, const int16_t* wind, const int32_t* segOff, const uint32_t* rgbx,
+                      const uint8_t* rule, const uint8_t* mode) {
   Runtime& r = rt();
   if (w <= 0 || h <= 0 || layers <= 0) return fail_pixie("Image width and height must be > 0");
   if (numFills < 0) return fail_pixie("negative fill count");
@@ -899,19 +892,6 @@ static int build_list(CmdList& L, int w, int h, int layers, int numFills, const 
   L.numEntries = entriesTotal;
   L.maxEntries = maxEntries;
 
-  std::vector<float4> seg4((size_t)numSegs);
-  if (numSegs) memcpy(seg4.data(), seg, (size_t)numSegs * 16);
-  std::vector<int16_t> windv(wind, wind + numSegs);
-  if (int rc = upload(&L.segs, seg4, r.stream)) return rc;
-  if (int rc = upload(&L.wind, windv, r.stream)) return rc;
-  if (int rc = upload(&L.fills, fills, r.stream)) return rc;
-  if (int rc = upload(&L.partFill, partFill, r.stream)) return rc;
-  if (int rc = upload(&L.entryOff, entryOff, r.stream)) return rc;
-  if (int rc = upload(&L.layerFillBegin, layerBegin, r.stream)) return rc;
-  PX_CUDA(cudaMalloc(&L.entries, std::max<size_t>(1, (size_t)entriesTotal) * sizeof(Entry)));
-  PX_CUDA(cudaMalloc(&L.flags, std::max<size_t>(1, partFill.size())));
-  PX_CUDA(cudaMalloc(&L.counters, 16));
-
   // raster launch geometry: persistent warps, one (layer, row) ticket at a time
   L.covBytes = ((w + 7) & ~3) + 4;             // coverage row, word aligned, with the covBase slack
   L.smemCap = 64;                              // entries per band handled from shared memory
@@ -927,10 +907,65 @@ static int build_list(CmdList& L, int w, int h, int layers, int numFills, const 
   long long wantBlocks = (totalRows + L.warpsPerBlock - 1) / L.warpsPerBlock;
   L.rasterBlocks = (int)std::min<long long>(wantBlocks, (long long)r.num_sms * blocksPerSm);
   L.rasterBlocks = std::max(L.rasterBlocks, 1);
-  if (maxEntries > L.smemCap) {
-    L.scratchWords = maxEntries * kScratchArrays;
-    PX_CUDA(cudaMalloc(&L.scratch, (size_t)L.rasterBlocks * L.warpsPerBlock * L.scratchWords * 4));
+  L.scratchWords = maxEntries > L.smemCap ? maxEntries * kScratchArrays : 0;
+
+  // One device block for the whole list.  The host-written part (segments, windings, headers,
+  // offsets) is contiguous so that it moves with a single H2D copy from a staging buffer.
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t off = 0;
+  const size_t oSegs = off;      off = al(off + (size_t)numSegs * 16);
+  const size_t oWind = off;      off = al(off + (size_t)numSegs * 2);
+  const size_t oFills = off;     off = al(off + fills.size() * sizeof(FillHeader));
+  const size_t oPartFill = off;  off = al(off + partFill.size() * 4);
+  const size_t oEntryOff = off;  off = al(off + entryOff.size() * 4);
+  const size_t oLayer = off;     off = al(off + layerBegin.size() * 4);
+  const size_t h2dBytes = off;
+  const size_t oEntries = off;   off = al(off + std::max<size_t>(1, (size_t)entriesTotal) * sizeof(Entry));
+  const size_t oFlags = off;     off = al(off + std::max<size_t>(1, partFill.size()));
+  const size_t oCounters = off;  off = al(off + 16);
+  const size_t oScratch = off;   off = al(off + (size_t)L.rasterBlocks * L.warpsPerBlock * L.scratchWords * 4);
+  const size_t total = off;
+
+  uint8_t* stage = nullptr;
+  std::vector<uint8_t> pageable;
+  if (arena) {  // per-call lists: library-owned growing arena + pinned staging, no malloc/free per call
+    void *blk, *pin;
+    if (int rc = get_scratch(2, total, &blk)) return rc;
+    if (int rc = staging_acquire(h2dBytes, &pin)) return rc;
+    L.block = (uint8_t*)blk;
+    L.owned = false;
+    stage = (uint8_t*)pin;
+  } else {
+    PX_CUDA(cudaMalloc(&L.block, total));
+    L.owned = true;
+    pageable.resize(h2dBytes);
+    stage = pageable.data();
   }
+  if (numSegs) {
+    memcpy(stage + oSegs, seg, (size_t)numSegs * 16);
+    memcpy(stage + oWind, wind, (size_t)numSegs * 2);
+  }
+  if (!fills.empty()) memcpy(stage + oFills, fills.data(), fills.size() * sizeof(FillHeader));
+  if (!partFill.empty()) memcpy(stage + oPartFill, partFill.data(), partFill.size() * 4);
+  memcpy(stage + oEntryOff, entryOff.data(), entryOff.size() * 4);
+  memcpy(stage + oLayer, layerBegin.data(), layerBegin.size() * 4);
+  PX_CUDA(cudaMemcpyAsync(L.block, stage, h2dBytes, cudaMemcpyHostToDevice, r.stream));
+  if (arena) {
+    if (int rc = staging_release()) return rc;
+  } else {
+    PX_CUDA(cudaStreamSynchronize(r.stream));  // the pageable staging vector dies with this scope
+  }
+  L.segs = (float4*)(L.block + oSegs);
+  L.wind = (int16_t*)(L.block + oWind);
+  L.fills = (FillHeader*)(L.block + oFills);
+  L.partFill = (int*)(L.block + oPartFill);
+  L.entryOff = (int*)(L.block + oEntryOff);
+  L.layerFillBegin = (int*)(L.block + oLayer);
+  L.entries = (Entry*)(L.block + oEntries);
+  L.flags = L.block + oFlags;
+  L.counters = (unsigned long long*)(L.block + oCounters);
+  L.scratch = L.scratchWords ? (uint32_t*)(L.block + oScratch) : nullptr;
+  L.h2dBytes = h2dBytes;
   return 0;
 }
 
@@ -990,13 +1025,12 @@ int pixie_cuda_cmdlist_create(int w, int h, int layers, int numFills, const int3
                               const uint8_t* mode, pixie_cmdlist_t* out) {
   if (int rc = ensure_init()) return rc;
   CmdList L;
-  int rc = build_list(L, w, h, layers, numFills, layerOf, seg, wind, segOff, rgbx, rule, mode);
+  int rc = build_list(L, false, w, h, layers, numFills, layerOf, seg, wind, segOff, rgbx, rule, mode);
   if (rc) {
     cudaStreamSynchronize(rt().stream);
     free_list(L);
     return rc;
   }
-  PX_CUDA(cudaStreamSynchronize(rt().stream));  // host staging vectors die here
   std::lock_guard<std::mutex> lk(rt().mu);
   const uint64_t hd = g_next_list++;
   g_lists[hd] = L;
@@ -1040,11 +1074,9 @@ int pixie_cuda_fill_batch(pixie_image_t image, int numFills, const int32_t* laye
   Image* im = find_image(image);
   if (!im) return 1;
   if (im->bpp != 4) return fail_pixie("fill needs an RGBX image");
-  CmdList L;
-  int rc = build_list(L, im->w, im->h, im->layers, numFills, layerOf, seg, wind, segOff, rgbx, rule, mode);
+  CmdList L;  // lives in the library arena: no allocation, no synchronisation, nothing to free
+  int rc = build_list(L, true, im->w, im->h, im->layers, numFills, layerOf, seg, wind, segOff, rgbx, rule, mode);
   if (!rc) rc = run_list(L, im, covered_px);
-  cudaStreamSynchronize(rt().stream);
-  free_list(L);
   return rc;
 }
 

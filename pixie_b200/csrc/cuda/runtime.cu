@@ -84,6 +84,24 @@ int get_pinned(size_t bytes, void** out) {
   return 0;
 }
 
+// Pinned staging buffer shared by every host->device parameter copy.  acquire() waits until the
+// previous copy that read it has completed; release() marks the copy just enqueued.
+int staging_acquire(size_t bytes, void** out) {
+  Runtime& r = rt();
+  if (r.staging_busy) {
+    PX_CUDA(cudaEventSynchronize(r.staging_done));
+    r.staging_busy = false;
+  }
+  return get_pinned(bytes, out);
+}
+int staging_release() {
+  Runtime& r = rt();
+  if (!r.staging_done) PX_CUDA(cudaEventCreateWithFlags(&r.staging_done, cudaEventDisableTiming));
+  PX_CUDA(cudaEventRecord(r.staging_done, r.stream));
+  r.staging_busy = true;
+  return 0;
+}
+
 __global__ void fill_kernel(uint4* __restrict__ p, size_t n16, uint32_t v) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
