@@ -221,6 +221,37 @@ def extras_single_gpu(dev, peak):
     return out
 
 
+def banded_blur_multi_gpu(dev, dist, rank, world, local_rank, peak):
+    """BASELINE config 4 across N GPUs: one 16384^2 canvas in row bands, `radius` halo rows exchanged
+    with ncclSend/ncclRecv (torch.distributed P2P over NVLink), then the row-band blur kernel."""
+    import torch
+
+    from pixie_b200 import host, multi, synth
+
+    n, r = 16384, 32
+    y0, y1 = multi.band_range(n, world, rank)
+    tile = torch.from_numpy(synth.random_premultiplied(256, n, 0xB10B + rank)).cuda()
+    band = tile.repeat((y1 - y0 + 255) // 256, 1, 1)[: y1 - y0].contiguous()
+    lut = host.gaussianKernel(r)
+    times = []
+    for it in range(4):
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        multi.blur_band(band, r, lut, 0, rank, world)
+        e1.record()
+        torch.cuda.synchronize()
+        if it:
+            times.append(e0.elapsed_time(e1))
+    t = torch.tensor([statistics.median(times)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev.set_stream(None)
+    ms = float(t.item())
+    return {"ms": round(ms, 3), "GB/s": round(n * n * 8 / ms / 1e6, 1), "frac_hbm_aggregate": round(n * n * 8 / ms / 1e6 / (peak * world), 3),
+            "halo_bytes_per_interior_edge": 2 * r * n * 4, "scaling": "strong (one 16384^2 canvas)"}
+
+
 def run_ours(args):
     import __graft_entry__ as g
     from pixie_b200 import device as dev
@@ -321,6 +352,12 @@ def run_ours(args):
     d2h = size * size * 4
     checksum_ok = int(pinned.array[:size * size * 4].view(np.uint32).sum(dtype=np.uint64)) != 0
 
+    banded = None
+    if dist is not None and not args.no_extras:
+        try:
+            banded = banded_blur_multi_gpu(dev, dist, rank, world, local_rank, peak)
+        except Exception as e:
+            banded = {"error": repr(e)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -365,6 +402,9 @@ def run_ours(args):
         "covered_px_per_step": int(covered), "cmdlist": info,
         "roofline": roofline, "cpu_baseline": cpu,
     }
+    if banded is not None:
+        extras = dict(extras or {})
+        extras["blur_r32_16384_row_bands"] = banded
     if extras is not None:
         out["extras"] = extras
     print(json.dumps(out))

@@ -1,0 +1,78 @@
+"""One process per GPU: how the hot path shards across the GPUs of one B200 box.
+
+* independent images (icons, per-rank canvases): ``shard_range`` — contiguous blocks of units per
+  rank, no data-path collective;
+* one giant canvas: horizontal row bands (``band_range``).  Fills and blends are per-pixel/per-row
+  independent, so bands need no exchange.  ``blur`` / ``spread`` / ``shadow`` need `radius` rows from
+  the vertical neighbours: ``exchange_halos`` moves them with point-to-point send/recv
+  (torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests) and ``blur_band`` then runs
+  the row-band form of the kernel (pixie_cuda_blur_rows) on band + halo.  The halo carries *input*
+  rows; the X pass is recomputed on them, which gives the same bytes as exchanging the X-blurred
+  intermediate because that intermediate is quantised per row (images.nim:341-352).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n_units: int, world: int, rank: int):
+    """Contiguous block [begin, end) of independent units owned by `rank`."""
+    base, rem = divmod(n_units, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def band_range(height: int, world: int, rank: int):
+    """Row band [y0, y1) of a canvas of `height` rows owned by `rank`."""
+    return shard_range(height, world, rank)
+
+
+def exchange_halos(band, radius: int, rank: int, world: int, group=None):
+    """band: torch uint8 tensor [rows, width, 4] (this rank's rows).  Returns (ext, top, bottom):
+    ext = [halo_top ; band ; halo_bottom] with `top` / `bottom` halo rows actually received from the
+    neighbours (0 at the image border, and at most the neighbour's band height)."""
+    import torch
+    import torch.distributed as dist
+
+    rows = band.shape[0]
+    # how many rows each neighbour can provide / we can provide: bands may be shorter than radius
+    mine = torch.tensor([rows], dtype=torch.int64, device=band.device)
+    sizes = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(sizes, mine, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    top = min(radius, sizes[rank - 1]) if rank > 0 else 0
+    bottom = min(radius, sizes[rank + 1]) if rank < world - 1 else 0
+    if (rank > 0 and sizes[rank - 1] < radius and rank - 1 > 0) or \
+       (rank < world - 1 and sizes[rank + 1] < radius and rank + 1 < world - 1):
+        raise ValueError("bands shorter than the blur radius need multi-hop halos: use fewer ranks")
+    ext = torch.empty((top + rows + bottom,) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device)
+    ext[top:top + rows].copy_(band)
+    ops = []
+    send_up = min(radius, rows)
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, band[:send_up].contiguous(), rank - 1, group=group))
+        ops.append(dist.P2POp(dist.irecv, ext[:top], rank - 1, group=group))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.isend, band[rows - send_up:].contiguous(), rank + 1, group=group))
+        ops.append(dist.P2POp(dist.irecv, ext[top + rows:], rank + 1, group=group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return ext, top, bottom
+
+
+def blur_band(band, radius: int, lut: np.ndarray, oob_rgbx: int, rank: int, world: int, group=None):
+    """Blur one row band of a canvas split across `world` GPUs, in place.  band: CUDA uint8 tensor
+    [rows, width, 4].  Rows at the true image border see `oob_rgbx`; interior cuts see the
+    neighbours' rows."""
+    import torch
+
+    from . import device as dev
+
+    dev.set_stream(torch.cuda.current_stream().cuda_stream)  # NCCL and the kernels share one stream
+    ext, top, bottom = exchange_halos(band, radius, rank, world, group)
+    rows, width = band.shape[0], band.shape[1]
+    img = dev.DeviceImage.wrap(ext.data_ptr(), width, ext.shape[0], owner=ext)
+    dev.blur_rows(img, lut, radius, oob_rgbx, top, top + rows)
+    band.copy_(ext[top:top + rows])
+    return band

@@ -1,0 +1,54 @@
+"""The N>1 host logic on CPU: world_size 2 and 3 over gloo (no GPU): shard ranges, the halo
+exchange, and that band + halo blurs reproduce the global blur (checked with the oracle)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, h, w, radius, tmpdir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    from pixie_b200 import host, multi, synth
+    from _oracle import OracleBackend
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        img = synth.random_premultiplied(h, w, 123)  # every rank builds the same global image
+        y0, y1 = multi.band_range(h, world, rank)
+        band = torch.from_numpy(np.ascontiguousarray(img[y0:y1]))
+        ext, top, bottom = multi.exchange_halos(band, radius, rank, world)
+        e0, e1 = y0 - top, y1 + bottom
+        assert np.array_equal(ext.numpy(), img[e0:e1]), "halo rows are not the neighbours' rows"
+        assert top == (min(radius, y0) if rank > 0 else 0)
+        # band + halo blurred with the oracle == the rows of the global blur
+        lut = host.gaussianKernel(radius)
+        ob = OracleBackend(0)
+        whole = img.copy()
+        ob.blur(whole, lut, radius, 0)
+        part = np.ascontiguousarray(ext.numpy().copy())
+        ob.blur(part, lut, radius, 0)
+        assert np.array_equal(part[top:top + (y1 - y0)], whole[y0:y1]), "banded blur differs from the global blur"
+        # shards of independent units cover the range exactly once
+        ranges = [multi.shard_range(1001, world, r) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == 1001 and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_banded_blur_halo_exchange(world, tmp_path):
+    import torch.multiprocessing as mp
+
+    port = 29500 + world + (os.getpid() % 500)
+    mp.spawn(_worker, args=(world, port, 150, 64, 12, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))

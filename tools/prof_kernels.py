@@ -1,0 +1,38 @@
+"""Runs each hot kernel a few times so that ncu can capture it (see profiles/README.md)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pixie_b200 import device as dev, host, synth  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+dev.init(0)
+if which in ("blend", "all"):
+    n = 8192
+    dst = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 1), (n // 512, 1, 1)))
+    src = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 2), (n // 512, 1, 1)))
+    mask = dev.DeviceImage(n, n, a8=True).upload(np.tile(synth.coverage_mask(512, n, 3), (n // 512, 1)))
+    for mode in (0, 16, 17, 2, 8):
+        for _ in range(3):
+            dev.blend_rect_masked(dst, src, mask, 0, 0, mode)
+    dev.sync()
+if which in ("blur", "all"):
+    n = int(os.environ.get("BLUR_N", "16384"))
+    img = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 4), (n // 512, 1, 1)))
+    for _ in range(3):
+        dev.blur(img, host.gaussianKernel(32), 32, 0)
+    dev.sync()
+if which in ("tiger", "all"):
+    sys.path.insert(0, ROOT)
+    from bench import tiger_arrays
+
+    arrays = tiger_arrays(4096)
+    img = dev.DeviceImage(4096, 4096)
+    cl = dev.CmdList(4096, 4096, 1, arrays)
+    for _ in range(3):
+        img.fill(0)
+        cl.run(img)
+    dev.sync()
