@@ -40,15 +40,57 @@ PXD uint4 ld16_stream(const void* p) {
 }
 
 // One thread = one 16-byte group of dst (4 px) x several rows.
+#ifndef PIXIE_BLEND_ROWS
+#define PIXIE_BLEND_ROWS 2   // rows in flight per thread (swept on B200: 2 rows x 4 CTAs/SM is best)
+#endif
+#ifndef PIXIE_BLEND_MINB
+#define PIXIE_BLEND_MINB 4
+#endif
 template <int MODE, int MASK>
-__global__ void __launch_bounds__(256) blend_rect_vec4(const RectArgs a) {
+__global__ void __launch_bounds__(256, PIXIE_BLEND_MINB) blend_rect_vec4(const RectArgs a) {
   const int g0 = a.xs >> 2;
   const int g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
   const int x = g << 2;
   if (x >= a.xe) return;
   const bool full_x = (x >= a.xs) && (x + 4 <= a.xe) && (x >= a.rx0) && (x + 4 <= a.rx1);
-  constexpr int ROWS = 4;
+  constexpr int ROWS = PIXIE_BLEND_ROWS;
   for (int yb = a.ys + blockIdx.y * ROWS; yb < a.ye; yb += gridDim.y * ROWS) {
+    // ---- fast path: this 4x4 block of pixels lies entirely inside the drawn rect: no predicates
+    if (full_x && a.src_aligned && yb >= a.ry0 && yb + ROWS <= a.ry1 && yb + ROWS <= a.ye) {
+      uint4 dv[ROWS], sv[ROWS];
+      uint32_t mw[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) {
+        const int y = yb + r;
+        const size_t sidx = (size_t)a.sw * (y - a.py) + (x - a.px);
+        if (MODE != OverwriteBlend) dv[r] = ld16(a.dst + (size_t)a.dw * y + x);
+        sv[r] = ld16_stream(a.src + sidx);
+        if (MASK == 1) {
+          const uint4 m = ld16_stream(reinterpret_cast<const px_t*>(a.mask) + sidx);
+          mw[r] = (m.x >> 24) | ((m.y >> 24) << 8) | ((m.z >> 24) << 16) | (m.w & 0xFF000000u);
+        } else if (MASK == 2) {
+          mw[r] = __ldg(reinterpret_cast<const uint32_t*>(a.mask + sidx));
+        } else {
+          mw[r] = 0xFFFFFFFFu;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) {
+        uint32_t* dp = reinterpret_cast<uint32_t*>(&dv[r]);
+        const uint32_t* sp = reinterpret_cast<const uint32_t*>(&sv[r]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          px_t sx = sp[k];
+          if (MASK != 0) {
+            const uint32_t m = (mw[r] >> (8 * k)) & 255u;
+            if (m != 255u) sx = mul_div255(sx, m);
+          }
+          dp[k] = rect_op<MODE>(MODE == OverwriteBlend ? 0u : dp[k], sx);
+        }
+        *reinterpret_cast<uint4*>(a.dst + (size_t)a.dw * (yb + r) + x) = dv[r];
+      }
+      continue;
+    }
     uint4 dv[ROWS], sv[ROWS];
     uint32_t mv[ROWS][4];
     bool rowin[ROWS];
@@ -65,25 +107,14 @@ __global__ void __launch_bounds__(256) blend_rect_vec4(const RectArgs a) {
       mv[r][0] = mv[r][1] = mv[r][2] = mv[r][3] = 255u;
       if (in_y) {
         const size_t sidx = (size_t)a.sw * (y - a.py) + (x - a.px);
-        if (full_x && a.src_aligned) {
-          sv[r] = ld16_stream(a.src + sidx);
-          if (MASK == 1) {
-            uint4 m = ld16_stream(reinterpret_cast<const px_t*>(a.mask) + sidx);
-            mv[r][0] = m.x >> 24; mv[r][1] = m.y >> 24; mv[r][2] = m.z >> 24; mv[r][3] = m.w >> 24;
-          } else if (MASK == 2) {
-            uint32_t m = __ldg(reinterpret_cast<const uint32_t*>(a.mask + sidx));
-            mv[r][0] = m & 255u; mv[r][1] = (m >> 8) & 255u; mv[r][2] = (m >> 16) & 255u; mv[r][3] = m >> 24;
-          }
-        } else {
-          uint32_t* sp = reinterpret_cast<uint32_t*>(&sv[r]);
+        uint32_t* sp = reinterpret_cast<uint32_t*>(&sv[r]);
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const int xx = x + k;
-            if (xx >= a.rx0 && xx < a.rx1 && xx >= a.xs && xx < a.xe) {
-              sp[k] = __ldg(a.src + sidx + k);
-              if (MASK == 1) mv[r][k] = __ldg(reinterpret_cast<const px_t*>(a.mask) + sidx + k) >> 24;
-              else if (MASK == 2) mv[r][k] = a.mask[sidx + k];
-            }
+        for (int k = 0; k < 4; k++) {
+          const int xx = x + k;
+          if (xx >= a.rx0 && xx < a.rx1 && xx >= a.xs && xx < a.xe) {
+            sp[k] = __ldg(a.src + sidx + k);
+            if (MASK == 1) mv[r][k] = __ldg(reinterpret_cast<const px_t*>(a.mask) + sidx + k) >> 24;
+            else if (MASK == 2) mv[r][k] = a.mask[sidx + k];
           }
         }
       }
@@ -102,9 +133,9 @@ __global__ void __launch_bounds__(256) blend_rect_vec4(const RectArgs a) {
         const bool in_rect = in_y && xx >= a.rx0 && xx < a.rx1;
         if (!in_region) continue;
         if (in_rect) {
-          px_t s = sp[k];
-          if (MASK != 0) s = mul_div255(s, mv[r][k]);
-          dp[k] = rect_op<MODE>(dp[k], s);
+          px_t sx = sp[k];
+          if (MASK != 0) sx = mul_div255(sx, mv[r][k]);
+          dp[k] = rect_op<MODE>(dp[k], sx);
         } else if (MODE == MaskBlend) {
           dp[k] = 0u;  // images.nim:501-520: MaskBlend clears everything the source does not cover
         }
@@ -145,7 +176,7 @@ static int launch_rect(const RectArgs& a) {
     dim3 grid((groups + 255) / 256, 1);
     int gy = target_blocks / (int)grid.x;
     if (gy < 1) gy = 1;
-    int max_gy = (rows + 3) / 4;
+    int max_gy = (rows + PIXIE_BLEND_ROWS - 1) / PIXIE_BLEND_ROWS;
     if (gy > max_gy) gy = max_gy;
     grid.y = gy;
     ProfScope ps(kProfBlend);

@@ -127,6 +127,176 @@ __global__ void __launch_bounds__(kWarps * 32) conv_tiled(const ConvArgs a, cons
   }
 }
 
+// ---- float32 variant -------------------------------------------------------------------------
+// Same tiling, but the tile is converted to float4 once when it is staged, the window lives in
+// registers as float4 and the MACs are Blackwell's packed FFMA2 (fma.rn.f32x2: two channels per
+// instruction).  Exact: every partial sum is an integer below 2^24 as long as 255 * sum(lut) < 2^24,
+// which the host checks (gaussianKernel LUTs sum to ~65 280); otherwise the u32 kernel above runs.
+constexpr int kMaxFloatRadius = 250; // 2 x (64 + 2r + 16) x 33 x 4 B of shared memory (double buffer)
+
+PXD unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+PXD unsigned long long pack2(float x, float y) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(x), "f"(y));
+  return d;
+}
+PXD void unpack2(unsigned long long v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+
+// Gaussian LUT as floats in constant memory: the tap index is warp-uniform, so the weight reaches
+// FFMA2 through the uniform datapath (UR operand) instead of a vector register + shared-memory load.
+constexpr int kConstLutTaps = 2 * 250 + 1 + 16;
+__constant__ float c_blur_lut[kConstLutTaps];
+
+PXD unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// two channels of a packed pixel -> two floats: PRMT builds 0x4B0000cc = 2^23 + c, one packed FADD2 removes the bias
+template <int LO>
+PXD unsigned long long px_pair_f32(px_t p) {
+  const uint32_t x = __byte_perm(p, 0x4B000000u, LO ? 0x7650 : 0x7652);
+  const uint32_t y = __byte_perm(p, 0x4B000000u, LO ? 0x7651 : 0x7653);
+  unsigned long long v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(x), "r"(y));
+  return fadd2(v, pack2(-8388608.0f, -8388608.0f));
+}
+PXD void cp_async4(uint32_t* smem_dst, const px_t* gsrc) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+PXD void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+PXD void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Persistent, double-buffered: each CTA walks tiles (8 warps x TT outputs along the blur axis x 32 lines);
+// the raw RGBX tile of the NEXT tile streams into shared memory with cp.async while the FFMA2
+// pipe works on the current one.
+template <bool VERTICAL, int TT>
+__global__ void __launch_bounds__(kWarps * 32, TT <= 8 ? 2 : 1) conv_tiled_f32(const ConvArgs a, const uint16_t* __restrict__ lut_g,
+                                                                int tilesA, int numTiles) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  constexpr int OUTA = TT * kWarps;
+  const int a_ext = OUTA + a.ntaps_pad + TT;
+  uint32_t* buf0 = smem;                                // 2 x a_ext * kPitch words
+  uint32_t* obuf = buf0 + 2 * a_ext * kPitch;           // OUTA * kPitch words (X pass output transpose)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int a_len = VERTICAL ? a.h : a.w;
+  const int l_len = VERTICAL ? a.w : a.sy1;
+
+  auto tile_origin = [&](int tile, int& a0, int& l0) {
+    const int tl = tile / tilesA, ta = tile - tl * tilesA;
+    a0 = ta * OUTA + (VERTICAL ? a.y0 : 0);
+    l0 = tl * 32 + (VERTICAL ? 0 : a.sy0);
+  };
+  auto prefetch = [&](int tile, uint32_t* buf) {
+    int a0, l0;
+    tile_origin(tile, a0, l0);
+    if (VERTICAL) {
+      const int x = l0 + lane;
+      for (int aa = warp; aa < a_ext; aa += kWarps) {
+        const int y = a0 - a.radius + aa;
+        uint32_t* d = buf + aa * kPitch + lane;
+        if (y >= 0 && y < a_len && x < l_len) cp_async4(d, a.src + (size_t)a.w * y + x);
+        else *d = a.oob;
+      }
+    } else {
+      for (int ln = warp; ln < 32; ln += kWarps) {
+        const int y = l0 + ln;
+        const px_t* row = a.src + (size_t)a.w * y;
+        for (int aa = lane; aa < a_ext; aa += 32) {
+          const int x = a0 - a.radius + aa;
+          uint32_t* d = buf + aa * kPitch + ln;
+          if (x >= 0 && x < a_len && y < l_len) cp_async4(d, row + x);
+          else *d = a.oob;
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  int tile = blockIdx.x;
+  if (tile < numTiles) prefetch(tile, buf0);
+  for (int it = 0; tile < numTiles; tile += gridDim.x, it++) {
+    uint32_t* cur = buf0 + (it & 1) * a_ext * kPitch;
+    const int nextTile = tile + gridDim.x;
+    if (nextTile < numTiles) {
+      prefetch(nextTile, buf0 + ((it + 1) & 1) * a_ext * kPitch);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    unsigned long long accRG[TT], accBA[TT], winRG[TT], winBA[TT];
+#pragma unroll
+    for (int t = 0; t < TT; t++) accRG[t] = accBA[t] = 0ull;
+    const uint32_t* col = cur + (warp * TT) * kPitch + lane;
+#pragma unroll
+    for (int j = 0; j < TT; j++) {
+      const px_t v = col[j * kPitch];
+      winRG[j] = px_pair_f32<1>(v);
+      winBA[j] = px_pair_f32<0>(v);
+    }
+    for (int i0 = 0; i0 < a.ntaps_pad; i0 += TT) {
+#pragma unroll
+      for (int u = 0; u < TT; u++) {
+        const float kw = c_blur_lut[i0 + u];
+        const unsigned long long kk = pack2(kw, kw);
+#pragma unroll
+        for (int t = 0; t < TT; t++) {
+          const int s = (u + t) % TT;
+          accRG[t] = ffma2(kk, winRG[s], accRG[t]);
+          accBA[t] = ffma2(kk, winBA[s], accBA[t]);
+        }
+        const px_t v = col[(i0 + u + TT) * kPitch];
+        winRG[u] = px_pair_f32<1>(v);
+        winBA[u] = px_pair_f32<0>(v);
+      }
+    }
+
+    int a0, l0;
+    tile_origin(tile, a0, l0);
+    px_t outv[TT];
+#pragma unroll
+    for (int t = 0; t < TT; t++) {
+      float r, g, b, al;
+      unpack2(accRG[t], r, g);
+      unpack2(accBA[t], b, al);
+      const uint32_t q[4] = {__float2uint_rz(r), __float2uint_rz(g), __float2uint_rz(b), __float2uint_rz(al)};
+      outv[t] = quantize4(q);
+    }
+    if (VERTICAL) {
+      const int x = l0 + lane;
+      if (x < a.w) {
+#pragma unroll
+        for (int t = 0; t < TT; t++) {
+          const int y = a0 + warp * TT + t;
+          if (y < a.y1) a.dst[(size_t)a.w * y + x] = outv[t];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < TT; t++) obuf[(warp * TT + t) * kPitch + lane] = outv[t];
+      __syncthreads();
+      for (int ln = warp; ln < 32; ln += kWarps) {
+        const int y = l0 + ln;
+        if (y < a.sy1) {
+          for (int aa = lane; aa < OUTA; aa += 32) {
+            const int x = a0 + aa;
+            if (x < a.w) a.dst[(size_t)a.w * y + x] = obuf[aa * kPitch + ln];
+          }
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with `cur` (and obuf) before the next prefetch overwrites it
+  }
+}
+
 // Any-radius fallback (radius > kMaxTiledRadius): one thread per output pixel.
 template <bool VERTICAL>
 __global__ void __launch_bounds__(256) conv_naive(const ConvArgs a, const uint16_t* __restrict__ lut) {
@@ -142,6 +312,44 @@ __global__ void __launch_bounds__(256) conv_naive(const ConvArgs a, const uint16
     acc[0] += k * pR(v); acc[1] += k * pG(v); acc[2] += k * pB(v); acc[3] += k * pA(v);
   }
   a.dst[(size_t)a.w * y + x] = quantize4(acc);
+}
+
+#ifndef PIXIE_BLUR_TT
+#define PIXIE_BLUR_TT 8
+#endif
+template <int TT>
+static int launch_f32(ConvArgs a, Image* im, void* tmp, const uint16_t* lut_d, int y0, int y1) {
+  Runtime& r = rt();
+  constexpr int OUTA = TT * kWarps;
+  const int ntaps = 2 * a.radius + 1;
+  a.ntaps_pad = (ntaps + TT - 1) / TT * TT;
+  const size_t smemF = (2 * (size_t)(OUTA + a.ntaps_pad + TT) * kPitch + (size_t)OUTA * kPitch) * 4;
+  static size_t configuredF = 0;
+  if (smemF > 48 * 1024 && configuredF < smemF) {
+    PX_CUDA(cudaFuncSetAttribute(conv_tiled_f32<false, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemF));
+    PX_CUDA(cudaFuncSetAttribute(conv_tiled_f32<true, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemF));
+    configuredF = smemF;
+  }
+  const int ctasPerSm = (TT <= 8 && smemF * 2 <= 200 * 1024) ? 2 : 1;
+  {  // X pass: image -> tmp, rows [sy0, sy1)
+    a.src = (const px_t*)im->data; a.dst = (px_t*)tmp;
+    const int tilesA = (im->w + OUTA - 1) / OUTA, tilesL = (a.sy1 - a.sy0 + 31) / 32;
+    const int numTiles = tilesA * tilesL;
+    const int grid = std::min(numTiles, r.num_sms * ctasPerSm);
+    ProfScope ps(kProfBlurX);
+    conv_tiled_f32<false, TT><<<grid, kWarps * 32, smemF, r.stream>>>(a, lut_d, tilesA, numTiles);
+  }
+  PX_LAUNCHED();
+  {  // Y pass: tmp -> image rows [y0, y1)
+    a.src = (const px_t*)tmp; a.dst = (px_t*)im->data;
+    const int tilesA = (y1 - y0 + OUTA - 1) / OUTA, tilesL = (im->w + 31) / 32;
+    const int numTiles = tilesA * tilesL;
+    const int grid = std::min(numTiles, r.num_sms * ctasPerSm);
+    ProfScope ps(kProfBlurY);
+    conv_tiled_f32<true, TT><<<grid, kWarps * 32, smemF, r.stream>>>(a, lut_d, tilesA, numTiles);
+  }
+  PX_LAUNCHED();
+  return 0;
 }
 
 static int blur_impl(Image* im, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1) {
@@ -169,7 +377,21 @@ static int blur_impl(Image* im, const uint16_t* lut_host, int radius, uint32_t o
   a.sy1 = std::min(im->h, y1 + radius);
   const size_t smem = ((size_t)a.ntaps_pad + (size_t)(kOutA + a.ntaps_pad + kT) * kPitch) * 4;
 
-  if (radius <= kMaxTiledRadius) {
+  unsigned long long lutSum = 0;
+  for (int i = 0; i < ntaps; i++) lutSum += lut_host[i];
+  const bool exactInFloat = lutSum * 255ull < (1ull << 24);
+  if (radius <= kMaxFloatRadius && exactInFloat) {
+    {  // float LUT (zero padded) -> constant memory, through the pinned staging buffer
+      void* pinf;
+      const int padded = (ntaps + 15) / 16 * 16;
+      if (int rc = staging_acquire((size_t)padded * 4, &pinf)) return rc;
+      float* lf = (float*)pinf;
+      for (int i = 0; i < padded; i++) lf[i] = i < ntaps ? (float)lut_host[i] : 0.0f;
+      PX_CUDA(cudaMemcpyToSymbolAsync(c_blur_lut, lf, (size_t)padded * 4, 0, cudaMemcpyHostToDevice, r.stream));
+      if (int rc = staging_release()) return rc;
+    }
+    if (int rc = launch_f32<PIXIE_BLUR_TT>(a, im, tmp, (const uint16_t*)lut_d, y0, y1)) return rc;
+  } else if (radius <= kMaxTiledRadius) {
     static size_t configured[2] = {0, 0};
     if (smem > 48 * 1024) {
       if (configured[0] < smem) {

@@ -15,7 +15,7 @@ import numpy as np
 from .common import PixieError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "pixie_cuda.so")
+LIB_PATH = os.environ.get("PIXIE_CUDA_LIB") or os.path.join(_HERE, "pixie_cuda.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pixie_cuda.h")
 
 _lib = None
