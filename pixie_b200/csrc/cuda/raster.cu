@@ -49,6 +49,7 @@ struct CmdList {
   float4* segs = nullptr;
   int16_t* wind = nullptr;
   FillHeader* fills = nullptr;
+  int2* rowRange = nullptr;
   int* partFill = nullptr;
   int* entryOff = nullptr;
   int* layerFillBegin = nullptr;
@@ -124,51 +125,66 @@ __global__ void __launch_bounds__(256) partition_kernel(const FillHeader* __rest
     const int outBase = entryOff[gp];
     int out = outBase;
     bool aa = false;
-    for (int base = 0; base < H.segCount; base += 32) {
-      const int i = base + lane;
-      bool touches = false;
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < H.segCount) {
-        s = segs[H.segBegin + i];
-        if (H.numPartitions == 1) {
-          touches = true;
-        } else {  // partitionRange (:1201-1213)
-          unsigned atP = __float2uint_rz(fmaxf(0.0f, s.y - startYf)) / ph;
-          unsigned toP = __float2uint_rz(fmaxf(0.0f, s.w - startYf)) / ph;
-          atP = min(atP, lastP);
-          toP = min(toP, lastP);
-          touches = (unsigned)p >= atP && (unsigned)p <= toP;
+    constexpr int kChunks = 4;  // 128 segments in flight per iteration: the scan is latency bound
+    for (int base0 = 0; base0 < H.segCount; base0 += 32 * kChunks) {
+      float4 sv[kChunks];
+      int wv[kChunks];
+#pragma unroll
+      for (int q = 0; q < kChunks; q++) {
+        const int i = base0 + q * 32 + lane;
+        sv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        wv[q] = 0;
+        if (i < H.segCount) {
+          sv[q] = segs[H.segBegin + i];
+          wv[q] = (int)wind[H.segBegin + i];
         }
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, touches);
-      if (touches) {
-        Entry e;  // initPartitionEntry (:1127-1135)
-        e.ax = s.x; e.ay = s.y; e.bx = s.z; e.by = s.w;
-        e.winding = (int)wind[H.segBegin + i];
-        e.pad = 0;
-        e.m = 0.0f;
-        e.b = 0.0f;
-        const float d = s.x - s.z;
-        if (d == 0.0f) {
-          e.b = s.x;
-        } else {
-          e.m = (s.y - s.w) / d;
-          e.b = s.y - e.m * s.x;
+#pragma unroll
+      for (int q = 0; q < kChunks; q++) {
+        const int i = base0 + q * 32 + lane;
+        const float4 s = sv[q];
+        bool touches = false;
+        if (i < H.segCount) {
+          if (H.numPartitions == 1) {
+            touches = true;
+          } else {  // partitionRange (:1201-1213)
+            unsigned atP = __float2uint_rz(fmaxf(0.0f, s.y - startYf)) / ph;
+            unsigned toP = __float2uint_rz(fmaxf(0.0f, s.w - startYf)) / ph;
+            atP = min(atP, lastP);
+            toP = min(toP, lastP);
+            touches = (unsigned)p >= atP && (unsigned)p <= toP;
+          }
         }
-        // requiresAntiAliasing (:1149-1160) — on the unclipped segment
-        if (s.x != s.z || (s.x - truncf(s.x) != 0.0f) || (s.y - truncf(s.y) != 0.0f) || (s.w - truncf(s.w) != 0.0f))
-          aa = true;
-        // clip entries that span the whole band (:1242-1248)
-        if (e.ay <= topf && e.by >= botf) {
-          float atx = 0.0f, aty = 0.0f;
-          seg_line(e.ax, e.ay, e.bx, e.by, topf, atx, aty);
-          e.ax = atx; e.ay = aty;
-          seg_line(e.ax, e.ay, e.bx, e.by, botf, atx, aty);
-          e.bx = atx; e.by = aty;
+        const unsigned bal = __ballot_sync(0xffffffffu, touches);
+        if (touches) {
+          Entry e;  // initPartitionEntry (:1127-1135)
+          e.ax = s.x; e.ay = s.y; e.bx = s.z; e.by = s.w;
+          e.winding = wv[q];
+          e.pad = 0;
+          e.m = 0.0f;
+          e.b = 0.0f;
+          const float d = s.x - s.z;
+          if (d == 0.0f) {
+            e.b = s.x;
+          } else {
+            e.m = (s.y - s.w) / d;
+            e.b = s.y - e.m * s.x;
+          }
+          // requiresAntiAliasing (:1149-1160) — on the unclipped segment
+          if (s.x != s.z || (s.x - truncf(s.x) != 0.0f) || (s.y - truncf(s.y) != 0.0f) || (s.w - truncf(s.w) != 0.0f))
+            aa = true;
+          // clip entries that span the whole band (:1242-1248)
+          if (e.ay <= topf && e.by >= botf) {
+            float atx = 0.0f, aty = 0.0f;
+            seg_line(e.ax, e.ay, e.bx, e.by, topf, atx, aty);
+            e.ax = atx; e.ay = aty;
+            seg_line(e.ax, e.ay, e.bx, e.by, botf, atx, aty);
+            e.bx = atx; e.by = aty;
+          }
+          entries[out + __popc(bal & ((1u << lane) - 1u))] = e;
         }
-        entries[out + __popc(bal & ((1u << lane) - 1u))] = e;
+        out += __popc(bal);
       }
-      out += __popc(bal);
     }
     const bool aaAny = __any_sync(0xffffffffu, aa);
     __syncwarp();
@@ -198,6 +214,7 @@ struct RasterArgs {
   px_t* canvas;
   int w, h, layers;
   const FillHeader* fills;
+  const int2* rowRange;        // rows [x, y) of the canvas each fill has to visit (empty when inactive)
   const int* layerFillBegin;
   const int* entryOff;
   const Entry* entries;
@@ -672,9 +689,18 @@ __device__ __noinline__ void fill_row(WarpCtx& c, const FillHeader& H, const Ras
             if (px >= covX0 && px < covX1) c.cov[idx] = (uint8_t)(c.cov[idx] + (uint8_t)fx_integer(rightCover * sampleCoverage));
           }
         }
-        const int fillEnd = fx_integer(at);
-        for (int j = fillStart + lane; j < fillEnd; j += 32) {
-          if (j >= covX0 && j < covX1) c.cov[j - covBase] = (uint8_t)(c.cov[j - covBase] + sampleCoverage);
+        // interior of the span: +sampleCoverage per pixel.  Spans of one sample line are disjoint, so
+        // a coverage byte never exceeds 255 and whole words can be added without carries.
+        const int i0 = max(fillStart, covX0) - covBase, i1 = min(fx_integer(at), covX1) - covBase;
+        if (i1 - i0 >= 96) {
+          const int a0 = (i0 + 3) & ~3, a1 = i1 & ~3;
+          for (int j = i0 + lane; j < a0; j += 32) c.cov[j] = (uint8_t)(c.cov[j] + sampleCoverage);
+          uint32_t* cw = reinterpret_cast<uint32_t*>(c.cov);
+          const uint32_t add4 = 0x01010101u * (uint32_t)sampleCoverage;
+          for (int w = (a0 >> 2) + lane; w < (a1 >> 2); w += 32) cw[w] += add4;
+          for (int j = a1 + lane; j < i1; j += 32) c.cov[j] = (uint8_t)(c.cov[j] + sampleCoverage);
+        } else {
+          for (int j = i0 + lane; j < i1; j += 32) c.cov[j] = (uint8_t)(c.cov[j] + sampleCoverage);
         }
         __syncwarp();
       }
@@ -731,29 +757,38 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
     c.vec_ok = (A.w & 3) == 0 && (reinterpret_cast<uintptr_t>(A.canvas) & 15) == 0;
     c.covered = 0;
     const int f0 = A.layerFillBegin[layer], f1 = A.layerFillBegin[layer + 1];
-    for (int f = f0; f < f1; f++) {
-      const FillHeader H = A.fills[f];
-      if (!H.active) continue;
-      if (H.mode != MaskBlend && (y < H.startY || y >= H.pathHeight)) continue;
-      // scratch: shared memory when the band's entries fit, else the global spill area
-      uint32_t* scr = sscr;
-      int cap = A.smemCap;
-      if (y >= H.startY && y < H.pathHeight) {
-        int p = (y - H.startY) / H.partitionHeight;
-        if (p > H.numPartitions - 1) p = H.numPartitions - 1;
-        const int gp = H.partBase + p;
-        const int eCnt = A.entryOff[gp + 1] - A.entryOff[gp];
-        if (eCnt > A.smemCap) {
-          scr = gscr;
-          cap = A.scratchCap;
-        }
+    for (int fb = f0; fb < f1; fb += 32) {  // 32 fills per step: which of them touch this row?
+      const int fl = fb + lane;
+      bool act = false;
+      if (fl < f1) {
+        const int2 rr = A.rowRange[fl];
+        act = y >= rr.x && y < rr.y;
       }
-      c.mode = H.mode;
-      if (H.mode == NormalBlend) fill_row<NormalBlend>(c, H, A, scr, cap);
-      else if (H.mode == OverwriteBlend) fill_row<OverwriteBlend>(c, H, A, scr, cap);
-      else if (H.mode == MaskBlend) fill_row<MaskBlend>(c, H, A, scr, cap);
-      else fill_row<GenericMode>(c, H, A, scr, cap);
-      __syncwarp();
+      unsigned todo = __ballot_sync(0xffffffffu, act);
+      while (todo) {  // ascending order = the reference's sequential order of fills
+        const int f = fb + __ffs(todo) - 1;
+        todo &= todo - 1;
+        const FillHeader H = A.fills[f];
+        // scratch: shared memory when the band's entries fit, else the global spill area
+        uint32_t* scr = sscr;
+        int cap = A.smemCap;
+        if (y >= H.startY && y < H.pathHeight) {
+          int p = (y - H.startY) / H.partitionHeight;
+          if (p > H.numPartitions - 1) p = H.numPartitions - 1;
+          const int gp = H.partBase + p;
+          const int eCnt = A.entryOff[gp + 1] - A.entryOff[gp];
+          if (eCnt > A.smemCap) {
+            scr = gscr;
+            cap = A.scratchCap;
+          }
+        }
+        c.mode = H.mode;
+        if (H.mode == NormalBlend) fill_row<NormalBlend>(c, H, A, scr, cap);
+        else if (H.mode == OverwriteBlend) fill_row<OverwriteBlend>(c, H, A, scr, cap);
+        else if (H.mode == MaskBlend) fill_row<MaskBlend>(c, H, A, scr, cap);
+        else fill_row<GenericMode>(c, H, A, scr, cap);
+        __syncwarp();
+      }
     }
     covered += c.covered;
   }
@@ -902,8 +937,11 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   if (perWarp * L.warpsPerBlock > 200 * 1024) return fail_pixie("canvas too wide for the shared-memory coverage row");
   L.smemBytes = perWarp * L.warpsPerBlock;
   const long long totalRows = (long long)layers * h;
-  int blocksPerSm = (int)std::min<size_t>(8, (200 * 1024) / std::max<size_t>(L.smemBytes, 1));
-  blocksPerSm = std::max(1, std::min(blocksPerSm, 64 / L.warpsPerBlock));
+  if (L.smemBytes > 48 * 1024)
+    PX_CUDA(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes));
+  int blocksPerSm = 1;  // resident CTAs per SM for this shared-memory footprint: one wave, rows by ticket
+  PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, raster_kernel, L.warpsPerBlock * 32, L.smemBytes));
+  blocksPerSm = std::max(1, blocksPerSm);
   long long wantBlocks = (totalRows + L.warpsPerBlock - 1) / L.warpsPerBlock;
   L.rasterBlocks = (int)std::min<long long>(wantBlocks, (long long)r.num_sms * blocksPerSm);
   L.rasterBlocks = std::max(L.rasterBlocks, 1);
@@ -916,6 +954,7 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   const size_t oSegs = off;      off = al(off + (size_t)numSegs * 16);
   const size_t oWind = off;      off = al(off + (size_t)numSegs * 2);
   const size_t oFills = off;     off = al(off + fills.size() * sizeof(FillHeader));
+  const size_t oRowRange = off;  off = al(off + fills.size() * sizeof(int2));
   const size_t oPartFill = off;  off = al(off + partFill.size() * 4);
   const size_t oEntryOff = off;  off = al(off + entryOff.size() * 4);
   const size_t oLayer = off;     off = al(off + layerBegin.size() * 4);
@@ -945,7 +984,16 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
     memcpy(stage + oSegs, seg, (size_t)numSegs * 16);
     memcpy(stage + oWind, wind, (size_t)numSegs * 2);
   }
-  if (!fills.empty()) memcpy(stage + oFills, fills.data(), fills.size() * sizeof(FillHeader));
+  if (!fills.empty()) {
+    memcpy(stage + oFills, fills.data(), fills.size() * sizeof(FillHeader));
+    int2* rr = reinterpret_cast<int2*>(stage + oRowRange);
+    for (size_t k = 0; k < fills.size(); k++) {
+      const FillHeader& F = fills[k];
+      if (!F.active) rr[k] = make_int2(0, 0);
+      else if (F.mode == MaskBlend) rr[k] = make_int2(0, h);  // clears every row it does not cover
+      else rr[k] = make_int2(F.startY, F.pathHeight);
+    }
+  }
   if (!partFill.empty()) memcpy(stage + oPartFill, partFill.data(), partFill.size() * 4);
   memcpy(stage + oEntryOff, entryOff.data(), entryOff.size() * 4);
   memcpy(stage + oLayer, layerBegin.data(), layerBegin.size() * 4);
@@ -958,6 +1006,7 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   L.segs = (float4*)(L.block + oSegs);
   L.wind = (int16_t*)(L.block + oWind);
   L.fills = (FillHeader*)(L.block + oFills);
+  L.rowRange = (int2*)(L.block + oRowRange);
   L.partFill = (int*)(L.block + oPartFill);
   L.entryOff = (int*)(L.block + oEntryOff);
   L.layerFillBegin = (int*)(L.block + oLayer);
@@ -991,7 +1040,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px) {
   RasterArgs A;
   A.canvas = (px_t*)im->data;
   A.w = L.w; A.h = L.h; A.layers = L.layers;
-  A.fills = L.fills; A.layerFillBegin = L.layerFillBegin; A.entryOff = L.entryOff; A.entries = L.entries;
+  A.fills = L.fills; A.rowRange = L.rowRange; A.layerFillBegin = L.layerFillBegin; A.entryOff = L.entryOff; A.entries = L.entries;
   A.flags = L.flags; A.gscratch = L.scratch; A.counters = L.counters;
   A.smemCap = L.smemCap; A.scratchCap = L.maxEntries; A.covBytes = L.covBytes;
   A.countCovered = covered_px ? 1 : 0;
