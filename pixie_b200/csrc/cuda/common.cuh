@@ -34,8 +34,8 @@ struct Runtime {
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // scratch buffers that grow on demand (stream-ordered reuse)
-  void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
-  size_t scratch_bytes[4] = {0, 0, 0, 0};
+  void* scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   cudaEvent_t staging_done = nullptr;  // recorded after the H2D copy that reads `pinned`

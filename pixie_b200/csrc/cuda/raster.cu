@@ -16,7 +16,12 @@
 //
 // All geometry is IEEE float32 with one rounding per operation (compiled with -fmad=false,
 // -prec-div=true) so that every mode decision equals the CPU reference's.
+#include <xmmintrin.h>
+
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -50,7 +55,6 @@ struct CmdList {
   int16_t* wind = nullptr;
   FillHeader* fills = nullptr;
   int2* rowRange = nullptr;
-  int* partFill = nullptr;
   int* entryOff = nullptr;
   int* layerFillBegin = nullptr;
   Entry* entries = nullptr;
@@ -59,7 +63,8 @@ struct CmdList {
   unsigned long long* counters = nullptr;  // [0] row ticket, [1] covered px
   int rasterBlocks = 0, warpsPerBlock = 0, scratchWords = 0, covBytes = 0, smemCap = 0;
   size_t smemBytes = 0, h2dBytes = 0;
-  uint8_t* block = nullptr;  // single device allocation (or a slice of the library arena) holding all of the above
+  uint8_t* block = nullptr;   // block A: host-written inputs + device-made offsets/flags/counters
+  uint8_t* blockB = nullptr;  // block B: band entries + spill scratch (sized after the device-side count)
   bool owned = false;
 };
 
@@ -106,8 +111,81 @@ PXD bool intersects_inside(const Entry& a, const Entry& b) {  // internal.nim:36
 // ---------------------------------------------------------------------------------------------
 // K1: partitionSegments
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) partition_kernel(const FillHeader* __restrict__ fills,
-                                                        const int* __restrict__ partFill,
+// last fill whose field (segBegin / partBase, non-decreasing over fills) is <= v
+template <bool BY_PART>
+PXD int find_fill(const FillHeader* __restrict__ fills, int numFills, int v) {
+  int lo = 0, hi = numFills;  // first index with key > v
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int key = BY_PART ? fills[mid].partBase : fills[mid].segBegin;
+    if (key <= v) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo - 1;
+}
+
+// K1a: entries per band (one thread per segment; order is irrelevant for counting)
+__global__ void __launch_bounds__(256) count_kernel(const FillHeader* __restrict__ fills, int numFills,
+                                                    const float4* __restrict__ segs, int numSegs, int* __restrict__ cnt) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < numSegs; i += gridDim.x * blockDim.x) {
+    int f = find_fill<false>(fills, numFills, i);
+    while (f > 0 && fills[f].segCount == 0) f--;  // empty fills share their segBegin with the next one
+    const FillHeader H = fills[f];
+    if (!H.active || H.numPartitions <= 0 || i >= H.segBegin + H.segCount) continue;
+    if (H.numPartitions == 1) {
+      atomicAdd(&cnt[H.partBase], 1);
+      continue;
+    }
+    const float4 s = segs[i];
+    const float startYf = (float)(unsigned)H.startY;
+    const unsigned ph = (unsigned)H.partitionHeight, lastP = (unsigned)(H.numPartitions - 1);
+    unsigned atP = __float2uint_rz(fmaxf(0.0f, s.y - startYf)) / ph;
+    unsigned toP = __float2uint_rz(fmaxf(0.0f, s.w - startYf)) / ph;
+    atP = min(atP, lastP);
+    toP = min(toP, lastP);
+    for (unsigned p = atP; p <= toP; p++) atomicAdd(&cnt[H.partBase + (int)p], 1);
+  }
+}
+
+// K1b: exclusive scan of the band counts in place (cnt[n] receives the total); meta = {total, max}
+__global__ void __launch_bounds__(1024) scan_kernel(int* __restrict__ cnt, int n, unsigned long long* __restrict__ meta) {
+  __shared__ long long sums[1024];
+  __shared__ int maxs[1024];
+  const int tid = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int b = min(tid * per, n), e = min(b + per, n);
+  long long sum = 0;
+  int mx = 0;
+  for (int i = b; i < e; i++) {
+    const int c = cnt[i];
+    sum += c;
+    mx = max(mx, c);
+  }
+  sums[tid] = sum;
+  maxs[tid] = mx;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan of the per-thread sums
+    const long long v = tid >= o ? sums[tid - o] : 0;
+    const int m = tid >= o ? maxs[tid - o] : 0;
+    __syncthreads();
+    sums[tid] += v;
+    maxs[tid] = max(maxs[tid], m);
+    __syncthreads();
+  }
+  long long run = sums[tid] - sum;
+  for (int i = b; i < e; i++) {
+    const int c = cnt[i];
+    cnt[i] = (int)run;
+    run += c;
+  }
+  if (tid == 1023) {
+    cnt[n] = (int)sums[1023];
+    meta[0] = (unsigned long long)sums[1023];
+    meta[1] = (unsigned long long)maxs[1023];
+  }
+}
+
+__global__ void __launch_bounds__(256) partition_kernel(const FillHeader* __restrict__ fills, int numFills,
                                                         const int* __restrict__ entryOff,
                                                         const float4* __restrict__ segs,
                                                         const int16_t* __restrict__ wind, Entry* __restrict__ entries,
@@ -115,7 +193,7 @@ __global__ void __launch_bounds__(256) partition_kernel(const FillHeader* __rest
   const int lane = threadIdx.x & 31;
   const int warpsTotal = (gridDim.x * blockDim.x) >> 5;
   for (int gp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gp < numParts; gp += warpsTotal) {
-    const FillHeader H = fills[partFill[gp]];
+    const FillHeader H = fills[find_fill<true>(fills, numFills, gp)];
     const int p = gp - H.partBase;
     const int top = H.startY + p * H.partitionHeight;
     const int bottom = (p == H.numPartitions - 1) ? H.pathHeight : top + H.partitionHeight;
@@ -814,22 +892,28 @@ static inline uint32_t f2u_host(float f) {  // matches __float2uint_rz (saturati
 
 static void free_list(CmdList& L) {
   if (L.owned && L.block) cudaFree(L.block);
-  L.block = nullptr;
+  if (L.owned && L.blockB) cudaFree(L.blockB);
+  L.block = L.blockB = nullptr;
 }
+
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static const bool g_trace = getenv("PIXIE_CUDA_TRACE") != nullptr;
 
 static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numFills, const int32_t* layerOf,
                       const float* seg, const int16_t* wind, const int32_t* segOff, const uint32_t* rgbx,
                       const uint8_t* rule, const uint8_t* mode) {
   Runtime& r = rt();
+  const double t0 = now_ms();
   if (w <= 0 || h <= 0 || layers <= 0) return fail_pixie("Image width and height must be > 0");
   if (numFills < 0) return fail_pixie("negative fill count");
   L.w = w; L.h = h; L.layers = layers; L.numFills = numFills;
   std::vector<FillHeader> fills(numFills);
-  std::vector<int> partFill, entryOff, layerBegin(layers + 1, 0);
-  entryOff.push_back(0);
-  int64_t entriesTotal = 0;
-  int maxEntries = 2;
+  std::vector<int> layerBegin(layers + 1, 0);
+  int64_t numPartsTotal = 0;
   int prevLayer = 0;
+  double tBounds = 0;
   for (int k = 0; k < numFills; k++) {
     const int layer = layerOf ? layerOf[k] : 0;
     if (layer < prevLayer || layer >= layers || layer < 0) return fail_pixie("layer_of_fill must be non-decreasing and < layers");
@@ -844,18 +928,31 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
     H.segBegin = s0; H.segCount = n; H.rgbx = rgbx[k]; H.rule = rule[k]; H.mode = mode[k];
     if (n == 0) {  // empty path: nothing is drawn (the reference's tiger has one, "M-65.4,9z")
       H.active = 0;
-      H.partBase = (int)partFill.size();
+      H.partBase = (int)numPartsTotal;
       continue;
     }
     // computeBounds (:1098-1117) + snapToPixels (common.nim:92-101) + clip to the image (:1605-1613)
     float xMin = INFINITY, xMax = -INFINITY, yMin = INFINITY, yMax = -INFINITY;
-    for (int i = s0; i < s1; i++) {
-      const float ax = seg[4 * (size_t)i], ay = seg[4 * (size_t)i + 1], bx = seg[4 * (size_t)i + 2], by = seg[4 * (size_t)i + 3];
-      xMin = fminf(xMin, fminf(ax, bx));
-      xMax = fmaxf(xMax, fmaxf(ax, bx));
-      yMin = fminf(yMin, ay);
-      yMax = fmaxf(yMax, by);
+    const double tb0 = g_trace ? now_ms() : 0;
+    // Nim's min/max (`if x <= y: x else: y`) == MINPS/MAXPS(acc, v) including their NaN behaviour
+    // (second operand when unordered); one 4-lane min + max per segment {at.x, at.y, to.x, to.y}.
+    {
+      const float* sp = seg + 4 * (size_t)s0;
+      __m128 vmin = _mm_set1_ps(INFINITY), vmax = _mm_set1_ps(-INFINITY);
+      for (int i = 0; i < n; i++, sp += 4) {
+        const __m128 v = _mm_loadu_ps(sp);
+        vmin = _mm_min_ps(vmin, v);
+        vmax = _mm_max_ps(vmax, v);
+      }
+      float mn[4], mx[4];
+      _mm_storeu_ps(mn, vmin);
+      _mm_storeu_ps(mx, vmax);
+      xMin = mn[0] <= mn[2] ? mn[0] : mn[2];
+      xMax = mx[2] <= mx[0] ? mx[0] : mx[2];
+      yMin = mn[1];  // at.y < to.y for every segment
+      yMax = mx[3];
     }
+    if (g_trace) tBounds += now_ms() - tb0;
     float bx_ = 0, by_ = 0, bw_ = 0, bh_ = 0;
     if (!(xMin != xMin || xMax != xMax || yMin != yMin || yMax != yMax)) {
       bx_ = xMin; by_ = yMin; bw_ = xMax - xMin; bh_ = yMax - yMin;
@@ -868,14 +965,14 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
     const int64_t pathHeight = std::min<int64_t>(h, f2i_host(sy + sh));
     if (pathWidth == 0) {  // :1615-1616
       H.active = 0;
-      H.partBase = (int)partFill.size();
+      H.partBase = (int)numPartsTotal;
       continue;
     }
     if (pathWidth < 0) return fail_pixie("Path int overflow detected");  // :1618-1619
     H.active = 1;
     H.startX = (int)startX;
     H.pathWidth = (int)pathWidth;
-    H.partBase = (int)partFill.size();
+    H.partBase = (int)numPartsTotal;
     if (pathHeight <= startY) {  // no scanline is touched; MaskBlend still clears the canvas
       H.startY = (int)std::min<int64_t>(startY, h);
       H.pathHeight = H.startY;
@@ -892,40 +989,15 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
     const uint32_t partitionHeight = (uint32_t)height / numPartitions;
     H.numPartitions = (int)numPartitions;
     H.partitionHeight = (int)partitionHeight;
-    std::vector<int> diff(numPartitions + 1, 0);
-    if (numPartitions == 1) {
-      diff[0] = n;
-      diff[1] -= n;
-    } else {
-      const float startYf = (float)(uint32_t)startY;
-      for (int i = s0; i < s1; i++) {
-        uint32_t a = f2u_host(fmaxf(0.0f, seg[4 * (size_t)i + 1] - startYf)) / partitionHeight;
-        uint32_t b = f2u_host(fmaxf(0.0f, seg[4 * (size_t)i + 3] - startYf)) / partitionHeight;
-        a = std::min(a, numPartitions - 1);
-        b = std::min(b, numPartitions - 1);
-        if (b >= a) {
-          diff[a]++;
-          diff[b + 1]--;
-        }
-      }
-    }
-    int run = 0;
-    for (uint32_t p = 0; p < numPartitions; p++) {
-      run += diff[p];
-      partFill.push_back(k);
-      entriesTotal += run;
-      if (entriesTotal > 0x7fffffff) return fail_pixie("command list too large");
-      entryOff.push_back((int)entriesTotal);
-      maxEntries = std::max(maxEntries, run);
-    }
+    numPartsTotal += numPartitions;
+    if (numPartsTotal > 0x3fffffff) return fail_pixie("command list too large");
   }
   for (int l = 1; l <= layers; l++) layerBegin[l] = std::max(layerBegin[l], layerBegin[l - 1]);
 
+  const double t1 = now_ms();
   const int64_t numSegs = numFills ? segOff[numFills] : 0;
   L.numSegs = numSegs;
-  L.numParts = (int64_t)partFill.size();
-  L.numEntries = entriesTotal;
-  L.maxEntries = maxEntries;
+  L.numParts = numPartsTotal;
 
   // raster launch geometry: persistent warps, one (layer, row) ticket at a time
   L.covBytes = ((w + 7) & ~3) + 4;             // coverage row, word aligned, with the covBase slack
@@ -945,37 +1017,35 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   long long wantBlocks = (totalRows + L.warpsPerBlock - 1) / L.warpsPerBlock;
   L.rasterBlocks = (int)std::min<long long>(wantBlocks, (long long)r.num_sms * blocksPerSm);
   L.rasterBlocks = std::max(L.rasterBlocks, 1);
-  L.scratchWords = maxEntries > L.smemCap ? maxEntries * kScratchArrays : 0;
 
-  // One device block for the whole list.  The host-written part (segments, windings, headers,
-  // offsets) is contiguous so that it moves with a single H2D copy from a staging buffer.
+  // Device block A.  The host-written part (segments, windings, headers, row ranges, layer table)
+  // is contiguous so that it moves with a single H2D copy from a staging buffer; band counts,
+  // entry offsets, flags and counters are produced on the device.
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t P = (size_t)numPartsTotal;
   size_t off = 0;
   const size_t oSegs = off;      off = al(off + (size_t)numSegs * 16);
   const size_t oWind = off;      off = al(off + (size_t)numSegs * 2);
   const size_t oFills = off;     off = al(off + fills.size() * sizeof(FillHeader));
   const size_t oRowRange = off;  off = al(off + fills.size() * sizeof(int2));
-  const size_t oPartFill = off;  off = al(off + partFill.size() * 4);
-  const size_t oEntryOff = off;  off = al(off + entryOff.size() * 4);
   const size_t oLayer = off;     off = al(off + layerBegin.size() * 4);
   const size_t h2dBytes = off;
-  const size_t oEntries = off;   off = al(off + std::max<size_t>(1, (size_t)entriesTotal) * sizeof(Entry));
-  const size_t oFlags = off;     off = al(off + std::max<size_t>(1, partFill.size()));
-  const size_t oCounters = off;  off = al(off + 16);
-  const size_t oScratch = off;   off = al(off + (size_t)L.rasterBlocks * L.warpsPerBlock * L.scratchWords * 4);
-  const size_t total = off;
+  const size_t oEntryOff = off;  off = al(off + (P + 1) * 4);   // band counts, scanned in place to offsets
+  const size_t oFlags = off;     off = al(off + std::max<size_t>(1, P));
+  const size_t oCounters = off;  off = al(off + 32);            // [0] row ticket, [1] covered px, [2] entries, [3] max
+  const size_t totalA = off;
 
   uint8_t* stage = nullptr;
   std::vector<uint8_t> pageable;
   if (arena) {  // per-call lists: library-owned growing arena + pinned staging, no malloc/free per call
     void *blk, *pin;
-    if (int rc = get_scratch(2, total, &blk)) return rc;
+    if (int rc = get_scratch(2, totalA, &blk)) return rc;
     if (int rc = staging_acquire(h2dBytes, &pin)) return rc;
     L.block = (uint8_t*)blk;
     L.owned = false;
     stage = (uint8_t*)pin;
   } else {
-    PX_CUDA(cudaMalloc(&L.block, total));
+    PX_CUDA(cudaMalloc(&L.block, totalA));
     L.owned = true;
     pageable.resize(h2dBytes);
     stage = pageable.data();
@@ -994,27 +1064,55 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
       else rr[k] = make_int2(F.startY, F.pathHeight);
     }
   }
-  if (!partFill.empty()) memcpy(stage + oPartFill, partFill.data(), partFill.size() * 4);
-  memcpy(stage + oEntryOff, entryOff.data(), entryOff.size() * 4);
   memcpy(stage + oLayer, layerBegin.data(), layerBegin.size() * 4);
   PX_CUDA(cudaMemcpyAsync(L.block, stage, h2dBytes, cudaMemcpyHostToDevice, r.stream));
   if (arena) {
     if (int rc = staging_release()) return rc;
-  } else {
-    PX_CUDA(cudaStreamSynchronize(r.stream));  // the pageable staging vector dies with this scope
   }
   L.segs = (float4*)(L.block + oSegs);
   L.wind = (int16_t*)(L.block + oWind);
   L.fills = (FillHeader*)(L.block + oFills);
   L.rowRange = (int2*)(L.block + oRowRange);
-  L.partFill = (int*)(L.block + oPartFill);
-  L.entryOff = (int*)(L.block + oEntryOff);
   L.layerFillBegin = (int*)(L.block + oLayer);
-  L.entries = (Entry*)(L.block + oEntries);
+  L.entryOff = (int*)(L.block + oEntryOff);
   L.flags = L.block + oFlags;
   L.counters = (unsigned long long*)(L.block + oCounters);
-  L.scratch = L.scratchWords ? (uint32_t*)(L.block + oScratch) : nullptr;
   L.h2dBytes = h2dBytes;
+
+  // K1a/K1b on the device: how many entries each band gets (partitionRange :1201-1213), exclusive
+  // scan to entry offsets, total and maximum -> 16 bytes back to the host to size block B.
+  long long meta[2] = {0, 2};
+  if (P > 0) {
+    PX_CUDA(cudaMemsetAsync(L.entryOff, 0, (P + 1) * 4, r.stream));
+    const int cblocks = (int)std::min<int64_t>((numSegs + 255) / 256, (int64_t)r.num_sms * 8);
+    count_kernel<<<std::max(cblocks, 1), 256, 0, r.stream>>>(L.fills, numFills, L.segs, (int)numSegs, L.entryOff);
+    PX_LAUNCHED();
+    scan_kernel<<<1, 1024, 0, r.stream>>>(L.entryOff, (int)P, L.counters + 2);
+    PX_LAUNCHED();
+    PX_CUDA(cudaMemcpyAsync(meta, L.counters + 2, 16, cudaMemcpyDeviceToHost, r.stream));
+  }
+  PX_CUDA(cudaStreamSynchronize(r.stream));  // also retires the pageable staging vector of owned lists
+  if (meta[0] > 0x7fffffffll) return fail_pixie("command list too large");
+  L.numEntries = meta[0];
+  L.maxEntries = (int)std::max<long long>(2, meta[1]);
+  L.scratchWords = L.maxEntries > L.smemCap ? L.maxEntries * kScratchArrays : 0;
+
+  // Device block B: band entries + the per-warp spill scratch for bands with more entries than fit in smem.
+  const size_t entriesBytes = al(std::max<size_t>(1, (size_t)L.numEntries) * sizeof(Entry));
+  const size_t totalB = entriesBytes + al((size_t)L.rasterBlocks * L.warpsPerBlock * L.scratchWords * 4);
+  if (arena) {
+    void* blk;
+    if (int rc = get_scratch(4, totalB, &blk)) return rc;
+    L.blockB = (uint8_t*)blk;
+  } else {
+    PX_CUDA(cudaMalloc(&L.blockB, totalB));
+  }
+  L.entries = (Entry*)L.blockB;
+  L.scratch = L.scratchWords ? (uint32_t*)(L.blockB + entriesBytes) : nullptr;
+  if (g_trace)
+    fprintf(stderr, "[pixie_cuda] build_list: host plan %.3f ms (bounds %.3f), stage + device count/scan + readback %.3f ms "
+            "(%zu B staged, blocks %zu + %zu B, %lld entries, max %d per band)\n",
+            t1 - t0, tBounds, now_ms() - t1, h2dBytes, totalA, totalB, (long long)L.numEntries, L.maxEntries);
   return 0;
 }
 
@@ -1026,13 +1124,13 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px) {
     if (covered_px) *covered_px = 0;
     return 0;
   }
-  PX_CUDA(cudaMemsetAsync(L.counters, 0, 16, r.stream));
+  PX_CUDA(cudaMemsetAsync(L.counters, 0, 16, r.stream));  // row ticket + covered px
   if (L.numParts > 0) {
     const int warps = (int)std::min<int64_t>(L.numParts, (int64_t)r.num_sms * 32);
     const int blocks = (warps + 7) / 8;
     {
       ProfScope ps(kProfPartition);
-      partition_kernel<<<blocks, 256, 0, r.stream>>>(L.fills, L.partFill, L.entryOff, L.segs, L.wind, L.entries,
+      partition_kernel<<<blocks, 256, 0, r.stream>>>(L.fills, L.numFills, L.entryOff, L.segs, L.wind, L.entries,
                                                      L.flags, (int)L.numParts);
     }
     PX_LAUNCHED();
