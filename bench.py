@@ -12,8 +12,8 @@ scaling "weak".
 metric  = Mpixels/s filled+blended: sum over fills of pixels touched with non-zero coverage
           (35.8 Mpx per tiger at 4096^2, counted by the kernel and equal to the oracle's count) / time.
 value   = inputs (segments + fill headers) already resident in HBM, CUDA-event timed.
-e2e     = through the C-ABI entry point with HOST buffers: pixie_cuda_fill_batch(host segments) +
-          pixie_cuda_image_download_async to pinned memory, wall clock, H2D/D2H inside the timed region.
+e2e     = through the C-ABI entry point with HOST buffers: pixie_cuda_render_batch_host(host segments in,
+          host pixels out, pinned), wall clock, H2D/D2H inside the timed region.
 L2 is flushed between timed iterations (256 MiB device write); canvas = 64 MiB < 126 MB L2.
 
 `--impl reference` times the reference's CPU path restated by the oracle (oracle/, kind "port": the
@@ -329,20 +329,15 @@ def run_ours(args):
 
     # ---- end to end through the C ABI with host buffers
     for i in range(min(args.warmup, 3)):
-        img.fill(0)
-        dev.fill_batch(img, arrays)
-        dev.download_async(img, pinned)
-        dev.sync()
+        dev.render_batch_host(pinned.ptr, size, size, arrays)
     e2e_s = []
     barrier()
     for i in range(args.steps):
         l2_flush(i)
         dev.sync()
         t0 = time.perf_counter()
-        img.fill(0)
-        dev.fill_batch(img, arrays)      # host segments -> H2D -> partition + raster kernels
-        dev.download_async(img, pinned)  # canvas -> pinned host memory
-        dev.sync()
+        # one C-ABI call: fresh canvas, host segments -> H2D -> count/scan/partition/raster kernels -> canvas -> pinned host
+        dev.render_batch_host(pinned.ptr, size, size, arrays)
         e2e_s.append(time.perf_counter() - t0)
     barrier()
     clocks = sampler.stop()

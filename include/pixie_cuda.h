@@ -85,6 +85,16 @@ int pixie_cuda_fill_batch(pixie_image_t image, int num_fills, const int32_t* lay
                           const uint32_t* rgbx, const uint8_t* winding_rule, const uint8_t* blend_mode,
                           uint64_t* covered_px);
 
+/* One-shot newImage(svg)-style render with host pixels out: a width x height canvas (transparent when
+ * clear != 0, else initialised from `pixels`), the ordered fills, and the result written to `pixels`.
+ * The canvas is rasterised in row bands on concurrent streams and each band is copied out as soon as it
+ * is done, so the D2H copy overlaps the rendering when `pixels` is page-locked (pixie_cuda_host_alloc).
+ * Blocks until `pixels` is complete. */
+int pixie_cuda_render_batch_host(uint8_t* pixels, int width, int height, int clear, int num_fills,
+                                 const float* seg_xyxy, const int16_t* winding, const int32_t* seg_offsets,
+                                 const uint32_t* rgbx, const uint8_t* winding_rule, const uint8_t* blend_mode,
+                                 uint64_t* covered_px);
+
 /* Same, split so the inputs can stay resident in HBM: create uploads segments + per-fill headers
  * for canvases of (width, height, layers); run rasterises them into `image`. */
 int pixie_cuda_cmdlist_create(int width, int height, int layers, int num_fills, const int32_t* layer_of_fill,

@@ -40,6 +40,11 @@ struct Runtime {
   size_t pinned_bytes = 0;
   cudaEvent_t staging_done = nullptr;  // recorded after the H2D copy that reads `pinned`
   bool staging_busy = false;
+  // row-band streams of pixie_cuda_render_batch_host (rasterise band b while band b-1 goes to the host)
+  static constexpr int kBands = 4;
+  cudaStream_t band_stream[kBands] = {};
+  cudaEvent_t band_done[kBands] = {};
+  cudaEvent_t band_start = nullptr;
   // per-kernel CUDA-event timing (pixie_cuda_set_profiling): slot -> (begin, end) of the last launch
   bool profiling = false;
   cudaEvent_t prof[8][2] = {};

@@ -299,6 +299,9 @@ struct RasterArgs {
   const uint8_t* flags;
   uint32_t* gscratch;          // per-warp global spill (scratchWords words each), may be null
   unsigned long long* counters;
+  long long rowBegin, rowEnd;  // flattened (layer * h + y) rows this launch owns
+  int ticketSlot;              // counters[ticketSlot] hands out rows
+  int scratchBlockBase;        // first block of this launch in the global spill area
   int smemCap;                 // entries whose scratch fits in shared memory
   int scratchCap;              // capacity of the global spill
   int covBytes;                // bytes of the per-warp coverage row in shared memory
@@ -813,18 +816,17 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
   uint8_t* cov = mine;
   uint32_t* sscr = reinterpret_cast<uint32_t*>(mine + A.covBytes);
   uint32_t* gscr = A.gscratch
-                       ? A.gscratch + (size_t)(blockIdx.x * warpsPerBlock + warp) * ((size_t)A.scratchCap * kScratchArrays)
+                       ? A.gscratch + (size_t)((A.scratchBlockBase + blockIdx.x) * warpsPerBlock + warp) * ((size_t)A.scratchCap * kScratchArrays)
                        : nullptr;
   for (int i = lane * 4; i < A.covBytes; i += 128) *reinterpret_cast<uint32_t*>(cov + i) = 0u;
   __syncwarp();
 
-  const long long totalRows = (long long)A.layers * A.h;
   unsigned covered = 0;
   while (true) {
     unsigned long long ticket = 0;
-    if (lane == 0) ticket = atomicAdd(&A.counters[0], 1ull);
-    ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    if ((long long)ticket >= totalRows) break;
+    if (lane == 0) ticket = atomicAdd(&A.counters[A.ticketSlot], 1ull);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0) + (unsigned long long)A.rowBegin;
+    if ((long long)ticket >= A.rowEnd) break;
     const int layer = (int)(ticket / (unsigned)A.h), y = (int)(ticket % (unsigned)A.h);
     WarpCtx c;
     c.row = A.canvas + ((size_t)layer * A.h + y) * A.w;
@@ -1032,7 +1034,7 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   const size_t h2dBytes = off;
   const size_t oEntryOff = off;  off = al(off + (P + 1) * 4);   // band counts, scanned in place to offsets
   const size_t oFlags = off;     off = al(off + std::max<size_t>(1, P));
-  const size_t oCounters = off;  off = al(off + 32);            // [0] row ticket, [1] covered px, [2] entries, [3] max
+  const size_t oCounters = off;  off = al(off + 128);           // [0] row ticket, [1] covered px, [2] entries, [3] max, [4..] band tickets
   const size_t totalA = off;
 
   uint8_t* stage = nullptr;
@@ -1116,7 +1118,7 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   return 0;
 }
 
-static int run_list(CmdList& L, Image* im, uint64_t* covered_px) {
+static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_pixels = nullptr) {
   Runtime& r = rt();
   if (im->bpp != 4 || im->w != L.w || im->h != L.h || im->layers != L.layers)
     return fail_pixie("command list was built for a different canvas shape");
@@ -1124,7 +1126,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px) {
     if (covered_px) *covered_px = 0;
     return 0;
   }
-  PX_CUDA(cudaMemsetAsync(L.counters, 0, 16, r.stream));  // row ticket + covered px
+  PX_CUDA(cudaMemsetAsync(L.counters, 0, 128, r.stream));  // row tickets + covered px
   if (L.numParts > 0) {
     const int warps = (int)std::min<int64_t>(L.numParts, (int64_t)r.num_sms * 32);
     const int blocks = (warps + 7) / 8;
@@ -1147,11 +1149,43 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px) {
     PX_CUDA(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes));
     configured = L.smemBytes;
   }
-  {
-    ProfScope ps(kProfRaster);
-    raster_kernel<<<L.rasterBlocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
+  const long long totalRows = (long long)L.layers * L.h;
+  if (!host_pixels) {
+    A.rowBegin = 0; A.rowEnd = totalRows; A.ticketSlot = 0; A.scratchBlockBase = 0;
+    {
+      ProfScope ps(kProfRaster);
+      raster_kernel<<<L.rasterBlocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
+    }
+    PX_LAUNCHED();
+  } else {
+    // Row bands on concurrent streams: each band's pixels start their way to the host as soon as the
+    // band is rasterised, while the heavier bands are still being worked on.
+    constexpr int K = Runtime::kBands;
+    if (!r.band_stream[0]) {
+      for (int b = 0; b < K; b++) {
+        PX_CUDA(cudaStreamCreateWithFlags(&r.band_stream[b], cudaStreamNonBlocking));
+        PX_CUDA(cudaEventCreateWithFlags(&r.band_done[b], cudaEventDisableTiming));
+      }
+      PX_CUDA(cudaEventCreateWithFlags(&r.band_start, cudaEventDisableTiming));
+    }
+    PX_CUDA(cudaEventRecord(r.band_start, r.stream));
+    const int gridB = std::max(1, L.rasterBlocks / K);
+    const size_t rowBytes = (size_t)L.w * 4;
+    for (int b = 0; b < K; b++) {
+      A.rowBegin = totalRows * b / K;
+      A.rowEnd = totalRows * (b + 1) / K;
+      A.ticketSlot = 4 + b;
+      A.scratchBlockBase = b * gridB;
+      if (A.rowEnd <= A.rowBegin) continue;
+      PX_CUDA(cudaStreamWaitEvent(r.band_stream[b], r.band_start, 0));
+      raster_kernel<<<gridB, L.warpsPerBlock * 32, L.smemBytes, r.band_stream[b]>>>(A);
+      PX_LAUNCHED();
+      PX_CUDA(cudaMemcpyAsync(host_pixels + (size_t)A.rowBegin * rowBytes, im->data + (size_t)A.rowBegin * rowBytes,
+                              (size_t)(A.rowEnd - A.rowBegin) * rowBytes, cudaMemcpyDeviceToHost, r.band_stream[b]));
+      PX_CUDA(cudaEventRecord(r.band_done[b], r.band_stream[b]));
+      PX_CUDA(cudaStreamWaitEvent(r.stream, r.band_done[b], 0));
+    }
   }
-  PX_LAUNCHED();
   if (covered_px) {
     unsigned long long host[2];
     PX_CUDA(cudaMemcpyAsync(host, L.counters, 16, cudaMemcpyDeviceToHost, r.stream));
@@ -1225,6 +1259,32 @@ int pixie_cuda_fill_batch(pixie_image_t image, int numFills, const int32_t* laye
   int rc = build_list(L, true, im->w, im->h, im->layers, numFills, layerOf, seg, wind, segOff, rgbx, rule, mode);
   if (!rc) rc = run_list(L, im, covered_px);
   return rc;
+}
+
+int pixie_cuda_render_batch_host(uint8_t* pixels, int width, int height, int clear, int numFills, const float* seg,
+                                 const int16_t* wind, const int32_t* segOff, const uint32_t* rgbx, const uint8_t* rule,
+                                 const uint8_t* mode, uint64_t* covered_px) {
+  if (int rc = ensure_init()) return rc;
+  if (width <= 0 || height <= 0) return fail_pixie("Image width and height must be > 0");
+  Runtime& r = rt();
+  void* canvas;
+  const size_t bytes = (size_t)width * height * 4;
+  if (int rc = get_scratch(5, bytes, &canvas)) return rc;
+  if (clear) PX_CUDA(cudaMemsetAsync(canvas, 0, bytes, r.stream));                        // newImage(width, height)
+  else PX_CUDA(cudaMemcpyAsync(canvas, pixels, bytes, cudaMemcpyHostToDevice, r.stream));  // draw over existing pixels
+  Image im;
+  im.data = (uint8_t*)canvas; im.w = width; im.h = height; im.layers = 1; im.bpp = 4; im.owned = false;
+  CmdList L;
+  int rc = build_list(L, true, width, height, 1, numFills, nullptr, seg, wind, segOff, rgbx, rule, mode);
+  if (rc) return rc;
+  if (numFills == 0) {
+    PX_CUDA(cudaMemcpyAsync(pixels, canvas, bytes, cudaMemcpyDeviceToHost, r.stream));
+  } else {
+    rc = run_list(L, &im, covered_px, pixels);
+    if (rc) return rc;
+  }
+  PX_CUDA(cudaStreamSynchronize(r.stream));
+  return 0;
 }
 
 int pixie_cuda_fill_segments(pixie_image_t image, const float* seg, const int16_t* wind, int n, uint32_t rgbx,

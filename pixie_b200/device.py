@@ -44,6 +44,7 @@ _SIGNATURES = {
     "pixie_cuda_image_checksum": [u64, P(u64)],
     "pixie_cuda_fill_segments": [u64, vp, vp, i32, u32, i32, i32],
     "pixie_cuda_fill_batch": [u64, i32, vp, vp, vp, vp, vp, vp, vp, P(u64)],
+    "pixie_cuda_render_batch_host": [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, P(u64)],
     "pixie_cuda_cmdlist_create": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, P(u64)],
     "pixie_cuda_cmdlist_run": [u64, u64, P(u64)],
     "pixie_cuda_cmdlist_info": [u64, P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64)],
@@ -239,6 +240,17 @@ def fill_batch(image: DeviceImage, arrays: dict, count_covered=False):
     cov = u64(0)
     check(lib().pixie_cuda_fill_batch(
         image.handle, len(arrays["rgbx"]), _ptr(arrays["layer"]), _ptr(arrays["xyxy"]), _ptr(arrays["winding"]),
+        _ptr(arrays["seg_offsets"]), _ptr(arrays["rgbx"]), _ptr(arrays["rule"]), _ptr(arrays["mode"]),
+        C.byref(cov) if count_covered else None))
+    return cov.value
+
+
+def render_batch_host(pixels_ptr: int, width: int, height: int, arrays: dict, clear=True, count_covered=False):
+    """pixie_cuda_render_batch_host: fresh canvas + ordered fills + pixels back to host memory at `pixels_ptr`
+    (ideally a PinnedBuffer).  Single-layer command lists only."""
+    cov = u64(0)
+    check(lib().pixie_cuda_render_batch_host(
+        pixels_ptr, width, height, 1 if clear else 0, len(arrays["rgbx"]), _ptr(arrays["xyxy"]), _ptr(arrays["winding"]),
         _ptr(arrays["seg_offsets"]), _ptr(arrays["rgbx"]), _ptr(arrays["rule"]), _ptr(arrays["mode"]),
         C.byref(cov) if count_covered else None))
     return cov.value

@@ -63,3 +63,29 @@ def test_tiger_per_fill_coverage_maps():
     bad = [(k, diff_report(got[k], want[k])[:2]) for k in range(n) if diff_report(got[k], want[k])[0]]
     assert not bad, bad[:10]
     assert gc_ == wc
+
+
+def test_render_batch_host_equals_resident_path():
+    """pixie_cuda_render_batch_host (row bands on concurrent streams, D2H overlapped) gives the same bytes
+    as fill_batch + download, with pinned and with pageable host memory, with and without `clear`."""
+    from pixie_b200 import device as dev
+
+    size = 1024
+    arrays = psvg.svg_fill_batch(psvg.parseSvg(open(TIGER).read(), size, size)).arrays()
+    dev.init(0)
+    img = dev.DeviceImage(size, size)
+    c0 = dev.fill_batch(img, arrays, count_covered=True)
+    want = img.download()
+    pinned = dev.PinnedBuffer(size * size * 4)
+    c1 = dev.render_batch_host(pinned.ptr, size, size, arrays, count_covered=True)
+    assert c1 == c0 and np.array_equal(pinned.array.reshape(size, size, 4), want)
+    host = np.full((size, size, 4), 7, np.uint8)
+    dev.render_batch_host(host.ctypes.data, size, size, arrays)
+    assert np.array_equal(host, want)
+    # clear = False: draw over existing pixels
+    bg = np.full((size, size, 4), 255, np.uint8)
+    img.upload(bg)
+    dev.fill_batch(img, arrays)
+    over = bg.copy()
+    dev.render_batch_host(over.ctypes.data, size, size, arrays, clear=False)
+    assert np.array_equal(over, img.download())
