@@ -36,7 +36,7 @@ struct FillHeader {
   uint32_t rgbx;
   int rule, mode;
   int active;   // 0: pathWidth == 0, the reference returns before touching the image (:1615-1616)
-  int pad;
+  int wrapRows; // MaskBlend only: rows above a scanline that its negative-x clears can reach (see mask_wrap_clears)
 };
 
 struct __align__(16) Entry {
@@ -513,6 +513,115 @@ PXD void blend_coverage_row(WarpCtx& c, int startX, int pathWidth, int covBase, 
   }
 }
 
+// MaskBlend + trapezoid shortcut with geometry left of the canvas.  The reference clears the gaps between
+// fill pairs with clearUnsafe(min(filledTo, width), y, min(clearTo, width), y) (:1856-1866, :1433-1440),
+// which addresses the canvas LINEARLY (dataIndex = width * y + x): when filledTo / clearTo are negative
+// the cleared range lies in the rows above y, which the same fill has already finished.  Those writes are
+// inside the image, so they are part of the reference's result; a warp owns one row, so after its own
+// work on row c.y it replays the mode-B decision of row yy > c.y and applies the part of row yy's clears
+// that lands on its row.  Clears commute, so the order among the rows below does not matter.
+__device__ __noinline__ void mask_wrap_clears(WarpCtx& c, const FillHeader& H, const RasterArgs& A, int yy, uint32_t* sscr,
+                                              uint32_t* gscr) {
+  const int lane = c.lane, W = c.w;
+  int p = (yy - H.startY) / H.partitionHeight;
+  if (p > H.numPartitions - 1) p = H.numPartitions - 1;
+  const int gp = H.partBase + p;
+  const int eBeg = A.entryOff[gp];
+  const int eCnt = A.entryOff[gp + 1] - eBeg;
+  const unsigned fl = A.flags[gp];
+  const bool aa = (fl & 1u) != 0, two = (fl & 2u) != 0;
+  if (two && !aa) return;  // mode A clamps its spans to the row
+  const Entry* ent = A.entries + eBeg;
+  uint32_t* scr = eCnt > A.smemCap ? gscr : sscr;
+  const int cap = eCnt > A.smemCap ? A.scratchCap : A.smemCap;
+  int* sel = reinterpret_cast<int*>(scr);
+  float* tax = reinterpret_cast<float*>(scr + 2 * cap);
+  float* tbx = reinterpret_cast<float*>(scr + 3 * cap);
+  float* mid = reinterpret_cast<float*>(scr + 4 * cap);
+  int* idx = reinterpret_cast<int*>(scr + 5 * cap);
+  float* midS = reinterpret_cast<float*>(scr + 6 * cap);
+  int* order = reinterpret_cast<int*>(scr + 7 * cap);
+  const float scanTop = (float)yy, scanBottom = (float)(yy + 1);
+  bool allSpan = true;
+  int nsel = 0;
+  if (two) {
+    nsel = 2;
+    if (lane < 2) sel[lane] = lane;
+  } else {
+    for (int base = 0; base < eCnt; base += 32) {
+      const int i = base + lane;
+      bool take = false, partial = false;
+      if (i < eCnt) {
+        const float ay = ent[i].ay, by = ent[i].by;
+        take = !(by <= scanTop || ay >= scanBottom);
+        partial = take && (ay > scanTop || by < scanBottom);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, take);
+      if (__any_sync(0xffffffffu, partial)) allSpan = false;
+      if (take) sel[nsel + __popc(bal & ((1u << lane) - 1u))] = i;
+      nsel += __popc(bal);
+    }
+  }
+  __syncwarp();
+  if (!allSpan || (nsel % 2) != 0) return;  // computeCoverage path: its clears stay inside the row
+  for (int s = lane; s < nsel; s += 32) {
+    const Entry e = ent[sel[s]];
+    const float xa = solve_x(e.m, e.b, scanTop), xb = solve_x(e.m, e.b, scanBottom);
+    tax[s] = xa;
+    tbx[s] = xb;
+    mid[s] = (xa + xb) * 0.5f;
+    idx[s] = s;
+  }
+  __syncwarp();
+  warp_stable_sort<float>(nsel, lane, mid, idx, midS, order);
+  __syncwarp();
+  bool ok = true;
+  for (int i = lane; i < nsel - 1; i += 32) {
+    const int l = order[i], r = order[i + 1];
+    if (f2ll(ceilf(fmaxf(tax[l], tbx[l]))) > f2ll(fminf(tax[r], tbx[r]))) ok = false;
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (ok) {
+    int carry = 0;
+    for (int base = 0; base < nsel; base += 32) {
+      const int i = base + lane;
+      int pre = (i < nsel) ? ent[sel[order[i]]].winding : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += t;
+      }
+      pre += carry;
+      if (i < nsel) {
+        const bool f = should_fill(H.rule, pre);
+        if (((i & 1) == 0) ? !f : f) ok = false;
+      }
+      carry = __shfl_sync(0xffffffffu, pre, 31);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+  }
+  if (!ok) return;
+  // linear pixel index of x on row yy, relative to the start of row c.y
+  const long long rowOff = (long long)(yy - c.y) * W;
+  long long filledTo = 0;
+  for (int i = 0; i < nsel; i += 2) {
+    const int ls = order[i], rs = order[i + 1];
+    const long long clearTo = f2ll(fminf(tax[ls], tbx[ls]));
+    const long long a = filledTo < W ? filledTo : W, b = clearTo < W ? clearTo : W;
+    if (a != W) {
+      const long long x0 = rowOff + a, x1 = rowOff + b;
+      if (x1 > 0 && x0 < W) clear_span(c, (int)(x0 > 0 ? x0 : 0), (int)(x1 < W ? x1 : W));
+    }
+    filledTo = f2ll(ceilf(fmaxf(tax[rs], tbx[rs])));
+  }
+  const long long a = filledTo < W ? filledTo : W;
+  if (a != W) {
+    const long long x0 = rowOff + a;
+    if (x0 < W) clear_span(c, (int)(x0 > 0 ? x0 : 0), W);
+  }
+  __syncwarp();
+}
+
 // One fill on one scanline.  Returns nothing; all lanes of the warp participate.
 template <int MODE>
 __device__ __noinline__ void fill_row(WarpCtx& c, const FillHeader& H, const RasterArgs& A, uint32_t* scr, int cap) {
@@ -868,6 +977,11 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
         else if (H.mode == MaskBlend) fill_row<MaskBlend>(c, H, A, scr, cap);
         else fill_row<GenericMode>(c, H, A, scr, cap);
         __syncwarp();
+        if (H.wrapRows > 0 && y >= H.startY) {  // only MaskBlend fills reaching left of the canvas
+          const int yEnd = min(H.pathHeight, y + 1 + H.wrapRows);
+          for (int yy = y + 1; yy < yEnd; yy++) mask_wrap_clears(c, H, A, yy, sscr, gscr);
+          __syncwarp();
+        }
       }
     }
     covered += c.covered;
@@ -991,6 +1105,10 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
     const uint32_t partitionHeight = (uint32_t)height / numPartitions;
     H.numPartitions = (int)numPartitions;
     H.partitionHeight = (int)partitionHeight;
+    if (H.mode == MaskBlend && xMin < 0.0f) {  // rows a negative-x clearUnsafe range can reach back (mask_wrap_clears)
+      const double reach = (-(double)floorf(xMin) + 1.0 + (double)w - 1.0) / (double)w;
+      H.wrapRows = reach >= (double)h ? h : (int)reach;
+    }
     numPartsTotal += numPartitions;
     if (numPartsTotal > 0x3fffffff) return fail_pixie("command list too large");
   }

@@ -118,3 +118,27 @@ def test_single_fill_entry_point_and_host_variant():
     dev.check(dev.lib().pixie_cuda_fill_segments_host(px.ctypes.data, 200, 150, segs.xyxy.ctypes.data,
                                                       segs.winding.ctypes.data, len(segs), pack(10, 20, 30, 200), 0, 0))
     assert diff_report(px, want)[0] == 0
+
+
+@pytest.mark.parametrize("pairs", [((-1.45, -1.2), (-0.5, -0.2), (0.25, 0.6)), ((-3.4, -2.9), (-1.7, -1.2), (0.25, 0.6)),
+                                   ((-0.9, -0.1), (0.25, 0.6)), ((-5.0, -4.5), (-0.3, 0.3), (0.5, 1.4))])
+@pytest.mark.parametrize("width", [40, 37])
+def test_mask_clears_left_of_canvas_wrap_into_rows_above(width, pairs):
+    """MaskBlend through the trapezoid shortcut with fill pairs left of x = 0: the reference's
+    clearUnsafe(min(filledTo, w), y, min(clearTo, w), y) (paths.nim:1856-1866, :1433-1440) addresses the
+    canvas linearly, so a negative x range clears pixels of the rows above — inside the image, hence
+    part of the reference's result (the oracle does the same; only indices < 0 are dropped)."""
+    w, h = width, 24
+    rows, wind = [], []
+    for x0, x1 in pairs:
+        rows.append([x0 * w, -2.0, x0 * w + 3.0, h + 2.0])
+        rows.append([x1 * w + 2.0, -2.0, x1 * w, h + 2.0])
+        wind += [1, -1]
+    segs = host.Segments(np.array(rows, np.float32), np.array(wind, np.int16))
+    bg = synth.random_premultiplied(h, w, 7)
+    for rule in (0, 1):
+        for col in (pack(255, 255, 255, 255), pack(60, 50, 40, 120)):
+            b = FillBatch()
+            b.add(segs, col, rule, MaskBlend)
+            b.add(segs, pack(10, 200, 30, 255), rule, NormalBlend)
+            _check(b.arrays(), w, h, background=bg)
