@@ -50,7 +50,7 @@ struct Runtime {
   cudaEvent_t prof[8][2] = {};
 };
 
-enum ProfSlot { kProfPartition = 0, kProfRaster = 1, kProfBlurX = 2, kProfBlurY = 3, kProfBlend = 4, kProfSpread = 5 };
+enum ProfSlot { kProfPartition = 0, kProfRaster = 1, kProfBlurX = 2, kProfBlurY = 3, kProfBlend = 4, kProfSpread = 5, kProfPlan = 6 };
 struct ProfScope {  // brackets one kernel launch with events on the library stream when profiling is on
   int slot;
   explicit ProfScope(int s);

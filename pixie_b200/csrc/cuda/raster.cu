@@ -5,14 +5,14 @@
 //                          into equal-height y bands (one warp per band, ballot compaction keeps
 //                          segment order), per-band requiresAntiAliasing (:1149-1166), clipping of
 //                          spanning entries (:1236-1248), twoNonintersectingSpanningSegments (:1250-1262)
-//   K2+K3 raster_kernel    the scanline loop (:1631-1908) fused with the blend:
-//                          one warp owns one (layer, scanline) and walks the ordered fill list, so
-//                          fills of one canvas keep the reference's sequential semantics with a
-//                          single launch and no inter-fill synchronisation; per fill it picks
-//                          mode A (pixel-aligned pair :1644-1668), mode B (exact-area trapezoids
-//                          :1691-1872) or mode C (computeCoverage :1350-1431, 5 sample lines, with
-//                          `walk` :1298-1330 emulated literally) and blends straight into the
-//                          canvas (fillCoverage / fillHits :1479-1591, blends.nim).
+//   K2  plan_kernel        the scanline loop (:1631-1908) up to the canvas: one warp per (fill, scanline)
+//                          job picks mode A (pixel-aligned pair :1644-1668), mode B (exact-area
+//                          trapezoids :1691-1872) or mode C (computeCoverage :1350-1431: 5 sample lines
+//                          side by side, `walk` :1298-1330 emulated literally) and stores a small plan
+//   K3  raster_kernel      one warp per canvas row applies the plans of the row's fills in order, so fills
+//                          of one canvas keep the reference's sequential semantics with a single launch:
+//                          coverage accumulation in shared memory, fillCoverage / fillHits (:1479-1591),
+//                          trapezoid edge pixels, blends.nim
 //
 // All geometry is IEEE float32 with one rounding per operation (compiled with -fmad=false,
 // -prec-div=true) so that every mode decision equals the CPU reference's.
@@ -46,6 +46,7 @@ struct __align__(16) Entry {
   int pad;
 };
 
+struct JobHdr;
 struct CmdList {
   int w = 0, h = 0, layers = 1;
   int numFills = 0;
@@ -55,6 +56,12 @@ struct CmdList {
   int16_t* wind = nullptr;
   FillHeader* fills = nullptr;
   int2* rowRange = nullptr;
+  int* fillJobBase = nullptr;
+  unsigned* payOff = nullptr;
+  JobHdr* jobs = nullptr;
+  uint2* payload = nullptr;
+  int totalJobs = 0, planBlocks = 0;
+  size_t planSmem = 0;
   int* entryOff = nullptr;
   int* layerFillBegin = nullptr;
   Entry* entries = nullptr;
@@ -286,29 +293,55 @@ __global__ void __launch_bounds__(256) partition_kernel(const FillHeader* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2+K3: scanlines
+// K2 + K3: scanlines.
+//
+// A *job* is one fill on one scanline inside the path's rows.  What a job does splits cleanly:
+//   plan_kernel   (K2) everything that depends on the geometry only — the scanline loop of fillShapes
+//                 (:1631-1908) up to the point where it touches the canvas: entry selection, the
+//                 trapezoid shortcut's sort and checks, computeCoverage's hits / sort / walk.  Jobs are
+//                 independent, so all (fill, scanline) pairs of a command list run in parallel; the
+//                 result is a 16-byte JobHdr plus a short payload (sorted edges or spans).
+//   raster_kernel (K3) one warp per canvas row walks the row's fills IN ORDER and applies their plans:
+//                 trapezoid edge pixels and interiors, the coverage row (accumulated in shared memory
+//                 from the spans) and its blend, integer spans, MaskBlend's clears.
+// Two kernels instead of one fused one because of the instruction cache: the fused kernel with every
+// primitive inlined was 0.6 MB of SASS, 24 warps per SM all in different places of it, and ncu showed
+// `no_instruction` as the top stall reason (icc hit rate 70-79 %).  Each half now fits the 32 KB L1.5
+// I-cache, and the expensive half no longer sits on the critical path of the heaviest row.
 // ---------------------------------------------------------------------------------------------
+struct JobHdr {
+  int kind;    // PlanKind
+  int n;       // Trapezoids: edges (even); Coverage / Spans: spans
+  int pa, pb;  // Aligned: the span [pa, pb)
+};
+
 struct RasterArgs {
   px_t* canvas;
   int w, h, layers;
+  int numFills;
   const FillHeader* fills;
   const int2* rowRange;        // rows [x, y) of the canvas each fill has to visit (empty when inactive)
   const int* layerFillBegin;
   const int* entryOff;
   const Entry* entries;
   const uint8_t* flags;
-  uint32_t* gscratch;          // per-warp global spill (scratchWords words each), may be null
+  const int* fillJobBase;      // [numFills + 1] first job of each fill; job = fillJobBase[f] + (y - startY)
+  const unsigned* payOff;      // [numParts + 1] payload offset of each band, in entry-rows
+  JobHdr* jobs;
+  uint2* payload;              // kPaySlots 8-byte slots per entry-row
+  int totalJobs;
+  uint32_t* gscratch;          // per-warp global spill (scratchCap * kScratchArrays words each), may be null
   unsigned long long* counters;
   long long rowBegin, rowEnd;  // flattened (layer * h + y) rows this launch owns
   int ticketSlot;              // counters[ticketSlot] hands out rows
-  int scratchBlockBase;        // first block of this launch in the global spill area
   int smemCap;                 // entries whose scratch fits in shared memory
   int scratchCap;              // capacity of the global spill
   int covBytes;                // bytes of the per-warp coverage row in shared memory
   int countCovered;
 };
 
-constexpr int kScratchArrays = 8;
+constexpr int kScratchArrays = 18;  // scratch words per band entry (see the layout in plan_row)
+constexpr int kPaySlots = 5;        // payload slots per entry-row: <= 5 spans (one per sample line) or 2 per edge
 
 constexpr int GenericMode = -1;  // every mode that goes through blender() per pixel, chosen at run time
 
@@ -323,84 +356,20 @@ PXD px_t blend_any(int mode, px_t b, px_t s) {
   return blend_px < MODE == GenericMode ? 0 : MODE > (b, s);
 }
 
-struct WarpCtx {
-  int mode;         // run-time blend mode (used by the GenericMode instantiation)
-  px_t* row;        // canvas row of this warp
-  int w;            // canvas width
-  int y;
-  int lane;
-  uint8_t* cov;     // coverage row (index 0 = pixel covBase)
-  bool vec_ok;      // rows are 16-byte aligned
-  unsigned covered; // per-lane count of pixels touched with non-zero coverage
+enum PlanKind {
+  PlanOutside = -1,    // the path does not reach this row (only MaskBlend touches it, :1910-1912)
+  PlanNothing = 0,
+  PlanAligned = 1,     // mode A (:1644-1668): one pixel-aligned span [pa, pb)
+  PlanTrapezoids = 2,  // mode B (:1691-1872): n sorted edges, exact-area edge pixels + interiors
+  PlanCoverage = 3,    // computeCoverage with anti-aliasing: n spans (24.8 fixed) of the 5 sample lines
+  PlanSpans = 4,       // computeCoverage without: n spans of the single sample line (fillHits over walkInteger)
 };
 
-template <int MODE>
-PXD px_t span_op(int mode, px_t d, px_t rgbx) {  // fillHits per-pixel op (:1551-1591)
-  if (MODE == NormalBlend) return line_normal(d, rgbx);   // blendLineNormal (sse2.nim:568-588)
-  if (MODE == MaskBlend) return line_mask(d, rgbx);       // blendLineMask (sse2.nim:669-688)
-  if (MODE == OverwriteBlend) return rgbx;
-  return blend_any<MODE>(mode, d, rgbx);
-}
-
-PXD void clear_span(WarpCtx& c, int x0, int x1) {  // [x0, x1) -> transparent
-  x0 = max(x0, 0);
-  x1 = min(x1, c.w);
-  for (int x = x0 + c.lane; x < x1; x += 32) c.row[x] = 0u;
-}
-
-// interior span of fillHits: [x0, x1) gets the solid colour blended in
-template <int MODE>
-PXD void fill_span(WarpCtx& c, int x0, int x1, px_t rgbx) {
-  x0 = max(x0, 0);
-  x1 = min(x1, c.w);
-  if (x1 <= x0) return;
-  const bool store_only = MODE == OverwriteBlend || (MODE == NormalBlend && pA(rgbx) == 255u);
-  if (MODE == MaskBlend && pA(rgbx) == 255u) {  // :1576-1577: opaque mask leaves the span untouched
-    if (c.lane == 0) c.covered += (unsigned)(x1 - x0);
-    return;
-  }
-  if (c.vec_ok && x1 - x0 >= 64) {
-    const int xa = (x0 + 3) & ~3, xb = x1 & ~3;
-    for (int x = x0 + c.lane; x < xa; x += 32) {
-      c.row[x] = store_only ? rgbx : span_op<MODE>(c.mode, c.row[x], rgbx);
-      c.covered++;
-    }
-    for (int x = xa + 4 * c.lane; x < xb; x += 128) {
-      uint4* p = reinterpret_cast<uint4*>(c.row + x);
-      uint4 v;
-      if (store_only) {
-        v = make_uint4(rgbx, rgbx, rgbx, rgbx);
-      } else {
-        v = *p;
-        v.x = span_op<MODE>(c.mode, v.x, rgbx); v.y = span_op<MODE>(c.mode, v.y, rgbx);
-        v.z = span_op<MODE>(c.mode, v.z, rgbx); v.w = span_op<MODE>(c.mode, v.w, rgbx);
-      }
-      *p = v;
-      c.covered += 4;
-    }
-    for (int x = xb + c.lane; x < x1; x += 32) {
-      c.row[x] = store_only ? rgbx : span_op<MODE>(c.mode, c.row[x], rgbx);
-      c.covered++;
-    }
-  } else {
-    for (int x = x0 + c.lane; x < x1; x += 32) {
-      c.row[x] = store_only ? rgbx : span_op<MODE>(c.mode, c.row[x], rgbx);
-      c.covered++;
-    }
-  }
-}
-
-// trapezoid edge pixel: blender()(backdrop, rgbx * area) (:1803-1809, :1841-1847)
-template <int MODE>
-PXD void edge_pixel(WarpCtx& c, int x, float area, px_t rgbx) {
-  const px_t src = mul_area(rgbx, area);
-  c.row[x] = blend_any<MODE>(c.mode, c.row[x], src);
-  c.covered++;
-}
-
-// walk (:1298-1330) executed by one lane over sorted hits; spans are appended to spanA/spanB.
+// walk (:1298-1330) executed by one lane over sorted hits; spans are appended to spanA/spanB, which may be
+// the hit arrays themselves: span k is emitted while reading hit i > k.
 PXD int walk_spans(const int* hitAt, const int* hitW, int numHits, int rule, int* spanA, int* spanB) {
   int i = 0, count = 0, prevAt = 0, ns = 0;
+#pragma unroll 1
   while (i < numHits) {
     const int at = hitAt[i], winding = hitW[i];
     if (at > 0) {
@@ -429,87 +398,656 @@ PXD int walk_spans(const int* hitAt, const int* hitW, int numHits, int rule, int
   return ns;
 }
 
-// stable sort of n (key, val) pairs by key, ascending; equal keys keep their order
-// (= the reference's insertion sorts, :1277-1286 and :1707-1716).  src -> dst arrays.
-template <typename K>
-PXD void warp_stable_sort(int n, int lane, const K* key, const int* val, K* keyOut, int* valOut) {
-  for (int i = lane; i < n; i += 32) {
-    const K ki = key[i];
-    int r = 0;
-    for (int j = 0; j < n; j++) {
-      const K kj = key[j];
-      r += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+// last fill whose first job is <= j (fills without jobs share their base with the next one)
+PXD int find_fill_by_job(const int* __restrict__ jobBase, int numFills, int j) {
+  int lo = 0, hi = numFills;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (jobBase[mid] <= j) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo - 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: plan_kernel — one warp per job.
+//
+// Scratch per warp (cap = entries the scratch was sized for, kScratchArrays * cap words):
+//   [0, cap) sel      indices of the band entries that cross the scanline, in entry order (:1681-1689)
+//   [cap, 2cap) sel2  the same in trapezoid mid-x order (what computeCoverage sees after a failed mode B)
+//   mode B:   tax, tbx, mid, wnd, -, order  at 2cap .. 8cap
+//   coverage: uAt[T], sAt[T], sW[T], lineHits[8] at 2cap ..   with T = quality * nsel <= 5 cap
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warpsPerBlock = blockDim.x >> 5;
+  uint32_t* sscr = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * A.smemCap * kScratchArrays;
+  uint32_t* gscr = A.gscratch ? A.gscratch + (size_t)(blockIdx.x * warpsPerBlock + warp) * ((size_t)A.scratchCap * kScratchArrays)
+                              : nullptr;
+  const int W = A.w;
+  const float wf = (float)W;
+  const int warpsTotal = gridDim.x * warpsPerBlock;
+#pragma unroll 1
+  for (int job = blockIdx.x * warpsPerBlock + warp; job < A.totalJobs; job += warpsTotal) {
+    const int f = find_fill_by_job(A.fillJobBase, A.numFills, job);
+    const FillHeader* Hp = A.fills + f;
+    const int startY = Hp->startY, rule = Hp->rule;
+    const int y = startY + (job - A.fillJobBase[f]);
+    const int ph = Hp->partitionHeight;
+    int p = (y - startY) / ph;
+    if (p > Hp->numPartitions - 1) p = Hp->numPartitions - 1;
+    const int gp = Hp->partBase + p;
+    const int eBeg = A.entryOff[gp];
+    const int eCnt = A.entryOff[gp + 1] - eBeg;
+    const unsigned fl = A.flags[gp];
+    const Entry* ent = A.entries + eBeg;
+    uint2* pay = A.payload + ((size_t)A.payOff[gp] + (size_t)(y - (startY + p * ph)) * (size_t)eCnt) * kPaySlots;
+    uint32_t* scr = eCnt > A.smemCap ? gscr : sscr;
+    const int cap = eCnt > A.smemCap ? A.scratchCap : A.smemCap;
+    const bool aa = (fl & 1u) != 0, two = (fl & 2u) != 0;
+    JobHdr hdr;
+    hdr.kind = PlanNothing;
+    hdr.n = 0;
+    hdr.pa = 0;
+    hdr.pb = 0;
+    __syncwarp();
+
+    if (two && !aa) {  // mode A (:1644-1668): two vertical pixel-aligned lines
+      hdr.kind = PlanAligned;
+      hdr.pa = clampi(f2ll(ent[0].ax), 0, W);
+      hdr.pb = clampi(f2ll(ent[1].ax), 0, W);
+      if (lane == 0) A.jobs[job] = hdr;
+      continue;
     }
-    keyOut[r] = ki;
-    valOut[r] = val[i];
+
+    int* sel = reinterpret_cast<int*>(scr);
+    int* sel2 = sel + cap;
+    const float scanTop = (float)y, scanBottom = (float)(y + 1);
+    bool allSpan = true;
+    int nsel = 0;
+    const int* selC = sel;  // entry order seen by computeCoverage
+    if (two) {
+      nsel = 2;
+      if (lane < 2) sel[lane] = lane;
+    } else {  // :1681-1689
+#pragma unroll 1
+      for (int base = 0; base < eCnt; base += 32) {
+        const int i = base + lane;
+        bool take = false, partial = false;
+        if (i < eCnt) {
+          const float ay = ent[i].ay, by = ent[i].by;
+          take = !(by <= scanTop || ay >= scanBottom);
+          partial = take && (ay > scanTop || by < scanBottom);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, take);
+        if (__any_sync(0xffffffffu, partial)) allSpan = false;
+        if (take) sel[nsel + __popc(bal & ((1u << lane) - 1u))] = i;
+        nsel += __popc(bal);
+      }
+    }
+    __syncwarp();
+
+    if (allSpan && (nsel % 2) == 0) {  // mode B (:1691-1872)
+      float* tax = reinterpret_cast<float*>(scr + 2 * cap);
+      float* tbx = reinterpret_cast<float*>(scr + 3 * cap);
+      float* mid = reinterpret_cast<float*>(scr + 4 * cap);
+      int* wnd = reinterpret_cast<int*>(scr + 5 * cap);
+      int* order = reinterpret_cast<int*>(scr + 7 * cap);
+#pragma unroll 1
+      for (int s = lane; s < nsel; s += 32) {
+        const Entry e = ent[sel[s]];
+        const float xa = solve_x(e.m, e.b, scanTop), xb = solve_x(e.m, e.b, scanBottom);
+        tax[s] = xa;
+        tbx[s] = xb;
+        mid[s] = (xa + xb) * 0.5f;
+        wnd[s] = e.winding;
+      }
+      __syncwarp();
+      // stable sort by mid x (= the reference's insertion sort, :1707-1716): order[rank] = selected position
+#pragma unroll 1
+      for (int i = lane; i < nsel; i += 32) {
+        const float ki = mid[i];
+        int r = 0;
+#pragma unroll 4
+        for (int j = 0; j < nsel; j++) {
+          const float kj = mid[j];
+          r += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+        }
+        order[r] = i;
+      }
+      __syncwarp();
+      bool ok = true;
+#pragma unroll 1
+      for (int i = lane; i < nsel - 1; i += 32) {  // partial-coverage areas must not overlap (:1720-1728)
+        const int l = order[i], r = order[i + 1];
+        const float leftMaxX = fmaxf(tax[l], tbx[l]), rightMinX = fminf(tax[r], tbx[r]);
+        if (f2ll(ceilf(leftMaxX)) > f2ll(rightMinX)) ok = false;
+      }
+      ok = __all_sync(0xffffffffu, ok);
+      if (ok) {  // only simple fill pairs (:1732-1744): prefix winding count, filled after even, empty after odd
+        int carry = 0;
+#pragma unroll 1
+        for (int base = 0; base < nsel; base += 32) {
+          const int i = base + lane;
+          int pre = (i < nsel) ? wnd[order[i]] : 0;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += t;
+          }
+          pre += carry;
+          if (i < nsel) {
+            const bool fillIt = should_fill(rule, pre);
+            if (((i & 1) == 0) ? !fillIt : fillIt) ok = false;
+          }
+          carry = __shfl_sync(0xffffffffu, pre, 31);
+        }
+        ok = __all_sync(0xffffffffu, ok);
+      }
+      if (ok) {  // payload: per sorted edge {m, b} {x at the top, x at the bottom of the scanline}
+        hdr.kind = PlanTrapezoids;
+        hdr.n = nsel;
+#pragma unroll 1
+        for (int i = lane; i < nsel; i += 32) {
+          const int es = order[i];
+          const Entry e = ent[sel[es]];
+          pay[2 * i] = make_uint2(__float_as_uint(e.m), __float_as_uint(e.b));
+          pay[2 * i + 1] = make_uint2(__float_as_uint(tax[es]), __float_as_uint(tbx[es]));
+        }
+        if (lane == 0) A.jobs[job] = hdr;
+        continue;
+      }
+      // The reference sorts entryIndices in place (:1707-1716) before it decides whether the shortcut
+      // applies, so when it falls through, computeCoverage walks the entries in mid-x order.
+#pragma unroll 1
+      for (int i = lane; i < nsel; i += 32) sel2[i] = sel[order[i]];
+      selC = sel2;
+      __syncwarp();
+    }
+
+    // mode C: computeCoverage (:1350-1431).  The reference walks the `quality` sample lines one after the
+    // other; they are independent until their spans meet in the coverage row, so item t = m * nsel + s
+    // (line m, selected entry s) gets its own lane: hits, the stable sort by x (rank = number of hits of
+    // the same line that sort before it, ties by entry order = the insertion sort of :1277-1286) and the
+    // `walk` of each line (lane m) run concurrently.
+    const int quality = aa ? 5 : 1;
+    const float offset = 1.0f / (float)quality;
+    const float initialOffset = offset / 2.0f + (float)(0.0001 * 3.141592653589793238462643383279502884);
+    const int n = nsel, T = quality * n;
+    int* uAt = reinterpret_cast<int*>(scr + 2 * cap);  // hit x per item, entry order (kNoHit: none)
+    int* sAt = uAt + T;                                // per line: hits sorted by x, later the spans' begin
+    int* sW = sAt + T;                                 //           their windings,    later the spans' end
+    int* lineHits = sW + T;                            // [quality]
+    constexpr int kNoHit = INT_MAX;
+    hdr.kind = aa ? PlanCoverage : PlanSpans;
+    if (n > 0) {
+#pragma unroll 1
+      for (int t = lane; t < T; t += 32) {  // :1373-1385
+        const int m = t / n, s = t - m * n;
+        float yLine = (float)y + initialOffset - offset;
+#pragma unroll 1
+        for (int k = 0; k <= m; k++) yLine += offset;  // the reference accumulates yLine line by line (:1362-1371)
+        const Entry e = ent[selC[s]];
+        int at = kNoHit;
+        if (e.ay <= yLine && e.by >= yLine) {
+          float x = e.m == 0.0f ? e.b : (yLine - e.b) / e.m;
+          x = (x != x) ? wf : (x < wf ? x : wf);  // min(x, width.float32)
+          at = fixed32(x);
+        }
+        uAt[t] = at;
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int t = lane; t < T; t += 32) {
+        const int m = t / n, s = t - m * n;
+        const int at = uAt[t];
+        const int* line = uAt + m * n;
+        int r = 0, cnt = 0;
+#pragma unroll 4
+        for (int j = 0; j < n; j++) {
+          const int aj = line[j];
+          r += (aj < at || (aj == at && j < s)) ? 1 : 0;
+          cnt += aj != kNoHit ? 1 : 0;
+        }
+        if (at != kNoHit) {
+          sAt[m * n + r] = at;
+          sW[m * n + r] = ent[selC[s]].winding;
+        }
+        if (s == 0) lineHits[m] = cnt;
+      }
+      __syncwarp();
+      int ns = 0;  // spans of line `lane`
+      if (lane < quality) ns = walk_spans(sAt + lane * n, sW + lane * n, lineHits[lane], rule, sAt + lane * n, sW + lane * n);
+      __syncwarp();
+      const int n0 = __shfl_sync(0xffffffffu, ns, 0), n1 = __shfl_sync(0xffffffffu, ns, 1);
+      const int n2 = __shfl_sync(0xffffffffu, ns, 2), n3 = __shfl_sync(0xffffffffu, ns, 3);
+      const int n4 = __shfl_sync(0xffffffffu, ns, 4);
+      const int pre1 = n0, pre2 = pre1 + n1, pre3 = pre2 + n2, pre4 = pre3 + n3, S = pre4 + n4;
+      hdr.n = S;
+#pragma unroll 1
+      for (int g = lane; g < S; g += 32) {  // payload: the spans of all lines, {begin, end} in 24.8 fixed point
+        const int m = (g >= pre1) + (g >= pre2) + (g >= pre3) + (g >= pre4);
+        const int k = g - (m == 0 ? 0 : m == 1 ? pre1 : m == 2 ? pre2 : m == 3 ? pre3 : pre4);
+        pay[g] = make_uint2((uint32_t)sAt[m * n + k], (uint32_t)sW[m * n + k]);
+      }
+    }
+    if (lane == 0) A.jobs[job] = hdr;
   }
 }
 
-// fillCoverage (:1479-1526) on the accumulated coverage row, then zero it (:1896).
+// ---------------------------------------------------------------------------------------------
+// K3: raster_kernel — apply the plans to the canvas, row by row, fills in order
+// ---------------------------------------------------------------------------------------------
+struct WarpCtx {
+  int mode;         // run-time blend mode (used by the GenericMode instantiation)
+  px_t* row;        // canvas row of this warp
+  int w;            // canvas width
+  int y;
+  int lane;
+  uint8_t* cov;     // coverage row in shared memory (index 0 = pixel covBase)
+  bool vec_ok;      // rows are 16-byte aligned
+  unsigned covered; // per-lane count of pixels touched with non-zero coverage
+};
+
 template <int MODE>
-PXD void blend_coverage_row(WarpCtx& c, int startX, int pathWidth, int covBase, px_t rgbx) {
+PXD px_t span_op(int mode, px_t d, px_t rgbx) {  // fillHits per-pixel op (:1551-1591)
+  if (MODE == NormalBlend) return line_normal(d, rgbx);   // blendLineNormal (sse2.nim:568-588)
+  if (MODE == MaskBlend) return line_mask(d, rgbx);       // blendLineMask (sse2.nim:669-688)
+  if (MODE == OverwriteBlend) return rgbx;
+  return blend_any<MODE>(mode, d, rgbx);
+}
+
+__device__ __noinline__ void clear_span(WarpCtx& c, int x0, int x1) {  // [x0, x1) -> transparent
+  x0 = max(x0, 0);
+  x1 = min(x1, c.w);
+  px_t* row = c.row;
+#pragma unroll 1
+  for (int x = x0 + c.lane; x < x1; x += 32) row[x] = 0u;
+}
+
+// interior span of fillHits: [x0, x1) gets the solid colour blended in
+template <int MODE>
+__device__ __noinline__ void fill_span(WarpCtx& c, int x0, int x1, px_t rgbx) {
+  x0 = max(x0, 0);
+  x1 = min(x1, c.w);
+  if (x1 <= x0) return;
+  const bool store_only = MODE == OverwriteBlend || (MODE == NormalBlend && pA(rgbx) == 255u);
+  const int lane = c.lane, mode = c.mode;
+  if (MODE == MaskBlend && pA(rgbx) == 255u) {  // :1576-1577: opaque mask leaves the span untouched
+    if (lane == 0) c.covered += (unsigned)(x1 - x0);
+    return;
+  }
+  px_t* row = c.row;
+  unsigned cnt = 0;
+  int xa = x1, xb = x1;  // [xa, xb): the 16-byte aligned middle
+  if (c.vec_ok && x1 - x0 >= 64) {
+    xa = (x0 + 3) & ~3;
+    xb = x1 & ~3;
+  }
+#pragma unroll 1
+  for (int x = x0 + lane; x < xa; x += 32) {
+    row[x] = store_only ? rgbx : span_op<MODE>(mode, row[x], rgbx);
+    cnt++;
+  }
+#pragma unroll 1
+  for (int x = xa + 4 * lane; x < xb; x += 128) {
+    uint4* p = reinterpret_cast<uint4*>(row + x);
+    uint4 v;
+    if (store_only) {
+      v = make_uint4(rgbx, rgbx, rgbx, rgbx);
+    } else {
+      v = *p;
+      v.x = span_op<MODE>(mode, v.x, rgbx); v.y = span_op<MODE>(mode, v.y, rgbx);
+      v.z = span_op<MODE>(mode, v.z, rgbx); v.w = span_op<MODE>(mode, v.w, rgbx);
+    }
+    *p = v;
+    cnt += 4;
+  }
+#pragma unroll 1
+  for (int x = xb + lane; x < x1; x += 32) {
+    row[x] = store_only ? rgbx : span_op<MODE>(mode, row[x], rgbx);
+    cnt++;
+  }
+  c.covered += cnt;
+}
+
+// One pixel of a trapezoid edge of scanline y: blender()(backdrop, rgbx * area).  Left edges (:1772-1809)
+// cover pixels [trunc(min x), ceil(max x)), right edges (:1811-1847) likewise; xa / xb are the edge's x at
+// the top and the bottom of the scanline, `first` the first pixel of the edge (where the pen starts).
+template <int MODE>
+__device__ __noinline__ void edge_px(px_t* row, int mode, int y, long long xl, bool left, float em, float eb, float xa,
+                                     float xb, long long first, px_t rgbx) {
+  const int x = (int)xl;
+  float area;
+  if (left) {
+    const bool inverted = xa < xb;
+    const float sliverStart = fminf(xa, xb), rectStart = fmaxf(xa, xb);
+    const float prevPen = (xl == first) ? sliverStart : (float)x;
+    const float prevPenY = (xl == first) ? (inverted ? (float)y : (float)(y + 1)) : (em * (float)x + eb);
+    float pen = (float)(x + 1), rightRectArea = 0.0f;
+    if (pen > rectStart) {
+      rightRectArea = pen - rectStart;
+      pen = rectStart;
+    }
+    const float penY = em * pen + eb;
+    const float run = pen - prevPen;
+    const float triangleArea = 0.5f * run * fabsf(penY - prevPenY);
+    const float rectArea = inverted ? (prevPenY - (float)y) * run : ((float)(y + 1) - prevPenY) * run;
+    area = triangleArea + rectArea + rightRectArea;
+  } else {
+    const bool inverted = xa > xb;
+    const float rectEnd = fminf(xa, xb), sliverEnd = fmaxf(xa, xb);
+    const float prevPen = (xl == first) ? rectEnd : (float)x;
+    const float prevPenY = (xl == first) ? (inverted ? (float)(y + 1) : (float)y) : (em * (float)x + eb);
+    float pen = (float)(x + 1);
+    const float leftRectArea = frac_vmath(prevPen);
+    if (pen > sliverEnd) pen = sliverEnd;
+    const float penY = em * pen + eb;
+    const float run = pen - prevPen;
+    const float triangleArea = 0.5f * run * fabsf(penY - prevPenY);
+    const float rectArea = inverted ? (penY - (float)y) * run : ((float)(y + 1) - penY) * run;
+    area = leftRectArea + triangleArea + rectArea;
+  }
+  row[x] = blend_any<MODE>(mode, row[x], mul_area(rgbx, area));  // (:1803-1809, :1841-1847)
+}
+
+PXD void smem_add(uint32_t* p, uint32_t v) {  // shared-memory reduction, no return value
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+// computeCoverage's accumulation (:1391-1431) of S spans into the coverage row, then fillCoverage
+// (:1479-1526), then the row is zero again (:1896).  Spans of one sample line are disjoint and a line adds
+// at most 255 div 5 to a pixel, so a coverage byte never exceeds 255 and word-wide adds carry nothing:
+// every span gets a lane, long interiors are handed to the whole warp.
+template <int MODE>
+__device__ __noinline__ void coverage_row(WarpCtx& c, const uint2* __restrict__ spans, int S, int startX, int pathWidth,
+                                          px_t rgbx) {
+  const int lane = c.lane, mode = c.mode;
+  const int covBase = c.vec_ok ? (startX & ~3) : startX;
+  const int covX0 = startX, covX1 = startX + pathWidth;  // coverages[] of the reference spans [covX0, covX1)
+  constexpr int sampleCoverage = 255 / 5;
+  uint8_t* cov = c.cov;
+  uint32_t* cw = reinterpret_cast<uint32_t*>(cov);
+  int pxLo = INT_MAX, pxHi = INT_MIN;
+  const uint32_t add4 = 0x01010101u * (uint32_t)sampleCoverage;
+#pragma unroll 1
+  for (int base = 0; base < S; base += 32) {
+    const int g = base + lane;
+    int i0 = 0, i1 = 0;
+    if (g < S) {
+      const uint2 sp = spans[g];
+      const int prevAt = (int)sp.x, at = (int)sp.y;
+      int fillStart = fx_integer(prevAt);
+      const bool pixelCrossed = fx_integer(at) != fx_integer(prevAt);
+      const int leftCover = pixelCrossed ? fx_trunc(prevAt) + 256 - prevAt : at - prevAt;
+      pxLo = min(pxLo, fillStart);
+      pxHi = max(pxHi, fx_integer(at) + 1);
+      if (leftCover != 0) {
+        fillStart++;
+        const int px = fx_integer(prevAt), idx = px - covBase;
+        const uint32_t v = (uint32_t)(uint8_t)fx_integer(leftCover * sampleCoverage);
+        if (px >= covX0 && px < covX1 && v) smem_add(&cw[idx >> 2], v << (8 * (idx & 3)));
+      }
+      if (pixelCrossed) {
+        const int rightCover = at - fx_trunc(at);
+        if (rightCover > 0) {
+          const int px = fx_integer(at), idx = px - covBase;
+          const uint32_t v = (uint32_t)(uint8_t)fx_integer(rightCover * sampleCoverage);
+          if (px >= covX0 && px < covX1 && v) smem_add(&cw[idx >> 2], v << (8 * (idx & 3)));
+        }
+      }
+      i0 = max(fillStart, covX0) - covBase;
+      i1 = min(fx_integer(at), covX1) - covBase;
+    }
+    // interiors: +sampleCoverage on bytes [i0, i1) as masked word adds
+    const bool some = i1 > i0;
+    const bool isLong = some && (((i1 - 1) >> 2) - (i0 >> 2) >= 6);
+    if (some && !isLong) {
+      const int wl = (i1 - 1) >> 2;
+#pragma unroll 1
+      for (int w = i0 >> 2; w <= wl; w++) {
+        uint32_t mask = 0xFFFFFFFFu;
+        if (w == (i0 >> 2)) mask &= 0xFFFFFFFFu << (8 * (i0 & 3));
+        if (w == wl) mask &= 0xFFFFFFFFu >> (8 * (3 - ((i1 - 1) & 3)));
+        smem_add(&cw[w], add4 & mask);
+      }
+    }
+    unsigned longs = __ballot_sync(0xffffffffu, isLong);
+#pragma unroll 1
+    while (longs) {
+      const int src = __ffs(longs) - 1;
+      longs &= longs - 1;
+      const int j0 = __shfl_sync(0xffffffffu, i0, src), j1 = __shfl_sync(0xffffffffu, i1, src);
+      const int wl = (j1 - 1) >> 2;
+#pragma unroll 1
+      for (int w = (j0 >> 2) + lane; w <= wl; w += 32) {
+        uint32_t mask = 0xFFFFFFFFu;
+        if (w == (j0 >> 2)) mask &= 0xFFFFFFFFu << (8 * (j0 & 3));
+        if (w == wl) mask &= 0xFFFFFFFFu >> (8 * (3 - ((j1 - 1) & 3)));
+        smem_add(&cw[w], add4 & mask);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pxLo = min(pxLo, __shfl_xor_sync(0xffffffffu, pxLo, o));
+    pxHi = max(pxHi, __shfl_xor_sync(0xffffffffu, pxHi, o));
+  }
+  __syncwarp();
+  if (MODE != MaskBlend && S == 0) return;
+
+  // fillCoverage; [pxLo, pxHi) bounds the pixels whose coverage can be non-zero (MaskBlend visits all)
   const int x0 = startX, x1 = startX + pathWidth;
+  px_t* row = c.row;
+  unsigned cnt = 0;
   if (c.vec_ok) {
     // covBase is a multiple of 4: coverage word j <-> pixels covBase + 4j .. +3 (one uint4 of the row)
-    const int words = (x1 - covBase + 3) >> 2;
-    uint32_t* cw = reinterpret_cast<uint32_t*>(c.cov);
-    for (int j = c.lane; j < words; j += 32) {
+    int words = (x1 - covBase + 3) >> 2, word0 = 0;
+    if (MODE != MaskBlend) {
+      word0 = (max(pxLo, x0) - covBase) >> 2;
+      words = min(words, (min(pxHi, x1) - covBase + 3) >> 2);
+    }
+#pragma unroll 1
+    for (int j = word0 + lane; j < words; j += 32) {
       const uint32_t cv = cw[j];
       const int x = covBase + 4 * j;
       if (MODE != MaskBlend && cv == 0u) continue;
       cw[j] = 0u;
-      uint4* p = reinterpret_cast<uint4*>(c.row + x);
+      uint4* p = reinterpret_cast<uint4*>(row + x);
       const bool full = (x >= x0) && (x + 4 <= x1);
       uint4 v;
       if ((MODE == OverwriteBlend || (MODE == NormalBlend && pA(rgbx) == 255u)) && cv == 0xFFFFFFFFu && full) {
         v = make_uint4(rgbx, rgbx, rgbx, rgbx);  // sse2.nim:552-555, 648-651
         *p = v;
-        c.covered += 4;
+        cnt += 4;
         continue;
       }
       if (MODE == MaskBlend && pA(rgbx) == 255u && cv == 0xFFFFFFFFu && full) {  // sse2.nim:750-751
-        c.covered += 4;
+        cnt += 4;
         continue;
       }
       v = *p;
       uint32_t* vp = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const uint32_t cov = (cv >> (8 * k)) & 255u;
+        const uint32_t cvk = (cv >> (8 * k)) & 255u;
         const int xx = x + k;
         if (xx < x0 || xx >= x1) continue;
-        if (cov != 0u) c.covered++;
+        if (cvk != 0u) cnt++;
         if (MODE == OverwriteBlend) {
-          if (cov != 0u) vp[k] = mul_cov_floor(rgbx, cov);
+          if (cvk != 0u) vp[k] = mul_cov_floor(rgbx, cvk);
         } else if (MODE == NormalBlend) {
-          if (cov != 0u) vp[k] = line_normal(vp[k], mul_cov_floor(rgbx, cov));
+          if (cvk != 0u) vp[k] = line_normal(vp[k], mul_cov_floor(rgbx, cvk));
         } else if (MODE == MaskBlend) {
-          vp[k] = line_mask(vp[k], mul_cov_floor(rgbx, cov));
+          vp[k] = line_mask(vp[k], mul_cov_floor(rgbx, cvk));
         } else {
-          if (cov != 0u) vp[k] = blend_any<MODE>(c.mode, vp[k], mul_cov_round(rgbx, cov));
+          if (cvk != 0u) vp[k] = blend_any<MODE>(mode, vp[k], mul_cov_round(rgbx, cvk));
         }
       }
       *p = v;
     }
   } else {
-    for (int x = x0 + c.lane; x < x1; x += 32) {
-      const uint32_t cov = c.cov[x - covBase];
-      c.cov[x - covBase] = 0;
-      if (cov != 0u) c.covered++;
+    const int xlo = MODE != MaskBlend ? max(pxLo, x0) : x0, xhi = MODE != MaskBlend ? min(pxHi, x1) : x1;
+#pragma unroll 1
+    for (int x = xlo + lane; x < xhi; x += 32) {
+      const uint32_t cvk = cov[x - covBase];
+      cov[x - covBase] = 0;
+      if (cvk != 0u) cnt++;
       if (MODE == OverwriteBlend) {
-        if (cov != 0u) c.row[x] = mul_cov_floor(rgbx, cov);
+        if (cvk != 0u) row[x] = mul_cov_floor(rgbx, cvk);
       } else if (MODE == NormalBlend) {
-        if (cov != 0u) c.row[x] = line_normal(c.row[x], mul_cov_floor(rgbx, cov));
+        if (cvk != 0u) row[x] = line_normal(row[x], mul_cov_floor(rgbx, cvk));
       } else if (MODE == MaskBlend) {
-        c.row[x] = line_mask(c.row[x], mul_cov_floor(rgbx, cov));
+        row[x] = line_mask(row[x], mul_cov_floor(rgbx, cvk));
       } else {
-        if (cov != 0u) c.row[x] = blend_any<MODE>(c.mode, c.row[x], mul_cov_round(rgbx, cov));
+        if (cvk != 0u) row[x] = blend_any<MODE>(mode, row[x], mul_cov_round(rgbx, cvk));
       }
     }
   }
+  c.covered += cnt;
   if (MODE == MaskBlend) {  // :1516-1517
     clear_span(c, 0, x0);
     clear_span(c, x1, c.w);
+  }
+}
+
+// apply_row: what the planned fill does to the canvas row (fillHits :1540-1591, the trapezoid pixels
+// :1772-1866, fillCoverage :1479-1526), for one class of blend modes.
+template <int MODE>
+__device__ __noinline__ void apply_row(WarpCtx& c, px_t rgbx, int startX, int pathWidth, int kind, int n, int pa, int pb,
+                                       const uint2* __restrict__ pay) {
+  const int lane = c.lane, W = c.w, y = c.y;
+  if (kind == PlanOutside) {
+    if (MODE == MaskBlend) clear_span(c, 0, W);
+  } else if (kind == PlanAligned) {
+    const int minX = pa, maxX = pb;
+    if (maxX > minX) {
+      if (MODE == MaskBlend) clear_span(c, 0, minX);
+      fill_span<MODE>(c, minX, maxX, rgbx);
+      if (MODE == MaskBlend) clear_span(c, maxX, W);
+    } else if (MODE == MaskBlend) {
+      clear_span(c, 0, W);
+    }
+  } else if (kind == PlanTrapezoids) {
+    px_t* row = c.row;
+    const int mode = c.mode;
+    if (MODE != MaskBlend) {
+      // The partial-coverage pixels of the sorted edges and the interiors between them are pairwise
+      // disjoint (that is what the two checks of the plan establish), so they can be written in any
+      // order: every edge gets a lane, long edges and long interiors are handed to the whole warp.
+      unsigned cnt = 0;
+#pragma unroll 1
+      for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        float em = 0.0f, eb = 0.0f, xa = 0.0f, xb = 0.0f;
+        long long xFirst = 0, pxB = 0, pxE = 0, xEnd = 0;
+        if (i < n) {
+          const uint2 mb = pay[2 * i], ab = pay[2 * i + 1];
+          em = __uint_as_float(mb.x); eb = __uint_as_float(mb.y);
+          xa = __uint_as_float(ab.x); xb = __uint_as_float(ab.y);
+          xFirst = f2ll(fminf(xa, xb));
+          xEnd = f2ll(ceilf(fmaxf(xa, xb)));
+          pxB = xFirst > 0 ? xFirst : 0;
+          pxE = xEnd < W ? xEnd : W;
+        }
+        const bool isLeft = (lane & 1) == 0;  // base is a multiple of 32: even sorted positions are left edges
+        // interior of the pair: [ceil(left max x), trunc(right min x)) (:1849-1854); the right edge is the next lane
+        const long long rightMin = __shfl_down_sync(0xffffffffu, xFirst, 1);
+        int fillBegin = 0, fillEnd = 0;
+        if (i < n && isLeft) {
+          fillBegin = clampi(xEnd, 0, W);
+          fillEnd = clampi(rightMin, 0, W);
+        }
+        const bool longEdge = pxE - pxB > 6;
+        if (!longEdge) {
+#pragma unroll 1
+          for (long long xl = pxB; xl < pxE; xl++) {
+            edge_px<MODE>(row, mode, y, xl, isLeft, em, eb, xa, xb, xFirst, rgbx);
+            cnt++;
+          }
+        }
+        unsigned todoE = __ballot_sync(0xffffffffu, longEdge);
+#pragma unroll 1
+        while (todoE) {
+          const int src = __ffs(todoE) - 1;
+          todoE &= todoE - 1;
+          const float sm_ = __shfl_sync(0xffffffffu, em, src), sb_ = __shfl_sync(0xffffffffu, eb, src);
+          const float sa_ = __shfl_sync(0xffffffffu, xa, src), sx_ = __shfl_sync(0xffffffffu, xb, src);
+          const long long sf_ = __shfl_sync(0xffffffffu, xFirst, src);
+          const long long b_ = __shfl_sync(0xffffffffu, pxB, src), e_ = __shfl_sync(0xffffffffu, pxE, src);
+#pragma unroll 1
+          for (long long xl = b_ + lane; xl < e_; xl += 32) {
+            edge_px<MODE>(row, mode, y, xl, (src & 1) == 0, sm_, sb_, sa_, sx_, sf_, rgbx);
+            cnt++;
+          }
+        }
+        const bool store_only = MODE == OverwriteBlend || (MODE == NormalBlend && pA(rgbx) == 255u);
+        const bool longFill = fillEnd - fillBegin > 12;
+        if (!longFill) {
+#pragma unroll 1
+          for (int x = fillBegin; x < fillEnd; x++) {
+            row[x] = store_only ? rgbx : span_op<MODE>(mode, row[x], rgbx);
+            cnt++;
+          }
+        }
+        unsigned todoF = __ballot_sync(0xffffffffu, longFill);
+#pragma unroll 1
+        while (todoF) {
+          const int src = __ffs(todoF) - 1;
+          todoF &= todoF - 1;
+          fill_span<MODE>(c, __shfl_sync(0xffffffffu, fillBegin, src), __shfl_sync(0xffffffffu, fillEnd, src), rgbx);
+        }
+      }
+      c.covered += cnt;
+    } else {  // MaskBlend: pair by pair, with the clears of :1856-1872
+      int filledTo = 0;
+      unsigned cnt = 0;
+#pragma unroll 1
+      for (int i = 0; i < n; i += 2) {
+        float lax = 0.f, lbx = 0.f, rax = 0.f, rbx = 0.f;
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+          const uint2 mb = pay[2 * (i + side)], ab = pay[2 * (i + side) + 1];
+          const float em = __uint_as_float(mb.x), eb = __uint_as_float(mb.y);
+          const float xa = __uint_as_float(ab.x), xb = __uint_as_float(ab.y);
+          if (side == 0) { lax = xa; lbx = xb; } else { rax = xa; rbx = xb; }
+          const long long xFirst = f2ll(fminf(xa, xb)), xEnd = f2ll(ceilf(fmaxf(xa, xb)));
+          const long long b_ = xFirst > 0 ? xFirst : 0, e_ = xEnd < W ? xEnd : W;
+#pragma unroll 1
+          for (long long xl = b_ + lane; xl < e_; xl += 32) {
+            edge_px<MODE>(row, mode, y, xl, side == 0, em, eb, xa, xb, xFirst, rgbx);
+            cnt++;
+          }
+        }
+        const int fillBegin = clampi(f2ll(ceilf(fmaxf(lax, lbx))), 0, W);
+        const int fillEnd = clampi(f2ll(truncf(fminf(rax, rbx))), 0, W);
+        fill_span<MODE>(c, fillBegin, fillEnd, rgbx);  // fillHits(..., maskClears = false) (:1849-1854)
+        const long long clearTo = f2ll(fminf(lax, lbx));
+        clear_span(c, min(filledTo, W), (int)(clearTo < W ? clearTo : W));
+        filledTo = clampi(f2ll(ceilf(fmaxf(rax, rbx))), INT_MIN / 2, W);
+      }
+      clear_span(c, min(filledTo, W), W);
+      c.covered += cnt;
+    }
+  } else if (kind == PlanCoverage) {
+    coverage_row<MODE>(c, pay, n, startX, pathWidth, rgbx);
+  } else if (kind == PlanSpans) {  // fillHits over walkInteger (:1897-1906, :1540-1591)
+    int filledTo = startX;
+#pragma unroll 1
+    for (int k = 0; k < n; k++) {
+      const uint2 sp = pay[k];
+      const int start = fx_integer((int)sp.x);
+      const int len = fx_integer((int)sp.y) - start;
+      if (len <= 0) continue;
+      if (MODE == MaskBlend) clear_span(c, filledTo, start);
+      fill_span<MODE>(c, start, start + len, rgbx);
+      filledTo = start + len;
+    }
+    if (MODE == MaskBlend) {
+      clear_span(c, 0, startX);
+      clear_span(c, filledTo, W);
+    }
   }
 }
 
@@ -518,101 +1056,22 @@ PXD void blend_coverage_row(WarpCtx& c, int startX, int pathWidth, int covBase, 
 // which addresses the canvas LINEARLY (dataIndex = width * y + x): when filledTo / clearTo are negative
 // the cleared range lies in the rows above y, which the same fill has already finished.  Those writes are
 // inside the image, so they are part of the reference's result; a warp owns one row, so after its own
-// work on row c.y it replays the mode-B decision of row yy > c.y and applies the part of row yy's clears
+// work on row c.y it looks at the trapezoid plan of row yy > c.y and applies the part of row yy's clears
 // that lands on its row.  Clears commute, so the order among the rows below does not matter.
-__device__ __noinline__ void mask_wrap_clears(WarpCtx& c, const FillHeader& H, const RasterArgs& A, int yy, uint32_t* sscr,
-                                              uint32_t* gscr) {
-  const int lane = c.lane, W = c.w;
-  int p = (yy - H.startY) / H.partitionHeight;
-  if (p > H.numPartitions - 1) p = H.numPartitions - 1;
-  const int gp = H.partBase + p;
-  const int eBeg = A.entryOff[gp];
-  const int eCnt = A.entryOff[gp + 1] - eBeg;
-  const unsigned fl = A.flags[gp];
-  const bool aa = (fl & 1u) != 0, two = (fl & 2u) != 0;
-  if (two && !aa) return;  // mode A clamps its spans to the row
-  const Entry* ent = A.entries + eBeg;
-  uint32_t* scr = eCnt > A.smemCap ? gscr : sscr;
-  const int cap = eCnt > A.smemCap ? A.scratchCap : A.smemCap;
-  int* sel = reinterpret_cast<int*>(scr);
-  float* tax = reinterpret_cast<float*>(scr + 2 * cap);
-  float* tbx = reinterpret_cast<float*>(scr + 3 * cap);
-  float* mid = reinterpret_cast<float*>(scr + 4 * cap);
-  int* idx = reinterpret_cast<int*>(scr + 5 * cap);
-  float* midS = reinterpret_cast<float*>(scr + 6 * cap);
-  int* order = reinterpret_cast<int*>(scr + 7 * cap);
-  const float scanTop = (float)yy, scanBottom = (float)(yy + 1);
-  bool allSpan = true;
-  int nsel = 0;
-  if (two) {
-    nsel = 2;
-    if (lane < 2) sel[lane] = lane;
-  } else {
-    for (int base = 0; base < eCnt; base += 32) {
-      const int i = base + lane;
-      bool take = false, partial = false;
-      if (i < eCnt) {
-        const float ay = ent[i].ay, by = ent[i].by;
-        take = !(by <= scanTop || ay >= scanBottom);
-        partial = take && (ay > scanTop || by < scanBottom);
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, take);
-      if (__any_sync(0xffffffffu, partial)) allSpan = false;
-      if (take) sel[nsel + __popc(bal & ((1u << lane) - 1u))] = i;
-      nsel += __popc(bal);
-    }
-  }
-  __syncwarp();
-  if (!allSpan || (nsel % 2) != 0) return;  // computeCoverage path: its clears stay inside the row
-  for (int s = lane; s < nsel; s += 32) {
-    const Entry e = ent[sel[s]];
-    const float xa = solve_x(e.m, e.b, scanTop), xb = solve_x(e.m, e.b, scanBottom);
-    tax[s] = xa;
-    tbx[s] = xb;
-    mid[s] = (xa + xb) * 0.5f;
-    idx[s] = s;
-  }
-  __syncwarp();
-  warp_stable_sort<float>(nsel, lane, mid, idx, midS, order);
-  __syncwarp();
-  bool ok = true;
-  for (int i = lane; i < nsel - 1; i += 32) {
-    const int l = order[i], r = order[i + 1];
-    if (f2ll(ceilf(fmaxf(tax[l], tbx[l]))) > f2ll(fminf(tax[r], tbx[r]))) ok = false;
-  }
-  ok = __all_sync(0xffffffffu, ok);
-  if (ok) {
-    int carry = 0;
-    for (int base = 0; base < nsel; base += 32) {
-      const int i = base + lane;
-      int pre = (i < nsel) ? ent[sel[order[i]]].winding : 0;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, pre, o);
-        if (lane >= o) pre += t;
-      }
-      pre += carry;
-      if (i < nsel) {
-        const bool f = should_fill(H.rule, pre);
-        if (((i & 1) == 0) ? !f : f) ok = false;
-      }
-      carry = __shfl_sync(0xffffffffu, pre, 31);
-    }
-    ok = __all_sync(0xffffffffu, ok);
-  }
-  if (!ok) return;
-  // linear pixel index of x on row yy, relative to the start of row c.y
-  const long long rowOff = (long long)(yy - c.y) * W;
+__device__ __noinline__ void mask_wrap_clears(WarpCtx& c, int yy, int n, const uint2* __restrict__ pay) {
+  const int W = c.w;
+  const long long rowOff = (long long)(yy - c.y) * W;  // linear pixel index of row yy relative to row c.y
   long long filledTo = 0;
-  for (int i = 0; i < nsel; i += 2) {
-    const int ls = order[i], rs = order[i + 1];
-    const long long clearTo = f2ll(fminf(tax[ls], tbx[ls]));
+#pragma unroll 1
+  for (int i = 0; i < n; i += 2) {
+    const uint2 l = pay[2 * i + 1], r = pay[2 * i + 3];
+    const long long clearTo = f2ll(fminf(__uint_as_float(l.x), __uint_as_float(l.y)));
     const long long a = filledTo < W ? filledTo : W, b = clearTo < W ? clearTo : W;
     if (a != W) {
       const long long x0 = rowOff + a, x1 = rowOff + b;
       if (x1 > 0 && x0 < W) clear_span(c, (int)(x0 > 0 ? x0 : 0), (int)(x1 < W ? x1 : W));
     }
-    filledTo = f2ll(ceilf(fmaxf(tax[rs], tbx[rs])));
+    filledTo = f2ll(ceilf(fmaxf(__uint_as_float(r.x), __uint_as_float(r.y))));
   }
   const long long a = filledTo < W ? filledTo : W;
   if (a != W) {
@@ -622,313 +1081,25 @@ __device__ __noinline__ void mask_wrap_clears(WarpCtx& c, const FillHeader& H, c
   __syncwarp();
 }
 
-// One fill on one scanline.  Returns nothing; all lanes of the warp participate.
-template <int MODE>
-__device__ __noinline__ void fill_row(WarpCtx& c, const FillHeader& H, const RasterArgs& A, uint32_t* scr, int cap) {
-  const int lane = c.lane, y = c.y, W = c.w;
-  const px_t rgbx = H.rgbx;
-  const int rule = H.rule;
-
-  // rows the path does not reach: only MaskBlend touches them (:1910-1912)
-  if (y < H.startY || y >= H.pathHeight) {
-    if (MODE == MaskBlend) clear_span(c, 0, W);
-    return;
-  }
-  int p = (y - H.startY) / H.partitionHeight;
-  if (p > H.numPartitions - 1) p = H.numPartitions - 1;
-  const int gp = H.partBase + p;
+PXD const uint2* job_payload(const RasterArgs& A, const FillHeader* Hp, int y, int* jobOut) {
+  const int startY = Hp->startY, ph = Hp->partitionHeight;
+  int p = (y - startY) / ph;
+  const int np = Hp->numPartitions;
+  if (p > np - 1) p = np - 1;
+  const int gp = Hp->partBase + p;
   const int eBeg = A.entryOff[gp];
   const int eCnt = A.entryOff[gp + 1] - eBeg;
-  const unsigned fl = A.flags[gp];
-  const bool aa = (fl & 1u) != 0, two = (fl & 2u) != 0;
-  const Entry* ent = A.entries + eBeg;
-
-  if (two && !aa) {  // mode A (:1644-1668): two vertical pixel-aligned lines
-    const int minX = clampi(f2ll(ent[0].ax), 0, W), maxX = clampi(f2ll(ent[1].ax), 0, W);
-    if (maxX > minX) {
-      if (MODE == MaskBlend) clear_span(c, 0, minX);
-      fill_span<MODE>(c, minX, maxX, rgbx);
-      if (MODE == MaskBlend) clear_span(c, maxX, W);
-    } else if (MODE == MaskBlend) {
-      clear_span(c, 0, W);
-    }
-    return;
-  }
-
-  int* sel = reinterpret_cast<int*>(scr);
-  int* sel2 = sel + cap;
-  float* tax = reinterpret_cast<float*>(scr + 2 * cap);
-  float* tbx = reinterpret_cast<float*>(scr + 3 * cap);
-  int* hitAt = reinterpret_cast<int*>(scr + 4 * cap);
-  int* hitW = reinterpret_cast<int*>(scr + 5 * cap);
-  int* hitAt2 = reinterpret_cast<int*>(scr + 6 * cap);
-  int* hitW2 = reinterpret_cast<int*>(scr + 7 * cap);
-
-  const float scanTop = (float)y, scanBottom = (float)(y + 1);
-  bool allSpan = true;
-  int nsel = 0;
-  const int* selC = sel;  // entry order seen by computeCoverage
-  if (two) {
-    nsel = 2;
-    if (lane < 2) sel[lane] = lane;
-  } else {  // :1681-1689
-    for (int base = 0; base < eCnt; base += 32) {
-      const int i = base + lane;
-      bool take = false, partial = false;
-      if (i < eCnt) {
-        const float ay = ent[i].ay, by = ent[i].by;
-        take = !(by <= scanTop || ay >= scanBottom);
-        partial = take && (ay > scanTop || by < scanBottom);
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, take);
-      if (__any_sync(0xffffffffu, partial)) allSpan = false;
-      if (take) sel[nsel + __popc(bal & ((1u << lane) - 1u))] = i;
-      nsel += __popc(bal);
-    }
-  }
-  __syncwarp();
-
-#ifdef PIXIE_DEBUG_ROW
-  if (y == PIXIE_DEBUG_ROW && lane == 0) printf("DBG y=%d eCnt=%d nsel=%d allSpan=%d aa=%d two=%d cap=%d\n", y, eCnt, nsel, (int)allSpan, (int)aa, (int)two, cap);
-#endif
-  if (allSpan && (nsel % 2) == 0) {  // mode B (:1691-1872)
-    float* mid = reinterpret_cast<float*>(hitAt);  // sort keys
-    for (int s = lane; s < nsel; s += 32) {
-      const Entry e = ent[sel[s]];
-      const float xa = solve_x(e.m, e.b, scanTop), xb = solve_x(e.m, e.b, scanBottom);
-      tax[s] = xa;
-      tbx[s] = xb;
-      mid[s] = (xa + xb) * 0.5f;
-      hitW[s] = s;  // payload: position in sel
-    }
-    __syncwarp();
-    float* midS = reinterpret_cast<float*>(hitAt2);
-    warp_stable_sort<float>(nsel, lane, mid, hitW, midS, hitW2);  // hitW2[r] = selected position, sorted by mid x
-    __syncwarp();
-    bool ok = true;
-    for (int i = lane; i < nsel - 1; i += 32) {  // partial-coverage areas must not overlap (:1720-1728)
-      const int l = hitW2[i], r = hitW2[i + 1];
-      const float leftMaxX = fmaxf(tax[l], tbx[l]), rightMinX = fminf(tax[r], tbx[r]);
-      if (f2ll(ceilf(leftMaxX)) > f2ll(rightMinX)) ok = false;
-    }
-    ok = __all_sync(0xffffffffu, ok);
-    if (ok) {  // only simple fill pairs (:1732-1744): prefix winding count, filled after even, empty after odd
-      int carry = 0;
-      for (int base = 0; base < nsel; base += 32) {
-        const int i = base + lane;
-        int wv = (i < nsel) ? ent[sel[hitW2[i]]].winding : 0;
-        int pre = wv;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, pre, o);
-          if (lane >= o) pre += t;
-        }
-        pre += carry;
-        if (i < nsel) {
-          const bool f = should_fill(rule, pre);
-          if (((i & 1) == 0) ? !f : f) ok = false;
-        }
-        carry = __shfl_sync(0xffffffffu, pre, 31);
-      }
-      ok = __all_sync(0xffffffffu, ok);
-    }
-#ifdef PIXIE_DEBUG_ROW
-    if (y == PIXIE_DEBUG_ROW && lane == 0) {
-      printf("DBG modeB ok=%d order:", (int)ok);
-      for (int i = 0; i < nsel; i++) printf(" %d(%.6f)", sel[hitW2[i]], midS[i]);
-      printf("\n");
-    }
-#endif
-    if (ok) {
-      int filledTo = 0;
-      for (int i = 0; i < nsel; i += 2) {
-        const int ls = hitW2[i], rs = hitW2[i + 1];
-        const Entry left = ent[sel[ls]], right = ent[sel[rs]];
-        const float lax = tax[ls], lbx = tbx[ls], rax = tax[rs], rbx = tbx[rs];
-        const float leftMaxX = fmaxf(lax, lbx), rightMinX = fminf(rax, rbx);
-        const long long leftCoverEnd = f2ll(ceilf(leftMaxX)), rightCoverBegin = f2ll(truncf(rightMinX));
-        {  // left-side partial coverage (:1772-1809)
-          const bool inverted = lax < lbx;
-          const float sliverStart = fminf(lax, lbx), rectStart = leftMaxX;
-          const long long xFirst = f2ll(sliverStart), xEnd = f2ll(ceilf(rectStart));
-          const long long xb = xFirst > 0 ? xFirst : 0, xe = xEnd < W ? xEnd : W;
-          for (long long xl = xb + lane; xl < xe; xl += 32) {
-            const int x = (int)xl;
-            const float prevPen = (xl == xFirst) ? sliverStart : (float)x;
-            const float prevPenY = (xl == xFirst) ? (inverted ? (float)y : (float)(y + 1)) : (left.m * (float)x + left.b);
-            float pen = (float)(x + 1), rightRectArea = 0.0f;
-            if (pen > rectStart) {
-              rightRectArea = pen - rectStart;
-              pen = rectStart;
-            }
-            const float penY = left.m * pen + left.b;
-            const float run = pen - prevPen;
-            const float triangleArea = 0.5f * run * fabsf(penY - prevPenY);
-            const float rectArea = inverted ? (prevPenY - (float)y) * run : ((float)(y + 1) - prevPenY) * run;
-            edge_pixel<MODE>(c, x, triangleArea + rectArea + rightRectArea, rgbx);
-          }
-        }
-        {  // right-side partial coverage (:1811-1847)
-          const bool inverted = rax > rbx;
-          const float rectEnd = rightMinX, sliverEnd = fmaxf(rax, rbx);
-          const long long xFirst = f2ll(rectEnd), xEnd = f2ll(ceilf(sliverEnd));
-          const long long xb = xFirst > 0 ? xFirst : 0, xe = xEnd < W ? xEnd : W;
-          for (long long xl = xb + lane; xl < xe; xl += 32) {
-            const int x = (int)xl;
-            const float prevPen = (xl == xFirst) ? rectEnd : (float)x;
-            const float prevPenY = (xl == xFirst) ? (inverted ? (float)(y + 1) : (float)y) : (right.m * (float)x + right.b);
-            float pen = (float)(x + 1);
-            const float leftRectArea = frac_vmath(prevPen);
-            if (pen > sliverEnd) pen = sliverEnd;
-            const float penY = right.m * pen + right.b;
-            const float run = pen - prevPen;
-            const float triangleArea = 0.5f * run * fabsf(penY - prevPenY);
-            const float rectArea = inverted ? (penY - (float)y) * run : ((float)(y + 1) - penY) * run;
-            edge_pixel<MODE>(c, x, leftRectArea + triangleArea + rectArea, rgbx);
-          }
-        }
-        const int fillBegin = clampi(leftCoverEnd, 0, W), fillEnd = clampi(rightCoverBegin, 0, W);
-        fill_span<MODE>(c, fillBegin, fillEnd, rgbx);  // fillHits(..., maskClears = false) (:1849-1854)
-        if (MODE == MaskBlend) {
-          const long long clearTo = f2ll(fminf(lax, lbx));
-          clear_span(c, min(filledTo, W), (int)(clearTo < W ? clearTo : W));
-        }
-        filledTo = clampi(f2ll(ceilf(fmaxf(rax, rbx))), INT_MIN / 2, W);
-      }
-      if (MODE == MaskBlend) clear_span(c, min(filledTo, W), W);
-      return;
-    }
-    // The reference sorts entryIndices in place (:1707-1716) before it decides whether the shortcut
-    // applies, so when it falls through, computeCoverage walks the entries in mid-x order.
-    for (int i = lane; i < nsel; i += 32) sel2[i] = sel[hitW2[i]];
-    selC = sel2;
-    __syncwarp();
-  }
-
-  // mode C: computeCoverage (:1350-1431)
-  const int quality = aa ? 5 : 1;
-  const int sampleCoverage = 255 / quality;
-  const float offset = 1.0f / (float)quality;
-  const float initialOffset = offset / 2.0f + (float)(0.0001 * 3.141592653589793238462643383279502884);
-  const int covBase = c.vec_ok ? (H.startX & ~3) : H.startX;
-  const int covX0 = H.startX, covX1 = H.startX + H.pathWidth;  // coverages[] of the reference spans [covX0, covX1)
-  float yLine = (float)y + initialOffset - offset;
-  const float wf = (float)W;
-  int numHits = 0;
-  for (int m = 0; m < quality; m++) {
-    yLine += offset;
-    numHits = 0;
-    for (int base = 0; base < nsel; base += 32) {  // :1373-1385 (entry order preserved)
-      const int s = base + lane;
-      bool hit = false;
-      int at = 0, wv = 0;
-      if (s < nsel) {
-        const Entry e = ent[selC[s]];
-        if (e.ay <= yLine && e.by >= yLine) {
-          float x = e.m == 0.0f ? e.b : (yLine - e.b) / e.m;
-          x = (x != x) ? wf : (x < wf ? x : wf);  // min(x, width.float32)
-          at = fixed32(x);
-          wv = e.winding;
-          hit = true;
-        }
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      if (hit) {
-        const int pos = numHits + __popc(bal & ((1u << lane) - 1u));
-        hitAt[pos] = at;
-        hitW[pos] = wv;
-      }
-      numHits += __popc(bal);
-    }
-    __syncwarp();
-    if (numHits > 0) warp_stable_sort<int>(numHits, lane, hitAt, hitW, hitAt2, hitW2);
-    __syncwarp();
-    // walk -> spans (re-using tax/tbx as int span arrays)
-    int* spanA = reinterpret_cast<int*>(tax);
-    int* spanB = reinterpret_cast<int*>(tbx);
-    int ns = 0;
-    if (lane == 0) ns = walk_spans(hitAt2, hitW2, numHits, rule, spanA, spanB);
-    ns = __shfl_sync(0xffffffffu, ns, 0);
-    __syncwarp();
-#ifdef PIXIE_DEBUG_ROW
-    if (y == PIXIE_DEBUG_ROW && lane == 0) {
-      printf("DBG m=%d yLine=%.9g hits:", m, yLine);
-      for (int i = 0; i < numHits; i++) printf(" %d/%d", hitAt2[i], hitW2[i]);
-      printf(" spans:");
-      for (int i = 0; i < ns; i++) printf(" [%d,%d)", spanA[i], spanB[i]);
-      printf("\n");
-    }
-#endif
-    if (aa) {
-      for (int k = 0; k < ns; k++) {  // :1391-1431
-        const int prevAt = spanA[k], at = spanB[k];
-        int fillStart = fx_integer(prevAt);
-        const bool pixelCrossed = fx_integer(at) != fx_integer(prevAt);
-        const int leftCover = pixelCrossed ? fx_trunc(prevAt) + 256 - prevAt : at - prevAt;
-        if (leftCover != 0) {
-          fillStart++;
-          if (lane == 0) {
-            const int px = fx_integer(prevAt), idx = px - covBase;
-            if (px >= covX0 && px < covX1) c.cov[idx] = (uint8_t)(c.cov[idx] + (uint8_t)fx_integer(leftCover * sampleCoverage));
-          }
-        }
-        if (pixelCrossed && lane == 0) {
-          const int rightCover = at - fx_trunc(at);
-          if (rightCover > 0) {
-            const int px = fx_integer(at), idx = px - covBase;
-            if (px >= covX0 && px < covX1) c.cov[idx] = (uint8_t)(c.cov[idx] + (uint8_t)fx_integer(rightCover * sampleCoverage));
-          }
-        }
-        // interior of the span: +sampleCoverage per pixel.  Spans of one sample line are disjoint, so
-        // a coverage byte never exceeds 255 and whole words can be added without carries.
-        const int i0 = max(fillStart, covX0) - covBase, i1 = min(fx_integer(at), covX1) - covBase;
-        if (i1 - i0 >= 96) {
-          const int a0 = (i0 + 3) & ~3, a1 = i1 & ~3;
-          for (int j = i0 + lane; j < a0; j += 32) c.cov[j] = (uint8_t)(c.cov[j] + sampleCoverage);
-          uint32_t* cw = reinterpret_cast<uint32_t*>(c.cov);
-          const uint32_t add4 = 0x01010101u * (uint32_t)sampleCoverage;
-          for (int w = (a0 >> 2) + lane; w < (a1 >> 2); w += 32) cw[w] += add4;
-          for (int j = a1 + lane; j < i1; j += 32) c.cov[j] = (uint8_t)(c.cov[j] + sampleCoverage);
-        } else {
-          for (int j = i0 + lane; j < i1; j += 32) c.cov[j] = (uint8_t)(c.cov[j] + sampleCoverage);
-        }
-        __syncwarp();
-      }
-    } else {  // fillHits over walkInteger (:1897-1906, :1540-1591)
-      int filledTo = H.startX;
-      for (int k = 0; k < ns; k++) {
-        const int start = fx_integer(spanA[k]);
-        const int len = fx_integer(spanB[k]) - start;
-        if (len <= 0) continue;
-        if (MODE == MaskBlend) clear_span(c, filledTo, start);
-        fill_span<MODE>(c, start, start + len, rgbx);
-        filledTo = start + len;
-      }
-      if (MODE == MaskBlend) {
-        clear_span(c, 0, H.startX);
-        clear_span(c, filledTo, W);
-      }
-    }
-  }
-  if (aa) {
-    __syncwarp();
-    blend_coverage_row<MODE>(c, H.startX, H.pathWidth, covBase, rgbx);
-  }
+  return A.payload + ((size_t)A.payOff[gp] + (size_t)(y - (startY + p * ph)) * (size_t)eCnt) * kPaySlots;
 }
 
 __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int warpsPerBlock = blockDim.x >> 5;
-  const int scratchWordsSmem = A.smemCap * kScratchArrays;
-  uint8_t* mine = smem_raw + (size_t)warp * ((size_t)A.covBytes + (size_t)scratchWordsSmem * 4);
-  uint8_t* cov = mine;
-  uint32_t* sscr = reinterpret_cast<uint32_t*>(mine + A.covBytes);
-  uint32_t* gscr = A.gscratch
-                       ? A.gscratch + (size_t)((A.scratchBlockBase + blockIdx.x) * warpsPerBlock + warp) * ((size_t)A.scratchCap * kScratchArrays)
-                       : nullptr;
+  uint8_t* cov = smem_raw + (size_t)warp * (size_t)A.covBytes;
   for (int i = lane * 4; i < A.covBytes; i += 128) *reinterpret_cast<uint32_t*>(cov + i) = 0u;
   __syncwarp();
+  const bool vecGlobal = (A.w & 3) == 0 && (reinterpret_cast<uintptr_t>(A.canvas) & 15) == 0;
+  const unsigned H_ = (unsigned)A.h;
 
   unsigned covered = 0;
   while (true) {
@@ -936,50 +1107,68 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
     if (lane == 0) ticket = atomicAdd(&A.counters[A.ticketSlot], 1ull);
     ticket = __shfl_sync(0xffffffffu, ticket, 0) + (unsigned long long)A.rowBegin;
     if ((long long)ticket >= A.rowEnd) break;
-    const int layer = (int)(ticket / (unsigned)A.h), y = (int)(ticket % (unsigned)A.h);
+    const unsigned t32 = (unsigned)ticket;  // layers * h < 2^31 (checked by the host)
+    const int layer = (int)(t32 / H_), y = (int)(t32 - (unsigned)layer * H_);
     WarpCtx c;
-    c.row = A.canvas + ((size_t)layer * A.h + y) * A.w;
+    c.row = A.canvas + (size_t)t32 * (size_t)A.w;
     c.w = A.w;
     c.y = y;
     c.lane = lane;
     c.cov = cov;
-    c.vec_ok = (A.w & 3) == 0 && (reinterpret_cast<uintptr_t>(A.canvas) & 15) == 0;
+    c.vec_ok = vecGlobal;
     c.covered = 0;
     const int f0 = A.layerFillBegin[layer], f1 = A.layerFillBegin[layer + 1];
+#pragma unroll 1
     for (int fb = f0; fb < f1; fb += 32) {  // 32 fills per step: which of them touch this row?
       const int fl = fb + lane;
       bool act = false;
+      // every lane fetches the plan of its own fill: no dependent loads in the ordered loop below
+      int kind = PlanOutside, n = 0, pa = 0, pb = 0, startX = 0, pathWidth = 0, bmode = 0, wrapRows = 0, rowsBelow = 0;
+      px_t rgbx = 0;
+      const uint2* pay = nullptr;
       if (fl < f1) {
         const int2 rr = A.rowRange[fl];
         act = y >= rr.x && y < rr.y;
-      }
-      unsigned todo = __ballot_sync(0xffffffffu, act);
-      while (todo) {  // ascending order = the reference's sequential order of fills
-        const int f = fb + __ffs(todo) - 1;
-        todo &= todo - 1;
-        const FillHeader H = A.fills[f];
-        // scratch: shared memory when the band's entries fit, else the global spill area
-        uint32_t* scr = sscr;
-        int cap = A.smemCap;
-        if (y >= H.startY && y < H.pathHeight) {
-          int p = (y - H.startY) / H.partitionHeight;
-          if (p > H.numPartitions - 1) p = H.numPartitions - 1;
-          const int gp = H.partBase + p;
-          const int eCnt = A.entryOff[gp + 1] - A.entryOff[gp];
-          if (eCnt > A.smemCap) {
-            scr = gscr;
-            cap = A.scratchCap;
+        if (act) {
+          const FillHeader* Hp = A.fills + fl;
+          const int sY = Hp->startY, pH = Hp->pathHeight;
+          rgbx = Hp->rgbx; bmode = Hp->mode; startX = Hp->startX; pathWidth = Hp->pathWidth;
+          if (y >= sY && y < pH) {
+            const JobHdr hd = A.jobs[A.fillJobBase[fl] + (y - sY)];
+            kind = hd.kind; n = hd.n; pa = hd.pa; pb = hd.pb;
+            pay = job_payload(A, Hp, y, nullptr);
+            wrapRows = Hp->wrapRows;
+            rowsBelow = pH - 1 - y;
           }
         }
-        c.mode = H.mode;
-        if (H.mode == NormalBlend) fill_row<NormalBlend>(c, H, A, scr, cap);
-        else if (H.mode == OverwriteBlend) fill_row<OverwriteBlend>(c, H, A, scr, cap);
-        else if (H.mode == MaskBlend) fill_row<MaskBlend>(c, H, A, scr, cap);
-        else fill_row<GenericMode>(c, H, A, scr, cap);
+      }
+      unsigned todo = __ballot_sync(0xffffffffu, act);
+#pragma unroll 1
+      while (todo) {  // ascending order = the reference's sequential order of fills
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int k_ = __shfl_sync(0xffffffffu, kind, src), n_ = __shfl_sync(0xffffffffu, n, src);
+        const int pa_ = __shfl_sync(0xffffffffu, pa, src), pb_ = __shfl_sync(0xffffffffu, pb, src);
+        const int sx_ = __shfl_sync(0xffffffffu, startX, src), pw_ = __shfl_sync(0xffffffffu, pathWidth, src);
+        const int md_ = __shfl_sync(0xffffffffu, bmode, src);
+        const px_t col_ = __shfl_sync(0xffffffffu, rgbx, src);
+        const uint2* pay_ = reinterpret_cast<const uint2*>(__shfl_sync(0xffffffffu, (unsigned long long)pay, src));
+        c.mode = md_;
+        if (md_ == NormalBlend) apply_row<NormalBlend>(c, col_, sx_, pw_, k_, n_, pa_, pb_, pay_);
+        else if (md_ == OverwriteBlend) apply_row<OverwriteBlend>(c, col_, sx_, pw_, k_, n_, pa_, pb_, pay_);
+        else if (md_ == MaskBlend) apply_row<MaskBlend>(c, col_, sx_, pw_, k_, n_, pa_, pb_, pay_);
+        else apply_row<GenericMode>(c, col_, sx_, pw_, k_, n_, pa_, pb_, pay_);
         __syncwarp();
-        if (H.wrapRows > 0 && y >= H.startY) {  // only MaskBlend fills reaching left of the canvas
-          const int yEnd = min(H.pathHeight, y + 1 + H.wrapRows);
-          for (int yy = y + 1; yy < yEnd; yy++) mask_wrap_clears(c, H, A, yy, sscr, gscr);
+        const int wr_ = __shfl_sync(0xffffffffu, wrapRows, src);
+        if (wr_ > 0) {  // only MaskBlend fills reaching left of the canvas
+          const int below = min(wr_, __shfl_sync(0xffffffffu, rowsBelow, src));
+          const FillHeader* Hp = A.fills + (fb + src);
+          const int jb = A.fillJobBase[fb + src] - Hp->startY;
+#pragma unroll 1
+          for (int yy = y + 1; yy <= y + below; yy++) {
+            const JobHdr hd = A.jobs[jb + yy];
+            if (hd.kind == PlanTrapezoids) mask_wrap_clears(c, yy, hd.n, job_payload(A, Hp, yy, nullptr));
+          }
           __syncwarp();
         }
       }
@@ -990,6 +1179,43 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(0xffffffffu, covered, o);
     if (lane == 0 && covered) atomicAdd(&A.counters[1], (unsigned long long)covered);
+  }
+}
+
+// K1c: payload offsets.  Band gp owns rows(gp) * entries(gp) entry-rows of plan payload; exclusive scan
+// over the bands (one block), total -> meta[0].
+__global__ void __launch_bounds__(1024) payload_scan_kernel(const FillHeader* __restrict__ fills, int numFills,
+                                                            const int* __restrict__ entryOff, int numParts,
+                                                            unsigned* __restrict__ payOff, unsigned long long* __restrict__ meta) {
+  __shared__ unsigned long long sums[1024];
+  const int tid = threadIdx.x;
+  const int per = (numParts + 1023) / 1024;
+  const int b = min(tid * per, numParts), e = min(b + per, numParts);
+  auto weight = [&](int gp) -> unsigned long long {
+    const FillHeader H = fills[find_fill<true>(fills, numFills, gp)];
+    const int p = gp - H.partBase;
+    const int top = H.startY + p * H.partitionHeight;
+    const int bottom = (p == H.numPartitions - 1) ? H.pathHeight : top + H.partitionHeight;
+    return (unsigned long long)(bottom - top) * (unsigned long long)(entryOff[gp + 1] - entryOff[gp]);
+  };
+  unsigned long long sum = 0;
+  for (int i = b; i < e; i++) sum += weight(i);
+  sums[tid] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const unsigned long long v = tid >= o ? sums[tid - o] : 0;
+    __syncthreads();
+    sums[tid] += v;
+    __syncthreads();
+  }
+  unsigned long long run = sums[tid] - sum;
+  for (int i = b; i < e; i++) {
+    payOff[i] = (unsigned)run;
+    run += weight(i);
+  }
+  if (tid == 1023) {
+    payOff[numParts] = (unsigned)sums[1023];
+    meta[0] = sums[1023];
   }
 }
 
@@ -1027,7 +1253,8 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   L.w = w; L.h = h; L.layers = layers; L.numFills = numFills;
   std::vector<FillHeader> fills(numFills);
   std::vector<int> layerBegin(layers + 1, 0);
-  int64_t numPartsTotal = 0;
+  int64_t numPartsTotal = 0, jobsTotal = 0;  // jobs: (fill, scanline) pairs inside the paths' rows
+  std::vector<int> jobBase(numFills + 1, 0);
   int prevLayer = 0;
   double tBounds = 0;
   for (int k = 0; k < numFills; k++) {
@@ -1041,6 +1268,7 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
     const int n = s1 - s0;
     FillHeader& H = fills[k];
     memset(&H, 0, sizeof(H));
+    jobBase[k] = (int)jobsTotal;
     H.segBegin = s0; H.segCount = n; H.rgbx = rgbx[k]; H.rule = rule[k]; H.mode = mode[k];
     if (n == 0) {  // empty path: nothing is drawn (the reference's tiger has one, "M-65.4,9z")
       H.active = 0;
@@ -1110,33 +1338,40 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
       H.wrapRows = reach >= (double)h ? h : (int)reach;
     }
     numPartsTotal += numPartitions;
-    if (numPartsTotal > 0x3fffffff) return fail_pixie("command list too large");
+    jobsTotal += height;
+    if (numPartsTotal > 0x3fffffff || jobsTotal > 0x3fffffff) return fail_pixie("command list too large");
   }
   for (int l = 1; l <= layers; l++) layerBegin[l] = std::max(layerBegin[l], layerBegin[l - 1]);
+  jobBase[numFills] = (int)jobsTotal;
+  L.totalJobs = (int)jobsTotal;
+  if ((long long)layers * h > 0x7fffffffll) return fail_pixie("canvas stack too large");
 
   const double t1 = now_ms();
   const int64_t numSegs = numFills ? segOff[numFills] : 0;
   L.numSegs = numSegs;
   L.numParts = numPartsTotal;
 
-  // raster launch geometry: persistent warps, one (layer, row) ticket at a time
+  // launch geometry: plan_kernel strides over the jobs, raster_kernel's persistent warps take one
+  // (layer, row) ticket at a time; both sized to what is resident on the GPU
   L.covBytes = ((w + 7) & ~3) + 4;             // coverage row, word aligned, with the covBase slack
-  L.smemCap = 64;                              // entries per band handled from shared memory
-  while (L.smemCap > 8 && (size_t)L.covBytes + (size_t)L.smemCap * kScratchArrays * 4 > 24 * 1024) L.smemCap /= 2;
-  size_t perWarp = (size_t)L.covBytes + (size_t)L.smemCap * kScratchArrays * 4;
+  L.smemCap = 64;                              // entries per band planned from shared memory
   L.warpsPerBlock = 8;
-  while (L.warpsPerBlock > 1 && perWarp * L.warpsPerBlock > 96 * 1024) L.warpsPerBlock /= 2;
-  if (perWarp * L.warpsPerBlock > 200 * 1024) return fail_pixie("canvas too wide for the shared-memory coverage row");
-  L.smemBytes = perWarp * L.warpsPerBlock;
+  while (L.warpsPerBlock > 1 && (size_t)L.covBytes * L.warpsPerBlock > 96 * 1024) L.warpsPerBlock /= 2;
+  if ((size_t)L.covBytes * L.warpsPerBlock > 200 * 1024) return fail_pixie("canvas too wide for the shared-memory coverage row");
+  L.smemBytes = (size_t)L.covBytes * L.warpsPerBlock;
+  L.planSmem = (size_t)L.smemCap * kScratchArrays * 4 * 8;
   const long long totalRows = (long long)layers * h;
   if (L.smemBytes > 48 * 1024)
     PX_CUDA(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes));
-  int blocksPerSm = 1;  // resident CTAs per SM for this shared-memory footprint: one wave, rows by ticket
+  int blocksPerSm = 1;
   PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, raster_kernel, L.warpsPerBlock * 32, L.smemBytes));
   blocksPerSm = std::max(1, blocksPerSm);
   long long wantBlocks = (totalRows + L.warpsPerBlock - 1) / L.warpsPerBlock;
-  L.rasterBlocks = (int)std::min<long long>(wantBlocks, (long long)r.num_sms * blocksPerSm);
-  L.rasterBlocks = std::max(L.rasterBlocks, 1);
+  L.rasterBlocks = (int)std::max<long long>(1, std::min<long long>(wantBlocks, (long long)r.num_sms * blocksPerSm));
+  int planPerSm = 1;
+  PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&planPerSm, plan_kernel, 256, L.planSmem));
+  planPerSm = std::max(1, planPerSm);
+  L.planBlocks = (int)std::max<long long>(1, std::min<long long>((jobsTotal + 7) / 8, (long long)r.num_sms * planPerSm));
 
   // Device block A.  The host-written part (segments, windings, headers, row ranges, layer table)
   // is contiguous so that it moves with a single H2D copy from a staging buffer; band counts,
@@ -1149,9 +1384,11 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   const size_t oFills = off;     off = al(off + fills.size() * sizeof(FillHeader));
   const size_t oRowRange = off;  off = al(off + fills.size() * sizeof(int2));
   const size_t oLayer = off;     off = al(off + layerBegin.size() * 4);
+  const size_t oJobBase = off;   off = al(off + jobBase.size() * 4);
   const size_t h2dBytes = off;
   const size_t oEntryOff = off;  off = al(off + (P + 1) * 4);   // band counts, scanned in place to offsets
   const size_t oFlags = off;     off = al(off + std::max<size_t>(1, P));
+  const size_t oPayOff = off;    off = al(off + (P + 1) * 4);   // plan payload offset of each band
   const size_t oCounters = off;  off = al(off + 128);           // [0] row ticket, [1] covered px, [2] entries, [3] max, [4..] band tickets
   const size_t totalA = off;
 
@@ -1185,6 +1422,7 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
     }
   }
   memcpy(stage + oLayer, layerBegin.data(), layerBegin.size() * 4);
+  memcpy(stage + oJobBase, jobBase.data(), jobBase.size() * 4);
   PX_CUDA(cudaMemcpyAsync(L.block, stage, h2dBytes, cudaMemcpyHostToDevice, r.stream));
   if (arena) {
     if (int rc = staging_release()) return rc;
@@ -1194,6 +1432,8 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   L.fills = (FillHeader*)(L.block + oFills);
   L.rowRange = (int2*)(L.block + oRowRange);
   L.layerFillBegin = (int*)(L.block + oLayer);
+  L.fillJobBase = (int*)(L.block + oJobBase);
+  L.payOff = (unsigned*)(L.block + oPayOff);
   L.entryOff = (int*)(L.block + oEntryOff);
   L.flags = L.block + oFlags;
   L.counters = (unsigned long long*)(L.block + oCounters);
@@ -1201,7 +1441,7 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
 
   // K1a/K1b on the device: how many entries each band gets (partitionRange :1201-1213), exclusive
   // scan to entry offsets, total and maximum -> 16 bytes back to the host to size block B.
-  long long meta[2] = {0, 2};
+  long long meta[4] = {0, 2, 0, 0};  // entries, max entries per band, payload entry-rows
   if (P > 0) {
     PX_CUDA(cudaMemsetAsync(L.entryOff, 0, (P + 1) * 4, r.stream));
     const int cblocks = (int)std::min<int64_t>((numSegs + 255) / 256, (int64_t)r.num_sms * 8);
@@ -1209,17 +1449,23 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
     PX_LAUNCHED();
     scan_kernel<<<1, 1024, 0, r.stream>>>(L.entryOff, (int)P, L.counters + 2);
     PX_LAUNCHED();
-    PX_CUDA(cudaMemcpyAsync(meta, L.counters + 2, 16, cudaMemcpyDeviceToHost, r.stream));
+    payload_scan_kernel<<<1, 1024, 0, r.stream>>>(L.fills, numFills, L.entryOff, (int)P, L.payOff, L.counters + 4);
+    PX_LAUNCHED();
+    PX_CUDA(cudaMemcpyAsync(meta, L.counters + 2, 24, cudaMemcpyDeviceToHost, r.stream));
   }
   PX_CUDA(cudaStreamSynchronize(r.stream));  // also retires the pageable staging vector of owned lists
   if (meta[0] > 0x7fffffffll) return fail_pixie("command list too large");
   L.numEntries = meta[0];
   L.maxEntries = (int)std::max<long long>(2, meta[1]);
   L.scratchWords = L.maxEntries > L.smemCap ? L.maxEntries * kScratchArrays : 0;
+  if (meta[2] > 0xffffffffll) return fail_pixie("command list too large");
 
-  // Device block B: band entries + the per-warp spill scratch for bands with more entries than fit in smem.
+  // Device block B: band entries, the plans (header per job + payload per entry-row) and plan_kernel's
+  // per-warp spill scratch for bands with more entries than fit in shared memory.
   const size_t entriesBytes = al(std::max<size_t>(1, (size_t)L.numEntries) * sizeof(Entry));
-  const size_t totalB = entriesBytes + al((size_t)L.rasterBlocks * L.warpsPerBlock * L.scratchWords * 4);
+  const size_t jobsBytes = al(std::max<size_t>(1, (size_t)L.totalJobs) * sizeof(JobHdr));
+  const size_t payBytes = al(std::max<size_t>(1, (size_t)meta[2]) * kPaySlots * sizeof(uint2));
+  const size_t totalB = entriesBytes + jobsBytes + payBytes + al((size_t)L.planBlocks * 8 * L.scratchWords * 4);
   if (arena) {
     void* blk;
     if (int rc = get_scratch(4, totalB, &blk)) return rc;
@@ -1228,7 +1474,9 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
     PX_CUDA(cudaMalloc(&L.blockB, totalB));
   }
   L.entries = (Entry*)L.blockB;
-  L.scratch = L.scratchWords ? (uint32_t*)(L.blockB + entriesBytes) : nullptr;
+  L.jobs = (JobHdr*)(L.blockB + entriesBytes);
+  L.payload = (uint2*)(L.blockB + entriesBytes + jobsBytes);
+  L.scratch = L.scratchWords ? (uint32_t*)(L.blockB + entriesBytes + jobsBytes + payBytes) : nullptr;
   if (g_trace)
     fprintf(stderr, "[pixie_cuda] build_list: host plan %.3f ms (bounds %.3f), stage + device count/scan + readback %.3f ms "
             "(%zu B staged, blocks %zu + %zu B, %lld entries, max %d per band)\n",
@@ -1262,6 +1510,14 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
   A.flags = L.flags; A.gscratch = L.scratch; A.counters = L.counters;
   A.smemCap = L.smemCap; A.scratchCap = L.maxEntries; A.covBytes = L.covBytes;
   A.countCovered = covered_px ? 1 : 0;
+  A.numFills = L.numFills;
+  A.fillJobBase = L.fillJobBase; A.payOff = L.payOff; A.jobs = L.jobs; A.payload = L.payload; A.totalJobs = L.totalJobs;
+  A.rowBegin = 0; A.rowEnd = 0; A.ticketSlot = 0;
+  if (L.totalJobs > 0) {
+    ProfScope ps(kProfPlan);
+    plan_kernel<<<L.planBlocks, 256, L.planSmem, r.stream>>>(A);
+  }
+  PX_LAUNCHED();
   static size_t configured = 0;
   if (L.smemBytes > 48 * 1024 && configured < L.smemBytes) {
     PX_CUDA(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes));
@@ -1269,7 +1525,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
   }
   const long long totalRows = (long long)L.layers * L.h;
   if (!host_pixels) {
-    A.rowBegin = 0; A.rowEnd = totalRows; A.ticketSlot = 0; A.scratchBlockBase = 0;
+    A.rowBegin = 0; A.rowEnd = totalRows; A.ticketSlot = 0;
     {
       ProfScope ps(kProfRaster);
       raster_kernel<<<L.rasterBlocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
@@ -1293,7 +1549,6 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
       A.rowBegin = totalRows * b / K;
       A.rowEnd = totalRows * (b + 1) / K;
       A.ticketSlot = 4 + b;
-      A.scratchBlockBase = b * gridB;
       if (A.rowEnd <= A.rowBegin) continue;
       PX_CUDA(cudaStreamWaitEvent(r.band_stream[b], r.band_start, 0));
       raster_kernel<<<gridB, L.warpsPerBlock * 32, L.smemBytes, r.band_stream[b]>>>(A);
@@ -1353,7 +1608,7 @@ int pixie_cuda_cmdlist_info(pixie_cmdlist_t list, int64_t* numSegs, int64_t* num
   if (numSegs) *numSegs = it->second.numSegs;
   if (numParts) *numParts = it->second.numParts;
   if (numEntries) *numEntries = it->second.numEntries;
-  if (launches) *launches = it->second.numParts > 0 ? 2 : 1;
+  if (launches) *launches = it->second.numParts > 0 ? 3 : 1;
   return 0;
 }
 

@@ -344,7 +344,7 @@ def upload_async(image: DeviceImage, pinned: PinnedBuffer):
     check(lib().pixie_cuda_image_upload_async(image.handle, pinned.ptr))
 
 
-PROF_PARTITION, PROF_RASTER, PROF_BLUR_X, PROF_BLUR_Y, PROF_BLEND, PROF_SPREAD = range(6)
+PROF_PARTITION, PROF_RASTER, PROF_BLUR_X, PROF_BLUR_Y, PROF_BLEND, PROF_SPREAD, PROF_PLAN = range(7)
 
 
 def set_profiling(enabled: bool):
