@@ -337,7 +337,7 @@ def run_ours(args):
         cl.run(img)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    step_ms, part_ms, rast_ms = [], [], []
+    step_ms, part_ms, plan_ms, rast_ms = [], [], [], []
     launches0 = dev.launch_count()
     launches_timed = 0
     barrier()
@@ -351,6 +351,7 @@ def run_ours(args):
         step_ms.append(dev.timer_end())
         launches_timed += dev.launch_count() - l0
         part_ms.append(dev.profile_read(dev.PROF_PARTITION))
+        plan_ms.append(dev.profile_read(dev.PROF_PLAN))
         rast_ms.append(dev.profile_read(dev.PROF_RASTER))
     barrier()
     total_ms = max_over_ranks(sum(step_ms))
@@ -399,7 +400,7 @@ def run_ours(args):
                 # `ncu --set full` capture summarised in profiles/r01_raster_metrics.txt (canvas stays in the 126 MB L2)
                 "traffic": 39995392 if size == 4096 else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(rast, 4),
-                "partition_kernel_ms": round(part, 4), "share_of_step": round(rast / statistics.mean(step_ms), 3),
+                "partition_kernel_ms": round(part, 4), "plan_kernel_ms": round(statistics.mean(plan_ms), 4), "share_of_step": round(rast / statistics.mean(step_ms), 3),
                 "note": "305 order-dependent fills: latency/occupancy-bound, not bandwidth-bound (SURVEY.md 7.1)"}
 
     cpu = None
