@@ -41,7 +41,7 @@ struct Runtime {
   cudaEvent_t staging_done = nullptr;  // recorded after the H2D copy that reads `pinned`
   bool staging_busy = false;
   // row-band streams of pixie_cuda_render_batch_host (rasterise band b while band b-1 goes to the host)
-  static constexpr int kBands = 4;
+  static constexpr int kBands = 8;
   cudaStream_t band_stream[kBands] = {};
   cudaEvent_t band_done[kBands] = {};
   cudaEvent_t band_start = nullptr;

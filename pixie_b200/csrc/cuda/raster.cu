@@ -61,11 +61,18 @@ struct CmdList {
   JobHdr* jobs = nullptr;
   uint2* payload = nullptr;
   int totalJobs = 0, planBlocks = 0;
+  // row bands of pixie_cuda_render_batch_host: band b plans + rasterises rows [h*b/bands, h*(b+1)/bands)
+  int bands = 1;
+  int* bandJobBase = nullptr;              // [bands][numFills + 1] job prefix of each band
+  int bandJobs[Runtime::kBands] = {};
+  unsigned* scratchSlots = nullptr;        // bitmap: spill-scratch block slots in use
+  int scratchSlotCount = 0;
   size_t planSmem = 0;
   int* entryOff = nullptr;
   int* layerFillBegin = nullptr;
   Entry* entries = nullptr;
   uint8_t* flags = nullptr;
+  uint32_t* ranges = nullptr;  // per segment: first | last << 16 band it touches (count_kernel)
   uint32_t* scratch = nullptr;  // per-warp spill area when a band has more entries than fit in smem
   unsigned long long* counters = nullptr;  // [0] row ticket, [1] covered px
   int rasterBlocks = 0, warpsPerBlock = 0, scratchWords = 0, covBytes = 0, smemCap = 0;
@@ -131,25 +138,38 @@ PXD int find_fill(const FillHeader* __restrict__ fills, int numFills, int v) {
   return lo - 1;
 }
 
-// K1a: entries per band (one thread per segment; order is irrelevant for counting)
+// K1a: entries per band (one thread per segment; order is irrelevant for counting).  The band range of
+// every segment (partitionRange :1201-1213) is kept as `atP | toP << 16` for partition_kernel, whose band
+// warps then scan 4 bytes per segment instead of the segment itself; kNoBand marks segments that belong to
+// no band (inactive fills) and kWideBands fills with more than 65535 bands (recomputed from the segment).
+constexpr uint32_t kNoBand = 0x0000FFFFu;  // atP = 65535 > toP = 0
+constexpr int kMaxPackedBands = 65535;
+PXD void band_range(const FillHeader& H, float ay, float by, unsigned& atP, unsigned& toP) {
+  const float startYf = (float)(unsigned)H.startY;
+  const unsigned ph = (unsigned)H.partitionHeight, lastP = (unsigned)(H.numPartitions - 1);
+  atP = min(__float2uint_rz(fmaxf(0.0f, ay - startYf)) / ph, lastP);
+  toP = min(__float2uint_rz(fmaxf(0.0f, by - startYf)) / ph, lastP);
+}
 __global__ void __launch_bounds__(256) count_kernel(const FillHeader* __restrict__ fills, int numFills,
-                                                    const float4* __restrict__ segs, int numSegs, int* __restrict__ cnt) {
+                                                    const float4* __restrict__ segs, int numSegs, int* __restrict__ cnt,
+                                                    uint32_t* __restrict__ ranges) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < numSegs; i += gridDim.x * blockDim.x) {
     int f = find_fill<false>(fills, numFills, i);
     while (f > 0 && fills[f].segCount == 0) f--;  // empty fills share their segBegin with the next one
     const FillHeader H = fills[f];
-    if (!H.active || H.numPartitions <= 0 || i >= H.segBegin + H.segCount) continue;
+    if (!H.active || H.numPartitions <= 0 || i >= H.segBegin + H.segCount) {
+      ranges[i] = kNoBand;
+      continue;
+    }
     if (H.numPartitions == 1) {
       atomicAdd(&cnt[H.partBase], 1);
+      ranges[i] = 0u;
       continue;
     }
     const float4 s = segs[i];
-    const float startYf = (float)(unsigned)H.startY;
-    const unsigned ph = (unsigned)H.partitionHeight, lastP = (unsigned)(H.numPartitions - 1);
-    unsigned atP = __float2uint_rz(fmaxf(0.0f, s.y - startYf)) / ph;
-    unsigned toP = __float2uint_rz(fmaxf(0.0f, s.w - startYf)) / ph;
-    atP = min(atP, lastP);
-    toP = min(toP, lastP);
+    unsigned atP, toP;
+    band_range(H, s.y, s.w, atP, toP);
+    ranges[i] = H.numPartitions <= kMaxPackedBands ? (atP | (toP << 16)) : kNoBand;
     for (unsigned p = atP; p <= toP; p++) atomicAdd(&cnt[H.partBase + (int)p], 1);
   }
 }
@@ -195,7 +215,8 @@ __global__ void __launch_bounds__(1024) scan_kernel(int* __restrict__ cnt, int n
 __global__ void __launch_bounds__(256) partition_kernel(const FillHeader* __restrict__ fills, int numFills,
                                                         const int* __restrict__ entryOff,
                                                         const float4* __restrict__ segs,
-                                                        const int16_t* __restrict__ wind, Entry* __restrict__ entries,
+                                                        const int16_t* __restrict__ wind,
+                                                        const uint32_t* __restrict__ ranges, Entry* __restrict__ entries,
                                                         uint8_t* __restrict__ flags, int numParts) {
   const int lane = threadIdx.x & 31;
   const int warpsTotal = (gridDim.x * blockDim.x) >> 5;
@@ -205,46 +226,40 @@ __global__ void __launch_bounds__(256) partition_kernel(const FillHeader* __rest
     const int top = H.startY + p * H.partitionHeight;
     const int bottom = (p == H.numPartitions - 1) ? H.pathHeight : top + H.partitionHeight;
     const float topf = (float)top, botf = (float)bottom;
-    const float startYf = (float)(unsigned)H.startY;
-    const unsigned ph = (unsigned)H.partitionHeight, lastP = (unsigned)(H.numPartitions - 1);
+    const bool packed = H.numPartitions <= kMaxPackedBands;
     const int outBase = entryOff[gp];
     int out = outBase;
     bool aa = false;
-    constexpr int kChunks = 4;  // 128 segments in flight per iteration: the scan is latency bound
+    constexpr int kChunks = 8;  // 256 segments in flight per iteration: the scan is latency bound
     for (int base0 = 0; base0 < H.segCount; base0 += 32 * kChunks) {
-      float4 sv[kChunks];
-      int wv[kChunks];
+      uint32_t rv[kChunks];
 #pragma unroll
       for (int q = 0; q < kChunks; q++) {
         const int i = base0 + q * 32 + lane;
-        sv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        wv[q] = 0;
+        rv[q] = kNoBand;
         if (i < H.segCount) {
-          sv[q] = segs[H.segBegin + i];
-          wv[q] = (int)wind[H.segBegin + i];
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < kChunks; q++) {
-        const int i = base0 + q * 32 + lane;
-        const float4 s = sv[q];
-        bool touches = false;
-        if (i < H.segCount) {
-          if (H.numPartitions == 1) {
-            touches = true;
-          } else {  // partitionRange (:1201-1213)
-            unsigned atP = __float2uint_rz(fmaxf(0.0f, s.y - startYf)) / ph;
-            unsigned toP = __float2uint_rz(fmaxf(0.0f, s.w - startYf)) / ph;
-            atP = min(atP, lastP);
-            toP = min(toP, lastP);
-            touches = (unsigned)p >= atP && (unsigned)p <= toP;
+          if (packed) {
+            rv[q] = ranges[H.segBegin + i];
+          } else {  // more bands than the packed form holds: partitionRange from the segment itself
+            const float4 s = segs[H.segBegin + i];
+            unsigned atP, toP;
+            band_range(H, s.y, s.w, atP, toP);
+            rv[q] = ((unsigned)p >= atP && (unsigned)p <= toP) ? ((unsigned)p & 0xFFFFu) * 0x00010001u : kNoBand;
           }
         }
+      }
+      const unsigned pk = (unsigned)p & 0xFFFFu;
+#pragma unroll
+      for (int q = 0; q < kChunks; q++) {
+        const int i = base0 + q * 32 + lane;
+        const unsigned atP = rv[q] & 0xFFFFu, toP = rv[q] >> 16;
+        const bool touches = pk >= atP && pk <= toP;
         const unsigned bal = __ballot_sync(0xffffffffu, touches);
         if (touches) {
+          const float4 s = segs[H.segBegin + i];
           Entry e;  // initPartitionEntry (:1127-1135)
           e.ax = s.x; e.ay = s.y; e.bx = s.z; e.by = s.w;
-          e.winding = wv[q];
+          e.winding = (int)wind[H.segBegin + i];
           e.pad = 0;
           e.m = 0.0f;
           e.b = 0.0f;
@@ -326,6 +341,10 @@ struct RasterArgs {
   const Entry* entries;
   const uint8_t* flags;
   const int* fillJobBase;      // [numFills + 1] first job of each fill; job = fillJobBase[f] + (y - startY)
+  const int* planJobBase;      // [numFills + 1] the same restricted to the rows [planY0, planY1) of this plan launch
+  int planY0, planJobs;        // jobs of this plan launch (whole list: planJobBase = fillJobBase, planY0 = 0)
+  unsigned* scratchSlots;      // bitmap of the spill-scratch block slots in use (plan launches of several row
+  int scratchSlotCount;        // bands run concurrently and share one pool sized for the resident blocks)
   const unsigned* payOff;      // [numParts + 1] payload offset of each band, in entry-rows
   JobHdr* jobs;
   uint2* payload;              // kPaySlots 8-byte slots per entry-row
@@ -423,17 +442,34 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warpsPerBlock = blockDim.x >> 5;
   uint32_t* sscr = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * A.smemCap * kScratchArrays;
-  uint32_t* gscr = A.gscratch ? A.gscratch + (size_t)(blockIdx.x * warpsPerBlock + warp) * ((size_t)A.scratchCap * kScratchArrays)
-                              : nullptr;
+  // Spill scratch for bands with more entries than fit in shared memory: a block claims one slot of a pool
+  // that has as many slots as plan_kernel blocks can be resident on the GPU, whatever launch they belong to.
+  __shared__ int s_slot;
+  uint32_t* gscr = nullptr;
+  if (A.gscratch) {
+    if (threadIdx.x == 0) {
+      const int words = (A.scratchSlotCount + 31) >> 5;
+      int wi = blockIdx.x % words, bit = (blockIdx.x / words) & 31, slot = -1;
+      while (slot < 0) {
+        const int cand = wi * 32 + bit;
+        if (cand < A.scratchSlotCount && !(atomicOr(A.scratchSlots + wi, 1u << bit) & (1u << bit))) slot = cand;
+        else if (++bit == 32) { bit = 0; wi = (wi + 1) % words; }
+      }
+      s_slot = slot;
+    }
+    __syncthreads();
+    gscr = A.gscratch + (size_t)(s_slot * warpsPerBlock + warp) * ((size_t)A.scratchCap * kScratchArrays);
+  }
   const int W = A.w;
   const float wf = (float)W;
   const int warpsTotal = gridDim.x * warpsPerBlock;
 #pragma unroll 1
-  for (int job = blockIdx.x * warpsPerBlock + warp; job < A.totalJobs; job += warpsTotal) {
-    const int f = find_fill_by_job(A.fillJobBase, A.numFills, job);
+  for (int bj = blockIdx.x * warpsPerBlock + warp; bj < A.planJobs; bj += warpsTotal) {
+    const int f = find_fill_by_job(A.planJobBase, A.numFills, bj);
     const FillHeader* Hp = A.fills + f;
     const int startY = Hp->startY, rule = Hp->rule;
-    const int y = startY + (job - A.fillJobBase[f]);
+    const int y = max(startY, A.planY0) + (bj - A.planJobBase[f]);
+    const int job = A.fillJobBase[f] + (y - startY);
     const int ph = Hp->partitionHeight;
     int p = (y - startY) / ph;
     if (p > Hp->numPartitions - 1) p = Hp->numPartitions - 1;
@@ -633,6 +669,10 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
       }
     }
     if (lane == 0) A.jobs[job] = hdr;
+  }
+  if (A.gscratch) {
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAnd(A.scratchSlots + (s_slot >> 5), ~(1u << (s_slot & 31)));
   }
 }
 
@@ -1232,6 +1272,15 @@ static inline uint32_t f2u_host(float f) {  // matches __float2uint_rz (saturati
   return (uint32_t)f;
 }
 
+// Row bands of pixie_cuda_render_batch_host.  The copy engine can start once the first band is rasterised and
+// is the bottleneck from then on, so the first bands are short (their latency is what the whole call waits
+// for) and the rest share the canvas evenly: edges in 32nds of the height.
+static int band_edge(long long rows, int b, int K) {
+  static const int edges8[9] = {0, 1, 3, 7, 12, 17, 22, 27, 32};
+  if (K == Runtime::kBands && K == 8) return (int)(rows * edges8[b] / 32);
+  return (int)(rows * b / K);
+}
+
 static void free_list(CmdList& L) {
   if (L.owned && L.block) cudaFree(L.block);
   if (L.owned && L.blockB) cudaFree(L.blockB);
@@ -1243,7 +1292,7 @@ static double now_ms() {
 }
 static const bool g_trace = getenv("PIXIE_CUDA_TRACE") != nullptr;
 
-static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numFills, const int32_t* layerOf,
+static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layers, int numFills, const int32_t* layerOf,
                       const float* seg, const int16_t* wind, const int32_t* segOff, const uint32_t* rgbx,
                       const uint8_t* rule, const uint8_t* mode) {
   Runtime& r = rt();
@@ -1257,6 +1306,35 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   std::vector<int> jobBase(numFills + 1, 0);
   int prevLayer = 0;
   double tBounds = 0;
+  const int64_t numSegs = numFills ? segOff[numFills] : 0;
+  if (numSegs < 0 || numSegs > 0x7fffffffll) return fail_pixie("invalid seg_offsets");
+  L.numSegs = numSegs;
+  L.bands = (bands > 1 && layers == 1) ? std::min(bands, (int)Runtime::kBands) : 1;
+
+  // Device block A.  The host-written part (segments, windings, headers, row ranges, layer table) is
+  // contiguous and goes through a staging buffer; the segments are written into it by the same pass that
+  // computes the bounds of each path, and start their way to the device before the headers are finished.
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t off = 0;
+  const size_t oSegs = off;      off = al(off + (size_t)numSegs * 16);
+  const size_t oWind = off;      off = al(off + (size_t)numSegs * 2);
+  const size_t oFills = off;     off = al(off + fills.size() * sizeof(FillHeader));
+  const size_t oRowRange = off;  off = al(off + fills.size() * sizeof(int2));
+  const size_t oLayer = off;     off = al(off + layerBegin.size() * 4);
+  const size_t oJobBase = off;   off = al(off + jobBase.size() * 4);
+  const size_t oBandJobs = off;  off = al(off + (L.bands > 1 ? (size_t)L.bands * jobBase.size() * 4 : 0));
+  const size_t h2dBytes = off;
+  uint8_t* stage = nullptr;
+  std::vector<uint8_t> pageable;
+  if (arena) {  // per-call lists: library-owned growing arena + pinned staging, no malloc/free per call
+    void* pin;
+    if (int rc = staging_acquire(h2dBytes, &pin)) return rc;
+    stage = (uint8_t*)pin;
+  } else {
+    pageable.resize(h2dBytes + 16);
+    stage = pageable.data();
+    stage += (16 - (reinterpret_cast<uintptr_t>(stage) & 15)) & 15;
+  }
   for (int k = 0; k < numFills; k++) {
     const int layer = layerOf ? layerOf[k] : 0;
     if (layer < prevLayer || layer >= layers || layer < 0) return fail_pixie("layer_of_fill must be non-decreasing and < layers");
@@ -1264,7 +1342,7 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
     layerBegin[layer + 1] = k + 1;
     if (mode[k] >= NumBlendModes || rule[k] > 1) return fail_pixie("invalid blend mode / winding rule");
     const int s0 = segOff[k], s1 = segOff[k + 1];
-    if (s1 < s0) return fail_pixie("seg_offsets must be non-decreasing");
+    if (s1 < s0 || s0 < 0 || s1 > numSegs) return fail_pixie("seg_offsets must be non-decreasing");
     const int n = s1 - s0;
     FillHeader& H = fills[k];
     memset(&H, 0, sizeof(H));
@@ -1279,14 +1357,42 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
     float xMin = INFINITY, xMax = -INFINITY, yMin = INFINITY, yMax = -INFINITY;
     const double tb0 = g_trace ? now_ms() : 0;
     // Nim's min/max (`if x <= y: x else: y`) == MINPS/MAXPS(acc, v) including their NaN behaviour
-    // (second operand when unordered); one 4-lane min + max per segment {at.x, at.y, to.x, to.y}.
+    // (second operand when unordered); one 4-lane min + max per segment {at.x, at.y, to.x, to.y}, and the
+    // segment goes to the staging buffer on the way (streaming stores: the DMA engine is the only reader).
     {
       const float* sp = seg + 4 * (size_t)s0;
+      float* dp = reinterpret_cast<float*>(stage + oSegs) + 4 * (size_t)s0;
       __m128 vmin = _mm_set1_ps(INFINITY), vmax = _mm_set1_ps(-INFINITY);
-      for (int i = 0; i < n; i++, sp += 4) {
+      // four independent min/max chains (the loop is bound by their latency); without NaNs the result does
+      // not depend on the order, with a NaN anywhere the path is folded again in the reference's order
+      __m128 mn1 = vmin, mn2 = vmin, mn3 = vmin, mx1 = vmax, mx2 = vmax, mx3 = vmax, nan = _mm_setzero_ps();
+      int i = 0;
+      for (; i + 4 <= n; i += 4, sp += 16, dp += 16) {
+        const __m128 v0 = _mm_loadu_ps(sp), v1 = _mm_loadu_ps(sp + 4), v2 = _mm_loadu_ps(sp + 8), v3 = _mm_loadu_ps(sp + 12);
+        _mm_stream_ps(dp, v0); _mm_stream_ps(dp + 4, v1); _mm_stream_ps(dp + 8, v2); _mm_stream_ps(dp + 12, v3);
+        vmin = _mm_min_ps(vmin, v0); mn1 = _mm_min_ps(mn1, v1); mn2 = _mm_min_ps(mn2, v2); mn3 = _mm_min_ps(mn3, v3);
+        vmax = _mm_max_ps(vmax, v0); mx1 = _mm_max_ps(mx1, v1); mx2 = _mm_max_ps(mx2, v2); mx3 = _mm_max_ps(mx3, v3);
+        nan = _mm_or_ps(nan, _mm_or_ps(_mm_or_ps(_mm_cmpunord_ps(v0, v0), _mm_cmpunord_ps(v1, v1)),
+                                       _mm_or_ps(_mm_cmpunord_ps(v2, v2), _mm_cmpunord_ps(v3, v3))));
+      }
+      vmin = _mm_min_ps(_mm_min_ps(vmin, mn1), _mm_min_ps(mn2, mn3));
+      vmax = _mm_max_ps(_mm_max_ps(vmax, mx1), _mm_max_ps(mx2, mx3));
+      for (; i < n; i++, sp += 4, dp += 4) {
         const __m128 v = _mm_loadu_ps(sp);
+        _mm_stream_ps(dp, v);
         vmin = _mm_min_ps(vmin, v);
         vmax = _mm_max_ps(vmax, v);
+        nan = _mm_or_ps(nan, _mm_cmpunord_ps(v, v));
+      }
+      if (_mm_movemask_ps(nan)) {
+        sp = seg + 4 * (size_t)s0;
+        vmin = _mm_set1_ps(INFINITY);
+        vmax = _mm_set1_ps(-INFINITY);
+        for (i = 0; i < n; i++, sp += 4) {
+          const __m128 v = _mm_loadu_ps(sp);
+          vmin = _mm_min_ps(vmin, v);
+          vmax = _mm_max_ps(vmax, v);
+        }
       }
       float mn[4], mx[4];
       _mm_storeu_ps(mn, vmin);
@@ -1347,8 +1453,6 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   if ((long long)layers * h > 0x7fffffffll) return fail_pixie("canvas stack too large");
 
   const double t1 = now_ms();
-  const int64_t numSegs = numFills ? segOff[numFills] : 0;
-  L.numSegs = numSegs;
   L.numParts = numPartsTotal;
 
   // launch geometry: plan_kernel strides over the jobs, raster_kernel's persistent warps take one
@@ -1361,55 +1465,43 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   L.smemBytes = (size_t)L.covBytes * L.warpsPerBlock;
   L.planSmem = (size_t)L.smemCap * kScratchArrays * 4 * 8;
   const long long totalRows = (long long)layers * h;
-  if (L.smemBytes > 48 * 1024)
-    PX_CUDA(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes));
-  int blocksPerSm = 1;
-  PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, raster_kernel, L.warpsPerBlock * 32, L.smemBytes));
-  blocksPerSm = std::max(1, blocksPerSm);
+  static size_t occSmem = ~(size_t)0;  // occupancy of the two kernels, looked up once per coverage-row size
+  static int occRaster = 1, occPlan = 1;
+  if (occSmem != L.smemBytes) {
+    if (L.smemBytes > 48 * 1024)
+      PX_CUDA(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes));
+    PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occRaster, raster_kernel, L.warpsPerBlock * 32, L.smemBytes));
+    PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occPlan, plan_kernel, 256, L.planSmem));
+    occSmem = L.smemBytes;
+  }
+  const int blocksPerSm = std::max(1, occRaster), planPerSm = std::max(1, occPlan);
   long long wantBlocks = (totalRows + L.warpsPerBlock - 1) / L.warpsPerBlock;
   L.rasterBlocks = (int)std::max<long long>(1, std::min<long long>(wantBlocks, (long long)r.num_sms * blocksPerSm));
-  int planPerSm = 1;
-  PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&planPerSm, plan_kernel, 256, L.planSmem));
-  planPerSm = std::max(1, planPerSm);
   L.planBlocks = (int)std::max<long long>(1, std::min<long long>((jobsTotal + 7) / 8, (long long)r.num_sms * planPerSm));
+  L.scratchSlotCount = r.num_sms * planPerSm;
 
-  // Device block A.  The host-written part (segments, windings, headers, row ranges, layer table)
-  // is contiguous so that it moves with a single H2D copy from a staging buffer; band counts,
-  // entry offsets, flags and counters are produced on the device.
-  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  // device-made part of block A: band counts, entry offsets, flags and counters
   const size_t P = (size_t)numPartsTotal;
-  size_t off = 0;
-  const size_t oSegs = off;      off = al(off + (size_t)numSegs * 16);
-  const size_t oWind = off;      off = al(off + (size_t)numSegs * 2);
-  const size_t oFills = off;     off = al(off + fills.size() * sizeof(FillHeader));
-  const size_t oRowRange = off;  off = al(off + fills.size() * sizeof(int2));
-  const size_t oLayer = off;     off = al(off + layerBegin.size() * 4);
-  const size_t oJobBase = off;   off = al(off + jobBase.size() * 4);
-  const size_t h2dBytes = off;
   const size_t oEntryOff = off;  off = al(off + (P + 1) * 4);   // band counts, scanned in place to offsets
   const size_t oFlags = off;     off = al(off + std::max<size_t>(1, P));
   const size_t oPayOff = off;    off = al(off + (P + 1) * 4);   // plan payload offset of each band
+  const size_t oRanges = off;    off = al(off + std::max<size_t>(1, (size_t)numSegs) * 4);  // packed band range of each segment
+  const size_t oSlots = off;     off = al(off + (size_t)((L.scratchSlotCount + 31) / 32) * 4);
   const size_t oCounters = off;  off = al(off + 128);           // [0] row ticket, [1] covered px, [2] entries, [3] max, [4..] band tickets
   const size_t totalA = off;
-
-  uint8_t* stage = nullptr;
-  std::vector<uint8_t> pageable;
-  if (arena) {  // per-call lists: library-owned growing arena + pinned staging, no malloc/free per call
-    void *blk, *pin;
+  if (arena) {
+    void* blk;
     if (int rc = get_scratch(2, totalA, &blk)) return rc;
-    if (int rc = staging_acquire(h2dBytes, &pin)) return rc;
     L.block = (uint8_t*)blk;
     L.owned = false;
-    stage = (uint8_t*)pin;
   } else {
     PX_CUDA(cudaMalloc(&L.block, totalA));
     L.owned = true;
-    pageable.resize(h2dBytes);
-    stage = pageable.data();
   }
-  if (numSegs) {
-    memcpy(stage + oSegs, seg, (size_t)numSegs * 16);
+  if (numSegs) {  // segments (staged by the bounds pass) + windings go first
     memcpy(stage + oWind, wind, (size_t)numSegs * 2);
+    _mm_sfence();
+    PX_CUDA(cudaMemcpyAsync(L.block, stage, oFills, cudaMemcpyHostToDevice, r.stream));
   }
   if (!fills.empty()) {
     memcpy(stage + oFills, fills.data(), fills.size() * sizeof(FillHeader));
@@ -1423,7 +1515,21 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   }
   memcpy(stage + oLayer, layerBegin.data(), layerBegin.size() * 4);
   memcpy(stage + oJobBase, jobBase.data(), jobBase.size() * 4);
-  PX_CUDA(cudaMemcpyAsync(L.block, stage, h2dBytes, cudaMemcpyHostToDevice, r.stream));
+  if (L.bands > 1) {  // per band: prefix over the fills of the scanlines of each path inside the band
+    int* bj = reinterpret_cast<int*>(stage + oBandJobs);
+    for (int b = 0; b < L.bands; b++, bj += jobBase.size()) {
+      const int y0 = band_edge(h, b, L.bands), y1 = band_edge(h, b + 1, L.bands);
+      int run = 0;
+      for (int k = 0; k < numFills; k++) {
+        const FillHeader& F = fills[k];
+        bj[k] = run;
+        if (F.active && F.numPartitions > 0) run += std::max(0, std::min(F.pathHeight, y1) - std::max(F.startY, y0));
+      }
+      bj[numFills] = run;
+      L.bandJobs[b] = run;
+    }
+  }
+  PX_CUDA(cudaMemcpyAsync(L.block + oFills, stage + oFills, h2dBytes - oFills, cudaMemcpyHostToDevice, r.stream));
   if (arena) {
     if (int rc = staging_release()) return rc;
   }
@@ -1433,9 +1539,12 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   L.rowRange = (int2*)(L.block + oRowRange);
   L.layerFillBegin = (int*)(L.block + oLayer);
   L.fillJobBase = (int*)(L.block + oJobBase);
+  L.bandJobBase = L.bands > 1 ? (int*)(L.block + oBandJobs) : nullptr;
+  L.scratchSlots = (unsigned*)(L.block + oSlots);
   L.payOff = (unsigned*)(L.block + oPayOff);
   L.entryOff = (int*)(L.block + oEntryOff);
   L.flags = L.block + oFlags;
+  L.ranges = (uint32_t*)(L.block + oRanges);
   L.counters = (unsigned long long*)(L.block + oCounters);
   L.h2dBytes = h2dBytes;
 
@@ -1444,8 +1553,9 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   long long meta[4] = {0, 2, 0, 0};  // entries, max entries per band, payload entry-rows
   if (P > 0) {
     PX_CUDA(cudaMemsetAsync(L.entryOff, 0, (P + 1) * 4, r.stream));
+    PX_CUDA(cudaMemsetAsync(L.scratchSlots, 0, (size_t)((L.scratchSlotCount + 31) / 32) * 4, r.stream));
     const int cblocks = (int)std::min<int64_t>((numSegs + 255) / 256, (int64_t)r.num_sms * 8);
-    count_kernel<<<std::max(cblocks, 1), 256, 0, r.stream>>>(L.fills, numFills, L.segs, (int)numSegs, L.entryOff);
+    count_kernel<<<std::max(cblocks, 1), 256, 0, r.stream>>>(L.fills, numFills, L.segs, (int)numSegs, L.entryOff, L.ranges);
     PX_LAUNCHED();
     scan_kernel<<<1, 1024, 0, r.stream>>>(L.entryOff, (int)P, L.counters + 2);
     PX_LAUNCHED();
@@ -1465,7 +1575,7 @@ static int build_list(CmdList& L, bool arena, int w, int h, int layers, int numF
   const size_t entriesBytes = al(std::max<size_t>(1, (size_t)L.numEntries) * sizeof(Entry));
   const size_t jobsBytes = al(std::max<size_t>(1, (size_t)L.totalJobs) * sizeof(JobHdr));
   const size_t payBytes = al(std::max<size_t>(1, (size_t)meta[2]) * kPaySlots * sizeof(uint2));
-  const size_t totalB = entriesBytes + jobsBytes + payBytes + al((size_t)L.planBlocks * 8 * L.scratchWords * 4);
+  const size_t totalB = entriesBytes + jobsBytes + payBytes + al((size_t)L.scratchSlotCount * 8 * L.scratchWords * 4);
   if (arena) {
     void* blk;
     if (int rc = get_scratch(4, totalB, &blk)) return rc;
@@ -1498,7 +1608,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
     const int blocks = (warps + 7) / 8;
     {
       ProfScope ps(kProfPartition);
-      partition_kernel<<<blocks, 256, 0, r.stream>>>(L.fills, L.numFills, L.entryOff, L.segs, L.wind, L.entries,
+      partition_kernel<<<blocks, 256, 0, r.stream>>>(L.fills, L.numFills, L.entryOff, L.segs, L.wind, L.ranges, L.entries,
                                                      L.flags, (int)L.numParts);
     }
     PX_LAUNCHED();
@@ -1513,50 +1623,97 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
   A.numFills = L.numFills;
   A.fillJobBase = L.fillJobBase; A.payOff = L.payOff; A.jobs = L.jobs; A.payload = L.payload; A.totalJobs = L.totalJobs;
   A.rowBegin = 0; A.rowEnd = 0; A.ticketSlot = 0;
-  if (L.totalJobs > 0) {
-    ProfScope ps(kProfPlan);
-    plan_kernel<<<L.planBlocks, 256, L.planSmem, r.stream>>>(A);
-  }
-  PX_LAUNCHED();
+  A.scratchSlots = L.scratchSlots; A.scratchSlotCount = L.scratchSlotCount;
+  A.planJobBase = L.fillJobBase; A.planY0 = 0; A.planJobs = L.totalJobs;
   static size_t configured = 0;
   if (L.smemBytes > 48 * 1024 && configured < L.smemBytes) {
     PX_CUDA(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes));
     configured = L.smemBytes;
   }
   const long long totalRows = (long long)L.layers * L.h;
-  if (!host_pixels) {
+  if (!host_pixels || L.bands <= 1) {
+    if (L.totalJobs > 0) {
+      ProfScope ps(kProfPlan);
+      plan_kernel<<<L.planBlocks, 256, L.planSmem, r.stream>>>(A);
+    }
+    PX_LAUNCHED();
     A.rowBegin = 0; A.rowEnd = totalRows; A.ticketSlot = 0;
     {
       ProfScope ps(kProfRaster);
       raster_kernel<<<L.rasterBlocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
     }
     PX_LAUNCHED();
+    if (host_pixels)
+      PX_CUDA(cudaMemcpyAsync(host_pixels, im->data, (size_t)totalRows * L.w * 4, cudaMemcpyDeviceToHost, r.stream));
   } else {
-    // Row bands on concurrent streams: each band's pixels start their way to the host as soon as the
-    // band is rasterised, while the heavier bands are still being worked on.
-    constexpr int K = Runtime::kBands;
+    // Row bands on concurrent streams: band b is planned and rasterised while band b-1 is on its way to the
+    // host, so the copy engine starts after 1/bands of the work and stays busy from then on.  Kernels are
+    // enqueued in pipeline order (plan b+1 before raster b) with full-size grids; the hardware runs them
+    // roughly in that order and fills the GPU with whatever is next.
+    const int K = L.bands;
     if (!r.band_stream[0]) {
-      for (int b = 0; b < K; b++) {
-        PX_CUDA(cudaStreamCreateWithFlags(&r.band_stream[b], cudaStreamNonBlocking));
+      int least = 0, greatest = 0;  // earlier bands first: their pixels are the next ones the copy engine needs
+      PX_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      for (int b = 0; b < Runtime::kBands; b++) {
+        PX_CUDA(cudaStreamCreateWithPriority(&r.band_stream[b], cudaStreamNonBlocking, std::min(least, greatest + b)));
         PX_CUDA(cudaEventCreateWithFlags(&r.band_done[b], cudaEventDisableTiming));
       }
       PX_CUDA(cudaEventCreateWithFlags(&r.band_start, cudaEventDisableTiming));
     }
+    static cudaEvent_t tev[1 + 3 * Runtime::kBands] = {};  // PIXIE_CUDA_TRACE: band timeline
+    if (g_trace && !tev[0])
+      for (auto& e : tev) PX_CUDA(cudaEventCreate(&e));
+    if (g_trace) PX_CUDA(cudaEventRecord(tev[0], r.stream));
     PX_CUDA(cudaEventRecord(r.band_start, r.stream));
-    const int gridB = std::max(1, L.rasterBlocks / K);
     const size_t rowBytes = (size_t)L.w * 4;
-    for (int b = 0; b < K; b++) {
-      A.rowBegin = totalRows * b / K;
-      A.rowEnd = totalRows * (b + 1) / K;
-      A.ticketSlot = 4 + b;
-      if (A.rowEnd <= A.rowBegin) continue;
+    const size_t fillsP1 = (size_t)L.numFills + 1;
+    auto launch_plan = [&](int b) -> int {
       PX_CUDA(cudaStreamWaitEvent(r.band_stream[b], r.band_start, 0));
-      raster_kernel<<<gridB, L.warpsPerBlock * 32, L.smemBytes, r.band_stream[b]>>>(A);
+      if (L.bandJobs[b] <= 0) return 0;
+      RasterArgs B = A;
+      B.planJobBase = L.bandJobBase + (size_t)b * fillsP1;
+      B.planY0 = band_edge(L.h, b, K);
+      B.planJobs = L.bandJobs[b];
+      const int blocks = std::max(1, std::min((L.bandJobs[b] + 7) / 8, L.planBlocks));
+      plan_kernel<<<blocks, 256, L.planSmem, r.band_stream[b]>>>(B);
       PX_LAUNCHED();
-      PX_CUDA(cudaMemcpyAsync(host_pixels + (size_t)A.rowBegin * rowBytes, im->data + (size_t)A.rowBegin * rowBytes,
-                              (size_t)(A.rowEnd - A.rowBegin) * rowBytes, cudaMemcpyDeviceToHost, r.band_stream[b]));
+      if (g_trace) PX_CUDA(cudaEventRecord(tev[1 + 3 * b], r.band_stream[b]));
+      return 0;
+    };
+    auto launch_raster = [&](int b) -> int {
+      RasterArgs B = A;
+      B.rowBegin = band_edge(totalRows, b, K);
+      B.rowEnd = band_edge(totalRows, b + 1, K);
+      B.ticketSlot = 4 + b;
+      if (B.rowEnd <= B.rowBegin) return 0;
+      const int blocks = (int)std::max<long long>(1, std::min<long long>((B.rowEnd - B.rowBegin + L.warpsPerBlock - 1) / L.warpsPerBlock,
+                                                                       L.rasterBlocks));
+      raster_kernel<<<blocks, L.warpsPerBlock * 32, L.smemBytes, r.band_stream[b]>>>(B);
+      PX_LAUNCHED();
+      if (g_trace) PX_CUDA(cudaEventRecord(tev[2 + 3 * b], r.band_stream[b]));
+      PX_CUDA(cudaMemcpyAsync(host_pixels + (size_t)B.rowBegin * rowBytes, im->data + (size_t)B.rowBegin * rowBytes,
+                              (size_t)(B.rowEnd - B.rowBegin) * rowBytes, cudaMemcpyDeviceToHost, r.band_stream[b]));
+      if (g_trace) PX_CUDA(cudaEventRecord(tev[3 + 3 * b], r.band_stream[b]));
       PX_CUDA(cudaEventRecord(r.band_done[b], r.band_stream[b]));
       PX_CUDA(cudaStreamWaitEvent(r.stream, r.band_done[b], 0));
+      return 0;
+    };
+    if (int rc = launch_plan(0)) return rc;
+    for (int b = 0; b < K; b++) {
+      if (b + 1 < K)
+        if (int rc = launch_plan(b + 1)) return rc;
+      if (int rc = launch_raster(b)) return rc;
+    }
+    if (g_trace) {
+      PX_CUDA(cudaStreamSynchronize(r.stream));
+      fprintf(stderr, "[pixie_cuda] bands (ms after the prologue; plan / raster / on host):");
+      for (int b = 0; b < K; b++) {
+        float t[3] = {0, 0, 0};
+        for (int k = 0; k < 3; k++)
+          if (cudaEventQuery(tev[1 + 3 * b + k]) == cudaSuccess) cudaEventElapsedTime(&t[k], tev[0], tev[1 + 3 * b + k]);
+        fprintf(stderr, " [%d] %.3f %.3f %.3f", b, t[0], t[1], t[2]);
+      }
+      fprintf(stderr, "\n");
     }
   }
   if (covered_px) {
@@ -1579,7 +1736,7 @@ int pixie_cuda_cmdlist_create(int w, int h, int layers, int numFills, const int3
                               const uint8_t* mode, pixie_cmdlist_t* out) {
   if (int rc = ensure_init()) return rc;
   CmdList L;
-  int rc = build_list(L, false, w, h, layers, numFills, layerOf, seg, wind, segOff, rgbx, rule, mode);
+  int rc = build_list(L, false, 1, w, h, layers, numFills, layerOf, seg, wind, segOff, rgbx, rule, mode);
   if (rc) {
     cudaStreamSynchronize(rt().stream);
     free_list(L);
@@ -1629,7 +1786,7 @@ int pixie_cuda_fill_batch(pixie_image_t image, int numFills, const int32_t* laye
   if (!im) return 1;
   if (im->bpp != 4) return fail_pixie("fill needs an RGBX image");
   CmdList L;  // lives in the library arena: no allocation, no synchronisation, nothing to free
-  int rc = build_list(L, true, im->w, im->h, im->layers, numFills, layerOf, seg, wind, segOff, rgbx, rule, mode);
+  int rc = build_list(L, true, 1, im->w, im->h, im->layers, numFills, layerOf, seg, wind, segOff, rgbx, rule, mode);
   if (!rc) rc = run_list(L, im, covered_px);
   return rc;
 }
@@ -1648,7 +1805,7 @@ int pixie_cuda_render_batch_host(uint8_t* pixels, int width, int height, int cle
   Image im;
   im.data = (uint8_t*)canvas; im.w = width; im.h = height; im.layers = 1; im.bpp = 4; im.owned = false;
   CmdList L;
-  int rc = build_list(L, true, width, height, 1, numFills, nullptr, seg, wind, segOff, rgbx, rule, mode);
+  int rc = build_list(L, true, Runtime::kBands, width, height, 1, numFills, nullptr, seg, wind, segOff, rgbx, rule, mode);
   if (rc) return rc;
   if (numFills == 0) {
     PX_CUDA(cudaMemcpyAsync(pixels, canvas, bytes, cudaMemcpyDeviceToHost, r.stream));
