@@ -1032,21 +1032,438 @@ int orc_spread(uint8_t* img, int w, int h, int spread) {  // images.nim:700-758
   return 0;
 }
 
+int orc_draw(uint8_t* dst, int dw, int dh, const uint8_t* src, int sw, int sh, const float* mat, int mode);
+
 int orc_shadow(const uint8_t* img, int w, int h, float ox, float oy, int spread, const uint16_t* lut, int radius,
                uint32_t rgbx, uint8_t* out) {  // images.nim:760-776
-  if (ox != truncf(ox) || oy != truncf(oy)) {
-    g_err = "non-integer shadow offsets go through drawSmooth (not on this path)";
-    return 1;
-  }
   std::vector<uint8_t> mask((size_t)w * h * 4, 0);
-  if (ox == 0 && oy == 0) memcpy(mask.data(), img, mask.size());
-  else orc_blend_rect(mask.data(), w, h, img, w, h, (int)ox, (int)oy, OverwriteBlend);
+  if (ox == 0 && oy == 0) {
+    memcpy(mask.data(), img, mask.size());
+  } else {  // mask.draw(image, translate(offset), OverwriteBlend)
+    const float t[9] = {1, 0, 0, 0, 1, 0, ox, oy, 1};
+    orc_draw(mask.data(), w, h, img, w, h, t, OverwriteBlend);
+  }
   orc_spread(mask.data(), w, h, spread);
   int rc = orc_blur(mask.data(), w, h, lut, radius, 0);
   if (rc) return rc;
   px_t* o = (px_t*)out;
   for (size_t i = 0; i < (size_t)w * h; i++) o[i] = rgbx;
   return orc_blend_rect(out, w, h, mask.data(), w, h, 0, 0, MaskBlend);
+}
+
+
+// =====================================================================================================
+// draw with any transform (images.nim:636-678): minifyBy2 / magnifyBy2 (:168-259), getRgbaSmooth
+// (:367-403), drawSmooth (:531-634), drawCorrect / drawTiled (:405-449, :680-683); gradient paints
+// (paints.nim:68-248).  vmath / bumpy pieces restated from their published definitions.
+// =====================================================================================================
+}  // extern "C" (internal helpers follow)
+
+namespace {
+
+struct V2 { float x, y; };
+inline V2 v2(float x, float y) { V2 r = {x, y}; return r; }
+inline V2 operator+(V2 a, V2 b) { return v2(a.x + b.x, a.y + b.y); }
+inline V2 operator-(V2 a, V2 b) { return v2(a.x - b.x, a.y - b.y); }
+inline V2 operator*(V2 a, float s) { return v2(a.x * s, a.y * s); }
+inline V2 operator/(V2 a, float s) { return v2(a.x / s, a.y / s); }
+inline float vlen(V2 a) { return sqrtf(a.x * a.x + a.y * a.y); }
+struct M3 { float m[9]; };  // vmath Mat3, column-major: m[c*3+r]
+inline V2 mulV(const M3& a, V2 b) { return v2(a.m[0] * b.x + a.m[3] * b.y + a.m[6], a.m[1] * b.x + a.m[4] * b.y + a.m[7]); }
+inline M3 mulM(const M3& a, const M3& b) {  // vmath `*`(a, b: Mat3)
+  M3 r;
+  for (int c = 0; c < 3; c++)
+    for (int row = 0; row < 3; row++)
+      r.m[c * 3 + row] = b.m[c * 3 + 0] * a.m[0 * 3 + row] + b.m[c * 3 + 1] * a.m[1 * 3 + row] + b.m[c * 3 + 2] * a.m[2 * 3 + row];
+  return r;
+}
+inline M3 scaleM(float x, float y) { M3 r = {{x, 0, 0, 0, y, 0, 0, 0, 1}}; return r; }
+inline M3 translateM(float x, float y) { M3 r = {{1, 0, 0, 0, 1, 0, x, y, 1}}; return r; }
+inline M3 rotateM(float angle) {
+  const float s = sinf(angle), c = cosf(angle);
+  M3 r = {{c, s, 0, -s, c, 0, 0, 0, 1}};
+  return r;
+}
+M3 inverseM(const M3& a) {  // vmath inverse(Mat3): adjugate * (1 / determinant); A(c, r) = a.m[c*3+r]
+#define A_(c, r) a.m[(c) * 3 + (r)]
+  const float det = A_(0, 0) * (A_(1, 1) * A_(2, 2) - A_(2, 1) * A_(1, 2)) - A_(0, 1) * (A_(1, 0) * A_(2, 2) - A_(1, 2) * A_(2, 0)) +
+                    A_(0, 2) * (A_(1, 0) * A_(2, 1) - A_(1, 1) * A_(2, 0));
+  const float inv = 1.0f / det;
+  M3 r;
+#define R_(c, r_) r.m[(c) * 3 + (r_)]
+  R_(0, 0) = +(A_(1, 1) * A_(2, 2) - A_(2, 1) * A_(1, 2)) * inv;
+  R_(0, 1) = -(A_(0, 1) * A_(2, 2) - A_(0, 2) * A_(2, 1)) * inv;
+  R_(0, 2) = +(A_(0, 1) * A_(1, 2) - A_(0, 2) * A_(1, 1)) * inv;
+  R_(1, 0) = -(A_(1, 0) * A_(2, 2) - A_(1, 2) * A_(2, 0)) * inv;
+  R_(1, 1) = +(A_(0, 0) * A_(2, 2) - A_(0, 2) * A_(2, 0)) * inv;
+  R_(1, 2) = -(A_(0, 0) * A_(1, 2) - A_(1, 0) * A_(0, 2)) * inv;
+  R_(2, 0) = +(A_(1, 0) * A_(2, 1) - A_(2, 0) * A_(1, 1)) * inv;
+  R_(2, 1) = -(A_(0, 0) * A_(2, 1) - A_(2, 0) * A_(0, 1)) * inv;
+  R_(2, 2) = +(A_(0, 0) * A_(1, 1) - A_(1, 0) * A_(0, 1)) * inv;
+#undef A_
+#undef R_
+  return r;
+}
+inline float fractionalV(float v) { v = fabsf(v); return v - truncf(v); }
+inline float fixAngleV(float a) {
+  const float pi = (float)3.141592653589793238462643383279502884, tau = (float)(2 * 3.141592653589793238462643383279502884);
+  while (a > pi) a -= tau;
+  while (a < -pi) a += tau;
+  return a;
+}
+
+struct Img {
+  int w = 0, h = 0;
+  std::vector<px_t> d;
+  Img() {}
+  Img(int w_, int h_) : w(w_), h(h_), d((size_t)w_ * h_, 0) {}
+};
+
+inline px_t mixPx(px_t a, px_t b, float t) {  // common.nim:59-65
+  const uint32_t x = (uint32_t)(int64_t)roundf(t * 255);
+  return mk((R(a) * (255 - x) + R(b) * x + 127) / 255, (G(a) * (255 - x) + G(b) * x + 127) / 255,
+            (B(a) * (255 - x) + B(b) * x + 127) / 255, (A(a) * (255 - x) + A(b) * x + 127) / 255);
+}
+
+Img minifyOnce(const Img& src) {  // images.nim:181-236 (the SSE2 body :363-468 computes the same bytes)
+  const bool wOdd = src.w % 2 != 0, hOdd = src.h % 2 != 0;
+  const int ew = src.w / 2, eh = src.h / 2;
+  Img r(wOdd ? ew + 1 : ew, hOdd ? eh + 1 : eh);
+  auto at = [&](int x, int y) { return src.d[(size_t)src.w * y + x]; };
+  for (int y = 0; y < eh; y++) {
+    for (int x = 0; x < ew; x++) {
+      const px_t a = at(2 * x, 2 * y), b = at(2 * x + 1, 2 * y), c = at(2 * x + 1, 2 * y + 1), d = at(2 * x, 2 * y + 1);
+      r.d[(size_t)r.w * y + x] = mk((R(a) + R(b) + R(c) + R(d) + 2) / 4, (G(a) + G(b) + G(c) + G(d) + 2) / 4,
+                                    (B(a) + B(b) + B(c) + B(d) + 2) / 4, (A(a) + A(b) + A(c) + A(d) + 2) / 4);
+    }
+    if (wOdd) r.d[(size_t)r.w * y + r.w - 1] = mulAreaScalar(mixPx(at(src.w - 1, 2 * y), at(src.w - 1, 2 * y + 1), 0.5f), 0.5f);
+  }
+  if (hOdd) {
+    for (int x = 0; x < ew; x++)
+      r.d[(size_t)r.w * (r.h - 1) + x] = mulAreaScalar(mixPx(at(2 * x, src.h - 1), at(2 * x + 1, src.h - 1), 0.5f), 0.5f);
+    if (wOdd) r.d[(size_t)r.w * (r.h - 1) + r.w - 1] = mulAreaScalar(at(src.w - 1, src.h - 1), 0.25f);
+  }
+  return r;
+}
+
+Img magnifyOnce(const Img& src) {  // images.nim:238-259 with power = 1
+  Img r(src.w * 2, src.h * 2);
+  for (int y = 0; y < r.h; y++)
+    for (int x = 0; x < r.w; x++) r.d[(size_t)r.w * y + x] = src.d[(size_t)src.w * (y / 2) + x / 2];
+  return r;
+}
+
+inline px_t getPx(const Img& im, int64_t x, int64_t y) {  // image[x, y]: transparent outside
+  if (x < 0 || y < 0 || x >= im.w || y >= im.h) return 0;
+  return im.d[(size_t)im.w * y + x];
+}
+inline px_t getPxWrapped(const Img& im, int64_t x, int64_t y) {
+  // image.unsafe[x mod w, y mod h]: Nim's mod keeps the sign of the dividend, so negative coordinates
+  // address the pixel `linear index` w * (y mod h) + (x mod w); outside the buffer reads as transparent
+  const int64_t idx = (int64_t)im.w * (y % im.h) + (x % im.w);
+  if (idx < 0 || idx >= (int64_t)im.d.size()) return 0;
+  return im.d[(size_t)idx];
+}
+
+px_t getRgbaSmooth(const Img& im, float x, float y, bool wrapped) {  // images.nim:367-403
+  const float fx = floorf(x), fy = floorf(y);
+  const int64_t x0 = f2i(fx), y0 = f2i(fy), x1 = x0 + 1, y1 = y0 + 1;
+  const float xFrac = x - fx, yFrac = y - fy;
+  px_t x0y0, x1y0, x0y1, x1y1;
+  if (wrapped) {
+    x0y0 = getPxWrapped(im, x0, y0); x1y0 = getPxWrapped(im, x1, y0);
+    x0y1 = getPxWrapped(im, x0, y1); x1y1 = getPxWrapped(im, x1, y1);
+  } else {
+    x0y0 = getPx(im, x0, y0); x1y0 = getPx(im, x1, y0);
+    x0y1 = getPx(im, x0, y1); x1y1 = getPx(im, x1, y1);
+  }
+  px_t top = x0y0;
+  if (xFrac > 0 && x0y0 != x1y0) top = mixPx(x0y0, x1y0, xFrac);
+  px_t bottom = x0y1;
+  if (xFrac > 0 && x0y1 != x1y1) bottom = mixPx(x0y1, x1y1, xFrac);
+  if (yFrac != 0 && top != bottom) return mixPx(top, bottom, yFrac);
+  return top;
+}
+
+// bumpy intersects(Line, Segment, at): line a-b against the segment at-to
+inline bool lineSegment(V2 la, V2 lb, V2 sat, V2 sto, V2& at) {
+  const V2 s1 = lb - la, s2 = sto - sat;
+  const float den = (-s2.x * s1.y + s1.x * s2.y);
+  const float num = s1.x * (la.y - sat.y) - s1.y * (la.x - sat.x);
+  const float u = num / den;
+  if (u >= 0 && u <= 1) {
+    at = sat + s2 * u;
+    return true;
+  }
+  return false;
+}
+inline int64_t clampI(int64_t v, int64_t lo, int64_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+void drawSmooth(Img& a, const Img& b, const M3& transform, int mode) {  // images.nim:531-634
+  const float hh = 0.5f;
+  const V2 corners[4] = {mulV(transform, v2(0, 0)), mulV(transform, v2((float)b.w, 0)),
+                         mulV(transform, v2((float)b.w, (float)b.h)), mulV(transform, v2(0, (float)b.h))};
+  const M3 inv = inverseM(transform);
+  const V2 p = mulV(inv, v2(0 + hh, 0 + hh));
+  const V2 dx = mulV(inv, v2(1 + hh, 0 + hh)) - p;
+  const V2 dy = mulV(inv, v2(0 + hh, 1 + hh)) - p;
+  int64_t yStart = a.h, yEnd = 0;
+  for (int k = 0; k < 4; k++) {
+    yStart = std::min<int64_t>(yStart, f2i(floorf(corners[k].y)));
+    yEnd = std::max<int64_t>(yEnd, f2i(ceilf(corners[k].y)));
+  }
+  yStart = clampI(yStart, 0, a.h);
+  yEnd = clampI(yEnd, 0, a.h);
+  if (mode == MaskBlend && yStart > 0) std::fill(a.d.begin(), a.d.begin() + (size_t)yStart * a.w, 0u);
+  std::vector<px_t> sampleLine(a.w);
+  for (int64_t y = yStart; y < yEnd; y++) {
+    float xMin = (float)a.w, xMax = 0.0f;
+    for (int yo = 0; yo < 2; yo++) {
+      const V2 la = v2(-1000, (float)y + (float)yo), lb = v2(1000, (float)y + (float)yo);
+      for (int k = 0; k < 4; k++) {
+        const V2 sat = corners[k], sto = corners[(k + 1) & 3];
+        V2 at = v2(0, 0);
+        if (lineSegment(la, lb, sat, sto, at) && (sto.x != at.x || sto.y != at.y)) {
+          xMin = xMin <= at.x ? xMin : at.x;  // Nim min/max
+          xMax = at.x <= xMax ? xMax : at.x;
+        }
+      }
+    }
+    const int64_t xStart = clampI(f2i(floorf(xMin)), 0, a.w), xEnd = clampI(f2i(ceilf(xMax)), 0, a.w);
+    if (xEnd - xStart == 0) continue;
+    V2 srcPos = (p + dx * (float)xStart) + dy * (float)y;
+    srcPos = v2(srcPos.x - hh, srcPos.y - hh);
+    for (int64_t x = xStart; x < xEnd; x++) {
+      sampleLine[x] = getRgbaSmooth(b, srcPos.x, srcPos.y, false);
+      srcPos = srcPos + dx;
+    }
+    px_t* row = a.d.data() + (size_t)a.w * y;
+    if (mode == MaskBlend) {
+      for (int64_t x = 0; x < xStart; x++) row[x] = 0;
+      for (int64_t x = xStart; x < xEnd; x++) row[x] = lineMask(row[x], sampleLine[x]);
+      for (int64_t x = xEnd; x < a.w; x++) row[x] = 0;
+    } else {
+      for (int64_t x = xStart; x < xEnd; x++) {
+        if (mode == NormalBlend) row[x] = lineNormal(row[x], sampleLine[x]);
+        else if (mode == OverwriteBlend) row[x] = sampleLine[x];
+        else row[x] = blendPx(mode, row[x], sampleLine[x]);
+      }
+    }
+  }
+  if (mode == MaskBlend && a.h - yEnd > 0) std::fill(a.d.begin() + (size_t)yEnd * a.w, a.d.end(), 0u);
+}
+
+void drawAny(Img& a, const Img& b0, M3 transform, int mode) {  // draw, images.nim:636-678
+  const float hh = 0.5f;
+  const M3 inv = inverseM(transform);
+  V2 p = mulV(inv, v2(0 + hh, 0 + hh));
+  V2 dx = mulV(inv, v2(1 + hh, 0 + hh)) - p;
+  V2 dy = mulV(inv, v2(0 + hh, 1 + hh)) - p;
+  float filterBy2 = std::max(vlen(dx), vlen(dy));
+  Img tmp;
+  const Img* b = &b0;
+  while (filterBy2 >= 2.0f) {
+    tmp = minifyOnce(*b);
+    b = &tmp;
+    p = p / 2; dx = dx / 2; dy = dy / 2;
+    filterBy2 /= 2;
+    transform = mulM(transform, scaleM(2, 2));
+  }
+  while (filterBy2 <= 0.5f) {
+    tmp = magnifyOnce(*b);
+    b = &tmp;
+    p = p * 2; dx = dx * 2; dy = dy * 2;
+    filterBy2 *= 2;
+    transform = mulM(transform, scaleM(1.0f / 2, 1.0f / 2));
+  }
+  const bool hasRotationOrScaling = !(dx.x == 1 && dx.y == 0 && dy.x == 0 && dy.y == 1);
+  const bool smooth = !(vlen(dx) == 1.0f && vlen(dy) == 1.0f && fractionalV(transform.m[6]) == 0.0f &&
+                        fractionalV(transform.m[7]) == 0.0f);
+  if (hasRotationOrScaling || smooth) {
+    drawSmooth(a, *b, transform, mode);
+  } else {
+    orc_blend_rect((uint8_t*)a.d.data(), a.w, a.h, (const uint8_t*)b->d.data(), b->w, b->h, (int)transform.m[6],
+                   (int)transform.m[7], mode);
+  }
+}
+
+void drawCorrect(Img& a, const Img& b0, const M3& transform, int mode, bool tiled) {  // images.nim:405-449
+  const float hh = 0.5f;
+  M3 inv = inverseM(transform);
+  V2 p = mulV(inv, v2(0 + hh, 0 + hh));
+  V2 dx = mulV(inv, v2(1 + hh, 0 + hh)) - p;
+  V2 dy = mulV(inv, v2(0 + hh, 1 + hh)) - p;
+  float filterBy2 = std::max(vlen(dx), vlen(dy));
+  Img tmp;
+  const Img* b = &b0;
+  while (filterBy2 >= 2.0f) {
+    tmp = minifyOnce(*b);
+    b = &tmp;
+    p = p / 2; dx = dx / 2; dy = dy / 2;
+    filterBy2 /= 2;
+    inv = mulM(scaleM(0.5f, 0.5f), inv);
+  }
+  while (filterBy2 <= 0.5f) {
+    tmp = magnifyOnce(*b);
+    b = &tmp;
+    p = p * 2; dx = dx * 2; dy = dy * 2;
+    filterBy2 *= 2;
+    inv = mulM(scaleM(2, 2), inv);
+  }
+  for (int y = 0; y < a.h; y++)
+    for (int x = 0; x < a.w; x++) {
+      const V2 sp = mulV(inv, v2((float)x + hh, (float)y + hh));
+      const px_t sample = getRgbaSmooth(*b, sp.x - hh, sp.y - hh, tiled);
+      px_t& d = a.d[(size_t)a.w * y + x];
+      d = blendPx(mode, d, sample);
+    }
+}
+
+// ---- gradient paints (paints.nim:68-248); chroma Color = 4 x float32, straight alpha
+struct ColF { float r, g, b, a; };
+inline uint32_t quantF(float v) {  // chroma Color -> ColorRGBA channel: round(v * 255), clamped
+  float r = floorf(v * 255.0f + 0.5f);
+  if (!(r > 0.0f)) return 0;
+  return r > 255.0f ? 255u : (uint32_t)r;
+}
+inline px_t colorToRgbx(ColF c) {  // chroma Color.rgbx(): quantise, then premultiply (c*a+127) div 255
+  const uint32_t a = quantF(c.a);
+  const uint32_t r = quantF(c.r), g = quantF(c.g), b = quantF(c.b);
+  if (a == 255) return mk(r, g, b, a);
+  return mk((r * a + 127) / 255, (g * a + 127) / 255, (b * a + 127) / 255, a);
+}
+struct Gradient {
+  int n;
+  const float* pos;
+  const ColF* col;
+  float opacity;
+};
+px_t gradientColor(const Gradient& g, float t) {  // paints.nim:68-94
+  int index = -1;
+  for (int i = 0; i < g.n; i++) {
+    if (g.pos[i] < t) index = i;
+    if (g.pos[i] > t) break;
+  }
+  ColF c;
+  if (index == -1) c = g.col[0];
+  else if (index + 1 >= g.n) c = g.col[index];
+  else {
+    const ColF a = g.col[index], b = g.col[index + 1];
+    const float v = (t - g.pos[index]) / (g.pos[index + 1] - g.pos[index]);
+    c.r = a.r * (1.0f - v) + b.r * v;  // chroma mix(a, b: Color, v): lerp per channel
+    c.g = a.g * (1.0f - v) + b.g * v;
+    c.b = a.b * (1.0f - v) + b.b * v;
+    c.a = a.a * (1.0f - v) + b.a * v;
+  }
+  c.a *= g.opacity;
+  return colorToRgbx(c);
+}
+
+}  // namespace
+
+extern "C" {
+
+int orc_minify_by2(const uint8_t* src, int w, int h, int power, uint8_t* out, int* ow, int* oh) {
+  if (power < 0) { g_err = "Cannot minifyBy2 with negative power"; return 1; }
+  Img cur(w, h);
+  memcpy(cur.d.data(), src, (size_t)w * h * 4);
+  for (int i = 0; i < power; i++) cur = minifyOnce(cur);
+  *ow = cur.w; *oh = cur.h;
+  if (out) memcpy(out, cur.d.data(), cur.d.size() * 4);
+  return 0;
+}
+int orc_magnify_by2(const uint8_t* src, int w, int h, int power, uint8_t* out) {
+  if (power < 0) { g_err = "Cannot magnifyBy2 with negative power"; return 1; }
+  const int scale = 1 << power;
+  const px_t* s = (const px_t*)src;
+  px_t* o = (px_t*)out;
+  for (int y = 0; y < h * scale; y++)
+    for (int x = 0; x < w * scale; x++) o[(size_t)w * scale * y + x] = s[(size_t)w * (y / scale) + x / scale];
+  return 0;
+}
+/* draw(a, b, transform, blendMode): mat = vmath Mat3 storage (column-major, 9 floats). */
+int orc_draw(uint8_t* dst, int dw, int dh, const uint8_t* src, int sw, int sh, const float* mat, int mode) {
+  Img a(dw, dh), b(sw, sh);
+  memcpy(a.d.data(), dst, a.d.size() * 4);
+  memcpy(b.d.data(), src, b.d.size() * 4);
+  M3 t;
+  memcpy(t.m, mat, sizeof t.m);
+  drawAny(a, b, t, mode);
+  memcpy(dst, a.d.data(), a.d.size() * 4);
+  return 0;
+}
+/* drawTiled(dst, src, mat, blendMode) = drawCorrect(..., tiled = true) (images.nim:680-683); tiled = 0
+ * gives drawCorrect's untiled form. */
+int orc_draw_correct(uint8_t* dst, int dw, int dh, const uint8_t* src, int sw, int sh, const float* mat, int mode,
+                     int tiled) {
+  Img a(dw, dh), b(sw, sh);
+  memcpy(a.d.data(), dst, a.d.size() * 4);
+  memcpy(b.d.data(), src, b.d.size() * 4);
+  M3 t;
+  memcpy(t.m, mat, sizeof t.m);
+  drawCorrect(a, b, t, mode, tiled != 0);
+  memcpy(dst, a.d.data(), a.d.size() * 4);
+  return 0;
+}
+/* fillGradient (paints.nim:236-248).  kind: 3 linear, 4 radial, 5 angular (ord(PaintKind)); handles:
+ * n_handles x {x, y}; stops: n_stops positions + n_stops x {r, g, b, a} float32 straight colours. */
+int orc_fill_gradient(uint8_t* img, int w, int h, int kind, const float* handles, int n_handles, const float* stop_pos,
+                      const float* stop_rgba, int n_stops, float opacity) {
+  if (kind < 3 || kind > 5) { g_err = "Paint must be a gradient"; return 1; }
+  const int need = kind == 3 ? 2 : 3;
+  if (n_handles != need) {
+    g_err = kind == 3 ? "Linear gradient requires 2 handles" : kind == 4 ? "Radial gradient requires 3 handles"
+                                                                         : "Angular gradient requires 2 handles";
+    return 1;
+  }
+  if (n_stops == 0) { g_err = "Gradient must have at least 1 color stop"; return 1; }
+  opacity = opacity < 0 ? 0 : (opacity > 1 ? 1 : opacity);
+  if (opacity == 0) return 0;
+  Gradient g = {n_stops, stop_pos, (const ColF*)stop_rgba, opacity};
+  px_t* d = (px_t*)img;
+  const V2 h0 = v2(handles[0], handles[1]), h1 = v2(handles[2], handles[3]);
+  if (kind == 3) {
+    auto toLineSpace = [](V2 at, V2 to, V2 pt) {
+      const V2 dd = to - at;
+      const float det = dd.x * dd.x + dd.y * dd.y;
+      return (dd.y * (pt.y - at.y) + dd.x * (pt.x - at.x)) / det;
+    };
+    for (int y = 0; y < h; y++)
+      for (int x = 0; x < w; x++) {
+        // the horizontal / vertical special cases (:115-165) evaluate the same expression at (x, 0) / (0, y)
+        V2 xy = v2((float)x, (float)y);
+        if (h0.y == h1.y) xy.y = 0;
+        else if (h0.x == h1.x) xy.x = 0;
+        d[(size_t)w * y + x] = gradientColor(g, toLineSpace(h0, h1, xy));
+      }
+    return 0;
+  }
+  const V2 h2 = v2(handles[4], handles[5]);
+  if (kind == 4) {
+    const V2 center = h0, edge = h1, skew = h2;
+    const float distanceX = vlen(center - edge), distanceY = vlen(center - skew);
+    const V2 n = (center - edge) / vlen(center - edge);
+    const float gradientAngle = fixAngleV(atan2f(n.y, n.x));
+    const M3 mat = inverseM(mulM(mulM(translateM(center.x, center.y), rotateM(gradientAngle)), scaleM(distanceX, distanceY)));
+    for (int y = 0; y < h; y++)
+      for (int x = 0; x < w; x++) d[(size_t)w * y + x] = gradientColor(g, vlen(mulV(mat, v2((float)x, (float)y))));
+    return 0;
+  }
+  const V2 center = h0, edge = h1;
+  const float pi = (float)3.141592653589793238462643383279502884;
+  const V2 n = (edge - center) / vlen(edge - center);
+  const float gradientAngle = fixAngleV(atan2f(n.y, n.x));
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      const V2 dlt = v2((float)x, (float)y) - center;
+      const V2 nn = dlt / vlen(dlt);
+      // arctan2 in float32: evaluated in double and rounded, which is what a correctly rounded atan2f
+      // returns (the GPU kernel does the same, so the two agree bit for bit)
+      const float angle = (float)atan2((double)nn.y, (double)nn.x);
+      const float t = fixAngleV(angle + gradientAngle + pi / 2) / 2 / pi + 0.5f;
+      d[(size_t)w * y + x] = gradientColor(g, t);
+    }
+  return 0;
 }
 
 }  // extern "C"

@@ -13,6 +13,9 @@
  *   src/pixie/common.nim  :67-101 ColorRGBX*float32, ColorRGBX*uint8, snapToPixels
  *   src/pixie/images.nim  :261-277 applyOpacity, :304-365 blur, :468-529 blendRect,
  *                         :700-758 spread, :760-776 shadow
+ *                         :168-259 minifyBy2/magnifyBy2, :367-449 getRgbaSmooth/drawCorrect,
+ *                         :531-683 drawSmooth/draw/drawTiled
+ *   src/pixie/paints.nim  :68-248 gradientColor, fillGradient{Linear,Radial,Angular}
  *   src/pixie/simd/sse2.nim :6-46, :510-524 (the x86 numerics of the row kernels)
  *
  * Parity status: pinned against the reference's own golden PNGs (tests/golden/, see
@@ -59,6 +62,19 @@ int orc_spread(uint8_t* img, int w, int h, int spread);
 /* shadow: out (w*h*4) = shadow(img, offset, spread, blur LUT, colour). */
 int orc_shadow(const uint8_t* img, int w, int h, float ox, float oy, int spread, const uint16_t* lut,
                int radius, uint32_t rgbx, uint8_t* out);
+
+/* minifyBy2 / magnifyBy2 (images.nim:168-259).  minify: out may be NULL to query the size. */
+int orc_minify_by2(const uint8_t* src, int w, int h, int power, uint8_t* out, int* out_w, int* out_h);
+int orc_magnify_by2(const uint8_t* src, int w, int h, int power, uint8_t* out);
+/* draw (images.nim:636-678) with any transform: minify/magnify chain, drawSmooth (:531-634) or
+ * blendRect.  mat = vmath Mat3 storage (column-major, 9 floats). */
+int orc_draw(uint8_t* dst, int dw, int dh, const uint8_t* src, int sw, int sh, const float* mat, int blend_mode);
+/* drawCorrect (images.nim:405-449); tiled != 0 is drawTiled (:680-683). */
+int orc_draw_correct(uint8_t* dst, int dw, int dh, const uint8_t* src, int sw, int sh, const float* mat,
+                     int blend_mode, int tiled);
+/* fillGradient (paints.nim:68-248).  kind = ord(PaintKind): 3 linear, 4 radial, 5 angular. */
+int orc_fill_gradient(uint8_t* img, int w, int h, int kind, const float* handles_xy, int n_handles,
+                      const float* stop_pos, const float* stop_rgba, int n_stops, float opacity);
 
 #ifdef __cplusplus
 }

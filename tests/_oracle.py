@@ -30,6 +30,11 @@ def lib():
         L.orc_blur.argtypes = [vp, i32, i32, vp, i32, u32]
         L.orc_spread.argtypes = [vp, i32, i32, i32]
         L.orc_shadow.argtypes = [vp, i32, i32, f32, f32, i32, vp, i32, u32, vp]
+        L.orc_minify_by2.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+        L.orc_magnify_by2.argtypes = [vp, i32, i32, i32, vp]
+        L.orc_draw.argtypes = [vp, i32, i32, vp, i32, i32, vp, i32]
+        L.orc_draw_correct.argtypes = [vp, i32, i32, vp, i32, i32, vp, i32, i32]
+        L.orc_fill_gradient.argtypes = [vp, i32, i32, i32, vp, i32, vp, vp, i32, f32]
         _lib = L
     return _lib
 
@@ -80,6 +85,45 @@ class OracleBackend:
         _chk(lib().orc_shadow(img.ctypes.data, img.shape[1], img.shape[0], ox, oy, spread, lut.ctypes.data, radius,
                               rgbx, out.ctypes.data))
         return out
+
+
+    def apply_opacity(self, img, opacity):
+        _chk(lib().orc_apply_opacity(img.ctypes.data, img.shape[1], img.shape[0], opacity))
+
+    def draw(self, dst, src, mat, mode):
+        m = np.ascontiguousarray(mat, np.float32)
+        src = np.ascontiguousarray(src)
+        _chk(lib().orc_draw(dst.ctypes.data, dst.shape[1], dst.shape[0], src.ctypes.data, src.shape[1], src.shape[0],
+                            m.ctypes.data, mode))
+
+    def draw_tiled(self, dst, src, mat, mode, tiled=True):
+        m = np.ascontiguousarray(mat, np.float32)
+        src = np.ascontiguousarray(src)
+        _chk(lib().orc_draw_correct(dst.ctypes.data, dst.shape[1], dst.shape[0], src.ctypes.data, src.shape[1],
+                                    src.shape[0], m.ctypes.data, mode, 1 if tiled else 0))
+
+    def minify_by2(self, img, power=1):
+        img = np.ascontiguousarray(img)
+        ow, oh = C.c_int(0), C.c_int(0)
+        _chk(lib().orc_minify_by2(img.ctypes.data, img.shape[1], img.shape[0], power, None, C.addressof(ow), C.addressof(oh)))
+        out = np.zeros((oh.value, ow.value, 4), np.uint8)
+        _chk(lib().orc_minify_by2(img.ctypes.data, img.shape[1], img.shape[0], power, out.ctypes.data, C.addressof(ow),
+                                  C.addressof(oh)))
+        return out
+
+    def magnify_by2(self, img, power=1):
+        img = np.ascontiguousarray(img)
+        out = np.zeros((img.shape[0] << power, img.shape[1] << power, 4), np.uint8)
+        _chk(lib().orc_magnify_by2(img.ctypes.data, img.shape[1], img.shape[0], power, out.ctypes.data))
+        return out
+
+    def fill_gradient(self, img, kind, handles, stops, opacity=1.0):
+        """stops: [(position, (r, g, b, a))] with float colours (chroma Color)."""
+        hx = np.ascontiguousarray(np.asarray(handles, np.float32).reshape(-1))
+        pos = np.ascontiguousarray([s[0] for s in stops], np.float32)
+        col = np.ascontiguousarray([s[1] for s in stops], np.float32).reshape(-1)
+        _chk(lib().orc_fill_gradient(img.ctypes.data, img.shape[1], img.shape[0], kind, hx.ctypes.data, len(hx) // 2,
+                                     pos.ctypes.data, col.ctypes.data, len(stops), opacity))
 
 
 def blend_px(mode, backdrop, source):

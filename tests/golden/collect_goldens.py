@@ -33,6 +33,18 @@ FILES = [(f"tests/paths/{n}.png", f"paths_{n}.png") for n in PATHS] + [
     ("tests/fileformats/svg/masters/Ghostscript_Tiger.png", "svg_masters_Ghostscript_Tiger.png"),
 ] + [(f"tests/images/maskClearsOnDraw{i}.png", f"images_maskClearsOnDraw{i}.png") for i in range(5)]
 
+# draw with any transform, minify / magnify, non-solid paints (tests/test_images_draw.nim, test_images.nim,
+# test_paints.nim) and the input images those tests read
+PAINTS = """paintSolid paintImage paintImageOpacity paintImageTiled paintImageTiledOpacity gradientLinear
+gradientLinear2 gradientRadial gradientAngular gradientAngularOpacity fillImagePaint fillTiledImagePaint""".split()
+DRAWS = """rotate0 rotate90 rotate180 rotate270 rotate360 scaleHalf fillOptimization fillOptimization2 flipped1
+minifiedBy2 magnifiedBy2 minifiedBy4 magnifiedBy4 minifiedMandrill turtle turtle@10x rock""".split()
+MASTERS = [f"smooth{i}" for i in range(1, 13)] + ["minify_odd", "rock_minified", "rock_minified2"]
+FILES += [(f"tests/paths/{n}.png", f"paths_{n}.png") for n in PAINTS]
+FILES += [(f"tests/images/{n}.png", f"images_{n}.png") for n in DRAWS]
+FILES += [(f"tests/images/masters/{n}.png", f"images_masters_{n}.png") for n in MASTERS]
+FILES += [("tests/fileformats/png/mandrill.png", "fileformats_png_mandrill.png")]
+
 for src, dst in FILES:
     shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
     print(dst)

@@ -12,12 +12,18 @@ from _oracle import OracleBackend
 @pytest.mark.parametrize("name", sorted(gc.CASES))
 def test_oracle_reproduces_golden(name):
     out = gc.CASES[name](OracleBackend(sem=0))
+    if name in gc.SCORE_ONLY:  # masters the reference compares by score only (see golden_cases.SCORE_ONLY)
+        score = gc.xray_score(out, gc.load_golden(name))
+        assert score < gc.SCORE_ONLY[name], f"{name}: xray score {score}"
+        return
     mism, mx = gc.compare(out, gc.load_golden(name))
     assert (mism, mx) == (0, 0), f"{name}: {mism} pixels differ, max |delta| {mx}"
 
 
 @pytest.mark.parametrize("name", sorted(gc.CASES))
 def test_scalar_semantics_within_one_lsb(name):
+    if name in gc.SCORE_ONLY:
+        pytest.skip("score-only master")
     out = gc.CASES[name](OracleBackend(sem=1))
     mism, mx = gc.compare(out, gc.load_golden(name))
     assert mx <= 1, f"{name}: scalar semantics differ by {mx} LSB"
