@@ -119,6 +119,33 @@ int pixie_cuda_blend_rect_masked(pixie_image_t dst, pixie_image_t src, pixie_ima
                                  int blend_mode);
 int pixie_cuda_apply_opacity(pixie_image_t image, float opacity);              /* images.nim:261-277 */
 
+/* ---- draw with any transform (images.nim:636-678) -------------------------------------------
+ * Replaces the body of draw(a, b, transform, blendMode): mat is vmath Mat3 storage (9 float32, column-major:
+ * mat[0..2] = column 0, mat[6], mat[7] = translation).  Exactly the reference's flow: movement vectors from
+ * the inverse transform, minifyBy2 / magnifyBy2 of the source while the scale is >= 2 or <= 0.5
+ * (:649-663), then drawSmooth (:531-634: per-row x range from the transformed perimeter, bilinear
+ * getRgbaSmooth :367-403, blendLineNormal / Overwrite / Mask or blender()) or, for integer translations,
+ * blendRect (:678).  dst and src must be different single-layer RGBX images. */
+int pixie_cuda_draw(pixie_image_t dst, pixie_image_t src, const float* mat, int blend_mode);
+/* drawTiled (images.nim:680-683) = drawCorrect(..., tiled = true) (:405-449): every dst pixel samples the
+ * wrapped source through blender(); used by TiledImagePaint fills (paths.nim:2131-2132). */
+int pixie_cuda_draw_tiled(pixie_image_t dst, pixie_image_t src, const float* mat, int blend_mode);
+int pixie_cuda_draw_correct(pixie_image_t dst, pixie_image_t src, const float* mat, int blend_mode); /* untiled */
+/* minifyBy2 / magnifyBy2 (images.nim:168-259): *out receives a new image handle.  power < 0 -> 1
+ * "Cannot minifyBy2 with negative power" (:172-173, :242-243). */
+int pixie_cuda_minify_by2(pixie_image_t src, int power, pixie_image_t* out);
+int pixie_cuda_magnify_by2(pixie_image_t src, int power, pixie_image_t* out);
+
+/* ---- gradient paints: fillGradient (paints.nim:68-248) ---------------------------------------
+ * kind = ord(PaintKind) (paints.nim:4-10): 3 LinearGradientPaint (2 handles), 4 RadialGradientPaint (3),
+ * 5 AngularGradientPaint (3).  handles_xy: n_handles x {x, y} (gradientHandlePositions); stops:
+ * stop_pos[n_stops] and stop_rgba[n_stops][4] = chroma Color (straight float32 r, g, b, a) in list order
+ * (gradientStops); opacity = paint.opacity (clamped to 0..1, 0 is a no-op).  Errors as the reference:
+ * "Linear gradient requires 2 handles", "Gradient must have at least 1 color stop", ...
+ * Every pixel of the image is overwritten (image.unsafe[x, y] = gradientColor(t)). */
+int pixie_cuda_fill_gradient(pixie_image_t image, int kind, const float* handles_xy, int n_handles,
+                             const float* stop_pos, const float* stop_rgba, int n_stops, float opacity);
+
 /* ---- blur / spread / shadow (images.nim:304-365, :700-758, :760-776) ------------------------
  * lut = gaussianKernel(radius) (internal.nim:17-34), 2*radius+1 uint16 taps, computed by the
  * caller.  radius < 0 -> 1 "Cannot apply negative blur" (:311-312); radius == 0 is a no-op. */
@@ -129,8 +156,8 @@ int pixie_cuda_blur(pixie_image_t image, const uint16_t* lut, int radius, uint32
 int pixie_cuda_blur_rows(pixie_image_t image, const uint16_t* lut, int radius, uint32_t out_of_bounds_rgbx,
                          int y0, int y1);
 int pixie_cuda_spread(pixie_image_t image, int spread);
-/* dst <- shadow(src, offset, spread, blur, color); offset must be integral (a fractional offset
- * goes through drawSmooth in the reference, which is not on this path -> returns 1). */
+/* dst <- shadow(src, offset, spread, blur, color); the offset copy is mask.draw(image, translate(offset),
+ * OverwriteBlend) (:768-769): blendRect for integral offsets, drawSmooth otherwise. */
 int pixie_cuda_shadow(pixie_image_t src, pixie_image_t dst, float offset_x, float offset_y, int spread,
                       const uint16_t* lut, int radius, uint32_t rgbx);
 

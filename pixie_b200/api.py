@@ -8,8 +8,9 @@ Same names, argument meaning and error behaviour as the reference (treeform/pixi
 building, Gaussian LUT) runs in libpixie_host.so as it does in Nim; everything that touches pixels
 runs in pixie_cuda.so.  There is no CPU fallback.
 
-Out of this path (raise PixieError): draw() with rotation/scale/fractional translate (drawSmooth),
-gradient paints, tiled image paints.
+``draw`` takes any transform (minifyBy2 / magnifyBy2 chain + drawSmooth, images.nim:531-678), ``Paint`` covers
+all six PaintKinds (paints.nim:4-24): image / tiled image / linear, radial, angular gradients are composited as
+the reference does (paths.nim:2115-2142) with the last two draws fused into one masked blend.
 """
 from __future__ import annotations
 
@@ -24,7 +25,8 @@ from .common import (MaskBlend, NormalBlend, OverwriteBlend, PixieError, parseHt
 from .host import (BevelJoin, ButtCap, EvenOdd, MiterJoin, NonZero, RoundCap, RoundJoin, SquareCap,  # noqa: F401
                    Path, defaultMiterLimit, newPath, parsePath)
 
-SolidPaint, ImagePaint = 0, 1  # paints.nim PaintKind (the kinds that stay on this path)
+# paints.nim:4-10 PaintKind
+SolidPaint, ImagePaint, TiledImagePaint, LinearGradientPaint, RadialGradientPaint, AngularGradientPaint = range(6)
 
 
 def _color_to_rgbx(color, opacity=1.0) -> int:
@@ -62,6 +64,15 @@ class Paint:
     color: tuple = (0.0, 0.0, 0.0, 1.0)
     image: "Image | None" = None
     imageMat: np.ndarray = field(default_factory=host.mat3)
+    gradientHandlePositions: list = field(default_factory=list)  # [(x, y)] in image space
+    gradientStops: list = field(default_factory=list)            # [ColorStop]
+
+
+@dataclass
+class ColorStop:
+    """paints.nim:26-29."""
+    color: tuple = (0.0, 0.0, 0.0, 1.0)
+    position: float = 0.0
 
 
 def newPaint(kind=SolidPaint) -> Paint:
@@ -105,11 +116,27 @@ class Image:
     # -- pixie.nim:120-131
     def fill(self, color):
         if isinstance(color, Paint):
-            if color.kind != SolidPaint:
-                raise PixieError("only SolidPaint fills are on this path")
-            self._d.fill(_color_to_rgbx(color.color, color.opacity))
+            paint = color
+            if paint.kind == SolidPaint:
+                self._d.fill(_color_to_rgbx(paint.color))
+            elif paint.kind in (ImagePaint, TiledImagePaint):
+                self._d.fill(0)
+                path = newPath()
+                path.rect(0, 0, float(self.width), float(self.height))
+                self.fillPath(path, paint)
+            else:
+                self.fillGradient(paint)
         else:
             self._d.fill(_color_to_rgbx(_some_color(color)))
+
+    # -- paints.nim:236-248
+    def fillGradient(self, paint: Paint):
+        if paint.kind not in (LinearGradientPaint, RadialGradientPaint, AngularGradientPaint):
+            raise PixieError("Paint must be a gradient")
+        # ColorStop.color is a chroma Color: straight float r, g, b, a (or an HTML colour string)
+        stops = [(float(st.position), tuple(float(v) for v in (_some_color(st.color) if isinstance(st.color, str) else st.color)))
+                 for st in paint.gradientStops]
+        dev.fill_gradient(self._d, paint.kind, [tuple(h) for h in paint.gradientHandlePositions], stops, paint.opacity)
 
     # -- paths.nim:2093-2142
     def fillPath(self, path, paint, transform=None, windingRule=NonZero):
@@ -145,19 +172,45 @@ class Image:
     def _composite_non_solid(self, mask: "Image", paint: Paint):
         """paths.nim:2115-2142: fill image + mask, `fill.draw(mask, MaskBlend); image.draw(fill, blendMode)`
         fused into one pass (pixie_cuda_blend_rect_masked)."""
-        if paint.kind != ImagePaint or paint.image is None:
-            raise PixieError("gradient / tiled paints are not on this path")
-        tx, ty = _integer_translate(paint.imageMat)
         fill = Image(self.width, self.height)
-        dev.blend_rect(fill._d, paint.image._d, tx, ty, NormalBlend)  # fill.draw(paint.image, paint.imageMat)
+        if paint.kind == ImagePaint:
+            dev.draw(fill._d, paint.image._d, paint.imageMat, NormalBlend)        # fill.draw(paint.image, paint.imageMat)
+        elif paint.kind == TiledImagePaint:
+            dev.draw_tiled(fill._d, paint.image._d, paint.imageMat, NormalBlend)  # fill.drawTiled(...)
+        else:
+            saved, paint.opacity = paint.opacity, 1.0                             # paths.nim:2123-2136
+            try:
+                fill.fillGradient(paint)
+            finally:
+                paint.opacity = saved
         if paint.opacity != 1:
             dev.apply_opacity(mask._d, paint.opacity)
         dev.blend_rect_masked(self._d, fill._d, mask._d, 0, 0, paint.blendMode)
 
     # -- images.nim:636-678
     def draw(self, other: "Image", transform=None, blendMode=NormalBlend):
-        tx, ty = _integer_translate(transform)
-        dev.blend_rect(self._d, other._d, tx, ty, blendMode)
+        dev.draw(self._d, other._d, host.mat3() if transform is None else transform, blendMode)
+
+    def drawTiled(self, other: "Image", mat, blendMode=NormalBlend):
+        dev.draw_tiled(self._d, other._d, mat, blendMode)
+
+    # -- images.nim:168-259
+    def minifyBy2(self, power=1) -> "Image":
+        d = dev.minify_by2(self._d, power)
+        return Image(d.width, d.height, _dev=d)
+
+    def magnifyBy2(self, power=1) -> "Image":
+        d = dev.magnify_by2(self._d, power)
+        return Image(d.width, d.height, _dev=d)
+
+    # -- images.nim:685-698
+    def resize(self, width, height) -> "Image":
+        if width == self.width and height == self.height:
+            return self.copy()
+        out = newImage(width, height)
+        f = np.float32
+        out.draw(self, host.scale(f(width) / f(self.width), f(height) / f(self.height)), OverwriteBlend)
+        return out
 
     def applyOpacity(self, opacity):
         dev.apply_opacity(self._d, opacity)
@@ -195,17 +248,6 @@ def set_device(index: int):
     global _DEVICE
     _DEVICE = index
     dev.init(index)
-
-
-def _integer_translate(transform):
-    """draw() takes the blendRect fast path only for pure integer translations (images.nim:666-678)."""
-    if transform is None:
-        return 0, 0
-    m = np.asarray(transform, dtype=np.float32).reshape(9)
-    if not (m[0] == 1 and m[1] == 0 and m[3] == 0 and m[4] == 1) or m[6] != np.trunc(m[6]) or m[7] != np.trunc(m[7]):
-        raise PixieError("draw() with rotation, scale or a fractional translate goes through drawSmooth, "
-                         "which is not on this path")
-    return int(m[6]), int(m[7])
 
 
 def newImage(width, height) -> Image:

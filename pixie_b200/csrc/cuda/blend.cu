@@ -200,6 +200,42 @@ static int dispatch_rect(int mode, const RectArgs& a) {
   return rc;
 }
 
+// dst <- blend(dst, src at (px, py)); src / mask given as raw device pointers (draw.cu passes minified copies)
+static int blend_rect_core(Image* d, const px_t* src, int sw, int sh, const uint8_t* mask, int mask_bpp, int px, int py,
+                           int mode) {
+  RectArgs a;
+  a.dst = (px_t*)d->data;
+  a.src = src;
+  a.mask = mask;
+  a.dw = d->w; a.dh = d->h; a.sw = sw; a.sh = sh; a.px = px; a.py = py;
+  a.src_aligned = ((px & 3) == 0 && (sw & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                   (!mask || (reinterpret_cast<uintptr_t>(mask) & 15) == 0)) ? 1 : 0;
+  // images.nim:473-476
+  const bool outside = (int64_t)px >= d->w || (int64_t)px + sw <= 0 || (int64_t)py >= d->h || (int64_t)py + sh <= 0;
+  if (outside) {
+    if (mode == MaskBlend) PX_CUDA(cudaMemsetAsync(d->data, 0, d->layer_bytes(), rt().stream));
+    return 0;
+  }
+  // images.nim:478-482 (in dst space)
+  a.rx0 = px > 0 ? px : 0;
+  a.ry0 = py > 0 ? py : 0;
+  a.rx1 = (px + sw < d->w) ? px + sw : d->w;
+  a.ry1 = (py + sh < d->h) ? py + sh : d->h;
+  if (mode == MaskBlend) {
+    a.xs = 0; a.xe = d->w; a.ys = 0; a.ye = d->h;
+  } else {
+    a.xs = a.rx0; a.xe = a.rx1; a.ys = a.ry0; a.ye = a.ry1;
+  }
+  const int mk_ = !mask ? 0 : (mask_bpp == 4 ? 1 : 2);
+  if (mk_ == 0) return dispatch_rect<0>(mode, a);
+  if (mk_ == 1) return dispatch_rect<1>(mode, a);
+  return dispatch_rect<2>(mode, a);
+}
+
+int blend_rect_raw(Image* d, const px_t* src, int sw, int sh, int px, int py, int mode) {
+  return blend_rect_core(d, src, sw, sh, nullptr, 0, px, py, mode);
+}
+
 static int blend_rect_impl(pixie_image_t dsth, pixie_image_t srch, pixie_image_t maskh, bool masked, int px, int py,
                            int mode) {
   if (int rc = ensure_init()) return rc;
@@ -215,33 +251,7 @@ static int blend_rect_impl(pixie_image_t dsth, pixie_image_t srch, pixie_image_t
     if (m->w != s->w || m->h != s->h) return fail_pixie("mask must have the size of src");
   }
   if (d->data == s->data) return fail_pixie("blend_rect: dst and src must be different images");
-  RectArgs a;
-  a.dst = (px_t*)d->data;
-  a.src = (const px_t*)s->data;
-  a.mask = m ? m->data : nullptr;
-  a.dw = d->w; a.dh = d->h; a.sw = s->w; a.sh = s->h; a.px = px; a.py = py;
-  a.src_aligned = ((px & 3) == 0 && (s->w & 3) == 0 && (reinterpret_cast<uintptr_t>(s->data) & 15) == 0 &&
-                   (!m || (reinterpret_cast<uintptr_t>(m->data) & 15) == 0)) ? 1 : 0;
-  // images.nim:473-476
-  const bool outside = (int64_t)px >= d->w || (int64_t)px + s->w <= 0 || (int64_t)py >= d->h || (int64_t)py + s->h <= 0;
-  if (outside) {
-    if (mode == MaskBlend) return pixie_cuda_image_fill(dsth, 0u);
-    return 0;
-  }
-  // images.nim:478-482 (in dst space)
-  a.rx0 = px > 0 ? px : 0;
-  a.ry0 = py > 0 ? py : 0;
-  a.rx1 = (px + s->w < d->w) ? px + s->w : d->w;
-  a.ry1 = (py + s->h < d->h) ? py + s->h : d->h;
-  if (mode == MaskBlend) {
-    a.xs = 0; a.xe = d->w; a.ys = 0; a.ye = d->h;
-  } else {
-    a.xs = a.rx0; a.xe = a.rx1; a.ys = a.ry0; a.ye = a.ry1;
-  }
-  const int mk_ = !m ? 0 : (m->bpp == 4 ? 1 : 2);
-  if (mk_ == 0) return dispatch_rect<0>(mode, a);
-  if (mk_ == 1) return dispatch_rect<1>(mode, a);
-  return dispatch_rect<2>(mode, a);
+  return blend_rect_core(d, (const px_t*)s->data, s->w, s->h, m ? m->data : nullptr, m ? m->bpp : 0, px, py, mode);
 }
 
 __global__ void __launch_bounds__(256) apply_opacity_kernel(uint4* __restrict__ p, size_t n16, uint32_t o) {

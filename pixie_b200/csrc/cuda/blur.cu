@@ -525,14 +525,15 @@ int pixie_cuda_shadow(pixie_image_t srch, pixie_image_t dsth, float ox, float oy
   if (s->w != d->w || s->h != d->h || s->bpp != 4 || d->bpp != 4 || s->layers != 1 || d->layers != 1)
     return fail_pixie("shadow: src and dst must be single-layer RGBX images of the same size");
   if (s->data == d->data) return fail_pixie("shadow: src and dst must be different images");
-  if (ox != truncf(ox) || oy != truncf(oy))
-    return fail_pixie("shadow: fractional offsets go through drawSmooth, which is not on this path");
-  // mask = copy / offset copy (images.nim:764-769), built directly in dst
+  // mask = copy / mask.draw(image, translate(offset), OverwriteBlend) (images.nim:764-769), built directly in dst;
+  // integer offsets end in blendRect, fractional ones in drawSmooth, as in draw()
   if (ox == 0 && oy == 0) {
     if (int rc = pixie_cuda_image_copy(dsth, srch)) return rc;
   } else {
     if (int rc = pixie_cuda_image_fill(dsth, 0u)) return rc;
-    if (int rc = pixie_cuda_blend_rect(dsth, srch, (int)ox, (int)oy, OverwriteBlend)) return rc;
+    const float t[9] = {1, 0, 0, 0, 1, 0, ox, oy, 1};
+    if (int rc = pixie_cuda_draw(dsth, srch, t, OverwriteBlend)) return rc;
+    d = find_image(dsth);
   }
   if (int rc = spread_impl(d, spread)) return rc;
   if (int rc = blur_impl(d, lut, radius, 0u, 0, d->h)) return rc;

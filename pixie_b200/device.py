@@ -52,6 +52,12 @@ _SIGNATURES = {
     "pixie_cuda_blend_rect": [u64, u64, i32, i32, i32],
     "pixie_cuda_blend_rect_masked": [u64, u64, u64, i32, i32, i32],
     "pixie_cuda_apply_opacity": [u64, f32],
+    "pixie_cuda_draw": [u64, u64, vp, i32],
+    "pixie_cuda_draw_tiled": [u64, u64, vp, i32],
+    "pixie_cuda_draw_correct": [u64, u64, vp, i32],
+    "pixie_cuda_minify_by2": [u64, i32, P(u64)],
+    "pixie_cuda_magnify_by2": [u64, i32, P(u64)],
+    "pixie_cuda_fill_gradient": [u64, i32, vp, i32, vp, vp, i32, f32],
     "pixie_cuda_blur": [u64, vp, i32, u32],
     "pixie_cuda_blur_rows": [u64, vp, i32, u32, i32, i32],
     "pixie_cuda_spread": [u64, i32],
@@ -296,6 +302,45 @@ def blend_rect_masked(dst: DeviceImage, src: DeviceImage, mask: DeviceImage, px,
 
 def apply_opacity(image: DeviceImage, opacity):
     check(lib().pixie_cuda_apply_opacity(image.handle, opacity))
+
+
+def draw(dst: DeviceImage, src: DeviceImage, mat, mode):
+    """draw(a, b, transform, blendMode) with any transform (images.nim:636-678)."""
+    m = np.ascontiguousarray(mat, np.float32).reshape(9)
+    check(lib().pixie_cuda_draw(dst.handle, src.handle, m.ctypes.data, mode))
+
+
+def draw_tiled(dst: DeviceImage, src: DeviceImage, mat, mode, tiled=True):
+    m = np.ascontiguousarray(mat, np.float32).reshape(9)
+    fn = lib().pixie_cuda_draw_tiled if tiled else lib().pixie_cuda_draw_correct
+    check(fn(dst.handle, src.handle, m.ctypes.data, mode))
+
+
+def _new_image_from_handle(handle) -> DeviceImage:
+    w, h, l, b = i32(0), i32(0), i32(0), i32(0)
+    check(lib().pixie_cuda_image_info(handle, C.byref(w), C.byref(h), C.byref(l), C.byref(b), None))
+    return DeviceImage(w.value, h.value, l.value, b.value == 1, _handle=handle)
+
+
+def minify_by2(src: DeviceImage, power=1) -> DeviceImage:
+    h = u64(0)
+    check(lib().pixie_cuda_minify_by2(src.handle, power, C.byref(h)))
+    return _new_image_from_handle(h.value)
+
+
+def magnify_by2(src: DeviceImage, power=1) -> DeviceImage:
+    h = u64(0)
+    check(lib().pixie_cuda_magnify_by2(src.handle, power, C.byref(h)))
+    return _new_image_from_handle(h.value)
+
+
+def fill_gradient(image: DeviceImage, kind, handles, stops, opacity=1.0):
+    """fillGradient (paints.nim:236-248); stops: [(position, (r, g, b, a))] float colours."""
+    hx = np.ascontiguousarray(np.asarray(handles, np.float32).reshape(-1))
+    pos = np.ascontiguousarray([s[0] for s in stops], np.float32)
+    col = np.ascontiguousarray([s[1] for s in stops], np.float32).reshape(-1)
+    check(lib().pixie_cuda_fill_gradient(image.handle, kind, hx.ctypes.data, len(hx) // 2, pos.ctypes.data,
+                                         col.ctypes.data, len(stops), opacity))
 
 
 def blur(image: DeviceImage, lut, radius, oob=0):

@@ -51,3 +51,29 @@ class GpuBackend:
         d = dev.DeviceImage(img.shape[1], img.shape[0])
         dev.shadow(s, d, ox, oy, spread, lut, radius, rgbx)
         return d.download()
+
+    def apply_opacity(self, img, opacity):
+        d = self._up(img)
+        dev.apply_opacity(d, opacity)
+        d.download(img)
+
+    def draw(self, dst, src, mat, mode):
+        d, s = self._up(dst), self._up(np.ascontiguousarray(src))
+        dev.draw(d, s, mat, mode)
+        d.download(dst)
+
+    def draw_tiled(self, dst, src, mat, mode, tiled=True):
+        d, s = self._up(dst), self._up(np.ascontiguousarray(src))
+        dev.draw_tiled(d, s, mat, mode, tiled)
+        d.download(dst)
+
+    def minify_by2(self, img, power=1):
+        return dev.minify_by2(self._up(np.ascontiguousarray(img)), power).download()
+
+    def magnify_by2(self, img, power=1):
+        return dev.magnify_by2(self._up(np.ascontiguousarray(img)), power).download()
+
+    def fill_gradient(self, img, kind, handles, stops, opacity=1.0):
+        d = self._up(img)
+        dev.fill_gradient(d, kind, handles, stops, opacity)
+        d.download(img)

@@ -70,8 +70,8 @@ def test_paint_opacity_stroke_and_errors():  # tests/test_paths.nim:595-606
         pixie.newImage(0, 5)
     with pytest.raises(PixieError, match="negative blur"):
         image.blur(-3)
-    with pytest.raises(PixieError, match="drawSmooth"):
-        image.draw(pixie.newImage(10, 10), host.scale(0.5, 0.5))
+    with pytest.raises(PixieError, match="Cannot minifyBy2 with negative power"):
+        image.minifyBy2(-1)
 
 
 def test_image_paint_composite_matches_two_draws():

@@ -1,0 +1,235 @@
+"""GPU parity of draw-with-transform, minify / magnify and the gradient paints (through the C ABI) against
+the CPU oracle on seeded inputs: bit-exact for every blend mode, transform class and odd size.
+(images.nim:168-259, :367-449, :531-683; paints.nim:68-248)"""
+import math
+
+import numpy as np
+import pytest
+
+from pixie_b200 import host, synth
+from pixie_b200.common import MaskBlend, NormalBlend, OverwriteBlend
+
+pytestmark = pytest.mark.gpu
+
+f = np.float32
+
+
+def _backends():
+    from _gpu_backend import GpuBackend
+    from _oracle import OracleBackend
+
+    return GpuBackend(), OracleBackend(0)
+
+
+def _rand(h, w, seed):
+    return synth.random_premultiplied(h, w, seed)
+
+
+def _T(x, y):
+    return host.translate(f(x), f(y))
+
+
+def _mats():
+    r = lambda deg: host.rotate(f(f(deg) * f(math.pi) / f(180)))
+    return {
+        "identity": host.mat3(),
+        "int_translate": _T(7, -3),
+        "frac_translate": _T(10.25, 3.75),
+        "rotate30": host.matmul(_T(40, 10), r(30)),
+        "rotate-75_scale": host.matmul(host.matmul(_T(5, 60), r(-75)), host.scale(f(1.3), f(0.8))),
+        "scale_half": host.matmul(_T(3, 3), host.scale(f(0.5), f(0.5))),
+        "scale_0.2": host.scale(f(0.2), f(0.2)),
+        "scale_3.7": host.matmul(_T(-20, -30), host.scale(f(3.7), f(3.7))),
+        "scale_0.07_rot": host.matmul(host.matmul(_T(50, 50), r(12)), host.scale(f(0.07), f(0.07))),
+        "shear": np.array([1, 0.3, 0, -0.2, 1, 0, 12, 5, 1], np.float32),
+        "flip": host.matmul(_T(90, 0), host.scale(f(-1), f(1))),
+        "offscreen": _T(500, 500),
+    }
+
+
+@pytest.mark.parametrize("name", sorted(_mats()))
+@pytest.mark.parametrize("mode", [NormalBlend, OverwriteBlend, MaskBlend, 2, 8, 11, 19])
+def test_draw_transforms(name, mode):
+    gb, ob = _backends()
+    src = _rand(97, 131, 5)
+    base = _rand(101, 127, 6)
+    a, b = base.copy(), base.copy()
+    gb.draw(a, src, _mats()[name], mode)
+    ob.draw(b, src, _mats()[name], mode)
+    d = np.abs(a.astype(int) - b.astype(int))
+    assert d.max() == 0, f"{name} mode {mode}: {(d.max(-1) > 0).sum()} px differ, max {d.max()}"
+
+
+@pytest.mark.parametrize("mode", list(range(20)))
+def test_draw_smooth_all_modes(mode):
+    gb, ob = _backends()
+    src = _rand(64, 64, 7 + mode)
+    base = _rand(80, 96, 8)
+    m = host.matmul(_T(20.5, 9.25), host.rotate(f(0.4)))
+    a, b = base.copy(), base.copy()
+    gb.draw(a, src, m, mode)
+    ob.draw(b, src, m, mode)
+    assert np.array_equal(a, b), f"mode {mode}: {(np.abs(a.astype(int) - b.astype(int)).max(-1) > 0).sum()} px differ"
+
+
+def test_draw_large_wide_rows():
+    """Rows longer than one warp pass many times: the position accumulates over thousands of additions."""
+    gb, ob = _backends()
+    src = _rand(300, 2100, 9)
+    base = _rand(256, 4100, 10)
+    m = host.matmul(_T(3.3, -20.7), host.scale(f(1.9), f(1.1)))
+    a, b = base.copy(), base.copy()
+    gb.draw(a, src, m, NormalBlend)
+    ob.draw(b, src, m, NormalBlend)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("tiled", [True, False])
+@pytest.mark.parametrize("mode", [NormalBlend, 5, MaskBlend])
+def test_draw_correct(tiled, mode):
+    gb, ob = _backends()
+    src = _rand(37, 53, 11)
+    base = _rand(90, 110, 12)
+    for m in (host.scale(f(0.3), f(0.3)), host.matmul(_T(13.5, 4.5), host.rotate(f(-0.3))), host.scale(f(2.5), f(2.5)),
+              _T(-30.5, -20.25)):
+        a, b = base.copy(), base.copy()
+        gb.draw_tiled(a, src, m, mode, tiled)
+        ob.draw_tiled(b, src, m, mode, tiled)
+        assert np.array_equal(a, b), f"tiled={tiled} mode={mode}"
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 2), (3, 5), (99, 101), (100, 100), (257, 64), (64, 257), (1, 9), (9, 1)])
+def test_minify_magnify(shape):
+    gb, ob = _backends()
+    img = _rand(shape[0], shape[1], 13)
+    for power in (0, 1, 2, 3):
+        assert np.array_equal(gb.minify_by2(img, power), ob.minify_by2(img, power)), f"minify {shape} power {power}"
+    for power in (0, 1, 2):
+        assert np.array_equal(gb.magnify_by2(img, power), ob.magnify_by2(img, power)), f"magnify {shape} power {power}"
+
+
+def test_minify_negative_power_raises():
+    from pixie_b200 import device as dev
+    from pixie_b200.common import PixieError
+
+    dev.init(0)
+    d = dev.DeviceImage(4, 4)
+    with pytest.raises(PixieError, match="Cannot minifyBy2 with negative power"):
+        dev.minify_by2(d, -1)
+    with pytest.raises(PixieError, match="Cannot magnifyBy2 with negative power"):
+        dev.magnify_by2(d, -1)
+
+
+_STOPS3 = [(0.0, (1, 0, 0, 1)), (0.3, (0, 1, 0, 0.5)), (0.8, (0.2, 0.4, 1, 1)), (1.0, (1, 1, 1, 0.1))]
+
+
+@pytest.mark.parametrize("kind,handles", [
+    (3, [(0, 50), (100, 50)]), (3, [(50, 0), (50, 100)]), (3, [(10, 20), (150, 90)]), (3, [(120, 80), (-10, 5)]),
+    (4, [(50, 50), (100, 50), (50, 100)]), (4, [(70, 40), (120, 90), (30, 60)]),
+    (5, [(50, 50), (100, 50), (50, 100)]), (5, [(81.5, 33.25), (10, 90), (0, 0)]),
+])
+@pytest.mark.parametrize("opacity", [1.0, 0.37])
+def test_gradients(kind, handles, opacity):
+    gb, ob = _backends()
+    for shape in ((100, 100), (77, 203)):
+        a = _rand(shape[0], shape[1], 14)
+        b = a.copy()
+        gb.fill_gradient(a, kind, handles, _STOPS3, opacity)
+        ob.fill_gradient(b, kind, handles, _STOPS3, opacity)
+        d = np.abs(a.astype(int) - b.astype(int))
+        assert d.max() == 0, f"kind {kind} {handles}: {(d.max(-1) > 0).sum()} px differ, max {d.max()}"
+
+
+def test_gradient_errors_and_single_stop():
+    from pixie_b200 import device as dev
+    from pixie_b200.common import PixieError
+
+    gb, ob = _backends()
+    d = dev.DeviceImage(8, 8)
+    with pytest.raises(PixieError, match="Linear gradient requires 2 handles"):
+        dev.fill_gradient(d, 3, [(0, 0)], _STOPS3)
+    with pytest.raises(PixieError, match="Radial gradient requires 3 handles"):
+        dev.fill_gradient(d, 4, [(0, 0), (1, 1)], _STOPS3)
+    with pytest.raises(PixieError, match="Gradient must have at least 1 color stop"):
+        dev.fill_gradient(d, 3, [(0, 0), (1, 1)], [])
+    a = np.zeros((16, 16, 4), np.uint8)
+    b = a.copy()
+    gb.fill_gradient(a, 3, [(0, 0), (16, 16)], [(0.5, (0.2, 0.5, 0.7, 0.6))])
+    ob.fill_gradient(b, 3, [(0, 0), (16, 16)], [(0.5, (0.2, 0.5, 0.7, 0.6))])
+    assert np.array_equal(a, b) and a.any()
+
+
+def test_shadow_fractional_offset():
+    """shadow() with a fractional offset: the offset copy goes through drawSmooth (images.nim:768-769)."""
+    gb, ob = _backends()
+    img = np.zeros((90, 120, 4), np.uint8)
+    img[20:60, 30:90] = (255, 255, 255, 255)
+    lut = host.gaussianKernel(6)
+    got = gb.shadow(img, 3.5, -2.25, 2, lut, 6, 0xC8000000)
+    want = ob.shadow(img, 3.5, -2.25, 2, lut, 6, 0xC8000000)
+    assert np.array_equal(got, want)
+
+
+def test_api_paints_match_reference_goldens():
+    """tests/test_paints.nim written against pixie_b200.api: gradient and image paints, byte for byte."""
+    import golden_cases as gc
+    from pixie_b200 import api as pixie
+
+    stops = [pixie.ColorStop((1, 0, 0, 1), 0.0), pixie.ColorStop((1, 0, 0, 0.15625), 1.0)]
+    for golden, kind, handles, opacity in [
+        ("paths_gradientLinear.png", pixie.LinearGradientPaint, [(0, 50), (100, 50)], 1.0),
+        ("paths_gradientLinear2.png", pixie.LinearGradientPaint, [(50, 0), (50, 100)], 1.0),
+        ("paths_gradientRadial.png", pixie.RadialGradientPaint, [(50, 50), (100, 50), (50, 100)], 1.0),
+        ("paths_gradientAngular.png", pixie.AngularGradientPaint, [(50, 50), (100, 50), (50, 100)], 1.0),
+        ("paths_gradientAngularOpacity.png", pixie.AngularGradientPaint, [(50, 50), (100, 50), (50, 100)], 0.5),
+    ]:
+        paint = pixie.newPaint(kind)
+        paint.gradientHandlePositions = handles
+        paint.gradientStops = stops
+        paint.opacity = opacity
+        image = pixie.newImage(100, 100)
+        image.fillPath(gc.HEART_PAINT, paint)
+        assert gc.compare(image.data, gc.load_golden(golden)) == (0, 0), golden
+
+    mandrill = pixie.newImage(512, 512)
+    mandrill.data = gc.load_golden("fileformats_png_mandrill.png")
+    for golden, kind, s, opacity in [
+        ("paths_paintImage.png", pixie.ImagePaint, 0.2, 1.0), ("paths_paintImageOpacity.png", pixie.ImagePaint, 0.2, 0.5),
+        ("paths_paintImageTiled.png", pixie.TiledImagePaint, 0.02, 1.0),
+        ("paths_paintImageTiledOpacity.png", pixie.TiledImagePaint, 0.02, 0.5),
+    ]:
+        paint = pixie.newPaint(kind)
+        paint.image = mandrill
+        paint.imageMat = host.scale(f(s), f(s))
+        paint.opacity = opacity
+        image = pixie.newImage(100, 100)
+        image.fillPath(gc.HEART_PAINT, paint)
+        assert gc.compare(image.data, gc.load_golden(golden)) == (0, 0), golden
+
+    for golden, kind, s in [("paths_fillImagePaint.png", pixie.ImagePaint, 0.2),
+                            ("paths_fillTiledImagePaint.png", pixie.TiledImagePaint, 0.1)]:
+        paint = pixie.newPaint(kind)
+        paint.image = mandrill
+        paint.imageMat = host.scale(f(s), f(s))
+        paint.opacity = 0.5
+        image = pixie.newImage(128, 128)
+        image.fill((0, 255, 0, 255))
+        image.fill(paint)
+        assert gc.compare(image.data, gc.load_golden(golden)) == (0, 0), golden
+
+
+def test_api_draw_rotate_and_resize():
+    import golden_cases as gc
+    from pixie_b200 import api as pixie
+
+    a = pixie.newImage(1000, 1000)
+    b = pixie.newImage(500, 500)
+    a.fill((255, 0, 0, 255))
+    b.fill((0, 255, 0, 255))
+    a.draw(b, host.matmul(_T(250, 250), host.rotate(f(f(-90) * f(math.pi) / f(180)))))
+    assert gc.compare(a.data, gc.load_golden("images_rotate90.png")) == (0, 0)
+    small = b.resize(100, 60)
+    assert (small.width, small.height) == (100, 60)
+    assert tuple(small[50, 30]) == (0, 255, 0, 255)
+    mini = a.minifyBy2(2)
+    assert (mini.width, mini.height) == (250, 250)

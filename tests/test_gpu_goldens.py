@@ -16,5 +16,8 @@ def test_gpu_matches_oracle_and_golden(name):
     want = gc.CASES[name](ob)
     mism, mx = gc.compare(got, want)
     assert (mism, mx) == (0, 0), f"{name}: GPU vs oracle {mism} px differ (max {mx})"
-    assert gc.compare(got, gc.load_golden(name)) == (0, 0), f"{name}: GPU vs reference golden"
+    if name in gc.SCORE_ONLY:  # masters the reference itself only scores (golden_cases.SCORE_ONLY)
+        assert gc.xray_score(got, gc.load_golden(name)) < gc.SCORE_ONLY[name]
+    else:
+        assert gc.compare(got, gc.load_golden(name)) == (0, 0), f"{name}: GPU vs reference golden"
     assert gb.covered == ob.covered, f"{name}: covered-pixel count {gb.covered} != {ob.covered}"
