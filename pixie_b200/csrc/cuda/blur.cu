@@ -11,6 +11,9 @@
 // (lane = line, so every shared-memory access is conflict-free), each warp keeps a sliding window
 // of 8 unpacked pixels in registers and produces 8 outputs per line: 32 IMAD per tap against
 // 1 LDS + 4 PRMT.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace pixie {
@@ -352,6 +355,8 @@ static int launch_f32(ConvArgs a, Image* im, void* tmp, const uint16_t* lut_d, i
   return 0;
 }
 
+int blur_mma(Image* im, void* tmp, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1);  // blur_mma.cu
+
 static int blur_impl(Image* im, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1) {
   Runtime& r = rt();
   if (radius == 0) return 0;
@@ -363,6 +368,14 @@ static int blur_impl(Image* im, const uint16_t* lut_host, int radius, uint32_t o
   const int ntaps = 2 * radius + 1;
   void *tmp, *lut_d, *pin;
   if (int rc = get_scratch(0, im->bytes(), &tmp)) return rc;
+  {  // radii 1..64 with an exactly representable contraction go to the tensor cores (blur_mma.cu);
+     // PIXIE_CUDA_BLUR=cores keeps the CUDA-core kernels (A/B timing, parity tests of both paths)
+    static const char* force = getenv("PIXIE_CUDA_BLUR");
+    if (!(force && strcmp(force, "cores") == 0)) {
+      const int rc = blur_mma(im, tmp, lut_host, radius, oob, y0, y1);
+      if (rc >= 0) return rc;
+    }
+  }
   if (int rc = get_scratch(1, (size_t)ntaps * 2, &lut_d)) return rc;
   if (int rc = staging_acquire((size_t)ntaps * 2, &pin)) return rc;
   memcpy(pin, lut_host, (size_t)ntaps * 2);

@@ -1,0 +1,324 @@
+// K5b — the separable Gaussian blur (images.nim:304-365) as an exact banded contraction on the tensor cores.
+//
+// A blur pass is  out[a] = (sum_t lut[t] * in[a - r + t]) div 256 div 255  per channel and line: a Toeplitz
+// (banded) matrix times the pixel columns.  With 65 taps x 4 channels x 2 passes per pixel the CUDA-core
+// kernels of blur.cu are ALU-bound at ~4 % of the HBM roofline; the contraction itself is
+// exact in the tensor cores' number formats:
+//   * pixel bytes 0..255 are exact in fp16;
+//   * a uint16 tap k splits into  k = lo + hi * 2048  with lo < 2048 (11 significant bits) and hi * 2048 <= 63488,
+//     both exact in fp16 (Gaussian LUTs of radius >= 29 have hi == 0 everywhere: one MMA per tile);
+//   * every product is an integer < 2^24 and so is every partial sum (sum lut * 255 < 2^24 is checked by the
+//     caller), so the fp32 accumulation never rounds.
+// The results are therefore bit-identical to the reference's uint32 arithmetic; `div 256 div 255` happens in
+// integer registers after the accumulator is read back.
+//
+// Shape: mma.sync.m16n8k16 (fp16 x fp16 -> fp32).  M = 16 outputs along the blur axis, K = 16 inputs, N = 8
+// lines.  The A operand is the Toeplitz block  A_q[m][k] = lut[16 q + k - m]  (q = 0 .. KT-1 with
+// KT = ceil((2r + 16) / 16)); it is the same for every tile, lives in registers, and only KT of the
+// (outputs/16 + KT - 1) k-tiles of a row of tiles are non-zero — 65/80 of the multiply-adds are useful at r = 32.
+// B is the pixel data, staged global -> shared as four planar fp16 channel planes (coalesced 4-byte loads, one
+// PRMT + HSUB2 per two bytes) and read back with ldmatrix (.trans for the vertical pass), each k-tile once per warp
+// for all the m-tiles it feeds.  One CTA = 128 outputs x 32 lines x 4 channels; a warp owns 4 m-tiles x 8 lines.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace pixie {
+
+struct MmaBlurArgs {
+  const px_t* src;
+  px_t* dst;
+  int w, h;
+  int radius;
+  uint32_t oob;
+  int y0, y1;    // vertical pass: output rows
+  int sy0, sy1;  // horizontal pass: rows to produce
+  int pitch;     // shared-memory row pitch in halfs
+  int hasHi;     // some tap >= 2048
+};
+
+constexpr int kMmaOut = 128;   // outputs per CTA along the blur axis
+constexpr int kMmaLines = 32;  // lines per CTA
+constexpr int kMaxTaps = 2 * 64 + 1;
+__constant__ uint16_t c_mma_lut[kMaxTaps + 3];
+
+PXD void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <bool TRANS>
+PXD void ldmatrix_x2(uint32_t& r0, uint32_t& r1, const __half* p) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  if (TRANS) asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(addr));
+  else asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+PXD uint32_t pack_h2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+PXD int tap_at(int t, int ntaps) { return (t >= 0 && t < ntaps) ? (int)c_mma_lut[t] : 0; }
+
+PXD void cp_async_4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+PXD void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+PXD void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// VERTICAL = false: blur along x: a tile is 32 rows (lines) x IN_A pixels, planes are [line][a];
+// VERTICAL = true:  blur along y: a tile is IN_A rows x 32 pixels (lines), planes are [a][line], read with
+//                   ldmatrix.trans.  Either way the raw tile and the planes are [tile row][tile column] with the
+// image's x running along the columns, so staging and conversion are the same code.
+//
+// Persistent CTAs: the Toeplitz fragments are built once; per tile the raw RGBX bytes of the NEXT tile are
+// fetched with cp.async while the tensor cores work on the current one.
+template <bool VERTICAL, int KT>
+__global__ void __launch_bounds__(256) blur_mma_kernel(const MmaBlurArgs a, int tilesA, int numTiles) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int IN_A = kMmaOut - 16 + 16 * KT;  // inputs along the blur axis
+  constexpr int ROWS = VERTICAL ? IN_A : kMmaLines, COLS = VERTICAL ? kMmaLines : IN_A;  // tile shape in pixels
+  const int pitch = a.pitch;
+  const int planeHalfs = ROWS * pitch;
+  __half* planes = reinterpret_cast<__half*>(smem_raw);
+  px_t* raw = reinterpret_cast<px_t*>(smem_raw + (size_t)4 * planeHalfs * sizeof(__half));  // ROWS x COLS pixels
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ntaps = 2 * a.radius + 1;
+  const int a_len = VERTICAL ? a.h : a.w;
+  const int l_end = VERTICAL ? a.w : a.sy1;
+  const bool vec_ok = (a.w & 3) == 0 && (reinterpret_cast<uintptr_t>(a.src) & 15) == 0 && (VERTICAL || (a.radius & 3) == 0);
+
+  // ---- Toeplitz fragments (row-major m16 x k16): A_q[m][k] = lut[16 q + k - m], split lo + hi * 2048
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t Alo[KT][4], Ahi[KT][4];
+#pragma unroll
+  for (int q = 0; q < KT; q++) {
+#pragma unroll
+    for (int rIdx = 0; rIdx < 4; rIdx++) {
+      const int m = g + ((rIdx & 1) ? 8 : 0), k = 2 * t + ((rIdx & 2) ? 8 : 0);
+      const int k0 = tap_at(16 * q + k - m, ntaps), k1 = tap_at(16 * q + k + 1 - m, ntaps);
+      Alo[q][rIdx] = pack_h2((float)(k0 & 2047), (float)(k1 & 2047));
+      Ahi[q][rIdx] = pack_h2((float)((k0 >> 11) << 11), (float)((k1 >> 11) << 11));
+    }
+  }
+
+  auto tile_origin = [&](int tile, int& a0, int& l0) {
+    const int ta = tile % tilesA, tl = tile / tilesA;
+    a0 = ta * kMmaOut + (VERTICAL ? a.y0 : 0);     // first output along the blur axis
+    l0 = tl * kMmaLines + (VERTICAL ? 0 : a.sy0);  // first line
+  };
+  // raw tile <- global (cp.async), out-of-image pixels <- the out-of-bounds colour
+  auto prefetch = [&](int tile) {
+    int a0, l0;
+    tile_origin(tile, a0, l0);
+    const int x0 = VERTICAL ? l0 : a0 - a.radius, y0 = VERTICAL ? a0 - a.radius : l0;
+    const int xEnd = VERTICAL ? l_end : a_len, yEnd = VERTICAL ? a_len : l_end;
+    constexpr int G = COLS / 4;  // groups of 4 pixels per tile row
+    for (int idx = tid; idx < ROWS * G; idx += 256) {
+      const int row = idx / G, c4 = (idx - row * G) * 4;
+      const int y = y0 + row, x = x0 + c4;
+      px_t* dst = raw + row * COLS + c4;
+      const bool rowIn = y >= 0 && y < yEnd;
+      if (rowIn && vec_ok && x >= 0 && x + 4 <= xEnd) {
+        cp_async_16(dst, a.src + (size_t)a.w * y + x);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (rowIn && x + j >= 0 && x + j < xEnd) cp_async_4(dst + j, a.src + (size_t)a.w * y + x + j);
+          else dst[j] = a.oob;
+        }
+      }
+    }
+  };
+
+  const uint32_t magic = 0x64006400u;  // half2(1024, 1024): 0x6400 | byte is the half 1024 + byte
+  const __half2 magic_h = *reinterpret_cast<const __half2*>(&magic);
+  const int nt = warp & 3, mg = warp >> 2;
+
+  int tile = blockIdx.x;
+  if (tile < numTiles) prefetch(tile);
+#pragma unroll 1
+  for (; tile < numTiles; tile += gridDim.x) {
+    cp_async_wait_all();
+    __syncthreads();  // the raw tile is complete, and nobody reads the planes of the previous tile any more
+    {                 // raw RGBX bytes -> four planar fp16 planes, 4 pixels per thread and step
+      constexpr int G = COLS / 4;
+      for (int idx = tid; idx < ROWS * G; idx += 256) {
+        const int row = idx / G, c4 = (idx - row * G) * 4;
+        const uint4 p = *reinterpret_cast<const uint4*>(raw + row * COLS + c4);
+        const uint32_t rg01 = __byte_perm(p.x, p.y, 0x5140), ba01 = __byte_perm(p.x, p.y, 0x7362);
+        const uint32_t rg23 = __byte_perm(p.z, p.w, 0x5140), ba23 = __byte_perm(p.z, p.w, 0x7362);
+        uint32_t w[8];
+        w[0] = __byte_perm(rg01, 0x64u, 0x4140); w[1] = __byte_perm(rg23, 0x64u, 0x4140);  // r0 r1 | r2 r3
+        w[2] = __byte_perm(rg01, 0x64u, 0x4342); w[3] = __byte_perm(rg23, 0x64u, 0x4342);  // g
+        w[4] = __byte_perm(ba01, 0x64u, 0x4140); w[5] = __byte_perm(ba23, 0x64u, 0x4140);  // b
+        w[6] = __byte_perm(ba01, 0x64u, 0x4342); w[7] = __byte_perm(ba23, 0x64u, 0x4342);  // a
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const __half2 hv = __hsub2(*reinterpret_cast<const __half2*>(&w[k]), magic_h);
+          w[k] = *reinterpret_cast<const uint32_t*>(&hv);
+        }
+        __half* d = planes + row * pitch + c4;
+#pragma unroll
+        for (int c = 0; c < 4; c++) *reinterpret_cast<uint2*>(d + c * planeHalfs) = make_uint2(w[2 * c], w[2 * c + 1]);
+      }
+    }
+    __syncthreads();  // planes ready; the raw buffer is free again
+    if (tile + (int)gridDim.x < numTiles) prefetch(tile + gridDim.x);
+
+    int a0, l0;
+    tile_origin(tile, a0, l0);
+    // ---- contraction: warp = 8 lines (nt) x 4 m-tiles (mg), all four channels
+    uint32_t pix[4][4];  // [m-tile][fragment slot]: packed RGBX of the lane's 4 outputs per m-tile
+#pragma unroll
+    for (int i = 0; i < 4; i++) pix[i][0] = pix[i][1] = pix[i][2] = pix[i][3] = 0u;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
+      const __half* plane = planes + c * planeHalfs;
+#pragma unroll
+      for (int kt = 0; kt < 4 + KT - 1; kt++) {
+        const int kbase = (mg * 4 + kt) * 16;  // first input of this k-tile, relative to the tile origin
+        uint32_t b0, b1;
+        if (VERTICAL) {  // rows of the stored matrix = inputs (k), columns = lines
+          ldmatrix_x2<true>(b0, b1, plane + (kbase + (lane & 15)) * pitch + nt * 8);
+        } else {  // rows of the stored matrix = lines, columns = inputs (k)
+          ldmatrix_x2<false>(b0, b1, plane + (nt * 8 + (lane & 7)) * pitch + kbase + ((lane & 8) ? 8 : 0));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int q = kt - i;
+          if (q >= 0 && q < KT) {
+            mma_16816(acc[i], Alo[q], b0, b1);
+            if (a.hasHi) mma_16816(acc[i], Ahi[q], b0, b1);
+          }
+        }
+      }
+      // div 256 div 255 == div 65280 (images.nim:332-338), then the channel goes into its byte
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int s_ = 0; s_ < 4; s_++) pix[i][s_] |= (((uint32_t)acc[i][s_]) / 65280u) << (8 * c);
+      }
+    }
+
+    // ---- store: fragment slot s of m-tile i is output (m = g + 8 (s >> 1), n = 2 t + (s & 1))
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int abase = a0 + (mg * 4 + i) * 16;
+      if (VERTICAL) {
+        const int x = l0 + nt * 8 + 2 * t;
+#pragma unroll
+        for (int hrow = 0; hrow < 2; hrow++) {
+          const int y = abase + g + 8 * hrow;
+          if (y < a.y1 && y < a.h) {
+            px_t* p = a.dst + (size_t)a.w * y + x;
+            if (x + 1 < a.w && ((reinterpret_cast<uintptr_t>(p) & 7) == 0)) {
+              *reinterpret_cast<uint2*>(p) = make_uint2(pix[i][2 * hrow], pix[i][2 * hrow + 1]);
+            } else {
+              if (x < a.w) p[0] = pix[i][2 * hrow];
+              if (x + 1 < a.w) p[1] = pix[i][2 * hrow + 1];
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s_ = 0; s_ < 4; s_++) {
+          const int x = abase + g + 8 * (s_ >> 1), y = l0 + nt * 8 + 2 * t + (s_ & 1);
+          if (x < a.w && y < l_end) a.dst[(size_t)a.w * y + x] = pix[i][s_];
+        }
+      }
+    }
+  }
+}
+
+template <bool VERTICAL, int KT>
+static int launch_pass(const MmaBlurArgs& a, int tilesA, int tilesL, size_t smem, cudaStream_t st) {
+  static size_t configured = 0;
+  static int perSm = 1;
+  if (configured != smem) {
+    if (smem > 48 * 1024)
+      PX_CUDA(cudaFuncSetAttribute(blur_mma_kernel<VERTICAL, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, blur_mma_kernel<VERTICAL, KT>, 256, smem));
+    perSm = std::max(1, perSm);
+    configured = smem;
+  }
+  const int numTiles = tilesA * tilesL;
+  if (numTiles <= 0) return 0;
+  const int grid = std::min(numTiles, rt().num_sms * perSm);
+  blur_mma_kernel<VERTICAL, KT><<<grid, 256, smem, st>>>(a, tilesA, numTiles);
+  PX_LAUNCHED();
+  return 0;
+}
+
+template <int KT>
+static int launch_both(MmaBlurArgs a, Image* im, void* tmp, int y0, int y1) {
+  Runtime& r = rt();
+  constexpr int IN_A = kMmaOut - 16 + 16 * KT;
+  const size_t rawBytes = (size_t)IN_A * kMmaLines * 4;
+  {  // X pass: image -> tmp, rows [sy0, sy1).  Plane [line][a]: pitch = 8 mod 64 halfs keeps ldmatrix conflict-free
+    a.src = (const px_t*)im->data; a.dst = (px_t*)tmp;
+    a.pitch = IN_A + ((8 - IN_A) % 64 + 64) % 64;
+    const size_t smem = (size_t)4 * kMmaLines * a.pitch * sizeof(__half) + rawBytes;
+    ProfScope ps(kProfBlurX);
+    if (int rc = launch_pass<false, KT>(a, (im->w + kMmaOut - 1) / kMmaOut, (a.sy1 - a.sy0 + kMmaLines - 1) / kMmaLines, smem,
+                                        r.stream))
+      return rc;
+  }
+  {  // Y pass: tmp -> image rows [y0, y1).  Plane [a][line]: 40-half rows
+    a.src = (const px_t*)tmp; a.dst = (px_t*)im->data;
+    a.pitch = kMmaLines + 8;
+    const size_t smem = (size_t)4 * IN_A * a.pitch * sizeof(__half) + rawBytes;
+    ProfScope ps(kProfBlurY);
+    if (int rc = launch_pass<true, KT>(a, (y1 - y0 + kMmaOut - 1) / kMmaOut, (im->w + kMmaLines - 1) / kMmaLines, smem, r.stream))
+      return rc;
+  }
+  return 0;
+}
+
+// Tensor-core blur of rows [y0, y1) of `im` through the scratch plane `tmp`.  Returns -1 when the radius / LUT is
+// outside what this path holds exactly (the caller then takes the CUDA-core kernels).
+int blur_mma(Image* im, void* tmp, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1) {
+  const int ntaps = 2 * radius + 1;
+  if (radius < 1 || ntaps > kMaxTaps) return -1;
+  unsigned long long sum = 0;
+  int hasHi = 0;
+  for (int i = 0; i < ntaps; i++) {
+    sum += lut_host[i];
+    if (lut_host[i] >= 2048) hasHi = 1;
+  }
+  if (sum * 255ull >= (1ull << 24)) return -1;  // partial sums must stay exact in fp32
+  Runtime& r = rt();
+  {
+    void* pin;
+    if (int rc = staging_acquire(sizeof(uint16_t) * (kMaxTaps + 3), &pin)) return rc;
+    memset(pin, 0, sizeof(uint16_t) * (kMaxTaps + 3));
+    memcpy(pin, lut_host, (size_t)ntaps * 2);
+    PX_CUDA(cudaMemcpyToSymbolAsync(c_mma_lut, pin, sizeof(uint16_t) * (kMaxTaps + 3), 0, cudaMemcpyHostToDevice, r.stream));
+    if (int rc = staging_release()) return rc;
+  }
+  MmaBlurArgs a;
+  a.w = im->w; a.h = im->h; a.radius = radius; a.oob = oob; a.hasHi = hasHi;
+  a.y0 = y0; a.y1 = y1;
+  a.sy0 = std::max(0, y0 - radius);
+  a.sy1 = std::min(im->h, y1 + radius);
+  a.pitch = 0; a.src = nullptr; a.dst = nullptr;
+  const int KT = (2 * radius + 16 + 15) / 16;
+  switch (KT) {
+    case 2: return launch_both<2>(a, im, tmp, y0, y1);
+    case 3: return launch_both<3>(a, im, tmp, y0, y1);
+    case 4: return launch_both<4>(a, im, tmp, y0, y1);
+    case 5: return launch_both<5>(a, im, tmp, y0, y1);
+    case 6: return launch_both<6>(a, im, tmp, y0, y1);
+    case 7: return launch_both<7>(a, im, tmp, y0, y1);
+    case 8: return launch_both<8>(a, im, tmp, y0, y1);
+    case 9: return launch_both<9>(a, im, tmp, y0, y1);
+    default: return -1;
+  }
+}
+
+}  // namespace pixie

@@ -360,7 +360,6 @@ struct RasterArgs {
 };
 
 constexpr int kScratchArrays = 18;  // scratch words per band entry (see the layout in plan_row)
-constexpr int kHeavyJob = 48;       // plan_kernel runs the jobs of bands with more entries than this first
 constexpr int kPaySlots = 5;        // payload slots per entry-row: <= 5 spans (one per sample line) or 2 per edge
 
 constexpr int GenericMode = -1;  // every mode that goes through blender() per pixel, chosen at run time
@@ -464,10 +463,6 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
   const int W = A.w;
   const float wf = (float)W;
   const int warpsTotal = gridDim.x * warpsPerBlock;
-  // two passes: the jobs of crowded bands first (a single one can take tens of microseconds: the sorts are
-  // quadratic), so that the tail of the kernel is made of short jobs
-#pragma unroll 1
-  for (int pass = 0; pass < 2; pass++)
 #pragma unroll 1
   for (int bj = blockIdx.x * warpsPerBlock + warp; bj < A.planJobs; bj += warpsTotal) {
     const int f = find_fill_by_job(A.planJobBase, A.numFills, bj);
@@ -481,7 +476,6 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
     const int gp = Hp->partBase + p;
     const int eBeg = A.entryOff[gp];
     const int eCnt = A.entryOff[gp + 1] - eBeg;
-    if ((eCnt > kHeavyJob) != (pass == 0)) continue;
     const unsigned fl = A.flags[gp];
     const Entry* ent = A.entries + eBeg;
     uint2* pay = A.payload + ((size_t)A.payOff[gp] + (size_t)(y - (startY + p * ph)) * (size_t)eCnt) * kPaySlots;
