@@ -75,7 +75,7 @@ PXD void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory")
 //
 // Persistent CTAs: the Toeplitz fragments are built once; per tile the raw RGBX bytes of the NEXT tile are
 // fetched with cp.async while the tensor cores work on the current one.
-template <bool VERTICAL, int KT>
+template <bool VERTICAL, int KT, bool HI>
 __global__ void __launch_bounds__(256) blur_mma_kernel(const MmaBlurArgs a, int tilesA, int numTiles) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int IN_A = kMmaOut - 16 + 16 * KT;  // inputs along the blur axis
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) blur_mma_kernel(const MmaBlurArgs a, int 
 
   // ---- Toeplitz fragments (row-major m16 x k16): A_q[m][k] = lut[16 q + k - m], split lo + hi * 2048
   const int g = lane >> 2, t = lane & 3;
-  uint32_t Alo[KT][4], Ahi[KT][4];
+  uint32_t Alo[KT][4], Ahi[HI ? KT : 1][4];
 #pragma unroll
   for (int q = 0; q < KT; q++) {
 #pragma unroll
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) blur_mma_kernel(const MmaBlurArgs a, int 
       const int m = g + ((rIdx & 1) ? 8 : 0), k = 2 * t + ((rIdx & 2) ? 8 : 0);
       const int k0 = tap_at(16 * q + k - m, ntaps), k1 = tap_at(16 * q + k + 1 - m, ntaps);
       Alo[q][rIdx] = pack_h2((float)(k0 & 2047), (float)(k1 & 2047));
-      Ahi[q][rIdx] = pack_h2((float)((k0 >> 11) << 11), (float)((k1 >> 11) << 11));
+      if (HI) Ahi[q][rIdx] = pack_h2((float)((k0 >> 11) << 11), (float)((k1 >> 11) << 11));
     }
   }
 
@@ -171,9 +171,9 @@ __global__ void __launch_bounds__(256) blur_mma_kernel(const MmaBlurArgs a, int 
     int a0, l0;
     tile_origin(tile, a0, l0);
     // ---- contraction: warp = 8 lines (nt) x 4 m-tiles (mg), all four channels
-    uint32_t pix[4][4];  // [m-tile][fragment slot]: packed RGBX of the lane's 4 outputs per m-tile
-#pragma unroll
-    for (int i = 0; i < 4; i++) pix[i][0] = pix[i][1] = pix[i][2] = pix[i][3] = 0u;
+    // Quantised outputs are kept two per register while the channels come in: rg[i][h] / ba[i][h] hold the bytes
+    // {c0 of slot 2h, c1 of slot 2h, c0 of slot 2h+1, c1 of slot 2h+1} of m-tile i.
+    uint32_t rg[4][2], ba[4][2];
 #pragma unroll
     for (int c = 0; c < 4; c++) {
       float acc[4][4];
@@ -194,15 +194,34 @@ __global__ void __launch_bounds__(256) blur_mma_kernel(const MmaBlurArgs a, int 
           const int q = kt - i;
           if (q >= 0 && q < KT) {
             mma_16816(acc[i], Alo[q], b0, b1);
-            if (a.hasHi) mma_16816(acc[i], Ahi[q], b0, b1);
+            if (HI) mma_16816(acc[i], Ahi[q], b0, b1);
           }
         }
       }
-      // div 256 div 255 == div 65280 (images.nim:332-338), then the channel goes into its byte
+      // `div 256 div 255` (images.nim:332-338) without leaving the FMA / ALU pipes: acc * 2^-8 + 2^23 truncated
+      // (FFMA.RZ) has floor(acc / 256) (< 65536) in its low 16 bits; two of them per register go through the
+      // packed div255; the two result bytes are merged with the other channel of the pair by one PRMT.
 #pragma unroll
       for (int i = 0; i < 4; i++) {
 #pragma unroll
-        for (int s_ = 0; s_ < 4; s_++) pix[i][s_] |= (((uint32_t)acc[i][s_]) / 65280u) << (8 * c);
+        for (int hh = 0; hh < 2; hh++) {
+          const uint32_t t0 = __float_as_uint(__fmaf_rz(acc[i][2 * hh], 0.00390625f, 8388608.0f));
+          const uint32_t t1 = __float_as_uint(__fmaf_rz(acc[i][2 * hh + 1], 0.00390625f, 8388608.0f));
+          const uint32_t qq = div255x2(__byte_perm(t0, t1, 0x5410));  // bytes {q0, 0, q1, 0}
+          if (c == 0) rg[i][hh] = qq;
+          else if (c == 1) rg[i][hh] = __byte_perm(rg[i][hh], qq, 0x6240);  // {r0, g0, r1, g1}
+          else if (c == 2) ba[i][hh] = qq;
+          else ba[i][hh] = __byte_perm(ba[i][hh], qq, 0x6240);
+        }
+      }
+    }
+    uint32_t pix[4][4];  // [m-tile][fragment slot]: packed RGBX of the lane's 4 outputs per m-tile
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+      for (int hh = 0; hh < 2; hh++) {
+        pix[i][2 * hh] = __byte_perm(rg[i][hh], ba[i][hh], 0x5410);
+        pix[i][2 * hh + 1] = __byte_perm(rg[i][hh], ba[i][hh], 0x7632);
       }
     }
 
@@ -236,26 +255,26 @@ __global__ void __launch_bounds__(256) blur_mma_kernel(const MmaBlurArgs a, int 
   }
 }
 
-template <bool VERTICAL, int KT>
+template <bool VERTICAL, int KT, bool HI>
 static int launch_pass(const MmaBlurArgs& a, int tilesA, int tilesL, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
   static int perSm = 1;
   if (configured != smem) {
     if (smem > 48 * 1024)
-      PX_CUDA(cudaFuncSetAttribute(blur_mma_kernel<VERTICAL, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, blur_mma_kernel<VERTICAL, KT>, 256, smem));
+      PX_CUDA(cudaFuncSetAttribute(blur_mma_kernel<VERTICAL, KT, HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, blur_mma_kernel<VERTICAL, KT, HI>, 256, smem));
     perSm = std::max(1, perSm);
     configured = smem;
   }
   const int numTiles = tilesA * tilesL;
   if (numTiles <= 0) return 0;
   const int grid = std::min(numTiles, rt().num_sms * perSm);
-  blur_mma_kernel<VERTICAL, KT><<<grid, 256, smem, st>>>(a, tilesA, numTiles);
+  blur_mma_kernel<VERTICAL, KT, HI><<<grid, 256, smem, st>>>(a, tilesA, numTiles);
   PX_LAUNCHED();
   return 0;
 }
 
-template <int KT>
+template <int KT, bool HI>
 static int launch_both(MmaBlurArgs a, Image* im, void* tmp, int y0, int y1) {
   Runtime& r = rt();
   constexpr int IN_A = kMmaOut - 16 + 16 * KT;
@@ -265,7 +284,7 @@ static int launch_both(MmaBlurArgs a, Image* im, void* tmp, int y0, int y1) {
     a.pitch = IN_A + ((8 - IN_A) % 64 + 64) % 64;
     const size_t smem = (size_t)4 * kMmaLines * a.pitch * sizeof(__half) + rawBytes;
     ProfScope ps(kProfBlurX);
-    if (int rc = launch_pass<false, KT>(a, (im->w + kMmaOut - 1) / kMmaOut, (a.sy1 - a.sy0 + kMmaLines - 1) / kMmaLines, smem,
+    if (int rc = launch_pass<false, KT, HI>(a, (im->w + kMmaOut - 1) / kMmaOut, (a.sy1 - a.sy0 + kMmaLines - 1) / kMmaLines, smem,
                                         r.stream))
       return rc;
   }
@@ -274,7 +293,7 @@ static int launch_both(MmaBlurArgs a, Image* im, void* tmp, int y0, int y1) {
     a.pitch = kMmaLines + 8;
     const size_t smem = (size_t)4 * IN_A * a.pitch * sizeof(__half) + rawBytes;
     ProfScope ps(kProfBlurY);
-    if (int rc = launch_pass<true, KT>(a, (y1 - y0 + kMmaOut - 1) / kMmaOut, (im->w + kMmaLines - 1) / kMmaLines, smem, r.stream))
+    if (int rc = launch_pass<true, KT, HI>(a, (y1 - y0 + kMmaOut - 1) / kMmaOut, (im->w + kMmaLines - 1) / kMmaLines, smem, r.stream))
       return rc;
   }
   return 0;
@@ -309,14 +328,14 @@ int blur_mma(Image* im, void* tmp, const uint16_t* lut_host, int radius, uint32_
   a.pitch = 0; a.src = nullptr; a.dst = nullptr;
   const int KT = (2 * radius + 16 + 15) / 16;
   switch (KT) {
-    case 2: return launch_both<2>(a, im, tmp, y0, y1);
-    case 3: return launch_both<3>(a, im, tmp, y0, y1);
-    case 4: return launch_both<4>(a, im, tmp, y0, y1);
-    case 5: return launch_both<5>(a, im, tmp, y0, y1);
-    case 6: return launch_both<6>(a, im, tmp, y0, y1);
-    case 7: return launch_both<7>(a, im, tmp, y0, y1);
-    case 8: return launch_both<8>(a, im, tmp, y0, y1);
-    case 9: return launch_both<9>(a, im, tmp, y0, y1);
+    case 2: return hasHi ? launch_both<2, true>(a, im, tmp, y0, y1) : launch_both<2, false>(a, im, tmp, y0, y1);
+    case 3: return hasHi ? launch_both<3, true>(a, im, tmp, y0, y1) : launch_both<3, false>(a, im, tmp, y0, y1);
+    case 4: return hasHi ? launch_both<4, true>(a, im, tmp, y0, y1) : launch_both<4, false>(a, im, tmp, y0, y1);
+    case 5: return hasHi ? launch_both<5, true>(a, im, tmp, y0, y1) : launch_both<5, false>(a, im, tmp, y0, y1);
+    case 6: return hasHi ? launch_both<6, true>(a, im, tmp, y0, y1) : launch_both<6, false>(a, im, tmp, y0, y1);
+    case 7: return hasHi ? launch_both<7, true>(a, im, tmp, y0, y1) : launch_both<7, false>(a, im, tmp, y0, y1);
+    case 8: return hasHi ? launch_both<8, true>(a, im, tmp, y0, y1) : launch_both<8, false>(a, im, tmp, y0, y1);
+    case 9: return hasHi ? launch_both<9, true>(a, im, tmp, y0, y1) : launch_both<9, false>(a, im, tmp, y0, y1);
     default: return -1;
   }
 }
