@@ -23,11 +23,13 @@ namespace pixie {
 PXD long long f2ll_(float f) { return (long long)f; }
 PXD int clampll(long long v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : (int)v); }
 
-// ColorRGBX mix (common.nim:59-65)
+// ColorRGBX mix (common.nim:59-65): (a * (255 - x) + b * x + 127) div 255 per channel, two channels per
+// register (16-bit lanes: the sums are <= 65152, below both the lane width and div255x2's 65534 limit)
 PXD px_t mix_px(px_t a, px_t b, float t) {
   const uint32_t x = (uint32_t)(long long)roundf(t * 255.0f), ix = 255u - x;
-  return mk((pR(a) * ix + pR(b) * x + 127u) / 255u, (pG(a) * ix + pG(b) * x + 127u) / 255u,
-            (pB(a) * ix + pB(b) * x + 127u) / 255u, (pA(a) * ix + pA(b) * x + 127u) / 255u);
+  const uint32_t rb = (a & 0x00FF00FFu) * ix + (b & 0x00FF00FFu) * x + 0x007F007Fu;
+  const uint32_t ga = ((a >> 8) & 0x00FF00FFu) * ix + ((b >> 8) & 0x00FF00FFu) * x + 0x007F007Fu;
+  return div255x2(rb) | (div255x2(ga) << 8);
 }
 // ColorRGBX * float32 (common.nim:67-77)
 PXD px_t mul_opacity(px_t c, float opacity) {

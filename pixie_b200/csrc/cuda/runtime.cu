@@ -167,6 +167,13 @@ int pixie_cuda_init(int device) {
   r.num_sms = prop.multiProcessorCount;
   if (!r.own_stream) PX_CUDA(cudaStreamCreateWithFlags(&r.own_stream, cudaStreamNonBlocking));
   r.stream = r.own_stream;
+  {  // temporaries of draw() (minify / magnify chain) come from the stream-ordered pool: keep its memory cached
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if (!r.ev0) PX_CUDA(cudaEventCreate(&r.ev0));
   if (!r.ev1) PX_CUDA(cudaEventCreate(&r.ev1));
   r.inited = true;
