@@ -210,7 +210,10 @@ def extras_single_gpu(dev, peak):
                              "y_pass_ms": round(statistics.median(msy), 3),
                              "GB/s": round(n * n * 8 / t / 1e6, 1), "frac_hbm": round(n * n * 8 / t / 1e6 / peak, 3),
                              "bytes_per_px": 8, "Gtaps_per_s": round(n * n * 4 * 2 * 65 / t / 1e6, 1),
-                             "bound": "ALU (65 taps x 4 ch x 2 passes per px), not HBM"}
+                             "traffic_bytes_per_px": 16,
+                             "bound": "tensor-core Toeplitz contraction (blur_mma.cu, bit-exact): issue-bound by the u8->fp16 "
+                                      "staging and the integer epilogue; two passes move 16 B/px, the 8 B/px figure is the "
+                                      "single-pass ideal of SURVEY 8(d)"}
     dstimg = dev.DeviceImage(n, n)
     ms = []
     for it in range(2):
@@ -218,6 +221,41 @@ def extras_single_gpu(dev, peak):
         dev.shadow(img, dstimg, 8, 8, 4, lut, 32, 0xC8000000)
         ms.append(dev.timer_end())
     out["shadow_16384"] = {"ms": round(ms[-1], 3), "GB/s": round(n * n * 8 / ms[-1] / 1e6, 1)}
+    del img, dstimg
+    # ---- SURVEY 8(f) rows built this round: draw with a transform, minifyBy2, gradient fill (8192^2)
+    n = 8192
+    f = np.float32
+    dst0 = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 0x5EED), (n // 512, 1, 1)))
+    src = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 0x5EED + 1), (n // 512, 1, 1)))
+    dst = dev.DeviceImage(n, n)
+
+    def timed(fn):
+        ts = []
+        for it in range(3):
+            dst.copy_from(dst0)
+            dev.timer_begin()
+            fn()
+            t = dev.timer_end()
+            if it:
+                ts.append(t)
+        return statistics.median(ts)
+
+    rot = host.matmul(host.translate(f(n / 2), f(-n / 5)), host.rotate(f(0.5)))
+    stops = [(0.0, (1, 0, 0, 1)), (0.3, (0, 1, 0, 0.5)), (1.0, (0, 0, 1, 1))]
+    draws = {}
+    for name, fn, nbytes in [
+        ("draw_rotate_normal", lambda: dev.draw(dst, src, rot, 0), 12 * n * n),
+        ("draw_frac_translate_normal", lambda: dev.draw(dst, src, host.translate(f(10.5), f(3.25)), 0), 12 * n * n),
+        ("draw_scale_half_normal", lambda: dev.draw(dst, src, host.scale(f(0.5), f(0.5)), 0), 5 * n * n + 3 * n * n),
+        ("draw_tiled_scale_0.37", lambda: dev.draw_tiled(dst, src, host.scale(f(0.37), f(0.37)), 0), 12 * n * n),
+        ("fill_gradient_linear", lambda: dev.fill_gradient(dst, 3, [(10, 20), (n - 10, n - 30)], stops, 1.0), 4 * n * n),
+        ("fill_gradient_radial", lambda: dev.fill_gradient(dst, 4, [(n / 2, n / 2), (n, n / 2), (n / 2, n)], stops, 1.0), 4 * n * n),
+        ("fill_gradient_angular", lambda: dev.fill_gradient(dst, 5, [(n / 2, n / 2), (n, n / 2), (n / 2, n)], stops, 1.0), 4 * n * n),
+    ]:
+        t = timed(fn)
+        draws[name] = {"ms": round(t, 4), "GB/s": round(nbytes / t / 1e6, 1), "frac_hbm": round(nbytes / t / 1e6 / peak, 3)}
+    out["draw_paint_8192"] = {"bytes_per_px": "draw 12 (dst r+w, src r); scale 0.5: minify 5/src px + draw over the covered quarter; "
+                                              "gradient 4 (write)", "ops": draws}
     return out
 
 
@@ -397,8 +435,8 @@ def run_ours(args):
     roofline = {"kernel": "raster_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4),
                 # dram__bytes_read.sum + dram__bytes_write.sum of one raster_kernel launch on this workload, from the
-                # `ncu --set full` capture summarised in profiles/r01_raster_metrics.txt (canvas stays in the 126 MB L2)
-                "traffic": 39995392 if size == 4096 else None, "peak_source": peak_src,
+                # `ncu --set full` capture summarised in profiles/r01_raster_metrics.txt (20.07 MB read + 19.73 MB written: the canvas stays in the 126 MB L2)
+                "traffic": 39804160 if size == 4096 else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(rast, 4),
                 "partition_kernel_ms": round(part, 4), "plan_kernel_ms": round(statistics.mean(plan_ms), 4), "share_of_step": round(rast / statistics.mean(step_ms), 3),
                 "note": "305 order-dependent fills: latency/occupancy-bound, not bandwidth-bound (SURVEY.md 7.1)"}

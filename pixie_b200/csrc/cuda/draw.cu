@@ -25,8 +25,13 @@ PXD int clampll(long long v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi
 
 // ColorRGBX mix (common.nim:59-65): (a * (255 - x) + b * x + 127) div 255 per channel, two channels per
 // register (16-bit lanes: the sums are <= 65152, below both the lane width and div255x2's 65534 limit)
+PXD uint32_t round_half_away(float v) {  // Nim round() on a non-negative value below 2^23: exact
+  uint32_t r = __float2uint_rz(v);
+  if (v - (float)r >= 0.5f) r++;
+  return r;
+}
 PXD px_t mix_px(px_t a, px_t b, float t) {
-  const uint32_t x = (uint32_t)(long long)roundf(t * 255.0f), ix = 255u - x;
+  const uint32_t x = round_half_away(t * 255.0f), ix = 255u - x;
   const uint32_t rb = (a & 0x00FF00FFu) * ix + (b & 0x00FF00FFu) * x + 0x007F007Fu;
   const uint32_t ga = ((a >> 8) & 0x00FF00FFu) * ix + ((b >> 8) & 0x00FF00FFu) * x + 0x007F007Fu;
   return div255x2(rb) | (div255x2(ga) << 8);
@@ -34,7 +39,7 @@ PXD px_t mix_px(px_t a, px_t b, float t) {
 // ColorRGBX * float32 (common.nim:67-77)
 PXD px_t mul_opacity(px_t c, float opacity) {
   if (opacity == 0.0f) return 0u;
-  const uint32_t x = (uint32_t)(long long)roundf(opacity * 255.0f);
+  const uint32_t x = round_half_away(opacity * 255.0f);
   return mk((pR(c) * x + 127u) / 255u, (pG(c) * x + 127u) / 255u, (pB(c) * x + 127u) / 255u, (pA(c) * x + 127u) / 255u);
 }
 
@@ -99,21 +104,61 @@ PXD px_t get_px_wrapped(const SrcView& s, long long x, long long y) {
 template <bool WRAPPED>
 PXD px_t rgba_smooth(const SrcView& s, float x, float y) {
   const float fx = floorf(x), fy = floorf(y);
-  const long long x0 = f2ll_(fx), y0 = f2ll_(fy), x1 = x0 + 1, y1 = y0 + 1;
   const float xFrac = x - fx, yFrac = y - fy;
   px_t x0y0, x1y0, x0y1, x1y1;
   if (WRAPPED) {
+    const long long x0 = f2ll_(fx), y0 = f2ll_(fy), x1 = x0 + 1, y1 = y0 + 1;
     x0y0 = get_px_wrapped(s, x0, y0); x1y0 = get_px_wrapped(s, x1, y0);
     x0y1 = get_px_wrapped(s, x0, y1); x1y1 = get_px_wrapped(s, x1, y1);
   } else {
-    x0y0 = get_px(s, x0, y0); x1y0 = get_px(s, x1, y0);
-    x0y1 = get_px(s, x0, y1); x1y1 = get_px(s, x1, y1);
+    // image[x, y] is transparent outside; positions beyond +-2^30 (or NaN) are outside whatever their low bits
+    const bool sane = fabsf(fx) < 1073741824.0f && fabsf(fy) < 1073741824.0f;
+    const int x0 = sane ? (int)fx : -2, y0 = sane ? (int)fy : -2, x1 = x0 + 1, y1 = y0 + 1;
+    const bool cx0 = (unsigned)x0 < (unsigned)s.w, cx1 = (unsigned)x1 < (unsigned)s.w;
+    const bool cy0 = (unsigned)y0 < (unsigned)s.h, cy1 = (unsigned)y1 < (unsigned)s.h;
+    const px_t* r0 = s.d + (size_t)s.w * (size_t)(cy0 ? y0 : 0);
+    const px_t* r1 = s.d + (size_t)s.w * (size_t)(cy1 ? y1 : 0);
+    x0y0 = (cx0 && cy0) ? r0[x0] : 0u;
+    x1y0 = (cx1 && cy0) ? r0[x1] : 0u;
+    x0y1 = (cx0 && cy1) ? r1[x0] : 0u;
+    x1y1 = (cx1 && cy1) ? r1[x1] : 0u;
   }
   px_t top = x0y0;
   if (xFrac > 0.0f && x0y0 != x1y0) top = mix_px(x0y0, x1y0, xFrac);
   px_t bottom = x0y1;
   if (xFrac > 0.0f && x0y1 != x1y1) bottom = mix_px(x0y1, x1y1, xFrac);
   if (yFrac != 0.0f && top != bottom) return mix_px(top, bottom, yFrac);
+  return top;
+}
+
+// getRgbaSmooth in two halves, so that a thread can have the gathers of several pixels in flight before it mixes
+struct Quad {
+  px_t x0y0, x1y0, x0y1, x1y1;
+  float xFrac, yFrac;
+};
+PXD Quad fetch_quad(const SrcView& s, float x, float y) {
+  Quad q;
+  const float fx = floorf(x), fy = floorf(y);
+  q.xFrac = x - fx;
+  q.yFrac = y - fy;
+  const bool sane = fabsf(fx) < 1073741824.0f && fabsf(fy) < 1073741824.0f;
+  const int x0 = sane ? (int)fx : -2, y0 = sane ? (int)fy : -2, x1 = x0 + 1, y1 = y0 + 1;
+  const bool cx0 = (unsigned)x0 < (unsigned)s.w, cx1 = (unsigned)x1 < (unsigned)s.w;
+  const bool cy0 = (unsigned)y0 < (unsigned)s.h, cy1 = (unsigned)y1 < (unsigned)s.h;
+  const px_t* r0 = s.d + (size_t)s.w * (size_t)(cy0 ? y0 : 0);
+  const px_t* r1 = s.d + (size_t)s.w * (size_t)(cy1 ? y1 : 0);
+  q.x0y0 = (cx0 && cy0) ? __ldg(r0 + x0) : 0u;
+  q.x1y0 = (cx1 && cy0) ? __ldg(r0 + x1) : 0u;
+  q.x0y1 = (cx0 && cy1) ? __ldg(r1 + x0) : 0u;
+  q.x1y1 = (cx1 && cy1) ? __ldg(r1 + x1) : 0u;
+  return q;
+}
+PXD px_t resolve_quad(const Quad& q) {
+  px_t top = q.x0y0;
+  if (q.xFrac > 0.0f && q.x0y0 != q.x1y0) top = mix_px(q.x0y0, q.x1y0, q.xFrac);
+  px_t bottom = q.x0y1;
+  if (q.xFrac > 0.0f && q.x0y1 != q.x1y1) bottom = mix_px(q.x0y1, q.x1y1, q.xFrac);
+  if (q.yFrac != 0.0f && top != bottom) return mix_px(top, bottom, q.yFrac);
   return top;
 }
 
@@ -151,10 +196,71 @@ PXD bool line_segment(float ly, float sax, float say, float sbx, float sby, floa
   return false;
 }
 
+// The reference accumulates the source position along a row with `srcPos += dx` (:588): a float32 sum whose
+// roundings depend on every previous step.  It still has a closed form, piecewise: while pos and pos + d stay in
+// one binade [2^e, 2^(e+1)) every result is a multiple of the binade's ulp u, so fl(pos + d) = pos + D u with a
+// constant integer D (ties-to-even settles after one step: the result of a tie is even, and from an even
+// mantissa the same neighbour wins every time).  build_chain() walks one component of one row binade by binade
+// — a handful of real additions at each crossing, one division for the length of the run — and leaves segments
+// {first index, value, exact increment}; every pixel then gets its position as base + (k - k0) * inc, two exact
+// float operations, in any order.  Rows whose chain does not fit the table (non-finite or wildly changing
+// positions) take the sequential form below.
+struct ChainSeg {
+  int k0;
+  float base, inc;
+};
+constexpr int kMaxSegs = 128;
+
+__device__ __noinline__ int build_chain(float v0, float d, int n, ChainSeg* seg) {
+  int ns = 0, k = 0;
+  float cur = v0;
+#pragma unroll 1
+  while (k < n) {
+    if (ns > kMaxSegs - 4) return -1;
+    const float p1 = cur + d, p2 = p1 + d, p3 = p2 + d;
+    const uint32_t b2 = __float_as_uint(p2);
+    const uint32_t e1 = __float_as_uint(p1) >> 23, e2 = b2 >> 23, e3 = __float_as_uint(p3) >> 23;  // sign + exponent
+    const bool run = e1 == e2 && e2 == e3 && (e2 & 0xFFu) != 0u && (e2 & 0xFFu) != 0xFFu;
+    seg[ns].k0 = k; seg[ns].base = cur; seg[ns].inc = 0.0f; ns++;
+    if (!run) {
+      cur = p1;
+      k++;
+      continue;
+    }
+    seg[ns].k0 = k + 1; seg[ns].base = p1; seg[ns].inc = 0.0f; ns++;
+    const float inc = p3 - p2;  // exact: same binade
+    long long J = n;            // steps of the run after p2; inc == 0 never leaves the binade
+    if (inc != 0.0f) {
+      const float lo = __uint_as_float(b2 & 0x7F800000u);                 // 2^e
+      const double u = (double)lo * (1.0 / 8388608.0);                     // ulp of the binade
+      const double a2 = fabs((double)p2), ai = (p2 < 0.0f) ? -(double)inc : (double)inc;  // magnitude and its step
+      if (ai > 0.0) {  // growing: results must stay below 2^(e+1)
+        const double hi = 2.0 * (double)lo;
+        J = (long long)floor((hi - a2) / ai);
+        while (J > 0 && a2 + (double)J * ai >= hi) J--;
+        while (a2 + (double)(J + 1) * ai < hi) J++;
+      } else {  // shrinking: a result equal to 2^e may come from an exact sum below it, where the grid is finer
+        const double lo1 = (double)lo + u;
+        J = (long long)floor((a2 - lo1) / -ai);
+        while (J > 0 && a2 + (double)J * ai < lo1) J--;
+        while (a2 + (double)(J + 1) * ai >= lo1) J++;
+      }
+      if (J < 1) J = 1;  // p3 is in the binade
+      if (J > n) J = n;
+    }
+    seg[ns].k0 = k + 2; seg[ns].base = p2; seg[ns].inc = inc; ns++;
+    cur = (p2 + (float)J * inc) + d;  // the value after the run: a real addition again
+    k = k + 2 + (int)J + 1;
+  }
+  seg[ns].k0 = INT_MAX; seg[ns].base = 0.0f; seg[ns].inc = 0.0f;
+  return ns;
+}
+
 // MODE: NormalBlend / OverwriteBlend / MaskBlend get the blendLine* bodies, -1 = blender() chosen at run time
 template <int MODE>
 __global__ void __launch_bounds__(256) draw_smooth_kernel(const SmoothArgs A) {
-  const int lane = threadIdx.x & 31;
+  __shared__ ChainSeg s_segs[8][2][kMaxSegs];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rowsBegin = MODE == MaskBlend ? 0 : A.yStart, rowsEnd = MODE == MaskBlend ? A.ah : A.yEnd;
   const int y = rowsBegin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (y >= rowsEnd) return;
@@ -183,30 +289,69 @@ __global__ void __launch_bounds__(256) draw_smooth_kernel(const SmoothArgs A) {
     for (int x = lane; x < xStart; x += 32) row[x] = 0u;
     for (int x = max(xEnd, 0) + lane; x < A.aw; x += 32) row[x] = 0u;
   }
+  if (xEnd < xStart) return;
   // srcPos = p + dx * xStart + dy * y - h, then += dx per pixel (:584-588)
   float sx = (A.px + A.dxx * (float)xStart) + A.dyx * (float)y;
   float sy = (A.py + A.dxy * (float)xStart) + A.dyy * (float)y;
   sx = sx - 0.5f;
   sy = sy - 0.5f;
+  const int n = xEnd - xStart;
+  int ns = 0;
+  if (lane < 2) ns = build_chain(lane == 0 ? sx : sy, lane == 0 ? A.dxx : A.dxy, n, s_segs[warp][lane]);
+  __syncwarp();
+  const bool closedForm = __shfl_sync(0xffffffffu, ns, 0) >= 0 && __shfl_sync(0xffffffffu, ns, 1) >= 0;
+  const ChainSeg* segx = s_segs[warp][0];
+  const ChainSeg* segy = s_segs[warp][1];
+  int jx = 0, jy = 0;
+  constexpr int U = 4;  // chunks of 32 pixels per iteration: 4 U gathers + U destination loads in flight per thread
 #pragma unroll 1
-  for (int base = xStart; base < xEnd; base += 32) {
-    float mx = sx, my = sy;
+  for (int base = xStart; base < xEnd; base += 32 * U) {
+    float mx[U], my[U];
+    if (closedForm) {
 #pragma unroll
-    for (int i = 0; i < 32; i++) {
-      if (i == lane) {
-        mx = sx;
-        my = sy;
+      for (int u = 0; u < U; u++) {
+        const int k = base - xStart + 32 * u + lane;
+        while (segx[jx + 1].k0 <= k) jx++;
+        while (segy[jy + 1].k0 <= k) jy++;
+        mx[u] = segx[jx].base + (float)(k - segx[jx].k0) * segx[jx].inc;
+        my[u] = segy[jy].base + (float)(k - segy[jy].k0) * segy[jy].inc;
       }
-      sx += A.dxx;
-      sy += A.dxy;
+    } else {  // sequential form: every lane replays the additions of the chunk and keeps its own steps
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        mx[u] = sx;
+        my[u] = sy;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          if (i == lane) {
+            mx[u] = sx;
+            my[u] = sy;
+          }
+          sx += A.dxx;
+          sy += A.dxy;
+        }
+      }
     }
-    const int x = base + lane;
-    if (x < xEnd) {
-      const px_t s = rgba_smooth<false>(A.b, mx, my);
-      if (MODE == OverwriteBlend) row[x] = s;
-      else if (MODE == NormalBlend) row[x] = line_normal(row[x], s);
-      else if (MODE == MaskBlend) row[x] = line_mask(row[x], s);
-      else row[x] = blend_px_any(A.mode, row[x], s);
+    Quad q[U];
+    px_t d[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int x = base + 32 * u + lane;
+      if (x < xEnd) {
+        q[u] = fetch_quad(A.b, mx[u], my[u]);
+        if (MODE != OverwriteBlend) d[u] = row[x];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int x = base + 32 * u + lane;
+      if (x < xEnd) {
+        const px_t s = resolve_quad(q[u]);
+        if (MODE == OverwriteBlend) row[x] = s;
+        else if (MODE == NormalBlend) row[x] = line_normal(d[u], s);
+        else if (MODE == MaskBlend) row[x] = line_mask(d[u], s);
+        else row[x] = blend_px_any(A.mode, d[u], s);
+      }
     }
   }
 }
@@ -286,33 +431,38 @@ PXD px_t gradient_color(const GradientArgs& G, float t) {  // :68-94
   return mk((r8 * a8 + 127u) / 255u, (g8 * a8 + 127u) / 255u, (b8 * a8 + 127u) / 255u, a8);
 }
 
+PXD float gradient_t(const GradientArgs& G, int x, int y) {
+  if (G.kind == 3) {  // toLineSpace (:107-113); the horizontal / vertical fast paths evaluate it at (x, 0) / (0, y)
+    float qx = (float)x, qy = (float)y;
+    if (G.h0y == G.h1y) qy = 0.0f;
+    else if (G.h0x == G.h1x) qx = 0.0f;
+    const float ddx = G.h1x - G.h0x, ddy = G.h1y - G.h0y;
+    const float det = ddx * ddx + ddy * ddy;
+    return (ddy * (qy - G.h0y) + ddx * (qx - G.h0x)) / det;
+  }
+  if (G.kind == 4) {
+    const float vx = (float)x, vy = (float)y;
+    const float mx = G.m[0] * vx + G.m[3] * vy + G.m[6], my = G.m[1] * vx + G.m[4] * vy + G.m[7];
+    return sqrtf(mx * mx + my * my);
+  }
+  const float pi = (float)3.141592653589793238462643383279502884;
+  const float ex = (float)x - G.h0x, ey = (float)y - G.h0y;
+  const float len = sqrtf(ex * ex + ey * ey);
+  const float nx = ex / len, ny = ey / len;
+  // arctan2 in float32 = the double result rounded (what a correctly rounded atan2f returns)
+  const float angle = (float)atan2((double)ny, (double)nx);
+  return fix_angle(angle + G.gradientAngle + pi / 2.0f) / 2.0f / pi + 0.5f;
+}
+
 __global__ void __launch_bounds__(256) gradient_kernel(const __grid_constant__ GradientArgs G) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= G.w) return;
-  for (int y = blockIdx.y; y < G.h; y += gridDim.y) {
-    float t;
-    if (G.kind == 3) {  // toLineSpace (:107-113); the horizontal / vertical fast paths evaluate it at (x, 0) / (0, y)
-      float qx = (float)x, qy = (float)y;
-      if (G.h0y == G.h1y) qy = 0.0f;
-      else if (G.h0x == G.h1x) qx = 0.0f;
-      const float ddx = G.h1x - G.h0x, ddy = G.h1y - G.h0y;
-      const float det = ddx * ddx + ddy * ddy;
-      t = (ddy * (qy - G.h0y) + ddx * (qx - G.h0x)) / det;
-    } else if (G.kind == 4) {
-      const float vx = (float)x, vy = (float)y;
-      const float mx = G.m[0] * vx + G.m[3] * vy + G.m[6], my = G.m[1] * vx + G.m[4] * vy + G.m[7];
-      t = sqrtf(mx * mx + my * my);
-    } else {
-      const float pi = (float)3.141592653589793238462643383279502884;
-      const float ex = (float)x - G.h0x, ey = (float)y - G.h0y;
-      const float len = sqrtf(ex * ex + ey * ey);
-      const float nx = ex / len, ny = ey / len;
-      // arctan2 in float32 = the double result rounded (what a correctly rounded atan2f returns)
-      const float angle = (float)atan2((double)ny, (double)nx);
-      t = fix_angle(angle + G.gradientAngle + pi / 2.0f) / 2.0f / pi + 0.5f;
-    }
-    G.img[(size_t)G.w * y + x] = gradient_color(G, t);
+  if (G.kind == 3 && G.h0y == G.h1y) {  // horizontal gradient: one colour per column (:115-147)
+    const px_t c = gradient_color(G, gradient_t(G, x, 0));
+    for (int y = blockIdx.y; y < G.h; y += gridDim.y) G.img[(size_t)G.w * y + x] = c;
+    return;
   }
+  for (int y = blockIdx.y; y < G.h; y += gridDim.y) G.img[(size_t)G.w * y + x] = gradient_color(G, gradient_t(G, x, y));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -137,7 +137,8 @@ static int new_image(int w, int h, int layers, int bpp, void* wrap, pixie_image_
     im.data = (uint8_t*)wrap;
     im.owned = false;
   } else {
-    PX_CUDA(cudaMalloc(&im.data, im.bytes()));
+    // stream-ordered allocation from the device pool (its memory stays cached: no driver call per newImage)
+    PX_CUDA(cudaMallocAsync(&im.data, im.bytes(), r.stream));
     PX_CUDA(cudaMemsetAsync(im.data, 0, im.bytes(), r.stream));
   }
   std::lock_guard<std::mutex> lk(r.mu);
@@ -222,8 +223,10 @@ int pixie_cuda_image_destroy(pixie_image_t h) {
   auto it = r.images.find(h);
   if (it == r.images.end()) return fail_pixie("invalid image handle");
   if (it->second.owned) {
-    PX_CUDA(cudaStreamSynchronize(r.stream));
-    PX_CUDA(cudaFree(it->second.data));
+    // the memory goes back to the pool once everything issued so far has run; with a caller-provided
+    // stream other streams may still be using the image, so wait for the current one first
+    if (r.stream != r.own_stream) PX_CUDA(cudaStreamSynchronize(r.stream));
+    PX_CUDA(cudaFreeAsync(it->second.data, r.stream));
   }
   r.images.erase(it);
   return 0;

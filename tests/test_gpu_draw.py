@@ -233,3 +233,32 @@ def test_api_draw_rotate_and_resize():
     assert tuple(small[50, 30]) == (0, 255, 0, 255)
     mini = a.minifyBy2(2)
     assert (mini.width, mini.height) == (250, 250)
+
+
+def test_draw_random_transforms_fuzz():
+    """The closed-form position chain (draw.cu build_chain) against the oracle's sequential `srcPos += dx` on
+    random affine transforms, including near-axis-aligned rotations, dyadic scales (rounding ties) and rows that
+    cross zero."""
+    gb, ob = _backends()
+    rng = np.random.default_rng(2026)
+    src = _rand(120, 150, 21)
+    base = _rand(140, 1300, 22)
+    for trial in range(40):
+        kind = trial % 5
+        if kind == 0:
+            m = host.matmul(_T(rng.uniform(-200, 900), rng.uniform(-100, 100)), host.rotate(f(rng.uniform(-3.2, 3.2))))
+        elif kind == 1:
+            m = host.matmul(_T(rng.uniform(0, 600), rng.uniform(0, 60)), host.rotate(f(rng.uniform(-1e-3, 1e-3))))
+        elif kind == 2:
+            s_ = f(2.0 ** rng.integers(-1, 2)) * f(rng.choice([0.75, 1.0, 1.25, 1.5]))
+            m = host.matmul(_T(rng.integers(-50, 700) + rng.choice([0.0, 0.5, 0.25]), rng.integers(-20, 40)), host.scale(s_, s_))
+        elif kind == 3:
+            m = np.array([rng.uniform(0.6, 1.9), rng.uniform(-0.5, 0.5), 0, rng.uniform(-0.5, 0.5), rng.uniform(0.6, 1.9), 0,
+                          rng.uniform(-100, 800), rng.uniform(-60, 60), 1], np.float32)
+        else:
+            m = host.matmul(host.matmul(_T(rng.uniform(300, 900), rng.uniform(20, 100)), host.rotate(f(rng.uniform(-3.2, 3.2)))),
+                            host.scale(f(rng.uniform(0.55, 1.9)), f(rng.uniform(0.55, 1.9))))
+        a, b = base.copy(), base.copy()
+        gb.draw(a, src, m, NormalBlend)
+        ob.draw(b, src, m, NormalBlend)
+        assert np.array_equal(a, b), f"trial {trial} kind {kind}: {(np.abs(a.astype(int) - b.astype(int)).max(-1) > 0).sum()} px differ"

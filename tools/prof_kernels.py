@@ -36,3 +36,13 @@ if which in ("tiger", "all"):
         img.fill(0)
         cl.run(img)
     dev.sync()
+if which in ("draw", "all"):
+    n = 8192
+    f = np.float32
+    dst = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 1), (n // 512, 1, 1)))
+    src = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 2), (n // 512, 1, 1)))
+    rot = host.matmul(host.translate(f(n / 2), f(-n / 5)), host.rotate(f(0.5)))
+    dev.draw(dst, src, rot, 0)
+    dev.draw(dst, src, host.scale(f(0.5), f(0.5)), 0)
+    dev.fill_gradient(dst, 4, [(n / 2, n / 2), (n, n / 2), (n / 2, n)], [(0.0, (1, 0, 0, 1)), (1.0, (0, 0, 1, 0.5))], 1.0)
+    dev.sync()
