@@ -171,6 +171,18 @@ int pixie_cuda_blur_host(uint8_t* pixels, int width, int height, const uint16_t*
 int pixie_cuda_shadow_host(const uint8_t* src_pixels, uint8_t* dst_pixels, int width, int height, float offset_x,
                            float offset_y, int spread, const uint16_t* lut, int radius, uint32_t rgbx);
 
+/* draw(a, b, transform, blendMode) / drawTiled on host pixels (tiled != 0), images.nim:636-683 */
+int pixie_cuda_draw_host(uint8_t* dst_pixels, int dst_width, int dst_height, const uint8_t* src_pixels, int src_width,
+                         int src_height, const float* mat, int blend_mode, int tiled);
+/* image.fillGradient(paint) on host pixels, paints.nim:236-248 */
+int pixie_cuda_fill_gradient_host(uint8_t* pixels, int width, int height, int kind, const float* handles_xy,
+                                  int n_handles, const float* stop_pos, const float* stop_rgba, int n_stops,
+                                  float opacity);
+/* minifyBy2 / magnifyBy2 on host pixels; dst holds ceil(w / 2^power) x ceil(h / 2^power) resp. (w << power) x
+ * (h << power) pixels (images.nim:168-259) */
+int pixie_cuda_minify_by2_host(const uint8_t* src_pixels, int width, int height, int power, uint8_t* dst_pixels);
+int pixie_cuda_magnify_by2_host(const uint8_t* src_pixels, int width, int height, int power, uint8_t* dst_pixels);
+
 /* page-locked host staging memory for the *_async copies */
 int pixie_cuda_host_alloc(size_t bytes, void** out);
 int pixie_cuda_host_free(void* ptr);
@@ -179,8 +191,8 @@ int pixie_cuda_host_free(void* ptr);
 /* number of kernels this library has launched since init (bench.py's gpu_launches) */
 int pixie_cuda_launch_count(uint64_t* out);
 /* per-kernel CUDA-event timing on the library's stream.  Slots: 0 partition kernel, 1 raster kernel,
- * 2 blur X pass, 3 blur Y pass, 4 blend_rect kernel, 5 spread kernels.  profile_read waits for the
- * slot's last launch and returns its duration in milliseconds. */
+ * 2 blur X pass, 3 blur Y pass, 4 blend_rect kernel, 5 spread kernels,
+ * 6 plan kernel.  profile_read waits for the slot's last launch and returns its duration in milliseconds. */
 int pixie_cuda_set_profiling(int enabled);
 int pixie_cuda_profile_read(int slot, float* elapsed_ms);
 /* CUDA-event timing on the library's stream: begin/end bracket, elapsed in milliseconds */

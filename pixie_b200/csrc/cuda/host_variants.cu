@@ -55,4 +55,40 @@ int pixie_cuda_shadow_host(const uint8_t* src, uint8_t* dst, int w, int h, float
   return pixie_cuda_image_download(d.h, dst);
 }
 
+int pixie_cuda_draw_host(uint8_t* dst, int dw, int dh, const uint8_t* src, int sw, int sh, const float* mat, int mode,
+                         int tiled) {
+  TmpImage d, s;
+  if (int rc = pixie_cuda_image_create(dw, dh, &d.h)) return rc;
+  if (int rc = pixie_cuda_image_create(sw, sh, &s.h)) return rc;
+  if (int rc = pixie_cuda_image_upload(d.h, dst)) return rc;
+  if (int rc = pixie_cuda_image_upload(s.h, src)) return rc;
+  if (int rc = tiled ? pixie_cuda_draw_tiled(d.h, s.h, mat, mode) : pixie_cuda_draw(d.h, s.h, mat, mode)) return rc;
+  return pixie_cuda_image_download(d.h, dst);
+}
+
+int pixie_cuda_fill_gradient_host(uint8_t* pixels, int w, int h, int kind, const float* handles, int n_handles,
+                                  const float* stop_pos, const float* stop_rgba, int n_stops, float opacity) {
+  TmpImage im;
+  if (int rc = pixie_cuda_image_create(w, h, &im.h)) return rc;
+  if (int rc = pixie_cuda_image_upload(im.h, pixels)) return rc;  // opacity 0 leaves the image as it is
+  if (int rc = pixie_cuda_fill_gradient(im.h, kind, handles, n_handles, stop_pos, stop_rgba, n_stops, opacity)) return rc;
+  return pixie_cuda_image_download(im.h, pixels);
+}
+
+int pixie_cuda_minify_by2_host(const uint8_t* src, int w, int h, int power, uint8_t* dst) {
+  TmpImage s, d;
+  if (int rc = pixie_cuda_image_create(w, h, &s.h)) return rc;
+  if (int rc = pixie_cuda_image_upload(s.h, src)) return rc;
+  if (int rc = pixie_cuda_minify_by2(s.h, power, &d.h)) return rc;
+  return pixie_cuda_image_download(d.h, dst);
+}
+
+int pixie_cuda_magnify_by2_host(const uint8_t* src, int w, int h, int power, uint8_t* dst) {
+  TmpImage s, d;
+  if (int rc = pixie_cuda_image_create(w, h, &s.h)) return rc;
+  if (int rc = pixie_cuda_image_upload(s.h, src)) return rc;
+  if (int rc = pixie_cuda_magnify_by2(s.h, power, &d.h)) return rc;
+  return pixie_cuda_image_download(d.h, dst);
+}
+
 }  // extern "C"

@@ -66,6 +66,10 @@ _SIGNATURES = {
     "pixie_cuda_blend_rect_host": [vp, i32, i32, vp, i32, i32, i32, i32, i32],
     "pixie_cuda_blur_host": [vp, i32, i32, vp, i32, u32],
     "pixie_cuda_shadow_host": [vp, vp, i32, i32, f32, f32, i32, vp, i32, u32],
+    "pixie_cuda_draw_host": [vp, i32, i32, vp, i32, i32, vp, i32, i32],
+    "pixie_cuda_fill_gradient_host": [vp, i32, i32, i32, vp, i32, vp, vp, i32, f32],
+    "pixie_cuda_minify_by2_host": [vp, i32, i32, i32, vp],
+    "pixie_cuda_magnify_by2_host": [vp, i32, i32, i32, vp],
     "pixie_cuda_host_alloc": [C.c_size_t, P(vp)],
     "pixie_cuda_host_free": [vp],
     "pixie_cuda_set_profiling": [i32],

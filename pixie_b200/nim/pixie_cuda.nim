@@ -25,6 +25,16 @@ proc pixie_cuda_blur_host(pixels: ptr uint8, width, height: cint, lut: ptr uint1
 proc pixie_cuda_shadow_host(src, dst: ptr uint8, width, height: cint, ox, oy: cfloat,
     spread: cint, lut: ptr uint16, radius: cint, rgbx: uint32): cint {.importc, dynlib: lib, cdecl.}
 
+proc pixie_cuda_draw_host(dst: ptr uint8, dw, dh: cint, src: ptr uint8, sw, sh: cint,
+    mat: ptr float32, blendMode, tiled: cint): cint {.importc, dynlib: lib, cdecl.}
+proc pixie_cuda_fill_gradient_host(pixels: ptr uint8, width, height, kind: cint,
+    handlesXy: ptr float32, nHandles: cint, stopPos, stopRgba: ptr float32, nStops: cint,
+    opacity: cfloat): cint {.importc, dynlib: lib, cdecl.}
+proc pixie_cuda_minify_by2_host(src: ptr uint8, width, height, power: cint,
+    dst: ptr uint8): cint {.importc, dynlib: lib, cdecl.}
+proc pixie_cuda_magnify_by2_host(src: ptr uint8, width, height, power: cint,
+    dst: ptr uint8): cint {.importc, dynlib: lib, cdecl.}
+
 # device-resident variants (handles), for callers that keep canvases in HBM between calls
 proc pixie_cuda_image_create(width, height: cint, outH: ptr PixieImageT): cint {.importc, dynlib: lib, cdecl.}
 proc pixie_cuda_image_upload(image: PixieImageT, pixels: ptr uint8): cint {.importc, dynlib: lib, cdecl.}
@@ -93,3 +103,53 @@ proc shadowCuda*(image: Image, offset: Vec2, spread, blur: float32, color: Color
     cast[ptr uint8](image.data[0].addr), cast[ptr uint8](result.data[0].addr),
     image.width.cint, image.height.cint, offset.x.cfloat, offset.y.cfloat,
     round(spread).cint, kernel[0].addr, radius.cint, color.asU32)
+
+# ---- images.nim: body of draw (:636-678) and drawTiled (:680-683) -------------------------------
+# vmath Mat3 is array[3, Vec3] in column-major order: its memory is the 9 float32 the C ABI takes.
+proc drawCuda*(a, b: Image, transform: Mat3, blendMode: BlendMode, tiled = false)
+    {.raises: [PixieError].} =
+  var m = transform
+  check pixie_cuda_draw_host(
+    cast[ptr uint8](a.data[0].addr), a.width.cint, a.height.cint,
+    cast[ptr uint8](b.data[0].addr), b.width.cint, b.height.cint,
+    cast[ptr float32](m.addr), blendMode.ord.cint, tiled.ord.cint)
+
+# ---- images.nim: bodies of minifyBy2 (:168-236) / magnifyBy2 (:238-259) --------------------------
+proc minifyBy2Cuda*(image: Image, power = 1): Image {.raises: [PixieError].} =
+  if power < 0:
+    raise newException(PixieError, "Cannot minifyBy2 with negative power")
+  var (w, h) = (image.width, image.height)
+  for _ in 1 .. power:
+    w = (w + 1) div 2
+    h = (h + 1) div 2
+  result = newImage(w, h)
+  check pixie_cuda_minify_by2_host(
+    cast[ptr uint8](image.data[0].addr), image.width.cint, image.height.cint, power.cint,
+    cast[ptr uint8](result.data[0].addr))
+
+proc magnifyBy2Cuda*(image: Image, power = 1): Image {.raises: [PixieError].} =
+  if power < 0:
+    raise newException(PixieError, "Cannot magnifyBy2 with negative power")
+  result = newImage(image.width shl power, image.height shl power)
+  check pixie_cuda_magnify_by2_host(
+    cast[ptr uint8](image.data[0].addr), image.width.cint, image.height.cint, power.cint,
+    cast[ptr uint8](result.data[0].addr))
+
+# ---- paints.nim: body of fillGradient (:236-248) --------------------------------------------------
+# `Paint` is declared in paints.nim, which imports this module's callers; pass its fields.
+proc fillGradientCuda*(image: Image, kind: int, handles: seq[Vec2], stopPositions: seq[float32],
+                       stopColors: seq[Color], opacity: float32) {.raises: [PixieError].} =
+  var
+    hx = newSeq[float32](handles.len * 2)
+    col = newSeq[float32](stopColors.len * 4)
+    pos = stopPositions
+  for i, p in handles:
+    hx[i * 2] = p.x
+    hx[i * 2 + 1] = p.y
+  for i, c in stopColors:
+    col[i * 4] = c.r; col[i * 4 + 1] = c.g; col[i * 4 + 2] = c.b; col[i * 4 + 3] = c.a
+  check pixie_cuda_fill_gradient_host(
+    cast[ptr uint8](image.data[0].addr), image.width.cint, image.height.cint, kind.cint,
+    (if hx.len > 0: hx[0].addr else: nil), handles.len.cint,
+    (if pos.len > 0: pos[0].addr else: nil), (if col.len > 0: col[0].addr else: nil),
+    stopColors.len.cint, opacity.cfloat)

@@ -262,3 +262,32 @@ def test_draw_random_transforms_fuzz():
         gb.draw(a, src, m, NormalBlend)
         ob.draw(b, src, m, NormalBlend)
         assert np.array_equal(a, b), f"trial {trial} kind {kind}: {(np.abs(a.astype(int) - b.astype(int)).max(-1) > 0).sum()} px differ"
+
+
+def test_host_variants_equal_handle_path():
+    """pixie_cuda_draw_host / fill_gradient_host / minify_by2_host / magnify_by2_host (what the Nim shim binds)."""
+    from pixie_b200 import device as dev
+
+    gb, ob = _backends()
+    L = dev.lib()
+    src = _rand(60, 70, 31)
+    base = _rand(90, 110, 32)
+    m = np.ascontiguousarray(host.matmul(_T(12.5, 7.25), host.rotate(f(0.3))), np.float32)
+    for tiled in (0, 1):
+        got, want = base.copy(), base.copy()
+        dev.check(L.pixie_cuda_draw_host(got.ctypes.data, 110, 90, src.ctypes.data, 70, 60, m.ctypes.data, NormalBlend, tiled))
+        (ob.draw_tiled if tiled else ob.draw)(want, src, m, NormalBlend)
+        assert np.array_equal(got, want)
+    got, want = base.copy(), base.copy()
+    hx = np.array([10, 20, 90, 70], np.float32)
+    pos = np.array([0.0, 1.0], np.float32)
+    col = np.array([1, 0, 0, 1, 0, 0, 1, 0.25], np.float32)
+    dev.check(L.pixie_cuda_fill_gradient_host(got.ctypes.data, 110, 90, 3, hx.ctypes.data, 2, pos.ctypes.data, col.ctypes.data, 2, 0.8))
+    ob.fill_gradient(want, 3, [(10, 20), (90, 70)], [(0.0, (1, 0, 0, 1)), (1.0, (0, 0, 1, 0.25))], 0.8)
+    assert np.array_equal(got, want)
+    mini = np.zeros((45, 55, 4), np.uint8)
+    dev.check(L.pixie_cuda_minify_by2_host(base.ctypes.data, 110, 90, 1, mini.ctypes.data))
+    assert np.array_equal(mini, ob.minify_by2(base, 1))
+    big = np.zeros((180, 220, 4), np.uint8)
+    dev.check(L.pixie_cuda_magnify_by2_host(base.ctypes.data, 110, 90, 1, big.ctypes.data))
+    assert np.array_equal(big, ob.magnify_by2(base, 1))
