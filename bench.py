@@ -289,6 +289,49 @@ def icons_batch(dev, rank, world, n_icons=1024, size=512):
             "GB/s_algorithmic": round((8 * covered + 18 * nseg) / t / 1e6, 1), "checksum": img.checksum()}
 
 
+def icons_sharded(dev, dist, rank, world, per_rank, size=512, chunk=2048):
+    """BASELINE config 5 at scale: `per_rank * world` synthetic 512^2 icons (100 000 on 8 GPUs), contiguous shard per
+    rank (multi.shard_range), rendered chunk by chunk into one reused stack of canvases; results stay on the device
+    (checksum of checksums), no data-path collective.  Time = device time of the launches, max over ranks."""
+    import torch
+
+    from pixie_b200 import multi, synth
+    from pixie_b200.device import FillBatch
+
+    total = per_rank * world
+    b0, b1 = multi.shard_range(total, world, rank)
+    img = dev.DeviceImage(size, size, min(chunk, b1 - b0))
+    ms, covered, nseg, nfills, checksum = 0.0, 0, 0, 0, 0
+    for c0 in range(b0, b1, chunk):
+        c1 = min(c0 + chunk, b1)
+        batch = FillBatch()
+        for i in range(c0, c1):
+            synth.icon_fills(i, size, i - c0, batch)
+        arrays = batch.arrays()
+        if c1 - c0 != img.layers:
+            img = dev.DeviceImage(size, size, c1 - c0)
+        cl = dev.CmdList(size, size, c1 - c0, arrays)
+        img.fill(0)
+        dev.sync()
+        dev.timer_begin()
+        covered += cl.run(img, count_covered=True)
+        ms += dev.timer_end()
+        nseg += int(arrays["seg_offsets"][-1])
+        nfills += len(arrays["rgbx"])
+        checksum = (checksum * 1000003 + img.checksum()) % (1 << 64)
+        del cl
+    t = torch.tensor([ms, float(covered), float(nseg), float(nfills)], dtype=torch.float64, device="cuda")
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    ms_max = float(tmax[0].item())
+    cov, segs = float(t[1].item()), float(t[2].item())
+    return {"icons": total, "icons_per_rank": b1 - b0, "fills": int(t[3].item()), "segments": int(segs), "covered_px": int(cov),
+            "ms_max_over_ranks": round(ms_max, 3), "icons_per_s": round(total / ms_max * 1e3),
+            "Mpixel/s": round(cov / ms_max / 1e3, 1), "GB/s_algorithmic": round((8 * cov + 18 * segs) / ms_max / 1e6, 1),
+            "checksum_rank0": checksum, "scaling": "weak (12 500 icons per GPU)", "chunk": chunk}
+
+
 def banded_blur_multi_gpu(dev, dist, rank, world, local_rank, peak):
     """BASELINE config 4 across N GPUs: one 16384^2 canvas in row bands, `radius` halo rows exchanged
     with ncclSend/ncclRecv (torch.distributed P2P over NVLink), then the row-band blur kernel."""
@@ -417,11 +460,16 @@ def run_ours(args):
     checksum_ok = int(pinned.array[:size * size * 4].view(np.uint32).sum(dtype=np.uint64)) != 0
 
     banded = None
+    icons_multi = None
     if dist is not None and not args.no_extras:
         try:
             banded = banded_blur_multi_gpu(dev, dist, rank, world, local_rank, peak)
         except Exception as e:
             banded = {"error": repr(e)}
+        try:
+            icons_multi = icons_sharded(dev, dist, rank, world, args.icons_per_gpu)
+        except Exception as e:
+            icons_multi = {"error": repr(e)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -473,6 +521,7 @@ def run_ours(args):
     if banded is not None:
         extras = dict(extras or {})
         extras["blur_r32_16384_row_bands"] = banded
+        extras["icons_512_sharded"] = icons_multi
     if extras is not None:
         out["extras"] = extras
     print(json.dumps(out))
@@ -489,6 +538,7 @@ def main():
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--icons-per-gpu", type=int, default=12500, help="N>1 extras: icons per GPU (BASELINE config 5: 100k on 8)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -1253,7 +1253,7 @@ void drawSmooth(Img& a, const Img& b, const M3& transform, int mode) {  // image
   if (mode == MaskBlend && a.h - yEnd > 0) std::fill(a.d.begin() + (size_t)yEnd * a.w, a.d.end(), 0u);
 }
 
-void drawAny(Img& a, const Img& b0, M3 transform, int mode) {  // draw, images.nim:636-678
+bool drawAny(Img& a, const Img& b0, M3 transform, int mode) {  // draw, images.nim:636-678
   const float hh = 0.5f;
   const M3 inv = inverseM(transform);
   V2 p = mulV(inv, v2(0 + hh, 0 + hh));
@@ -1270,6 +1270,8 @@ void drawAny(Img& a, const Img& b0, M3 transform, int mode) {  // draw, images.n
     transform = mulM(transform, scaleM(2, 2));
   }
   while (filterBy2 <= 0.5f) {
+    // the reference keeps doubling until it runs out of memory; both sides stop at 2^28 pixels (1 GiB) with an error
+    if ((long long)b->w * 2 * b->h * 2 > (1ll << 28)) return false;
     tmp = magnifyOnce(*b);
     b = &tmp;
     p = p * 2; dx = dx * 2; dy = dy * 2;
@@ -1285,9 +1287,10 @@ void drawAny(Img& a, const Img& b0, M3 transform, int mode) {  // draw, images.n
     orc_blend_rect((uint8_t*)a.d.data(), a.w, a.h, (const uint8_t*)b->d.data(), b->w, b->h, (int)transform.m[6],
                    (int)transform.m[7], mode);
   }
+  return true;
 }
 
-void drawCorrect(Img& a, const Img& b0, const M3& transform, int mode, bool tiled) {  // images.nim:405-449
+bool drawCorrect(Img& a, const Img& b0, const M3& transform, int mode, bool tiled) {  // images.nim:405-449
   const float hh = 0.5f;
   M3 inv = inverseM(transform);
   V2 p = mulV(inv, v2(0 + hh, 0 + hh));
@@ -1304,6 +1307,7 @@ void drawCorrect(Img& a, const Img& b0, const M3& transform, int mode, bool tile
     inv = mulM(scaleM(0.5f, 0.5f), inv);
   }
   while (filterBy2 <= 0.5f) {
+    if ((long long)b->w * 2 * b->h * 2 > (1ll << 28)) return false;
     tmp = magnifyOnce(*b);
     b = &tmp;
     p = p * 2; dx = dx * 2; dy = dy * 2;
@@ -1317,6 +1321,7 @@ void drawCorrect(Img& a, const Img& b0, const M3& transform, int mode, bool tile
       px_t& d = a.d[(size_t)a.w * y + x];
       d = blendPx(mode, d, sample);
     }
+  return true;
 }
 
 // ---- gradient paints (paints.nim:68-248); chroma Color = 4 x float32, straight alpha
@@ -1388,7 +1393,10 @@ int orc_draw(uint8_t* dst, int dw, int dh, const uint8_t* src, int sw, int sh, c
   memcpy(b.d.data(), src, b.d.size() * 4);
   M3 t;
   memcpy(t.m, mat, sizeof t.m);
-  drawAny(a, b, t, mode);
+  if (!drawAny(a, b, t, mode)) {
+    g_err = "draw: magnified source image too large";
+    return 1;
+  }
   memcpy(dst, a.d.data(), a.d.size() * 4);
   return 0;
 }
@@ -1401,7 +1409,10 @@ int orc_draw_correct(uint8_t* dst, int dw, int dh, const uint8_t* src, int sw, i
   memcpy(b.d.data(), src, b.d.size() * 4);
   M3 t;
   memcpy(t.m, mat, sizeof t.m);
-  drawCorrect(a, b, t, mode, tiled != 0);
+  if (!drawCorrect(a, b, t, mode, tiled != 0)) {
+    g_err = "draw: magnified source image too large";
+    return 1;
+  }
   memcpy(dst, a.d.data(), a.d.size() * 4);
   return 0;
 }

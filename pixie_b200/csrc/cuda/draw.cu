@@ -615,7 +615,7 @@ static int draw_impl(Image* a, Image* b, const float* mat, int mode) {
     transform = mul_m(transform, scale_m(2, 2));
   }
   while (!rc && filterBy2 <= 0.5f) {  // :657-663
-    if ((long long)sw * 2 * sh * 2 > (1ll << 31)) {
+    if ((long long)sw * 2 * sh * 2 > (1ll << 28)) {  // the reference would double until it runs out of memory
       rc = fail_pixie("draw: magnified source image too large");
       break;
     }
@@ -664,7 +664,7 @@ static int draw_correct_impl(Image* a, Image* b, const float* mat, int mode, boo
     inv = mul_m(scale_m(0.5f, 0.5f), inv);
   }
   while (!rc && filterBy2 <= 0.5f) {
-    if ((long long)sw * 2 * sh * 2 > (1ll << 31)) {
+    if ((long long)sw * 2 * sh * 2 > (1ll << 28)) {  // the reference would double until it runs out of memory
       rc = fail_pixie("draw: magnified source image too large");
       break;
     }

@@ -291,3 +291,30 @@ def test_host_variants_equal_handle_path():
     big = np.zeros((180, 220, 4), np.uint8)
     dev.check(L.pixie_cuda_magnify_by2_host(base.ctypes.data, 110, 90, 1, big.ctypes.data))
     assert np.array_equal(big, ob.magnify_by2(base, 1))
+
+
+@pytest.mark.parametrize("mat", [
+    [0, 0, 0, 0, 0, 0, 5, 5, 1],          # singular: the inverse is inf / NaN everywhere
+    [1, 0, 0, 0, 0, 0, 3, 4, 1],          # rank 1
+    [1e-30, 0, 0, 0, 1e-30, 0, 10, 10, 1],  # astronomically small scale: magnify loop is bounded by the size check
+    [1e6, 0, 0, 0, 1e6, 0, -3e7, -2e7, 1],  # one source pixel covers everything
+], ids=["zero", "rank1", "tiny", "huge"])
+def test_draw_degenerate_transforms(mat):
+    """Degenerate transforms must neither hang nor crash, and agree with the oracle where it has an answer."""
+    from pixie_b200.common import PixieError
+
+    gb, ob = _backends()
+    src = _rand(8, 9, 41)
+    base = _rand(40, 50, 42)
+    m = np.array(mat, np.float32)
+    a, b = base.copy(), base.copy()
+    from _oracle import OracleError
+
+    try:
+        ob.draw(b, src, m, NormalBlend)
+    except OracleError:  # the source would have to be magnified beyond 2^28 pixels (the reference runs out of memory)
+        with pytest.raises(PixieError, match="too large"):
+            gb.draw(a, src, m, NormalBlend)
+        return
+    gb.draw(a, src, m, NormalBlend)
+    assert np.array_equal(a, b)
