@@ -45,6 +45,9 @@ struct Runtime {
   cudaStream_t band_stream[kBands] = {};
   cudaEvent_t band_done[kBands] = {};
   cudaEvent_t band_start = nullptr;
+  // auxiliary streams: the two plan kernels of a launch run side by side ([0] library stream, [1 + b] band b)
+  cudaStream_t aux_stream[kBands + 1] = {};
+  cudaEvent_t aux_fork[kBands + 1] = {}, aux_join[kBands + 1] = {};
   // per-kernel CUDA-event timing (pixie_cuda_set_profiling): slot -> (begin, end) of the last launch
   bool profiling = false;
   cudaEvent_t prof[8][2] = {};

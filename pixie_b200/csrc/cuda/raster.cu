@@ -65,6 +65,7 @@ struct CmdList {
   int bands = 1;
   int* bandJobBase = nullptr;              // [bands][numFills + 1] job prefix of each band
   int bandJobs[Runtime::kBands] = {};
+  int* heavyList = nullptr;                // [totalJobs] jobs left for plan_kernel, one region per plan launch
   unsigned* scratchSlots = nullptr;        // bitmap: spill-scratch block slots in use
   int scratchSlotCount = 0;
   size_t planSmem = 0;
@@ -343,6 +344,8 @@ struct RasterArgs {
   const int* fillJobBase;      // [numFills + 1] first job of each fill; job = fillJobBase[f] + (y - startY)
   const int* planJobBase;      // [numFills + 1] the same restricted to the rows [planY0, planY1) of this plan launch
   int planY0, planJobs;        // jobs of this plan launch (whole list: planJobBase = fillJobBase, planY0 = 0)
+  int* heavyList;              // jobs of crowded bands (> kLightMax entries), compacted by plan_light_kernel for
+  unsigned long long* heavyCount;  // plan_kernel; one list region + counter per plan launch
   unsigned* scratchSlots;      // bitmap of the spill-scratch block slots in use (plan launches of several row
   int scratchSlotCount;        // bands run concurrently and share one pool sized for the resident blocks)
   const unsigned* payOff;      // [numParts + 1] payload offset of each band, in entry-rows
@@ -429,6 +432,218 @@ PXD int find_fill_by_job(const int* __restrict__ jobBase, int numFills, int j) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// K2a: plan_light_kernel — one THREAD per job for bands with at most kLightMax entries (nine jobs out of ten in
+// the tiger: a handful of edges cross a scanline).  A warp per job leaves most lanes idle on those and pays
+// several hundred warp instructions of fixed overhead each; here a lane runs the reference's sequential code for
+// its own scanline (selection, the trapezoid checks with their insertion sort, hits / sortHits / walk per
+// sample line), 32 neighbouring scanlines of a path per warp, which mostly take the same branches.  Jobs of
+// crowded bands are appended to a list for plan_kernel (K2b), where the quadratic sorts get a whole warp.
+// Per-thread scratch: kLightArrays arrays of kLightMax words in shared memory, interleaved by thread.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLightMax = 16;
+constexpr int kLightArrays = 5;
+constexpr int kLightThreads = 128;
+
+// which jobs are heavy: one thread per job, before the two plan kernels (which then run side by side)
+__global__ void __launch_bounds__(256) plan_classify_kernel(const RasterArgs A) {
+  const int bj = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bj >= A.planJobs) return;
+  const int f = find_fill_by_job(A.planJobBase, A.numFills, bj);
+  const FillHeader* Hp = A.fills + f;
+  const int startY = Hp->startY;
+  const int y = max(startY, A.planY0) + (bj - A.planJobBase[f]);
+  int p = (int)((unsigned)(y - startY) / (unsigned)Hp->partitionHeight);
+  if (p > Hp->numPartitions - 1) p = Hp->numPartitions - 1;
+  const int gp = Hp->partBase + p;
+  const bool heavy = A.entryOff[gp + 1] - A.entryOff[gp] > kLightMax;
+  // one atomic per warp: the heavy jobs of the warp take consecutive slots
+  const unsigned bal = __ballot_sync(__activemask(), heavy);
+  if (heavy) {
+    const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(A.heavyCount, (unsigned long long)__popc(bal));
+    base = __shfl_sync(bal, base, leader);
+    A.heavyList[base + __popc(bal & ((1u << lane) - 1u))] = bj;
+  }
+}
+
+__global__ void __launch_bounds__(kLightThreads) plan_light_kernel(const RasterArgs A) {
+  __shared__ uint32_t lsm[kLightArrays * kLightMax * kLightThreads];
+  const int tid = threadIdx.x;
+  auto at = [&](int arr, int i) -> uint32_t& { return lsm[(arr * kLightMax + i) * kLightThreads + tid]; };
+  auto atf = [&](int arr, int i) -> float& { return reinterpret_cast<float*>(lsm)[(arr * kLightMax + i) * kLightThreads + tid]; };
+  const int W = A.w;
+  const float wf = (float)W;
+  const int bj = blockIdx.x * kLightThreads + tid;
+  if (bj >= A.planJobs) return;
+  const int f = find_fill_by_job(A.planJobBase, A.numFills, bj);
+  const FillHeader* Hp = A.fills + f;
+  const int startY = Hp->startY, rule = Hp->rule;
+  const int y = max(startY, A.planY0) + (bj - A.planJobBase[f]);
+  const int job = A.fillJobBase[f] + (y - startY);
+  const int ph = Hp->partitionHeight;
+  int p = (int)((unsigned)(y - startY) / (unsigned)ph);
+  if (p > Hp->numPartitions - 1) p = Hp->numPartitions - 1;
+  const int gp = Hp->partBase + p;
+  const int eBeg = A.entryOff[gp];
+  const int eCnt = A.entryOff[gp + 1] - eBeg;
+  if (eCnt > kLightMax) return;  // plan_kernel's (plan_classify_kernel has listed it)
+  const unsigned fl = A.flags[gp];
+  const Entry* ent = A.entries + eBeg;
+  uint2* pay = A.payload + ((size_t)A.payOff[gp] + (size_t)(y - (startY + p * ph)) * (size_t)eCnt) * kPaySlots;
+  const bool aa = (fl & 1u) != 0, two = (fl & 2u) != 0;
+  JobHdr hdr;
+  hdr.kind = PlanNothing;
+  hdr.n = 0;
+  hdr.pa = 0;
+  hdr.pb = 0;
+  if (two && !aa) {  // mode A (:1644-1668)
+    hdr.kind = PlanAligned;
+    hdr.pa = clampi(f2ll(ent[0].ax), 0, W);
+    hdr.pb = clampi(f2ll(ent[1].ax), 0, W);
+    A.jobs[job] = hdr;
+    return;
+  }
+  // arrays: 0 sel (entry indices, in the order computeCoverage will see them)
+  //         mode B: 1 tax, 2 tbx, 3 mid, 4 order        coverage: 1 hit x, 2 hit winding
+  const float scanTop = (float)y, scanBottom = (float)(y + 1);
+  bool allSpan = true;
+  int nsel = 0;
+  if (two) {
+    nsel = 2;
+    at(0, 0) = 0u;
+    at(0, 1) = 1u;
+  } else {  // :1681-1689
+#pragma unroll 1
+    for (int i = 0; i < eCnt; i++) {
+      const float ay = ent[i].ay, by = ent[i].by;
+      if (!(by <= scanTop || ay >= scanBottom)) {
+        if (ay > scanTop || by < scanBottom) allSpan = false;
+        at(0, nsel++) = (uint32_t)i;
+      }
+    }
+  }
+  if (allSpan && (nsel % 2) == 0) {  // mode B (:1691-1872)
+#pragma unroll 1
+    for (int s = 0; s < nsel; s++) {
+      const Entry* e = ent + at(0, s);
+      const float em = e->m, eb = e->b;
+      const float xa = solve_x(em, eb, scanTop), xb = solve_x(em, eb, scanBottom);
+      atf(1, s) = xa;
+      atf(2, s) = xb;
+      atf(3, s) = (xa + xb) * 0.5f;
+    }
+    // insertion sort of the positions by mid x (:1707-1716), stable
+#pragma unroll 1
+    for (int i = 0; i < nsel; i++) {
+      const float ki = atf(3, i);
+      int j = i - 1;
+      while (j >= 0 && atf(3, (int)at(4, j)) > ki) {
+        at(4, j + 1) = at(4, j);
+        j--;
+      }
+      at(4, j + 1) = (uint32_t)i;
+    }
+    bool ok = true;
+#pragma unroll 1
+    for (int i = 0; i + 1 < nsel; i++) {  // partial-coverage areas must not overlap (:1720-1728)
+      const int l = (int)at(4, i), r = (int)at(4, i + 1);
+      const float leftMaxX = fmaxf(atf(1, l), atf(2, l)), rightMinX = fminf(atf(1, r), atf(2, r));
+      if (f2ll(ceilf(leftMaxX)) > f2ll(rightMinX)) ok = false;
+    }
+    if (ok) {  // only simple fill pairs (:1732-1744)
+      int pre = 0;
+#pragma unroll 1
+      for (int i = 0; i < nsel; i++) {
+        pre += ent[at(0, (int)at(4, i))].winding;
+        const bool fillIt = should_fill(rule, pre);
+        if (((i & 1) == 0) ? !fillIt : fillIt) ok = false;
+      }
+    }
+    if (ok) {
+      hdr.kind = PlanTrapezoids;
+      hdr.n = nsel;
+#pragma unroll 1
+      for (int i = 0; i < nsel; i++) {
+        const int es = (int)at(4, i);
+        const Entry* e = ent + at(0, es);
+        pay[2 * i] = make_uint2(__float_as_uint(e->m), __float_as_uint(e->b));
+        pay[2 * i + 1] = make_uint2(__float_as_uint(atf(1, es)), __float_as_uint(atf(2, es)));
+      }
+      A.jobs[job] = hdr;
+      return;
+    }
+    // the reference has sorted entryIndices in place (:1707-1716): computeCoverage sees them in mid-x order
+#pragma unroll 1
+    for (int i = 0; i < nsel; i++) at(1, i) = at(0, (int)at(4, i));
+#pragma unroll 1
+    for (int i = 0; i < nsel; i++) at(0, i) = at(1, i);
+  }
+
+  // mode C: computeCoverage (:1350-1431), sample line after sample line
+  const int quality = aa ? 5 : 1;
+  const float offset = 1.0f / (float)quality;
+  const float initialOffset = offset / 2.0f + (float)(0.0001 * 3.141592653589793238462643383279502884);
+  hdr.kind = aa ? PlanCoverage : PlanSpans;
+  int S = 0;
+  if (nsel > 0) {
+    float yLine = (float)y + initialOffset - offset;
+#pragma unroll 1
+    for (int m = 0; m < quality; m++) {
+      yLine += offset;
+      int nh = 0;
+#pragma unroll 1
+      for (int s = 0; s < nsel; s++) {  // hits in entry order, inserted by x: the stable insertion sort of :1277-1286
+        const Entry* e = ent + at(0, s);
+        if (e->ay <= yLine && e->by >= yLine) {
+          const float em = e->m, eb = e->b;
+          float x = em == 0.0f ? eb : (yLine - eb) / em;
+          x = (x != x) ? wf : (x < wf ? x : wf);  // min(x, width.float32)
+          const int hx = fixed32(x);
+          int j = nh - 1;
+          while (j >= 0 && (int)at(1, j) > hx) {
+            at(1, j + 1) = at(1, j);
+            at(2, j + 1) = at(2, j);
+            j--;
+          }
+          at(1, j + 1) = (uint32_t)hx;
+          at(2, j + 1) = (uint32_t)e->winding;
+          nh++;
+        }
+      }
+      // walk (:1298-1330)
+      int i = 0, count = 0, prevAt = 0;
+#pragma unroll 1
+      while (i < nh) {
+        const int hat = (int)at(1, i), winding = (int)at(2, i);
+        if (hat > 0) {
+          if (should_fill(rule, count)) {
+            if (i < nh - 1) {
+              const int nextAt = (int)at(1, i + 1), nextWinding = (int)at(2, i + 1);
+              if (nextAt == hat && winding + nextWinding == 0) {
+                i += 2;
+                continue;
+              }
+              if (rule == 0 && count + winding != 0) {
+                count += winding;
+                i++;
+                continue;
+              }
+            }
+            pay[S++] = make_uint2((uint32_t)prevAt, (uint32_t)hat);
+          }
+          prevAt = hat;
+        }
+        count += winding;
+        i++;
+      }
+    }
+  }
+  hdr.n = S;
+  A.jobs[job] = hdr;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2: plan_kernel — one warp per job.
 //
 // Scratch per warp (cap = entries the scratch was sized for, kScratchArrays * cap words):
@@ -463,8 +678,10 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
   const int W = A.w;
   const float wf = (float)W;
   const int warpsTotal = gridDim.x * warpsPerBlock;
+  const int numHeavy = (int)*A.heavyCount;  // jobs plan_light_kernel left for a whole warp
 #pragma unroll 1
-  for (int bj = blockIdx.x * warpsPerBlock + warp; bj < A.planJobs; bj += warpsTotal) {
+  for (int hj = blockIdx.x * warpsPerBlock + warp; hj < numHeavy; hj += warpsTotal) {
+    const int bj = A.heavyList[hj];
     const int f = find_fill_by_job(A.planJobBase, A.numFills, bj);
     const FillHeader* Hp = A.fills + f;
     const int startY = Hp->startY, rule = Hp->rule;
@@ -1487,7 +1704,7 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   const size_t oPayOff = off;    off = al(off + (P + 1) * 4);   // plan payload offset of each band
   const size_t oRanges = off;    off = al(off + std::max<size_t>(1, (size_t)numSegs) * 4);  // packed band range of each segment
   const size_t oSlots = off;     off = al(off + (size_t)((L.scratchSlotCount + 31) / 32) * 4);
-  const size_t oCounters = off;  off = al(off + 128);           // [0] row ticket, [1] covered px, [2] entries, [3] max, [4..] band tickets
+  const size_t oCounters = off;  off = al(off + 256);           // [0] row ticket, [1] covered px, [2] entries, [3] max, [4..11] band tickets, [16..23] heavy-job counts
   const size_t totalA = off;
   if (arena) {
     void* blk;
@@ -1575,7 +1792,8 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   const size_t entriesBytes = al(std::max<size_t>(1, (size_t)L.numEntries) * sizeof(Entry));
   const size_t jobsBytes = al(std::max<size_t>(1, (size_t)L.totalJobs) * sizeof(JobHdr));
   const size_t payBytes = al(std::max<size_t>(1, (size_t)meta[2]) * kPaySlots * sizeof(uint2));
-  const size_t totalB = entriesBytes + jobsBytes + payBytes + al((size_t)L.scratchSlotCount * 8 * L.scratchWords * 4);
+  const size_t heavyBytes = al(std::max<size_t>(1, (size_t)L.totalJobs) * sizeof(int));
+  const size_t totalB = entriesBytes + jobsBytes + payBytes + heavyBytes + al((size_t)L.scratchSlotCount * 8 * L.scratchWords * 4);
   if (arena) {
     void* blk;
     if (int rc = get_scratch(4, totalB, &blk)) return rc;
@@ -1586,11 +1804,36 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   L.entries = (Entry*)L.blockB;
   L.jobs = (JobHdr*)(L.blockB + entriesBytes);
   L.payload = (uint2*)(L.blockB + entriesBytes + jobsBytes);
-  L.scratch = L.scratchWords ? (uint32_t*)(L.blockB + entriesBytes + jobsBytes + payBytes) : nullptr;
+  L.heavyList = (int*)(L.blockB + entriesBytes + jobsBytes + payBytes);
+  L.scratch = L.scratchWords ? (uint32_t*)(L.blockB + entriesBytes + jobsBytes + payBytes + heavyBytes) : nullptr;
   if (g_trace)
     fprintf(stderr, "[pixie_cuda] build_list: host plan %.3f ms (bounds %.3f), stage + device count/scan + readback %.3f ms "
             "(%zu B staged, blocks %zu + %zu B, %lld entries, max %d per band)\n",
             t1 - t0, tBounds, now_ms() - t1, h2dBytes, totalA, totalB, (long long)L.numEntries, L.maxEntries);
+  return 0;
+}
+
+// K2 on stream `st`: classify, then the thread-per-job kernel on an auxiliary stream next to the warp-per-job one
+// (both are latency bound and leave most of the machine idle on their own)
+static int launch_plan_kernels(const CmdList& L, const RasterArgs& A, int jobs, int heavyBlocks, cudaStream_t st, int auxIndex) {
+  Runtime& r = rt();
+  if (jobs <= 0) return 0;
+  if (!r.aux_stream[auxIndex]) {
+    PX_CUDA(cudaStreamCreateWithFlags(&r.aux_stream[auxIndex], cudaStreamNonBlocking));
+    PX_CUDA(cudaEventCreateWithFlags(&r.aux_fork[auxIndex], cudaEventDisableTiming));
+    PX_CUDA(cudaEventCreateWithFlags(&r.aux_join[auxIndex], cudaEventDisableTiming));
+  }
+  cudaStream_t aux = r.aux_stream[auxIndex];
+  plan_classify_kernel<<<(jobs + 255) / 256, 256, 0, st>>>(A);
+  PX_LAUNCHED();
+  PX_CUDA(cudaEventRecord(r.aux_fork[auxIndex], st));
+  PX_CUDA(cudaStreamWaitEvent(aux, r.aux_fork[auxIndex], 0));
+  plan_light_kernel<<<(jobs + kLightThreads - 1) / kLightThreads, kLightThreads, 0, aux>>>(A);
+  PX_LAUNCHED();
+  PX_CUDA(cudaEventRecord(r.aux_join[auxIndex], aux));
+  plan_kernel<<<heavyBlocks, 256, L.planSmem, st>>>(A);
+  PX_LAUNCHED();
+  PX_CUDA(cudaStreamWaitEvent(st, r.aux_join[auxIndex], 0));
   return 0;
 }
 
@@ -1602,7 +1845,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
     if (covered_px) *covered_px = 0;
     return 0;
   }
-  PX_CUDA(cudaMemsetAsync(L.counters, 0, 128, r.stream));  // row tickets + covered px
+  PX_CUDA(cudaMemsetAsync(L.counters, 0, 256, r.stream));  // row tickets, covered px, heavy-job counts
   if (L.numParts > 0) {
     const int warps = (int)std::min<int64_t>(L.numParts, (int64_t)r.num_sms * 32);
     const int blocks = (warps + 7) / 8;
@@ -1634,9 +1877,10 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
   if (!host_pixels || L.bands <= 1) {
     if (L.totalJobs > 0) {
       ProfScope ps(kProfPlan);
-      plan_kernel<<<L.planBlocks, 256, L.planSmem, r.stream>>>(A);
+      A.heavyList = L.heavyList;
+      A.heavyCount = L.counters + 16;
+      if (int rc = launch_plan_kernels(L, A, L.totalJobs, L.planBlocks, r.stream, 0)) return rc;
     }
-    PX_LAUNCHED();
     A.rowBegin = 0; A.rowEnd = totalRows; A.ticketSlot = 0;
     {
       ProfScope ps(kProfRaster);
@@ -1674,9 +1918,12 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
       B.planJobBase = L.bandJobBase + (size_t)b * fillsP1;
       B.planY0 = band_edge(L.h, b, K);
       B.planJobs = L.bandJobs[b];
+      int before = 0;
+      for (int bb = 0; bb < b; bb++) before += L.bandJobs[bb];
+      B.heavyList = L.heavyList + before;
+      B.heavyCount = L.counters + 16 + b;
       const int blocks = std::max(1, std::min((L.bandJobs[b] + 7) / 8, L.planBlocks));
-      plan_kernel<<<blocks, 256, L.planSmem, r.band_stream[b]>>>(B);
-      PX_LAUNCHED();
+      if (int rc = launch_plan_kernels(L, B, L.bandJobs[b], blocks, r.band_stream[b], 1 + b)) return rc;
       if (g_trace) PX_CUDA(cudaEventRecord(tev[1 + 3 * b], r.band_stream[b]));
       return 0;
     };
@@ -1765,7 +2012,7 @@ int pixie_cuda_cmdlist_info(pixie_cmdlist_t list, int64_t* numSegs, int64_t* num
   if (numSegs) *numSegs = it->second.numSegs;
   if (numParts) *numParts = it->second.numParts;
   if (numEntries) *numEntries = it->second.numEntries;
-  if (launches) *launches = it->second.numParts > 0 ? 3 : 1;
+  if (launches) *launches = it->second.numParts > 0 ? 5 : 1;
   return 0;
 }
 
