@@ -420,6 +420,38 @@ PXD int walk_spans(const int* hitAt, const int* hitW, int numHits, int rule, int
   return ns;
 }
 
+// Warp-wide bitonic sort of P (a power of two) 64-bit keys held as two word arrays, ascending.  The crowded
+// bands' stable sorts use it with key = {sortable value, original position}: unique keys, so the result is the
+// stable order, in O(P log^2 P / 32) steps per lane instead of the quadratic rank count.
+PXD void warp_bitonic_sort(uint32_t* khi, uint32_t* klo, int P, int lane) {
+#pragma unroll 1
+  for (int k = 2; k <= P; k <<= 1) {
+#pragma unroll 1
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 1
+      for (int i = lane; i < P; i += 32) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint32_t ah = khi[i], al = klo[i], bh = khi[ixj], bl = klo[ixj];
+          const bool aGreater = ah > bh || (ah == bh && al > bl);
+          if (aGreater == ((i & k) == 0)) {
+            khi[i] = bh; klo[i] = bl;
+            khi[ixj] = ah; klo[ixj] = al;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+PXD uint32_t sortable_float(float f) {  // order-preserving map to uint32; -0 and +0 compare equal in the reference
+  if (f == 0.0f) return 0x80000000u;
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+constexpr int kBitonicMin = 64;   // above this many selected entries the sorts go through warp_bitonic_sort
+constexpr int kBitonicMax = 512;  // 2 x 512 words of keys fit a warp's shared-memory scratch (smemCap * kScratchArrays)
+
 // last fill whose first job is <= j (fills without jobs share their base with the next one)
 PXD int find_fill_by_job(const int* __restrict__ jobBase, int numFills, int j) {
   int lo = 0, hi = numFills;
@@ -758,16 +790,32 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
       }
       __syncwarp();
       // stable sort by mid x (= the reference's insertion sort, :1707-1716): order[rank] = selected position
+      if (nsel > kBitonicMin && nsel <= kBitonicMax && scr != sscr) {
+        int P = 2 * kBitonicMin;
+        while (P < nsel) P <<= 1;
+        uint32_t* khi = sscr;  // the warp's shared-memory scratch is free while the band's arrays live in HBM
+        uint32_t* klo = khi + P;
 #pragma unroll 1
-      for (int i = lane; i < nsel; i += 32) {
-        const float ki = mid[i];
-        int r = 0;
-#pragma unroll 4
-        for (int j = 0; j < nsel; j++) {
-          const float kj = mid[j];
-          r += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+        for (int i = lane; i < P; i += 32) {
+          khi[i] = i < nsel ? sortable_float(mid[i]) : 0xFFFFFFFFu;
+          klo[i] = (uint32_t)i;
         }
-        order[r] = i;
+        __syncwarp();
+        warp_bitonic_sort(khi, klo, P, lane);
+#pragma unroll 1
+        for (int i = lane; i < nsel; i += 32) order[i] = (int)klo[i];
+      } else {
+#pragma unroll 1
+        for (int i = lane; i < nsel; i += 32) {
+          const float ki = mid[i];
+          int r = 0;
+#pragma unroll 4
+          for (int j = 0; j < nsel; j++) {
+            const float kj = mid[j];
+            r += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+          }
+          order[r] = i;
+        }
       }
       __syncwarp();
       bool ok = true;
@@ -835,6 +883,48 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
     constexpr int kNoHit = INT_MAX;
     hdr.kind = aa ? PlanCoverage : PlanSpans;
     if (n > 0) {
+      if (n > kBitonicMin && n <= kBitonicMax && scr != sscr) {
+        // crowded scanline: line after line, hits keyed {x, entry position} through the bitonic sort; the keys
+        // live in the warp's shared-memory scratch, which is free while the band's arrays are in HBM
+        int P = 2 * kBitonicMin;
+        while (P < n) P <<= 1;
+        uint32_t* khi = sscr;
+        uint32_t* klo = khi + P;
+        float yLine = (float)y + initialOffset - offset;
+#pragma unroll 1
+        for (int m = 0; m < quality; m++) {
+          yLine += offset;  // the reference accumulates yLine line by line (:1362-1371)
+#pragma unroll 1
+          for (int s = lane; s < P; s += 32) {
+            int at = kNoHit;
+            if (s < n) {
+              const Entry e = ent[selC[s]];
+              if (e.ay <= yLine && e.by >= yLine) {
+                float x = e.m == 0.0f ? e.b : (yLine - e.b) / e.m;
+                x = (x != x) ? wf : (x < wf ? x : wf);  // min(x, width.float32)
+                at = fixed32(x);
+              }
+            }
+            khi[s] = (uint32_t)at ^ 0x80000000u;  // kNoHit -> 0xFFFFFFFF sorts last
+            klo[s] = (uint32_t)s;
+          }
+          __syncwarp();
+          warp_bitonic_sort(khi, klo, P, lane);
+          int cnt = 0;
+#pragma unroll 1
+          for (int base = 0; base < n; base += 32) {
+            const int r = base + lane;
+            const bool hit = r < n && khi[r] != 0xFFFFFFFFu;
+            if (hit) {
+              sAt[m * n + r] = (int)(khi[r] ^ 0x80000000u);
+              sW[m * n + r] = ent[selC[klo[r]]].winding;
+            }
+            cnt += __popc(__ballot_sync(0xffffffffu, hit));
+          }
+          if (lane == 0) lineHits[m] = cnt;
+          __syncwarp();
+        }
+      } else {
 #pragma unroll 1
       for (int t = lane; t < T; t += 32) {  // :1373-1385
         const int m = t / n, s = t - m * n;
@@ -868,6 +958,7 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
           sW[m * n + r] = ent[selC[s]].winding;
         }
         if (s == 0) lineHits[m] = cnt;
+      }
       }
       __syncwarp();
       int ns = 0;  // spans of line `lane`
