@@ -473,6 +473,7 @@ PXD int find_fill_by_job(const int* __restrict__ jobBase, int numFills, int j) {
 // Per-thread scratch: kLightArrays arrays of kLightMax words in shared memory, interleaved by thread.
 // ---------------------------------------------------------------------------------------------
 constexpr int kLightMax = 16;
+constexpr int kVeryHeavy = 64;  // bands with more entries than this are planned first
 constexpr int kLightArrays = 5;
 constexpr int kLightThreads = 128;
 
@@ -487,15 +488,26 @@ __global__ void __launch_bounds__(256) plan_classify_kernel(const RasterArgs A) 
   int p = (int)((unsigned)(y - startY) / (unsigned)Hp->partitionHeight);
   if (p > Hp->numPartitions - 1) p = Hp->numPartitions - 1;
   const int gp = Hp->partBase + p;
-  const bool heavy = A.entryOff[gp + 1] - A.entryOff[gp] > kLightMax;
-  // one atomic per warp: the heavy jobs of the warp take consecutive slots
-  const unsigned bal = __ballot_sync(__activemask(), heavy);
-  if (heavy) {
-    const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
+  const int eCnt = A.entryOff[gp + 1] - A.entryOff[gp];
+  // The list is filled from both ends: jobs of very crowded bands (their sorts and walks are the longest single
+  // pieces of work of the whole launch) from the front, so that plan_kernel starts them first, the rest from the
+  // back.  One atomic per warp and class: the jobs of a warp take consecutive slots.
+  const bool heavy = eCnt > kLightMax, very = eCnt > kVeryHeavy;
+  const int lane = threadIdx.x & 31;
+  const unsigned act = __activemask();
+  const unsigned balV = __ballot_sync(act, heavy && very), balH = __ballot_sync(act, heavy && !very);
+  if (heavy && very) {
+    const int leader = __ffs(balV) - 1;
     unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(A.heavyCount, (unsigned long long)__popc(bal));
-    base = __shfl_sync(bal, base, leader);
-    A.heavyList[base + __popc(bal & ((1u << lane) - 1u))] = bj;
+    if (lane == leader) base = atomicAdd(A.heavyCount, (unsigned long long)__popc(balV));
+    base = __shfl_sync(balV, base, leader);
+    A.heavyList[base + __popc(balV & ((1u << lane) - 1u))] = bj;
+  } else if (heavy) {
+    const int leader = __ffs(balH) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(A.heavyCount + 8, (unsigned long long)__popc(balH));
+    base = __shfl_sync(balH, base, leader);
+    A.heavyList[A.planJobs - 1 - (int)(base + __popc(balH & ((1u << lane) - 1u)))] = bj;
   }
 }
 
@@ -710,10 +722,11 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
   const int W = A.w;
   const float wf = (float)W;
   const int warpsTotal = gridDim.x * warpsPerBlock;
-  const int numHeavy = (int)*A.heavyCount;  // jobs plan_light_kernel left for a whole warp
+  // jobs plan_classify_kernel left for a whole warp: the very crowded ones from the front of the list, then the rest
+  const int numFront = (int)A.heavyCount[0], numHeavy = numFront + (int)A.heavyCount[8];
 #pragma unroll 1
   for (int hj = blockIdx.x * warpsPerBlock + warp; hj < numHeavy; hj += warpsTotal) {
-    const int bj = A.heavyList[hj];
+    const int bj = A.heavyList[hj < numFront ? hj : A.planJobs - 1 - (hj - numFront)];
     const int f = find_fill_by_job(A.planJobBase, A.numFills, bj);
     const FillHeader* Hp = A.fills + f;
     const int startY = Hp->startY, rule = Hp->rule;
@@ -1795,7 +1808,7 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   const size_t oPayOff = off;    off = al(off + (P + 1) * 4);   // plan payload offset of each band
   const size_t oRanges = off;    off = al(off + std::max<size_t>(1, (size_t)numSegs) * 4);  // packed band range of each segment
   const size_t oSlots = off;     off = al(off + (size_t)((L.scratchSlotCount + 31) / 32) * 4);
-  const size_t oCounters = off;  off = al(off + 256);           // [0] row ticket, [1] covered px, [2] entries, [3] max, [4..11] band tickets, [16..23] heavy-job counts
+  const size_t oCounters = off;  off = al(off + 256);           // [0] row ticket, [1] covered px, [2] entries, [3] max, [4..11] band tickets, [16..31] heavy-job counts (front / back of each launch's list)
   const size_t totalA = off;
   if (arena) {
     void* blk;
