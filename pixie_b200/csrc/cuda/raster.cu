@@ -5,10 +5,11 @@
 //                          into equal-height y bands (one warp per band, ballot compaction keeps
 //                          segment order), per-band requiresAntiAliasing (:1149-1166), clipping of
 //                          spanning entries (:1236-1248), twoNonintersectingSpanningSegments (:1250-1262)
-//   K2  plan_kernel        the scanline loop (:1631-1908) up to the canvas: one warp per (fill, scanline)
-//                          job picks mode A (pixel-aligned pair :1644-1668), mode B (exact-area
-//                          trapezoids :1691-1872) or mode C (computeCoverage :1350-1431: 5 sample lines
-//                          side by side, `walk` :1298-1330 emulated literally) and stores a small plan
+//   K2  plan_light_kernel  the scanline loop (:1631-1908) up to the canvas: every (fill, scanline) job picks
+//       plan_kernel        mode A (pixel-aligned pair :1644-1668), mode B (exact-area trapezoids :1691-1872) or
+//                          mode C (computeCoverage :1350-1431, `walk` :1298-1330 emulated literally) and stores
+//                          a small plan; one thread per job for bands with <= 16 entries, one warp per job (5
+//                          sample lines side by side) for crowded bands, the two kernels side by side
 //   K3  raster_kernel      one warp per canvas row applies the plans of the row's fills in order, so fills
 //                          of one canvas keep the reference's sequential semantics with a single launch:
 //                          coverage accumulation in shared memory, fillCoverage / fillHits (:1479-1591),
@@ -390,32 +391,55 @@ enum PlanKind {
 // walk (:1298-1330) executed by one lane over sorted hits; spans are appended to spanA/spanB, which may be
 // the hit arrays themselves: span k is emitted while reading hit i > k.
 PXD int walk_spans(const int* hitAt, const int* hitW, int numHits, int rule, int* spanA, int* spanB) {
-  int i = 0, count = 0, prevAt = 0, ns = 0;
+  // The hits of crowded scanlines live in HBM scratch and the state machine below consumes them one by one: reading
+  // them 8 (+1 of lookahead) at a time keeps 18 loads in flight instead of one dependent load per step.
+  int count = 0, prevAt = 0, ns = 0;
+  bool skipNext = false;  // the previous hit cancelled this one (`i += 2`, :1306-1308)
 #pragma unroll 1
-  while (i < numHits) {
-    const int at = hitAt[i], winding = hitW[i];
-    if (at > 0) {
-      if (should_fill(rule, count)) {
-        if (i < numHits - 1) {
-          const int nextAt = hitAt[i + 1], nextWinding = hitW[i + 1];
-          if (nextAt == at && winding + nextWinding == 0) {
-            i += 2;
-            continue;
-          }
-          if (rule == 0 && count + winding != 0) {
-            count += winding;
-            i++;
-            continue;
-          }
-        }
-        spanA[ns] = prevAt;
-        spanB[ns] = at;
-        ns++;
-      }
-      prevAt = at;
+  for (int b = 0; b < numHits; b += 8) {
+    int ca[9], cw[9];
+#pragma unroll
+    for (int u = 0; u < 9; u++) {
+      const bool in = b + u < numHits;
+      ca[u] = in ? hitAt[b + u] : 0;
+      cw[u] = in ? hitW[b + u] : 0;
     }
-    count += winding;
-    i++;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int i = b + u;
+      if (i < numHits) {
+        if (skipNext) {
+          skipNext = false;
+        } else {
+          const int at = ca[u], winding = cw[u];
+          bool consumed = false;  // `continue` of the reference's loop: count already updated or hit skipped
+          if (at > 0) {
+            if (should_fill(rule, count)) {
+              bool emit = true;
+              if (i < numHits - 1) {
+                const int nextAt = ca[u + 1], nextWinding = cw[u + 1];
+                if (nextAt == at && winding + nextWinding == 0) {
+                  skipNext = true;
+                  consumed = true;
+                  emit = false;
+                } else if (rule == 0 && count + winding != 0) {
+                  count += winding;
+                  consumed = true;
+                  emit = false;
+                }
+              }
+              if (emit) {
+                spanA[ns] = prevAt;
+                spanB[ns] = at;
+                ns++;
+              }
+            }
+            if (!consumed) prevAt = at;
+          }
+          if (!consumed) count += winding;
+        }
+      }
+    }
   }
   return ns;
 }
