@@ -447,26 +447,46 @@ PXD int walk_spans(const int* hitAt, const int* hitW, int numHits, int rule, int
 // Warp-wide bitonic sort of P (a power of two) 64-bit keys held as two word arrays, ascending.  The crowded
 // bands' stable sorts use it with key = {sortable value, original position}: unique keys, so the result is the
 // stable order, in O(P log^2 P / 32) steps per lane instead of the quadratic rank count.
-PXD void warp_bitonic_sort(uint32_t* khi, uint32_t* klo, int P, int lane) {
+template <int U>  // U = P / 64 compare-exchanges per lane and step
+PXD void warp_bitonic_sort_u(uint32_t* khi, uint32_t* klo, int lane) {
+  constexpr int P = 64 * U;
+  constexpr int B = U < 4 ? U : 4;  // pairs in flight per lane
 #pragma unroll 1
   for (int k = 2; k <= P; k <<= 1) {
 #pragma unroll 1
     for (int j = k >> 1; j > 0; j >>= 1) {
+      // pair t: i = t with a zero inserted at bit j, partner i | j; the loads of a batch first (they are
+      // independent, but the compiler cannot tell that from the stores), then the exchanges
 #pragma unroll 1
-      for (int i = lane; i < P; i += 32) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const uint32_t ah = khi[i], al = klo[i], bh = khi[ixj], bl = klo[ixj];
-          const bool aGreater = ah > bh || (ah == bh && al > bl);
+      for (int u0 = 0; u0 < U; u0 += B) {
+        uint32_t ah[B], al[B], bh[B], bl[B];
+        int ii[B];
+#pragma unroll
+        for (int u = 0; u < B; u++) {
+          const int t = lane + 32 * (u0 + u);
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          ii[u] = i;
+          ah[u] = khi[i]; al[u] = klo[i];
+          bh[u] = khi[i | j]; bl[u] = klo[i | j];
+        }
+#pragma unroll
+        for (int u = 0; u < B; u++) {
+          const int i = ii[u];
+          const bool aGreater = ah[u] > bh[u] || (ah[u] == bh[u] && al[u] > bl[u]);
           if (aGreater == ((i & k) == 0)) {
-            khi[i] = bh; klo[i] = bl;
-            khi[ixj] = ah; klo[ixj] = al;
+            khi[i] = bh[u]; klo[i] = bl[u];
+            khi[i | j] = ah[u]; klo[i | j] = al[u];
           }
         }
       }
       __syncwarp();
     }
   }
+}
+PXD void warp_bitonic_sort(uint32_t* khi, uint32_t* klo, int P, int lane) {  // P = 128, 256 or 512
+  if (P == 128) warp_bitonic_sort_u<2>(khi, klo, lane);
+  else if (P == 256) warp_bitonic_sort_u<4>(khi, klo, lane);
+  else warp_bitonic_sort_u<8>(khi, klo, lane);
 }
 PXD uint32_t sortable_float(float f) {  // order-preserving map to uint32; -0 and +0 compare equal in the reference
   if (f == 0.0f) return 0x80000000u;

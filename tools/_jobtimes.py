@@ -11,18 +11,12 @@ cl = dev.CmdList(4096, 4096, 1, arrays)
 for _ in range(3):
     img.fill(0); cl.run(img)
 dev.sync()
-a = np.fromfile("gpurun_out/jobtimes.bin", dtype=np.int64).reshape(-1, 4)
+a = np.fromfile("gpurun_out/jobtimes.bin", dtype=np.int64).reshape(-1, 16)
 a = a[a[:, 0] != 0]
-t0 = a[:, 0].min()
-dur = a[:, 1] - a[:, 0]
-ecnt = a[:, 2] >> 32
-kn = a[:, 2] & 0xFFFFFFFF
-print("heavy jobs", len(a), "span cycles", a[:, 1].max() - t0)
-order = np.argsort(-dur)[:15]
-for i in order:
-    print("dur %8d start %8d eCnt %4d kind %d n %5d warp %x" % (dur[i], a[i, 0] - t0, ecnt[i], kn[i] // 100000, kn[i] % 100000, a[i, 3]))
-print("sum dur", dur.sum(), "mean", dur.mean())
-for lo, hi in ((17, 32), (33, 64), (65, 128), (129, 256), (257, 1024)):
-    m = (ecnt >= lo) & (ecnt <= hi)
-    if m.any(): print("eCnt %d-%d: %d jobs, mean dur %.0f, max %d, last end %d" % (lo, hi, m.sum(), dur[m].mean(), dur[m].max(), (a[m, 1] - t0).max()))
-# per-warp finish
+ecnt = a[:, 15] >> 32; nsel = a[:, 15] & 0xFFFFFFFF
+nst = (a[:, :14] != 0).sum(1)
+last = a[np.arange(len(a)), nst - 1]
+dur = last - a[:, 0]
+for i in np.argsort(-dur)[:8]:
+    st = a[i, :nst[i]] - a[i, 0]
+    print("eCnt %d nsel %d dur %d phases %s" % (ecnt[i], nsel[i], dur[i], np.diff(st).tolist()))
