@@ -77,7 +77,7 @@ struct CmdList {
   uint32_t* ranges = nullptr;  // per segment: first | last << 16 band it touches (count_kernel)
   uint32_t* scratch = nullptr;  // per-warp spill area when a band has more entries than fit in smem
   unsigned long long* counters = nullptr;  // [0] row ticket, [1] covered px
-  int rasterBlocks = 0, warpsPerBlock = 0, scratchWords = 0, covBytes = 0, smemCap = 0;
+  int rasterBlocks = 0, warpsPerBlock = 0, scratchWords = 0, covBytes = 0, smemCap = 0, tileW = 0, tiles = 1;
   size_t smemBytes = 0, h2dBytes = 0;
   uint8_t* block = nullptr;   // block A: host-written inputs + device-made offsets/flags/counters
   uint8_t* blockB = nullptr;  // block B: band entries + spill scratch (sized after the device-side count)
@@ -359,6 +359,7 @@ struct RasterArgs {
   int ticketSlot;              // counters[ticketSlot] hands out rows
   int smemCap;                 // entries whose scratch fits in shared memory
   int scratchCap;              // capacity of the global spill
+  int tileW, tiles;            // a canvas row is rasterised in `tiles` pieces of tileW columns, one warp each
   int covBytes;                // bytes of the per-warp coverage row in shared memory
   int countCovered;
 };
@@ -1048,6 +1049,7 @@ struct WarpCtx {
   int mode;         // run-time blend mode (used by the GenericMode instantiation)
   px_t* row;        // canvas row of this warp
   int w;            // canvas width
+  int tx0, tx1;     // the columns [tx0, tx1) this warp owns (a tile of the row); everything it writes is clamped to them
   int y;
   int lane;
   uint8_t* cov;     // coverage row in shared memory (index 0 = pixel covBase)
@@ -1064,8 +1066,8 @@ PXD px_t span_op(int mode, px_t d, px_t rgbx) {  // fillHits per-pixel op (:1551
 }
 
 __device__ __noinline__ void clear_span(WarpCtx& c, int x0, int x1) {  // [x0, x1) -> transparent
-  x0 = max(x0, 0);
-  x1 = min(x1, c.w);
+  x0 = max(x0, c.tx0);
+  x1 = min(x1, c.tx1);
   px_t* row = c.row;
 #pragma unroll 1
   for (int x = x0 + c.lane; x < x1; x += 32) row[x] = 0u;
@@ -1074,8 +1076,8 @@ __device__ __noinline__ void clear_span(WarpCtx& c, int x0, int x1) {  // [x0, x
 // interior span of fillHits: [x0, x1) gets the solid colour blended in
 template <int MODE>
 __device__ __noinline__ void fill_span(WarpCtx& c, int x0, int x1, px_t rgbx) {
-  x0 = max(x0, 0);
-  x1 = min(x1, c.w);
+  x0 = max(x0, c.tx0);
+  x1 = min(x1, c.tx1);
   if (x1 <= x0) return;
   const bool store_only = MODE == OverwriteBlend || (MODE == NormalBlend && pA(rgbx) == 255u);
   const int lane = c.lane, mode = c.mode;
@@ -1095,19 +1097,30 @@ __device__ __noinline__ void fill_span(WarpCtx& c, int x0, int x1, px_t rgbx) {
     row[x] = store_only ? rgbx : span_op<MODE>(mode, row[x], rgbx);
     cnt++;
   }
+  if (store_only) {
+    const uint4 v = make_uint4(rgbx, rgbx, rgbx, rgbx);
 #pragma unroll 1
-  for (int x = xa + 4 * lane; x < xb; x += 128) {
-    uint4* p = reinterpret_cast<uint4*>(row + x);
-    uint4 v;
-    if (store_only) {
-      v = make_uint4(rgbx, rgbx, rgbx, rgbx);
-    } else {
-      v = *p;
-      v.x = span_op<MODE>(mode, v.x, rgbx); v.y = span_op<MODE>(mode, v.y, rgbx);
-      v.z = span_op<MODE>(mode, v.z, rgbx); v.w = span_op<MODE>(mode, v.w, rgbx);
+    for (int x = xa + 4 * lane; x < xb; x += 128) {
+      *reinterpret_cast<uint4*>(row + x) = v;
+      cnt += 4;
     }
-    *p = v;
-    cnt += 4;
+  } else {  // read-modify-write: two 16-byte groups per lane in flight
+#pragma unroll 1
+    for (int xs = xa + 4 * lane; xs < xb; xs += 256) {
+      const bool two = xs + 128 < xb;
+      uint4 v0 = *reinterpret_cast<const uint4*>(row + xs), v1 = v0;
+      if (two) v1 = *reinterpret_cast<const uint4*>(row + xs + 128);
+      v0.x = span_op<MODE>(mode, v0.x, rgbx); v0.y = span_op<MODE>(mode, v0.y, rgbx);
+      v0.z = span_op<MODE>(mode, v0.z, rgbx); v0.w = span_op<MODE>(mode, v0.w, rgbx);
+      *reinterpret_cast<uint4*>(row + xs) = v0;
+      cnt += 4;
+      if (two) {
+        v1.x = span_op<MODE>(mode, v1.x, rgbx); v1.y = span_op<MODE>(mode, v1.y, rgbx);
+        v1.z = span_op<MODE>(mode, v1.z, rgbx); v1.w = span_op<MODE>(mode, v1.w, rgbx);
+        *reinterpret_cast<uint4*>(row + xs + 128) = v1;
+        cnt += 4;
+      }
+    }
   }
 #pragma unroll 1
   for (int x = xb + lane; x < x1; x += 32) {
@@ -1169,8 +1182,9 @@ template <int MODE>
 __device__ __noinline__ void coverage_row(WarpCtx& c, const uint2* __restrict__ spans, int S, int startX, int pathWidth,
                                           px_t rgbx) {
   const int lane = c.lane, mode = c.mode;
-  const int covBase = c.vec_ok ? (startX & ~3) : startX;
-  const int covX0 = startX, covX1 = startX + pathWidth;  // coverages[] of the reference spans [covX0, covX1)
+  // coverages[] of the reference spans [startX, startX + pathWidth); this warp keeps the part inside its tile
+  const int covX0 = max(startX, c.tx0), covX1 = min(startX + pathWidth, c.tx1);
+  const int covBase = c.vec_ok ? (covX0 & ~3) : covX0;
   constexpr int sampleCoverage = 255 / 5;
   uint8_t* cov = c.cov;
   uint32_t* cw = reinterpret_cast<uint32_t*>(cov);
@@ -1243,7 +1257,7 @@ __device__ __noinline__ void coverage_row(WarpCtx& c, const uint2* __restrict__ 
   if (MODE != MaskBlend && S == 0) return;
 
   // fillCoverage; [pxLo, pxHi) bounds the pixels whose coverage can be non-zero (MaskBlend visits all)
-  const int x0 = startX, x1 = startX + pathWidth;
+  const int x0 = covX0, x1 = covX1;
   px_t* row = c.row;
   unsigned cnt = 0;
   if (c.vec_ok) {
@@ -1253,26 +1267,8 @@ __device__ __noinline__ void coverage_row(WarpCtx& c, const uint2* __restrict__ 
       word0 = (max(pxLo, x0) - covBase) >> 2;
       words = min(words, (min(pxHi, x1) - covBase + 3) >> 2);
     }
-#pragma unroll 1
-    for (int j = word0 + lane; j < words; j += 32) {
-      const uint32_t cv = cw[j];
-      const int x = covBase + 4 * j;
-      if (MODE != MaskBlend && cv == 0u) continue;
-      cw[j] = 0u;
-      uint4* p = reinterpret_cast<uint4*>(row + x);
-      const bool full = (x >= x0) && (x + 4 <= x1);
-      uint4 v;
-      if ((MODE == OverwriteBlend || (MODE == NormalBlend && pA(rgbx) == 255u)) && cv == 0xFFFFFFFFu && full) {
-        v = make_uint4(rgbx, rgbx, rgbx, rgbx);  // sse2.nim:552-555, 648-651
-        *p = v;
-        cnt += 4;
-        continue;
-      }
-      if (MODE == MaskBlend && pA(rgbx) == 255u && cv == 0xFFFFFFFFu && full) {  // sse2.nim:750-751
-        cnt += 4;
-        continue;
-      }
-      v = *p;
+    // one word (4 pixels) of coverage against its 16 bytes of canvas
+    auto blend_word = [&](uint32_t cv, int x, uint4 v) -> uint4 {
       uint32_t* vp = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -1290,7 +1286,52 @@ __device__ __noinline__ void coverage_row(WarpCtx& c, const uint2* __restrict__ 
           if (cvk != 0u) vp[k] = blend_any<MODE>(mode, vp[k], mul_cov_round(rgbx, cvk));
         }
       }
-      *p = v;
+      return v;
+    };
+    if (MODE == NormalBlend || MODE == OverwriteBlend) {
+      // two words per lane and step: both canvas loads are in flight before the first blend (a fill's row
+      // segment costs half as many dependent L2 round trips)
+      const bool solid = MODE == OverwriteBlend || pA(rgbx) == 255u;
+      const uint4 colour4 = make_uint4(rgbx, rgbx, rgbx, rgbx);
+#pragma unroll 1
+      for (int j = word0 + lane; j < words; j += 64) {
+        const int jb = j + 32;
+        const uint32_t cva = cw[j], cvb = jb < words ? cw[jb] : 0u;
+        const int xa_ = covBase + 4 * j, xb_ = covBase + 4 * jb;
+        const bool fulla = (xa_ >= x0) && (xa_ + 4 <= x1), fullb = (xb_ >= x0) && (xb_ + 4 <= x1);
+        const bool storea = solid && cva == 0xFFFFFFFFu && fulla, storeb = solid && cvb == 0xFFFFFFFFu && fullb;
+        const bool rmwa = cva != 0u && !storea, rmwb = cvb != 0u && !storeb;
+        uint4 va = colour4, vb = colour4;
+        if (rmwa) va = *reinterpret_cast<const uint4*>(row + xa_);
+        if (rmwb) vb = *reinterpret_cast<const uint4*>(row + xb_);
+        if (cva != 0u) {
+          cw[j] = 0u;
+          if (storea) cnt += 4;  // sse2.nim:552-555, 648-651
+          else va = blend_word(cva, xa_, va);
+          *reinterpret_cast<uint4*>(row + xa_) = va;
+        }
+        if (cvb != 0u) {
+          cw[jb] = 0u;
+          if (storeb) cnt += 4;
+          else vb = blend_word(cvb, xb_, vb);
+          *reinterpret_cast<uint4*>(row + xb_) = vb;
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int j = word0 + lane; j < words; j += 32) {
+        const uint32_t cv = cw[j];
+        const int x = covBase + 4 * j;
+        if (MODE != MaskBlend && cv == 0u) continue;
+        cw[j] = 0u;
+        uint4* p = reinterpret_cast<uint4*>(row + x);
+        const bool full = (x >= x0) && (x + 4 <= x1);
+        if (MODE == MaskBlend && pA(rgbx) == 255u && cv == 0xFFFFFFFFu && full) {  // sse2.nim:750-751
+          cnt += 4;
+          continue;
+        }
+        *p = blend_word(cv, x, *p);
+      }
     }
   } else {
     const int xlo = MODE != MaskBlend ? max(pxLo, x0) : x0, xhi = MODE != MaskBlend ? min(pxHi, x1) : x1;
@@ -1312,8 +1353,8 @@ __device__ __noinline__ void coverage_row(WarpCtx& c, const uint2* __restrict__ 
   }
   c.covered += cnt;
   if (MODE == MaskBlend) {  // :1516-1517
-    clear_span(c, 0, x0);
-    clear_span(c, x1, c.w);
+    clear_span(c, 0, startX);
+    clear_span(c, startX + pathWidth, c.w);
   }
 }
 
@@ -1353,16 +1394,16 @@ __device__ __noinline__ void apply_row(WarpCtx& c, px_t rgbx, int startX, int pa
           xa = __uint_as_float(ab.x); xb = __uint_as_float(ab.y);
           xFirst = f2ll(fminf(xa, xb));
           xEnd = f2ll(ceilf(fmaxf(xa, xb)));
-          pxB = xFirst > 0 ? xFirst : 0;
-          pxE = xEnd < W ? xEnd : W;
+          pxB = xFirst > c.tx0 ? xFirst : c.tx0;  // inside the image and inside this warp's tile
+          pxE = xEnd < c.tx1 ? xEnd : c.tx1;
         }
         const bool isLeft = (lane & 1) == 0;  // base is a multiple of 32: even sorted positions are left edges
         // interior of the pair: [ceil(left max x), trunc(right min x)) (:1849-1854); the right edge is the next lane
         const long long rightMin = __shfl_down_sync(0xffffffffu, xFirst, 1);
         int fillBegin = 0, fillEnd = 0;
         if (i < n && isLeft) {
-          fillBegin = clampi(xEnd, 0, W);
-          fillEnd = clampi(rightMin, 0, W);
+          fillBegin = clampi(xEnd, c.tx0, c.tx1);
+          fillEnd = clampi(rightMin, c.tx0, c.tx1);
         }
         const bool longEdge = pxE - pxB > 6;
         if (!longEdge) {
@@ -1418,7 +1459,7 @@ __device__ __noinline__ void apply_row(WarpCtx& c, px_t rgbx, int startX, int pa
           const float xa = __uint_as_float(ab.x), xb = __uint_as_float(ab.y);
           if (side == 0) { lax = xa; lbx = xb; } else { rax = xa; rbx = xb; }
           const long long xFirst = f2ll(fminf(xa, xb)), xEnd = f2ll(ceilf(fmaxf(xa, xb)));
-          const long long b_ = xFirst > 0 ? xFirst : 0, e_ = xEnd < W ? xEnd : W;
+          const long long b_ = xFirst > c.tx0 ? xFirst : c.tx0, e_ = xEnd < c.tx1 ? xEnd : c.tx1;
 #pragma unroll 1
           for (long long xl = b_ + lane; xl < e_; xl += 32) {
             edge_px<MODE>(row, mode, y, xl, side == 0, em, eb, xa, xb, xFirst, rgbx);
@@ -1510,13 +1551,17 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
   while (true) {
     unsigned long long ticket = 0;
     if (lane == 0) ticket = atomicAdd(&A.counters[A.ticketSlot], 1ull);
-    ticket = __shfl_sync(0xffffffffu, ticket, 0) + (unsigned long long)A.rowBegin;
-    if ((long long)ticket >= A.rowEnd) break;
-    const unsigned t32 = (unsigned)ticket;  // layers * h < 2^31 (checked by the host)
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    const unsigned long long rowOfTicket = ticket / (unsigned)A.tiles + (unsigned long long)A.rowBegin;
+    if ((long long)rowOfTicket >= A.rowEnd) break;
+    const int tile = (int)(ticket - (ticket / (unsigned)A.tiles) * (unsigned)A.tiles);
+    const unsigned t32 = (unsigned)rowOfTicket;  // layers * h < 2^31 (checked by the host)
     const int layer = (int)(t32 / H_), y = (int)(t32 - (unsigned)layer * H_);
     WarpCtx c;
     c.row = A.canvas + (size_t)t32 * (size_t)A.w;
     c.w = A.w;
+    c.tx0 = tile * A.tileW;
+    c.tx1 = min(c.tx0 + A.tileW, A.w);
     c.y = y;
     c.lane = lane;
     c.cov = cov;
@@ -1538,7 +1583,10 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
           const FillHeader* Hp = A.fills + fl;
           const int sY = Hp->startY, pH = Hp->pathHeight;
           rgbx = Hp->rgbx; bmode = Hp->mode; startX = Hp->startX; pathWidth = Hp->pathWidth;
-          if (y >= sY && y < pH) {
+          // a fill whose columns [startX, startX + pathWidth) (+-1: an edge pixel can round one past the bounds)
+          // miss this warp's tile has nothing to do here — except MaskBlend, which clears what it does not cover
+          act = bmode == MaskBlend || (startX - 1 < c.tx1 && startX + pathWidth + 1 > c.tx0);
+          if (act && y >= sY && y < pH) {
             const JobHdr hd = A.jobs[A.fillJobBase[fl] + (y - sY)];
             kind = hd.kind; n = hd.n; pa = hd.pa; pb = hd.pb;
             pay = job_payload(A, Hp, y, nullptr);
@@ -1822,7 +1870,11 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
 
   // launch geometry: plan_kernel strides over the jobs, raster_kernel's persistent warps take one
   // (layer, row) ticket at a time; both sized to what is resident on the GPU
-  L.covBytes = ((w + 7) & ~3) + 4;             // coverage row, word aligned, with the covBase slack
+  // canvas rows are rasterised in tiles of 1024 columns, one warp each: fills that miss a tile are skipped there,
+  // which shortens the ordered chain a warp walks, and a row's work runs on several warps at once
+  L.tileW = w > 1536 ? 1024 : ((w + 3) & ~3);
+  L.tiles = (w + L.tileW - 1) / L.tileW;
+  L.covBytes = ((L.tileW + 7) & ~3) + 4;       // coverage row of a tile, word aligned, with the covBase slack
   L.smemCap = 64;                              // entries per band planned from shared memory
   L.warpsPerBlock = 8;
   while (L.warpsPerBlock > 1 && (size_t)L.covBytes * L.warpsPerBlock > 96 * 1024) L.warpsPerBlock /= 2;
@@ -1840,7 +1892,7 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
     occSmem = L.smemBytes;
   }
   const int blocksPerSm = std::max(1, occRaster), planPerSm = std::max(1, occPlan);
-  long long wantBlocks = (totalRows + L.warpsPerBlock - 1) / L.warpsPerBlock;
+  long long wantBlocks = (totalRows * L.tiles + L.warpsPerBlock - 1) / L.warpsPerBlock;
   L.rasterBlocks = (int)std::max<long long>(1, std::min<long long>(wantBlocks, (long long)r.num_sms * blocksPerSm));
   L.planBlocks = (int)std::max<long long>(1, std::min<long long>((jobsTotal + 7) / 8, (long long)r.num_sms * planPerSm));
   L.scratchSlotCount = r.num_sms * planPerSm;
@@ -2009,7 +2061,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
   A.w = L.w; A.h = L.h; A.layers = L.layers;
   A.fills = L.fills; A.rowRange = L.rowRange; A.layerFillBegin = L.layerFillBegin; A.entryOff = L.entryOff; A.entries = L.entries;
   A.flags = L.flags; A.gscratch = L.scratch; A.counters = L.counters;
-  A.smemCap = L.smemCap; A.scratchCap = L.maxEntries; A.covBytes = L.covBytes;
+  A.smemCap = L.smemCap; A.scratchCap = L.maxEntries; A.covBytes = L.covBytes; A.tileW = L.tileW; A.tiles = L.tiles;
   A.countCovered = covered_px ? 1 : 0;
   A.numFills = L.numFills;
   A.fillJobBase = L.fillJobBase; A.payOff = L.payOff; A.jobs = L.jobs; A.payload = L.payload; A.totalJobs = L.totalJobs;
@@ -2081,7 +2133,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
       B.rowEnd = band_edge(totalRows, b + 1, K);
       B.ticketSlot = 4 + b;
       if (B.rowEnd <= B.rowBegin) return 0;
-      const int blocks = (int)std::max<long long>(1, std::min<long long>((B.rowEnd - B.rowBegin + L.warpsPerBlock - 1) / L.warpsPerBlock,
+      const int blocks = (int)std::max<long long>(1, std::min<long long>(((B.rowEnd - B.rowBegin) * L.tiles + L.warpsPerBlock - 1) / L.warpsPerBlock,
                                                                        L.rasterBlocks));
       raster_kernel<<<blocks, L.warpsPerBlock * 32, L.smemBytes, r.band_stream[b]>>>(B);
       PX_LAUNCHED();
