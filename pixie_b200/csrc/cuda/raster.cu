@@ -75,6 +75,7 @@ struct CmdList {
   Entry* entries = nullptr;
   uint8_t* flags = nullptr;
   uint32_t* ranges = nullptr;  // per segment: first | last << 16 band it touches (count_kernel)
+  uint32_t* groupRange = nullptr;  // the same per aligned group of 32 segments
   uint32_t* scratch = nullptr;  // per-warp spill area when a band has more entries than fit in smem
   unsigned long long* counters = nullptr;  // [0] row ticket, [1] covered px
   int rasterBlocks = 0, warpsPerBlock = 0, scratchWords = 0, covBytes = 0, smemCap = 0, tileW = 0, tiles = 1;
@@ -154,25 +155,44 @@ PXD void band_range(const FillHeader& H, float ay, float by, unsigned& atP, unsi
 }
 __global__ void __launch_bounds__(256) count_kernel(const FillHeader* __restrict__ fills, int numFills,
                                                     const float4* __restrict__ segs, int numSegs, int* __restrict__ cnt,
-                                                    uint32_t* __restrict__ ranges) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < numSegs; i += gridDim.x * blockDim.x) {
-    int f = find_fill<false>(fills, numFills, i);
-    while (f > 0 && fills[f].segCount == 0) f--;  // empty fills share their segBegin with the next one
-    const FillHeader H = fills[f];
-    if (!H.active || H.numPartitions <= 0 || i >= H.segBegin + H.segCount) {
-      ranges[i] = kNoBand;
-      continue;
+                                                    uint32_t* __restrict__ ranges, uint32_t* __restrict__ groupRange) {
+  // a warp = 32 consecutive segments, aligned to 32: besides the per-segment band range it leaves one summary word
+  // for the group (lowest first band | highest last band << 16), so that partition_kernel's band warps skip
+  // groups that cannot touch their band — consecutive segments of a path are neighbours in space
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < numSegs; base += gridDim.x * blockDim.x) {
+    const int i = base + (threadIdx.x & 31);
+    unsigned atP = 0xFFFFu, toP = 0u;  // kNoBand
+    int f = -1;
+    bool plain = false;  // a segment of an active, packed fill: its range can go into the summary
+    if (i < numSegs) {
+      f = find_fill<false>(fills, numFills, i);
+      while (f > 0 && fills[f].segCount == 0) f--;  // empty fills share their segBegin with the next one
+      const FillHeader H = fills[f];
+      if (!H.active || H.numPartitions <= 0 || i >= H.segBegin + H.segCount) {
+        ranges[i] = kNoBand;
+      } else if (H.numPartitions == 1) {
+        atomicAdd(&cnt[H.partBase], 1);
+        ranges[i] = 0u;
+        atP = toP = 0u;
+        plain = true;
+      } else {
+        const float4 s = segs[i];
+        band_range(H, s.y, s.w, atP, toP);
+        plain = H.numPartitions <= kMaxPackedBands;
+        ranges[i] = plain ? (atP | (toP << 16)) : kNoBand;
+        for (unsigned p = atP; p <= toP; p++) atomicAdd(&cnt[H.partBase + (int)p], 1);
+      }
     }
-    if (H.numPartitions == 1) {
-      atomicAdd(&cnt[H.partBase], 1);
-      ranges[i] = 0u;
-      continue;
+    const int f0 = __shfl_sync(0xffffffffu, f, 0);
+    const bool uniform = __all_sync(0xffffffffu, plain && f == f0);
+    unsigned lo = atP, hi = toP;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    const float4 s = segs[i];
-    unsigned atP, toP;
-    band_range(H, s.y, s.w, atP, toP);
-    ranges[i] = H.numPartitions <= kMaxPackedBands ? (atP | (toP << 16)) : kNoBand;
-    for (unsigned p = atP; p <= toP; p++) atomicAdd(&cnt[H.partBase + (int)p], 1);
+    // groups that mix fills (or hold segments without a packed range) are always scanned
+    if ((threadIdx.x & 31) == 0) groupRange[base >> 5] = uniform ? (lo | (hi << 16)) : 0xFFFF0000u;
   }
 }
 
@@ -218,7 +238,8 @@ __global__ void __launch_bounds__(256) partition_kernel(const FillHeader* __rest
                                                         const int* __restrict__ entryOff,
                                                         const float4* __restrict__ segs,
                                                         const int16_t* __restrict__ wind,
-                                                        const uint32_t* __restrict__ ranges, Entry* __restrict__ entries,
+                                                        const uint32_t* __restrict__ ranges,
+                                                        const uint32_t* __restrict__ groupRange, Entry* __restrict__ entries,
                                                         uint8_t* __restrict__ flags, int numParts) {
   const int lane = threadIdx.x & 31;
   const int warpsTotal = (gridDim.x * blockDim.x) >> 5;
@@ -232,36 +253,40 @@ __global__ void __launch_bounds__(256) partition_kernel(const FillHeader* __rest
     const int outBase = entryOff[gp];
     int out = outBase;
     bool aa = false;
-    constexpr int kChunks = 8;  // 256 segments in flight per iteration: the scan is latency bound
-    for (int base0 = 0; base0 < H.segCount; base0 += 32 * kChunks) {
-      uint32_t rv[kChunks];
-#pragma unroll
-      for (int q = 0; q < kChunks; q++) {
-        const int i = base0 + q * 32 + lane;
-        rv[q] = kNoBand;
-        if (i < H.segCount) {
+    // The fill's segments in groups of 32 aligned to the global segment index: 32 group summaries per step decide
+    // which groups can touch this band; only those are scanned (in order: groups ascending, lanes ascending).
+    const int gBegin = H.segBegin >> 5, gEnd = (H.segBegin + H.segCount + 31) >> 5;
+    const unsigned pk = (unsigned)p & 0xFFFFu;
+    for (int g0 = gBegin; g0 < gEnd; g0 += 32) {
+      bool need = false;
+      if (g0 + lane < gEnd) {
+        const uint32_t gr = packed ? groupRange[g0 + lane] : 0xFFFF0000u;
+        need = pk >= (gr & 0xFFFFu) && pk <= (gr >> 16);
+      }
+      unsigned todo = __ballot_sync(0xffffffffu, need);
+      while (todo) {
+        const int g = g0 + __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int gi = g * 32 + lane;          // global segment index
+        const int i = gi - H.segBegin;         // index within the fill
+        bool touches = false;
+        if (i >= 0 && i < H.segCount) {
           if (packed) {
-            rv[q] = ranges[H.segBegin + i];
+            const uint32_t rv = ranges[gi];
+            touches = pk >= (rv & 0xFFFFu) && pk <= (rv >> 16);
           } else {  // more bands than the packed form holds: partitionRange from the segment itself
-            const float4 s = segs[H.segBegin + i];
+            const float4 s = segs[gi];
             unsigned atP, toP;
             band_range(H, s.y, s.w, atP, toP);
-            rv[q] = ((unsigned)p >= atP && (unsigned)p <= toP) ? ((unsigned)p & 0xFFFFu) * 0x00010001u : kNoBand;
+            touches = (unsigned)p >= atP && (unsigned)p <= toP;
           }
         }
-      }
-      const unsigned pk = (unsigned)p & 0xFFFFu;
-#pragma unroll
-      for (int q = 0; q < kChunks; q++) {
-        const int i = base0 + q * 32 + lane;
-        const unsigned atP = rv[q] & 0xFFFFu, toP = rv[q] >> 16;
-        const bool touches = pk >= atP && pk <= toP;
         const unsigned bal = __ballot_sync(0xffffffffu, touches);
         if (touches) {
-          const float4 s = segs[H.segBegin + i];
+          const float4 s = segs[gi];
           Entry e;  // initPartitionEntry (:1127-1135)
           e.ax = s.x; e.ay = s.y; e.bx = s.z; e.by = s.w;
-          e.winding = (int)wind[H.segBegin + i];
+          e.winding = (int)wind[gi];
           e.pad = 0;
           e.m = 0.0f;
           e.b = 0.0f;
@@ -1903,6 +1928,7 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   const size_t oFlags = off;     off = al(off + std::max<size_t>(1, P));
   const size_t oPayOff = off;    off = al(off + (P + 1) * 4);   // plan payload offset of each band
   const size_t oRanges = off;    off = al(off + std::max<size_t>(1, (size_t)numSegs) * 4);  // packed band range of each segment
+  const size_t oGroups = off;    off = al(off + ((size_t)numSegs / 32 + 2) * 4);           // ... and of each group of 32
   const size_t oSlots = off;     off = al(off + (size_t)((L.scratchSlotCount + 31) / 32) * 4);
   const size_t oCounters = off;  off = al(off + 256);           // [0] row ticket, [1] covered px, [2] entries, [3] max, [4..11] band tickets, [16..31] heavy-job counts (front / back of each launch's list)
   const size_t totalA = off;
@@ -1962,6 +1988,7 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   L.entryOff = (int*)(L.block + oEntryOff);
   L.flags = L.block + oFlags;
   L.ranges = (uint32_t*)(L.block + oRanges);
+  L.groupRange = (uint32_t*)(L.block + oGroups);
   L.counters = (unsigned long long*)(L.block + oCounters);
   L.h2dBytes = h2dBytes;
 
@@ -1972,7 +1999,7 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
     PX_CUDA(cudaMemsetAsync(L.entryOff, 0, (P + 1) * 4, r.stream));
     PX_CUDA(cudaMemsetAsync(L.scratchSlots, 0, (size_t)((L.scratchSlotCount + 31) / 32) * 4, r.stream));
     const int cblocks = (int)std::min<int64_t>((numSegs + 255) / 256, (int64_t)r.num_sms * 8);
-    count_kernel<<<std::max(cblocks, 1), 256, 0, r.stream>>>(L.fills, numFills, L.segs, (int)numSegs, L.entryOff, L.ranges);
+    count_kernel<<<std::max(cblocks, 1), 256, 0, r.stream>>>(L.fills, numFills, L.segs, (int)numSegs, L.entryOff, L.ranges, L.groupRange);
     PX_LAUNCHED();
     scan_kernel<<<1, 1024, 0, r.stream>>>(L.entryOff, (int)P, L.counters + 2);
     PX_LAUNCHED();
@@ -2051,7 +2078,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
     const int blocks = (warps + 7) / 8;
     {
       ProfScope ps(kProfPartition);
-      partition_kernel<<<blocks, 256, 0, r.stream>>>(L.fills, L.numFills, L.entryOff, L.segs, L.wind, L.ranges, L.entries,
+      partition_kernel<<<blocks, 256, 0, r.stream>>>(L.fills, L.numFills, L.entryOff, L.segs, L.wind, L.ranges, L.groupRange, L.entries,
                                                      L.flags, (int)L.numParts);
     }
     PX_LAUNCHED();
