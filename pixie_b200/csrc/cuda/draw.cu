@@ -395,10 +395,10 @@ struct GradientArgs {
   float pos[kMaxStops];
   float col[kMaxStops][4];
 };
-PXD uint32_t quant_f(float v) {  // chroma Color channel -> uint8
-  const float r = floorf(v * 255.0f + 0.5f);
-  if (!(r > 0.0f)) return 0u;
-  return r > 255.0f ? 255u : (uint32_t)r;
+PXD uint32_t quant_f(float v) {  // chroma Color channel -> uint8: floor(v * 255 + 0.5) clamped to 0..255, NaN -> 0
+  const float r = v * 255.0f + 0.5f;
+  if (!(r >= 1.0f)) return 0u;
+  return r >= 255.0f ? 255u : (uint32_t)__float2int_rd(r);
 }
 PXD float fix_angle(float a) {
   const float pi = (float)3.141592653589793238462643383279502884, tau = (float)(2 * 3.141592653589793238462643383279502884);
@@ -428,7 +428,10 @@ PXD px_t gradient_color(const GradientArgs& G, float t) {  // :68-94
   a *= G.opacity;
   const uint32_t a8 = quant_f(a), r8 = quant_f(r), g8 = quant_f(g), b8 = quant_f(b);
   if (a8 == 255u) return mk(r8, g8, b8, a8);
-  return mk((r8 * a8 + 127u) / 255u, (g8 * a8 + 127u) / 255u, (b8 * a8 + 127u) / 255u, a8);
+  // (c * a + 127) div 255 on two channels at once (16-bit lanes, sums <= 65152)
+  const uint32_t rb = div255x2((r8 | (b8 << 16)) * a8 + 0x007F007Fu);
+  const uint32_t g_ = div255x2(g8 * a8 + 0x7Fu);
+  return (rb & 0xFFu) | ((g_ & 0xFFu) << 8) | (rb & 0x00FF0000u) | (a8 << 24);
 }
 
 PXD float gradient_t(const GradientArgs& G, int x, int y) {
