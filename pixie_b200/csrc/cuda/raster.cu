@@ -474,7 +474,7 @@ PXD int walk_spans(const int* hitAt, const int* hitW, int numHits, int rule, int
 // bands' stable sorts use it with key = {sortable value, original position}: unique keys, so the result is the
 // stable order, in O(P log^2 P / 32) steps per lane instead of the quadratic rank count.
 template <int U>  // U = P / 64 compare-exchanges per lane and step
-PXD void warp_bitonic_sort_u(uint32_t* khi, uint32_t* klo, int lane) {
+PXD void warp_bitonic_sort_u(uint2* key, int lane) {  // key = {low word, high word}
   constexpr int P = 64 * U;
   constexpr int B = U < 4 ? U : 4;  // pairs in flight per lane
 #pragma unroll 1
@@ -485,23 +485,23 @@ PXD void warp_bitonic_sort_u(uint32_t* khi, uint32_t* klo, int lane) {
       // independent, but the compiler cannot tell that from the stores), then the exchanges
 #pragma unroll 1
       for (int u0 = 0; u0 < U; u0 += B) {
-        uint32_t ah[B], al[B], bh[B], bl[B];
+        uint2 a[B], b[B];
         int ii[B];
 #pragma unroll
         for (int u = 0; u < B; u++) {
           const int t = lane + 32 * (u0 + u);
           const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
           ii[u] = i;
-          ah[u] = khi[i]; al[u] = klo[i];
-          bh[u] = khi[i | j]; bl[u] = klo[i | j];
+          a[u] = key[i];
+          b[u] = key[i | j];
         }
 #pragma unroll
         for (int u = 0; u < B; u++) {
           const int i = ii[u];
-          const bool aGreater = ah[u] > bh[u] || (ah[u] == bh[u] && al[u] > bl[u]);
+          const bool aGreater = a[u].y > b[u].y || (a[u].y == b[u].y && a[u].x > b[u].x);
           if (aGreater == ((i & k) == 0)) {
-            khi[i] = bh[u]; klo[i] = bl[u];
-            khi[i | j] = ah[u]; klo[i | j] = al[u];
+            key[i] = b[u];
+            key[i | j] = a[u];
           }
         }
       }
@@ -509,10 +509,10 @@ PXD void warp_bitonic_sort_u(uint32_t* khi, uint32_t* klo, int lane) {
     }
   }
 }
-PXD void warp_bitonic_sort(uint32_t* khi, uint32_t* klo, int P, int lane) {  // P = 128, 256 or 512
-  if (P == 128) warp_bitonic_sort_u<2>(khi, klo, lane);
-  else if (P == 256) warp_bitonic_sort_u<4>(khi, klo, lane);
-  else warp_bitonic_sort_u<8>(khi, klo, lane);
+PXD void warp_bitonic_sort(uint2* key, int P, int lane) {  // P = 128, 256 or 512
+  if (P == 128) warp_bitonic_sort_u<2>(key, lane);
+  else if (P == 256) warp_bitonic_sort_u<4>(key, lane);
+  else warp_bitonic_sort_u<8>(key, lane);
 }
 PXD uint32_t sortable_float(float f) {  // order-preserving map to uint32; -0 and +0 compare equal in the reference
   if (f == 0.0f) return 0x80000000u;
@@ -876,17 +876,13 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
       if (nsel > kBitonicMin && nsel <= kBitonicMax && scr != sscr) {
         int P = 2 * kBitonicMin;
         while (P < nsel) P <<= 1;
-        uint32_t* khi = sscr;  // the warp's shared-memory scratch is free while the band's arrays live in HBM
-        uint32_t* klo = khi + P;
+        uint2* key = reinterpret_cast<uint2*>(sscr);  // the warp's shared-memory scratch is free while the band's arrays live in HBM
 #pragma unroll 1
-        for (int i = lane; i < P; i += 32) {
-          khi[i] = i < nsel ? sortable_float(mid[i]) : 0xFFFFFFFFu;
-          klo[i] = (uint32_t)i;
-        }
+        for (int i = lane; i < P; i += 32) key[i] = make_uint2((uint32_t)i, i < nsel ? sortable_float(mid[i]) : 0xFFFFFFFFu);
         __syncwarp();
-        warp_bitonic_sort(khi, klo, P, lane);
+        warp_bitonic_sort(key, P, lane);
 #pragma unroll 1
-        for (int i = lane; i < nsel; i += 32) order[i] = (int)klo[i];
+        for (int i = lane; i < nsel; i += 32) order[i] = (int)key[i].x;
       } else {
 #pragma unroll 1
         for (int i = lane; i < nsel; i += 32) {
@@ -971,8 +967,7 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
         // live in the warp's shared-memory scratch, which is free while the band's arrays are in HBM
         int P = 2 * kBitonicMin;
         while (P < n) P <<= 1;
-        uint32_t* khi = sscr;
-        uint32_t* klo = khi + P;
+        uint2* key = reinterpret_cast<uint2*>(sscr);
         float yLine = (float)y + initialOffset - offset;
 #pragma unroll 1
         for (int m = 0; m < quality; m++) {
@@ -988,19 +983,19 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
                 at = fixed32(x);
               }
             }
-            khi[s] = (uint32_t)at ^ 0x80000000u;  // kNoHit -> 0xFFFFFFFF sorts last
-            klo[s] = (uint32_t)s;
+            key[s] = make_uint2((uint32_t)s, (uint32_t)at ^ 0x80000000u);  // kNoHit -> 0xFFFFFFFF sorts last
           }
           __syncwarp();
-          warp_bitonic_sort(khi, klo, P, lane);
+          warp_bitonic_sort(key, P, lane);
           int cnt = 0;
 #pragma unroll 1
           for (int base = 0; base < n; base += 32) {
             const int r = base + lane;
-            const bool hit = r < n && khi[r] != 0xFFFFFFFFu;
+            const uint2 kv = r < n ? key[r] : make_uint2(0u, 0xFFFFFFFFu);
+            const bool hit = kv.y != 0xFFFFFFFFu;
             if (hit) {
-              sAt[m * n + r] = (int)(khi[r] ^ 0x80000000u);
-              sW[m * n + r] = ent[selC[klo[r]]].winding;
+              sAt[m * n + r] = (int)(kv.y ^ 0x80000000u);
+              sW[m * n + r] = ent[selC[kv.x]].winding;
             }
             cnt += __popc(__ballot_sync(0xffffffffu, hit));
           }
