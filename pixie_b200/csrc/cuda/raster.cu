@@ -1890,9 +1890,9 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
 
   // launch geometry: plan_kernel strides over the jobs, raster_kernel's persistent warps take one
   // (layer, row) ticket at a time; both sized to what is resident on the GPU
-  // canvas rows are rasterised in tiles of 1024 columns, one warp each: fills that miss a tile are skipped there,
+  // canvas rows are rasterised in tiles of 2048 columns, one warp each: fills that miss a tile are skipped there,
   // which shortens the ordered chain a warp walks, and a row's work runs on several warps at once
-  L.tileW = w > 1536 ? 1024 : ((w + 3) & ~3);
+  L.tileW = w > 3072 ? 2048 : ((w + 3) & ~3);
   L.tiles = (w + L.tileW - 1) / L.tileW;
   L.covBytes = ((L.tileW + 7) & ~3) + 4;       // coverage row of a tile, word aligned, with the covBase slack
   L.smemCap = 64;                              // entries per band planned from shared memory

@@ -61,3 +61,32 @@ def test_segment_soup(style, seed):
         np.savez(f"gpurun_out/fuzz_fail_{style}_{seed}.npz", got=got, want=want, bg=bg, **arr)
     assert n == 0, f"{style}/{seed}: {n} px differ (max {mx}) at {where}"
     assert gc_ == wc
+
+
+@pytest.mark.parametrize("style", ["uniform", "grid", "wide", "sliver"])
+@pytest.mark.parametrize("w", [6144, 4100, 4101, 9001])
+def test_segment_soup_wide_canvas_row_tiles(style, w):
+    """Canvases wider than one raster tile (2048 columns): rows are rasterised by several warps, each clamped to
+    its tile — spans, trapezoid edges and MaskBlend clears that cross tile boundaries, vector and scalar rows."""
+    h = 24
+    rng = np.random.default_rng([w, ["uniform", "grid", "wide", "sliver"].index(style)])
+    b = FillBatch()
+    for k in range(8):
+        n = int(rng.integers(2, 160))
+        segs = _soup(rng, n, w, h, style)
+        if len(segs) == 0:
+            continue
+        col = int(rng.integers(0, 2 ** 32)) if k % 2 else 0xFF000000 | int(rng.integers(0, 2 ** 24))
+        mode = [0, 17, 16, 0, 11, 19, 0, 16][k]
+        b.add(segs, col, int(rng.integers(0, 2)), mode)
+    # axis-aligned rectangles that straddle the tile boundaries (mode A / trapezoid shortcuts)
+    for x0, x1 in ((2040.0, 2060.0), (1000.5, 5000.25), (2048.0, 4096.0), (-10.0, w + 10.0)):
+        xy = np.array([[x0, 2, x0, 20], [x1, 2, x1, 20]], np.float32)
+        b.add(Segments(xy, np.array([1, -1], np.int16)), 0x80402010, 0, int(rng.choice([0, 16, 17])))
+    arr = b.arrays()
+    bg = rng.integers(0, 256, (1, h, w, 4), dtype=np.uint8)
+    want, wc = oracle_render_batch(arr, w, h, background=bg)
+    got, gc_ = gpu_render_batch(arr, w, h, background=bg)
+    n, mx, where = diff_report(got, want)
+    assert n == 0, f"{style}/{w}: {n} px differ (max {mx}) at {where}"
+    assert gc_ == wc
