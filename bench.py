@@ -380,6 +380,11 @@ def run_ours(args):
         dist = dist_
     if not os.path.exists(dev.LIB_PATH):
         g.build()
+    numa = None
+    if world > 1:
+        from pixie_b200 import multi
+
+        numa = multi.bind_to_gpu_numa(local_rank)  # before any pinned allocation
     dev.init(local_rank)
     dev.set_profiling(True)
     peak, peak_src = load_peaks()
@@ -515,7 +520,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": round(1e3 * e2e_total / args.steps, 4), "result_nonzero": checksum_ok},
         "gpu_launches": int(launches_timed),
-        "covered_px_per_step": int(covered), "cmdlist": info,
+        "covered_px_per_step": int(covered), "cmdlist": info, "numa_binding_rank0": numa,
         "roofline": roofline, "cpu_baseline": cpu,
     }
     if banded is not None:

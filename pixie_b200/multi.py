@@ -15,6 +15,41 @@ from __future__ import annotations
 import numpy as np
 
 
+def bind_to_gpu_numa(device_index: int) -> dict:
+    """One process per GPU: run this process on the CPUs of the NUMA node its GPU hangs off, so that the pinned
+    staging buffers (first touch) and the host passes of the end-to-end path stay local to the PCIe root the
+    pixels cross.  Best effort: returns what it found and changes nothing when the topology is not exposed."""
+    import os
+
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # nvml reports an 8-digit domain, sysfs uses 4
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info = {"numa_node": node, "cpus": len(allowed)}
+    except Exception as e:  # no NVML, no sysfs entry, container without the topology: leave the affinity alone
+        info["error"] = repr(e)[:80]
+    return info
+
+
 def shard_range(n_units: int, world: int, rank: int):
     """Contiguous block [begin, end) of independent units owned by `rank`."""
     base, rem = divmod(n_units, world)
