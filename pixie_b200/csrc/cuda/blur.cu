@@ -447,39 +447,185 @@ static int blur_impl(Image* im, const uint16_t* lut_host, int radius, uint32_t o
 
 // ---------------------------------------------------------------- spread (images.nim:700-758)
 // Separable max (spread > 0) / min (< 0) filter of alpha with a window clamped at the borders.
+// Four neighbouring outputs per thread, rows in a grid-stride loop (one CTA per row piece would be a million CTAs
+// at 16384^2).  X pass: RGBX alpha -> A8 plane; Y pass: A8 plane -> rgbx(0, 0, 0, value), four columns at a time
+// with the byte-wise SIMD max / min.
 template <bool GROW>
 __global__ void __launch_bounds__(256) spread_x(const px_t* __restrict__ src, uint8_t* __restrict__ tmp, int w, int h, int s) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= w) return;
-  const px_t* row = src + (size_t)w * y;
-  const int lo = max(x - s, 0), hi = min(x + s, w - 1);
-  uint32_t v = GROW ? 0u : 255u;
-  for (int xx = lo; xx <= hi; xx++) {
-    const uint32_t al = row[xx] >> 24;
-    v = GROW ? max(v, al) : min(v, al);
+  const int x4 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (x4 >= w) return;
+  const bool vec = (w & 3) == 0;
+  for (int y = blockIdx.y; y < h; y += gridDim.y) {
+    const px_t* row = src + (size_t)w * y;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = GROW ? 0u : 255u;
+    const int lo = max(x4 - s, 0), hi = min(x4 + 3 + s, w - 1);
+    for (int xx = lo; xx <= hi; xx++) {
+      const uint32_t al = row[xx] >> 24;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (xx >= x4 + k - s && xx <= x4 + k + s) v[k] = GROW ? max(v[k], al) : min(v[k], al);
+      }
+    }
+    uint8_t* out = tmp + (size_t)w * y + x4;
+    if (vec) {
+      *reinterpret_cast<uint32_t*>(out) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (x4 + k < w) out[k] = (uint8_t)v[k];
+    }
   }
-  tmp[(size_t)w * y + x] = (uint8_t)v;
 }
 template <bool GROW>
 __global__ void __launch_bounds__(256) spread_y(const uint8_t* __restrict__ tmp, px_t* __restrict__ dst, int w, int h, int s) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= w) return;
-  const int lo = max(y - s, 0), hi = min(y + s, h - 1);
-  uint32_t v = GROW ? 0u : 255u;
-  for (int yy = lo; yy <= hi; yy++) {
-    const uint32_t al = tmp[(size_t)w * yy + x];
-    v = GROW ? max(v, al) : min(v, al);
+  const int x4 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (x4 >= w) return;
+  const bool vec = (w & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  if (vec) {  // two rows per step: their windows share all but one row each; 16x2 lanes (one VIMNMX per pair)
+    const uint32_t idn = GROW ? 0u : 0x00FF00FFu;
+    const uint8_t* col = tmp + x4;
+    auto acc = [&](uint32_t& e, uint32_t& o, uint32_t a4) {
+      const uint32_t ae = a4 & 0x00FF00FFu, ao = (a4 >> 8) & 0x00FF00FFu;  // bytes {0, 2} and {1, 3}
+      e = GROW ? __vmaxu2(e, ae) : __vminu2(e, ae);
+      o = GROW ? __vmaxu2(o, ao) : __vminu2(o, ao);
+    };
+    auto store = [&](int y, uint32_t e, uint32_t o) {  // rgbx(0, 0, 0, value)
+      *reinterpret_cast<uint4*>(dst + (size_t)w * y + x4) = make_uint4(e << 24, o << 24, (e >> 16) << 24, (o >> 16) << 24);
+    };
+    for (int y = 2 * blockIdx.y; y < h; y += 2 * gridDim.y) {
+      const int clo = max(y + 1 - s, 0), chi = min(y + s, h - 1);  // rows both windows hold
+      uint32_t e = idn, o = idn;
+      const uint8_t* p = col + (size_t)w * clo;
+      for (int yy = clo; yy <= chi; yy++, p += w) acc(e, o, *reinterpret_cast<const uint32_t*>(p));
+      uint32_t e0 = e, o0 = o, e1 = e, o1 = o;
+      if (y - s >= 0) acc(e0, o0, *reinterpret_cast<const uint32_t*>(col + (size_t)w * (y - s)));
+      if (y + 1 + s <= h - 1) acc(e1, o1, *reinterpret_cast<const uint32_t*>(col + (size_t)w * (y + 1 + s)));
+      store(y, e0, o0);
+      if (y + 1 < h) store(y + 1, e1, o1);
+    }
+    return;
   }
-  dst[(size_t)w * y + x] = v << 24;  // rgbx(0, 0, 0, value)
+  for (int y = blockIdx.y; y < h; y += gridDim.y) {
+    const int lo = max(y - s, 0), hi = min(y + s, h - 1);
+    {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (x4 + k >= w) break;
+        uint32_t v = GROW ? 0u : 255u;
+        for (int yy = lo; yy <= hi; yy++) {
+          const uint32_t al = tmp[(size_t)w * yy + x4 + k];
+          v = GROW ? max(v, al) : min(v, al);
+        }
+        dst[(size_t)w * y + x4 + k] = v << 24;
+      }
+    }
+  }
+}
+
+// X pass through shared memory: a CTA owns 1024 outputs of a row, stages the alpha bytes of the 1024 + 2s pixels
+// they look at (the source may be shifted by an integer offset: shadow's offset copy, images.nim:764-769, folded
+// into the read — pixels of the image the shifted source does not reach are transparent, pixels outside the image
+// do not take part, :717-718), then every thread forms its 4 outputs as byte-wise SIMD max / min over 2s + 1
+// unaligned 4-byte windows.
+template <bool GROW>
+__global__ void __launch_bounds__(256) spread_x_tiled(const px_t* __restrict__ src, int ox, int oy, uint8_t* __restrict__ tmp,
+                                                      int w, int h, int s) {
+  extern __shared__ __align__(16) uint8_t sa[];  // alpha of x in [x0 - s, x0 + 1024 + s), padded to words
+  const int x0 = blockIdx.x * 1024;
+  const int span = 1024 + 2 * s;
+  const bool vec = (w & 3) == 0;
+  for (int y = blockIdx.y; y < h; y += gridDim.y) {
+    const int sy = y - oy;
+    const px_t* row = src + (size_t)w * (sy >= 0 && sy < h ? sy : 0);
+    __syncthreads();
+    // alphas are staged as 16-bit lanes, two per shared word: byte-wise SIMD min / max is emulated on this
+    // architecture (7 instructions), the 16x2 form is one VIMNMX
+    uint32_t* sww = reinterpret_cast<uint32_t*>(sa);
+    const bool rowIn = sy >= 0 && sy < h;
+    for (int jw = threadIdx.x; jw < (span + 4 + 1) / 2; jw += blockDim.x) {  // two alphas -> one shared word
+      uint32_t word = 0u;
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const int i = 2 * jw + k, x = x0 - s + i;
+        uint32_t al = GROW ? 0u : 255u;  // outside the image: does not take part
+        if (x >= 0 && x < w && i < span) {
+          const int sx = x - ox;
+          al = (rowIn && sx >= 0 && sx < w) ? (row[sx] >> 24) : 0u;
+        }
+        word |= al << (16 * k);
+      }
+      sww[jw] = word;
+    }
+    __syncthreads();
+    const int x4 = x0 + 4 * threadIdx.x;
+    if (x4 < w) {
+      // outputs x4 + {0,1} and x4 + {2,3}: windows start at element 4 tid + {0,2} + d, d = 0 .. 2s
+      uint32_t v01 = GROW ? 0u : 0x00FF00FFu, v23 = v01;
+      const uint32_t* base = sww + 2 * threadIdx.x;
+      uint32_t w0 = base[0], w1 = base[1];
+      for (int d0 = 0; d0 <= 2 * s; d0 += 2) {
+        const uint32_t w2 = base[(d0 >> 1) + 2];
+        v01 = GROW ? __vmaxu2(v01, w0) : __vminu2(v01, w0);
+        v23 = GROW ? __vmaxu2(v23, w1) : __vminu2(v23, w1);
+        if (d0 + 1 <= 2 * s) {
+          const uint32_t o01 = __funnelshift_r(w0, w1, 16), o23 = __funnelshift_r(w1, w2, 16);
+          v01 = GROW ? __vmaxu2(v01, o01) : __vminu2(v01, o01);
+          v23 = GROW ? __vmaxu2(v23, o23) : __vminu2(v23, o23);
+        }
+        w0 = w1;
+        w1 = w2;
+      }
+      const uint32_t v = __byte_perm(v01, v23, 0x6420);  // four alpha bytes
+      uint8_t* out = tmp + (size_t)w * y + x4;
+      if (vec) {
+        *reinterpret_cast<uint32_t*>(out) = v;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (x4 + k < w) out[k] = (uint8_t)(v >> (8 * k));
+      }
+    }
+  }
+}
+
+// spread of `src` shifted by (ox, oy) into dst (dst may be src when the offset is zero)
+static int spread_impl(Image* im, int spread);
+static int spread_shifted(const Image* src, int ox, int oy, Image* dstIm, int spread) {
+  Runtime& r = rt();
+  const int s = spread > 0 ? spread : -spread;
+  void* tmp;
+  if (int rc = get_scratch(0, (size_t)dstIm->w * dstIm->h, &tmp)) return rc;
+  const int w = dstIm->w, h = dstIm->h;
+  dim3 gx((w + 1023) / 1024, 1);
+  gx.y = (unsigned)std::max(1, std::min(h, r.num_sms * 8 / (int)gx.x));
+  const size_t smem = (size_t)(2 * (1024 + 2 * s) + 32) & ~(size_t)3;  // 16-bit lanes
+  dim3 gy((w + 1023) / 1024, 1);
+  gy.y = (unsigned)std::max(1, std::min(h, r.num_sms * 16 / (int)gy.x));
+  ProfScope ps(kProfSpread);
+  if (spread > 0) {
+    spread_x_tiled<true><<<gx, 256, smem, r.stream>>>((const px_t*)src->data, ox, oy, (uint8_t*)tmp, w, h, s);
+    PX_LAUNCHED();
+    spread_y<true><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, (px_t*)dstIm->data, w, h, s);
+  } else {
+    spread_x_tiled<false><<<gx, 256, smem, r.stream>>>((const px_t*)src->data, ox, oy, (uint8_t*)tmp, w, h, s);
+    PX_LAUNCHED();
+    spread_y<false><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, (px_t*)dstIm->data, w, h, s);
+  }
+  PX_LAUNCHED();
+  return 0;
 }
 
 static int spread_impl(Image* im, int spread) {
   Runtime& r = rt();
   if (spread == 0) return 0;
   if (im->bpp != 4 || im->layers != 1) return fail_pixie("spread needs a single-layer RGBX image");
+  if (spread <= 8192 && spread >= -8192) return spread_shifted(im, 0, 0, im, spread);
   void* tmp;
   if (int rc = get_scratch(0, (size_t)im->w * im->h, &tmp)) return rc;
-  dim3 grid((im->w + 255) / 256, im->h);
+  dim3 grid((im->w + 1023) / 1024, 1);
+  grid.y = (unsigned)std::max(1, std::min(im->h, r.num_sms * 16 / (int)grid.x));
   const int s = spread > 0 ? spread : -spread;
   if (spread > 0) {
     spread_x<true><<<grid, 256, 0, r.stream>>>((const px_t*)im->data, (uint8_t*)tmp, im->w, im->h, s);
@@ -540,6 +686,18 @@ int pixie_cuda_shadow(pixie_image_t srch, pixie_image_t dsth, float ox, float oy
   if (s->data == d->data) return fail_pixie("shadow: src and dst must be different images");
   // mask = copy / mask.draw(image, translate(offset), OverwriteBlend) (images.nim:764-769), built directly in dst;
   // integer offsets end in blendRect, fractional ones in drawSmooth, as in draw()
+  const bool integral = ox == truncf(ox) && oy == truncf(oy) && fabsf(ox) < 1e9f && fabsf(oy) < 1e9f;
+  if (spread != 0 && spread <= 8192 && spread >= -8192 && integral) {
+    // the offset copy folded into the spread's read: no intermediate mask image
+    if (int rc = spread_shifted(s, (int)ox, (int)oy, d, spread)) return rc;
+    if (int rc = blur_impl(d, lut, radius, 0u, 0, d->h)) return rc;
+    Runtime& r = rt();
+    const size_t n = (size_t)d->w * d->h;
+    int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)r.num_sms * 16);
+    shadow_composite<<<blocks, 256, 0, r.stream>>>((px_t*)d->data, n, rgbx);
+    PX_LAUNCHED();
+    return 0;
+  }
   if (ox == 0 && oy == 0) {
     if (int rc = pixie_cuda_image_copy(dsth, srch)) return rc;
   } else {
