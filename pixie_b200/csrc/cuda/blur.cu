@@ -529,22 +529,25 @@ __global__ void __launch_bounds__(256) spread_y(const uint8_t* __restrict__ tmp,
 // into the read — pixels of the image the shifted source does not reach are transparent, pixels outside the image
 // do not take part, :717-718), then every thread forms its 4 outputs as byte-wise SIMD max / min over 2s + 1
 // unaligned 4-byte windows.
+constexpr int kSpreadRows = 4;  // rows per CTA step: their global loads are in flight together
 template <bool GROW>
 __global__ void __launch_bounds__(256) spread_x_tiled(const px_t* __restrict__ src, int ox, int oy, uint8_t* __restrict__ tmp,
                                                       int w, int h, int s) {
-  extern __shared__ __align__(16) uint8_t sa[];  // alpha of x in [x0 - s, x0 + 1024 + s), padded to words
+  extern __shared__ __align__(16) uint8_t sa[];  // kSpreadRows x alphas of x in [x0 - s, x0 + 1024 + s) as 16-bit lanes
   const int x0 = blockIdx.x * 1024;
   const int span = 1024 + 2 * s;
+  const int words = (span + 4 + 1) / 2 + 2;      // shared words per row
   const bool vec = (w & 3) == 0;
-  for (int y = blockIdx.y; y < h; y += gridDim.y) {
-    const int sy = y - oy;
-    const px_t* row = src + (size_t)w * (sy >= 0 && sy < h ? sy : 0);
+  uint32_t* sww = reinterpret_cast<uint32_t*>(sa);
+  for (int y0 = kSpreadRows * blockIdx.y; y0 < h; y0 += kSpreadRows * gridDim.y) {
     __syncthreads();
     // alphas are staged as 16-bit lanes, two per shared word: byte-wise SIMD min / max is emulated on this
     // architecture (7 instructions), the 16x2 form is one VIMNMX
-    uint32_t* sww = reinterpret_cast<uint32_t*>(sa);
-    const bool rowIn = sy >= 0 && sy < h;
-    for (int jw = threadIdx.x; jw < (span + 4 + 1) / 2; jw += blockDim.x) {  // two alphas -> one shared word
+    for (int idx = threadIdx.x; idx < kSpreadRows * words; idx += blockDim.x) {
+      const int r = idx / words, jw = idx - r * words;
+      const int y = y0 + r, sy = y - oy;
+      const bool rowIn = y < h && sy >= 0 && sy < h;
+      const px_t* row = src + (size_t)w * (rowIn ? sy : 0);
       uint32_t word = 0u;
 #pragma unroll
       for (int k = 0; k < 2; k++) {
@@ -556,35 +559,40 @@ __global__ void __launch_bounds__(256) spread_x_tiled(const px_t* __restrict__ s
         }
         word |= al << (16 * k);
       }
-      sww[jw] = word;
+      sww[idx] = word;
     }
     __syncthreads();
     const int x4 = x0 + 4 * threadIdx.x;
     if (x4 < w) {
-      // outputs x4 + {0,1} and x4 + {2,3}: windows start at element 4 tid + {0,2} + d, d = 0 .. 2s
-      uint32_t v01 = GROW ? 0u : 0x00FF00FFu, v23 = v01;
-      const uint32_t* base = sww + 2 * threadIdx.x;
-      uint32_t w0 = base[0], w1 = base[1];
-      for (int d0 = 0; d0 <= 2 * s; d0 += 2) {
-        const uint32_t w2 = base[(d0 >> 1) + 2];
-        v01 = GROW ? __vmaxu2(v01, w0) : __vminu2(v01, w0);
-        v23 = GROW ? __vmaxu2(v23, w1) : __vminu2(v23, w1);
-        if (d0 + 1 <= 2 * s) {
-          const uint32_t o01 = __funnelshift_r(w0, w1, 16), o23 = __funnelshift_r(w1, w2, 16);
-          v01 = GROW ? __vmaxu2(v01, o01) : __vminu2(v01, o01);
-          v23 = GROW ? __vmaxu2(v23, o23) : __vminu2(v23, o23);
-        }
-        w0 = w1;
-        w1 = w2;
-      }
-      const uint32_t v = __byte_perm(v01, v23, 0x6420);  // four alpha bytes
-      uint8_t* out = tmp + (size_t)w * y + x4;
-      if (vec) {
-        *reinterpret_cast<uint32_t*>(out) = v;
-      } else {
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-          if (x4 + k < w) out[k] = (uint8_t)(v >> (8 * k));
+      for (int r = 0; r < kSpreadRows; r++) {
+        const int y = y0 + r;
+        if (y >= h) break;
+        // outputs x4 + {0,1} and x4 + {2,3}: windows start at element 4 tid + {0,2} + d, d = 0 .. 2s
+        uint32_t v01 = GROW ? 0u : 0x00FF00FFu, v23 = v01;
+        const uint32_t* base = sww + r * words + 2 * threadIdx.x;
+        uint32_t w0 = base[0], w1 = base[1];
+        for (int d0 = 0; d0 <= 2 * s; d0 += 2) {
+          const uint32_t w2 = base[(d0 >> 1) + 2];
+          v01 = GROW ? __vmaxu2(v01, w0) : __vminu2(v01, w0);
+          v23 = GROW ? __vmaxu2(v23, w1) : __vminu2(v23, w1);
+          if (d0 + 1 <= 2 * s) {
+            const uint32_t o01 = __funnelshift_r(w0, w1, 16), o23 = __funnelshift_r(w1, w2, 16);
+            v01 = GROW ? __vmaxu2(v01, o01) : __vminu2(v01, o01);
+            v23 = GROW ? __vmaxu2(v23, o23) : __vminu2(v23, o23);
+          }
+          w0 = w1;
+          w1 = w2;
+        }
+        const uint32_t v = __byte_perm(v01, v23, 0x6420);  // four alpha bytes
+        uint8_t* out = tmp + (size_t)w * y + x4;
+        if (vec) {
+          *reinterpret_cast<uint32_t*>(out) = v;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (x4 + k < w) out[k] = (uint8_t)(v >> (8 * k));
+        }
       }
     }
   }
@@ -599,8 +607,8 @@ static int spread_shifted(const Image* src, int ox, int oy, Image* dstIm, int sp
   if (int rc = get_scratch(0, (size_t)dstIm->w * dstIm->h, &tmp)) return rc;
   const int w = dstIm->w, h = dstIm->h;
   dim3 gx((w + 1023) / 1024, 1);
-  gx.y = (unsigned)std::max(1, std::min(h, r.num_sms * 8 / (int)gx.x));
-  const size_t smem = (size_t)(2 * (1024 + 2 * s) + 32) & ~(size_t)3;  // 16-bit lanes
+  gx.y = (unsigned)std::max(1, std::min((h + kSpreadRows - 1) / kSpreadRows, r.num_sms * 8 / (int)gx.x));
+  const size_t smem = (size_t)kSpreadRows * (((1024 + 2 * s) + 4 + 1) / 2 + 2) * 4;  // 16-bit lanes, kSpreadRows rows
   dim3 gy((w + 1023) / 1024, 1);
   gy.y = (unsigned)std::max(1, std::min(h, r.num_sms * 16 / (int)gy.x));
   ProfScope ps(kProfSpread);
@@ -621,7 +629,7 @@ static int spread_impl(Image* im, int spread) {
   Runtime& r = rt();
   if (spread == 0) return 0;
   if (im->bpp != 4 || im->layers != 1) return fail_pixie("spread needs a single-layer RGBX image");
-  if (spread <= 8192 && spread >= -8192) return spread_shifted(im, 0, 0, im, spread);
+  if (spread <= 2048 && spread >= -2048) return spread_shifted(im, 0, 0, im, spread);
   void* tmp;
   if (int rc = get_scratch(0, (size_t)im->w * im->h, &tmp)) return rc;
   dim3 grid((im->w + 1023) / 1024, 1);
@@ -687,7 +695,7 @@ int pixie_cuda_shadow(pixie_image_t srch, pixie_image_t dsth, float ox, float oy
   // mask = copy / mask.draw(image, translate(offset), OverwriteBlend) (images.nim:764-769), built directly in dst;
   // integer offsets end in blendRect, fractional ones in drawSmooth, as in draw()
   const bool integral = ox == truncf(ox) && oy == truncf(oy) && fabsf(ox) < 1e9f && fabsf(oy) < 1e9f;
-  if (spread != 0 && spread <= 8192 && spread >= -8192 && integral) {
+  if (spread != 0 && spread <= 2048 && spread >= -2048 && integral) {
     // the offset copy folded into the spread's read: no intermediate mask image
     if (int rc = spread_shifted(s, (int)ox, (int)oy, d, spread)) return rc;
     if (int rc = blur_impl(d, lut, radius, 0u, 0, d->h)) return rc;
