@@ -196,3 +196,29 @@ def test_error_cases_match_reference():
     segs = host.Segments(np.array([[-1e30, 0, 1e30, 10], [1e30, 0, -1e30, 10]], np.float32), np.array([1, -1], np.int16))
     with pytest.raises(PixieError, match="Path int overflow"):
         dev.fill_segments(img, segs, 0xFF0000FF, 0, 0)
+
+
+@pytest.mark.parametrize("shape", [(37, 1030), (9, 2051), (130, 77), (5, 4), (64, 2048)])
+@pytest.mark.parametrize("amount", [1, -1, 3, -6, 40, 2100])
+def test_spread_shapes(shape, amount):
+    """Row tiles of 1024 outputs, widths that are not multiples of 4, more rows than one CTA step, windows wider
+    than the image, and the fallback beyond 2048."""
+    gb, ob = _backends()
+    img = synth.random_premultiplied(shape[0], shape[1], 9)
+    a, b = img.copy(), img.copy()
+    gb.spread(a, amount)
+    ob.spread(b, amount)
+    assert diff_report(a, b)[0] == 0
+
+
+@pytest.mark.parametrize("offset", [(1030, 3), (-1500, -2), (5, 70), (3000, 0)])
+@pytest.mark.parametrize("spread_", [2, -3])
+def test_shadow_wide(offset, spread_):
+    """The offset copy folded into the spread's read, on an image wider than one row tile (and offsets that push
+    the source out of the image)."""
+    gb, ob = _backends()
+    img = synth.random_premultiplied(40, 2300, 10)
+    lut = host.gaussianKernel(5)
+    a = gb.shadow(img, offset[0], offset[1], spread_, lut, 5, pack(10, 20, 30, 200))
+    b = ob.shadow(img, offset[0], offset[1], spread_, lut, 5, pack(10, 20, 30, 200))
+    assert diff_report(a, b)[0] == 0
