@@ -157,11 +157,33 @@ PXD px_t blend_normal(px_t b, px_t s) {  // :60-70
   if (pA(s) == 0u) return b;
   return line_normal(b, s);
 }
+// 256-entry tables of the two float divisions every un-premultiply / to-Color step makes: x / 255.0f and
+// 255.0f / a are IEEE-exact quotients of small integers, so a table lookup returns the very same float as the
+// division the reference performs (the divisions were most of the float blend modes' instructions).
+struct BlendTables {
+  float div255[256];   // (float)x / 255.0f
+  float mul255[256];   // 255.0f / (float)a   (a = 0 unused)
+};
+constexpr BlendTables make_blend_tables() {
+  BlendTables t{};
+  for (int i = 0; i < 256; i++) {
+    t.div255[i] = (float)i / 255.0f;
+    t.mul255[i] = i ? 255.0f / (float)i : 0.0f;
+  }
+  return t;
+}
+__device__ const BlendTables g_blend_tables = make_blend_tables();
+
+PXD uint32_t round_half_away_u(float v) {  // roundf() of a non-negative value below 2^23, as an integer: exact
+  uint32_t r = __float2uint_rz(v);
+  if (v - (float)r >= 0.5f) r++;
+  return r;
+}
 PXD uint32_t straight_(uint32_t c, uint32_t a) {  // internal.nim:68-74 stand-in for chroma rgba()
   if (a == 0u) return 0u;
-  float multiplier = 255.0f / (float)a;
-  float v = roundf((float)c * multiplier);
-  return v > 255.0f ? 255u : (uint32_t)v;
+  const float multiplier = __ldg(&g_blend_tables.mul255[a]);
+  const uint32_t v = round_half_away_u((float)c * multiplier);
+  return v > 255u ? 255u : v;
 }
 PXD px_t to_straight(px_t p) {
   uint32_t a = pA(p);
@@ -188,14 +210,15 @@ struct Col {
 };
 PXD Col to_color(px_t p) {
   px_t s = to_straight(p);
-  Col c = {(float)pR(s) / 255.0f, (float)pG(s) / 255.0f, (float)pB(s) / 255.0f, (float)pA(s) / 255.0f};
+  Col c = {__ldg(&g_blend_tables.div255[pR(s)]), __ldg(&g_blend_tables.div255[pG(s)]), __ldg(&g_blend_tables.div255[pB(s)]),
+           __ldg(&g_blend_tables.div255[pA(s)])};
   return c;
 }
-PXD uint32_t f2u8(float v) {
-  float x = roundf(v * 255.0f);
-  if (!(x > 0.0f)) return 0u;
-  if (x > 255.0f) return 255u;
-  return (uint32_t)x;
+PXD uint32_t f2u8(float v) {  // roundf(v * 255) clamped to 0..255 (NaN and negatives -> 0)
+  const float x = v * 255.0f;
+  if (!(x >= 0.5f)) return 0u;
+  if (x >= 255.0f) return 255u;
+  return round_half_away_u(x);
 }
 PXD px_t from_color(Col c) { return to_premul(mk(f2u8(c.r), f2u8(c.g), f2u8(c.b), f2u8(c.a))); }
 PXD float min3f(float a, float b, float c) { return fminf(a, fminf(b, c)); }
