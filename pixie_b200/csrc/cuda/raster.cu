@@ -1725,6 +1725,8 @@ static double now_ms() {
 }
 static const bool g_trace = getenv("PIXIE_CUDA_TRACE") != nullptr;
 
+constexpr int64_t kHostCountMaxSegs = 8192;  // lists up to this size are counted on the host (no sync in the call)
+
 static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layers, int numFills, const int32_t* layerOf,
                       const float* seg, const int16_t* wind, const int32_t* segOff, const uint32_t* rgbx,
                       const uint8_t* rule, const uint8_t* mode) {
@@ -1757,11 +1759,21 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   const size_t oJobBase = off;   off = al(off + jobBase.size() * 4);
   const size_t oBandJobs = off;  off = al(off + (L.bands > 1 ? (size_t)L.bands * jobBase.size() * 4 : 0));
   const size_t h2dBytes = off;
+  // Small lists (a single fillPath, a glyph, an icon): the band counts, their scans and the packed band ranges are
+  // made on the host while it stages the segments anyway, so the call needs no device round trip before it can
+  // size block B — fill_segments / fill_batch then only enqueue work (the reference's callers issue thousands of
+  // small fills; a synchronisation per call would cost more than the fill).
+  const bool hostCount = arena && numSegs <= kHostCountMaxSegs;
+  size_t stageBytes = h2dBytes;
+  if (hostCount) {
+    const size_t pMax = (size_t)numSegs / 2 + (size_t)numFills + 1;
+    stageBytes += 2 * al((pMax + 1) * 4) + al(pMax) + al(std::max<size_t>(1, (size_t)numSegs) * 4) + al(((size_t)numSegs / 32 + 2) * 4);
+  }
   uint8_t* stage = nullptr;
   std::vector<uint8_t> pageable;
   if (arena) {  // per-call lists: library-owned growing arena + pinned staging, no malloc/free per call
     void* pin;
-    if (int rc = staging_acquire(h2dBytes, &pin)) return rc;
+    if (int rc = staging_acquire(stageBytes, &pin)) return rc;
     stage = (uint8_t*)pin;
   } else {
     pageable.resize(h2dBytes + 16);
@@ -1967,7 +1979,75 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
       L.bandJobs[b] = run;
     }
   }
-  PX_CUDA(cudaMemcpyAsync(L.block + oFills, stage + oFills, h2dBytes - oFills, cudaMemcpyHostToDevice, r.stream));
+  long long meta[4] = {0, 2, 0, 0};  // entries, max entries per band, payload entry-rows
+  size_t copyEnd = h2dBytes;
+  if (hostCount && P > 0) {
+    int* cnt = reinterpret_cast<int*>(stage + oEntryOff);
+    unsigned* pOff = reinterpret_cast<unsigned*>(stage + oPayOff);
+    uint32_t* rng = reinterpret_cast<uint32_t*>(stage + oRanges);
+    uint32_t* grp = reinterpret_cast<uint32_t*>(stage + oGroups);
+    memset(cnt, 0, (P + 1) * 4);
+    for (int64_t i = 0; i < numSegs; i++) rng[i] = kNoBand;
+    for (int k = 0; k < numFills; k++) {  // count_kernel on the host: partitionRange (:1201-1213) per segment
+      const FillHeader& F = fills[k];
+      if (!F.active || F.numPartitions <= 0) continue;
+      const float startYf = (float)(unsigned)F.startY;
+      const unsigned ph = (unsigned)F.partitionHeight, lastP = (unsigned)(F.numPartitions - 1);
+      const float* sp = seg + 4 * (size_t)F.segBegin;
+      for (int i = 0; i < F.segCount; i++, sp += 4) {
+        unsigned atP = 0, toP = 0;
+        if (F.numPartitions > 1) {
+          atP = std::min(f2u_host(fmaxf(0.0f, sp[1] - startYf)) / ph, lastP);
+          toP = std::min(f2u_host(fmaxf(0.0f, sp[3] - startYf)) / ph, lastP);
+        }
+        rng[F.segBegin + i] = F.numPartitions <= kMaxPackedBands ? (atP | (toP << 16)) : kNoBand;
+        for (unsigned p_ = atP; p_ <= toP; p_++) cnt[F.partBase + (int)p_]++;
+      }
+    }
+    {  // group summaries (count_kernel's warp reduction): uniform groups of one plain fill get lo | hi << 16
+      int k = 0;
+      for (int64_t g0 = 0; g0 * 32 < numSegs; g0++) {
+        const int64_t b = g0 * 32, e = b + 32;
+        uint32_t out = 0xFFFF0000u;
+        while (k < numFills && (int64_t)fills[k].segBegin + fills[k].segCount <= b) k++;
+        if (e <= numSegs && k < numFills) {
+          const FillHeader& F = fills[k];
+          if (F.active && F.numPartitions > 0 && F.numPartitions <= kMaxPackedBands && F.segBegin <= b && (int64_t)F.segBegin + F.segCount >= e) {
+            uint32_t lo = 0xFFFFu, hi = 0u;
+            for (int64_t i = b; i < e; i++) {
+              lo = std::min(lo, rng[i] & 0xFFFFu);
+              hi = std::max(hi, rng[i] >> 16);
+            }
+            out = lo | (hi << 16);
+          }
+        }
+        grp[g0] = out;
+      }
+    }
+    long long run = 0, mx = 0, pay = 0;
+    {  // scan_kernel + payload_scan_kernel on the host
+      for (int k = 0; k < numFills; k++) {
+        const FillHeader& F = fills[k];
+        if (!F.active || F.numPartitions <= 0) continue;
+        for (int p_ = 0; p_ < F.numPartitions; p_++) {
+          const size_t gp = (size_t)F.partBase + (size_t)p_;
+          const int c = cnt[gp];
+          const int top = F.startY + p_ * F.partitionHeight;
+          const int bottom = (p_ == F.numPartitions - 1) ? F.pathHeight : top + F.partitionHeight;
+          cnt[gp] = (int)run;
+          pOff[gp] = (unsigned)pay;
+          run += c;
+          mx = std::max<long long>(mx, c);
+          pay += (long long)(bottom - top) * c;
+        }
+      }
+      cnt[P] = (int)run;
+      pOff[P] = (unsigned)pay;
+    }
+    meta[0] = run; meta[1] = mx; meta[2] = pay;
+    copyEnd = oSlots;  // entry offsets, (flags), payload offsets, ranges and group summaries travel with the headers
+  }
+  PX_CUDA(cudaMemcpyAsync(L.block + oFills, stage + oFills, copyEnd - oFills, cudaMemcpyHostToDevice, r.stream));
   if (arena) {
     if (int rc = staging_release()) return rc;
   }
@@ -1987,22 +2067,24 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   L.counters = (unsigned long long*)(L.block + oCounters);
   L.h2dBytes = h2dBytes;
 
-  // K1a/K1b on the device: how many entries each band gets (partitionRange :1201-1213), exclusive
-  // scan to entry offsets, total and maximum -> 16 bytes back to the host to size block B.
-  long long meta[4] = {0, 2, 0, 0};  // entries, max entries per band, payload entry-rows
-  if (P > 0) {
-    PX_CUDA(cudaMemsetAsync(L.entryOff, 0, (P + 1) * 4, r.stream));
-    PX_CUDA(cudaMemsetAsync(L.scratchSlots, 0, (size_t)((L.scratchSlotCount + 31) / 32) * 4, r.stream));
-    const int cblocks = (int)std::min<int64_t>((numSegs + 255) / 256, (int64_t)r.num_sms * 8);
-    count_kernel<<<std::max(cblocks, 1), 256, 0, r.stream>>>(L.fills, numFills, L.segs, (int)numSegs, L.entryOff, L.ranges, L.groupRange);
-    PX_LAUNCHED();
-    scan_kernel<<<1, 1024, 0, r.stream>>>(L.entryOff, (int)P, L.counters + 2);
-    PX_LAUNCHED();
-    payload_scan_kernel<<<1, 1024, 0, r.stream>>>(L.fills, numFills, L.entryOff, (int)P, L.payOff, L.counters + 4);
-    PX_LAUNCHED();
-    PX_CUDA(cudaMemcpyAsync(meta, L.counters + 2, 24, cudaMemcpyDeviceToHost, r.stream));
+  // K1a/K1b on the device (lists too large to count on the host): how many entries each band gets
+  // (partitionRange :1201-1213), exclusive scan to entry offsets, total and maximum -> 24 bytes back to the host
+  // to size block B.
+  PX_CUDA(cudaMemsetAsync(L.scratchSlots, 0, (size_t)((L.scratchSlotCount + 31) / 32) * 4, r.stream));
+  if (!hostCount) {
+    if (P > 0) {
+      PX_CUDA(cudaMemsetAsync(L.entryOff, 0, (P + 1) * 4, r.stream));
+      const int cblocks = (int)std::min<int64_t>((numSegs + 255) / 256, (int64_t)r.num_sms * 8);
+      count_kernel<<<std::max(cblocks, 1), 256, 0, r.stream>>>(L.fills, numFills, L.segs, (int)numSegs, L.entryOff, L.ranges, L.groupRange);
+      PX_LAUNCHED();
+      scan_kernel<<<1, 1024, 0, r.stream>>>(L.entryOff, (int)P, L.counters + 2);
+      PX_LAUNCHED();
+      payload_scan_kernel<<<1, 1024, 0, r.stream>>>(L.fills, numFills, L.entryOff, (int)P, L.payOff, L.counters + 4);
+      PX_LAUNCHED();
+      PX_CUDA(cudaMemcpyAsync(meta, L.counters + 2, 24, cudaMemcpyDeviceToHost, r.stream));
+    }
+    PX_CUDA(cudaStreamSynchronize(r.stream));  // also retires the pageable staging vector of owned lists
   }
-  PX_CUDA(cudaStreamSynchronize(r.stream));  // also retires the pageable staging vector of owned lists
   if (meta[0] > 0x7fffffffll) return fail_pixie("command list too large");
   L.numEntries = meta[0];
   L.maxEntries = (int)std::max<long long>(2, meta[1]);
