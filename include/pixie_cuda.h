@@ -79,7 +79,9 @@ int pixie_cuda_fill_segments(pixie_image_t image, const float* seg_xyxy, const i
  * layer_of_fill[k] (NULL = layer 0; must be non-decreasing).  Fills of one layer are applied in
  * list order (svg.nim:563-604 newImage(svg), fonts.nim:566-596); layers are independent.
  * covered_px (optional, may be NULL) receives the number of pixels touched with non-zero coverage
- * summed over fills — the work unit of the Mpixel/s metric (blocks the host when non-NULL). */
+ * summed over fills — the work unit of the Mpixel/s metric (blocks the host when non-NULL).
+ * Lists of up to 8192 segments (a fillPath, a glyph, an icon) are sized on the host and only enqueue work;
+ * larger lists wait once inside the call for a 24-byte device readback (the sizes of the band arrays). */
 int pixie_cuda_fill_batch(pixie_image_t image, int num_fills, const int32_t* layer_of_fill,
                           const float* seg_xyxy, const int16_t* winding, const int32_t* seg_offsets,
                           const uint32_t* rgbx, const uint8_t* winding_rule, const uint8_t* blend_mode,
