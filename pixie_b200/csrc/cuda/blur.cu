@@ -478,11 +478,14 @@ __global__ void __launch_bounds__(256) spread_x(const px_t* __restrict__ src, ui
     }
   }
 }
-template <bool GROW>
-__global__ void __launch_bounds__(256) spread_y(const uint8_t* __restrict__ tmp, px_t* __restrict__ dst, int w, int h, int s) {
+// A8OUT: the result stays an alpha plane (shadow's mask, blurred as one channel) instead of rgbx(0, 0, 0, a)
+template <bool GROW, bool A8OUT = false>
+__global__ void __launch_bounds__(256) spread_y(const uint8_t* __restrict__ tmp, void* __restrict__ dstv, int w, int h, int s) {
   const int x4 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   if (x4 >= w) return;
-  const bool vec = (w & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  px_t* dst = reinterpret_cast<px_t*>(dstv);
+  uint8_t* dst8 = reinterpret_cast<uint8_t*>(dstv);
+  const bool vec = (w & 3) == 0 && (reinterpret_cast<uintptr_t>(dstv) & 15) == 0;
   if (vec) {  // two rows per step: their windows share all but one row each; 16x2 lanes (one VIMNMX per pair)
     const uint32_t idn = GROW ? 0u : 0x00FF00FFu;
     const uint8_t* col = tmp + x4;
@@ -492,7 +495,8 @@ __global__ void __launch_bounds__(256) spread_y(const uint8_t* __restrict__ tmp,
       o = GROW ? __vmaxu2(o, ao) : __vminu2(o, ao);
     };
     auto store = [&](int y, uint32_t e, uint32_t o) {  // rgbx(0, 0, 0, value)
-      *reinterpret_cast<uint4*>(dst + (size_t)w * y + x4) = make_uint4(e << 24, o << 24, (e >> 16) << 24, (o >> 16) << 24);
+      if (A8OUT) *reinterpret_cast<uint32_t*>(dst8 + (size_t)w * y + x4) = e | (o << 8);
+      else *reinterpret_cast<uint4*>(dst + (size_t)w * y + x4) = make_uint4(e << 24, o << 24, (e >> 16) << 24, (o >> 16) << 24);
     };
     for (int y = 2 * blockIdx.y; y < h; y += 2 * gridDim.y) {
       const int clo = max(y + 1 - s, 0), chi = min(y + s, h - 1);  // rows both windows hold
@@ -518,7 +522,8 @@ __global__ void __launch_bounds__(256) spread_y(const uint8_t* __restrict__ tmp,
           const uint32_t al = tmp[(size_t)w * yy + x4 + k];
           v = GROW ? max(v, al) : min(v, al);
         }
-        dst[(size_t)w * y + x4 + k] = v << 24;
+        if (A8OUT) dst8[(size_t)w * y + x4 + k] = (uint8_t)v;
+        else dst[(size_t)w * y + x4 + k] = v << 24;
       }
     }
   }
@@ -542,24 +547,59 @@ __global__ void __launch_bounds__(256) spread_x_tiled(const px_t* __restrict__ s
   for (int y0 = kSpreadRows * blockIdx.y; y0 < h; y0 += kSpreadRows * gridDim.y) {
     __syncthreads();
     // alphas are staged as 16-bit lanes, two per shared word: byte-wise SIMD min / max is emulated on this
-    // architecture (7 instructions), the 16x2 form is one VIMNMX
-    for (int idx = threadIdx.x; idx < kSpreadRows * words; idx += blockDim.x) {
-      const int r = idx / words, jw = idx - r * words;
+    // architecture (7 instructions), the 16x2 form is one VIMNMX.  64 threads per row walk the SOURCE row in aligned
+    // quads of pixels (one 16-byte load each, four quads in flight per thread) and scatter the alphas to the elements
+    // they land on: element i is destination x = x0 - s + i, source x = that - ox.
+    {
+      const int sxBase = x0 - s - ox;                                      // source x of element 0
+      const int qFirst = (sxBase >= 0 ? sxBase : sxBase - 3) / 4;          // floor(sxBase / 4)
+      const int nElems = 2 * words;
+      const int nQuads = (nElems + 3) / 4 + 1;
+      const int r = threadIdx.x >> 6;
+      static_assert(kSpreadRows == 4, "64 threads per staged row");
+      uint16_t* srow16 = reinterpret_cast<uint16_t*>(sww + r * words);
       const int y = y0 + r, sy = y - oy;
       const bool rowIn = y < h && sy >= 0 && sy < h;
       const px_t* row = src + (size_t)w * (rowIn ? sy : 0);
-      uint32_t word = 0u;
+      const bool vecSrc = vec && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+      const uint32_t idn = GROW ? 0u : 255u;  // outside the image: does not take part
+      for (int jb = threadIdx.x & 63; jb < nQuads; jb += 256) {
+        uint4 v[4];
 #pragma unroll
-      for (int k = 0; k < 2; k++) {
-        const int i = 2 * jw + k, x = x0 - s + i;
-        uint32_t al = GROW ? 0u : 255u;  // outside the image: does not take part
-        if (x >= 0 && x < w && i < span) {
-          const int sx = x - ox;
-          al = (rowIn && sx >= 0 && sx < w) ? (row[sx] >> 24) : 0u;
+        for (int u = 0; u < 4; u++) {
+          const int j = jb + 64 * u, sx0 = 4 * (qFirst + j);
+          v[u] = make_uint4(0u, 0u, 0u, 0u);  // pixels the shifted source does not reach are transparent
+          if (j < nQuads && rowIn) {
+            if (vecSrc && sx0 >= 0 && sx0 + 3 < w) {
+              v[u] = *reinterpret_cast<const uint4*>(row + sx0);
+            } else {
+              if (sx0 >= 0 && sx0 < w) v[u].x = row[sx0];
+              if (sx0 + 1 >= 0 && sx0 + 1 < w) v[u].y = row[sx0 + 1];
+              if (sx0 + 2 >= 0 && sx0 + 2 < w) v[u].z = row[sx0 + 2];
+              if (sx0 + 3 >= 0 && sx0 + 3 < w) v[u].w = row[sx0 + 3];
+            }
+          }
         }
-        word |= al << (16 * k);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int j = jb + 64 * u;
+          if (j >= nQuads) break;
+          const int i0 = 4 * (qFirst + j) - sxBase, xd = x0 - s + i0;  // first element / destination x of the quad
+          const uint32_t a0 = v[u].x >> 24, a1 = v[u].y >> 24, a2 = v[u].z >> 24, a3 = v[u].w >> 24;
+          if (((i0 & 1) == 0) && i0 >= 0 && i0 + 3 < span && i0 + 3 < nElems && xd >= 0 && xd + 3 < w) {
+            uint32_t* d2 = reinterpret_cast<uint32_t*>(srow16 + i0);
+            d2[0] = a0 | (a1 << 16);
+            d2[1] = a2 | (a3 << 16);
+          } else {
+            const uint32_t al[4] = {a0, a1, a2, a3};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const int i = i0 + k, x = xd + k;
+              if (i >= 0 && i < nElems) srow16[i] = (uint16_t)((x >= 0 && x < w && i < span) ? al[k] : idn);
+            }
+          }
+        }
       }
-      sww[idx] = word;
     }
     __syncthreads();
     const int x4 = x0 + 4 * threadIdx.x;
@@ -600,11 +640,12 @@ __global__ void __launch_bounds__(256) spread_x_tiled(const px_t* __restrict__ s
 
 // spread of `src` shifted by (ox, oy) into dst (dst may be src when the offset is zero)
 static int spread_impl(Image* im, int spread);
-static int spread_shifted(const Image* src, int ox, int oy, Image* dstIm, int spread) {
+static int spread_shifted(const Image* src, int ox, int oy, Image* dstIm, int spread, void* tmp = nullptr,
+                          uint8_t* planeOut = nullptr) {
   Runtime& r = rt();
   const int s = spread > 0 ? spread : -spread;
-  void* tmp;
-  if (int rc = get_scratch(0, (size_t)dstIm->w * dstIm->h, &tmp)) return rc;
+  if (!tmp)
+    if (int rc = get_scratch(0, (size_t)dstIm->w * dstIm->h, &tmp)) return rc;
   const int w = dstIm->w, h = dstIm->h;
   dim3 gx((w + 1023) / 1024, 1);
   gx.y = (unsigned)std::max(1, std::min((h + kSpreadRows - 1) / kSpreadRows, r.num_sms * 8 / (int)gx.x));
@@ -615,11 +656,13 @@ static int spread_shifted(const Image* src, int ox, int oy, Image* dstIm, int sp
   if (spread > 0) {
     spread_x_tiled<true><<<gx, 256, smem, r.stream>>>((const px_t*)src->data, ox, oy, (uint8_t*)tmp, w, h, s);
     PX_LAUNCHED();
-    spread_y<true><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, (px_t*)dstIm->data, w, h, s);
+    if (planeOut) spread_y<true, true><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, planeOut, w, h, s);
+    else spread_y<true><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, dstIm->data, w, h, s);
   } else {
     spread_x_tiled<false><<<gx, 256, smem, r.stream>>>((const px_t*)src->data, ox, oy, (uint8_t*)tmp, w, h, s);
     PX_LAUNCHED();
-    spread_y<false><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, (px_t*)dstIm->data, w, h, s);
+    if (planeOut) spread_y<false, true><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, planeOut, w, h, s);
+    else spread_y<false><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, dstIm->data, w, h, s);
   }
   PX_LAUNCHED();
   return 0;
@@ -638,12 +681,12 @@ static int spread_impl(Image* im, int spread) {
   if (spread > 0) {
     spread_x<true><<<grid, 256, 0, r.stream>>>((const px_t*)im->data, (uint8_t*)tmp, im->w, im->h, s);
     PX_LAUNCHED();
-    spread_y<true><<<grid, 256, 0, r.stream>>>((const uint8_t*)tmp, (px_t*)im->data, im->w, im->h, s);
+    spread_y<true><<<grid, 256, 0, r.stream>>>((const uint8_t*)tmp, im->data, im->w, im->h, s);
     PX_LAUNCHED();
   } else {
     spread_x<false><<<grid, 256, 0, r.stream>>>((const px_t*)im->data, (uint8_t*)tmp, im->w, im->h, s);
     PX_LAUNCHED();
-    spread_y<false><<<grid, 256, 0, r.stream>>>((const uint8_t*)tmp, (px_t*)im->data, im->w, im->h, s);
+    spread_y<false><<<grid, 256, 0, r.stream>>>((const uint8_t*)tmp, im->data, im->w, im->h, s);
     PX_LAUNCHED();
   }
   return 0;
@@ -654,6 +697,91 @@ __global__ void __launch_bounds__(256) shadow_composite(px_t* __restrict__ p, si
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) p[i] = line_mask(color, p[i]);
+}
+
+// the alpha plane of `src` shifted by an integer offset (shadow's offset copy when there is no spread)
+__global__ void __launch_bounds__(256) alpha_shifted(const px_t* __restrict__ src, int ox, int oy, uint8_t* __restrict__ plane,
+                                                     int w, int h) {
+  const int x4 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (x4 >= w) return;
+  const bool vec = (w & 3) == 0;
+  for (int y = blockIdx.y; y < h; y += gridDim.y) {
+    const int sy = y - oy;
+    const bool rowIn = sy >= 0 && sy < h;
+    const px_t* row = src + (size_t)w * (rowIn ? sy : 0);
+    uint32_t v = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int sx = x4 + k - ox;
+      if (rowIn && sx >= 0 && sx < w && x4 + k < w) v |= (row[sx] >> 24) << (8 * k);
+    }
+    uint8_t* out = plane + (size_t)w * y + x4;
+    if (vec) {
+      *reinterpret_cast<uint32_t*>(out) = v;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (x4 + k < w) out[k] = (uint8_t)(v >> (8 * k));
+    }
+  }
+}
+
+// shadow's last step from an alpha plane: color MaskBlend rgbx(., ., ., a) = color * a / 255
+__global__ void __launch_bounds__(256) shadow_composite_a8(const uint8_t* __restrict__ plane, px_t* __restrict__ dst, size_t n,
+                                                           px_t color) {
+  size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  const size_t stride = 4 * (size_t)gridDim.x * blockDim.x;
+  const bool vec = (reinterpret_cast<uintptr_t>(plane) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  for (; i < n; i += stride) {
+    if (vec && i + 4 <= n) {
+      const uint32_t a4 = *reinterpret_cast<const uint32_t*>(plane + i);
+      *reinterpret_cast<uint4*>(dst + i) = make_uint4(mul_div255(color, a4 & 255u), mul_div255(color, (a4 >> 8) & 255u),
+                                                      mul_div255(color, (a4 >> 16) & 255u), mul_div255(color, a4 >> 24));
+    } else {
+      for (size_t k = i; k < n && k < i + 4; k++) dst[k] = mul_div255(color, plane[k]);
+    }
+  }
+}
+
+int blur_mma_a8(uint8_t* plane, uint8_t* tmp, int w, int h, const uint16_t* lut_host, int radius, uint32_t oobAlpha);
+
+// shadow with an integral offset as a one-channel pipeline: only the alpha of the mask reaches the result
+// (spread writes rgbx(0, 0, 0, a), blur treats channels independently, MaskBlend reads mask.a), so the
+// offset copy, spread, blur and composite run on an 8-bit plane.  -1: not applicable (blur outside the tensor-core
+// kernel's exact domain) — the caller takes the RGBX path.
+static int shadow_a8(const Image* s, Image* d, int ox, int oy, int spread, const uint16_t* lut, int radius, px_t rgbx) {
+  static const char* force = getenv("PIXIE_CUDA_BLUR");
+  if (force && strcmp(force, "cores") == 0) return -1;
+  if (radius < 0 || radius > 64 || spread > 2048 || spread < -2048) return -1;
+  if (radius > 0) {
+    unsigned long long sum = 0;
+    for (int i = 0; i < 2 * radius + 1; i++) sum += lut[i];
+    if (sum * 255ull >= (1ull << 24)) return -1;
+  }
+  Runtime& r = rt();
+  const int w = d->w, h = d->h;
+  const size_t planeBytes = ((size_t)w * h + 255) & ~(size_t)255;
+  void* blk;
+  if (int rc = get_scratch(0, 2 * planeBytes, &blk)) return rc;
+  uint8_t* tmp = (uint8_t*)blk;
+  uint8_t* plane = tmp + planeBytes;
+  if (spread != 0) {
+    if (int rc = spread_shifted(s, ox, oy, d, spread, tmp, plane)) return rc;
+  } else {
+    dim3 grid((w + 1023) / 1024, 1);
+    grid.y = (unsigned)std::max(1, std::min(h, r.num_sms * 16 / (int)grid.x));
+    alpha_shifted<<<grid, 256, 0, r.stream>>>((const px_t*)s->data, ox, oy, plane, w, h);
+    PX_LAUNCHED();
+  }
+  if (radius > 0) {
+    const int rc = blur_mma_a8(plane, tmp, w, h, lut, radius, 0u);
+    if (rc != 0) return rc > 0 ? rc : fail_pixie("shadow: alpha blur rejected a LUT it had accepted");
+  }
+  const size_t n = (size_t)w * h;
+  const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)r.num_sms * 16);
+  shadow_composite_a8<<<blocks, 256, 0, r.stream>>>(plane, (px_t*)d->data, n, rgbx);
+  PX_LAUNCHED();
+  return 0;
 }
 
 }  // namespace pixie
@@ -695,6 +823,10 @@ int pixie_cuda_shadow(pixie_image_t srch, pixie_image_t dsth, float ox, float oy
   // mask = copy / mask.draw(image, translate(offset), OverwriteBlend) (images.nim:764-769), built directly in dst;
   // integer offsets end in blendRect, fractional ones in drawSmooth, as in draw()
   const bool integral = ox == truncf(ox) && oy == truncf(oy) && fabsf(ox) < 1e9f && fabsf(oy) < 1e9f;
+  if (integral) {
+    const int rc = shadow_a8(s, d, (int)ox, (int)oy, spread, lut, radius, rgbx);
+    if (rc >= 0) return rc;
+  }
   if (spread != 0 && spread <= 2048 && spread >= -2048 && integral) {
     // the offset copy folded into the spread's read: no intermediate mask image
     if (int rc = spread_shifted(s, (int)ox, (int)oy, d, spread)) return rc;

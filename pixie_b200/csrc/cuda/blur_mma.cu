@@ -255,6 +255,276 @@ __global__ void __launch_bounds__(256) blur_mma_kernel(const MmaBlurArgs a, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same contraction on an 8-bit plane (one channel): shadow() only ever uses the alpha of its mask
+// (images.nim:760-776: spread leaves rgbx(0, 0, 0, a), blur keeps the channels apart, the final MaskBlend draw reads
+// mask.a), so its blur runs on the alpha plane — a quarter of the staging, MMA and epilogue work.
+// src / dst are uint8 planes of w x h.  With one byte per pixel the per-tile bookkeeping is what counts, so this
+// kernel differs from the RGBX one around the contraction:
+//   * the tile is fetched global -> registers in 16-byte pieces (two per thread, issued before the MMAs of the
+//     previous tile and converted after them), no raw copy in shared memory;
+//   * the horizontal tile starts at a0 - roundup16(radius) so that every piece is 16-byte aligned for any radius;
+//     the `shift` = roundup16(radius) - radius extra inputs on the left are folded into the Toeplitz fragments
+//     (A_q[m][k] = lut[16 q + k - m - shift]);
+//   * results leave through a shared-memory tile in image orientation and go out as 16-byte stores, one tile late
+//     (while the next tile is being converted), which keeps two barriers per tile.
+// ---------------------------------------------------------------------------------------------
+struct MmaBlurA8Args {
+  const uint8_t* src;
+  uint8_t* dst;
+  int w, h, radius;
+  int shift;     // extra inputs staged before a0 - radius (horizontal pass)
+  uint32_t oob;  // alpha of the out-of-bounds colour, replicated to 4 bytes
+  int pitch;     // plane row pitch in halfs
+};
+
+template <bool VERTICAL, int KT, bool HI>
+__global__ void __launch_bounds__(256) blur_mma_a8_kernel(const MmaBlurA8Args a, int tilesA, int numTiles) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int IN_A = kMmaOut - 16 + 16 * KT;
+  constexpr int ROWS = VERTICAL ? IN_A : kMmaLines, COLS = VERTICAL ? kMmaLines : IN_A;
+  constexpr int CH = COLS / 16;                     // 16-byte pieces per tile row
+  constexpr int NLD = (ROWS * CH + 255) / 256;      // pieces per thread
+  constexpr int OROWS = VERTICAL ? kMmaOut : kMmaLines, OCOLS = VERTICAL ? kMmaLines : kMmaOut;
+  constexpr int OPITCH = OCOLS + 16;                // bytes; keeps the fragment-order byte stores off each other's banks
+  constexpr int OCH = OCOLS / 16;
+  static_assert(OROWS * OCH == 256, "one 16-byte piece of the output tile per thread");
+  const int pitch = a.pitch;
+  __half* plane = reinterpret_cast<__half*>(smem_raw);
+  uint8_t* outb = smem_raw + (size_t)ROWS * pitch * sizeof(__half);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ntaps = 2 * a.radius + 1;
+  const bool vec4 = (a.w & 3) == 0 && (reinterpret_cast<uintptr_t>(a.src) & 3) == 0;
+  const bool vec16 = (a.w & 15) == 0 && (reinterpret_cast<uintptr_t>(a.src) & 15) == 0;
+  const bool st16 = (a.w & 15) == 0 && (reinterpret_cast<uintptr_t>(a.dst) & 15) == 0;
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t Alo[KT][4], Ahi[HI ? KT : 1][4];
+#pragma unroll
+  for (int q = 0; q < KT; q++) {
+#pragma unroll
+    for (int rIdx = 0; rIdx < 4; rIdx++) {
+      const int m = g + ((rIdx & 1) ? 8 : 0), k = 2 * t + ((rIdx & 2) ? 8 : 0);
+      const int k0 = tap_at(16 * q + k - m - a.shift, ntaps), k1 = tap_at(16 * q + k + 1 - m - a.shift, ntaps);
+      Alo[q][rIdx] = pack_h2((float)(k0 & 2047), (float)(k1 & 2047));
+      if (HI) Ahi[q][rIdx] = pack_h2((float)((k0 >> 11) << 11), (float)((k1 >> 11) << 11));
+    }
+  }
+  auto tile_origin = [&](int tile, int& a0, int& l0) {
+    const int tl = tile / tilesA, ta = tile - tl * tilesA;
+    a0 = ta * kMmaOut;
+    l0 = tl * kMmaLines;
+  };
+  uint4 v[NLD];
+  auto fetch = [&](int a0, int l0) {  // the tile's bytes -> registers
+    const int x0 = VERTICAL ? l0 : a0 - a.radius - a.shift, y0 = VERTICAL ? a0 - a.radius : l0;
+#pragma unroll
+    for (int u = 0; u < NLD; u++) {
+      const int c = tid + 256 * u;
+      const int row = c / CH, c16 = (c - row * CH) * 16;
+      const int y = y0 + row, x = x0 + c16;
+      v[u] = make_uint4(a.oob, a.oob, a.oob, a.oob);
+      if (c < ROWS * CH && y >= 0 && y < a.h && x + 16 > 0 && x < a.w) {
+        const uint8_t* p = a.src + (size_t)a.w * y + x;
+        if (vec16 && x >= 0 && x + 16 <= a.w) {
+          v[u] = *reinterpret_cast<const uint4*>(p);
+        } else {
+          uint32_t wd[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int xj = x + 4 * j;
+            wd[j] = a.oob;
+            if (vec4 && xj >= 0 && xj + 4 <= a.w) {
+              wd[j] = *reinterpret_cast<const uint32_t*>(p + 4 * j);
+            } else if (xj + 4 > 0 && xj < a.w) {
+#pragma unroll
+              for (int b = 0; b < 4; b++)
+                if (xj + b >= 0 && xj + b < a.w) wd[j] = (wd[j] & ~(0xFFu << (8 * b))) | ((uint32_t)p[4 * j + b] << (8 * b));
+            }
+          }
+          v[u] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        }
+      }
+    }
+  };
+  const uint32_t magic = 0x64006400u;
+  const __half2 magic_h = *reinterpret_cast<const __half2*>(&magic);
+  auto to_h2 = [&](uint32_t p, uint32_t sel) {
+    const uint32_t wv = __byte_perm(p, 0x64u, sel);
+    const __half2 hv = __hsub2(*reinterpret_cast<const __half2*>(&wv), magic_h);
+    return *reinterpret_cast<const uint32_t*>(&hv);
+  };
+  auto convert = [&]() {  // registers -> the fp16 plane
+#pragma unroll
+    for (int u = 0; u < NLD; u++) {
+      const int c = tid + 256 * u;
+      if (c < ROWS * CH) {
+        const int row = c / CH, c16 = (c - row * CH) * 16;
+        uint4* d = reinterpret_cast<uint4*>(plane + row * pitch + c16);
+        d[0] = make_uint4(to_h2(v[u].x, 0x4140), to_h2(v[u].x, 0x4342), to_h2(v[u].y, 0x4140), to_h2(v[u].y, 0x4342));
+        d[1] = make_uint4(to_h2(v[u].z, 0x4140), to_h2(v[u].z, 0x4342), to_h2(v[u].w, 0x4140), to_h2(v[u].w, 0x4342));
+      }
+    }
+  };
+  auto flush = [&](int a0, int l0) {  // output tile (shared) -> global, one 16-byte piece per thread
+    const int row = tid / OCH, c16 = (tid - row * OCH) * 16;
+    const int y = (VERTICAL ? a0 : l0) + row, x = (VERTICAL ? l0 : a0) + c16;
+    if (y < a.h && x < a.w) {
+      const uint4 q = *reinterpret_cast<const uint4*>(outb + row * OPITCH + c16);
+      uint8_t* p = a.dst + (size_t)a.w * y + x;
+      if (st16 && x + 16 <= a.w) {
+        *reinterpret_cast<uint4*>(p) = q;
+      } else {
+        const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+          if (x + j < a.w) p[j] = (uint8_t)(wd[j >> 2] >> (8 * (j & 3)));
+      }
+    }
+  };
+  const int nt = warp & 3, mg = warp >> 2;
+  int tile = blockIdx.x;
+  int a0 = 0, l0 = 0, a0p = 0, l0p = 0;
+  bool pending = false;
+  if (tile < numTiles) {
+    tile_origin(tile, a0, l0);
+    fetch(a0, l0);
+  }
+#pragma unroll 1
+  for (; tile < numTiles; tile += gridDim.x) {
+    __syncthreads();  // nobody reads the plane of the previous tile any more; its output tile is complete
+    convert();
+    if (pending) flush(a0p, l0p);
+    __syncthreads();  // plane ready; output tile free
+    a0p = a0;
+    l0p = l0;
+    pending = true;
+    const int a0c = a0, l0c = l0;
+    (void)l0c;
+    if (tile + (int)gridDim.x < numTiles) {
+      tile_origin(tile + gridDim.x, a0, l0);
+      fetch(a0, l0);
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
+#pragma unroll
+    for (int kt = 0; kt < 4 + KT - 1; kt++) {
+      const int kbase = (mg * 4 + kt) * 16;
+      uint32_t b0, b1;
+      if (VERTICAL) ldmatrix_x2<true>(b0, b1, plane + (kbase + (lane & 15)) * pitch + nt * 8);
+      else ldmatrix_x2<false>(b0, b1, plane + (nt * 8 + (lane & 7)) * pitch + kbase + ((lane & 8) ? 8 : 0));
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int q = kt - i;
+        if (q >= 0 && q < KT) {
+          mma_16816(acc[i], Alo[q], b0, b1);
+          if (HI) mma_16816(acc[i], Ahi[q], b0, b1);
+        }
+      }
+    }
+    (void)a0c;
+    // fragment slots 2hh, 2hh + 1 of m-tile i: outputs (m = g + 8 hh, n = 2t, 2t + 1) -> the output tile
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+      for (int hh = 0; hh < 2; hh++) {
+        const uint32_t t0 = __float_as_uint(__fmaf_rz(acc[i][2 * hh], 0.00390625f, 8388608.0f));
+        const uint32_t t1 = __float_as_uint(__fmaf_rz(acc[i][2 * hh + 1], 0.00390625f, 8388608.0f));
+        const uint32_t qq = div255x2(__byte_perm(t0, t1, 0x5410));  // bytes {q0, 0, q1, 0}
+        const int ao = (mg * 4 + i) * 16 + g + 8 * hh, lo = nt * 8 + 2 * t;  // position along the axis / line
+        if (VERTICAL) {
+          *reinterpret_cast<uint16_t*>(outb + ao * OPITCH + lo) = (uint16_t)__byte_perm(qq, 0u, 0x4420);
+        } else {
+          outb[lo * OPITCH + ao] = (uint8_t)qq;
+          outb[(lo + 1) * OPITCH + ao] = (uint8_t)(qq >> 16);
+        }
+      }
+    }
+  }
+  if (pending) {
+    __syncthreads();
+    flush(a0p, l0p);
+  }
+}
+
+template <bool VERTICAL, int KT, bool HI>
+static int launch_pass_a8(const MmaBlurA8Args& a, int tilesA, int tilesL, cudaStream_t st) {
+  constexpr int IN_A = kMmaOut - 16 + 16 * KT;
+  constexpr int ROWS = VERTICAL ? IN_A : kMmaLines;
+  constexpr int OROWS = VERTICAL ? kMmaOut : kMmaLines, OCOLS = VERTICAL ? kMmaLines : kMmaOut;
+  const size_t smem = (size_t)ROWS * a.pitch * sizeof(__half) + (size_t)OROWS * (OCOLS + 16);
+  static int perSm = 0;
+  if (perSm == 0) {
+    if (smem > 48 * 1024)
+      PX_CUDA(cudaFuncSetAttribute(blur_mma_a8_kernel<VERTICAL, KT, HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, blur_mma_a8_kernel<VERTICAL, KT, HI>, 256, smem));
+    perSm = std::max(1, perSm);
+  }
+  const int numTiles = tilesA * tilesL;
+  if (numTiles <= 0) return 0;
+  blur_mma_a8_kernel<VERTICAL, KT, HI><<<std::min(numTiles, rt().num_sms * perSm), 256, smem, st>>>(a, tilesA, numTiles);
+  PX_LAUNCHED();
+  return 0;
+}
+
+template <bool VERTICAL, bool HI>
+static int dispatch_a8(int KT, const MmaBlurA8Args& a, int tilesA, int tilesL, cudaStream_t st) {
+  switch (KT) {
+    case 2: return launch_pass_a8<VERTICAL, 2, HI>(a, tilesA, tilesL, st);
+    case 3: return launch_pass_a8<VERTICAL, 3, HI>(a, tilesA, tilesL, st);
+    case 4: return launch_pass_a8<VERTICAL, 4, HI>(a, tilesA, tilesL, st);
+    case 5: return launch_pass_a8<VERTICAL, 5, HI>(a, tilesA, tilesL, st);
+    case 6: return launch_pass_a8<VERTICAL, 6, HI>(a, tilesA, tilesL, st);
+    case 7: return launch_pass_a8<VERTICAL, 7, HI>(a, tilesA, tilesL, st);
+    case 8: return launch_pass_a8<VERTICAL, 8, HI>(a, tilesA, tilesL, st);
+    case 9: return launch_pass_a8<VERTICAL, 9, HI>(a, tilesA, tilesL, st);
+    default: return -1;
+  }
+}
+
+static int upload_mma_lut(const uint16_t* lut_host, int ntaps);
+
+// Tensor-core blur of an 8-bit plane in place (through `tmp`, a second w x h plane).  -1: radius / LUT outside the
+// exact domain (the caller falls back to the RGBX path).
+int blur_mma_a8(uint8_t* plane, uint8_t* tmp, int w, int h, const uint16_t* lut_host, int radius, uint32_t oobAlpha) {
+  const int ntaps = 2 * radius + 1;
+  if (radius < 1 || ntaps > kMaxTaps) return -1;
+  unsigned long long sum = 0;
+  bool hasHi = false;
+  for (int i = 0; i < ntaps; i++) {
+    sum += lut_host[i];
+    if (lut_host[i] >= 2048) hasHi = true;
+  }
+  if (sum * 255ull >= (1ull << 24)) return -1;
+  if (int rc = upload_mma_lut(lut_host, ntaps)) return rc;
+  Runtime& r = rt();
+  MmaBlurA8Args a;
+  a.w = w; a.h = h; a.radius = radius;
+  a.oob = (oobAlpha & 255u) * 0x01010101u;
+  {  // X pass: plane -> tmp
+    a.src = plane; a.dst = tmp;
+    a.shift = ((radius + 15) & ~15) - radius;
+    const int KT = (2 * radius + a.shift + 16 + 15) / 16;
+    const int IN_A = kMmaOut - 16 + 16 * KT;
+    a.pitch = IN_A + ((8 - IN_A) % 64 + 64) % 64;  // = 8 mod 64 halfs: ldmatrix rows 16 bytes apart in bank space
+    ProfScope ps(kProfBlurX);
+    const int tA = (w + kMmaOut - 1) / kMmaOut, tL = (h + kMmaLines - 1) / kMmaLines;
+    const int rc = hasHi ? dispatch_a8<false, true>(KT, a, tA, tL, r.stream) : dispatch_a8<false, false>(KT, a, tA, tL, r.stream);
+    if (rc) return rc;
+  }
+  {  // Y pass: tmp -> plane
+    a.src = tmp; a.dst = plane;
+    a.shift = 0;
+    const int KT = (2 * radius + 16 + 15) / 16;
+    a.pitch = kMmaLines + 8;
+    ProfScope ps(kProfBlurY);
+    const int tA = (h + kMmaOut - 1) / kMmaOut, tL = (w + kMmaLines - 1) / kMmaLines;
+    const int rc = hasHi ? dispatch_a8<true, true>(KT, a, tA, tL, r.stream) : dispatch_a8<true, false>(KT, a, tA, tL, r.stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 template <bool VERTICAL, int KT, bool HI>
 static int launch_pass(const MmaBlurArgs& a, int tilesA, int tilesL, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
@@ -299,6 +569,16 @@ static int launch_both(MmaBlurArgs a, Image* im, void* tmp, int y0, int y1) {
   return 0;
 }
 
+static int upload_mma_lut(const uint16_t* lut_host, int ntaps) {
+  Runtime& r = rt();
+  void* pin;
+  if (int rc = staging_acquire(sizeof(uint16_t) * (kMaxTaps + 3), &pin)) return rc;
+  memset(pin, 0, sizeof(uint16_t) * (kMaxTaps + 3));
+  memcpy(pin, lut_host, (size_t)ntaps * 2);
+  PX_CUDA(cudaMemcpyToSymbolAsync(c_mma_lut, pin, sizeof(uint16_t) * (kMaxTaps + 3), 0, cudaMemcpyHostToDevice, r.stream));
+  return staging_release();
+}
+
 // Tensor-core blur of rows [y0, y1) of `im` through the scratch plane `tmp`.  Returns -1 when the radius / LUT is
 // outside what this path holds exactly (the caller then takes the CUDA-core kernels).
 int blur_mma(Image* im, void* tmp, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1) {
@@ -311,15 +591,7 @@ int blur_mma(Image* im, void* tmp, const uint16_t* lut_host, int radius, uint32_
     if (lut_host[i] >= 2048) hasHi = 1;
   }
   if (sum * 255ull >= (1ull << 24)) return -1;  // partial sums must stay exact in fp32
-  Runtime& r = rt();
-  {
-    void* pin;
-    if (int rc = staging_acquire(sizeof(uint16_t) * (kMaxTaps + 3), &pin)) return rc;
-    memset(pin, 0, sizeof(uint16_t) * (kMaxTaps + 3));
-    memcpy(pin, lut_host, (size_t)ntaps * 2);
-    PX_CUDA(cudaMemcpyToSymbolAsync(c_mma_lut, pin, sizeof(uint16_t) * (kMaxTaps + 3), 0, cudaMemcpyHostToDevice, r.stream));
-    if (int rc = staging_release()) return rc;
-  }
+  if (int rc = upload_mma_lut(lut_host, ntaps)) return rc;
   MmaBlurArgs a;
   a.w = im->w; a.h = im->h; a.radius = radius; a.oob = oob; a.hasHi = hasHi;
   a.y0 = y0; a.y1 = y1;

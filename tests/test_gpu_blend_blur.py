@@ -222,3 +222,19 @@ def test_shadow_wide(offset, spread_):
     a = gb.shadow(img, offset[0], offset[1], spread_, lut, 5, pack(10, 20, 30, 200))
     b = ob.shadow(img, offset[0], offset[1], spread_, lut, 5, pack(10, 20, 30, 200))
     assert diff_report(a, b)[0] == 0
+
+
+@pytest.mark.parametrize("shape", [(37, 130), (131, 77), (5, 4), (64, 256), (300, 515)])
+@pytest.mark.parametrize("radius,spread_", [(1, 0), (3, 1), (4, -2), (8, 0), (29, 3), (32, 0), (64, 2), (70, 1), (0, 2), (0, 0)])
+def test_shadow_alpha_plane(shape, radius, spread_):
+    """shadow() with an integral offset runs offset copy, spread, blur and composite on the mask's alpha plane
+    (one-channel tensor-core blur): every tile shape of that kernel — widths off the 4-byte grid, radii on and off
+    the cp.async alignment, LUTs with and without high tap parts, no spread, no blur — and the RGBX fallback above
+    radius 64."""
+    gb, ob = _backends()
+    img = synth.random_premultiplied(shape[0], shape[1], 11 + radius)
+    img[: shape[0] // 3] = 0
+    lut = host.gaussianKernel(radius)
+    a = gb.shadow(img, 3, -2, spread_, lut, radius, pack(90, 20, 130, 220))
+    b = ob.shadow(img, 3, -2, spread_, lut, radius, pack(90, 20, 130, 220))
+    assert diff_report(a, b)[0] == 0
