@@ -743,7 +743,8 @@ __global__ void __launch_bounds__(256) shadow_composite_a8(const uint8_t* __rest
   }
 }
 
-int blur_mma_a8(uint8_t* plane, uint8_t* tmp, int w, int h, const uint16_t* lut_host, int radius, uint32_t oobAlpha);
+int blur_mma_a8(uint8_t* plane, uint8_t* tmp, int w, int h, const uint16_t* lut_host, int radius, uint32_t oobAlpha,
+                px_t* comp, px_t color);
 
 // shadow with an integral offset as a one-channel pipeline: only the alpha of the mask reaches the result
 // (spread writes rgbx(0, 0, 0, a), blur treats channels independently, MaskBlend reads mask.a), so the
@@ -773,9 +774,10 @@ static int shadow_a8(const Image* s, Image* d, int ox, int oy, int spread, const
     alpha_shifted<<<grid, 256, 0, r.stream>>>((const px_t*)s->data, ox, oy, plane, w, h);
     PX_LAUNCHED();
   }
-  if (radius > 0) {
-    const int rc = blur_mma_a8(plane, tmp, w, h, lut, radius, 0u);
+  if (radius > 0) {  // the composite rides on the blur's last pass
+    const int rc = blur_mma_a8(plane, tmp, w, h, lut, radius, 0u, (px_t*)d->data, rgbx);
     if (rc != 0) return rc > 0 ? rc : fail_pixie("shadow: alpha blur rejected a LUT it had accepted");
+    return 0;
   }
   const size_t n = (size_t)w * h;
   const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)r.num_sms * 16);

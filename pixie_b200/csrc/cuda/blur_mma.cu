@@ -276,9 +276,11 @@ struct MmaBlurA8Args {
   int shift;     // extra inputs staged before a0 - radius (horizontal pass)
   uint32_t oob;  // alpha of the out-of-bounds colour, replicated to 4 bytes
   int pitch;     // plane row pitch in halfs
+  px_t* comp;    // COMP: shadow's composite fused into the last pass: comp[i] = color MaskBlend alpha (images.nim:774-776)
+  px_t color;
 };
 
-template <bool VERTICAL, int KT, bool HI>
+template <bool VERTICAL, int KT, bool HI, bool COMP>
 __global__ void __launch_bounds__(256) blur_mma_a8_kernel(const MmaBlurA8Args a, int tilesA, int numTiles) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int IN_A = kMmaOut - 16 + 16 * KT;
@@ -292,7 +294,9 @@ __global__ void __launch_bounds__(256) blur_mma_a8_kernel(const MmaBlurA8Args a,
   const int pitch = a.pitch;
   __half* plane = reinterpret_cast<__half*>(smem_raw);
   uint8_t* outb = smem_raw + (size_t)ROWS * pitch * sizeof(__half);
+  px_t* comp_lut = reinterpret_cast<px_t*>(outb + OROWS * OPITCH);  // COMP: color * alpha / 255 for every alpha
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (COMP) comp_lut[tid] = mul_div255(a.color, (uint32_t)tid);  // read after the loop's barriers
   const int ntaps = 2 * a.radius + 1;
   const bool vec4 = (a.w & 3) == 0 && (reinterpret_cast<uintptr_t>(a.src) & 3) == 0;
   const bool vec16 = (a.w & 15) == 0 && (reinterpret_cast<uintptr_t>(a.src) & 15) == 0;
@@ -370,6 +374,21 @@ __global__ void __launch_bounds__(256) blur_mma_a8_kernel(const MmaBlurA8Args a,
     const int y = (VERTICAL ? a0 : l0) + row, x = (VERTICAL ? l0 : a0) + c16;
     if (y < a.h && x < a.w) {
       const uint4 q = *reinterpret_cast<const uint4*>(outb + row * OPITCH + c16);
+      if (COMP) {
+        px_t* cp = a.comp + (size_t)a.w * y + x;
+        const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+        if (st16 && x + 16 <= a.w && (reinterpret_cast<uintptr_t>(a.comp) & 15) == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            reinterpret_cast<uint4*>(cp)[j] = make_uint4(comp_lut[wd[j] & 255u], comp_lut[(wd[j] >> 8) & 255u],
+                                                         comp_lut[(wd[j] >> 16) & 255u], comp_lut[wd[j] >> 24]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; j++)
+            if (x + j < a.w) cp[j] = comp_lut[(wd[j >> 2] >> (8 * (j & 3))) & 255u];
+        }
+        return;
+      }
       uint8_t* p = a.dst + (size_t)a.w * y + x;
       if (st16 && x + 16 <= a.w) {
         *reinterpret_cast<uint4*>(p) = q;
@@ -447,37 +466,37 @@ __global__ void __launch_bounds__(256) blur_mma_a8_kernel(const MmaBlurA8Args a,
   }
 }
 
-template <bool VERTICAL, int KT, bool HI>
+template <bool VERTICAL, int KT, bool HI, bool COMP>
 static int launch_pass_a8(const MmaBlurA8Args& a, int tilesA, int tilesL, cudaStream_t st) {
   constexpr int IN_A = kMmaOut - 16 + 16 * KT;
   constexpr int ROWS = VERTICAL ? IN_A : kMmaLines;
   constexpr int OROWS = VERTICAL ? kMmaOut : kMmaLines, OCOLS = VERTICAL ? kMmaLines : kMmaOut;
-  const size_t smem = (size_t)ROWS * a.pitch * sizeof(__half) + (size_t)OROWS * (OCOLS + 16);
+  const size_t smem = (size_t)ROWS * a.pitch * sizeof(__half) + (size_t)OROWS * (OCOLS + 16) + (COMP ? 256 * sizeof(px_t) : 0);
   static int perSm = 0;
   if (perSm == 0) {
     if (smem > 48 * 1024)
-      PX_CUDA(cudaFuncSetAttribute(blur_mma_a8_kernel<VERTICAL, KT, HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, blur_mma_a8_kernel<VERTICAL, KT, HI>, 256, smem));
+      PX_CUDA(cudaFuncSetAttribute(blur_mma_a8_kernel<VERTICAL, KT, HI, COMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, blur_mma_a8_kernel<VERTICAL, KT, HI, COMP>, 256, smem));
     perSm = std::max(1, perSm);
   }
   const int numTiles = tilesA * tilesL;
   if (numTiles <= 0) return 0;
-  blur_mma_a8_kernel<VERTICAL, KT, HI><<<std::min(numTiles, rt().num_sms * perSm), 256, smem, st>>>(a, tilesA, numTiles);
+  blur_mma_a8_kernel<VERTICAL, KT, HI, COMP><<<std::min(numTiles, rt().num_sms * perSm), 256, smem, st>>>(a, tilesA, numTiles);
   PX_LAUNCHED();
   return 0;
 }
 
-template <bool VERTICAL, bool HI>
+template <bool VERTICAL, bool HI, bool COMP>
 static int dispatch_a8(int KT, const MmaBlurA8Args& a, int tilesA, int tilesL, cudaStream_t st) {
   switch (KT) {
-    case 2: return launch_pass_a8<VERTICAL, 2, HI>(a, tilesA, tilesL, st);
-    case 3: return launch_pass_a8<VERTICAL, 3, HI>(a, tilesA, tilesL, st);
-    case 4: return launch_pass_a8<VERTICAL, 4, HI>(a, tilesA, tilesL, st);
-    case 5: return launch_pass_a8<VERTICAL, 5, HI>(a, tilesA, tilesL, st);
-    case 6: return launch_pass_a8<VERTICAL, 6, HI>(a, tilesA, tilesL, st);
-    case 7: return launch_pass_a8<VERTICAL, 7, HI>(a, tilesA, tilesL, st);
-    case 8: return launch_pass_a8<VERTICAL, 8, HI>(a, tilesA, tilesL, st);
-    case 9: return launch_pass_a8<VERTICAL, 9, HI>(a, tilesA, tilesL, st);
+    case 2: return launch_pass_a8<VERTICAL, 2, HI, COMP>(a, tilesA, tilesL, st);
+    case 3: return launch_pass_a8<VERTICAL, 3, HI, COMP>(a, tilesA, tilesL, st);
+    case 4: return launch_pass_a8<VERTICAL, 4, HI, COMP>(a, tilesA, tilesL, st);
+    case 5: return launch_pass_a8<VERTICAL, 5, HI, COMP>(a, tilesA, tilesL, st);
+    case 6: return launch_pass_a8<VERTICAL, 6, HI, COMP>(a, tilesA, tilesL, st);
+    case 7: return launch_pass_a8<VERTICAL, 7, HI, COMP>(a, tilesA, tilesL, st);
+    case 8: return launch_pass_a8<VERTICAL, 8, HI, COMP>(a, tilesA, tilesL, st);
+    case 9: return launch_pass_a8<VERTICAL, 9, HI, COMP>(a, tilesA, tilesL, st);
     default: return -1;
   }
 }
@@ -486,7 +505,9 @@ static int upload_mma_lut(const uint16_t* lut_host, int ntaps);
 
 // Tensor-core blur of an 8-bit plane in place (through `tmp`, a second w x h plane).  -1: radius / LUT outside the
 // exact domain (the caller falls back to the RGBX path).
-int blur_mma_a8(uint8_t* plane, uint8_t* tmp, int w, int h, const uint16_t* lut_host, int radius, uint32_t oobAlpha) {
+// comp != nullptr: the last pass writes comp[i] = color MaskBlend blurred alpha instead of the plane.
+int blur_mma_a8(uint8_t* plane, uint8_t* tmp, int w, int h, const uint16_t* lut_host, int radius, uint32_t oobAlpha,
+                px_t* comp, px_t color) {
   const int ntaps = 2 * radius + 1;
   if (radius < 1 || ntaps > kMaxTaps) return -1;
   unsigned long long sum = 0;
@@ -501,6 +522,8 @@ int blur_mma_a8(uint8_t* plane, uint8_t* tmp, int w, int h, const uint16_t* lut_
   MmaBlurA8Args a;
   a.w = w; a.h = h; a.radius = radius;
   a.oob = (oobAlpha & 255u) * 0x01010101u;
+  a.comp = comp;
+  a.color = color;
   {  // X pass: plane -> tmp
     a.src = plane; a.dst = tmp;
     a.shift = ((radius + 15) & ~15) - radius;
@@ -509,7 +532,8 @@ int blur_mma_a8(uint8_t* plane, uint8_t* tmp, int w, int h, const uint16_t* lut_
     a.pitch = IN_A + ((8 - IN_A) % 64 + 64) % 64;  // = 8 mod 64 halfs: ldmatrix rows 16 bytes apart in bank space
     ProfScope ps(kProfBlurX);
     const int tA = (w + kMmaOut - 1) / kMmaOut, tL = (h + kMmaLines - 1) / kMmaLines;
-    const int rc = hasHi ? dispatch_a8<false, true>(KT, a, tA, tL, r.stream) : dispatch_a8<false, false>(KT, a, tA, tL, r.stream);
+    const int rc = hasHi ? dispatch_a8<false, true, false>(KT, a, tA, tL, r.stream)
+                         : dispatch_a8<false, false, false>(KT, a, tA, tL, r.stream);
     if (rc) return rc;
   }
   {  // Y pass: tmp -> plane
@@ -519,7 +543,10 @@ int blur_mma_a8(uint8_t* plane, uint8_t* tmp, int w, int h, const uint16_t* lut_
     a.pitch = kMmaLines + 8;
     ProfScope ps(kProfBlurY);
     const int tA = (h + kMmaOut - 1) / kMmaOut, tL = (w + kMmaLines - 1) / kMmaLines;
-    const int rc = hasHi ? dispatch_a8<true, true>(KT, a, tA, tL, r.stream) : dispatch_a8<true, false>(KT, a, tA, tL, r.stream);
+    const int rc = comp ? (hasHi ? dispatch_a8<true, true, true>(KT, a, tA, tL, r.stream)
+                                 : dispatch_a8<true, false, true>(KT, a, tA, tL, r.stream))
+                        : (hasHi ? dispatch_a8<true, true, false>(KT, a, tA, tL, r.stream)
+                                 : dispatch_a8<true, false, false>(KT, a, tA, tL, r.stream));
     if (rc) return rc;
   }
   return 0;
