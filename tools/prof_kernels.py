@@ -25,6 +25,13 @@ if which in ("blur", "all"):
     for _ in range(3):
         dev.blur(img, host.gaussianKernel(32), 32, 0)
     dev.sync()
+if which in ("shadow", "all"):
+    n = int(os.environ.get("BLUR_N", "16384"))
+    img = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 4), (n // 512, 1, 1)))
+    out = dev.DeviceImage(n, n)
+    for _ in range(3):
+        dev.shadow(img, out, 8, 8, 4, host.gaussianKernel(32), 32, 0xC8000000)
+    dev.sync()
 if which in ("tiger", "all"):
     sys.path.insert(0, ROOT)
     from bench import tiger_arrays

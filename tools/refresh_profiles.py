@@ -23,7 +23,7 @@ for src, dst in (("bench_cur.json", f"{tag}_bench_n1.json"), ("bench_cur_ref.jso
         with open(os.path.join(P, dst), "w") as f:
             f.write(last_line(p) + "\n")
 shutil.copyfile(os.path.join(G, "launches_cur.csv"), os.path.join(P, f"{tag}_launches_bench_tiger.csv"))
-for rep, name in (("prof_tiger_cur", "tiger"), ("prof_blur_cur", "blur_mma"), ("prof_blend_cur", "blend"), ("prof_draw_cur", "draw")):
+for rep, name in (("prof_tiger_cur", "tiger"), ("prof_blur_cur", "blur_mma"), ("prof_shadow_cur", "shadow"), ("prof_blend_cur", "blend"), ("prof_draw_cur", "draw")):
     subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "summarize_ncu.py"), os.path.join(G, rep + ".ncu-rep"),
                            os.path.join(P, f"{tag}_{name}")])
 d = json.loads(last_line(os.path.join(G, "bench_cur.json")))
