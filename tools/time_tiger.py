@@ -1,0 +1,29 @@
+"""Device time of one tiger 4096^2 step (clear + K1..K3) and of its raster kernel, for A/B runs under env switches
+(PIXIE_CUDA_TILE_SMEM, PIXIE_CUDA_TILEW)."""
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import tiger_arrays  # noqa: E402
+from pixie_b200 import device as dev  # noqa: E402
+
+size = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+dev.init(0)
+dev.set_profiling(True)
+arrays = tiger_arrays(size)
+img = dev.DeviceImage(size, size)
+cl = dev.CmdList(size, size, 1, arrays)
+steps, rast = [], []
+for it in range(25):
+    dev.timer_begin()
+    img.fill(0)
+    cl.run(img)
+    t = dev.timer_end()
+    if it >= 5:
+        steps.append(t)
+        rast.append(dev.profile_read(dev.PROF_RASTER))
+print("tiger %d^2  TILE_SMEM=%s TILEW=%s: step %.4f ms (min %.4f)  raster %.4f ms" % (
+    size, os.environ.get("PIXIE_CUDA_TILE_SMEM", "-"), os.environ.get("PIXIE_CUDA_TILEW", "-"),
+    statistics.median(steps), min(steps), statistics.median(rast)))
