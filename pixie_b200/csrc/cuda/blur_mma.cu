@@ -37,6 +37,8 @@ struct MmaBlurArgs {
   int hasHi;     // some tap >= 2048
 };
 
+// 1 / 65280 rounded to nearest float: floor(a * this) == a div 256 div 255 for all integers 0 <= a < 2^24
+#define kInv65280 __uint_as_float(0x37808081u)
 constexpr int kMmaOut = 128;   // outputs per CTA along the blur axis
 constexpr int kMmaLines = 32;  // lines per CTA
 constexpr int kMaxTaps = 2 * 64 + 1;
@@ -198,16 +200,18 @@ __global__ void __launch_bounds__(256) blur_mma_kernel(const MmaBlurArgs a, int 
           }
         }
       }
-      // `div 256 div 255` (images.nim:332-338) without leaving the FMA / ALU pipes: acc * 2^-8 + 2^23 truncated
-      // (FFMA.RZ) has floor(acc / 256) (< 65536) in its low 16 bits; two of them per register go through the
-      // packed div255; the two result bytes are merged with the other channel of the pair by one PRMT.
+      // `div 256 div 255` (images.nim:332-338) = floor(acc / 65280) in ONE instruction: with kInv65280 = 0x37808081
+      // (1 / 65280 rounded to nearest, which lies above it), floor(a * kInv65280) == a div 65280 for every integer
+      // a < 2^24 (checked exhaustively; tests/test_chain_closed_form.py repeats the check), and FFMA.RZ computes
+      // a * kInv65280 + 2^23 exactly before truncating at ulp 1, so the quotient sits in the low bits of the result.
+      // The two result bytes are merged with the other channel of the pair by one PRMT.
 #pragma unroll
       for (int i = 0; i < 4; i++) {
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) {
-          const uint32_t t0 = __float_as_uint(__fmaf_rz(acc[i][2 * hh], 0.00390625f, 8388608.0f));
-          const uint32_t t1 = __float_as_uint(__fmaf_rz(acc[i][2 * hh + 1], 0.00390625f, 8388608.0f));
-          const uint32_t qq = div255x2(__byte_perm(t0, t1, 0x5410));  // bytes {q0, 0, q1, 0}
+          const uint32_t t0 = __float_as_uint(__fmaf_rz(acc[i][2 * hh], kInv65280, 8388608.0f));
+          const uint32_t t1 = __float_as_uint(__fmaf_rz(acc[i][2 * hh + 1], kInv65280, 8388608.0f));
+          const uint32_t qq = __byte_perm(t0, t1, 0x5410);  // bytes {q0, q0 >> 8, q1, q1 >> 8}
           if (c == 0) rg[i][hh] = qq;
           else if (c == 1) rg[i][hh] = __byte_perm(rg[i][hh], qq, 0x6240);  // {r0, g0, r1, g1}
           else if (c == 2) ba[i][hh] = qq;
@@ -447,9 +451,9 @@ __global__ void __launch_bounds__(256) blur_mma_a8_kernel(const MmaBlurA8Args a,
     for (int i = 0; i < 4; i++) {
 #pragma unroll
       for (int hh = 0; hh < 2; hh++) {
-        const uint32_t t0 = __float_as_uint(__fmaf_rz(acc[i][2 * hh], 0.00390625f, 8388608.0f));
-        const uint32_t t1 = __float_as_uint(__fmaf_rz(acc[i][2 * hh + 1], 0.00390625f, 8388608.0f));
-        const uint32_t qq = div255x2(__byte_perm(t0, t1, 0x5410));  // bytes {q0, 0, q1, 0}
+        const uint32_t t0 = __float_as_uint(__fmaf_rz(acc[i][2 * hh], kInv65280, 8388608.0f));
+        const uint32_t t1 = __float_as_uint(__fmaf_rz(acc[i][2 * hh + 1], kInv65280, 8388608.0f));
+        const uint32_t qq = __byte_perm(t0, t1, 0x5410);  // bytes {q0, q0 >> 8, q1, q1 >> 8}
         const int ao = (mg * 4 + i) * 16 + g + 8 * hh, lo = nt * 8 + 2 * t;  // position along the axis / line
         if (VERTICAL) {
           *reinterpret_cast<uint16_t*>(outb + ao * OPITCH + lo) = (uint16_t)__byte_perm(qq, 0u, 0x4420);

@@ -110,3 +110,13 @@ def test_closed_form_equals_sequential_accumulation():
         a, b = closed_form(segs, n), sequential(v0, d, n)
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (trial, kind, v0, d, n)
     assert worst <= 124  # the kernel's table holds 128 segments; longer chains fall back to the sequential form
+
+
+def test_single_fma_div_65280_is_exact():
+    """blur_mma.cu quantises an accumulator with one FFMA.RZ: floor(a * float(0x37808081)) must equal
+    a div 256 div 255 (images.nim:332-338) for every integer a < 2^24.  The product is formed exactly by the FMA, so
+    the check is integer arithmetic on the float's mantissa: 0x808081 * 2^-39."""
+    a = np.arange(0, 1 << 24, dtype=np.uint64)
+    q = (a * np.uint64(0x808081)) >> np.uint64(39)
+    assert np.array_equal(q, (a // np.uint64(256)) // np.uint64(255))
+    assert np.array_equal(q, a // np.uint64(65280))
