@@ -37,8 +37,10 @@ struct MmaBlurArgs {
   int hasHi;     // some tap >= 2048
 };
 
-// 1 / 65280 rounded to nearest float: floor(a * this) == a div 256 div 255 for all integers 0 <= a < 2^24
+// float(1 / 65280): floor(a * kInv65280) == a div 256 div 255 for all integers 0 <= a < 2^24.  kInv65280s is the
+// same times 2^24, for accumulators that hold a * 2^-24 (pixel bytes entering the contraction as fp16 subnormals).
 #define kInv65280 __uint_as_float(0x37808081u)
+#define kInv65280s __uint_as_float(0x43808081u)
 constexpr int kMmaOut = 128;   // outputs per CTA along the blur axis
 constexpr int kMmaLines = 32;  // lines per CTA
 constexpr int kMaxTaps = 2 * 64 + 1;
@@ -78,7 +80,7 @@ PXD void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory")
 // Persistent CTAs: the Toeplitz fragments are built once; per tile the raw RGBX bytes of the NEXT tile are
 // fetched with cp.async while the tensor cores work on the current one.
 template <bool VERTICAL, int KT, bool HI>
-__global__ void __launch_bounds__(256) blur_mma_kernel(const MmaBlurArgs a, int tilesA, int numTiles) {
+__global__ void __launch_bounds__(256, 2) blur_mma_kernel(const MmaBlurArgs a, int tilesA, int numTiles) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int IN_A = kMmaOut - 16 + 16 * KT;  // inputs along the blur axis
   constexpr int ROWS = VERTICAL ? IN_A : kMmaLines, COLS = VERTICAL ? kMmaLines : IN_A;  // tile shape in pixels
@@ -112,9 +114,7 @@ __global__ void __launch_bounds__(256) blur_mma_kernel(const MmaBlurArgs a, int 
     l0 = tl * kMmaLines + (VERTICAL ? 0 : a.sy0);  // first line
   };
   // raw tile <- global (cp.async), out-of-image pixels <- the out-of-bounds colour
-  auto prefetch = [&](int tile) {
-    int a0, l0;
-    tile_origin(tile, a0, l0);
+  auto prefetch = [&](int a0, int l0) {
     const int x0 = VERTICAL ? l0 : a0 - a.radius, y0 = VERTICAL ? a0 - a.radius : l0;
     const int xEnd = VERTICAL ? l_end : a_len, yEnd = VERTICAL ? a_len : l_end;
     constexpr int G = COLS / 4;  // groups of 4 pixels per tile row
@@ -135,12 +135,14 @@ __global__ void __launch_bounds__(256) blur_mma_kernel(const MmaBlurArgs a, int 
     }
   };
 
-  const uint32_t magic = 0x64006400u;  // half2(1024, 1024): 0x6400 | byte is the half 1024 + byte
-  const __half2 magic_h = *reinterpret_cast<const __half2*>(&magic);
   const int nt = warp & 3, mg = warp >> 2;
 
   int tile = blockIdx.x;
-  if (tile < numTiles) prefetch(tile);
+  int a0n = 0, l0n = 0;  // origin of the tile being fetched: one division per tile
+  if (tile < numTiles) {
+    tile_origin(tile, a0n, l0n);
+    prefetch(a0n, l0n);
+  }
 #pragma unroll 1
   for (; tile < numTiles; tile += gridDim.x) {
     cp_async_wait_all();
@@ -152,26 +154,26 @@ __global__ void __launch_bounds__(256) blur_mma_kernel(const MmaBlurArgs a, int 
         const uint4 p = *reinterpret_cast<const uint4*>(raw + row * COLS + c4);
         const uint32_t rg01 = __byte_perm(p.x, p.y, 0x5140), ba01 = __byte_perm(p.x, p.y, 0x7362);
         const uint32_t rg23 = __byte_perm(p.z, p.w, 0x5140), ba23 = __byte_perm(p.z, p.w, 0x7362);
+        // a byte b next to a zero byte is the fp16 SUBNORMAL b * 2^-24: exact, no int -> float conversion at all; the
+        // whole contraction is scaled by 2^-24 (exact: every partial sum is a multiple of 2^-24 below 1) and the
+        // epilogue's multiplier takes the scale back
         uint32_t w[8];
-        w[0] = __byte_perm(rg01, 0x64u, 0x4140); w[1] = __byte_perm(rg23, 0x64u, 0x4140);  // r0 r1 | r2 r3
-        w[2] = __byte_perm(rg01, 0x64u, 0x4342); w[3] = __byte_perm(rg23, 0x64u, 0x4342);  // g
-        w[4] = __byte_perm(ba01, 0x64u, 0x4140); w[5] = __byte_perm(ba23, 0x64u, 0x4140);  // b
-        w[6] = __byte_perm(ba01, 0x64u, 0x4342); w[7] = __byte_perm(ba23, 0x64u, 0x4342);  // a
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const __half2 hv = __hsub2(*reinterpret_cast<const __half2*>(&w[k]), magic_h);
-          w[k] = *reinterpret_cast<const uint32_t*>(&hv);
-        }
+        w[0] = __byte_perm(rg01, 0u, 0x4140); w[1] = __byte_perm(rg23, 0u, 0x4140);  // r0 r1 | r2 r3
+        w[2] = __byte_perm(rg01, 0u, 0x4342); w[3] = __byte_perm(rg23, 0u, 0x4342);  // g
+        w[4] = __byte_perm(ba01, 0u, 0x4140); w[5] = __byte_perm(ba23, 0u, 0x4140);  // b
+        w[6] = __byte_perm(ba01, 0u, 0x4342); w[7] = __byte_perm(ba23, 0u, 0x4342);  // a
         __half* d = planes + row * pitch + c4;
 #pragma unroll
         for (int c = 0; c < 4; c++) *reinterpret_cast<uint2*>(d + c * planeHalfs) = make_uint2(w[2 * c], w[2 * c + 1]);
       }
     }
     __syncthreads();  // planes ready; the raw buffer is free again
-    if (tile + (int)gridDim.x < numTiles) prefetch(tile + gridDim.x);
+    const int a0 = a0n, l0 = l0n;
+    if (tile + (int)gridDim.x < numTiles) {
+      tile_origin(tile + gridDim.x, a0n, l0n);
+      prefetch(a0n, l0n);
+    }
 
-    int a0, l0;
-    tile_origin(tile, a0, l0);
     // ---- contraction: warp = 8 lines (nt) x 4 m-tiles (mg), all four channels
     // Quantised outputs are kept two per register while the channels come in: rg[i][h] / ba[i][h] hold the bytes
     // {c0 of slot 2h, c1 of slot 2h, c0 of slot 2h+1, c1 of slot 2h+1} of m-tile i.
@@ -209,8 +211,8 @@ __global__ void __launch_bounds__(256) blur_mma_kernel(const MmaBlurArgs a, int 
       for (int i = 0; i < 4; i++) {
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) {
-          const uint32_t t0 = __float_as_uint(__fmaf_rz(acc[i][2 * hh], kInv65280, 8388608.0f));
-          const uint32_t t1 = __float_as_uint(__fmaf_rz(acc[i][2 * hh + 1], kInv65280, 8388608.0f));
+          const uint32_t t0 = __float_as_uint(__fmaf_rz(acc[i][2 * hh], kInv65280s, 8388608.0f));
+          const uint32_t t1 = __float_as_uint(__fmaf_rz(acc[i][2 * hh + 1], kInv65280s, 8388608.0f));
           const uint32_t qq = __byte_perm(t0, t1, 0x5410);  // bytes {q0, q0 >> 8, q1, q1 >> 8}
           if (c == 0) rg[i][hh] = qq;
           else if (c == 1) rg[i][hh] = __byte_perm(rg[i][hh], qq, 0x6240);  // {r0, g0, r1, g1}
@@ -354,6 +356,8 @@ __global__ void __launch_bounds__(256) blur_mma_a8_kernel(const MmaBlurA8Args a,
       }
     }
   };
+  // 0x6400 | b is the half 1024 + b.  (The subnormal encoding of the RGBX kernel measured slower here: with one
+  // channel the MMAs are a larger share of the tile and they take longer on subnormal operands.)
   const uint32_t magic = 0x64006400u;
   const __half2 magic_h = *reinterpret_cast<const __half2*>(&magic);
   auto to_h2 = [&](uint32_t p, uint32_t sel) {
