@@ -611,18 +611,40 @@ __global__ void __launch_bounds__(256) spread_x_tiled(const px_t* __restrict__ s
         // outputs x4 + {0,1} and x4 + {2,3}: windows start at element 4 tid + {0,2} + d, d = 0 .. 2s
         uint32_t v01 = GROW ? 0u : 0x00FF00FFu, v23 = v01;
         const uint32_t* base = sww + r * words + 2 * threadIdx.x;
-        uint32_t w0 = base[0], w1 = base[1];
-        for (int d0 = 0; d0 <= 2 * s; d0 += 2) {
-          const uint32_t w2 = base[(d0 >> 1) + 2];
-          v01 = GROW ? __vmaxu2(v01, w0) : __vminu2(v01, w0);
-          v23 = GROW ? __vmaxu2(v23, w1) : __vminu2(v23, w1);
-          if (d0 + 1 <= 2 * s) {
-            const uint32_t o01 = __funnelshift_r(w0, w1, 16), o23 = __funnelshift_r(w1, w2, 16);
-            v01 = GROW ? __vmaxu2(v01, o01) : __vminu2(v01, o01);
-            v23 = GROW ? __vmaxu2(v23, o23) : __vminu2(v23, o23);
+        auto mm = [](uint32_t a, uint32_t b) { return GROW ? __vmaxu2(a, b) : __vminu2(a, b); };
+        if (s >= 3) {
+          // word W_j = elements (e[2j], e[2j+1]); output k reduces e[k .. k + 2s].  e[4 .. 2s-1] = W_2 .. W_{s-1} lie
+          // in all four windows: reduced once, both lanes folded together; the four windows then differ from that
+          // core by a few elements at either end, picked lane by lane from the edge words and their 16-bit shifts
+          const uint32_t W0 = base[0], W1 = base[1], W2 = base[2];
+          uint32_t M = W2, Wp = W2;  // Wp ends as W_{s-1}
+          for (int j = 3; j < s; j++) {
+            Wp = base[j];
+            M = mm(M, Wp);
           }
-          w0 = w1;
-          w1 = w2;
+          const uint32_t Ws = base[s], Ws1 = base[s + 1];
+          const uint32_t cc = mm(M, __funnelshift_r(M, M, 16));
+          const uint32_t F01 = __funnelshift_r(W0, W1, 16);   // (e1, e2)
+          const uint32_t F12 = __funnelshift_r(W1, W2, 16);   // (e3, e4)
+          const uint32_t G = __funnelshift_r(Wp, Ws, 16);     // (e[2s-1], e[2s])
+          const uint32_t Fs = __funnelshift_r(Ws, Ws1, 16);   // (e[2s+1], e[2s+2])
+          const uint32_t shared = mm(mm(cc, W1), mm(F12, mm(Ws, G)));  // in both pairs of windows
+          v01 = mm(shared, mm(W0, F01));   // lanes: e0..e[2s] | e1..e[2s+1]
+          v23 = mm(shared, mm(Fs, Ws1));   // lanes: e2..e[2s+2] | e3..e[2s+3]
+        } else {
+          uint32_t w0 = base[0], w1 = base[1];
+          for (int d0 = 0; d0 <= 2 * s; d0 += 2) {
+            const uint32_t w2 = base[(d0 >> 1) + 2];
+            v01 = mm(v01, w0);
+            v23 = mm(v23, w1);
+            if (d0 + 1 <= 2 * s) {
+              const uint32_t o01 = __funnelshift_r(w0, w1, 16), o23 = __funnelshift_r(w1, w2, 16);
+              v01 = mm(v01, o01);
+              v23 = mm(v23, o23);
+            }
+            w0 = w1;
+            w1 = w2;
+          }
         }
         const uint32_t v = __byte_perm(v01, v23, 0x6420);  // four alpha bytes
         uint8_t* out = tmp + (size_t)w * y + x4;

@@ -4,20 +4,23 @@
 // (banded) matrix times the pixel columns.  With 65 taps x 4 channels x 2 passes per pixel the CUDA-core
 // kernels of blur.cu are ALU-bound at ~4 % of the HBM roofline; the contraction itself is
 // exact in the tensor cores' number formats:
-//   * pixel bytes 0..255 are exact in fp16;
+//   * pixel bytes 0..255 are exact in fp16 — and need no conversion: a byte b next to a zero byte IS the fp16
+//     subnormal b * 2^-24, so the planes are built with byte permutes only and the whole contraction runs scaled by
+//     2^-24 (exact: every partial sum is a multiple of 2^-24 below 1);
 //   * a uint16 tap k splits into  k = lo + hi * 2048  with lo < 2048 (11 significant bits) and hi * 2048 <= 63488,
 //     both exact in fp16 (Gaussian LUTs of radius >= 29 have hi == 0 everywhere: one MMA per tile);
-//   * every product is an integer < 2^24 and so is every partial sum (sum lut * 255 < 2^24 is checked by the
-//     caller), so the fp32 accumulation never rounds.
-// The results are therefore bit-identical to the reference's uint32 arithmetic; `div 256 div 255` happens in
-// integer registers after the accumulator is read back.
+//   * every product is an integer (times 2^-24) below 2^24 and so is every partial sum (sum lut * 255 < 2^24 is
+//     checked by the caller), so the fp32 accumulation never rounds.
+// The results are therefore bit-identical to the reference's uint32 arithmetic; `div 256 div 255` is one FFMA.RZ on
+// the accumulator: floor(a * float(1 / 65280)) == a div 65280 for every integer a < 2^24 (exhaustive check in
+// tests/test_chain_closed_form.py), the FMA forms the product exactly, and adding 2^23 puts the truncation at ulp 1.
 //
 // Shape: mma.sync.m16n8k16 (fp16 x fp16 -> fp32).  M = 16 outputs along the blur axis, K = 16 inputs, N = 8
 // lines.  The A operand is the Toeplitz block  A_q[m][k] = lut[16 q + k - m]  (q = 0 .. KT-1 with
 // KT = ceil((2r + 16) / 16)); it is the same for every tile, lives in registers, and only KT of the
 // (outputs/16 + KT - 1) k-tiles of a row of tiles are non-zero — 65/80 of the multiply-adds are useful at r = 32.
-// B is the pixel data, staged global -> shared as four planar fp16 channel planes (coalesced 4-byte loads, one
-// PRMT + HSUB2 per two bytes) and read back with ldmatrix (.trans for the vertical pass), each k-tile once per warp
+// B is the pixel data, staged global -> shared as four planar fp16 channel planes (cp.async of the raw tile, then
+// 1.5 PRMT per two bytes) and read back with ldmatrix (.trans for the vertical pass), each k-tile once per warp
 // for all the m-tiles it feeds.  One CTA = 128 outputs x 32 lines x 4 channels; a warp owns 4 m-tiles x 8 lines.
 #include <cuda_fp16.h>
 
