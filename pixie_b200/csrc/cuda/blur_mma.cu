@@ -165,7 +165,10 @@ __global__ void __launch_bounds__(256, 2) blur_mma_kernel(const MmaBlurArgs a, i
         w[2] = __byte_perm(rg01, 0u, 0x4342); w[3] = __byte_perm(rg23, 0u, 0x4342);  // g
         w[4] = __byte_perm(ba01, 0u, 0x4140); w[5] = __byte_perm(ba23, 0u, 0x4140);  // b
         w[6] = __byte_perm(ba01, 0u, 0x4342); w[7] = __byte_perm(ba23, 0u, 0x4342);  // a
-        __half* d = planes + row * pitch + c4;
+        // vertical pass: rows are 32 halfs with no padding; the 16-byte chunk of a row is XOR-swizzled with
+        // (row >> 1) & 3, which keeps both these stores (two rows per half-warp) and ldmatrix.trans (8 rows of one
+        // chunk) on distinct banks
+        __half* d = VERTICAL ? planes + row * pitch + ((((c4 >> 3) ^ (row >> 1)) & 3) << 3) + (c4 & 7) : planes + row * pitch + c4;
 #pragma unroll
         for (int c = 0; c < 4; c++) *reinterpret_cast<uint2*>(d + c * planeHalfs) = make_uint2(w[2 * c], w[2 * c + 1]);
       }
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(256, 2) blur_mma_kernel(const MmaBlurArgs a, i
         const int kbase = (mg * 4 + kt) * 16;  // first input of this k-tile, relative to the tile origin
         uint32_t b0, b1;
         if (VERTICAL) {  // rows of the stored matrix = inputs (k), columns = lines
-          ldmatrix_x2<true>(b0, b1, plane + (kbase + (lane & 15)) * pitch + nt * 8);
+          ldmatrix_x2<true>(b0, b1, plane + (kbase + (lane & 15)) * pitch + (((nt ^ (lane >> 1)) & 3) << 3));  // kbase % 16 == 0
         } else {  // rows of the stored matrix = lines, columns = inputs (k)
           ldmatrix_x2<false>(b0, b1, plane + (nt * 8 + (lane & 7)) * pitch + kbase + ((lane & 8) ? 8 : 0));
         }
@@ -596,9 +599,9 @@ static int launch_both(MmaBlurArgs a, Image* im, void* tmp, int y0, int y1) {
                                         r.stream))
       return rc;
   }
-  {  // Y pass: tmp -> image rows [y0, y1).  Plane [a][line]: 40-half rows
+  {  // Y pass: tmp -> image rows [y0, y1).  Plane [a][line]: 32-half rows, 16-byte chunks XOR-swizzled by row
     a.src = (const px_t*)tmp; a.dst = (px_t*)im->data;
-    a.pitch = kMmaLines + 8;
+    a.pitch = kMmaLines;  // no padding: chunks are swizzled
     const size_t smem = (size_t)4 * IN_A * a.pitch * sizeof(__half) + rawBytes;
     ProfScope ps(kProfBlurY);
     if (int rc = launch_pass<true, KT, HI>(a, (y1 - y0 + kMmaOut - 1) / kMmaOut, (im->w + kMmaLines - 1) / kMmaLines, smem, r.stream))
