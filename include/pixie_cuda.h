@@ -159,7 +159,9 @@ int pixie_cuda_blur_rows(pixie_image_t image, const uint16_t* lut, int radius, u
                          int y0, int y1);
 int pixie_cuda_spread(pixie_image_t image, int spread);
 /* dst <- shadow(src, offset, spread, blur, color); the offset copy is mask.draw(image, translate(offset),
- * OverwriteBlend) (:768-769): blendRect for integral offsets, drawSmooth otherwise. */
+ * OverwriteBlend) (:768-769): blendRect for integral offsets, drawSmooth otherwise.  Only the mask's alpha reaches
+ * the result (:760-776), so with an integral offset and radius <= 64 the whole pipeline runs on an 8-bit alpha plane
+ * (same bytes out; other cases go through the RGBX mask as the reference does).  src and dst must differ. */
 int pixie_cuda_shadow(pixie_image_t src, pixie_image_t dst, float offset_x, float offset_y, int spread,
                       const uint16_t* lut, int radius, uint32_t rgbx);
 
