@@ -121,6 +121,17 @@ __global__ void __launch_bounds__(256, 2) blur_mma_kernel(const MmaBlurArgs a, i
     const int x0 = VERTICAL ? l0 : a0 - a.radius, y0 = VERTICAL ? a0 - a.radius : l0;
     const int xEnd = VERTICAL ? l_end : a_len, yEnd = VERTICAL ? a_len : l_end;
     constexpr int G = COLS / 4;  // groups of 4 pixels per tile row
+    if (vec_ok && x0 >= 0 && x0 + COLS <= xEnd && y0 >= 0 && y0 + ROWS <= yEnd) {
+      // tile inside the image: no per-piece checks, and the piece -> (row, column) map is the same for every tile
+      const px_t* base = a.src + (size_t)a.w * y0 + x0;
+#pragma unroll
+      for (int u = 0; u < (ROWS * G + 255) / 256; u++) {
+        const int idx = tid + 256 * u;
+        const int row = idx / G, c4 = (idx - row * G) * 4;
+        if (idx < ROWS * G) cp_async_16(raw + 4 * idx, base + (a.w * row + c4));
+      }
+      return;
+    }
     for (int idx = tid; idx < ROWS * G; idx += 256) {
       const int row = idx / G, c4 = (idx - row * G) * 4;
       const int y = y0 + row, x = x0 + c4;
@@ -238,6 +249,31 @@ __global__ void __launch_bounds__(256, 2) blur_mma_kernel(const MmaBlurArgs a, i
     }
 
     // ---- store: fragment slot s of m-tile i is output (m = g + 8 (s >> 1), n = 2 t + (s & 1))
+    const bool inside = VERTICAL ? (a0 + kMmaOut <= min(a.y1, a.h) && l0 + kMmaLines <= a.w && (a.w & 1) == 0 &&
+                                    (reinterpret_cast<uintptr_t>(a.dst) & 7) == 0)
+                                 : (a0 + kMmaOut <= a.w && l0 + kMmaLines <= l_end);
+    if (inside) {  // whole tile inside the image: one base pointer, constant strides, no checks
+      if (VERTICAL) {
+        px_t* p = a.dst + (size_t)a.w * (a0 + mg * 64 + g) + (l0 + nt * 8 + 2 * t);
+        const size_t w8 = (size_t)a.w * 8;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+          for (int hrow = 0; hrow < 2; hrow++, p += w8) *reinterpret_cast<uint2*>(p) = make_uint2(pix[i][2 * hrow], pix[i][2 * hrow + 1]);
+        }
+      } else {
+        px_t* p0 = a.dst + (size_t)a.w * (l0 + nt * 8 + 2 * t) + (a0 + mg * 64 + g);
+        px_t* p1 = p0 + a.w;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          p0[16 * i] = pix[i][0];
+          p1[16 * i] = pix[i][1];
+          p0[16 * i + 8] = pix[i][2];
+          p1[16 * i + 8] = pix[i][3];
+        }
+      }
+      continue;
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int abase = a0 + (mg * 4 + i) * 16;
