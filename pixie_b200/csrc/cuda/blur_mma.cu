@@ -369,6 +369,16 @@ __global__ void __launch_bounds__(256) blur_mma_a8_kernel(const MmaBlurA8Args a,
   uint4 v[NLD];
   auto fetch = [&](int a0, int l0) {  // the tile's bytes -> registers
     const int x0 = VERTICAL ? l0 : a0 - a.radius - a.shift, y0 = VERTICAL ? a0 - a.radius : l0;
+    if (vec16 && x0 >= 0 && x0 + COLS <= a.w && y0 >= 0 && y0 + ROWS <= a.h) {  // tile inside the image: no checks
+      const uint8_t* base = a.src + (size_t)a.w * y0 + x0;
+#pragma unroll
+      for (int u = 0; u < NLD; u++) {
+        const int c = tid + 256 * u;
+        const int row = c / CH, c16 = (c - row * CH) * 16;
+        if (c < ROWS * CH) v[u] = *reinterpret_cast<const uint4*>(base + (a.w * row + c16));
+      }
+      return;
+    }
 #pragma unroll
     for (int u = 0; u < NLD; u++) {
       const int c = tid + 256 * u;
