@@ -478,6 +478,47 @@ __global__ void __launch_bounds__(256) spread_x(const px_t* __restrict__ src, ui
     }
   }
 }
+// Y pass, 16 columns per thread (one 16-byte load per row): needs w % 16 == 0.  Two output rows per step share the
+// rows both windows hold, as in spread_y.
+template <bool GROW, bool A8OUT>
+__global__ void __launch_bounds__(256) spread_y_wide(const uint8_t* __restrict__ tmp, void* __restrict__ dstv, int w, int h, int s) {
+  const int x16 = 16 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (x16 >= w) return;
+  px_t* dst = reinterpret_cast<px_t*>(dstv);
+  uint8_t* dst8 = reinterpret_cast<uint8_t*>(dstv);
+  const uint32_t idn = GROW ? 0u : 0x00FF00FFu;
+  const uint8_t* col = tmp + x16;
+  auto acc = [&](uint32_t (&e)[4], uint32_t (&o)[4], const uint4 a4) {
+    const uint32_t a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t ae = a[k] & 0x00FF00FFu, ao = (a[k] >> 8) & 0x00FF00FFu;  // bytes {0, 2} and {1, 3}
+      e[k] = GROW ? __vmaxu2(e[k], ae) : __vminu2(e[k], ae);
+      o[k] = GROW ? __vmaxu2(o[k], ao) : __vminu2(o[k], ao);
+    }
+  };
+  auto store = [&](int y, const uint32_t (&e)[4], const uint32_t (&o)[4]) {
+    if (A8OUT) {
+      *reinterpret_cast<uint4*>(dst8 + (size_t)w * y + x16) = make_uint4(e[0] | (o[0] << 8), e[1] | (o[1] << 8), e[2] | (o[2] << 8), e[3] | (o[3] << 8));
+    } else {  // rgbx(0, 0, 0, value)
+      uint4* p = reinterpret_cast<uint4*>(dst + (size_t)w * y + x16);
+#pragma unroll
+      for (int k = 0; k < 4; k++) p[k] = make_uint4(e[k] << 24, o[k] << 24, (e[k] >> 16) << 24, (o[k] >> 16) << 24);
+    }
+  };
+  for (int y = 2 * blockIdx.y; y < h; y += 2 * gridDim.y) {
+    const int clo = max(y + 1 - s, 0), chi = min(y + s, h - 1);  // rows both windows hold
+    uint32_t e[4] = {idn, idn, idn, idn}, o[4] = {idn, idn, idn, idn};
+    const uint8_t* p = col + (size_t)w * clo;
+    for (int yy = clo; yy <= chi; yy++, p += w) acc(e, o, *reinterpret_cast<const uint4*>(p));
+    uint32_t e1[4] = {e[0], e[1], e[2], e[3]}, o1[4] = {o[0], o[1], o[2], o[3]};
+    if (y - s >= 0) acc(e, o, *reinterpret_cast<const uint4*>(col + (size_t)w * (y - s)));
+    if (y + 1 + s <= h - 1) acc(e1, o1, *reinterpret_cast<const uint4*>(col + (size_t)w * (y + 1 + s)));
+    store(y, e, o);
+    if (y + 1 < h) store(y + 1, e1, o1);
+  }
+}
+
 // A8OUT: the result stays an alpha plane (shadow's mask, blurred as one channel) instead of rgbx(0, 0, 0, a)
 template <bool GROW, bool A8OUT = false>
 __global__ void __launch_bounds__(256) spread_y(const uint8_t* __restrict__ tmp, void* __restrict__ dstv, int w, int h, int s) {
@@ -672,19 +713,25 @@ static int spread_shifted(const Image* src, int ox, int oy, Image* dstIm, int sp
   dim3 gx((w + 1023) / 1024, 1);
   gx.y = (unsigned)std::max(1, std::min((h + kSpreadRows - 1) / kSpreadRows, r.num_sms * 8 / (int)gx.x));
   const size_t smem = (size_t)kSpreadRows * (((1024 + 2 * s) + 4 + 1) / 2 + 2) * 4;  // 16-bit lanes, kSpreadRows rows
-  dim3 gy((w + 1023) / 1024, 1);
-  gy.y = (unsigned)std::max(1, std::min(h, r.num_sms * 16 / (int)gy.x));
+  void* const yOut = planeOut ? (void*)planeOut : dstIm->data;
+  const bool wide = (w & 15) == 0 && (reinterpret_cast<uintptr_t>(yOut) & 15) == 0 && (reinterpret_cast<uintptr_t>(tmp) & 15) == 0;
+  dim3 gy((w + (wide ? 4095 : 1023)) / (wide ? 4096 : 1024), 1);
+  gy.y = (unsigned)std::max(1, std::min((h + 1) / 2, r.num_sms * 16 / (int)gy.x));
   ProfScope ps(kProfSpread);
   if (spread > 0) {
     spread_x_tiled<true><<<gx, 256, smem, r.stream>>>((const px_t*)src->data, ox, oy, (uint8_t*)tmp, w, h, s);
     PX_LAUNCHED();
-    if (planeOut) spread_y<true, true><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, planeOut, w, h, s);
-    else spread_y<true><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, dstIm->data, w, h, s);
+    if (wide && planeOut) spread_y_wide<true, true><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, yOut, w, h, s);
+    else if (wide) spread_y_wide<true, false><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, yOut, w, h, s);
+    else if (planeOut) spread_y<true, true><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, yOut, w, h, s);
+    else spread_y<true><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, yOut, w, h, s);
   } else {
     spread_x_tiled<false><<<gx, 256, smem, r.stream>>>((const px_t*)src->data, ox, oy, (uint8_t*)tmp, w, h, s);
     PX_LAUNCHED();
-    if (planeOut) spread_y<false, true><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, planeOut, w, h, s);
-    else spread_y<false><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, dstIm->data, w, h, s);
+    if (wide && planeOut) spread_y_wide<false, true><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, yOut, w, h, s);
+    else if (wide) spread_y_wide<false, false><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, yOut, w, h, s);
+    else if (planeOut) spread_y<false, true><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, yOut, w, h, s);
+    else spread_y<false><<<gy, 256, 0, r.stream>>>((const uint8_t*)tmp, yOut, w, h, s);
   }
   PX_LAUNCHED();
   return 0;
