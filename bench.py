@@ -211,9 +211,9 @@ def extras_single_gpu(dev, peak):
                              "GB/s": round(n * n * 8 / t / 1e6, 1), "frac_hbm": round(n * n * 8 / t / 1e6 / peak, 3),
                              "bytes_per_px": 8, "Gtaps_per_s": round(n * n * 4 * 2 * 65 / t / 1e6, 1),
                              "traffic_bytes_per_px": 16,
-                             "bound": "tensor-core Toeplitz contraction (blur_mma.cu, bit-exact): issue-bound by the u8->fp16 "
-                                      "staging and the integer epilogue; two passes move 16 B/px, the 8 B/px figure is the "
-                                      "single-pass ideal of SURVEY 8(d)"}
+                             "bound": "tensor-core Toeplitz contraction (blur_mma.cu, bit-exact): bound by the HMMA pipe and "
+                                      "instruction issue (staging permutes, stores); two passes move 16 B/px, the 8 B/px "
+                                      "figure is the single-pass ideal of SURVEY 8(d)"}
     dstimg = dev.DeviceImage(n, n)
     ms = []
     for it in range(2):
