@@ -1,5 +1,4 @@
-"""Device time of one tiger 4096^2 step (clear + K1..K3) and of its raster kernel, for A/B runs under env switches
-(PIXIE_CUDA_TILE_SMEM, PIXIE_CUDA_TILEW)."""
+"""Device time of one tiger step (clear + K1..K3) and of its raster kernel; PIXIE_CUDA_LIB=<other build> for A/B runs."""
 import os
 import statistics
 import sys
@@ -24,6 +23,6 @@ for it in range(25):
     if it >= 5:
         steps.append(t)
         rast.append(dev.profile_read(dev.PROF_RASTER))
-print("tiger %d^2  TILE_SMEM=%s TILEW=%s: step %.4f ms (min %.4f)  raster %.4f ms" % (
-    size, os.environ.get("PIXIE_CUDA_TILE_SMEM", "-"), os.environ.get("PIXIE_CUDA_TILEW", "-"),
-    statistics.median(steps), min(steps), statistics.median(rast)))
+print("tiger %d^2 (%s): step %.4f ms (min %.4f)  raster %.4f ms" % (
+    size, os.path.basename(os.environ.get("PIXIE_CUDA_LIB", "pixie_cuda.so")), statistics.median(steps), min(steps),
+    statistics.median(rast)))
