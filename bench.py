@@ -342,7 +342,8 @@ def banded_blur_multi_gpu(dev, dist, rank, world, local_rank, peak):
     n, r = 16384, 32
     y0, y1 = multi.band_range(n, world, rank)
     tile = torch.from_numpy(synth.random_premultiplied(256, n, 0xB10B + rank)).cuda()
-    band = tile.repeat((y1 - y0 + 255) // 256, 1, 1)[: y1 - y0].contiguous()
+    rb = multi.RowBand(n, n, rank, world, margin=r)  # the band lives between its halo margins: no staging copies
+    rb.band.copy_(tile.repeat((y1 - y0 + 255) // 256, 1, 1)[: y1 - y0])
     lut = host.gaussianKernel(r)
     times = []
     for it in range(4):
@@ -350,16 +351,31 @@ def banded_blur_multi_gpu(dev, dist, rank, world, local_rank, peak):
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        multi.blur_band(band, r, lut, 0, rank, world)
+        rb.blur(r, lut, 0)
         e1.record()
         torch.cuda.synchronize()
         if it:
             times.append(e0.elapsed_time(e1))
     t = torch.tensor([statistics.median(times)], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # parity across the cut (outside the timed region): this rank also blurs the WHOLE canvas on its own GPU and
+    # compares its band's rows with what the banded blur produced
+    parts = []
+    for k in range(world):
+        a, b = multi.band_range(n, world, k)
+        tk = torch.from_numpy(synth.random_premultiplied(256, n, 0xB10B + k)).cuda()
+        parts.append(tk.repeat((b - a + 255) // 256, 1, 1)[: b - a])
+    whole = torch.cat(parts)
+    del parts
+    rb.band.copy_(whole[y0:y1])
+    rb.blur(r, lut, 0)
+    dev.blur(dev.DeviceImage.wrap(whole.data_ptr(), n, n, owner=whole), lut, r, 0)
+    same = torch.tensor([int(torch.equal(rb.band, whole[y0:y1]))], dtype=torch.int64, device="cuda")
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    del whole
     dev.set_stream(None)
     ms = float(t.item())
-    return {"ms": round(ms, 3), "GB/s": round(n * n * 8 / ms / 1e6, 1), "frac_hbm_aggregate": round(n * n * 8 / ms / 1e6 / (peak * world), 3),
+    return {"ms": round(ms, 3), "matches_single_gpu_blur_on_every_rank": bool(same.item()), "GB/s": round(n * n * 8 / ms / 1e6, 1), "frac_hbm_aggregate": round(n * n * 8 / ms / 1e6 / (peak * world), 3),
             "halo_bytes_per_interior_edge": 2 * r * n * 4, "scaling": "strong (one 16384^2 canvas)"}
 
 

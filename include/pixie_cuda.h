@@ -38,7 +38,8 @@ typedef uint64_t pixie_cmdlist_t; /* opaque handle of a device-resident fill com
 /* ---- runtime ------------------------------------------------------------------------- */
 int pixie_cuda_init(int device);               /* select device, create the stream; idempotent */
 const char* pixie_cuda_last_error(void);       /* bindings/bindings.nim:3-10 takeError analogue */
-int pixie_cuda_set_stream(void* cuda_stream);  /* cudaStream_t to issue on (NULL = library stream) */
+int pixie_cuda_set_stream(void* cuda_stream);  /* cudaStream_t to issue on (NULL = library stream; the legacy default
+                                                * stream is named by cudaStreamLegacy = (cudaStream_t)0x1) */
 int pixie_cuda_sync(void);                     /* wait for everything issued so far */
 int pixie_cuda_device_count(int* out);
 

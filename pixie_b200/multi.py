@@ -50,6 +50,15 @@ def bind_to_gpu_numa(device_index: int) -> dict:
     return info
 
 
+def torch_stream_handle() -> int:
+    """The CUDA stream torch is issuing on, as a handle pixie_cuda_set_stream understands.  torch's default stream is
+    the legacy stream, whose handle is 0 — which the C ABI reads as "the library's own stream"; cudaStreamLegacy (1)
+    names it explicitly, so that the kernels are ordered with torch's and NCCL's work on that stream."""
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream or 1
+
+
 def shard_range(n_units: int, world: int, rank: int):
     """Contiguous block [begin, end) of independent units owned by `rank`."""
     base, rem = divmod(n_units, world)
@@ -104,10 +113,71 @@ def blur_band(band, radius: int, lut: np.ndarray, oob_rgbx: int, rank: int, worl
 
     from . import device as dev
 
-    dev.set_stream(torch.cuda.current_stream().cuda_stream)  # NCCL and the kernels share one stream
+    dev.set_stream(torch_stream_handle())  # NCCL and the kernels share one stream
     ext, top, bottom = exchange_halos(band, radius, rank, world, group)
     rows, width = band.shape[0], band.shape[1]
     img = dev.DeviceImage.wrap(ext.data_ptr(), width, ext.shape[0], owner=ext)
     dev.blur_rows(img, lut, radius, oob_rgbx, top, top + rows)
     band.copy_(ext[top:top + rows])
     return band
+
+
+class RowBand:
+    """This rank's row band of one canvas split across `world` ranks, stored with `margin` spare rows above and
+    below it: the neighbours' halo rows are received straight into the margins and the row-band kernel runs on
+    [halo ; band ; halo] in place — no size exchange (band heights follow from `band_range`), no staging copies.
+
+    rb = RowBand(height, width, rank, world, margin=64); rb.band[...] = pixels; rb.blur(32, lut, 0)"""
+
+    def __init__(self, height: int, width: int, rank: int, world: int, margin: int, device="cuda", group=None):
+        import torch
+
+        self.height, self.width, self.rank, self.world, self.margin, self.group = height, width, rank, world, margin, group
+        self.sizes = [band_range(height, world, k)[1] - band_range(height, world, k)[0] for k in range(world)]
+        self.rows = self.sizes[rank]
+        self.buf = torch.zeros((margin + self.rows + margin, width, 4), dtype=torch.uint8, device=device)
+        self.band = self.buf[margin:margin + self.rows]
+
+    def halo_rows(self, radius: int):
+        """(top, bottom): halo rows this rank receives for a filter of `radius` rows."""
+        r, w, sizes = self.rank, self.world, self.sizes
+        if radius > self.margin:
+            raise ValueError("radius exceeds the band's margin")
+        if (r > 0 and sizes[r - 1] < radius and r - 1 > 0) or (r < w - 1 and sizes[r + 1] < radius and r + 1 < w - 1):
+            raise ValueError("bands shorter than the blur radius need multi-hop halos: use fewer ranks")
+        top = min(radius, sizes[r - 1]) if r > 0 else 0
+        bottom = min(radius, sizes[r + 1]) if r < w - 1 else 0
+        return top, bottom
+
+    def exchange(self, radius: int):
+        """Fill the margins with the neighbours' rows (point-to-point send / recv).  Returns (ext, top, bottom) with
+        ext = the contiguous view [halo_top ; band ; halo_bottom] of the buffer."""
+        import torch.distributed as dist
+
+        top, bottom = self.halo_rows(radius)
+        m, rows, r, w = self.margin, self.rows, self.rank, self.world
+        send = min(radius, rows)
+        ops = []
+        if r > 0:
+            ops.append(dist.P2POp(dist.isend, self.band[:send], r - 1, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, self.buf[m - top:m], r - 1, group=self.group))
+        if r < w - 1:
+            ops.append(dist.P2POp(dist.isend, self.band[rows - send:], r + 1, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, self.buf[m + rows:m + rows + bottom], r + 1, group=self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return self.buf[m - top:m + rows + bottom], top, bottom
+
+    def blur(self, radius: int, lut: np.ndarray, oob_rgbx: int):
+        """Blur the band in place as part of the whole canvas: rows at the true image border see `oob_rgbx`, interior
+        cuts see the neighbours' rows."""
+        import torch
+
+        from . import device as dev
+
+        dev.set_stream(torch_stream_handle())  # NCCL and the kernels share one stream
+        ext, top, bottom = self.exchange(radius)
+        img = dev.DeviceImage.wrap(ext.data_ptr(), self.width, ext.shape[0], owner=self.buf)
+        dev.blur_rows(img, lut, radius, oob_rgbx, top, top + self.rows)
+        return self.band

@@ -37,6 +37,13 @@ def _worker(rank, world, port, h, w, radius, tmpdir):
         part = np.ascontiguousarray(ext.numpy().copy())
         ob.blur(part, lut, radius, 0)
         assert np.array_equal(part[top:top + (y1 - y0)], whole[y0:y1]), "banded blur differs from the global blur"
+        # the same exchange with the band stored between its halo margins (multi.RowBand): no staging copies
+        rb = multi.RowBand(h, w, rank, world, margin=radius + 3, device="cpu")
+        rb.band.copy_(band)
+        ext2, top2, bottom2 = rb.exchange(radius)
+        assert (top2, bottom2) == (top, bottom) and ext2.is_contiguous()
+        assert np.array_equal(ext2.numpy(), img[e0:e1]), "RowBand halo rows are not the neighbours' rows"
+        assert np.array_equal(rb.band.numpy(), img[y0:y1])
         # shards of independent units cover the range exactly once
         ranges = [multi.shard_range(1001, world, r) for r in range(world)]
         assert ranges[0][0] == 0 and ranges[-1][1] == 1001 and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
