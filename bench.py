@@ -504,8 +504,8 @@ def run_ours(args):
     roofline = {"kernel": "raster_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4),
                 # dram__bytes_read.sum + dram__bytes_write.sum of one raster_kernel launch on this workload, from the
-                # `ncu --set full` capture summarised in profiles/r01_tiger_metrics.txt (20.30 MB read + 13.09 MB written: the canvas stays in the 126 MB L2)
-                "traffic": 33390080 if size == 4096 else None, "peak_source": peak_src,
+                # `ncu --set full` capture summarised in profiles/r01_tiger_metrics.txt (20.27 MB read + 12.00 MB written: the canvas stays in the 126 MB L2)
+                "traffic": 32271616 if size == 4096 else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(rast, 4),
                 "partition_kernel_ms": round(part, 4), "plan_kernel_ms": round(statistics.mean(plan_ms), 4), "share_of_step": round(rast / statistics.mean(step_ms), 3),
                 "note": "305 order-dependent fills: latency/occupancy-bound, not bandwidth-bound (SURVEY.md 7.1)"}
