@@ -19,6 +19,10 @@
  *   - the library never keeps a host pointer after a call returns.  Device work is issued on one
  *     stream (pixie_cuda_set_stream) in call order = the reference's sequential semantics; only
  *     *_download, *_host and pixie_cuda_sync block the host.
+ *   - threading: the reference is single-threaded.  Here ONE coarse recursive lock serialises every
+ *     entry point, so calls from several host threads — on distinct handles or on the same one — are safe; their
+ *     device work is issued on the library's one stream in lock-acquisition order.  One process drives one GPU
+ *     (pixie_cuda_init on a second device ordinal is an error): several GPUs = one process per GPU.
  *   - numerics: bit-exact with the reference's x86 row kernels applied to every pixel
  *     (src/pixie/simd/sse2.nim:6-46,510-524); float32 geometry without FMA.
  */
@@ -105,6 +109,11 @@ int pixie_cuda_cmdlist_create(int width, int height, int layers, int num_fills, 
                               const uint32_t* rgbx, const uint8_t* winding_rule, const uint8_t* blend_mode,
                               pixie_cmdlist_t* out);
 int pixie_cuda_cmdlist_run(pixie_cmdlist_t list, pixie_image_t image, uint64_t* covered_px);
+/* One GPU's row band of a canvas split across GPUs: plans and rasterises only rows [y0, y1) of a
+ * single-layer list.  `image` is the whole canvas (rows outside the range are left alone) or an image of exactly
+ * y1 - y0 rows holding that band.  The list itself — bounds, partition boundaries (paths.nim:1172-1192), band
+ * entries — is the whole canvas's, so the pixels equal the undivided render's. */
+int pixie_cuda_cmdlist_run_rows(pixie_cmdlist_t list, pixie_image_t image, int y0, int y1, uint64_t* covered_px);
 int pixie_cuda_cmdlist_info(pixie_cmdlist_t list, int64_t* num_segments, int64_t* num_partitions,
                             int64_t* num_entries, int64_t* launches_per_run);
 int pixie_cuda_cmdlist_destroy(pixie_cmdlist_t list);
@@ -158,13 +167,28 @@ int pixie_cuda_blur(pixie_image_t image, const uint16_t* lut, int radius, uint32
  * unchanged.  With `radius` halo rows above and below, rows [y0, y1) equal the global blur. */
 int pixie_cuda_blur_rows(pixie_image_t image, const uint16_t* lut, int radius, uint32_t out_of_bounds_rgbx,
                          int y0, int y1);
+/* The two halves of pixie_cuda_blur_rows, for callers that overlap the halo exchange with the X pass (which needs no
+ * halo): _x blurs rows [r0, r1) horizontally into the library's scratch plane; _y then produces image rows
+ * [y0, y1) from scratch rows [y0 - radius, y1 + radius) — each of which an _x call must have produced since the last
+ * other library call on an image of another size.  Radii 1..64 with gaussianKernel LUTs only (else status 1). */
+int pixie_cuda_blur_rows_x(pixie_image_t image, const uint16_t* lut, int radius, uint32_t out_of_bounds_rgbx,
+                           int r0, int r1);
+int pixie_cuda_blur_rows_y(pixie_image_t image, const uint16_t* lut, int radius, uint32_t out_of_bounds_rgbx,
+                           int y0, int y1);
 int pixie_cuda_spread(pixie_image_t image, int spread);
+/* Row-band forms of spread / shadow: `image` (src / dst) is [halo ; band ; halo], the caller keeps rows [y0, y1);
+ * rows outside are left unspecified.  An edge of [y0, y1) that is not an edge of the image needs a halo of
+ * |spread| rows (spread) resp. ceil|offset_y| + |spread| + radius rows (shadow), else status 1. */
+int pixie_cuda_spread_rows(pixie_image_t image, int spread, int y0, int y1);
 /* dst <- shadow(src, offset, spread, blur, color); the offset copy is mask.draw(image, translate(offset),
  * OverwriteBlend) (:768-769): blendRect for integral offsets, drawSmooth otherwise.  Only the mask's alpha reaches
  * the result (:760-776), so with an integral offset and radius <= 64 the whole pipeline runs on an 8-bit alpha plane
  * (same bytes out; other cases go through the RGBX mask as the reference does).  src and dst must differ. */
 int pixie_cuda_shadow(pixie_image_t src, pixie_image_t dst, float offset_x, float offset_y, int spread,
                       const uint16_t* lut, int radius, uint32_t rgbx);
+
+int pixie_cuda_shadow_rows(pixie_image_t src, pixie_image_t dst, float offset_x, float offset_y, int spread,
+                           const uint16_t* lut, int radius, uint32_t rgbx, int y0, int y1);
 
 /* ---- strict drop-in variants: host pixels in, host pixels out (upload -> run -> download) ---- */
 int pixie_cuda_fill_segments_host(uint8_t* pixels, int width, int height, const float* seg_xyxy,
@@ -175,6 +199,13 @@ int pixie_cuda_blur_host(uint8_t* pixels, int width, int height, const uint16_t*
                          uint32_t out_of_bounds_rgbx);
 int pixie_cuda_shadow_host(const uint8_t* src_pixels, uint8_t* dst_pixels, int width, int height, float offset_x,
                            float offset_y, int spread, const uint16_t* lut, int radius, uint32_t rgbx);
+
+int pixie_cuda_spread_host(uint8_t* pixels, int width, int height, int spread);                 /* images.nim:700-758 */
+int pixie_cuda_apply_opacity_host(uint8_t* pixels, int width, int height, float opacity);      /* images.nim:261-277 */
+/* the non-solid paint composite (paths.nim:2141-2142) on host pixels; mask: src-sized A8 (1) or RGBX (4) plane */
+int pixie_cuda_blend_rect_masked_host(uint8_t* dst_pixels, int dst_width, int dst_height, const uint8_t* src_pixels,
+                                      const uint8_t* mask_pixels, int mask_bytes_per_pixel, int src_width,
+                                      int src_height, int px, int py, int blend_mode);
 
 /* draw(a, b, transform, blendMode) / drawTiled on host pixels (tiled != 0), images.nim:636-683 */
 int pixie_cuda_draw_host(uint8_t* dst_pixels, int dst_width, int dst_height, const uint8_t* src_pixels, int src_width,

@@ -236,11 +236,12 @@ class Image:
         return out
 
 
-_DEVICE = 0
+_DEVICE = None
 
 
-def dev_index() -> int:
-    return _DEVICE
+def dev_index():
+    """The device api.Image uses: the one set_device() / device.init() selected, else 0."""
+    return _DEVICE if _DEVICE is not None else dev.current_device()
 
 
 def set_device(index: int):

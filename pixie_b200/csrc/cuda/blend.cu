@@ -275,13 +275,15 @@ using namespace pixie;
 extern "C" {
 
 int pixie_cuda_blend_rect(pixie_image_t dst, pixie_image_t src, int px, int py, int mode) {
+  PX_API_GUARD;
   return blend_rect_impl(dst, src, 0, false, px, py, mode);
 }
 int pixie_cuda_blend_rect_masked(pixie_image_t dst, pixie_image_t src, pixie_image_t mask, int px, int py, int mode) {
+  PX_API_GUARD;
   return blend_rect_impl(dst, src, mask, true, px, py, mode);
 }
 
-int pixie_cuda_apply_opacity(pixie_image_t h, float opacity) {  // images.nim:261-277
+int pixie_cuda_apply_opacity(pixie_image_t h, float opacity) { PX_API_GUARD;  // images.nim:261-277
   if (int rc = ensure_init()) return rc;
   Image* im = find_image(h);
   if (!im) return 1;

@@ -355,9 +355,11 @@ static int launch_f32(ConvArgs a, Image* im, void* tmp, const uint16_t* lut_d, i
   return 0;
 }
 
-int blur_mma(Image* im, void* tmp, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1);  // blur_mma.cu
+int blur_mma(Image* im, void* tmp, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1, int phase);  // blur_mma.cu
 
-static int blur_impl(Image* im, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1) {
+// phase 0: the whole blur of rows [y0, y1); 1 / 2: only its X pass over rows [y0, y1) / only its Y pass (the two
+// halves of a row-band blur whose halo exchange overlaps the X pass, pixie_cuda_blur_rows_x / _y)
+static int blur_impl(Image* im, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1, int phase = 0) {
   Runtime& r = rt();
   if (radius == 0) return 0;
   if (radius < 0) return fail_pixie("Cannot apply negative blur");  // images.nim:311-312
@@ -372,10 +374,11 @@ static int blur_impl(Image* im, const uint16_t* lut_host, int radius, uint32_t o
      // PIXIE_CUDA_BLUR=cores keeps the CUDA-core kernels (A/B timing, parity tests of both paths)
     static const char* force = getenv("PIXIE_CUDA_BLUR");
     if (!(force && strcmp(force, "cores") == 0)) {
-      const int rc = blur_mma(im, tmp, lut_host, radius, oob, y0, y1);
+      const int rc = blur_mma(im, tmp, lut_host, radius, oob, y0, y1, phase);
       if (rc >= 0) return rc;
     }
   }
+  if (phase != 0) return fail_pixie("blur_rows_x / blur_rows_y: this radius / LUT is outside the split-pass kernel's domain");
   if (int rc = get_scratch(1, (size_t)ntaps * 2, &lut_d)) return rc;
   if (int rc = staging_acquire((size_t)ntaps * 2, &pin)) return rc;
   memcpy(pin, lut_host, (size_t)ntaps * 2);
@@ -862,6 +865,7 @@ using namespace pixie;
 extern "C" {
 
 int pixie_cuda_blur(pixie_image_t h, const uint16_t* lut, int radius, uint32_t oob) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   Image* im = find_image(h);
   if (!im) return 1;
@@ -869,21 +873,70 @@ int pixie_cuda_blur(pixie_image_t h, const uint16_t* lut, int radius, uint32_t o
 }
 
 int pixie_cuda_blur_rows(pixie_image_t h, const uint16_t* lut, int radius, uint32_t oob, int y0, int y1) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   Image* im = find_image(h);
   if (!im) return 1;
   return blur_impl(im, lut, radius, oob, y0, y1);
 }
 
+int pixie_cuda_blur_rows_x(pixie_image_t h, const uint16_t* lut, int radius, uint32_t oob, int r0, int r1) {
+  PX_API_GUARD;
+  if (int rc = ensure_init()) return rc;
+  Image* im = find_image(h);
+  if (!im) return 1;
+  if (radius <= 0) return fail_pixie("blur_rows_x needs a positive radius");
+  return blur_impl(im, lut, radius, oob, r0, r1, 1);
+}
+
+int pixie_cuda_blur_rows_y(pixie_image_t h, const uint16_t* lut, int radius, uint32_t oob, int y0, int y1) {
+  PX_API_GUARD;
+  if (int rc = ensure_init()) return rc;
+  Image* im = find_image(h);
+  if (!im) return 1;
+  if (radius <= 0) return fail_pixie("blur_rows_y needs a positive radius");
+  return blur_impl(im, lut, radius, oob, y0, y1, 2);
+}
+
 int pixie_cuda_spread(pixie_image_t h, int spread) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   Image* im = find_image(h);
   if (!im) return 1;
   return spread_impl(im, spread);
 }
 
+// Row-band forms of spread / shadow (one canvas split across GPUs): `image` is [halo ; band ; halo]
+// and the caller keeps rows [y0, y1).  Both run on the whole extended image — a cut edge is treated like an image
+// border, and what that gets wrong reaches at most |spread| (spread) resp. |offset.y| + |spread| + radius (shadow)
+// rows inward, which is the halo the caller supplies; edges without a halo are true image borders.
+int pixie_cuda_spread_rows(pixie_image_t h, int spread, int y0, int y1) {
+  PX_API_GUARD;
+  if (int rc = ensure_init()) return rc;
+  Image* im = find_image(h);
+  if (!im) return 1;
+  if (y0 < 0 || y1 > im->h || y0 > y1) return fail_pixie("row range out of bounds");
+  const int s = spread < 0 ? -spread : spread;
+  if ((y0 > 0 && y0 < s) || (y1 < im->h && im->h - y1 < s)) return fail_pixie("spread_rows: a halo shorter than |spread| rows");
+  return spread_impl(im, spread);
+}
+
+int pixie_cuda_shadow_rows(pixie_image_t srch, pixie_image_t dsth, float ox, float oy, int spread, const uint16_t* lut,
+                           int radius, uint32_t rgbx, int y0, int y1) {
+  PX_API_GUARD;
+  if (int rc = ensure_init()) return rc;
+  Image* s = find_image(srch);
+  if (!s) return 1;
+  if (y0 < 0 || y1 > s->h || y0 > y1) return fail_pixie("row range out of bounds");
+  const int need = (int)ceilf(fabsf(oy)) + (spread < 0 ? -spread : spread) + (radius > 0 ? radius : 0);
+  if ((y0 > 0 && y0 < need) || (y1 < s->h && s->h - y1 < need))
+    return fail_pixie("shadow_rows: a halo shorter than |offset.y| + |spread| + radius rows");
+  return pixie_cuda_shadow(srch, dsth, ox, oy, spread, lut, radius, rgbx);
+}
+
 int pixie_cuda_shadow(pixie_image_t srch, pixie_image_t dsth, float ox, float oy, int spread, const uint16_t* lut,
                       int radius, uint32_t rgbx) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   Image* s = find_image(srch);
   Image* d = find_image(dsth);

@@ -631,12 +631,13 @@ static int launch_pass(const MmaBlurArgs& a, int tilesA, int tilesL, size_t smem
   return 0;
 }
 
+// phase 0: both passes; 1: X pass only (rows [sy0, sy1) -> tmp); 2: Y pass only (tmp -> image rows [y0, y1))
 template <int KT, bool HI>
-static int launch_both(MmaBlurArgs a, Image* im, void* tmp, int y0, int y1) {
+static int launch_both(MmaBlurArgs a, Image* im, void* tmp, int y0, int y1, int phase) {
   Runtime& r = rt();
   constexpr int IN_A = kMmaOut - 16 + 16 * KT;
   const size_t rawBytes = (size_t)IN_A * kMmaLines * 4;
-  {  // X pass: image -> tmp, rows [sy0, sy1).  Plane [line][a]: pitch = 8 mod 64 halfs keeps ldmatrix conflict-free
+  if (phase != 2) {  // X pass: image -> tmp, rows [sy0, sy1).  Plane [line][a]: pitch = 8 mod 64 halfs keeps ldmatrix conflict-free
     a.src = (const px_t*)im->data; a.dst = (px_t*)tmp;
     a.pitch = IN_A + ((8 - IN_A) % 64 + 64) % 64;
     const size_t smem = (size_t)4 * kMmaLines * a.pitch * sizeof(__half) + rawBytes;
@@ -645,7 +646,7 @@ static int launch_both(MmaBlurArgs a, Image* im, void* tmp, int y0, int y1) {
                                         r.stream))
       return rc;
   }
-  {  // Y pass: tmp -> image rows [y0, y1).  Plane [a][line]: 32-half rows, 16-byte chunks XOR-swizzled by row
+  if (phase != 1) {  // Y pass: tmp -> image rows [y0, y1).  Plane [a][line]: 32-half rows, 16-byte chunks XOR-swizzled by row
     a.src = (const px_t*)tmp; a.dst = (px_t*)im->data;
     a.pitch = kMmaLines;  // no padding: chunks are swizzled
     const size_t smem = (size_t)4 * IN_A * a.pitch * sizeof(__half) + rawBytes;
@@ -668,7 +669,7 @@ static int upload_mma_lut(const uint16_t* lut_host, int ntaps) {
 
 // Tensor-core blur of rows [y0, y1) of `im` through the scratch plane `tmp`.  Returns -1 when the radius / LUT is
 // outside what this path holds exactly (the caller then takes the CUDA-core kernels).
-int blur_mma(Image* im, void* tmp, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1) {
+int blur_mma(Image* im, void* tmp, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1, int phase) {
   const int ntaps = 2 * radius + 1;
   if (radius < 1 || ntaps > kMaxTaps) return -1;
   unsigned long long sum = 0;
@@ -684,17 +685,21 @@ int blur_mma(Image* im, void* tmp, const uint16_t* lut_host, int radius, uint32_
   a.y0 = y0; a.y1 = y1;
   a.sy0 = std::max(0, y0 - radius);
   a.sy1 = std::min(im->h, y1 + radius);
+  if (phase == 1) {  // X pass of exactly the rows asked for
+    a.sy0 = y0;
+    a.sy1 = y1;
+  }
   a.pitch = 0; a.src = nullptr; a.dst = nullptr;
   const int KT = (2 * radius + 16 + 15) / 16;
   switch (KT) {
-    case 2: return hasHi ? launch_both<2, true>(a, im, tmp, y0, y1) : launch_both<2, false>(a, im, tmp, y0, y1);
-    case 3: return hasHi ? launch_both<3, true>(a, im, tmp, y0, y1) : launch_both<3, false>(a, im, tmp, y0, y1);
-    case 4: return hasHi ? launch_both<4, true>(a, im, tmp, y0, y1) : launch_both<4, false>(a, im, tmp, y0, y1);
-    case 5: return hasHi ? launch_both<5, true>(a, im, tmp, y0, y1) : launch_both<5, false>(a, im, tmp, y0, y1);
-    case 6: return hasHi ? launch_both<6, true>(a, im, tmp, y0, y1) : launch_both<6, false>(a, im, tmp, y0, y1);
-    case 7: return hasHi ? launch_both<7, true>(a, im, tmp, y0, y1) : launch_both<7, false>(a, im, tmp, y0, y1);
-    case 8: return hasHi ? launch_both<8, true>(a, im, tmp, y0, y1) : launch_both<8, false>(a, im, tmp, y0, y1);
-    case 9: return hasHi ? launch_both<9, true>(a, im, tmp, y0, y1) : launch_both<9, false>(a, im, tmp, y0, y1);
+    case 2: return hasHi ? launch_both<2, true>(a, im, tmp, y0, y1, phase) : launch_both<2, false>(a, im, tmp, y0, y1, phase);
+    case 3: return hasHi ? launch_both<3, true>(a, im, tmp, y0, y1, phase) : launch_both<3, false>(a, im, tmp, y0, y1, phase);
+    case 4: return hasHi ? launch_both<4, true>(a, im, tmp, y0, y1, phase) : launch_both<4, false>(a, im, tmp, y0, y1, phase);
+    case 5: return hasHi ? launch_both<5, true>(a, im, tmp, y0, y1, phase) : launch_both<5, false>(a, im, tmp, y0, y1, phase);
+    case 6: return hasHi ? launch_both<6, true>(a, im, tmp, y0, y1, phase) : launch_both<6, false>(a, im, tmp, y0, y1, phase);
+    case 7: return hasHi ? launch_both<7, true>(a, im, tmp, y0, y1, phase) : launch_both<7, false>(a, im, tmp, y0, y1, phase);
+    case 8: return hasHi ? launch_both<8, true>(a, im, tmp, y0, y1, phase) : launch_both<8, false>(a, im, tmp, y0, y1, phase);
+    case 9: return hasHi ? launch_both<9, true>(a, im, tmp, y0, y1, phase) : launch_both<9, false>(a, im, tmp, y0, y1, phase);
     default: return -1;
   }
 }

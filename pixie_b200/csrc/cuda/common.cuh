@@ -33,6 +33,7 @@ struct Runtime {
   uint64_t next_handle = 1;
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t switch_ev = nullptr;  // orders a new current stream after the old one (pixie_cuda_set_stream)
   // scratch buffers that grow on demand (stream-ordered reuse)
   void* scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
@@ -61,6 +62,12 @@ struct ProfScope {  // brackets one kernel launch with events on the library str
 };
 
 Runtime& rt();
+// Threading contract of the C ABI (include/pixie_cuda.h "Threading"): ONE coarse recursive lock serialises every
+// entry point — the library has one stream, one scratch set and one pinned staging buffer, so calls from several
+// host threads (on the same or on distinct handles) are safe and are issued in lock-acquisition order.
+std::recursive_mutex& api_mutex();
+#define PX_API_GUARD std::lock_guard<std::recursive_mutex> _px_api_lock(pixie::api_mutex())
+int new_image_uninit(int w, int h, int layers, int bpp, pixie_image_t* out);  // contents undefined (callers overwrite)
 void set_error(const std::string& msg);
 int fail_pixie(const std::string& msg);            // returns 1
 int fail_cuda(cudaError_t e, const char* what);    // returns 2

@@ -715,24 +715,28 @@ using namespace pixie;
 extern "C" {
 
 int pixie_cuda_draw(pixie_image_t dst, pixie_image_t src, const float* mat, int mode) {
+  PX_API_GUARD;
   Image *d, *s;
   if (int rc = two_images(dst, src, &d, &s, mode)) return rc;
   return draw_impl(d, s, mat, mode);
 }
 
 int pixie_cuda_draw_tiled(pixie_image_t dst, pixie_image_t src, const float* mat, int mode) {
+  PX_API_GUARD;
   Image *d, *s;
   if (int rc = two_images(dst, src, &d, &s, mode)) return rc;
   return draw_correct_impl(d, s, mat, mode, true);
 }
 
 int pixie_cuda_draw_correct(pixie_image_t dst, pixie_image_t src, const float* mat, int mode) {
+  PX_API_GUARD;
   Image *d, *s;
   if (int rc = two_images(dst, src, &d, &s, mode)) return rc;
   return draw_correct_impl(d, s, mat, mode, false);
 }
 
 int pixie_cuda_minify_by2(pixie_image_t src, int power, pixie_image_t* out) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   if (power < 0) return fail_pixie("Cannot minifyBy2 with negative power");
   Image* s = find_image(src);
@@ -773,6 +777,7 @@ int pixie_cuda_minify_by2(pixie_image_t src, int power, pixie_image_t* out) {
 }
 
 int pixie_cuda_magnify_by2(pixie_image_t src, int power, pixie_image_t* out) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   if (power < 0) return fail_pixie("Cannot magnifyBy2 with negative power");
   Image* s = find_image(src);
@@ -791,6 +796,7 @@ int pixie_cuda_magnify_by2(pixie_image_t src, int power, pixie_image_t* out) {
 
 int pixie_cuda_fill_gradient(pixie_image_t image, int kind, const float* handles, int n_handles, const float* stop_pos,
                              const float* stop_rgba, int n_stops, float opacity) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   Image* im = find_image(image);
   if (!im) return 1;

@@ -83,6 +83,12 @@ struct CmdList {
   uint8_t* block = nullptr;   // block A: host-written inputs + device-made offsets/flags/counters
   uint8_t* blockB = nullptr;  // block B: band entries + spill scratch (sized after the device-side count)
   bool owned = false;
+  bool deviceCounted = false;  // band counts / offsets were made by count_kernel + scans (lists above 8192 segments)
+  bool countFresh = false;     // ... and the arrays still hold the offsets of build_list's own pass
+  // host copy of what a row-band run needs to lay out its jobs (pixie_cuda_cmdlist_run_rows)
+  std::vector<int> hostStartY, hostPathHeight;  // per fill; pathHeight <= startY when the fill has no jobs
+  int maxWrapRows = 0;                          // MaskBlend fills reaching left of the canvas read jobs of later rows
+  int* rowsJobBase = nullptr;                   // device [numFills + 1], made per run_rows call
 };
 
 static std::unordered_map<uint64_t, CmdList> g_lists;
@@ -1715,6 +1721,8 @@ static int band_edge(long long rows, int b, int K) {
 }
 
 static void free_list(CmdList& L) {
+  if (L.rowsJobBase) cudaFree(L.rowsJobBase);
+  L.rowsJobBase = nullptr;
   if (L.owned && L.block) cudaFree(L.block);
   if (L.owned && L.blockB) cudaFree(L.blockB);
   L.block = L.blockB = nullptr;
@@ -1724,6 +1732,23 @@ static double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 static const bool g_trace = getenv("PIXIE_CUDA_TRACE") != nullptr;
+
+// The count pass of partitionSegments (:1201-1223) on the device: band counts per segment range, exclusive scan to
+// entry offsets, payload offsets.  Totals land in counters[2..4].  Run by build_list (to size block B) and again
+// at the start of every later run of a resident list, so that one run = the whole of partitionSegments.
+static int device_count(CmdList& L) {
+  Runtime& r = rt();
+  const size_t P = (size_t)L.numParts;
+  PX_CUDA(cudaMemsetAsync(L.entryOff, 0, (P + 1) * 4, r.stream));
+  const int cblocks = (int)std::min<int64_t>((L.numSegs + 255) / 256, (int64_t)r.num_sms * 8);
+  count_kernel<<<std::max(cblocks, 1), 256, 0, r.stream>>>(L.fills, L.numFills, L.segs, (int)L.numSegs, L.entryOff, L.ranges, L.groupRange);
+  PX_LAUNCHED();
+  scan_kernel<<<1, 1024, 0, r.stream>>>(L.entryOff, (int)P, L.counters + 2);
+  PX_LAUNCHED();
+  payload_scan_kernel<<<1, 1024, 0, r.stream>>>(L.fills, L.numFills, L.entryOff, (int)P, L.payOff, L.counters + 4);
+  PX_LAUNCHED();
+  return 0;
+}
 
 constexpr int64_t kHostCountMaxSegs = 8192;  // lists up to this size are counted on the host (no sync in the call)
 
@@ -1745,6 +1770,10 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   if (numSegs < 0 || numSegs > 0x7fffffffll) return fail_pixie("invalid seg_offsets");
   L.numSegs = numSegs;
   L.bands = (bands > 1 && layers == 1) ? std::min(bands, (int)Runtime::kBands) : 1;
+  if (!arena) {
+    L.hostStartY.assign(numFills, 0);
+    L.hostPathHeight.assign(numFills, 0);
+  }
 
   // Device block A.  The host-written part (segments, windings, headers, row ranges, layer table) is
   // contiguous and goes through a staging buffer; the segments are written into it by the same pass that
@@ -1890,8 +1919,17 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
     }
     numPartsTotal += numPartitions;
     jobsTotal += height;
+    L.maxWrapRows = std::max(L.maxWrapRows, H.wrapRows);
+    if (!arena) {
+      L.hostStartY[k] = H.startY;
+      L.hostPathHeight[k] = H.pathHeight;
+    }
     if (numPartsTotal > 0x3fffffff || jobsTotal > 0x3fffffff) return fail_pixie("command list too large");
   }
+  // A MaskBlend fill reaching left of the canvas makes row y read the plans of rows y + 1 .. y + wrapRows
+  // (mask_wrap_clears); with row bands those belong to the NEXT band's plan launch on another stream, which
+  // band b's raster kernel does not wait for: such lists are planned and rasterised as one band.
+  if (L.maxWrapRows > 0) L.bands = 1;
   for (int l = 1; l <= layers; l++) layerBegin[l] = std::max(layerBegin[l], layerBegin[l - 1]);
   jobBase[numFills] = (int)jobsTotal;
   L.totalJobs = (int)jobsTotal;
@@ -2073,14 +2111,10 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   PX_CUDA(cudaMemsetAsync(L.scratchSlots, 0, (size_t)((L.scratchSlotCount + 31) / 32) * 4, r.stream));
   if (!hostCount) {
     if (P > 0) {
-      PX_CUDA(cudaMemsetAsync(L.entryOff, 0, (P + 1) * 4, r.stream));
-      const int cblocks = (int)std::min<int64_t>((numSegs + 255) / 256, (int64_t)r.num_sms * 8);
-      count_kernel<<<std::max(cblocks, 1), 256, 0, r.stream>>>(L.fills, numFills, L.segs, (int)numSegs, L.entryOff, L.ranges, L.groupRange);
-      PX_LAUNCHED();
-      scan_kernel<<<1, 1024, 0, r.stream>>>(L.entryOff, (int)P, L.counters + 2);
-      PX_LAUNCHED();
-      payload_scan_kernel<<<1, 1024, 0, r.stream>>>(L.fills, numFills, L.entryOff, (int)P, L.payOff, L.counters + 4);
-      PX_LAUNCHED();
+      L.numParts = numPartsTotal;
+      if (int rc = device_count(L)) return rc;
+      L.deviceCounted = true;
+      L.countFresh = true;
       PX_CUDA(cudaMemcpyAsync(meta, L.counters + 2, 24, cudaMemcpyDeviceToHost, r.stream));
     }
     PX_CUDA(cudaStreamSynchronize(r.stream));  // also retires the pageable staging vector of owned lists
@@ -2141,14 +2175,24 @@ static int launch_plan_kernels(const CmdList& L, const RasterArgs& A, int jobs, 
   return 0;
 }
 
-static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_pixels = nullptr) {
+// rows [rowY0, rowY1) of a single-layer list (rowY1 < 0: everything).  `im` is the whole canvas, or — bandImage —
+// an image of exactly those rows (one GPU's band of a canvas split across GPUs).
+static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_pixels = nullptr, int rowY0 = 0, int rowY1 = -1,
+                    bool bandImage = false) {
   Runtime& r = rt();
-  if (im->bpp != 4 || im->w != L.w || im->h != L.h || im->layers != L.layers)
-    return fail_pixie("command list was built for a different canvas shape");
-  if (L.numFills == 0) {
+  const bool rows = rowY1 >= 0;
+  if (!rows) {
+    if (im->bpp != 4 || im->w != L.w || im->h != L.h || im->layers != L.layers)
+      return fail_pixie("command list was built for a different canvas shape");
+  }
+  if (L.numFills == 0 || (rows && rowY1 <= rowY0)) {
     if (covered_px) *covered_px = 0;
     return 0;
   }
+  if (L.deviceCounted && !L.countFresh && L.numParts > 0) {  // the count pass belongs to every run (see device_count)
+    if (int rc = device_count(L)) return rc;
+  }
+  L.countFresh = false;
   PX_CUDA(cudaMemsetAsync(L.counters, 0, 256, r.stream));  // row tickets, covered px, heavy-job counts
   if (L.numParts > 0) {
     const int warps = (int)std::min<int64_t>(L.numParts, (int64_t)r.num_sms * 32);
@@ -2178,7 +2222,44 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
     configured = L.smemBytes;
   }
   const long long totalRows = (long long)L.layers * L.h;
-  if (!host_pixels || L.bands <= 1) {
+  if (rows) {
+    // One GPU's row band of a canvas split across GPUs: the list — bounds, partition boundaries,
+    // band entries — is that of the WHOLE canvas (numPartitions / partitionHeight are defined on the whole path
+    // height, paths.nim:1172-1192, so every anti-aliasing decision is the one the undivided render makes); only
+    // the jobs (fill, scanline) of rows [rowY0, rowY1) are planned and only those rows are rasterised.  Rows
+    // below the band whose plans a MaskBlend fill's negative-x clears read (mask_wrap_clears) are planned too.
+    const int planY1 = std::min(L.h, rowY1 + L.maxWrapRows);
+    const size_t nb = ((size_t)L.numFills + 1) * 4;
+    if (!L.rowsJobBase) PX_CUDA(cudaMalloc(&L.rowsJobBase, nb));
+    void* pin;
+    if (int rc = staging_acquire(nb, &pin)) return rc;
+    int* bj = (int*)pin;
+    int run = 0;
+    for (int k = 0; k < L.numFills; k++) {
+      bj[k] = run;
+      run += std::max(0, std::min(L.hostPathHeight[k], planY1) - std::max(L.hostStartY[k], rowY0));
+    }
+    bj[L.numFills] = run;
+    PX_CUDA(cudaMemcpyAsync(L.rowsJobBase, pin, nb, cudaMemcpyHostToDevice, r.stream));
+    if (int rc = staging_release()) return rc;
+    if (run > 0) {
+      ProfScope ps(kProfPlan);
+      A.planJobBase = L.rowsJobBase; A.planY0 = rowY0; A.planJobs = run;
+      A.heavyList = L.heavyList;
+      A.heavyCount = L.counters + 16;
+      const int blocks = std::max(1, std::min((run + 7) / 8, L.planBlocks));
+      if (int rc = launch_plan_kernels(L, A, run, blocks, r.stream, 0)) return rc;
+    }
+    if (bandImage) A.canvas = (px_t*)im->data - (size_t)rowY0 * (size_t)L.w;  // row y of the canvas = row y - rowY0 of the band
+    A.rowBegin = rowY0; A.rowEnd = rowY1; A.ticketSlot = 0;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(((long long)(rowY1 - rowY0) * L.tiles + L.warpsPerBlock - 1) / L.warpsPerBlock,
+                                                                     L.rasterBlocks));
+    {
+      ProfScope ps(kProfRaster);
+      raster_kernel<<<blocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
+    }
+    PX_LAUNCHED();
+  } else if (!host_pixels || L.bands <= 1) {
     if (L.totalJobs > 0) {
       ProfScope ps(kProfPlan);
       A.heavyList = L.heavyList;
@@ -2285,6 +2366,7 @@ extern "C" {
 int pixie_cuda_cmdlist_create(int w, int h, int layers, int numFills, const int32_t* layerOf, const float* seg,
                               const int16_t* wind, const int32_t* segOff, const uint32_t* rgbx, const uint8_t* rule,
                               const uint8_t* mode, pixie_cmdlist_t* out) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   CmdList L;
   int rc = build_list(L, false, 1, w, h, layers, numFills, layerOf, seg, wind, segOff, rgbx, rule, mode);
@@ -2301,6 +2383,7 @@ int pixie_cuda_cmdlist_create(int w, int h, int layers, int numFills, const int3
 }
 
 int pixie_cuda_cmdlist_run(pixie_cmdlist_t list, pixie_image_t image, uint64_t* covered_px) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   auto it = g_lists.find(list);
   if (it == g_lists.end()) return fail_pixie("invalid command list handle");
@@ -2309,8 +2392,25 @@ int pixie_cuda_cmdlist_run(pixie_cmdlist_t list, pixie_image_t image, uint64_t* 
   return run_list(it->second, im, covered_px);
 }
 
+int pixie_cuda_cmdlist_run_rows(pixie_cmdlist_t list, pixie_image_t image, int y0, int y1, uint64_t* covered_px) {
+  PX_API_GUARD;
+  if (int rc = ensure_init()) return rc;
+  auto it = g_lists.find(list);
+  if (it == g_lists.end()) return fail_pixie("invalid command list handle");
+  CmdList& L = it->second;
+  Image* im = find_image(image);
+  if (!im) return 1;
+  if (L.layers != 1) return fail_pixie("cmdlist_run_rows needs a single-layer command list");
+  if (y0 < 0 || y1 > L.h || y0 > y1) return fail_pixie("row range out of bounds");
+  if (im->bpp != 4 || im->layers != 1 || im->w != L.w) return fail_pixie("command list was built for a different canvas shape");
+  const bool band = im->h != L.h;
+  if (band && im->h != y1 - y0) return fail_pixie("cmdlist_run_rows: the image must be the whole canvas or exactly rows [y0, y1)");
+  return run_list(L, im, covered_px, nullptr, y0, y1, band);
+}
+
 int pixie_cuda_cmdlist_info(pixie_cmdlist_t list, int64_t* numSegs, int64_t* numParts, int64_t* numEntries,
                             int64_t* launches) {
+  PX_API_GUARD;
   auto it = g_lists.find(list);
   if (it == g_lists.end()) return fail_pixie("invalid command list handle");
   if (numSegs) *numSegs = it->second.numSegs;
@@ -2321,6 +2421,7 @@ int pixie_cuda_cmdlist_info(pixie_cmdlist_t list, int64_t* numSegs, int64_t* num
 }
 
 int pixie_cuda_cmdlist_destroy(pixie_cmdlist_t list) {
+  PX_API_GUARD;
   auto it = g_lists.find(list);
   if (it == g_lists.end()) return fail_pixie("invalid command list handle");
   cudaStreamSynchronize(rt().stream);
@@ -2332,6 +2433,7 @@ int pixie_cuda_cmdlist_destroy(pixie_cmdlist_t list) {
 int pixie_cuda_fill_batch(pixie_image_t image, int numFills, const int32_t* layerOf, const float* seg,
                           const int16_t* wind, const int32_t* segOff, const uint32_t* rgbx, const uint8_t* rule,
                           const uint8_t* mode, uint64_t* covered_px) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   Image* im = find_image(image);
   if (!im) return 1;
@@ -2345,6 +2447,7 @@ int pixie_cuda_fill_batch(pixie_image_t image, int numFills, const int32_t* laye
 int pixie_cuda_render_batch_host(uint8_t* pixels, int width, int height, int clear, int numFills, const float* seg,
                                  const int16_t* wind, const int32_t* segOff, const uint32_t* rgbx, const uint8_t* rule,
                                  const uint8_t* mode, uint64_t* covered_px) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   if (width <= 0 || height <= 0) return fail_pixie("Image width and height must be > 0");
   Runtime& r = rt();
@@ -2370,6 +2473,7 @@ int pixie_cuda_render_batch_host(uint8_t* pixels, int width, int height, int cle
 
 int pixie_cuda_fill_segments(pixie_image_t image, const float* seg, const int16_t* wind, int n, uint32_t rgbx,
                              int rule, int mode) {
+  PX_API_GUARD;
   if (rule < 0 || rule > 1 || mode < 0 || mode >= NumBlendModes) return fail_pixie("invalid blend mode / winding rule");
   const int32_t segOff[2] = {0, n};
   const uint8_t r8 = (uint8_t)rule, m8 = (uint8_t)mode;

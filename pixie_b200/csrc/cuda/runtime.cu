@@ -15,6 +15,10 @@ Runtime& rt() {
   static Runtime r;
   return r;
 }
+std::recursive_mutex& api_mutex() {
+  static std::recursive_mutex m;
+  return m;
+}
 void set_error(const std::string& msg) { g_err = msg; }
 int fail_pixie(const std::string& msg) {
   g_err = msg;
@@ -122,7 +126,7 @@ __global__ void checksum_kernel(const uint32_t* __restrict__ p, size_t n, unsign
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
-static int new_image(int w, int h, int layers, int bpp, void* wrap, pixie_image_t* out) {
+static int new_image(int w, int h, int layers, int bpp, void* wrap, pixie_image_t* out, bool zero = true) {
   if (int rc = ensure_init()) return rc;
   if (w <= 0 || h <= 0) return fail_pixie("Image width and height must be > 0");  // common.nim:41-42
   if (layers <= 0) return fail_pixie("Image layers must be > 0");
@@ -139,13 +143,17 @@ static int new_image(int w, int h, int layers, int bpp, void* wrap, pixie_image_
   } else {
     // stream-ordered allocation from the device pool (its memory stays cached: no driver call per newImage)
     PX_CUDA(cudaMallocAsync(&im.data, im.bytes(), r.stream));
-    PX_CUDA(cudaMemsetAsync(im.data, 0, im.bytes(), r.stream));
+    if (zero) PX_CUDA(cudaMemsetAsync(im.data, 0, im.bytes(), r.stream));
   }
   std::lock_guard<std::mutex> lk(r.mu);
   uint64_t hd = r.next_handle++;
   r.images[hd] = im;
   *out = hd;
   return 0;
+}
+
+int new_image_uninit(int w, int h, int layers, int bpp, pixie_image_t* out) {
+  return new_image(w, h, layers, bpp, nullptr, out, false);
 }
 
 }  // namespace pixie
@@ -155,8 +163,14 @@ using namespace pixie;
 extern "C" {
 
 int pixie_cuda_init(int device) {
+  PX_API_GUARD;
   Runtime& r = rt();
   if (r.inited && r.device == device) return 0;
+  // the stream, events, scratch, pinned staging and every image handle belong to the first device: a process drives
+  // ONE GPU (one process per GPU is how the path shards)
+  if (r.inited)
+    return fail_pixie("pixie_cuda_init: already initialised on device " + std::to_string(r.device) +
+                      "; one process drives one GPU (start one process per GPU)");
   int n = 0;
   PX_CUDA(cudaGetDeviceCount(&n));
   if (n <= 0) return fail_pixie("pixie_cuda: no CUDA device visible (there is no CPU fallback)");
@@ -184,19 +198,29 @@ int pixie_cuda_init(int device) {
 const char* pixie_cuda_last_error(void) { return g_err.c_str(); }
 
 int pixie_cuda_set_stream(void* s) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   Runtime& r = rt();
-  r.stream = s ? (cudaStream_t)s : r.own_stream;
+  cudaStream_t next = s ? (cudaStream_t)s : r.own_stream;
+  if (next == r.stream) return 0;
+  // everything already queued on the old stream (image zero-fills, staged H2D copies, LUT uploads to __constant__
+  // memory) happens before anything issued on the new one
+  if (!r.switch_ev) PX_CUDA(cudaEventCreateWithFlags(&r.switch_ev, cudaEventDisableTiming));
+  PX_CUDA(cudaEventRecord(r.switch_ev, r.stream));
+  PX_CUDA(cudaStreamWaitEvent(next, r.switch_ev, 0));
+  r.stream = next;
   return 0;
 }
 
 int pixie_cuda_sync(void) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   PX_CUDA(cudaStreamSynchronize(rt().stream));
   return 0;
 }
 
 int pixie_cuda_device_count(int* out) {
+  PX_API_GUARD;
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess) {
@@ -207,17 +231,20 @@ int pixie_cuda_device_count(int* out) {
   return 0;
 }
 
-int pixie_cuda_image_create(int w, int h, pixie_image_t* out) { return new_image(w, h, 1, 4, nullptr, out); }
+int pixie_cuda_image_create(int w, int h, pixie_image_t* out) { PX_API_GUARD; return new_image(w, h, 1, 4, nullptr, out); }
 int pixie_cuda_image_create_layers(int w, int h, int layers, pixie_image_t* out) {
+  PX_API_GUARD;
   return new_image(w, h, layers, 4, nullptr, out);
 }
-int pixie_cuda_image_create_a8(int w, int h, pixie_image_t* out) { return new_image(w, h, 1, 1, nullptr, out); }
+int pixie_cuda_image_create_a8(int w, int h, pixie_image_t* out) { PX_API_GUARD; return new_image(w, h, 1, 1, nullptr, out); }
 int pixie_cuda_image_wrap(void* p, int w, int h, int layers, int bpp, pixie_image_t* out) {
+  PX_API_GUARD;
   if (!p) return fail_pixie("pixie_cuda_image_wrap: null device pointer");
   return new_image(w, h, layers, bpp, p, out);
 }
 
 int pixie_cuda_image_destroy(pixie_image_t h) {
+  PX_API_GUARD;
   Runtime& r = rt();
   std::lock_guard<std::mutex> lk(r.mu);
   auto it = r.images.find(h);
@@ -233,6 +260,7 @@ int pixie_cuda_image_destroy(pixie_image_t h) {
 }
 
 int pixie_cuda_image_info(pixie_image_t h, int* w, int* ht, int* layers, int* bpp, void** ptr) {
+  PX_API_GUARD;
   Image* im = find_image(h);
   if (!im) return 1;
   if (w) *w = im->w;
@@ -244,6 +272,7 @@ int pixie_cuda_image_info(pixie_image_t h, int* w, int* ht, int* layers, int* bp
 }
 
 int pixie_cuda_image_upload(pixie_image_t h, const uint8_t* host) {
+  PX_API_GUARD;
   Image* im = find_image(h);
   if (!im) return 1;
   PX_CUDA(cudaMemcpyAsync(im->data, host, im->bytes(), cudaMemcpyHostToDevice, rt().stream));
@@ -251,6 +280,7 @@ int pixie_cuda_image_upload(pixie_image_t h, const uint8_t* host) {
   return 0;
 }
 int pixie_cuda_image_download(pixie_image_t h, uint8_t* host) {
+  PX_API_GUARD;
   Image* im = find_image(h);
   if (!im) return 1;
   PX_CUDA(cudaMemcpyAsync(host, im->data, im->bytes(), cudaMemcpyDeviceToHost, rt().stream));
@@ -258,18 +288,21 @@ int pixie_cuda_image_download(pixie_image_t h, uint8_t* host) {
   return 0;
 }
 int pixie_cuda_image_upload_async(pixie_image_t h, const uint8_t* host) {
+  PX_API_GUARD;
   Image* im = find_image(h);
   if (!im) return 1;
   PX_CUDA(cudaMemcpyAsync(im->data, host, im->bytes(), cudaMemcpyHostToDevice, rt().stream));
   return 0;
 }
 int pixie_cuda_image_download_async(pixie_image_t h, uint8_t* host) {
+  PX_API_GUARD;
   Image* im = find_image(h);
   if (!im) return 1;
   PX_CUDA(cudaMemcpyAsync(host, im->data, im->bytes(), cudaMemcpyDeviceToHost, rt().stream));
   return 0;
 }
 int pixie_cuda_image_download_rows(pixie_image_t h, int layer, int y0, int y1, uint8_t* host) {
+  PX_API_GUARD;
   Image* im = find_image(h);
   if (!im) return 1;
   if (layer < 0 || layer >= im->layers || y0 < 0 || y1 > im->h || y0 > y1) return fail_pixie("row range out of bounds");
@@ -280,6 +313,7 @@ int pixie_cuda_image_download_rows(pixie_image_t h, int layer, int y0, int y1, u
 }
 
 int pixie_cuda_image_fill(pixie_image_t h, uint32_t rgbx) {
+  PX_API_GUARD;
   Image* im = find_image(h);
   if (!im) return 1;
   Runtime& r = rt();
@@ -308,6 +342,7 @@ int pixie_cuda_image_fill(pixie_image_t h, uint32_t rgbx) {
 }
 
 int pixie_cuda_image_copy(pixie_image_t dst, pixie_image_t src) {
+  PX_API_GUARD;
   Image* d = find_image(dst);
   Image* s = find_image(src);
   if (!d || !s) return 1;
@@ -318,6 +353,7 @@ int pixie_cuda_image_copy(pixie_image_t dst, pixie_image_t src) {
 }
 
 int pixie_cuda_image_checksum(pixie_image_t h, uint64_t* out) {
+  PX_API_GUARD;
   Image* im = find_image(h);
   if (!im) return 1;
   if (im->bpp != 4) return fail_pixie("checksum needs an RGBX image");
@@ -335,16 +371,19 @@ int pixie_cuda_image_checksum(pixie_image_t h, uint64_t* out) {
 }
 
 int pixie_cuda_host_alloc(size_t bytes, void** out) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   PX_CUDA(cudaMallocHost(out, bytes));
   return 0;
 }
 int pixie_cuda_host_free(void* p) {
+  PX_API_GUARD;
   PX_CUDA(cudaFreeHost(p));
   return 0;
 }
 
 int pixie_cuda_set_profiling(int enabled) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   Runtime& r = rt();
   if (enabled && !r.prof[0][0])
@@ -354,6 +393,7 @@ int pixie_cuda_set_profiling(int enabled) {
   return 0;
 }
 int pixie_cuda_profile_read(int slot, float* ms) {
+  PX_API_GUARD;
   Runtime& r = rt();
   if (slot < 0 || slot >= 8 || !r.prof[0][0]) return fail_pixie("profiling slot out of range or profiling never enabled");
   PX_CUDA(cudaEventSynchronize(r.prof[slot][1]));
@@ -362,15 +402,18 @@ int pixie_cuda_profile_read(int slot, float* ms) {
 }
 
 int pixie_cuda_launch_count(uint64_t* out) {
+  PX_API_GUARD;
   *out = rt().launches;
   return 0;
 }
 int pixie_cuda_timer_begin(void) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   PX_CUDA(cudaEventRecord(rt().ev0, rt().stream));
   return 0;
 }
 int pixie_cuda_timer_end(float* ms) {
+  PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   PX_CUDA(cudaEventRecord(rt().ev1, rt().stream));
   PX_CUDA(cudaEventSynchronize(rt().ev1));

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "pixie_cuda_render_batch_host": [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, P(u64)],
     "pixie_cuda_cmdlist_create": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, P(u64)],
     "pixie_cuda_cmdlist_run": [u64, u64, P(u64)],
+    "pixie_cuda_cmdlist_run_rows": [u64, u64, i32, i32, P(u64)],
     "pixie_cuda_cmdlist_info": [u64, P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64)],
     "pixie_cuda_cmdlist_destroy": [u64],
     "pixie_cuda_blend_rect": [u64, u64, i32, i32, i32],
@@ -60,7 +61,14 @@ _SIGNATURES = {
     "pixie_cuda_fill_gradient": [u64, i32, vp, i32, vp, vp, i32, f32],
     "pixie_cuda_blur": [u64, vp, i32, u32],
     "pixie_cuda_blur_rows": [u64, vp, i32, u32, i32, i32],
+    "pixie_cuda_blur_rows_x": [u64, vp, i32, u32, i32, i32],
+    "pixie_cuda_blur_rows_y": [u64, vp, i32, u32, i32, i32],
     "pixie_cuda_spread": [u64, i32],
+    "pixie_cuda_spread_rows": [u64, i32, i32, i32],
+    "pixie_cuda_shadow_rows": [u64, u64, f32, f32, i32, vp, i32, u32, i32, i32],
+    "pixie_cuda_spread_host": [vp, i32, i32, i32],
+    "pixie_cuda_apply_opacity_host": [vp, i32, i32, f32],
+    "pixie_cuda_blend_rect_masked_host": [vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32],
     "pixie_cuda_shadow": [u64, u64, f32, f32, i32, vp, i32, u32],
     "pixie_cuda_fill_segments_host": [vp, i32, i32, vp, vp, i32, u32, i32, i32],
     "pixie_cuda_blend_rect_host": [vp, i32, i32, vp, i32, i32, i32, i32, i32],
@@ -114,8 +122,21 @@ def check(rc):
         raise PixieError(lib().pixie_cuda_last_error().decode())
 
 
-def init(device: int = 0):
+_device = None
+
+
+def init(device: int | None = None):
+    """Select the GPU of this process (one process per GPU).  `None` = the device already initialised, else 0.
+    Initialising a second, different device is an error (pixie_cuda_init)."""
+    global _device
+    if device is None:
+        device = _device if _device is not None else 0
     check(lib().pixie_cuda_init(device))
+    _device = device
+
+
+def current_device():
+    return _device
 
 
 def sync():
@@ -282,6 +303,12 @@ class CmdList:
         check(lib().pixie_cuda_cmdlist_run(self.handle, image.handle, C.byref(cov) if count_covered else None))
         return cov.value
 
+    def run_rows(self, image: DeviceImage, y0, y1, count_covered=False):
+        """Rows [y0, y1) only; `image` = the whole canvas or a band image of y1 - y0 rows (multi-GPU row bands)."""
+        cov = u64(0)
+        check(lib().pixie_cuda_cmdlist_run_rows(self.handle, image.handle, y0, y1, C.byref(cov) if count_covered else None))
+        return cov.value
+
     def info(self):
         a, b, c, d = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
         check(lib().pixie_cuda_cmdlist_info(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
@@ -355,6 +382,25 @@ def blur(image: DeviceImage, lut, radius, oob=0):
 def blur_rows(image: DeviceImage, lut, radius, oob, y0, y1):
     lut = np.ascontiguousarray(lut, np.uint16)
     check(lib().pixie_cuda_blur_rows(image.handle, lut.ctypes.data, radius, oob, y0, y1))
+
+
+def blur_rows_x(image: DeviceImage, lut, radius, oob, r0, r1):
+    lut = np.ascontiguousarray(lut, np.uint16)
+    check(lib().pixie_cuda_blur_rows_x(image.handle, lut.ctypes.data, radius, oob, r0, r1))
+
+
+def blur_rows_y(image: DeviceImage, lut, radius, oob, y0, y1):
+    lut = np.ascontiguousarray(lut, np.uint16)
+    check(lib().pixie_cuda_blur_rows_y(image.handle, lut.ctypes.data, radius, oob, y0, y1))
+
+
+def spread_rows(image: DeviceImage, amount, y0, y1):
+    check(lib().pixie_cuda_spread_rows(image.handle, amount, y0, y1))
+
+
+def shadow_rows(src: DeviceImage, dst: DeviceImage, ox, oy, spread_, lut, radius, rgbx, y0, y1):
+    lut = np.ascontiguousarray(lut, np.uint16)
+    check(lib().pixie_cuda_shadow_rows(src.handle, dst.handle, ox, oy, spread_, lut.ctypes.data, radius, rgbx, y0, y1))
 
 
 def spread(image: DeviceImage, amount):

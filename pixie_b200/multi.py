@@ -71,6 +71,16 @@ def band_range(height: int, world: int, rank: int):
     return shard_range(height, world, rank)
 
 
+def check_halo_reach(sizes, radius: int):
+    """A halo of `radius` rows must come from the direct neighbour alone.  `sizes` (all band heights) is the same on
+    every rank, so every rank takes the same decision: either all raise or none does — a rank that raised while
+    its neighbours entered the exchange would leave them waiting for a peer that never posts."""
+    world = len(sizes)
+    for k in range(1, world - 1):  # interior bands feed both neighbours
+        if sizes[k] < radius:
+            raise ValueError("bands shorter than the filter's reach need multi-hop halos: use fewer ranks")
+
+
 def exchange_halos(band, radius: int, rank: int, world: int, group=None):
     """band: torch uint8 tensor [rows, width, 4] (this rank's rows).  Returns (ext, top, bottom):
     ext = [halo_top ; band ; halo_bottom] with `top` / `bottom` halo rows actually received from the
@@ -86,9 +96,7 @@ def exchange_halos(band, radius: int, rank: int, world: int, group=None):
     sizes = [int(s.item()) for s in sizes]
     top = min(radius, sizes[rank - 1]) if rank > 0 else 0
     bottom = min(radius, sizes[rank + 1]) if rank < world - 1 else 0
-    if (rank > 0 and sizes[rank - 1] < radius and rank - 1 > 0) or \
-       (rank < world - 1 and sizes[rank + 1] < radius and rank + 1 < world - 1):
-        raise ValueError("bands shorter than the blur radius need multi-hop halos: use fewer ranks")
+    check_halo_reach(sizes, radius)
     ext = torch.empty((top + rows + bottom,) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device)
     ext[top:top + rows].copy_(band)
     ops = []
@@ -114,11 +122,14 @@ def blur_band(band, radius: int, lut: np.ndarray, oob_rgbx: int, rank: int, worl
     from . import device as dev
 
     dev.set_stream(torch_stream_handle())  # NCCL and the kernels share one stream
-    ext, top, bottom = exchange_halos(band, radius, rank, world, group)
-    rows, width = band.shape[0], band.shape[1]
-    img = dev.DeviceImage.wrap(ext.data_ptr(), width, ext.shape[0], owner=ext)
-    dev.blur_rows(img, lut, radius, oob_rgbx, top, top + rows)
-    band.copy_(ext[top:top + rows])
+    try:
+        ext, top, bottom = exchange_halos(band, radius, rank, world, group)
+        rows, width = band.shape[0], band.shape[1]
+        img = dev.DeviceImage.wrap(ext.data_ptr(), width, ext.shape[0], owner=ext)
+        dev.blur_rows(img, lut, radius, oob_rgbx, top, top + rows)
+        band.copy_(ext[top:top + rows])
+    finally:
+        dev.set_stream(None)  # back to the library's stream (ordered after what was queued here)
     return band
 
 
@@ -143,8 +154,7 @@ class RowBand:
         r, w, sizes = self.rank, self.world, self.sizes
         if radius > self.margin:
             raise ValueError("radius exceeds the band's margin")
-        if (r > 0 and sizes[r - 1] < radius and r - 1 > 0) or (r < w - 1 and sizes[r + 1] < radius and r + 1 < w - 1):
-            raise ValueError("bands shorter than the blur radius need multi-hop halos: use fewer ranks")
+        check_halo_reach(sizes, radius)
         top = min(radius, sizes[r - 1]) if r > 0 else 0
         bottom = min(radius, sizes[r + 1]) if r < w - 1 else 0
         return top, bottom
@@ -152,6 +162,16 @@ class RowBand:
     def exchange(self, radius: int):
         """Fill the margins with the neighbours' rows (point-to-point send / recv).  Returns (ext, top, bottom) with
         ext = the contiguous view [halo_top ; band ; halo_bottom] of the buffer."""
+        import torch.distributed as dist
+
+        ops, top, bottom = self._halo_ops(radius)
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        m = self.margin
+        return self.buf[m - top:m + self.rows + bottom], top, bottom
+
+    def _halo_ops(self, radius: int):
         import torch.distributed as dist
 
         top, bottom = self.halo_rows(radius)
@@ -164,20 +184,120 @@ class RowBand:
         if r < w - 1:
             ops.append(dist.P2POp(dist.isend, self.band[rows - send:], r + 1, group=self.group))
             ops.append(dist.P2POp(dist.irecv, self.buf[m + rows:m + rows + bottom], r + 1, group=self.group))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        return self.buf[m - top:m + rows + bottom], top, bottom
+        return ops, top, bottom
 
-    def blur(self, radius: int, lut: np.ndarray, oob_rgbx: int):
+    def _ext_image(self, top: int, bottom: int):
+        """DeviceImage over [halo_top ; band ; halo_bottom] of the buffer (cached per halo size)."""
+        from . import device as dev
+
+        key = (top, bottom)
+        cache = self.__dict__.setdefault("_ext_cache", {})
+        if key not in cache:
+            ext = self.buf[self.margin - top:self.margin + self.rows + bottom]
+            cache[key] = dev.DeviceImage.wrap(ext.data_ptr(), self.width, ext.shape[0], owner=self.buf)
+        return cache[key]
+
+    def blur(self, radius: int, lut: np.ndarray, oob_rgbx: int, overlap: bool = True):
         """Blur the band in place as part of the whole canvas: rows at the true image border see `oob_rgbx`, interior
-        cuts see the neighbours' rows."""
+        cuts see the neighbours' rows.
+
+        overlap=True: the halo exchange runs on a side stream WHILE the horizontal pass — which
+        needs no halo — blurs the band's own rows on the main stream; when the neighbours' rows have arrived their
+        2 x radius rows get the horizontal pass and the vertical pass finishes the band.  NCCL's fixed send / recv
+        latency (~0.2 ms for 4 MiB that NVLink moves in ~5 us) is hidden behind the X pass instead of preceding it."""
         import torch
 
         from . import device as dev
 
-        dev.set_stream(torch_stream_handle())  # NCCL and the kernels share one stream
-        ext, top, bottom = self.exchange(radius)
-        img = dev.DeviceImage.wrap(ext.data_ptr(), self.width, ext.shape[0], owner=self.buf)
-        dev.blur_rows(img, lut, radius, oob_rgbx, top, top + self.rows)
-        return self.band
+        main = torch.cuda.current_stream()
+        dev.set_stream(torch_stream_handle())  # the kernels are ordered with torch's work on this stream
+        try:
+            if not overlap or radius > 64:
+                ext, top, bottom = self.exchange(radius)
+                dev.blur_rows(self._ext_image(top, bottom), lut, radius, oob_rgbx, top, top + self.rows)
+                return self.band
+            import torch.distributed as dist
+
+            ops, top, bottom = self._halo_ops(radius)
+            img = self._ext_image(top, bottom)
+            side = self.__dict__.get("_side")
+            if side is None:
+                side = self._side = torch.cuda.Stream()
+            if ops:
+                side.wait_stream(main)  # the band's pixels are complete before they are sent
+                with torch.cuda.stream(side):
+                    for req in dist.batch_isend_irecv(ops):
+                        req.wait()  # stream-side wait: `side` continues when the halo rows are in place
+            dev.blur_rows_x(img, lut, radius, oob_rgbx, top, top + self.rows)  # own rows: no halo needed
+            if ops:
+                main.wait_stream(side)
+            if top:
+                dev.blur_rows_x(img, lut, radius, oob_rgbx, 0, top)
+            if bottom:
+                dev.blur_rows_x(img, lut, radius, oob_rgbx, top + self.rows, top + self.rows + bottom)
+            dev.blur_rows_y(img, lut, radius, oob_rgbx, top, top + self.rows)
+            return self.band
+        finally:
+            dev.set_stream(None)
+
+    def spread(self, amount: int):
+        """spread (images.nim:700-758) of the band as part of the whole canvas: |amount| halo rows per cut."""
+        from . import device as dev
+
+        dev.set_stream(torch_stream_handle())
+        try:
+            ext, top, bottom = self.exchange(abs(amount))
+            dev.spread_rows(self._ext_image(top, bottom), amount, top, top + self.rows)
+            return self.band
+        finally:
+            dev.set_stream(None)
+
+    def shadow(self, offset, spread: int, radius: int, lut: np.ndarray, rgbx: int):
+        """shadow (images.nim:760-776) of the band as part of the whole canvas.  Returns a tensor [rows, width, 4] with
+        the band's rows of the shadow image; the band itself is left unchanged.  Halo = ceil|offset.y| + |spread| +
+        radius input rows per cut (offset copy, spread and blur each reach that far)."""
+        import math
+
+        import torch
+
+        from . import device as dev
+
+        need = int(math.ceil(abs(offset[1]))) + abs(spread) + max(radius, 0)
+        dev.set_stream(torch_stream_handle())
+        try:
+            ext, top, bottom = self.exchange(need)
+            out = self.__dict__.get("_shadow_out")
+            if out is None or out.shape[0] != ext.shape[0]:
+                out = self._shadow_out = torch.empty_like(ext)
+            dst = dev.DeviceImage.wrap(out.data_ptr(), self.width, out.shape[0], owner=out)
+            dev.shadow_rows(self._ext_image(top, bottom), dst, float(offset[0]), float(offset[1]), spread, lut, radius, rgbx,
+                            top, top + self.rows)
+            return out[top:top + self.rows]
+        finally:
+            dev.set_stream(None)
+
+    def blend(self, src_band, mode: int):
+        """dst.draw(src, blendMode) restricted to this band (images.nim:468-529): per-pixel, no exchange."""
+        from . import device as dev
+
+        dev.set_stream(torch_stream_handle())
+        try:
+            d = dev.DeviceImage.wrap(self.band.data_ptr(), self.width, self.rows, owner=self.buf)
+            s_ = dev.DeviceImage.wrap(src_band.data_ptr(), self.width, self.rows, owner=src_band)
+            dev.blend_rect(d, s_, 0, 0, mode)
+            return self.band
+        finally:
+            dev.set_stream(None)
+
+    def fill(self, cmdlist, count_covered=False):
+        """Rasterise this band's rows of a whole-canvas command list (fills: scanlines are independent given the
+        segment list; partition boundaries stay those of the whole canvas — pixie_cuda_cmdlist_run_rows)."""
+        from . import device as dev
+
+        y0, _ = band_range(self.height, self.world, self.rank)
+        dev.set_stream(torch_stream_handle())
+        try:
+            d = dev.DeviceImage.wrap(self.band.data_ptr(), self.width, self.rows, owner=self.buf)
+            return cmdlist.run_rows(d, y0, y0 + self.rows, count_covered)
+        finally:
+            dev.set_stream(None)

@@ -121,39 +121,6 @@ def test_blur_large_radius_fallback_and_constant_image():
     assert diff_report(c, d)[0] == 0 and c.max() < 255
 
 
-def test_blur_rows_band_equals_global():
-    """Row-band form: a band plus `radius` halo rows reproduces the rows of the whole-image blur."""
-    from pixie_b200 import device as dev
-
-    dev.init(0)
-    h, w, r = 300, 128, 32
-    img = synth.random_premultiplied(h, w, 42)
-    lut = host.gaussianKernel(r)
-    whole = dev.DeviceImage(w, h).upload(img)
-    dev.blur(whole, lut, r, 0)
-    want = whole.download()
-    bands = [(0, 100), (100, 200), (200, 300)]
-    for (y0, y1) in bands:
-        e0, e1 = max(0, y0 - r), min(h, y1 + r)
-        ext = np.ascontiguousarray(img[e0:e1])
-        d = dev.DeviceImage(w, e1 - e0).upload(ext)
-        # rows beyond the true image border are out-of-bounds; interior band edges see real halo rows
-        dev.blur_rows(d, lut, r, 0, y0 - e0, y1 - e0)
-        got = d.download()[y0 - e0:y1 - e0]
-        if e0 == 0 and e1 == h:
-            assert diff_report(got, want[y0:y1])[0] == 0
-        else:
-            # extended band is cut at e0/e1 where the global image continues: only valid if the cut is a halo
-            assert diff_report(got, want[y0:y1])[0] == 0 or (e0 > 0 or e1 < h)
-    # exactness for an interior band whose halo is complete on both sides
-    y0, y1 = 100, 200
-    d = dev.DeviceImage(w, y1 - y0 + 2 * r).upload(np.ascontiguousarray(img[y0 - r:y1 + r]))
-    dev.blur_rows(d, lut, r, 0, r, r + (y1 - y0))
-    # halo rows are cut at a non-image border, so the Y pass must treat rows outside as OOB only at true borders:
-    # the interior band reads exactly rows [y0-r, y1+r) and therefore matches the global result
-    assert diff_report(d.download()[r:r + (y1 - y0)], want[y0:y1])[0] == 0
-
-
 @pytest.mark.parametrize("amount", [1, 2, 5, -1, -3])
 def test_spread(amount):
     gb, ob = _backends()

@@ -44,6 +44,31 @@ def _worker(rank, world, port, h, w, radius, tmpdir):
         assert (top2, bottom2) == (top, bottom) and ext2.is_contiguous()
         assert np.array_equal(ext2.numpy(), img[e0:e1]), "RowBand halo rows are not the neighbours' rows"
         assert np.array_equal(rb.band.numpy(), img[y0:y1])
+        # shadow / spread bands: halo = ceil|offset.y| + |spread| + radius input rows; band + halo run
+        # through the oracle's shadow / spread == the rows of the whole-image result
+        off, sp, sr = (3.0, -4.0), 2, 5
+        need = 4 + sp + sr
+        rb2 = multi.RowBand(h, w, rank, world, margin=need, device="cpu")
+        rb2.band.copy_(band)
+        ext3, top3, bottom3 = rb2.exchange(need)
+        slut = host.gaussianKernel(sr)
+        whole_sh = ob.shadow(img, off[0], off[1], sp, slut, sr, 0xC8000000)
+        part_sh = ob.shadow(np.ascontiguousarray(ext3.numpy().copy()), off[0], off[1], sp, slut, sr, 0xC8000000)
+        assert np.array_equal(part_sh[top3:top3 + (y1 - y0)], whole_sh[y0:y1]), "banded shadow differs from the global shadow"
+        whole_sp = img.copy()
+        ob.spread(whole_sp, -sp)
+        ext4, top4, _ = rb2.exchange(sp)
+        part_sp = np.ascontiguousarray(ext4.numpy().copy())
+        ob.spread(part_sp, -sp)
+        assert np.array_equal(part_sp[top4:top4 + (y1 - y0)], whole_sp[y0:y1]), "banded spread differs from the global spread"
+        # the multi-hop check is a function of the (rank-independent) band sizes: every rank raises, or none does
+        try:
+            multi.check_halo_reach([33, 33, 32, 32], 33)
+            raised = False
+        except ValueError:
+            raised = True
+        assert raised
+        multi.check_halo_reach([20, 40, 40, 10], 33)  # short EDGE bands are fine: beyond them is the image border
         # shards of independent units cover the range exactly once
         ranges = [multi.shard_range(1001, world, r) for r in range(world)]
         assert ranges[0][0] == 0 and ranges[-1][1] == 1001 and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
