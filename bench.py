@@ -164,19 +164,58 @@ def workload_config(size, arrays):
             "partition": "independent canvas per GPU"}
 
 
-def extras_single_gpu(dev, peak):
-    """BASELINE configs 3 and 4 on one GPU: blend 8192^2 and blur r=32 / shadow 16384^2 (GB/s vs HBM)."""
-    from pixie_b200 import host, synth
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _threaded(fn, pieces, cores):
+    """Run fn(piece) for every piece on `cores` host threads (the oracle's ctypes calls release the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        list(ex.map(fn, pieces))
+
+
+def _bands(rows, parts):
+    parts = max(1, min(parts, rows))
+    return [(rows * k // parts, rows * (k + 1) // parts) for k in range(parts)]
+
+
+def _parity(n, bad, mx):
+    return {"pixels_compared": int(n), "mismatching": int(bad), "max_abs_delta": int(mx), "fraction": (bad / n if n else None)}
+
+
+def extras_blend(dev, peak):
+    """BASELINE config 3: all 20 modes, 8192^2 dst / src + A8 coverage mask (13 B/px; Overwrite 9 B/px).
+    Beside every device time: oracle parity on sampled rows, the oracle's CPU time (1 thread and all host cores, on a
+    512-row slab of the same inputs), and for four representative modes the end-to-end time through
+    pixie_cuda_blend_rect_masked_host (pinned host pixels in and out)."""
+    from pixie_b200 import synth
     from pixie_b200.common import BLEND_MODE_NAMES
 
-    out = {}
-    # ---- C3: all 20 modes, 8192^2 dst/src + A8 coverage mask (13 B/px; Overwrite 9 B/px)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _windows as W
+    from _oracle import OracleBackend
+
     n = 8192
-    tile = synth.random_premultiplied(512, n, 0x5EED)
-    dst0 = dev.DeviceImage(n, n).upload(np.tile(tile, (n // 512, 1, 1)))
-    src = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 0x5EED + 1), (n // 512, 1, 1)))
-    mask = dev.DeviceImage(n, n, a8=True).upload(np.tile(synth.coverage_mask(512, n, 0x5EED + 2), (n // 512, 1)))
+    cores = _host_cores()
+    h_dst = np.tile(synth.random_premultiplied(512, n, 0x5EED), (n // 512, 1, 1))
+    h_src = np.tile(synth.random_premultiplied(512, n, 0x5EED + 1), (n // 512, 1, 1))
+    h_mask = np.tile(synth.coverage_mask(512, n, 0x5EED + 2), (n // 512, 1))
+    dst0 = dev.DeviceImage(n, n).upload(h_dst)
+    src = dev.DeviceImage(n, n).upload(h_src)
+    mask = dev.DeviceImage(n, n, a8=True).upload(h_mask)
     dst = dev.DeviceImage(n, n)
+    slab = 512  # CPU sample: rows [0, slab) of the same inputs
+    ob = OracleBackend(0)
+    pin_d = dev.PinnedBuffer(n * n * 4)
+    pin_s = dev.PinnedBuffer(n * n * 4)
+    pin_m = dev.PinnedBuffer(n * n)
+    pin_s.array[:] = h_src.reshape(-1)
+    pin_m.array[:] = h_mask.reshape(-1)
     blends = {}
     for mode in range(20):
         ms = []
@@ -188,41 +227,175 @@ def extras_single_gpu(dev, peak):
                 ms.append(t)
         t = statistics.median(ms)
         nbytes = n * n * (9 if mode == 17 else 13)
-        blends[BLEND_MODE_NAMES[mode]] = {"ms": round(t, 4), "GB/s": round(nbytes / t / 1e6, 1),
-                                          "frac_hbm": round(nbytes / t / 1e6 / peak, 3)}
-    out["blend_8192_masked"] = {"bytes_per_px": "13 (dst r+w, src r, 1-B coverage); Overwrite 9", "modes": blends}
-    del dst0, src, mask, dst
-    # ---- C4: blur r=32 on 16384^2 (8 B/px algorithmic) + shadow
-    n = 16384
-    img = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 0xB10B), (n // 512, 1, 1)))
-    lut = host.gaussianKernel(32)
+        cnt, bad, mx = W.check_blend_rows(dst, h_dst, h_src, h_mask, mode, [(0, 4), (4094, 4098), (n - 4, n)])
+        # CPU: the oracle's blendRect on the slab, one thread, then all cores by row bands (blends are order-free)
+        work = h_dst[:slab].copy()
+        t0 = time.perf_counter()
+        ob.blend_rect_masked(work, h_src[:slab], h_mask[:slab], 0, 0, mode)
+        t1 = time.perf_counter() - t0
+        work[:] = h_dst[:slab]
+
+        def band(b, mode=mode, work=work):
+            OracleBackend(0).blend_rect_masked(work[b[0]:b[1]], np.ascontiguousarray(h_src[b[0]:b[1]]),
+                                               np.ascontiguousarray(h_mask[b[0]:b[1]]), 0, 0, mode)
+
+        t0 = time.perf_counter()
+        _threaded(band, _bands(slab, cores), cores)
+        tn = time.perf_counter() - t0
+        entry = {"ms": round(t, 4), "GB/s": round(nbytes / t / 1e6, 1), "frac_hbm": round(nbytes / t / 1e6 / peak, 3),
+                 "Mpixel/s": round(n * n / t / 1e3, 1), "parity_vs_oracle": _parity(cnt, bad, mx),
+                 "cpu_Mpixel/s_1_thread": round(slab * n / t1 / 1e6, 1),
+                 f"cpu_Mpixel/s_{cores}_threads": round(slab * n / tn / 1e6, 1)}
+        if mode in (0, 7, 3, 12):  # Normal, Overlay, ColorBurn, Hue: end to end through the *_host entry point
+            es = []
+            for it in range(3):
+                pin_d.array[:] = h_dst.reshape(-1)
+                t0 = time.perf_counter()
+                dev.check(dev.lib().pixie_cuda_blend_rect_masked_host(pin_d.ptr, n, n, pin_s.ptr, pin_m.ptr, 1, n, n, 0, 0, mode))
+                es.append(time.perf_counter() - t0)
+            te = statistics.median(es[1:])
+            got = pin_d.array.reshape(n, n, 4)
+            want = h_dst[4094:4098].copy()
+            ob.blend_rect_masked(want, np.ascontiguousarray(h_src[4094:4098]), np.ascontiguousarray(h_mask[4094:4098]), 0, 0, mode)
+            entry["e2e"] = {"ms": round(te * 1e3, 2), "Mpixel/s": round(n * n / te / 1e6, 1), "h2d_bytes": n * n * 9,
+                            "d2h_bytes": n * n * 4, "rows_equal_oracle": bool(np.array_equal(got[4094:4098], want))}
+        blends[BLEND_MODE_NAMES[mode]] = entry
+    return {"bytes_per_px": "13 (dst r+w, src r, 1-B coverage); Overwrite 9",
+            "cpu_baseline": {"kind": "port", "cores": cores,
+                             "sample": f"rows [0, {slab}) of the same 8192-wide inputs ({slab * n} px) per mode: the oracle's "
+                                       "blendRect + mask composite, 1 thread and all host cores by row bands"},
+            "e2e": "pixie_cuda_blend_rect_masked_host, pinned host dst/src/mask in, dst out, wall clock (Normal, Overlay, ColorBurn, Hue)",
+            "modes": blends}
+
+
+def extras_blur_shadow(dev, peak):
+    """BASELINE config 4 on one GPU: blur r=32 and the drop shadow on 16384^2 (8 B/px algorithmic), with oracle parity
+    through windows (corners, tile seams), the oracle's CPU time on a 2048^2 crop, and end to end through
+    pixie_cuda_blur_host / pixie_cuda_shadow_host."""
+    from pixie_b200 import host, synth
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _windows as W
+    from _oracle import OracleBackend
+
+    out = {}
+    n, r = 16384, 32
+    cores = _host_cores()
+    h_img = np.tile(synth.random_premultiplied(512, n, 0xB10B), (n // 512, 1, 1))
+    img = dev.DeviceImage(n, n).upload(h_img)
+    work = dev.DeviceImage(n, n)
+    lut = host.gaussianKernel(r)
     ms, msx, msy = [], [], []
-    for it in range(3):
+    for it in range(4):
+        work.copy_from(img)
         dev.timer_begin()
-        dev.blur(img, lut, 32, 0)
+        dev.blur(work, lut, r, 0)
         t = dev.timer_end()
         if it:
             ms.append(t)
             msx.append(dev.profile_read(dev.PROF_BLUR_X))
             msy.append(dev.profile_read(dev.PROF_BLUR_Y))
     t = statistics.median(ms)
-    out["blur_r32_16384"] = {"ms": round(t, 3), "x_pass_ms": round(statistics.median(msx), 3),
-                             "y_pass_ms": round(statistics.median(msy), 3),
-                             "GB/s": round(n * n * 8 / t / 1e6, 1), "frac_hbm": round(n * n * 8 / t / 1e6 / peak, 3),
-                             "bytes_per_px": 8, "Gtaps_per_s": round(n * n * 4 * 2 * 65 / t / 1e6, 1),
-                             "traffic_bytes_per_px": 16,
-                             "bound": "tensor-core Toeplitz contraction (blur_mma.cu, bit-exact): bound by the HMMA pipe and "
-                                      "instruction issue (staging permutes, stores); two passes move 16 B/px, the 8 B/px "
-                                      "figure is the single-pass ideal of SURVEY 8(d)"}
-    dstimg = dev.DeviceImage(n, n)
+    cnt, bad, mx = W.check_blur_windows(work, h_img, lut, r, 0, W.corner_and_seam_windows(n, n))
+    # structured case (SURVEY 8d C4): an opaque rectangle on a transparent canvas
+    h_rect = np.zeros((n, n, 4), np.uint8)
+    h_rect[3000:9000, 5000:14000] = (200, 100, 50, 255)
+    work.upload(h_rect)
+    dev.timer_begin()
+    dev.blur(work, lut, r, 0)
+    t_rect = dev.timer_end()
+    c2, b2, m2 = W.check_blur_windows(work, h_rect, lut, r, 0, [(2976, 3024, 4976, 5024), (8976, 9024, 13976, 14024), (0, 48, 0, 48)])
+    del h_rect
+    # CPU: the literal oracle (scalar, O(taps) like the reference) on a 2048^2 crop, 1 thread, then all cores by row
+    # bands with `radius` halo rows each (every band recomputes the X pass of its halo)
+    c = 2048
+    crop = np.ascontiguousarray(h_img[:c, :c])
+    ob = OracleBackend(0)
+    a = crop.copy()
+    t0 = time.perf_counter()
+    ob.blur(a, lut, r, 0)
+    t1 = time.perf_counter() - t0
+
+    def band(b):
+        e0, e1 = max(0, b[0] - r), min(c, b[1] + r)
+        part = crop[e0:e1].copy()
+        OracleBackend(0).blur(part, lut, r, 0)
+
+    t0 = time.perf_counter()
+    _threaded(band, _bands(c, cores), cores)
+    tn = time.perf_counter() - t0
+    # end to end: pinned host pixels in, blurred pixels out
+    pin = dev.PinnedBuffer(n * n * 4)
+    es = []
+    for it in range(3):
+        pin.array[:] = h_img.reshape(-1)
+        t0 = time.perf_counter()
+        dev.check(dev.lib().pixie_cuda_blur_host(pin.ptr, n, n, np.ascontiguousarray(lut, np.uint16).ctypes.data, r, 0))
+        es.append(time.perf_counter() - t0)
+    te = statistics.median(es[1:])
+    got = pin.array.reshape(n, n, 4)
+    e2e_ok = bool(np.array_equal(got[8190:8194], work_rows(dev, img, work, lut, r, 8190, 8194)))
+    out["blur_r32_16384"] = {
+        "ms": round(t, 3), "x_pass_ms": round(statistics.median(msx), 3), "y_pass_ms": round(statistics.median(msy), 3),
+        "GB/s": round(n * n * 8 / t / 1e6, 1), "frac_hbm": round(n * n * 8 / t / 1e6 / peak, 3), "bytes_per_px": 8,
+        "Mpixel/s": round(n * n / t / 1e3, 1), "Gtaps_per_s": round(n * n * 4 * 2 * 65 / t / 1e6, 1),
+        "parity_vs_oracle": _parity(cnt, bad, mx),
+        "structured_rect_on_transparent": {"ms": round(t_rect, 3), "parity_vs_oracle": _parity(c2, b2, m2)},
+        "cpu_baseline": {"kind": "port", "cores": cores, "Mpixel/s_1_thread": round(c * c / t1 / 1e6, 2),
+                         f"Mpixel/s_{cores}_threads": round(c * c / tn / 1e6, 2),
+                         "sample": f"the oracle's scalar blur (65 taps x 4 channels x 2 passes per pixel, as the reference) on the "
+                                   f"{c}^2 top-left crop of the same image: 1 thread, and {cores} threads by row bands with {r} halo rows"},
+        "e2e": {"ms": round(te * 1e3, 2), "Mpixel/s": round(n * n / te / 1e6, 1), "h2d_bytes": n * n * 4, "d2h_bytes": n * n * 4,
+                "call": "pixie_cuda_blur_host (pinned host pixels)", "rows_equal_device_path": e2e_ok},
+        "bound": "see DESIGN.md section 4 (blur)"}
+    # ---- shadow: offset (8, 8), spread 4, blur 32, rgba(0, 0, 0, 200)
+    h_src = h_img.copy()
+    h_src[: n // 3] = 0
+    img.upload(h_src)
+    col = 0xC8000000
     ms = []
-    for it in range(2):
+    for it in range(3):
         dev.timer_begin()
-        dev.shadow(img, dstimg, 8, 8, 4, lut, 32, 0xC8000000)
+        dev.shadow(img, work, 8.0, 8.0, 4, lut, r, col)
         ms.append(dev.timer_end())
-    out["shadow_16384"] = {"ms": round(ms[-1], 3), "GB/s": round(n * n * 8 / ms[-1] / 1e6, 1)}
-    del img, dstimg
-    # ---- SURVEY 8(f) rows built this round: draw with a transform, minifyBy2, gradient fill (8192^2)
+    ts = statistics.median(ms[1:])
+    cnt, bad, mx = W.check_shadow_windows(work, h_src, (8, 8), 4, lut, r, col,
+                                          W.corner_and_seam_windows(n, n, seams=((n // 3, 4096), (8192, 8192 + 32))))
+    crop = np.ascontiguousarray(h_src[n // 3 - 1024:n // 3 + 1024, :c])
+    t0 = time.perf_counter()
+    ob.shadow(crop, 8.0, 8.0, 4, lut, r, col)
+    t1 = time.perf_counter() - t0
+    pin2 = dev.PinnedBuffer(n * n * 4)
+    pin.array[:] = h_src.reshape(-1)
+    es = []
+    for it in range(2):
+        t0 = time.perf_counter()
+        dev.check(dev.lib().pixie_cuda_shadow_host(pin.ptr, pin2.ptr, n, n, 8.0, 8.0, 4, np.ascontiguousarray(lut, np.uint16).ctypes.data, r, col))
+        es.append(time.perf_counter() - t0)
+    te = es[-1]
+    got = pin2.array.reshape(n, n, 4)
+    e2e_ok = bool(np.array_equal(got[n // 3 - 2:n // 3 + 2], work.download_rows(n // 3 - 2, n // 3 + 2)))
+    out["shadow_16384"] = {
+        "ms": round(ts, 3), "GB/s": round(n * n * 8 / ts / 1e6, 1), "frac_hbm": round(n * n * 8 / ts / 1e6 / peak, 3),
+        "Mpixel/s": round(n * n / ts / 1e3, 1), "parity_vs_oracle": _parity(cnt, bad, mx),
+        "cpu_baseline": {"kind": "port", "cores": 1, "Mpixel/s_1_thread": round(crop.shape[0] * crop.shape[1] / t1 / 1e6, 2),
+                         "sample": f"the oracle's shadow on a {crop.shape[0]}x{crop.shape[1]} crop across the shape's edge, 1 thread"},
+        "e2e": {"ms": round(te * 1e3, 2), "Mpixel/s": round(n * n / te / 1e6, 1), "h2d_bytes": n * n * 4, "d2h_bytes": n * n * 4,
+                "call": "pixie_cuda_shadow_host (pinned host pixels)", "rows_equal_device_path": e2e_ok}}
+    return out
+
+
+def work_rows(dev, img, work, lut, r, y0, y1):
+    """Rows [y0, y1) of blur(img) on the device path (for the e2e cross-check)."""
+    work.copy_from(img)
+    dev.blur(work, lut, r, 0)
+    return work.download_rows(y0, y1)
+
+
+def extras_draw_paint(dev, peak):
+    """draw with a transform, minifyBy2, gradient fill (8192^2)."""
+    from pixie_b200 import host, synth
+
     n = 8192
     f = np.float32
     dst0 = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 0x5EED), (n // 512, 1, 1)))
@@ -254,21 +427,31 @@ def extras_single_gpu(dev, peak):
     ]:
         t = timed(fn)
         draws[name] = {"ms": round(t, 4), "GB/s": round(nbytes / t / 1e6, 1), "frac_hbm": round(nbytes / t / 1e6 / peak, 3)}
-    out["draw_paint_8192"] = {"bytes_per_px": "draw 12 (dst r+w, src r); scale 0.5: minify 5/src px + draw over the covered quarter; "
-                                              "gradient 4 (write)", "ops": draws}
-    return out
+    return {"bytes_per_px": "draw 12 (dst r+w, src r); scale 0.5: minify 5/src px + draw over the covered quarter; "
+                            "gradient 4 (write)", "ops": draws}
 
 
-def icons_batch(dev, rank, world, n_icons=1024, size=512):
+def icons_batch(dev, rank, world, n_icons=1024, size=512, cpu_sample=128):
     """BASELINE config 5 (scaled to fit the time budget): synthetic icons, 512^2 each, every icon its own
-    layer of one device allocation, this rank's contiguous shard, ONE launch pair for the whole shard;
-    results stay on the device (checksum), algorithmic bytes 8 B x covered px + 18 B x segments."""
+    layer of one device allocation, this rank's contiguous shard, ONE launch set for the whole shard;
+    results stay on the device (checksum), algorithmic bytes 8 B x covered px + 18 B x segments.
+    `ms` = device time of one run of the resident list (count pass included); `e2e` = wall clock from host segment
+    arrays to the on-device checksum: command-list creation (H2D of the segments, count / scan kernels, readback of
+    the sizes) + the run + the checksum's 8-byte D2H.  CPU: the oracle over a sample of the same icons."""
     from pixie_b200 import multi, synth
     from pixie_b200.device import FillBatch
 
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _util import oracle_render_batch
+
     b0, b1 = multi.shard_range(n_icons * world, world, rank)
     batch = FillBatch()
+    per_icon = []
     for i in range(b0, b1):
+        one = FillBatch()
+        synth.icon_fills(i, size, 0, one)
+        if i - b0 < cpu_sample:
+            per_icon.append(one.arrays())
         synth.icon_fills(i, size, i - b0, batch)
     arrays = batch.arrays()
     img = dev.DeviceImage(size, size, b1 - b0)
@@ -284,9 +467,44 @@ def icons_batch(dev, rank, world, n_icons=1024, size=512):
             ms.append(t)
     t = statistics.median(ms)
     nseg = int(arrays["seg_offsets"][-1])
+    checksum = img.checksum()
+    es = []
+    for it in range(3):
+        img.fill(0)
+        dev.sync()
+        t0 = time.perf_counter()
+        cl2 = dev.CmdList(size, size, b1 - b0, arrays)
+        cl2.run(img)
+        c2 = img.checksum()
+        es.append(time.perf_counter() - t0)
+        del cl2
+    te = statistics.median(es[1:])
+    # parity + CPU baseline: the oracle renders the first `cpu_sample` icons (independent canvases: one icon per
+    # thread task), the GPU's layers of the same icons must be byte-equal
+    cores = _host_cores()
+    results = [None] * len(per_icon)
+
+    def one_icon(k):
+        results[k] = oracle_render_batch(per_icon[k], size, size)
+
+    one_icon(0)
+    t0 = time.perf_counter()
+    _threaded(one_icon, range(len(per_icon)), cores)
+    tc = time.perf_counter() - t0
+    cov_cpu = sum(r[1] for r in results)
+    layers = img.download().reshape(b1 - b0, size, size, 4)
+    bad = sum(int((layers[k] != results[k][0][0]).any(axis=-1).sum()) for k in range(len(per_icon)))
     return {"icons": b1 - b0, "fills": len(arrays["rgbx"]), "segments": nseg, "covered_px": int(covered), "ms": round(t, 3),
             "Mpixel/s": round(covered / t / 1e3, 1), "icons_per_s": round((b1 - b0) / t * 1e3),
-            "GB/s_algorithmic": round((8 * covered + 18 * nseg) / t / 1e6, 1), "checksum": img.checksum()}
+            "GB/s_algorithmic": round((8 * covered + 18 * nseg) / t / 1e6, 1), "checksum": checksum,
+            "e2e": {"ms": round(te * 1e3, 3), "icons_per_s": round((b1 - b0) / te), "Mpixel/s": round(covered / te / 1e6, 1),
+                    "h2d_bytes": nseg * 18 + len(arrays["rgbx"]) * 56, "d2h_bytes": 8 + 24,
+                    "call": "pixie_cuda_cmdlist_create + _run + _image_checksum from host segment arrays",
+                    "checksum_equal": bool(c2 == checksum)},
+            "parity_vs_oracle": _parity(len(per_icon) * size * size, bad, 0 if bad == 0 else 255),
+            "cpu_baseline": {"kind": "port", "cores": cores, "icons_per_s": round(len(per_icon) / tc, 1),
+                             "Mpixel/s": round(cov_cpu / tc / 1e6, 2),
+                             "sample": f"the first {len(per_icon)} icons of the same shard rendered by the oracle, one icon per task on {cores} host threads"}}
 
 
 def icons_sharded(dev, dist, rank, world, per_rank, size=512, chunk=2048):
@@ -522,11 +740,15 @@ def run_ours(args):
                          "canvas are order-dependent; the reference is single-threaded)",
                "covered_px_equal_to_gpu": bool(ccov == covered)}
         if not args.no_extras:
-            try:
-                extras = extras_single_gpu(dev, peak)
-                extras["icons_512_batch"] = icons_batch(dev, 0, 1)
-            except Exception as e:  # extras never block the headline line
-                extras = {"error": repr(e)}
+            extras = {}
+            for key, fn in [("blend_8192_masked", lambda: extras_blend(dev, peak)), ("blur_shadow_16384", lambda: extras_blur_shadow(dev, peak)),
+                            ("draw_paint_8192", lambda: extras_draw_paint(dev, peak)), ("icons_512_batch", lambda: icons_batch(dev, 0, 1))]:
+                try:  # extras never block the headline line
+                    extras[key] = fn()
+                except Exception as e:
+                    import traceback
+
+                    extras[key] = {"error": repr(e), "trace": traceback.format_exc()[-600:]}
 
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -34,7 +34,7 @@ def _crop(inp, win, reach):
     y0, y1, x0, x1 = win
     h, w = inp.shape[:2]
     cy0, cy1, cx0, cx1 = max(0, y0 - reach), min(h, y1 + reach), max(0, x0 - reach), min(w, x1 + reach)
-    return np.ascontiguousarray(inp[cy0:cy1, cx0:cx1]), (y0 - cy0, y1 - cy0, x0 - cx0, x1 - cx0)
+    return inp[cy0:cy1, cx0:cx1].copy(), (y0 - cy0, y1 - cy0, x0 - cx0, x1 - cx0)
 
 
 def _gpu_window(dimg, win):
@@ -88,7 +88,7 @@ def check_blend_rows(ddst, dst_in, src, mask, mode, row_ranges):
     ob = OracleBackend(0)
     n = bad = mx = 0
     for (y0, y1) in row_ranges:
-        want = np.ascontiguousarray(dst_in[y0:y1])
+        want = dst_in[y0:y1].copy()  # a slice of a contiguous array IS contiguous: ascontiguousarray would alias it
         s = np.ascontiguousarray(src[y0:y1])
         if mask is None:
             ob.blend_rect(want, s, 0, 0, mode)
