@@ -356,6 +356,7 @@ static int launch_f32(ConvArgs a, Image* im, void* tmp, const uint16_t* lut_d, i
 }
 
 int blur_mma(Image* im, void* tmp, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1, int phase);  // blur_mma.cu
+int blur_tc(const px_t* src, px_t* dst, int w, int h, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1);  // blur_tc.cu
 
 // phase 0: the whole blur of rows [y0, y1); 1 / 2: only its X pass over rows [y0, y1) / only its Y pass (the two
 // halves of a row-band blur whose halo exchange overlaps the X pass, pixie_cuda_blur_rows_x / _y)
@@ -370,9 +371,31 @@ static int blur_impl(Image* im, const uint16_t* lut_host, int radius, uint32_t o
   const int ntaps = 2 * radius + 1;
   void *tmp, *lut_d, *pin;
   if (int rc = get_scratch(0, im->bytes(), &tmp)) return rc;
-  {  // radii 1..64 with an exactly representable contraction go to the tensor cores (blur_mma.cu);
+  static const char* force = getenv("PIXIE_CUDA_BLUR");  // "mma": the two-pass mma.sync kernels, "cores": CUDA cores
+  if (phase == 0 && !force) {
+    // Radii 1..32: ONE fused pass on the tcgen05 tensor cores (blur_tc.cu).  It cannot run in place (strips read
+    // their neighbours' columns), so the result goes to a second buffer: a whole-image blur of a library-owned
+    // image takes a fresh buffer from the stream-ordered pool and the handle simply switches to it; row bands and
+    // caller-owned (wrapped) images get their rows copied back.
+    const bool swap = im->owned && y0 == 0 && y1 == im->h;
+    void* out = tmp;
+    if (swap) PX_CUDA(cudaMallocAsync(&out, im->bytes(), r.stream));
+    const int rc = blur_tc((const px_t*)im->data, (px_t*)out, im->w, im->h, lut_host, radius, oob, y0, y1);
+    if (rc == 0) {
+      if (swap) {
+        PX_CUDA(cudaFreeAsync(im->data, r.stream));
+        im->data = (uint8_t*)out;
+      } else {
+        const size_t rowBytes = (size_t)im->w * 4;
+        PX_CUDA(cudaMemcpyAsync(im->data + rowBytes * y0, (uint8_t*)out + rowBytes * y0, rowBytes * (y1 - y0), cudaMemcpyDeviceToDevice, r.stream));
+      }
+      return 0;
+    }
+    if (swap) PX_CUDA(cudaFreeAsync(out, r.stream));
+    if (rc > 0) return rc;
+  }
+  {  // radii up to 64 with an exactly representable contraction: the two-pass mma.sync kernels (blur_mma.cu);
      // PIXIE_CUDA_BLUR=cores keeps the CUDA-core kernels (A/B timing, parity tests of both paths)
-    static const char* force = getenv("PIXIE_CUDA_BLUR");
     if (!(force && strcmp(force, "cores") == 0)) {
       const int rc = blur_mma(im, tmp, lut_host, radius, oob, y0, y1, phase);
       if (rc >= 0) return rc;
