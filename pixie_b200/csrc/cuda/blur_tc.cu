@@ -25,6 +25,9 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -53,6 +56,7 @@ struct TcBlurArgs {
   int y0, y1;  // output rows
   int strips, chunks, chunkRows;
   unsigned* ticket;
+  unsigned long long* dbg;  // PIXIE_CUDA_TC_DEBUG: per-phase cycle sums of worker warp 0 and the two issuers
 };
 
 __constant__ uint16_t c_tc_lut[2 * kTcMaxRadius + 1 + 3];
@@ -73,7 +77,8 @@ PXD uint32_t tc_quant(uint32_t accBits) {  // (acc * 2^24) div 65280 in the low 
 //   barY     Y issuer -> workers   Y MMAs complete: D_y readable
 //   barYFree workers -> Y issuer   Y epilogue has loaded D_y
 // The ring has four slots of 32 rows: the Y MMAs of block i - 1 read slots i - 3 .. i - 1 while the workers convert
-// block i and drain X(i) into slot i % 4.
+// block i and drain X(i) into slot i % 4; D_y is double-buffered so that the workers drain Y(i - 2) while X(i) and
+// Y(i - 1) compute, and the X MMAs commit per output column block so that its epilogue starts while the other runs.
 constexpr int kTcWorkers = 512;
 
 __global__ void __launch_bounds__(kTcWorkers + 64, 1) blur_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcBlurArgs a) {
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(kTcWorkers + 64, 1) blur_tc_kernel(const __gri
   uint8_t* sAx = sToe + kToeBytes;
   uint8_t* sRing = sAx + kAxBytes;
   uint8_t* sRaw = sRing + kRingBytes;
-  __shared__ uint64_t barRaw, barAx, barX, barRing, barY, barYFree;
+  __shared__ uint64_t barRaw, barAx, barX[2], barRing, barY[2], barYFree[2];
   __shared__ uint32_t tmemSlot;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -100,19 +105,22 @@ __global__ void __launch_bounds__(kTcWorkers + 64, 1) blur_tc_kernel(const __gri
   if (tid == 0) {
     mbar_init(&barRaw, 1);
     mbar_init(&barAx, kTcWorkers / 32);
-    mbar_init(&barX, 1);
+    mbar_init(&barX[0], 1);
+    mbar_init(&barX[1], 1);
     mbar_init(&barRing, kTcWorkers / 32);
-    mbar_init(&barY, 1);
-    mbar_init(&barYFree, kTcWorkers / 32);
+    mbar_init(&barY[0], 1);
+    mbar_init(&barY[1], 1);
+    mbar_init(&barYFree[0], kTcWorkers / 32);
+    mbar_init(&barYFree[1], kTcWorkers / 32);
     fence_barrier_init();
     tma_prefetch_desc(&tmap);
   }
-  if (warp == 0) tmem_alloc(&tmemSlot, 256);
+  if (warp == 0) tmem_alloc(&tmemSlot, 512);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = tmemSlot;  // D_x: columns [0, 128), D_y: [128, 256)
+  const uint32_t tmem = tmemSlot;  // D_x: columns [0, 128); D_y (two buffers): [128, 256), [256, 384)
   const int total = a.strips * a.chunks;
 
   if (warp == kTcWorkers / 32) {
@@ -139,19 +147,22 @@ __global__ void __launch_bounds__(kTcWorkers + 64, 1) blur_tc_kernel(const __gri
         tma_load_2d(sRaw, &tmap, &barRaw, x0 - 32, rowBase);
 #pragma unroll 1
         for (int i = 0; i < nb; i++) {
+          const long long w0_ = a.dbg ? clock64() : 0;
           mbar_wait(&barAx, pAx);
           pAx ^= 1;
+          const long long w1_ = a.dbg ? clock64() : 0;
           tc_fence_after_sync();
           if (i + 1 < nb) {
             mbar_arrive_expect_tx(&barRaw, kRawBytes);
             tma_load_2d(sRaw, &tmap, &barRaw, x0 - 32, rowBase + kTcRows * (i + 1));
           }
 #pragma unroll
-          for (int j = 0; j < 2; j++) {
+          for (int j = 0; j < 2; j++) {  // one commit per output column block: its X epilogue starts while the other computes
 #pragma unroll
             for (int s = 0; s < 8; s++) mma_f16_ss(tmem + (uint32_t)(j * 64), ad[j][s], bd[s], idescX, s > 0 ? 1u : 0u);
+            mma_commit(&barX[j]);
           }
-          mma_commit(&barX);
+          if (a.dbg) { atomicAdd(&a.dbg[16], (unsigned long long)(w1_ - w0_)); atomicAdd(&a.dbg[17], (unsigned long long)(clock64() - w1_)); }
         }
       }
     }
@@ -164,22 +175,26 @@ __global__ void __launch_bounds__(kTcWorkers + 64, 1) blur_tc_kernel(const __gri
 #pragma unroll
       for (int s = 0; s < 6; s++) bd[s] = smem_desc_sw128(sToeA + (uint32_t)(s >> 2) * (64u * 128u) + (uint32_t)(s & 3) * 32u, 16, 1024);
       const uint64_t ad0 = smem_desc_sw128(sRingA, kRingBlock, 1024);  // + ring row * 128 / 16 per K step, + 2 blocks per channel
-      uint32_t pRing = 0, pYFree = 0;
-      bool anyY = false;
+      uint32_t pRing = 0, pYFree[2] = {0, 0};
+      uint32_t g = 0;  // running number of the Y block: accumulator buffer g & 1
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         const int chunk = t / a.strips;
         const int cy0 = a.y0 + chunk * a.chunkRows, cy1 = min(a.y1, cy0 + a.chunkRows);
         const int nb = (cy1 - cy0 + kTcRows - 1) / kTcRows + 2;
 #pragma unroll 1
         for (int k = 0; k < nb; k++) {
+          const long long w0_ = a.dbg ? clock64() : 0;
           mbar_wait(&barRing, pRing);
           pRing ^= 1;
+          if (a.dbg) atomicAdd(&a.dbg[18], (unsigned long long)(clock64() - w0_));
           if (k < 2) continue;
-          if (anyY) {
-            mbar_wait(&barYFree, pYFree);
-            pYFree ^= 1;
+          const long long w1_ = a.dbg ? clock64() : 0;
+          const uint32_t b = g & 1u;
+          if (g >= 2) {  // the epilogue of Y block g - 2 has loaded this buffer
+            mbar_wait(&barYFree[b], pYFree[b]);
+            pYFree[b] ^= 1;
           }
-          anyY = true;
+          g++;
           tc_fence_after_sync();
           const uint32_t start = (uint32_t)(kTcRows * ((k - 2) & 3));  // ring blocks k - 2, k - 1, k
 #pragma unroll
@@ -188,16 +203,19 @@ __global__ void __launch_bounds__(kTcWorkers + 64, 1) blur_tc_kernel(const __gri
             for (int s = 0; s < 6; s++) {
               const uint32_t row = (start + 16u * (uint32_t)s) & (uint32_t)(kTcRingRows - 1);
               const uint64_t ad = ad0 + (uint64_t)(((uint32_t)(c * 2) * kRingBlock + row * 128u) >> 4);
-              mma_f16_ss(tmem + 128u + (uint32_t)(c * 32), ad, bd[s], idescY, s > 0 ? 1u : 0u);
+              mma_f16_ss(tmem + 128u + 128u * b + (uint32_t)(c * 32), ad, bd[s], idescY, s > 0 ? 1u : 0u);
             }
           }
-          mma_commit(&barY);
+          mma_commit(&barY[b]);
+          if (a.dbg) atomicAdd(&a.dbg[19], (unsigned long long)(clock64() - w1_));
         }
       }
     }
   } else {
     // ================================================================ workers
-    uint32_t pRaw = 0, pX = 0, pY = 0;
+    uint32_t pRaw = 0, pX = 0, pY[2] = {0, 0}, g = 0;
+    long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = 0;
+#define TC_MARK(slot) if (a.dbg) { const long long n_ = clock64(); tm[slot] += n_ - tc0; tc0 = n_; }
     const int q = warp & 3, wg = warp >> 2;  // TMEM lane quarter; which quarter of the columns / rows this warp drains
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const int chunk = t / a.strips, strip = t - chunk * a.strips;
@@ -209,18 +227,22 @@ __global__ void __launch_bounds__(kTcWorkers + 64, 1) blur_tc_kernel(const __gri
 
       // Y epilogue of output block `ob`: lane = column, 8 rows per warp, four channels from four accumulators
       auto y_epilogue = [&](int ob) {
-        mbar_wait(&barY, pY);
-        pY ^= 1;
+        const uint32_t b = g & 1u;
+        g++;
+        if (a.dbg) { const long long n_ = clock64(); tm[2] += n_ - tc0; tc0 = n_; }
+        mbar_wait(&barY[b], pY[b]);
+        pY[b] ^= 1;
+        if (a.dbg) { const long long n_ = clock64(); tm[5] += n_ - tc0; tc0 = n_; }
         tc_fence_after_sync();
         const int x = x0 + 32 * q + lane;
         const int orow0 = cy0 + kTcRows * ob + 8 * wg;
         uint32_t v[4][8];
 #pragma unroll
-        for (int c = 0; c < 4; c++) tmem_ld8(tmem + ((uint32_t)(32 * q) << 16) + 128u + (uint32_t)(c * 32 + 8 * wg), v[c]);
+        for (int c = 0; c < 4; c++) tmem_ld8(tmem + ((uint32_t)(32 * q) << 16) + 128u + 128u * b + (uint32_t)(c * 32 + 8 * wg), v[c]);
         tmem_ld_wait();
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&barYFree);  // D_y is in registers: the next Y MMAs may overwrite it
+        if (lane == 0) mbar_arrive(&barYFree[b]);  // this D_y buffer is in registers: Y block g + 1 may overwrite it
         if (x < a.w) {
           px_t* p = a.dst + (size_t)a.w * (size_t)orow0 + x;
           const int rows = min(8, cy1 - orow0);
@@ -237,8 +259,10 @@ __global__ void __launch_bounds__(kTcWorkers + 64, 1) blur_tc_kernel(const __gri
 #pragma unroll 1
       for (int i = 0; i < nb; i++) {
         // ---- raw RGBX block -> planar fp16 planes A_x
+        if (a.dbg) tc0 = clock64();
         mbar_wait(&barRaw, pRaw);
         pRaw ^= 1;
+        TC_MARK(0)
 #pragma unroll
         for (int u = 0; u < 3; u++) {
           const int qd = tid + kTcWorkers * u;
@@ -266,9 +290,14 @@ __global__ void __launch_bounds__(kTcWorkers + 64, 1) blur_tc_kernel(const __gri
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&barAx);
+        TC_MARK(1)
+        // ---- while the X MMAs of this block run: drain the Y accumulators of block i - 2 (output block i - 4)
+        if (i >= 4) y_epilogue(i - 4);
+        TC_MARK(2)
         // ---- X epilogue: quantised rows -> ring slot i % 4.  Warp = (channel q, 32 of the 128 output columns).
-        mbar_wait(&barX, pX);
+        mbar_wait(&barX[wg >> 1], pX);
         pX ^= 1;
+        TC_MARK(3)
         tc_fence_after_sync();
         {
           const int grow = rowBase + kTcRows * i + lane;  // lane = row of the block
@@ -296,15 +325,17 @@ __global__ void __launch_bounds__(kTcWorkers + 64, 1) blur_tc_kernel(const __gri
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&barRing);
-        // ---- drain the Y accumulators of block i - 1 (output block i - 3), issued when block i - 1 reached the ring
-        if (i >= 3) y_epilogue(i - 3);
+        TC_MARK(4)
       }
-      y_epilogue(nb - 3);  // Y of the last block
+      if (nb >= 4) y_epilogue(nb - 4);  // Y of block nb - 2
+      y_epilogue(nb - 3);               // Y of the last block
     }
+    if (a.dbg && lane == 0 && (warp == 0 || warp == 9))
+      for (int k = 0; k < 6; k++) atomicAdd(&a.dbg[(warp ? 8 : 0) + k], (unsigned long long)tm[k]);
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -378,9 +409,29 @@ int blur_tc(const px_t* src, px_t* dst, int w, int h, const uint16_t* lut_host, 
   a.chunkRows = chunkRows;
   a.chunks = (rows + chunkRows - 1) / chunkRows;
   a.ticket = nullptr;  // tickets are dealt round-robin: every (strip, chunk) costs the same
+  a.dbg = nullptr;
+  static const bool dbgOn = getenv("PIXIE_CUDA_TC_DEBUG") != nullptr;
+  if (dbgOn) {
+    void* d;
+    if (int rc = get_scratch(3, 32 * 8, &d)) return rc;
+    PX_CUDA(cudaMemsetAsync(d, 0, 32 * 8, r.stream));
+    a.dbg = (unsigned long long*)d;
+  }
   const int blocks = std::min(a.strips * a.chunks, r.num_sms);
   ProfScope ps(kProfBlurX);
-  return launch_tc(tmap, a, blocks, r.stream);
+  const int rcl = launch_tc(tmap, a, blocks, r.stream);
+  if (dbgOn && rcl == 0) {
+    unsigned long long hd[32];
+    PX_CUDA(cudaMemcpyAsync(hd, a.dbg, sizeof(hd), cudaMemcpyDeviceToHost, r.stream));
+    PX_CUDA(cudaStreamSynchronize(r.stream));
+    const double nbk = (double)a.strips * a.chunks * ((double)a.chunkRows / kTcRows + 2) ;
+    const char* nm[6] = {"wait raw", "convert", "y epilogue", "wait X", "x epilogue", "wait Y"};
+    fprintf(stderr, "[blur_tc] cycles per block (sum over CTAs / blocks): ");
+    for (int k = 0; k < 6; k++) fprintf(stderr, "w0 %s %.0f | ", nm[k], hd[k] / nbk);
+    for (int k = 0; k < 6; k++) fprintf(stderr, "w9 %s %.0f | ", nm[k], hd[8 + k] / nbk);
+    fprintf(stderr, "Xiss wait %.0f issue %.0f | Yiss wait %.0f issue %.0f\n", hd[16] / nbk, hd[17] / nbk, hd[18] / nbk, hd[19] / nbk);
+  }
+  return rcl;
 }
 
 }  // namespace pixie
