@@ -86,6 +86,7 @@ constexpr int kTcWorkers = 512;
 constexpr int kTcThreads = kTcWorkers + 96;
 constexpr uint32_t kTmDx = 0, kTmRing = 128, kTmDy = 384;  // TMEM columns: D_x 128, ring 4 channels x 64 (128 rows / 2), D_y 4 x 32
 
+template <bool DBG>
 __global__ void __launch_bounds__(kTcThreads, 1) blur_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcBlurArgs a) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -153,8 +154,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc_kernel(const __grid_con
 #pragma unroll 1
         for (int i = 0; i < nb; i++) {
           const int b = i & 1;
+          const long long w0_ = DBG ? clock64() : 0;
           mbar_wait(&barAx[b], pAx[b]);
           pAx[b] ^= 1;
+          const long long w1_ = DBG ? clock64() : 0;
           if (i + 2 < nb) {
             mbar_arrive_expect_tx(&barRaw[b], kRawBytes);
             tma_load_2d(sRaw + b * kRawBytes, &tmap, &barRaw[b], x0 - 32, rowBase + kTcRows * (i + 2));
@@ -164,10 +167,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc_kernel(const __grid_con
             pRing ^= 1;
           }
           anyX = true;
+          const long long w2_ = DBG ? clock64() : 0;
           tc_fence_after_sync();
 #pragma unroll
           for (int s = 0; s < 12; s++) mma_f16_ss(tmem + kTmDx, ad[s], bd0[s] + (uint64_t)((uint32_t)b * (kAxBytes >> 4)), idescX, s > 0 ? 1u : 0u);
           mma_commit(&barX);
+          if (DBG) { atomicAdd(&a.dbg[16], (unsigned long long)(w1_ - w0_)); atomicAdd(&a.dbg[17], (unsigned long long)(w2_ - w1_)); atomicAdd(&a.dbg[18], (unsigned long long)(clock64() - w2_)); }
         }
       }
     }
@@ -188,14 +193,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc_kernel(const __grid_con
         const int nb = (cy1 - cy0 + kTcRows - 1) / kTcRows + 2;
 #pragma unroll 1
         for (int k = 0; k < nb; k++) {
+          const long long w0_ = (DBG && h == 0) ? clock64() : 0;
           mbar_wait(&barRing, pRing);
           pRing ^= 1;
+          const long long w1_ = (DBG && h == 0) ? clock64() : 0;
+          if (DBG && h == 0) atomicAdd(&a.dbg[19], (unsigned long long)(w1_ - w0_));
           if (k < 2) continue;
           if (anyY) {  // D_y drained
             mbar_wait(&barYFree, pYFree);
             pYFree ^= 1;
           }
           anyY = true;
+          const long long w2_ = (DBG && h == 0) ? clock64() : 0;
           tc_fence_after_sync();
           const uint32_t start = (uint32_t)(kTcRows * ((k - 2) & 3));  // ring blocks k - 2, k - 1, k
 #pragma unroll
@@ -208,12 +217,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc_kernel(const __grid_con
             }
           }
           mma_commit(&barY);
+          if (DBG && h == 0) { atomicAdd(&a.dbg[20], (unsigned long long)(w2_ - w1_)); atomicAdd(&a.dbg[21], (unsigned long long)(clock64() - w2_)); }
         }
       }
     }
   } else {
     // ================================================================ workers
     uint32_t pRaw[2] = {0, 0}, pX = 0, pY = 0;
+    long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = DBG ? clock64() : 0;
+#define TC_MARK(slot) if (DBG) { const long long n_ = clock64(); tm[slot] += n_ - tc0; tc0 = n_; }
     const int q = warp & 3, wg = warp >> 2;  // TMEM lane quarter (32 of the strip's columns); channel (X) / 8 rows (Y)
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const int chunk = t / a.strips, strip = t - chunk * a.strips;
@@ -226,8 +238,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc_kernel(const __grid_con
       // X epilogue of block ib: lane = output column, this warp's 32 accumulator columns = the 32 rows of channel wg;
       // quantised, two rows per word (fp16 subnormals), into the block's 16 ring columns of that channel
       auto x_epilogue = [&](int ib) {
+        TC_MARK(6)
         mbar_wait(&barX, pX);
         pX ^= 1;
+        TC_MARK(2)
         tc_fence_after_sync();
         uint32_t v0[16], v1[16];
         tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + kTmDx + (uint32_t)(32 * wg), v0);
@@ -254,11 +268,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc_kernel(const __grid_con
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&barRing);
+        TC_MARK(3)
       };
       // Y epilogue of output block `ob`: lane = column, 8 rows per warp, four channels from four accumulators
       auto y_epilogue = [&](int ob) {
+        TC_MARK(6)
         mbar_wait(&barY, pY);
         pY ^= 1;
+        TC_MARK(4)
         tc_fence_after_sync();
         const int x = x0 + 32 * q + lane;
         const int orow0 = cy0 + kTcRows * ob + 8 * wg;
@@ -280,43 +297,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc_kernel(const __grid_con
             p += a.w;
           }
         }
+        TC_MARK(5)
       };
 
 #pragma unroll 1
       for (int i = 0; i < nb; i++) {
         // ---- raw RGBX block -> planar fp16 planes A_x (buffer i & 1)
         const int b = i & 1;
+        TC_MARK(6)
         mbar_wait(&barRaw[b], pRaw[b]);
         pRaw[b] ^= 1;
+        TC_MARK(0)
         const uint8_t* raw = sRaw + b * kRawBytes;
         uint8_t* ax = sAx + b * kAxBytes;
+        // 768 tasks of 8 pixels (row, group g8 of the 24 per row): two 16-byte loads, byte permutes, one 16-byte store
+        // per channel plane (8 halfs = one swizzle chunk)
 #pragma unroll
-        for (int u = 0; u < 3; u++) {
+        for (int u = 0; u < 2; u++) {
           const int qd = tid + kTcWorkers * u;
-          const int row = qd / 48, g = qd - row * 48;
-          uint4 p = *reinterpret_cast<const uint4*>(raw + ((size_t)row * kTcInW + 4 * g) * 4);
-          if (patch) {  // columns outside the image carry the out-of-bounds colour (TMA filled them with zeros)
-            const int x = x0 - 32 + 4 * g;
-            if (x < 0 || x >= a.w) p.x = a.oob;
-            if (x + 1 < 0 || x + 1 >= a.w) p.y = a.oob;
-            if (x + 2 < 0 || x + 2 >= a.w) p.z = a.oob;
-            if (x + 3 < 0 || x + 3 >= a.w) p.w = a.oob;
-          }
-          const uint32_t rg01 = __byte_perm(p.x, p.y, 0x5140), ba01 = __byte_perm(p.x, p.y, 0x7362);
-          const uint32_t rg23 = __byte_perm(p.z, p.w, 0x5140), ba23 = __byte_perm(p.z, p.w, 0x7362);
-          uint32_t wv[8];
-          wv[0] = __byte_perm(rg01, 0u, 0x4140); wv[1] = __byte_perm(rg23, 0u, 0x4140);  // r0 r1 | r2 r3 as fp16 subnormals
-          wv[2] = __byte_perm(rg01, 0u, 0x4342); wv[3] = __byte_perm(rg23, 0u, 0x4342);  // g
-          wv[4] = __byte_perm(ba01, 0u, 0x4140); wv[5] = __byte_perm(ba23, 0u, 0x4140);  // b
-          wv[6] = __byte_perm(ba01, 0u, 0x4342); wv[7] = __byte_perm(ba23, 0u, 0x4342);  // a
-          // line = channel * 32 + row; column block g / 16, 16-byte chunk (g % 16) / 2, upper or lower half of it
-          uint8_t* d = ax + (uint32_t)(g >> 4) * kAxBlock + sw128_off((uint32_t)row, (uint32_t)(g & 15) >> 1) + (uint32_t)(g & 1) * 8u;
+          if (qd < kTcRows * (kTcInW / 8)) {
+            const int row = qd / (kTcInW / 8), g8 = qd - row * (kTcInW / 8);
+            const uint4* src = reinterpret_cast<const uint4*>(raw + ((size_t)row * kTcInW + 8 * g8) * 4);
+            uint4 p = src[0], p2 = src[1];
+            if (patch) {  // columns outside the image carry the out-of-bounds colour (TMA filled them with zeros)
+              const int x = x0 - 32 + 8 * g8;
+              uint32_t* pp = &p.x;
+              uint32_t* pq = &p2.x;
 #pragma unroll
-          for (int c = 0; c < 4; c++) *reinterpret_cast<uint2*>(d + c * (32 * 128)) = make_uint2(wv[2 * c], wv[2 * c + 1]);
+              for (int e = 0; e < 4; e++) {
+                if (x + e < 0 || x + e >= a.w) pp[e] = a.oob;
+                if (x + 4 + e < 0 || x + 4 + e >= a.w) pq[e] = a.oob;
+              }
+            }
+            const uint32_t rg01 = __byte_perm(p.x, p.y, 0x5140), ba01 = __byte_perm(p.x, p.y, 0x7362);
+            const uint32_t rg23 = __byte_perm(p.z, p.w, 0x5140), ba23 = __byte_perm(p.z, p.w, 0x7362);
+            const uint32_t rg45 = __byte_perm(p2.x, p2.y, 0x5140), ba45 = __byte_perm(p2.x, p2.y, 0x7362);
+            const uint32_t rg67 = __byte_perm(p2.z, p2.w, 0x5140), ba67 = __byte_perm(p2.z, p2.w, 0x7362);
+            // line = channel * 32 + row; column block g8 / 8, 16-byte chunk g8 % 8
+            uint8_t* d = ax + (uint32_t)(g8 >> 3) * kAxBlock + sw128_off((uint32_t)row, (uint32_t)(g8 & 7));
+            // a byte next to a zero byte is the fp16 subnormal b * 2^-24
+            *reinterpret_cast<uint4*>(d) = make_uint4(__byte_perm(rg01, 0u, 0x4140), __byte_perm(rg23, 0u, 0x4140),
+                                                      __byte_perm(rg45, 0u, 0x4140), __byte_perm(rg67, 0u, 0x4140));
+            *reinterpret_cast<uint4*>(d + 32 * 128) = make_uint4(__byte_perm(rg01, 0u, 0x4342), __byte_perm(rg23, 0u, 0x4342),
+                                                                 __byte_perm(rg45, 0u, 0x4342), __byte_perm(rg67, 0u, 0x4342));
+            *reinterpret_cast<uint4*>(d + 64 * 128) = make_uint4(__byte_perm(ba01, 0u, 0x4140), __byte_perm(ba23, 0u, 0x4140),
+                                                                 __byte_perm(ba45, 0u, 0x4140), __byte_perm(ba67, 0u, 0x4140));
+            *reinterpret_cast<uint4*>(d + 96 * 128) = make_uint4(__byte_perm(ba01, 0u, 0x4342), __byte_perm(ba23, 0u, 0x4342),
+                                                                 __byte_perm(ba45, 0u, 0x4342), __byte_perm(ba67, 0u, 0x4342));
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&barAx[b]);
+        TC_MARK(1)
         if (i >= 1) x_epilogue(i - 1);
         if (i >= 4) y_epilogue(i - 4);  // Y of block i - 2 = output block i - 4
       }
@@ -324,6 +357,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc_kernel(const __grid_con
       if (nb >= 4) y_epilogue(nb - 4);  // Y of block nb - 2
       y_epilogue(nb - 3);               // Y of the last block
     }
+    if (DBG && lane == 0 && (warp == 0 || warp == 9))
+      for (int k = 0; k < 7; k++) atomicAdd(&a.dbg[(warp ? 8 : 0) + k], (unsigned long long)tm[k]);
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -351,10 +386,12 @@ static int launch_tc(const CUtensorMap& tmap, const TcBlurArgs& a, int blocks, c
   const size_t smem = 1024 + kToeBytes + 2 * kAxBytes + 2 * kRawBytes;
   static bool configured = false;
   if (!configured) {
-    PX_CUDA(cudaFuncSetAttribute(blur_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PX_CUDA(cudaFuncSetAttribute(blur_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PX_CUDA(cudaFuncSetAttribute(blur_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  blur_tc_kernel<<<blocks, kTcThreads, smem, st>>>(tmap, a);
+  if (a.dbg) blur_tc_kernel<true><<<blocks, kTcThreads, smem, st>>>(tmap, a);
+  else blur_tc_kernel<false><<<blocks, kTcThreads, smem, st>>>(tmap, a);
   PX_LAUNCHED();
   return 0;
 }
@@ -402,9 +439,29 @@ int blur_tc(const px_t* src, px_t* dst, int w, int h, const uint16_t* lut_host, 
   a.chunks = (rows + chunkRows - 1) / chunkRows;
   a.ticket = nullptr;  // tickets are dealt round-robin: every (strip, chunk) costs the same
   a.dbg = nullptr;
+  static const bool dbgOn = getenv("PIXIE_CUDA_TC_DEBUG") != nullptr;
+  if (dbgOn) {
+    void* d;
+    if (int rc = get_scratch(3, 32 * 8, &d)) return rc;
+    PX_CUDA(cudaMemsetAsync(d, 0, 32 * 8, r.stream));
+    a.dbg = (unsigned long long*)d;
+  }
   const int blocks = std::min(a.strips * a.chunks, r.num_sms);
   ProfScope ps(kProfBlurX);
-  return launch_tc(tmap, a, blocks, r.stream);
+  const int rcl = launch_tc(tmap, a, blocks, r.stream);
+  if (dbgOn && rcl == 0) {  // per-phase cycles of worker warps 0 and 9 and of the issuers, averaged per 32-row block
+    unsigned long long hd[32];
+    PX_CUDA(cudaMemcpyAsync(hd, a.dbg, sizeof(hd), cudaMemcpyDeviceToHost, r.stream));
+    PX_CUDA(cudaStreamSynchronize(r.stream));
+    const double nbk = (double)a.strips * a.chunks * ((double)a.chunkRows / kTcRows + 2);
+    const char* nm[7] = {"wait raw", "convert", "wait X", "x epi", "wait Y", "y epi", "other"};
+    fprintf(stderr, "[blur_tc] cycles per block:");
+    for (int k = 0; k < 7; k++) fprintf(stderr, " w0 %s %.0f |", nm[k], hd[k] / nbk);
+    for (int k = 0; k < 7; k++) fprintf(stderr, " w9 %s %.0f |", nm[k], hd[8 + k] / nbk);
+    fprintf(stderr, " X issuer: wait planes %.0f, wait D_x %.0f, issue %.0f | Y issuer: wait ring %.0f, wait D_y %.0f, issue %.0f\n", hd[16] / nbk,
+            hd[17] / nbk, hd[18] / nbk, hd[19] / nbk, hd[20] / nbk, hd[21] / nbk);
+  }
+  return rcl;
 }
 
 }  // namespace pixie

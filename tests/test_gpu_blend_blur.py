@@ -205,3 +205,50 @@ def test_shadow_alpha_plane(shape, radius, spread_):
     a = gb.shadow(img, 3, -2, spread_, lut, radius, pack(90, 20, 130, 220))
     b = ob.shadow(img, 3, -2, spread_, lut, radius, pack(90, 20, 130, 220))
     assert diff_report(a, b)[0] == 0
+
+
+@pytest.mark.parametrize("radius", [29, 30, 31, 32])
+@pytest.mark.parametrize("shape", [(33, 128), (70, 132), (131, 260), (64, 4), (1, 512), (300, 388)])
+def test_blur_fused_tensor_core_path(radius, shape):
+    """The fused tcgen05 kernel (blur_tc.cu: radii whose taps stay below 2048, widths that are multiples of 4): strips
+    that end inside the last 128 columns, chunks that end inside a block of 32 rows, images shorter than one block,
+    out-of-bounds colours (rows above / below the image enter the vertical pass as the colour itself)."""
+    gb, ob = _backends()
+    h, w = shape
+    img = synth.random_premultiplied(h, w, radius * 7 + w)
+    lut = host.gaussianKernel(radius)
+    assert int(lut.max()) < 2048
+    for oob in (0, pack(10, 200, 30, 255), pack(255, 255, 255, 255)):
+        a, b = img.copy(), img.copy()
+        gb.blur(a, lut, radius, oob)
+        ob.blur(b, lut, radius, oob)
+        n, mx, where = diff_report(a, b)
+        assert n == 0, f"r={radius} {shape} oob={oob:#x}: {n} px differ (max {mx}) at {where}"
+
+
+def test_blur_fused_path_moves_owned_images_and_keeps_wrapped_ones():
+    """A whole-image blur of a library-owned image switches the handle to a fresh buffer (the fused pass cannot run in
+    place); a caller-owned (wrapped) image keeps its memory and gets the rows copied back."""
+    import torch
+
+    from pixie_b200 import device as dev
+
+    dev.init()
+    _, ob = _backends()
+    h, w, r = 200, 256, 32
+    img = synth.random_premultiplied(h, w, 77)
+    lut = host.gaussianKernel(r)
+    want = img.copy()
+    ob.blur(want, lut, r, 0)
+    t = torch.from_numpy(img.copy()).cuda()
+    wrapped = dev.DeviceImage.wrap(t.data_ptr(), w, h, owner=t)
+    dev.blur(wrapped, lut, r, 0)
+    dev.sync()
+    assert wrapped.device_ptr() == t.data_ptr()
+    assert diff_report(t.cpu().numpy(), want)[0] == 0
+    owned = dev.DeviceImage(w, h).upload(img)
+    dev.blur(owned, lut, r, 0)
+    assert diff_report(owned.download(), want)[0] == 0
+    dev.blur(owned, lut, r, 0)  # and again on the moved buffer
+    ob.blur(want, lut, r, 0)
+    assert diff_report(owned.download(), want)[0] == 0
