@@ -551,51 +551,183 @@ def icons_sharded(dev, dist, rank, world, per_rank, size=512, chunk=2048):
             "checksum_rank0": checksum, "scaling": "weak (12 500 icons per GPU)", "chunk": chunk}
 
 
-def banded_blur_multi_gpu(dev, dist, rank, world, local_rank, peak):
-    """BASELINE config 4 across N GPUs: one 16384^2 canvas in row bands, `radius` halo rows exchanged
-    with ncclSend/ncclRecv (torch.distributed P2P over NVLink), then the row-band blur kernel."""
-    import torch
+def _band_tile(n, k, rows=256):
+    """Rank k's band of the synthetic 16384-wide canvas: a 256-row tile of noise (seeded by the rank) repeated."""
+    from pixie_b200 import synth
 
-    from pixie_b200 import host, multi, synth
+    return synth.random_premultiplied(rows, n, 0xB10B + k)
 
-    n, r = 16384, 32
-    y0, y1 = multi.band_range(n, world, rank)
-    tile = torch.from_numpy(synth.random_premultiplied(256, n, 0xB10B + rank)).cuda()
-    rb = multi.RowBand(n, n, rank, world, margin=r)  # the band lives between its halo margins: no staging copies
-    rb.band.copy_(tile.repeat((y1 - y0 + 255) // 256, 1, 1)[: y1 - y0])
-    lut = host.gaussianKernel(r)
-    times = []
-    for it in range(4):
-        torch.cuda.synchronize()
-        dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        rb.blur(r, lut, 0)
-        e1.record()
-        torch.cuda.synchronize()
-        if it:
-            times.append(e0.elapsed_time(e1))
-    t = torch.tensor([statistics.median(times)], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    # parity across the cut (outside the timed region): this rank also blurs the WHOLE canvas on its own GPU and
-    # compares its band's rows with what the banded blur produced
-    parts = []
+
+def _global_rows(n, world, y0, y1, transparent_above=0):
+    """Rows [y0, y1) of the global canvas assembled on the host from the per-rank tiles (for the oracle windows)."""
+    from pixie_b200 import multi
+
+    out = np.zeros((y1 - y0, n, 4), np.uint8)
     for k in range(world):
         a, b = multi.band_range(n, world, k)
-        tk = torch.from_numpy(synth.random_premultiplied(256, n, 0xB10B + k)).cuda()
-        parts.append(tk.repeat((b - a + 255) // 256, 1, 1)[: b - a])
-    whole = torch.cat(parts)
-    del parts
-    rb.band.copy_(whole[y0:y1])
-    rb.blur(r, lut, 0)
-    dev.blur(dev.DeviceImage.wrap(whole.data_ptr(), n, n, owner=whole), lut, r, 0)
-    same = torch.tensor([int(torch.equal(rb.band, whole[y0:y1]))], dtype=torch.int64, device="cuda")
-    dist.all_reduce(same, op=dist.ReduceOp.MIN)
-    del whole
+        lo, hi = max(a, y0), min(b, y1)
+        if lo >= hi:
+            continue
+        tile = _band_tile(n, k)
+        idx = (np.arange(lo, hi) - a) % tile.shape[0]
+        out[lo - y0:hi - y0] = tile[idx]
+    if transparent_above > y0:
+        out[: min(transparent_above, y1) - y0] = 0
+    return out
+
+
+class _BandView:
+    """download_rows over a band tensor in global row coordinates (what tests/_windows.py reads)."""
+
+    def __init__(self, t, y0):
+        self.t, self.y0 = t, y0
+
+    def download_rows(self, a, b):
+        return self.t[a - self.y0:b - self.y0].cpu().numpy()
+
+
+def row_bands_multi_gpu(dev, dist, rank, world, local_rank, peak):
+    """BASELINE config 4 (+ the other row-band rows of SURVEY 8e) across N GPUs: one canvas in row bands.
+    blur / spread / shadow exchange halo rows with ncclSend / ncclRecv (torch.distributed P2P over NVLink) — for the
+    blur the exchange runs on a side stream while the halo-free horizontal pass blurs the band's own rows; blends and
+    fills need no exchange.  Every result is compared with the ORACLE on windows of this rank's band (two of them
+    straddling the cuts), built from the global canvas on the host."""
+    import torch
+
+    from pixie_b200 import host, multi, svg as psvg
+    from pixie_b200.common import NormalBlend
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _windows as W
+    from _oracle import OracleBackend
+
+    out = {}
+    n, r = 16384, 32
+    y0, y1 = multi.band_range(n, world, rank)
+    lut = host.gaussianKernel(r)
+
+    def fill_band(rb, transparent_above=0):
+        tile = torch.from_numpy(_band_tile(n, rank)).cuda()
+        rb.band.copy_(tile.repeat((y1 - y0 + 255) // 256, 1, 1)[: y1 - y0])
+        if transparent_above > y0:
+            rb.band[: min(transparent_above, y1) - y0] = 0
+
+    def timed(fn, reps=5):
+        ts = []
+        for it in range(reps):
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if it:
+                ts.append(e0.elapsed_time(e1))
+        t = torch.tensor([statistics.median(ts)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(bad):
+        t = torch.tensor([int(bad)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+    def windows():  # this rank's band: across its upper cut, across its lower cut, interior; all 48 x 48
+        wins = [(y0, y0 + 48, 0, 48), (y1 - 48, y1, n - 48, n), ((y0 + y1) // 2, (y0 + y1) // 2 + 48, 8192 - 24, 8192 + 24)]
+        return wins
+
+    def crop_check(fn_check, band_tensor, reach, transparent_above=0):
+        bad = cnt = 0
+        view = _BandView(band_tensor, y0)
+        for win in windows():
+            a, b = max(0, win[0] - reach - 8), min(n, win[1] + reach + 8)
+            rows = _global_rows(n, world, a, b, transparent_above)
+            # windows in the coordinates of the row slab [a, b): the slab's top / bottom are image borders only where
+            # a == 0 / b == n, otherwise they are farther than `reach` from the window
+            sub = (win[0] - a, win[1] - a, win[2], win[3])
+            c, bd, _ = fn_check(_BandView(band_tensor, y0 - a), rows, [sub])
+            cnt += c
+            bad += bd
+        return cnt, bad
+
+    margin = 64
+    rb = multi.RowBand(n, n, rank, world, margin=margin)
+    # ---- blur r=32: exchange overlapped with the horizontal pass, and the plain exchange-then-blur for comparison
+    # (timed on the band as it is: the cost does not depend on the pixel values; refilled before the parity run)
+    fill_band(rb)
+    t_ov = timed(lambda: rb.blur(r, lut, 0, overlap=True))
+    t_se = timed(lambda: rb.blur(r, lut, 0, overlap=False))
+    fill_band(rb)
+    rb.blur(r, lut, 0, overlap=True)
+    cnt, bad = crop_check(lambda v, rows, wins: W.check_blur_windows(v, rows, lut, r, 0, wins), rb.band, r)
+    out["blur_r32_16384_row_bands"] = {
+        "ms": round(t_ov, 3), "ms_exchange_then_blur": round(t_se, 3), "GB/s": round(n * n * 8 / t_ov / 1e6, 1),
+        "frac_hbm_aggregate": round(n * n * 8 / t_ov / 1e6 / (peak * world), 3),
+        "parity_vs_oracle": _parity(all_ok(cnt), all_ok(bad), 0), "halo_bytes_per_interior_edge": 2 * r * n * 4,
+        "scaling": "strong (one 16384^2 canvas)", "transport": rb.transport,
+        "exchange": "peer: a kernel stores the band's edge rows into the neighbour's CUDA-IPC mapped margin over NVLink and "
+                    "publishes an epoch flag there (pixie_cuda_halo_push / _wait, no NCCL launch); the band's interior rows "
+                    "(no halo needed) are blurred meanwhile, the two edge strips after the flag; ms_exchange_then_blur = "
+                    "the same without the split"}
+    # ---- spread 4 and the drop shadow (offset (8, 8), spread 4, blur 32): halo = |offset.y| + |spread| + radius rows
+    fill_band(rb)
+    t_sp = timed(lambda: rb.spread(4))
+    fill_band(rb)
+    rb.spread(4)
+    cnt, bad = crop_check(lambda v, rows, wins: W.check_spread_windows(v, rows, 4, wins), rb.band, 4)
+    out["spread4_16384_row_bands"] = {"ms": round(t_sp, 3), "parity_vs_oracle": _parity(all_ok(cnt), all_ok(bad), 0)}
+    ta = n // 3
+    fill_band(rb, transparent_above=ta)
+    col = 0xC8000000
+    t_sh = timed(lambda: rb.shadow((8.0, 8.0), 4, r, lut, col), reps=4)
+    sh = rb.shadow((8.0, 8.0), 4, r, lut, col)
+    cnt, bad = crop_check(lambda v, rows, wins: W.check_shadow_windows(v, rows, (8, 8), 4, lut, r, col, wins), sh, 8 + 4 + r, ta)
+    out["shadow_16384_row_bands"] = {"ms": round(t_sh, 3), "GB/s": round(n * n * 8 / t_sh / 1e6, 1),
+                                     "halo_rows": 8 + 4 + r, "parity_vs_oracle": _parity(all_ok(cnt), all_ok(bad), 0)}
+    del rb, sh
+    # ---- blends in row bands (no exchange): NormalBlend of a 16384-wide src band over the dst band
+    rbd = multi.RowBand(n, n, rank, world, margin=0)
+    fill_band(rbd)
+    src = torch.from_numpy(_band_tile(n, rank + 100)).cuda().repeat((y1 - y0 + 255) // 256, 1, 1)[: y1 - y0].contiguous()
+    t_bl = timed(lambda: rbd.blend(src, NormalBlend))
+    fill_band(rbd)
+    rbd.blend(src, NormalBlend)
+    want = _global_rows(n, world, y0, y0 + 4)
+    OracleBackend(0).blend_rect(want, np.ascontiguousarray(_band_tile(n, rank + 100)[:4]), 0, 0, NormalBlend)
+    bad = int((rbd.band[:4].cpu().numpy() != want).any(axis=-1).sum())
+    out["blend_normal_16384_row_bands"] = {"ms": round(t_bl, 3), "GB/s": round(n * n * 12 / t_bl / 1e6, 1),
+                                           "frac_hbm_aggregate": round(n * n * 12 / t_bl / 1e6 / (peak * world), 3),
+                                           "parity_vs_oracle": _parity(all_ok(4 * n), all_ok(bad), 0), "exchange": "none (per-pixel)"}
+    del rbd, src
+    # ---- one canvas of fills in row bands: the tiger at 8192^2, every rank holds the whole command list (replicated
+    # upload) and plans + rasterises only its rows; partition boundaries are those of the whole canvas
+    size = 8192
+    with open(os.path.join(ROOT, "tests", "golden", "tiger.svg")) as f:
+        arrays = psvg.svg_fill_batch(psvg.parseSvg(f.read(), size, size)).arrays()
+    fy0, fy1 = multi.band_range(size, world, rank)
+    rbf = multi.RowBand(size, size, rank, world, margin=0)
+    cl = dev.CmdList(size, size, 1, arrays)
+
+    def fills():
+        rbf.band.zero_()
+        return rbf.fill(cl)
+
+    t_fi = timed(fills)
+    rbf.band.zero_()
+    covered = rbf.fill(cl, count_covered=True)
+    from _util import oracle_render_batch
+
+    want_full, cov_cpu = oracle_render_batch(arrays, size, size)
+    bad = int((rbf.band.cpu().numpy() != want_full[0][fy0:fy1]).any(axis=-1).sum())
+    tcov = torch.tensor([float(covered)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tcov, op=dist.ReduceOp.SUM)
+    out["tiger_8192_fills_row_bands"] = {"ms": round(t_fi, 3), "Mpixel/s": round(float(tcov.item()) / t_fi / 1e3, 1),
+                                         "covered_px_sum_over_ranks": int(tcov.item()), "covered_px_oracle": int(cov_cpu),
+                                         "parity_vs_oracle": _parity(all_ok((fy1 - fy0) * size), all_ok(bad), 0),
+                                         "exchange": "none (segment list replicated; global partition boundaries, band-restricted plan + raster)"}
     dev.set_stream(None)
-    ms = float(t.item())
-    return {"ms": round(ms, 3), "matches_single_gpu_blur_on_every_rank": bool(same.item()), "GB/s": round(n * n * 8 / ms / 1e6, 1), "frac_hbm_aggregate": round(n * n * 8 / ms / 1e6 / (peak * world), 3),
-            "halo_bytes_per_interior_edge": 2 * r * n * 4, "scaling": "strong (one 16384^2 canvas)"}
+    return out
 
 
 def run_ours(args):
@@ -703,9 +835,11 @@ def run_ours(args):
     icons_multi = None
     if dist is not None and not args.no_extras:
         try:
-            banded = banded_blur_multi_gpu(dev, dist, rank, world, local_rank, peak)
+            banded = row_bands_multi_gpu(dev, dist, rank, world, local_rank, peak)
         except Exception as e:
-            banded = {"error": repr(e)}
+            import traceback
+
+            banded = {"error": repr(e), "trace": traceback.format_exc()[-800:]}
         try:
             icons_multi = icons_sharded(dev, dist, rank, world, args.icons_per_gpu)
         except Exception as e:
@@ -764,7 +898,7 @@ def run_ours(args):
     }
     if banded is not None:
         extras = dict(extras or {})
-        extras["blur_r32_16384_row_bands"] = banded
+        extras["row_bands"] = banded
         extras["icons_512_sharded"] = icons_multi
     if extras is not None:
         out["extras"] = extras

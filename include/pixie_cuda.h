@@ -45,6 +45,9 @@ const char* pixie_cuda_last_error(void);       /* bindings/bindings.nim:3-10 tak
 int pixie_cuda_set_stream(void* cuda_stream);  /* cudaStream_t to issue on (NULL = library stream; the legacy default
                                                 * stream is named by cudaStreamLegacy = (cudaStream_t)0x1) */
 int pixie_cuda_sync(void);                     /* wait for everything issued so far */
+/* Persistent kernels that fill the GPU with one CTA per SM (the fused blur) leave `sms` SMs free, so that a
+ * collective's kernels on another stream (NCCL send / recv of the halo rows) can run beside them.  Default 0. */
+int pixie_cuda_set_sm_reserve(int sms);
 int pixie_cuda_device_count(int* out);
 
 /* ---- images: newImage / copy / fill (common.nim:39-54, pixie.nim:120-131) -------------- */
@@ -161,12 +164,27 @@ int pixie_cuda_fill_gradient(pixie_image_t image, int kind, const float* handles
 /* ---- blur / spread / shadow (images.nim:304-365, :700-758, :760-776) ------------------------
  * lut = gaussianKernel(radius) (internal.nim:17-34), 2*radius+1 uint16 taps, computed by the
  * caller.  radius < 0 -> 1 "Cannot apply negative blur" (:311-312); radius == 0 is a no-op. */
+/* Radii whose taps stay below 2048 (29..32) on images whose width is a multiple of 4 run as ONE fused pass on the tcgen05
+ * tensor cores (blur_tc.cu); that pass is out of place, so a whole-image blur of a library-owned image moves its pixels
+ * to a fresh device buffer (pixie_cuda_image_info returns the new pointer); wrapped images keep their memory. */
 int pixie_cuda_blur(pixie_image_t image, const uint16_t* lut, int radius, uint32_t out_of_bounds_rgbx);
 /* Row-band form used when one canvas is split across GPUs: computes the blur of the whole image
  * but writes only rows [y0, y1); the other rows (the halo received from the neighbours) are left
  * unchanged.  With `radius` halo rows above and below, rows [y0, y1) equal the global blur. */
 int pixie_cuda_blur_rows(pixie_image_t image, const uint16_t* lut, int radius, uint32_t out_of_bounds_rgbx,
                          int y0, int y1);
+/* Out-of-place row-band blur: rows [y0, y1) of dst <- rows [y0, y1) of blur(src); src and the other rows of dst are
+ * left unchanged.  Several calls on one src (disjoint row ranges) compose: a band split across GPUs blurs its interior
+ * rows while the halo rows are still on their way and its edge rows afterwards (pixie_b200/multi.py). */
+int pixie_cuda_blur_rows_to(pixie_image_t src, pixie_image_t dst, const uint16_t* lut, int radius,
+                            uint32_t out_of_bounds_rgbx, int y0, int y1);
+/* The same for a band whose halo rows (rows [0, y0) and [y1, height) of src) are being stored by neighbour GPUs
+ * (pixie_cuda_halo_exchange): only the tiles that read halo rows wait — inside the kernel — until the flag the
+ * neighbour publishes after its rows has reached `epoch`; the band's interior is blurred meanwhile.  NULL = that side
+ * has no neighbour. */
+int pixie_cuda_blur_rows_to_flags(pixie_image_t src, pixie_image_t dst, const uint16_t* lut, int radius,
+                                  uint32_t out_of_bounds_rgbx, int y0, int y1, const void* top_flag,
+                                  const void* bottom_flag, uint32_t epoch);
 /* The two halves of pixie_cuda_blur_rows, for callers that overlap the halo exchange with the X pass (which needs no
  * halo): _x blurs rows [r0, r1) horizontally into the library's scratch plane; _y then produces image rows
  * [y0, y1) from scratch rows [y0 - radius, y1 + radius) — each of which an _x call must have produced since the last
@@ -189,6 +207,34 @@ int pixie_cuda_shadow(pixie_image_t src, pixie_image_t dst, float offset_x, floa
 
 int pixie_cuda_shadow_rows(pixie_image_t src, pixie_image_t dst, float offset_x, float offset_y, int spread,
                            const uint16_t* lut, int radius, uint32_t rgbx, int y0, int y1);
+
+/* ---- halo rows between the GPUs of one box, without a collective library (one process per GPU) ---------------
+ * peer_alloc: a device buffer other processes can map (cudaMalloc + CUDA IPC handle, 64 bytes, to be sent to the
+ * neighbours by any means); peer_open maps a neighbour's buffer into this process (peer access over NVLink).
+ * halo_push (stream-ordered): copies `bytes` from local `src_rows` into the neighbour's mapped memory and then stores
+ * `value` at `peer_flag` (a uint32 in the neighbour's buffer) with release semantics at system scope; halo_wait
+ * (stream-ordered): everything issued after it runs once the local flag has reached `value` (epochs only grow).
+ * Used by pixie_b200/multi.py RowBand(transport="peer") for blur / spread / shadow on a canvas split in row bands. */
+int pixie_cuda_peer_alloc(size_t bytes, void** device_ptr, uint8_t* ipc_handle_64);
+int pixie_cuda_peer_open(const uint8_t* ipc_handle_64, void** device_ptr);
+int pixie_cuda_peer_close(void* device_ptr);
+int pixie_cuda_peer_free(void* device_ptr);
+int pixie_cuda_halo_push(const void* src_rows, void* peer_dst_rows, size_t bytes, void* peer_flag, uint32_t value);
+int pixie_cuda_halo_wait(const void* local_flag, uint32_t value);
+/* One epoch's exchange with the upper and / or lower neighbour (NULL = none) in ONE launch: store `epoch` at the
+ * neighbours' ready flags ("my margin is free"), wait until the local ready flags written by the neighbours reach it,
+ * store the rows into their margins, store `epoch` at their data flags.  halo_wait2 then holds the stream until both
+ * local data flags have reached `epoch`. */
+typedef struct {
+  const void* src_rows;         /* local rows to send */
+  void* peer_dst_rows;          /* the neighbour's margin (mapped with pixie_cuda_peer_open) */
+  size_t bytes;
+  void* peer_ready_flag;        /* in the neighbour's buffer: this rank's margin is free for `epoch` */
+  void* peer_data_flag;         /* in the neighbour's buffer: the rows of `epoch` have arrived */
+  const void* local_ready_flag; /* in this rank's buffer, written by that neighbour */
+} pixie_halo_dir_t;
+int pixie_cuda_halo_exchange(const pixie_halo_dir_t* up, const pixie_halo_dir_t* down, uint32_t epoch);
+int pixie_cuda_halo_wait2(const void* local_flag_a, const void* local_flag_b, uint32_t value);
 
 /* ---- strict drop-in variants: host pixels in, host pixels out (upload -> run -> download) ---- */
 int pixie_cuda_fill_segments_host(uint8_t* pixels, int width, int height, const float* seg_xyxy,

@@ -356,7 +356,8 @@ static int launch_f32(ConvArgs a, Image* im, void* tmp, const uint16_t* lut_d, i
 }
 
 int blur_mma(Image* im, void* tmp, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1, int phase);  // blur_mma.cu
-int blur_tc(const px_t* src, px_t* dst, int w, int h, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1);  // blur_tc.cu
+int blur_tc(const px_t* src, px_t* dst, int w, int h, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1,
+            const unsigned* flagTop = nullptr, const unsigned* flagBottom = nullptr, unsigned epoch = 0);  // blur_tc.cu
 
 // phase 0: the whole blur of rows [y0, y1); 1 / 2: only its X pass over rows [y0, y1) / only its Y pass (the two
 // halves of a row-band blur whose halo exchange overlaps the X pass, pixie_cuda_blur_rows_x / _y)
@@ -901,6 +902,60 @@ int pixie_cuda_blur_rows(pixie_image_t h, const uint16_t* lut, int radius, uint3
   Image* im = find_image(h);
   if (!im) return 1;
   return blur_impl(im, lut, radius, oob, y0, y1);
+}
+
+// dst rows [y0, y1) <- rows [y0, y1) of blur(src); src is left unchanged (out of place: no scratch round trip, and the
+// source rows stay valid for further calls on other row ranges)
+int pixie_cuda_blur_rows_to(pixie_image_t srch, pixie_image_t dsth, const uint16_t* lut, int radius, uint32_t oob, int y0, int y1) {
+  return pixie_cuda_blur_rows_to_flags(srch, dsth, lut, radius, oob, y0, y1, nullptr, nullptr, 0);
+}
+
+int pixie_cuda_blur_rows_to_flags(pixie_image_t srch, pixie_image_t dsth, const uint16_t* lut, int radius, uint32_t oob, int y0, int y1,
+                                  const void* top_flag, const void* bottom_flag, uint32_t epoch) {
+  PX_API_GUARD;
+  if (int rc = ensure_init()) return rc;
+  Image* s = find_image(srch);
+  Image* d = find_image(dsth);
+  if (!s || !d) return 1;
+  if (radius < 0) return fail_pixie("Cannot apply negative blur");
+  if (s->w != d->w || s->h != d->h || s->bpp != 4 || d->bpp != 4 || s->layers != 1 || d->layers != 1)
+    return fail_pixie("blur_rows_to: src and dst must be single-layer RGBX images of the same size");
+  if (s->data == d->data) return fail_pixie("blur_rows_to: src and dst must be different images");
+  y0 = std::max(0, y0);
+  y1 = std::min(s->h, y1);
+  if (y0 >= y1) return 0;
+  Runtime& r = rt();
+  const size_t rowBytes = (size_t)s->w * 4;
+  static const char* force = getenv("PIXIE_CUDA_BLUR");
+  if (radius > 0 && !force) {
+    const int rc = blur_tc((const px_t*)s->data, (px_t*)d->data, s->w, s->h, lut, radius, oob, y0, y1, (const unsigned*)top_flag,
+                           (const unsigned*)bottom_flag, epoch);
+    if (rc >= 0) return rc;
+  }
+  if (top_flag || bottom_flag)
+    if (int rc = pixie_cuda_halo_wait2(top_flag, bottom_flag, epoch)) return rc;
+  // other radii / LUTs: the in-place kernels on a copy of the rows they read
+  const int c0 = std::max(0, y0 - radius), c1 = std::min(s->h, y1 + radius);
+  void* keep = nullptr;  // rows of dst outside [y0, y1) that the copy below overwrites are restored afterwards
+  const size_t above = (size_t)(y0 - c0) * rowBytes, below = (size_t)(c1 - y1) * rowBytes;
+  if (above + below) {
+    PX_CUDA(cudaMallocAsync(&keep, above + below, r.stream));
+    if (above) PX_CUDA(cudaMemcpyAsync(keep, d->data + rowBytes * c0, above, cudaMemcpyDeviceToDevice, r.stream));
+    if (below) PX_CUDA(cudaMemcpyAsync((uint8_t*)keep + above, d->data + rowBytes * y1, below, cudaMemcpyDeviceToDevice, r.stream));
+  }
+  PX_CUDA(cudaMemcpyAsync(d->data + rowBytes * c0, s->data + rowBytes * c0, rowBytes * (c1 - c0), cudaMemcpyDeviceToDevice, r.stream));
+  int rc = 0;
+  if (radius > 0) {
+    // the halo rows of dst now equal src's; a cut at c0 / c1 inside the image is farther than `radius` from [y0, y1) only
+    // if the caller's image really ends there, so blur the rows as part of the whole image
+    rc = blur_impl(d, lut, radius, oob, y0, y1);
+  }
+  if (keep) {
+    if (above) PX_CUDA(cudaMemcpyAsync(d->data + rowBytes * c0, keep, above, cudaMemcpyDeviceToDevice, r.stream));
+    if (below) PX_CUDA(cudaMemcpyAsync(d->data + rowBytes * y1, (uint8_t*)keep + above, below, cudaMemcpyDeviceToDevice, r.stream));
+    PX_CUDA(cudaFreeAsync(keep, r.stream));
+  }
+  return rc;
 }
 
 int pixie_cuda_blur_rows_x(pixie_image_t h, const uint16_t* lut, int radius, uint32_t oob, int r0, int r1) {

@@ -57,10 +57,26 @@ struct TcBlurArgs {
   int strips, chunks, chunkRows;
   unsigned* ticket;
   unsigned long long* dbg;  // PIXIE_CUDA_TC_DEBUG: per-phase cycle sums of worker warp 0 and the two issuers
+  // row bands across GPUs: rows [0, y0) / [y1, h) are halo rows a neighbour GPU stores into this image; a ticket that
+  // reads them first waits until the flag (written by that neighbour after its rows) has reached `epoch`
+  const unsigned* flagTop;
+  const unsigned* flagBottom;
+  unsigned epoch;
 };
+
+// tickets in the order interior chunks first, the two edge chunks (the only ones that read halo rows) last
+PXD int tc_chunk_of(int order, int chunks) {
+  if (chunks < 3) return order;
+  return order < chunks - 2 ? order + 1 : (order == chunks - 2 ? 0 : chunks - 1);
+}
 
 __constant__ uint16_t c_tc_lut[2 * kTcMaxRadius + 1 + 3];
 
+PXD unsigned ld_acquire_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 PXD uint32_t tc_quant(uint32_t accBits) {  // (acc * 2^24) div 65280 in the low byte of the result
   return __float_as_uint(__fmaf_rz(__uint_as_float(accBits), kTcInv65280s, 8388608.0f));
 }
@@ -93,8 +109,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc_kernel(const __grid_con
   uint8_t* sToe = base;                  // [128 m][192 k] fp16, K-major: 3 K-blocks of [128][128 B]
   uint8_t* sAx = sToe + kToeBytes;       // 2 buffers of 3 K-blocks [128 lines][128 B]
   uint8_t* sRaw = sAx + 2 * kAxBytes;    // 2 buffers of [32 rows][192 px] RGBX
-  __shared__ uint64_t barRaw[2], barAx[2], barX, barRing, barY, barYFree;
+  __shared__ uint64_t barRaw[2], barAx[2], barX, barRing, barY, barYFree, barTicket[2];
   __shared__ uint32_t tmemSlot;
+  __shared__ int sTicket[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   {  // ---- Toeplitz operand T[m][k] = lut[k - m - (32 - r)], K-major rows m = 0..127, k = 0..191, two halfs per store
@@ -116,6 +133,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc_kernel(const __grid_con
     mbar_init(&barRing, kTcWorkers / 32);
     mbar_init(&barY, 2);
     mbar_init(&barYFree, kTcWorkers / 32);
+    mbar_init(&barTicket[0], 1);
+    mbar_init(&barTicket[1], 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmap);
   }
@@ -140,12 +159,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc_kernel(const __grid_con
       }
       uint32_t pAx[2] = {0, 0}, pRing = 0;
       bool anyX = false;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int chunk = t / a.strips, strip = t - chunk * a.strips;
+      // Tickets (strip, row chunk) are taken from a global counter — a CTA that starts late (a collective's kernels
+      // may hold its SM for a while) simply takes fewer — and published to the other roles through sTicket[k & 1] /
+      // barTicket[k & 1]; the X issuer is the first role that needs the next ticket.
+      for (int kt = 0;; kt++) {
+        const int t = (int)atomicAdd(a.ticket, 1u);
+        sTicket[kt & 1] = t < total ? t : -1;
+        mbar_arrive(&barTicket[kt & 1]);
+        if (t >= total) break;
+        const int ord = t / a.strips, strip = t - ord * a.strips, chunk = tc_chunk_of(ord, a.chunks);
         const int x0 = strip * kTcStripW;
         const int cy0 = a.y0 + chunk * a.chunkRows, cy1 = min(a.y1, cy0 + a.chunkRows);
         const int nb = (cy1 - cy0 + kTcRows - 1) / kTcRows + 2;
         const int rowBase = cy0 - kTcRows;
+        if ((a.flagTop && rowBase < a.y0) || (a.flagBottom && rowBase + kTcRows * nb > a.y1)) {
+          // this ticket reads halo rows: they are complete once the neighbour's epoch flag is there
+          const unsigned* f = (a.flagTop && rowBase < a.y0) ? a.flagTop : nullptr;
+          const unsigned* g2 = (a.flagBottom && rowBase + kTcRows * nb > a.y1) ? a.flagBottom : nullptr;
+          const long long t0_ = clock64();
+          while ((f && (int)(ld_acquire_sys_u32(f) - a.epoch) < 0) || (g2 && (int)(ld_acquire_sys_u32(g2) - a.epoch) < 0)) {
+            __nanosleep(100);
+            if (clock64() - t0_ > 8000000000ll) __trap();
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");  // the TMA reads below come after the flag
+        }
 #pragma unroll 1
         for (int i = 0; i < 2 && i < nb; i++) {  // both raw buffers are free: every earlier block has been converted
           mbar_arrive_expect_tx(&barRaw[i], kRawBytes);
@@ -185,10 +222,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc_kernel(const __grid_con
       uint64_t bd[6];  // B = T[n][k], n < 32, k < 96: the first 32 rows of the X pass's Toeplitz operand
 #pragma unroll
       for (int s = 0; s < 6; s++) bd[s] = smem_desc_sw128(sToeA + (uint32_t)(s >> 2) * kAxBlock + (uint32_t)(s & 3) * 32u, 16, 1024);
-      uint32_t pRing = 0, pYFree = 0;
+      uint32_t pRing = 0, pYFree = 0, pT[2] = {0, 0};
       bool anyY = false;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int chunk = t / a.strips;
+      for (int kt = 0;; kt++) {
+        mbar_wait(&barTicket[kt & 1], pT[kt & 1]);
+        pT[kt & 1] ^= 1;
+        const int t = sTicket[kt & 1];
+        if (t < 0) break;
+        const int chunk = tc_chunk_of(t / a.strips, a.chunks);
         const int cy0 = a.y0 + chunk * a.chunkRows, cy1 = min(a.y1, cy0 + a.chunkRows);
         const int nb = (cy1 - cy0 + kTcRows - 1) / kTcRows + 2;
 #pragma unroll 1
@@ -227,8 +268,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc_kernel(const __grid_con
     long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = DBG ? clock64() : 0;
 #define TC_MARK(slot) if (DBG) { const long long n_ = clock64(); tm[slot] += n_ - tc0; tc0 = n_; }
     const int q = warp & 3, wg = warp >> 2;  // TMEM lane quarter (32 of the strip's columns); channel (X) / 8 rows (Y)
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      const int chunk = t / a.strips, strip = t - chunk * a.strips;
+    uint32_t pT[2] = {0, 0};
+    for (int kt = 0;; kt++) {
+      mbar_wait(&barTicket[kt & 1], pT[kt & 1]);
+      pT[kt & 1] ^= 1;
+      const int t = sTicket[kt & 1];
+      if (t < 0) break;
+      const int ord = t / a.strips, strip = t - ord * a.strips, chunk = tc_chunk_of(ord, a.chunks);
       const int x0 = strip * kTcStripW;
       const int cy0 = a.y0 + chunk * a.chunkRows, cy1 = min(a.y1, cy0 + a.chunkRows);
       const int outBlocks = (cy1 - cy0 + kTcRows - 1) / kTcRows, nb = outBlocks + 2;
@@ -398,7 +444,8 @@ static int launch_tc(const CUtensorMap& tmap, const TcBlurArgs& a, int blocks, c
 
 // Fused tensor-core blur of rows [y0, y1) of `src` (w x h RGBX) into `dst` (same geometry, a different buffer).
 // -1: outside this kernel's domain (radius > 32, LUT not exact in fp32, width not a multiple of 4, no TMA entry point).
-int blur_tc(const px_t* src, px_t* dst, int w, int h, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1) {
+int blur_tc(const px_t* src, px_t* dst, int w, int h, const uint16_t* lut_host, int radius, uint32_t oob, int y0, int y1,
+            const unsigned* flagTop, const unsigned* flagBottom, unsigned epoch) {
   if (radius < 1 || radius > kTcMaxRadius || (w & 3) != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0) return -1;
   const int ntaps = 2 * radius + 1;
   unsigned long long sum = 0;
@@ -429,6 +476,7 @@ int blur_tc(const px_t* src, px_t* dst, int w, int h, const uint16_t* lut_host, 
   }
   TcBlurArgs a;
   a.dst = dst; a.w = w; a.h = h; a.radius = radius; a.oob = oob; a.y0 = y0; a.y1 = y1;
+  a.flagTop = flagTop; a.flagBottom = flagBottom; a.epoch = epoch;
   a.strips = (w + kTcStripW - 1) / kTcStripW;
   // row chunks: a chunk re-blurs 64 warm-up rows horizontally, so long chunks are cheaper; but the tickets
   // (strip, chunk) are handed out dynamically to one CTA per SM and should outnumber the SMs a few times over
@@ -437,16 +485,19 @@ int blur_tc(const px_t* src, px_t* dst, int w, int h, const uint16_t* lut_host, 
   while (chunkRows > 128 && (long long)a.strips * ((rows + chunkRows - 1) / chunkRows) < 2ll * r.num_sms) chunkRows /= 2;
   a.chunkRows = chunkRows;
   a.chunks = (rows + chunkRows - 1) / chunkRows;
-  a.ticket = nullptr;  // tickets are dealt round-robin: every (strip, chunk) costs the same
+  void* tk;
+  if (int rc = get_scratch(3, 512, &tk)) return rc;
+  PX_CUDA(cudaMemsetAsync(tk, 0, 8, r.stream));
+  a.ticket = (unsigned*)tk;
   a.dbg = nullptr;
   static const bool dbgOn = getenv("PIXIE_CUDA_TC_DEBUG") != nullptr;
   if (dbgOn) {
     void* d;
-    if (int rc = get_scratch(3, 32 * 8, &d)) return rc;
+    d = (uint8_t*)tk + 64;
     PX_CUDA(cudaMemsetAsync(d, 0, 32 * 8, r.stream));
     a.dbg = (unsigned long long*)d;
   }
-  const int blocks = std::min(a.strips * a.chunks, r.num_sms);
+  const int blocks = std::max(1, std::min(a.strips * a.chunks, r.num_sms - r.sm_reserve));
   ProfScope ps(kProfBlurX);
   const int rcl = launch_tc(tmap, a, blocks, r.stream);
   if (dbgOn && rcl == 0) {  // per-phase cycles of worker warps 0 and 9 and of the issuers, averaged per 32-row block

@@ -26,6 +26,7 @@ struct Runtime {
   bool inited = false;
   int device = 0;
   int num_sms = 148;
+  int sm_reserve = 0;  // SMs the persistent one-CTA-per-SM kernels leave free (pixie_cuda_set_sm_reserve)
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   std::mutex mu;

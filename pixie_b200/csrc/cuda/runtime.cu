@@ -212,6 +212,14 @@ int pixie_cuda_set_stream(void* s) {
   return 0;
 }
 
+int pixie_cuda_set_sm_reserve(int sms) {
+  PX_API_GUARD;
+  if (int rc = ensure_init()) return rc;
+  Runtime& r = rt();
+  r.sm_reserve = std::max(0, std::min(sms, r.num_sms - 1));
+  return 0;
+}
+
 int pixie_cuda_sync(void) {
   PX_API_GUARD;
   if (int rc = ensure_init()) return rc;

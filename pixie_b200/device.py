@@ -27,6 +27,7 @@ _SIGNATURES = {
     "pixie_cuda_init": [i32],
     "pixie_cuda_set_stream": [vp],
     "pixie_cuda_sync": [],
+    "pixie_cuda_set_sm_reserve": [i32],
     "pixie_cuda_device_count": [P(i32)],
     "pixie_cuda_image_create": [i32, i32, P(u64)],
     "pixie_cuda_image_create_layers": [i32, i32, i32, P(u64)],
@@ -61,6 +62,8 @@ _SIGNATURES = {
     "pixie_cuda_fill_gradient": [u64, i32, vp, i32, vp, vp, i32, f32],
     "pixie_cuda_blur": [u64, vp, i32, u32],
     "pixie_cuda_blur_rows": [u64, vp, i32, u32, i32, i32],
+    "pixie_cuda_blur_rows_to": [u64, u64, vp, i32, u32, i32, i32],
+    "pixie_cuda_blur_rows_to_flags": [u64, u64, vp, i32, u32, i32, i32, vp, vp, u32],
     "pixie_cuda_blur_rows_x": [u64, vp, i32, u32, i32, i32],
     "pixie_cuda_blur_rows_y": [u64, vp, i32, u32, i32, i32],
     "pixie_cuda_spread": [u64, i32],
@@ -78,6 +81,14 @@ _SIGNATURES = {
     "pixie_cuda_fill_gradient_host": [vp, i32, i32, i32, vp, i32, vp, vp, i32, f32],
     "pixie_cuda_minify_by2_host": [vp, i32, i32, i32, vp],
     "pixie_cuda_magnify_by2_host": [vp, i32, i32, i32, vp],
+    "pixie_cuda_peer_alloc": [C.c_size_t, P(vp), vp],
+    "pixie_cuda_peer_open": [vp, P(vp)],
+    "pixie_cuda_peer_close": [vp],
+    "pixie_cuda_peer_free": [vp],
+    "pixie_cuda_halo_push": [vp, vp, C.c_size_t, vp, u32],
+    "pixie_cuda_halo_wait": [vp, u32],
+    "pixie_cuda_halo_exchange": [vp, vp, u32],
+    "pixie_cuda_halo_wait2": [vp, vp, u32],
     "pixie_cuda_host_alloc": [C.c_size_t, P(vp)],
     "pixie_cuda_host_free": [vp],
     "pixie_cuda_set_profiling": [i32],
@@ -141,6 +152,10 @@ def current_device():
 
 def sync():
     check(lib().pixie_cuda_sync())
+
+
+def set_sm_reserve(sms: int):
+    check(lib().pixie_cuda_set_sm_reserve(sms))
 
 
 def set_stream(cuda_stream_ptr):
@@ -384,6 +399,16 @@ def blur_rows(image: DeviceImage, lut, radius, oob, y0, y1):
     check(lib().pixie_cuda_blur_rows(image.handle, lut.ctypes.data, radius, oob, y0, y1))
 
 
+def blur_rows_to(src: DeviceImage, dst: DeviceImage, lut, radius, oob, y0, y1):
+    lut = np.ascontiguousarray(lut, np.uint16)
+    check(lib().pixie_cuda_blur_rows_to(src.handle, dst.handle, lut.ctypes.data, radius, oob, y0, y1))
+
+
+def blur_rows_to_flags(src: DeviceImage, dst: DeviceImage, lut, radius, oob, y0, y1, top_flag, bottom_flag, epoch):
+    lut = np.ascontiguousarray(lut, np.uint16)
+    check(lib().pixie_cuda_blur_rows_to_flags(src.handle, dst.handle, lut.ctypes.data, radius, oob, y0, y1, top_flag, bottom_flag, epoch))
+
+
 def blur_rows_x(image: DeviceImage, lut, radius, oob, r0, r1):
     lut = np.ascontiguousarray(lut, np.uint16)
     check(lib().pixie_cuda_blur_rows_x(image.handle, lut.ctypes.data, radius, oob, r0, r1))
@@ -410,6 +435,67 @@ def spread(image: DeviceImage, amount):
 def shadow(src: DeviceImage, dst: DeviceImage, ox, oy, spread_, lut, radius, rgbx):
     lut = np.ascontiguousarray(lut, np.uint16)
     check(lib().pixie_cuda_shadow(src.handle, dst.handle, ox, oy, spread_, lut.ctypes.data, radius, rgbx))
+
+
+class PeerBuffer:
+    """A device buffer other processes of the box can map (CUDA IPC), exposed to torch / numpy-style consumers through
+    __cuda_array_interface__ (uint8).  `handle` (64 bytes) goes to the neighbours; `PeerBuffer.open(handle, nbytes)`
+    maps theirs."""
+
+    def __init__(self, nbytes: int, _ptr=None, _opened=False):
+        self.nbytes, self._opened = nbytes, _opened
+        if _ptr is not None:
+            self.ptr, self.handle = _ptr, None
+            return
+        p = vp()
+        h = (C.c_uint8 * 64)()
+        check(lib().pixie_cuda_peer_alloc(nbytes, C.byref(p), h))
+        self.ptr, self.handle = p.value, bytes(h)
+
+    @classmethod
+    def open(cls, handle: bytes, nbytes: int):
+        p = vp()
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        check(lib().pixie_cuda_peer_open(h, C.byref(p)))
+        return cls(nbytes, _ptr=p.value, _opened=True)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            (lib().pixie_cuda_peer_close if self._opened else lib().pixie_cuda_peer_free)(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def halo_push(src_ptr: int, peer_dst_ptr: int, nbytes: int, peer_flag_ptr: int, value: int):
+    check(lib().pixie_cuda_halo_push(src_ptr, peer_dst_ptr, nbytes, peer_flag_ptr, value))
+
+
+class HaloDir(C.Structure):
+    """pixie_halo_dir_t of include/pixie_cuda.h."""
+    _fields_ = [("src_rows", vp), ("peer_dst_rows", vp), ("bytes", C.c_size_t), ("peer_ready_flag", vp),
+                ("peer_data_flag", vp), ("local_ready_flag", vp)]
+
+
+def halo_exchange(up, down, epoch: int):
+    """up / down: HaloDir or None."""
+    check(lib().pixie_cuda_halo_exchange(C.byref(up) if up is not None else None, C.byref(down) if down is not None else None, epoch))
+
+
+def halo_wait2(flag_a, flag_b, value: int):
+    check(lib().pixie_cuda_halo_wait2(flag_a, flag_b, value))
+
+
+def halo_wait(local_flag_ptr: int, value: int):
+    check(lib().pixie_cuda_halo_wait(local_flag_ptr, value))
 
 
 class PinnedBuffer:

@@ -140,14 +140,94 @@ class RowBand:
 
     rb = RowBand(height, width, rank, world, margin=64); rb.band[...] = pixels; rb.blur(32, lut, 0)"""
 
-    def __init__(self, height: int, width: int, rank: int, world: int, margin: int, device="cuda", group=None):
+    def __init__(self, height: int, width: int, rank: int, world: int, margin: int, device="cuda", group=None,
+                 transport: str = "auto"):
+        """transport: how halo rows travel.  "nccl": torch.distributed point-to-point send / recv (NCCL over NVLink on
+        GPUs, gloo in the CPU tests).  "peer": the band buffers are CUDA-IPC mapped into the neighbours' processes and a
+        small kernel stores the edge rows straight into the neighbour's margin over NVLink, followed by an epoch flag
+        (pixie_cuda_halo_push / _wait) — no collective launch, a few microseconds instead of a send / recv pair's
+        ~0.1 ms.  "auto": "peer" on CUDA devices when the IPC mapping works, else "nccl"."""
         import torch
 
         self.height, self.width, self.rank, self.world, self.margin, self.group = height, width, rank, world, margin, group
+        self.sm_reserve = 0
         self.sizes = [band_range(height, world, k)[1] - band_range(height, world, k)[0] for k in range(world)]
         self.rows = self.sizes[rank]
-        self.buf = torch.zeros((margin + self.rows + margin, width, 4), dtype=torch.uint8, device=device)
+        self.cur = 0      # which of the two buffers holds the band (blur is out of place and swaps them)
+        self.epoch = 0    # halo exchanges so far (identical on every rank: exchanges are collective calls)
+        self.transport = "nccl"
+        self._peer = None
+        on_cuda = str(device).startswith("cuda")
+        if transport in ("auto", "peer") and on_cuda and world > 1:
+            try:
+                self._init_peer()
+                self.transport = "peer"
+            except Exception as e:  # no IPC in this container, no peer access: fall back to send / recv
+                if transport == "peer":
+                    raise
+                self.peer_error = repr(e)[:120]
+        if self.transport == "nccl":
+            self.buf = torch.zeros((margin + self.rows + margin, width, 4), dtype=torch.uint8, device=device)
+            self.buf2 = None
         self.band = self.buf[margin:margin + self.rows]
+
+    # ---- peer transport: one IPC allocation per rank = [flags 256 B][buffer 0][buffer 1]
+    def _buf_bytes(self, k: int) -> int:
+        return ((self.margin + self.sizes[k] + self.margin) * self.width * 4 + 255) & ~255
+
+    def _init_peer(self):
+        import torch
+        import torch.distributed as dist
+
+        from . import device as dev
+
+        nbytes = 256 + 2 * self._buf_bytes(self.rank)
+        mine = dev.PeerBuffer(nbytes)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine.handle, group=self.group)
+        peers = {}
+        for k in (self.rank - 1, self.rank + 1):
+            if 0 <= k < self.world:
+                peers[k] = dev.PeerBuffer.open(handles[k], 256 + 2 * self._buf_bytes(k))
+        dist.barrier(group=self.group)  # every mapping exists before anybody pushes
+        self._peer = {"mine": mine, "peers": peers}
+        flat = torch.as_tensor(mine, device="cuda")
+        bb = self._buf_bytes(self.rank)
+        shape = (self.margin + self.rows + self.margin, self.width, 4)
+        nb = shape[0] * shape[1] * 4
+        self.buf = flat[256:256 + nb].view(shape)
+        self.buf2 = flat[256 + bb:256 + bb + nb].view(shape)
+        self._flat = flat
+
+    def _peer_exchange_start(self, radius: int):
+        """Stream-ordered: tell the neighbours this rank's margins are free, wait for theirs, push the edge rows."""
+        from . import device as dev
+
+        self.epoch += 1
+        e, r, w, m = self.epoch, self.rank, self.world, self.margin
+        top, bottom = self.halo_rows(radius)
+        send = min(radius, self.rows)
+        row_bytes = self.width * 4
+        mine, peers = self._peer["mine"], self._peer["peers"]
+        # flags of a rank (uint32, written by its neighbours): [0] rows from above arrived, [1] rows from below arrived,
+        # [2] the upper neighbour's bottom margin is free, [3] the lower neighbour's top margin is free
+        up = down = None
+        if r > 0:
+            k = r - 1
+            up = dev.HaloDir(self.band.data_ptr(), peers[k].ptr + 256 + self.cur * self._buf_bytes(k) + (m + self.sizes[k]) * row_bytes,
+                             send * row_bytes, peers[k].ptr + 12, peers[k].ptr + 4, mine.ptr + 8)
+        if r < w - 1:
+            k = r + 1
+            down = dev.HaloDir(self.band[self.rows - send:].data_ptr(), peers[k].ptr + 256 + self.cur * self._buf_bytes(k) + (m - send) * row_bytes,
+                               send * row_bytes, peers[k].ptr + 8, peers[k].ptr + 0, mine.ptr + 12)
+        dev.halo_exchange(up, down, e)
+        return top, bottom
+
+    def _peer_exchange_finish(self):
+        from . import device as dev
+
+        mine = self._peer["mine"]
+        dev.halo_wait2(mine.ptr + 0 if self.rank > 0 else None, mine.ptr + 4 if self.rank < self.world - 1 else None, self.epoch)
 
     def halo_rows(self, radius: int):
         """(top, bottom): halo rows this rank receives for a filter of `radius` rows."""
@@ -164,11 +244,18 @@ class RowBand:
         ext = the contiguous view [halo_top ; band ; halo_bottom] of the buffer."""
         import torch.distributed as dist
 
+        m = self.margin
+        if self.transport == "peer":
+            from . import device as dev
+
+            dev.set_stream(torch_stream_handle())
+            top, bottom = self._peer_exchange_start(radius)
+            self._peer_exchange_finish()
+            return self.buf[m - top:m + self.rows + bottom], top, bottom
         ops, top, bottom = self._halo_ops(radius)
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-        m = self.margin
         return self.buf[m - top:m + self.rows + bottom], top, bottom
 
     def _halo_ops(self, radius: int):
@@ -186,56 +273,78 @@ class RowBand:
             ops.append(dist.P2POp(dist.irecv, self.buf[m + rows:m + rows + bottom], r + 1, group=self.group))
         return ops, top, bottom
 
-    def _ext_image(self, top: int, bottom: int):
-        """DeviceImage over [halo_top ; band ; halo_bottom] of the buffer (cached per halo size)."""
+    def _ext_image(self, top: int, bottom: int, buf=None):
+        """DeviceImage over [halo_top ; band ; halo_bottom] of a buffer (cached per buffer and halo size)."""
         from . import device as dev
 
-        key = (top, bottom)
+        buf = self.buf if buf is None else buf
+        key = (buf.data_ptr(), top, bottom)
         cache = self.__dict__.setdefault("_ext_cache", {})
         if key not in cache:
-            ext = self.buf[self.margin - top:self.margin + self.rows + bottom]
-            cache[key] = dev.DeviceImage.wrap(ext.data_ptr(), self.width, ext.shape[0], owner=self.buf)
+            ext = buf[self.margin - top:self.margin + self.rows + bottom]
+            cache[key] = dev.DeviceImage.wrap(ext.data_ptr(), self.width, ext.shape[0], owner=buf)
         return cache[key]
 
     def blur(self, radius: int, lut: np.ndarray, oob_rgbx: int, overlap: bool = True):
-        """Blur the band in place as part of the whole canvas: rows at the true image border see `oob_rgbx`, interior
-        cuts see the neighbours' rows.
+        """Blur the band as part of the whole canvas: rows at the true image border see `oob_rgbx`, interior cuts see
+        the neighbours' rows.  Returns the band (``self.band``), which afterwards lives in the band's SECOND buffer:
+        the blur is out of place (pixie_cuda_blur_rows_to), the two buffers swap roles on every call.
 
-        overlap=True: the halo exchange runs on a side stream WHILE the horizontal pass — which
-        needs no halo — blurs the band's own rows on the main stream; when the neighbours' rows have arrived their
-        2 x radius rows get the horizontal pass and the vertical pass finishes the band.  NCCL's fixed send / recv
-        latency (~0.2 ms for 4 MiB that NVLink moves in ~5 us) is hidden behind the X pass instead of preceding it."""
+        overlap=True: the band's interior — which depends on the band's own rows only — is blurred
+        while the halo rows travel.  transport "peer": one exchange kernel (stores into the neighbours' margins + epoch
+        flags) and ONE blur kernel behind it whose tiles wait for the flags only if they read halo rows.  transport
+        "nccl": the send / recv pair is started first, the interior rows [radius, rows - radius) are blurred, and
+        after `wait()` the two edge strips of `radius` rows follow."""
         import torch
 
         from . import device as dev
 
         main = torch.cuda.current_stream()
+        if self.buf2 is None:
+            self.buf2 = torch.zeros_like(self.buf)
         dev.set_stream(torch_stream_handle())  # the kernels are ordered with torch's work on this stream
         try:
-            if not overlap or radius > 64:
-                ext, top, bottom = self.exchange(radius)
-                dev.blur_rows(self._ext_image(top, bottom), lut, radius, oob_rgbx, top, top + self.rows)
-                return self.band
             import torch.distributed as dist
 
-            ops, top, bottom = self._halo_ops(radius)
-            img = self._ext_image(top, bottom)
-            side = self.__dict__.get("_side")
-            if side is None:
-                side = self._side = torch.cuda.Stream()
-            if ops:
-                side.wait_stream(main)  # the band's pixels are complete before they are sent
-                with torch.cuda.stream(side):
+            peer = self.transport == "peer"
+            if peer:
+                top, bottom = self._peer_exchange_start(radius)  # the rows are on their way over NVLink
+                ops = []
+            else:
+                ops, top, bottom = self._halo_ops(radius)
+            src, dst = self._ext_image(top, bottom), self._ext_image(top, bottom, self.buf2)
+            b0, b1 = top, top + self.rows
+            split = overlap and (peer or ops) and self.rows > 2 * radius and self.world > 1
+            if peer:
+                # ONE blur launch right behind the exchange kernel: its interior tiles start at once, the tiles that
+                # read halo rows wait — inside the kernel — for the epoch flag the neighbour publishes after its rows
+                mine = self._peer["mine"]
+                if overlap:
+                    dev.blur_rows_to_flags(src, dst, lut, radius, oob_rgbx, b0, b1, mine.ptr + 0 if self.rank > 0 else None,
+                                           mine.ptr + 4 if self.rank < self.world - 1 else None, self.epoch)
+                else:
+                    self._peer_exchange_finish()
+                    dev.blur_rows_to(src, dst, lut, radius, oob_rgbx, b0, b1)
+            elif split:
+                # torch's NCCL process group runs send / recv on its own stream, ordered after the work already queued
+                # on this one; `req.wait()` makes this stream wait for them — so the exchange is simply started first
+                # and waited for after the interior rows
+                reqs = dist.batch_isend_irecv(ops)
+                dev.set_sm_reserve(self.sm_reserve)  # optionally leave SMs to NCCL beside the one-CTA-per-SM blur
+                dev.blur_rows_to(src, dst, lut, radius, oob_rgbx, b0 + radius, b1 - radius)  # no halo row is read
+                dev.set_sm_reserve(0)
+                for req in reqs:
+                    req.wait()
+                dev.blur_rows_to(src, dst, lut, radius, oob_rgbx, b0, b0 + radius)
+                dev.blur_rows_to(src, dst, lut, radius, oob_rgbx, b1 - radius, b1)
+            else:
+                if ops:
                     for req in dist.batch_isend_irecv(ops):
-                        req.wait()  # stream-side wait: `side` continues when the halo rows are in place
-            dev.blur_rows_x(img, lut, radius, oob_rgbx, top, top + self.rows)  # own rows: no halo needed
-            if ops:
-                main.wait_stream(side)
-            if top:
-                dev.blur_rows_x(img, lut, radius, oob_rgbx, 0, top)
-            if bottom:
-                dev.blur_rows_x(img, lut, radius, oob_rgbx, top + self.rows, top + self.rows + bottom)
-            dev.blur_rows_y(img, lut, radius, oob_rgbx, top, top + self.rows)
+                        req.wait()
+                dev.blur_rows_to(src, dst, lut, radius, oob_rgbx, b0, b1)
+            self.cur ^= 1
+            self.buf, self.buf2 = self.buf2, self.buf
+            self.band = self.buf[self.margin:self.margin + self.rows]
             return self.band
         finally:
             dev.set_stream(None)

@@ -274,3 +274,29 @@ def test_two_host_threads_on_distinct_handles():
         t.join()
     assert not errors, errors
     assert results == {1: 0, 2: 0, 3: 0, 4: 0}
+
+
+@pytest.mark.parametrize("radius,w", [(32, 128), (30, 260), (20, 96), (32, 101), (40, 64)])
+def test_blur_rows_to_composes_interior_and_edges(radius, w):
+    """pixie_cuda_blur_rows_to: out of place, src untouched, dst rows outside the range untouched; a band blurred as
+    interior rows + two edge strips (how multi.RowBand overlaps the halo exchange) equals the oracle — on the fused
+    tcgen05 path (taps < 2048, width % 4 == 0) and on the fallback (other radii / widths)."""
+    _, dev = _lib()
+    h = 260
+    img = synth.random_premultiplied(h, w, radius + w)
+    lut = host.gaussianKernel(radius)
+    oob = pack(7, 9, 11, 130)
+    want = img.copy()
+    _o().blur(want, lut, radius, oob)
+    s = dev.DeviceImage(w, h).upload(img)
+    canary = np.full((h, w, 4), 0x5A, np.uint8)
+    d = dev.DeviceImage(w, h).upload(canary)
+    y0, y1 = 40, 230
+    dev.blur_rows_to(s, d, lut, radius, oob, y0 + radius, y1 - radius)
+    dev.blur_rows_to(s, d, lut, radius, oob, y0, y0 + radius)
+    dev.blur_rows_to(s, d, lut, radius, oob, y1 - radius, y1)
+    got = d.download()
+    n, mx, where = diff_report(got[y0:y1], want[y0:y1])
+    assert n == 0, f"{n} px differ (max {mx}) at {where}"
+    assert np.array_equal(got[:y0], canary[:y0]) and np.array_equal(got[y1:], canary[y1:]), "rows outside [y0, y1) of dst changed"
+    assert np.array_equal(s.download(), img), "src changed"
