@@ -89,6 +89,8 @@ struct CmdList {
   std::vector<int> hostStartY, hostPathHeight;  // per fill; pathHeight <= startY when the fill has no jobs
   int maxWrapRows = 0;                          // MaskBlend fills reaching left of the canvas read jobs of later rows
   int* rowsJobBase = nullptr;                   // device [numFills + 1], made per run_rows call
+  int* bandRows = nullptr;                      // device [numParts]: rows of every band (static)
+  unsigned long long* chunkSums = nullptr;      // device [2 * chunks]: scratch of the band scans
 };
 
 static std::unordered_map<uint64_t, CmdList> g_lists;
@@ -1698,6 +1700,121 @@ __global__ void __launch_bounds__(1024) payload_scan_kernel(const FillHeader* __
   }
 }
 
+// Rows of every band (static per list: the last band of a fill absorbs the remainder, :1192) — made once at build.
+__global__ void __launch_bounds__(256) band_rows_kernel(const FillHeader* __restrict__ fills, int numFills, int numParts,
+                                                        int* __restrict__ bandRows) {
+  const int gp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gp >= numParts) return;
+  const FillHeader H = fills[find_fill<true>(fills, numFills, gp)];
+  const int p = gp - H.partBase;
+  const int top = H.startY + p * H.partitionHeight;
+  const int bottom = (p == H.numPartitions - 1) ? H.pathHeight : top + H.partitionHeight;
+  bandRows[gp] = bottom - top;
+}
+
+// K1b / K1c as two short multi-block kernels (the single-block scans took 1 ms on a 118 000-band icon batch):
+// band_sum_kernel: per chunk of kScanChunk bands the sums of entries and of payload entry-rows and the largest
+// count; the last block to finish turns the chunk sums into exclusive prefixes and leaves {entries, max, payload}
+// in meta.  band_scan_kernel: each block rescans its chunk from its prefix: counts -> entry offsets (in place),
+// payload offsets.
+constexpr int kScanChunk = 2048;  // 256 threads x 8 bands
+__global__ void __launch_bounds__(256) band_sum_kernel(const int* __restrict__ cnt, const int* __restrict__ bandRows, int n,
+                                                       unsigned long long* __restrict__ chunkCnt, unsigned long long* __restrict__ chunkPay,
+                                                       unsigned* __restrict__ ticket, unsigned long long* __restrict__ meta, int numChunks) {
+  __shared__ unsigned long long sc[8], sp[8];
+  __shared__ int sm[8];
+  __shared__ bool last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int base = blockIdx.x * kScanChunk;
+  unsigned long long c = 0, pay = 0;
+  int mx = 0;
+  for (int i = base + tid; i < min(base + kScanChunk, n); i += 256) {
+    const int v = cnt[i];
+    c += (unsigned long long)v;
+    pay += (unsigned long long)v * (unsigned long long)bandRows[i];
+    mx = max(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    pay += __shfl_xor_sync(0xffffffffu, pay, o);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) { sc[warp] = c; sp[warp] = pay; sm[warp] = mx; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 1; k < 8; k++) { c += sc[k]; pay += sp[k]; mx = max(mx, sm[k]); }
+    chunkCnt[blockIdx.x] = c;
+    chunkPay[blockIdx.x] = pay;
+    atomicMax(reinterpret_cast<unsigned long long*>(&meta[1]), (unsigned long long)mx);
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == (unsigned)numChunks - 1u;
+  }
+  __syncthreads();
+  if (last && warp == 0) {  // exclusive prefixes of the chunk sums, 32 chunks per step
+    __threadfence();
+    unsigned long long runC = 0, runP = 0;
+    for (int b0 = 0; b0 < numChunks; b0 += 32) {
+      const int k = b0 + lane;
+      const unsigned long long vc = k < numChunks ? chunkCnt[k] : 0, vp = k < numChunks ? chunkPay[k] : 0;
+      unsigned long long ic = vc, ip = vp;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long tc = __shfl_up_sync(0xffffffffu, ic, o), tp = __shfl_up_sync(0xffffffffu, ip, o);
+        if (lane >= o) { ic += tc; ip += tp; }
+      }
+      if (k < numChunks) { chunkCnt[k] = runC + ic - vc; chunkPay[k] = runP + ip - vp; }
+      runC += __shfl_sync(0xffffffffu, ic, 31);
+      runP += __shfl_sync(0xffffffffu, ip, 31);
+    }
+    if (lane == 0) {
+      meta[0] = runC;
+      meta[2] = runP;
+      *ticket = 0u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) band_scan_kernel(int* __restrict__ cnt, const int* __restrict__ bandRows, unsigned* __restrict__ payOff,
+                                                        int n, const unsigned long long* __restrict__ chunkCnt,
+                                                        const unsigned long long* __restrict__ chunkPay, const unsigned long long* __restrict__ meta) {
+  __shared__ unsigned long long wc[8], wp[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = blockIdx.x * kScanChunk + tid * 8;  // 8 consecutive bands per thread
+  int v[8];
+  unsigned long long w[8], c = 0, pay = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    v[k] = i0 + k < n ? cnt[i0 + k] : 0;
+    w[k] = i0 + k < n ? (unsigned long long)v[k] * (unsigned long long)bandRows[i0 + k] : 0;
+    c += (unsigned long long)v[k];
+    pay += w[k];
+  }
+  unsigned long long ic = c, ip = pay;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long tc = __shfl_up_sync(0xffffffffu, ic, o), tp = __shfl_up_sync(0xffffffffu, ip, o);
+    if (lane >= o) { ic += tc; ip += tp; }
+  }
+  if (lane == 31) { wc[warp] = ic; wp[warp] = ip; }
+  __syncthreads();
+  unsigned long long runC = chunkCnt[blockIdx.x] + ic - c, runP = chunkPay[blockIdx.x] + ip - pay;
+  for (int k = 0; k < warp; k++) { runC += wc[k]; runP += wp[k]; }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    if (i0 + k < n) {
+      cnt[i0 + k] = (int)runC;
+      payOff[i0 + k] = (unsigned)runP;
+    }
+    runC += (unsigned long long)v[k];
+    runP += w[k];
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    cnt[n] = (int)meta[0];
+    payOff[n] = (unsigned)meta[2];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host: command lists
 // ---------------------------------------------------------------------------------------------
@@ -1743,9 +1860,12 @@ static int device_count(CmdList& L) {
   const int cblocks = (int)std::min<int64_t>((L.numSegs + 255) / 256, (int64_t)r.num_sms * 8);
   count_kernel<<<std::max(cblocks, 1), 256, 0, r.stream>>>(L.fills, L.numFills, L.segs, (int)L.numSegs, L.entryOff, L.ranges, L.groupRange);
   PX_LAUNCHED();
-  scan_kernel<<<1, 1024, 0, r.stream>>>(L.entryOff, (int)P, L.counters + 2);
+  const int numChunks = (int)((P + kScanChunk - 1) / kScanChunk);
+  PX_CUDA(cudaMemsetAsync(L.counters + 2, 0, 24, r.stream));  // {entries, max, payload}
+  band_sum_kernel<<<numChunks, 256, 0, r.stream>>>(L.entryOff, L.bandRows, (int)P, L.chunkSums, L.chunkSums + numChunks,
+                                                   reinterpret_cast<unsigned*>(L.counters + 5), L.counters + 2, numChunks);
   PX_LAUNCHED();
-  payload_scan_kernel<<<1, 1024, 0, r.stream>>>(L.fills, L.numFills, L.entryOff, (int)P, L.payOff, L.counters + 4);
+  band_scan_kernel<<<numChunks, 256, 0, r.stream>>>(L.entryOff, L.bandRows, L.payOff, (int)P, L.chunkSums, L.chunkSums + numChunks, L.counters + 2);
   PX_LAUNCHED();
   return 0;
 }
@@ -1976,6 +2096,9 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   const size_t oGroups = off;    off = al(off + ((size_t)numSegs / 32 + 2) * 4);           // ... and of each group of 32
   const size_t oSlots = off;     off = al(off + (size_t)((L.scratchSlotCount + 31) / 32) * 4);
   const size_t oCounters = off;  off = al(off + 256);           // [0] row ticket, [1] covered px, [2] entries, [3] max, [4..11] band tickets, [16..31] heavy-job counts (front / back of each launch's list)
+  // device-only scratch of the band scans (not part of what a host-counted list copies in)
+  const size_t oBandRows = off;  off = al(off + std::max<size_t>(1, P) * 4);
+  const size_t oChunks = off;    off = al(off + (2 * ((P + kScanChunk - 1) / kScanChunk) + 2) * 8);
   const size_t totalA = off;
   if (arena) {
     void* blk;
@@ -2103,6 +2226,8 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   L.ranges = (uint32_t*)(L.block + oRanges);
   L.groupRange = (uint32_t*)(L.block + oGroups);
   L.counters = (unsigned long long*)(L.block + oCounters);
+  L.bandRows = (int*)(L.block + oBandRows);
+  L.chunkSums = (unsigned long long*)(L.block + oChunks);
   L.h2dBytes = h2dBytes;
 
   // K1a/K1b on the device (lists too large to count on the host): how many entries each band gets
@@ -2112,6 +2237,9 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   if (!hostCount) {
     if (P > 0) {
       L.numParts = numPartsTotal;
+      PX_CUDA(cudaMemsetAsync(L.counters, 0, 256, r.stream));
+      band_rows_kernel<<<(int)((P + 255) / 256), 256, 0, r.stream>>>(L.fills, numFills, (int)P, L.bandRows);
+      PX_LAUNCHED();
       if (int rc = device_count(L)) return rc;
       L.deviceCounted = true;
       L.countFresh = true;
@@ -2259,7 +2387,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
       raster_kernel<<<blocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
     }
     PX_LAUNCHED();
-  } else if (!host_pixels || L.bands <= 1) {
+  } else if (L.bands <= 1) {
     if (L.totalJobs > 0) {
       ProfScope ps(kProfPlan);
       A.heavyList = L.heavyList;
@@ -2323,8 +2451,9 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
       raster_kernel<<<blocks, L.warpsPerBlock * 32, L.smemBytes, r.band_stream[b]>>>(B);
       PX_LAUNCHED();
       if (g_trace) PX_CUDA(cudaEventRecord(tev[2 + 3 * b], r.band_stream[b]));
-      PX_CUDA(cudaMemcpyAsync(host_pixels + (size_t)B.rowBegin * rowBytes, im->data + (size_t)B.rowBegin * rowBytes,
-                              (size_t)(B.rowEnd - B.rowBegin) * rowBytes, cudaMemcpyDeviceToHost, r.band_stream[b]));
+      if (host_pixels)
+        PX_CUDA(cudaMemcpyAsync(host_pixels + (size_t)B.rowBegin * rowBytes, im->data + (size_t)B.rowBegin * rowBytes,
+                                (size_t)(B.rowEnd - B.rowBegin) * rowBytes, cudaMemcpyDeviceToHost, r.band_stream[b]));
       if (g_trace) PX_CUDA(cudaEventRecord(tev[3 + 3 * b], r.band_stream[b]));
       PX_CUDA(cudaEventRecord(r.band_done[b], r.band_stream[b]));
       PX_CUDA(cudaStreamWaitEvent(r.stream, r.band_done[b], 0));
@@ -2369,7 +2498,10 @@ int pixie_cuda_cmdlist_create(int w, int h, int layers, int numFills, const int3
   PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   CmdList L;
-  int rc = build_list(L, false, 1, w, h, layers, numFills, layerOf, seg, wind, segOff, rgbx, rule, mode);
+  static const int residentBands = getenv("PIXIE_CUDA_BANDS") ? atoi(getenv("PIXIE_CUDA_BANDS")) : 1;
+  // single-canvas lists are planned and rasterised in row bands on concurrent streams (plan of band b + 1 beside the
+  // raster of band b: both kernels are latency bound and leave most of the machine idle on their own)
+  int rc = build_list(L, false, residentBands, w, h, layers, numFills, layerOf, seg, wind, segOff, rgbx, rule, mode);
   if (rc) {
     cudaStreamSynchronize(rt().stream);
     free_list(L);

@@ -25,6 +25,7 @@ int fail_pixie(const std::string& msg) {
   return 1;
 }
 int fail_cuda(cudaError_t e, const char* what) {
+  cudaGetLastError();  // the error is reported here: do not let it surface again at the next launch check
   g_err = std::string("CUDA error: ") + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ") at " + what;
   return 2;
 }

@@ -22,7 +22,10 @@ for it in range(25):
     t = dev.timer_end()
     if it >= 5:
         steps.append(t)
-        rast.append(dev.profile_read(dev.PROF_RASTER))
+        try:
+            rast.append(dev.profile_read(dev.PROF_RASTER))
+        except Exception:
+            rast.append(float('nan'))
 print("tiger %d^2 (%s): step %.4f ms (min %.4f)  raster %.4f ms" % (
-    size, os.path.basename(os.environ.get("PIXIE_CUDA_LIB", "pixie_cuda.so")), statistics.median(steps), min(steps),
+    size, os.environ.get("PIXIE_CUDA_BANDS", "8") + " bands", statistics.median(steps), min(steps),
     statistics.median(rast)))
