@@ -1840,8 +1840,9 @@ static int band_edge(long long rows, int b, int K) {
 static void free_list(CmdList& L) {
   if (L.rowsJobBase) cudaFree(L.rowsJobBase);
   L.rowsJobBase = nullptr;
-  if (L.owned && L.block) cudaFree(L.block);
-  if (L.owned && L.blockB) cudaFree(L.blockB);
+  // owned blocks come from the stream-ordered pool (its memory stays cached: no driver allocation per list)
+  if (L.owned && L.block) cudaFreeAsync(L.block, rt().stream);
+  if (L.owned && L.blockB) cudaFreeAsync(L.blockB, rt().stream);
   L.block = L.blockB = nullptr;
 }
 
@@ -1918,16 +1919,13 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
     const size_t pMax = (size_t)numSegs / 2 + (size_t)numFills + 1;
     stageBytes += 2 * al((pMax + 1) * 4) + al(pMax) + al(std::max<size_t>(1, (size_t)numSegs) * 4) + al(((size_t)numSegs / 32 + 2) * 4);
   }
+  // the host-written part is assembled in the library's pinned staging buffer (grown on demand, reused): the H2D
+  // copies run at PCIe speed and nothing is allocated or page-faulted per list
   uint8_t* stage = nullptr;
-  std::vector<uint8_t> pageable;
-  if (arena) {  // per-call lists: library-owned growing arena + pinned staging, no malloc/free per call
+  {
     void* pin;
     if (int rc = staging_acquire(stageBytes, &pin)) return rc;
     stage = (uint8_t*)pin;
-  } else {
-    pageable.resize(h2dBytes + 16);
-    stage = pageable.data();
-    stage += (16 - (reinterpret_cast<uintptr_t>(stage) & 15)) & 15;
   }
   for (int k = 0; k < numFills; k++) {
     const int layer = layerOf ? layerOf[k] : 0;
@@ -2106,7 +2104,7 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
     L.block = (uint8_t*)blk;
     L.owned = false;
   } else {
-    PX_CUDA(cudaMalloc(&L.block, totalA));
+    PX_CUDA(cudaMallocAsync((void**)&L.block, totalA, r.stream));
     L.owned = true;
   }
   if (numSegs) {  // segments (staged by the bounds pass) + windings go first
@@ -2209,9 +2207,7 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
     copyEnd = oSlots;  // entry offsets, (flags), payload offsets, ranges and group summaries travel with the headers
   }
   PX_CUDA(cudaMemcpyAsync(L.block + oFills, stage + oFills, copyEnd - oFills, cudaMemcpyHostToDevice, r.stream));
-  if (arena) {
-    if (int rc = staging_release()) return rc;
-  }
+  if (int rc = staging_release()) return rc;
   L.segs = (float4*)(L.block + oSegs);
   L.wind = (int16_t*)(L.block + oWind);
   L.fills = (FillHeader*)(L.block + oFills);
@@ -2265,7 +2261,7 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
     if (int rc = get_scratch(4, totalB, &blk)) return rc;
     L.blockB = (uint8_t*)blk;
   } else {
-    PX_CUDA(cudaMalloc(&L.blockB, totalB));
+    PX_CUDA(cudaMallocAsync((void**)&L.blockB, totalB, r.stream));
   }
   L.entries = (Entry*)L.blockB;
   L.jobs = (JobHdr*)(L.blockB + entriesBytes);
