@@ -134,13 +134,31 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from _util import oracle_render_batch
 
+    # N GPUs render N independent canvases: the CPU arm renders N of them too, one host thread each (fills of ONE
+    # canvas are order-dependent and the reference is single-threaded, so a canvas cannot use more than one)
+    threads = max(1, min(args.gpus, _host_cores()))
+
+    def one_step():
+        res = [None] * threads
+
+        def work(k):
+            res[k] = oracle_render_batch(arrays, args.size, args.size)[1]
+
+        if threads == 1:
+            work(0)
+        else:
+            _threaded(work, range(threads), threads)
+        return sum(res) * args.gpus // threads
+
     for _ in range(args.warmup):
-        oracle_render_batch(arrays, args.size, args.size)
+        one_step()
     times, covered = [], 0
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        _, covered = oracle_render_batch(arrays, args.size, args.size)
+        covered = one_step()
         times.append(time.perf_counter() - t0)
+    if threads < args.gpus:  # fewer cores than canvases: the remaining canvases would follow in further rounds
+        times = [t * args.gpus / threads for t in times]
     ms = 1e3 * sum(times) / len(times)
     val = covered / (ms * 1e-3) / 1e6
     out = {
@@ -148,9 +166,9 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "tests/golden/tiger.svg (reference fixture)",
         "config": workload_config(args.size, arrays),
-        "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{args.steps} full tiger renders at {args.size}^2 (whole workload, 1 thread: "
-                                   "fills are order-dependent and the reference is single-threaded)"},
+        "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps of {args.gpus} full tiger render(s) at {args.size}^2, one host thread per "
+                                   "canvas (fills of a canvas are order-dependent and the reference is single-threaded)"},
         "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -586,6 +604,31 @@ class _BandView:
         return self.t[a - self.y0:b - self.y0].cpu().numpy()
 
 
+def host_link_probe(dev, dist, world, mib=64, reps=10):
+    """What the e2e number runs into at N > 1: every rank returns 64 MiB of pixels per step over its PCIe link.  All
+    ranks copy a 64 MiB device buffer to pinned host memory at the same time; the aggregate is the host side's ceiling
+    for N concurrent result streams (root complexes / host memory), measured in the same run."""
+    import torch
+
+    n = mib << 20
+    img = dev.DeviceImage(n // 4 // 4096, 4096)
+    pin = dev.PinnedBuffer(n)
+    for _ in range(2):
+        dev.download_async(img, pin)
+    dev.sync()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dev.download_async(img, pin)
+    dev.sync()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tmax = float(t.item())
+    return {"d2h_GBps_per_rank_concurrent": round(n * reps / tmax / 1e9, 1), "d2h_GBps_aggregate": round(world * n * reps / tmax / 1e9, 1),
+            "MiB_per_copy": mib, "ranks_copying_at_once": world}
+
+
 def row_bands_multi_gpu(dev, dist, rank, world, local_rank, peak):
     """BASELINE config 4 (+ the other row-band rows of SURVEY 8e) across N GPUs: one canvas in row bands.
     blur / spread / shadow exchange halo rows with ncclSend / ncclRecv (torch.distributed P2P over NVLink) — for the
@@ -844,6 +887,12 @@ def run_ours(args):
             icons_multi = icons_sharded(dev, dist, rank, world, args.icons_per_gpu)
         except Exception as e:
             icons_multi = {"error": repr(e)}
+    host_link = None
+    if dist is not None and not args.no_extras:
+        try:
+            host_link = host_link_probe(dev, dist, world)
+        except Exception as e:
+            host_link = {"error": repr(e)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -900,6 +949,7 @@ def run_ours(args):
         extras = dict(extras or {})
         extras["row_bands"] = banded
         extras["icons_512_sharded"] = icons_multi
+        extras["host_link"] = host_link
     if extras is not None:
         out["extras"] = extras
     print(json.dumps(out))

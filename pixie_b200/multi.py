@@ -26,25 +26,37 @@ def bind_to_gpu_numa(device_index: int) -> dict:
         import pynvml
 
         pynvml.nvmlInit()
-        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
-        bus = bus.decode() if isinstance(bus, bytes) else bus
-        bus = bus.lower()
-        if len(bus.split(":")[0]) == 8:  # nvml reports an 8-digit domain, sysfs uses 4
-            bus = bus[4:]
-        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
-            node = int(f.read().strip())
-        if node < 0:
-            return info
-        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
-            cpulist = f.read().strip()
-        cpus = set()
-        for part in cpulist.split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        cpus, node = set(), None
+        try:
+            bus = pynvml.nvmlDeviceGetPciInfo(handle).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            bus = bus.lower()
+            if len(bus.split(":")[0]) == 8:  # nvml reports an 8-digit domain, sysfs uses 4
+                bus = bus[4:]
+            with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+                node = int(f.read().strip())
+            if node >= 0:
+                with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                    for part in f.read().strip().split(","):
+                        a, _, b = part.partition("-")
+                        cpus.update(range(int(a), int(b or a) + 1))
+        except Exception:
+            node = None
+        if not cpus:
+            # virtualised hosts report numa_node = -1: ask the driver for the GPU's ideal CPU set instead
+            # (the "CPU Affinity" column of `nvidia-smi topo -m`)
+            words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+            for wi, word in enumerate(mask):
+                for bit in range(64):
+                    if (int(word) >> bit) & 1:
+                        cpus.add(wi * 64 + bit)
+            info["source"] = "nvmlDeviceGetCpuAffinity"
         allowed = os.sched_getaffinity(0) & cpus
         if allowed:
             os.sched_setaffinity(0, allowed)
-            info = {"numa_node": node, "cpus": len(allowed)}
+            info.update({"numa_node": node if node is not None and node >= 0 else None, "cpus": len(allowed)})
     except Exception as e:  # no NVML, no sysfs entry, container without the topology: leave the affinity alone
         info["error"] = repr(e)[:80]
     return info

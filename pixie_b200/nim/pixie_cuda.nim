@@ -7,8 +7,12 @@
 ## public signature (`fillPath`, `strokePath`, `draw`, `blur`, `shadow`, `Paint`, `WindingRule`,
 ## `BlendMode`) untouched.  See INTEGRATION.md.
 
-import chroma, vmath
-import pixie/common   # Image, BlendMode, PixieError
+## Imports: only modules that do NOT import this one.  `WindingRule` lives in pixie/paths (which imports the shim), so
+## fillShapesCuda takes `ord(windingRule)`; `Paint` likewise (pixie/paints), so fillGradientCuda takes its fields.
+import std/math                # round
+import bumpy, chroma, vmath    # Segment; Color, ColorRGBX; Vec2, Ivec2, Mat3
+import pixie/common            # Image, BlendMode, PixieError, newImage
+import pixie/internal          # gaussianKernel (internal.nim:17-34)
 
 const lib = "pixie_cuda.so"
 
@@ -24,6 +28,11 @@ proc pixie_cuda_blur_host(pixels: ptr uint8, width, height: cint, lut: ptr uint1
     radius: cint, outOfBounds: uint32): cint {.importc, dynlib: lib, cdecl.}
 proc pixie_cuda_shadow_host(src, dst: ptr uint8, width, height: cint, ox, oy: cfloat,
     spread: cint, lut: ptr uint16, radius: cint, rgbx: uint32): cint {.importc, dynlib: lib, cdecl.}
+
+proc pixie_cuda_spread_host(pixels: ptr uint8, width, height, spread: cint): cint {.importc, dynlib: lib, cdecl.}
+proc pixie_cuda_apply_opacity_host(pixels: ptr uint8, width, height: cint, opacity: cfloat): cint {.importc, dynlib: lib, cdecl.}
+proc pixie_cuda_blend_rect_masked_host(dst: ptr uint8, dw, dh: cint, src, mask: ptr uint8,
+    maskBytesPerPixel, sw, sh, px, py, blendMode: cint): cint {.importc, dynlib: lib, cdecl.}
 
 proc pixie_cuda_draw_host(dst: ptr uint8, dw, dh: cint, src: ptr uint8, sw, sh: cint,
     mat: ptr float32, blendMode, tiled: cint): cint {.importc, dynlib: lib, cdecl.}
@@ -55,7 +64,7 @@ proc fillShapesCuda*(
   image: Image,
   segments: seq[(Segment, int16)],   # output of shapesToSegments (paths.nim:1059-1090)
   rgbx: ColorRGBX,                   # color.asRgbx() (paths.nim:1603)
-  windingRule: WindingRule,
+  windingRule: int,                  # ord(WindingRule): NonZero = 0, EvenOdd = 1 (paths.nim:5-8)
   blendMode: BlendMode
 ) {.raises: [PixieError].} =
   var
@@ -72,7 +81,7 @@ proc fillShapesCuda*(
   check pixie_cuda_fill_segments_host(
     cast[ptr uint8](image.data[0].addr), image.width.cint, image.height.cint,
     xyxy[0].addr, winding[0].addr, segments.len.cint, rgbx.asU32,
-    windingRule.ord.cint, blendMode.ord.cint)
+    windingRule.cint, blendMode.ord.cint)
 
 # ---- images.nim: body of blendRect -------------------------------------------------------------
 proc blendRectCuda*(a, b: Image, pos: Ivec2, blendMode: BlendMode) {.raises: [PixieError].} =
@@ -92,6 +101,26 @@ proc blurCuda*(image: Image, radius: float32, outOfBounds: ColorRGBX) {.raises: 
   check pixie_cuda_blur_host(
     cast[ptr uint8](image.data[0].addr), image.width.cint, image.height.cint,
     kernel[0].addr, radius.cint, outOfBounds.asU32)
+
+# ---- images.nim: body of spread (:700-758) -----------------------------------------------------------
+proc spreadCuda*(image: Image, spread: float32) {.raises: [PixieError].} =
+  let spread = round(spread).int
+  if spread == 0:
+    return
+  check pixie_cuda_spread_host(
+    cast[ptr uint8](image.data[0].addr), image.width.cint, image.height.cint, spread.cint)
+
+# ---- images.nim: body of applyOpacity (:261-277) ------------------------------------------------------
+proc applyOpacityCuda*(image: Image, opacity: float32) {.raises: [PixieError].} =
+  check pixie_cuda_apply_opacity_host(
+    cast[ptr uint8](image.data[0].addr), image.width.cint, image.height.cint, opacity.cfloat)
+
+# ---- paths.nim:2141-2142: fill.draw(mask, MaskBlend); image.draw(fill, blendMode) in one pass ---------
+proc drawMaskedCuda*(image, fill, mask: Image, blendMode: BlendMode) {.raises: [PixieError].} =
+  check pixie_cuda_blend_rect_masked_host(
+    cast[ptr uint8](image.data[0].addr), image.width.cint, image.height.cint,
+    cast[ptr uint8](fill.data[0].addr), cast[ptr uint8](mask.data[0].addr), 4.cint,
+    fill.width.cint, fill.height.cint, 0.cint, 0.cint, blendMode.ord.cint)
 
 # ---- images.nim: body of shadow ----------------------------------------------------------------
 proc shadowCuda*(image: Image, offset: Vec2, spread, blur: float32, color: ColorRGBX): Image
