@@ -53,6 +53,11 @@ struct Runtime {
   // per-kernel CUDA-event timing (pixie_cuda_set_profiling): slot -> (begin, end) of the last launch
   bool profiling = false;
   cudaEvent_t prof[8][2] = {};
+  // a command list run in row bands (plan of band b + 1 beside the raster of band b) has one plan span and one raster
+  // launch per band, each on the band's stream: [band][0..1] plan, [band][2..3] raster; prof_bands = bands of the
+  // last run (0: the run was not banded and slots kProfPlan / kProfRaster hold its times)
+  cudaEvent_t band_prof[kBands][4] = {};
+  int prof_bands = 0;
 };
 
 enum ProfSlot { kProfPartition = 0, kProfRaster = 1, kProfBlurX = 2, kProfBlurY = 3, kProfBlend = 4, kProfSpread = 5, kProfPlan = 6 };

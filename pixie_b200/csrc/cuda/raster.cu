@@ -2317,6 +2317,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
     if (int rc = device_count(L)) return rc;
   }
   L.countFresh = false;
+  r.prof_bands = 0;
   PX_CUDA(cudaMemsetAsync(L.counters, 0, 256, r.stream));  // row tickets, covered px, heavy-job counts
   if (L.numParts > 0) {
     const int warps = (int)std::min<int64_t>(L.numParts, (int64_t)r.num_sms * 32);
@@ -2420,8 +2421,12 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
     PX_CUDA(cudaEventRecord(r.band_start, r.stream));
     const size_t rowBytes = (size_t)L.w * 4;
     const size_t fillsP1 = (size_t)L.numFills + 1;
+    const bool prof = r.profiling && r.band_prof[0][0];
+    if (prof) r.prof_bands = K;
     auto launch_plan = [&](int b) -> int {
       PX_CUDA(cudaStreamWaitEvent(r.band_stream[b], r.band_start, 0));
+      if (prof) PX_CUDA(cudaEventRecord(r.band_prof[b][0], r.band_stream[b]));
+      if (prof && L.bandJobs[b] <= 0) PX_CUDA(cudaEventRecord(r.band_prof[b][1], r.band_stream[b]));
       if (L.bandJobs[b] <= 0) return 0;
       RasterArgs B = A;
       B.planJobBase = L.bandJobBase + (size_t)b * fillsP1;
@@ -2433,6 +2438,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
       B.heavyCount = L.counters + 16 + b;
       const int blocks = std::max(1, std::min((L.bandJobs[b] + 7) / 8, L.planBlocks));
       if (int rc = launch_plan_kernels(L, B, L.bandJobs[b], blocks, r.band_stream[b], 1 + b)) return rc;
+      if (prof) PX_CUDA(cudaEventRecord(r.band_prof[b][1], r.band_stream[b]));
       if (g_trace) PX_CUDA(cudaEventRecord(tev[1 + 3 * b], r.band_stream[b]));
       return 0;
     };
@@ -2441,11 +2447,14 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
       B.rowBegin = band_edge(totalRows, b, K);
       B.rowEnd = band_edge(totalRows, b + 1, K);
       B.ticketSlot = 4 + b;
+      if (prof) PX_CUDA(cudaEventRecord(r.band_prof[b][2], r.band_stream[b]));
+      if (prof && B.rowEnd <= B.rowBegin) PX_CUDA(cudaEventRecord(r.band_prof[b][3], r.band_stream[b]));
       if (B.rowEnd <= B.rowBegin) return 0;
       const int blocks = (int)std::max<long long>(1, std::min<long long>(((B.rowEnd - B.rowBegin) * L.tiles + L.warpsPerBlock - 1) / L.warpsPerBlock,
                                                                        L.rasterBlocks));
       raster_kernel<<<blocks, L.warpsPerBlock * 32, L.smemBytes, r.band_stream[b]>>>(B);
       PX_LAUNCHED();
+      if (prof) PX_CUDA(cudaEventRecord(r.band_prof[b][3], r.band_stream[b]));
       if (g_trace) PX_CUDA(cudaEventRecord(tev[2 + 3 * b], r.band_stream[b]));
       if (host_pixels)
         PX_CUDA(cudaMemcpyAsync(host_pixels + (size_t)B.rowBegin * rowBytes, im->data + (size_t)B.rowBegin * rowBytes,
@@ -2494,10 +2503,12 @@ int pixie_cuda_cmdlist_create(int w, int h, int layers, int numFills, const int3
   PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   CmdList L;
-  static const int residentBands = getenv("PIXIE_CUDA_BANDS") ? atoi(getenv("PIXIE_CUDA_BANDS")) : 1;
+  static const int residentBands = getenv("PIXIE_CUDA_BANDS") ? atoi(getenv("PIXIE_CUDA_BANDS")) : 4;
   // single-canvas lists are planned and rasterised in row bands on concurrent streams (plan of band b + 1 beside the
   // raster of band b: both kernels are latency bound and leave most of the machine idle on their own)
-  int rc = build_list(L, false, residentBands, w, h, layers, numFills, layerOf, seg, wind, segOff, rgbx, rule, mode);
+  // (small canvases keep one band: four more launch sets would cost more than the overlap gains)
+  const int bands = (h >= 2048 && numFills >= 16) ? residentBands : 1;
+  int rc = build_list(L, false, bands, w, h, layers, numFills, layerOf, seg, wind, segOff, rgbx, rule, mode);
   if (rc) {
     cudaStreamSynchronize(rt().stream);
     free_list(L);
@@ -2544,7 +2555,8 @@ int pixie_cuda_cmdlist_info(pixie_cmdlist_t list, int64_t* numSegs, int64_t* num
   if (numSegs) *numSegs = it->second.numSegs;
   if (numParts) *numParts = it->second.numParts;
   if (numEntries) *numEntries = it->second.numEntries;
-  if (launches) *launches = it->second.numParts > 0 ? 5 : 1;
+  // count + two scans + partition, then per band: classify, two plan kernels, raster
+  if (launches) *launches = it->second.numParts > 0 ? (it->second.deviceCounted ? 4 : 1) + 4 * std::max(1, it->second.bands) : 1;
   return 0;
 }
 

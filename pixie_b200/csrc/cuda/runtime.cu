@@ -398,6 +398,9 @@ int pixie_cuda_set_profiling(int enabled) {
   if (enabled && !r.prof[0][0])
     for (int i = 0; i < 8; i++)
       for (int j = 0; j < 2; j++) PX_CUDA(cudaEventCreate(&r.prof[i][j]));
+  if (enabled && !r.band_prof[0][0])
+    for (int i = 0; i < Runtime::kBands; i++)
+      for (int j = 0; j < 4; j++) PX_CUDA(cudaEventCreate(&r.band_prof[i][j]));
   r.profiling = enabled != 0;
   return 0;
 }
@@ -405,6 +408,21 @@ int pixie_cuda_profile_read(int slot, float* ms) {
   PX_API_GUARD;
   Runtime& r = rt();
   if (slot < 0 || slot >= 8 || !r.prof[0][0]) return fail_pixie("profiling slot out of range or profiling never enabled");
+  if (r.prof_bands > 0 && (slot == kProfPlan || slot == kProfRaster)) {
+    // banded run: the sum over the bands' launches (they overlap other bands' kernels, so this is an upper bound of
+    // the time the kernel would take alone)
+    const int k0 = slot == kProfPlan ? 0 : 2;
+    float sum = 0.0f;
+    for (int b = 0; b < r.prof_bands; b++) {
+      if (cudaEventQuery(r.band_prof[b][k0 + 1]) == cudaErrorInvalidResourceHandle) continue;
+      float t = 0.0f;
+      PX_CUDA(cudaEventSynchronize(r.band_prof[b][k0 + 1]));
+      PX_CUDA(cudaEventElapsedTime(&t, r.band_prof[b][k0], r.band_prof[b][k0 + 1]));
+      sum += t;
+    }
+    *ms = sum;
+    return 0;
+  }
   PX_CUDA(cudaEventSynchronize(r.prof[slot][1]));
   PX_CUDA(cudaEventElapsedTime(ms, r.prof[slot][0], r.prof[slot][1]));
   return 0;

@@ -1,16 +1,43 @@
 #!/bin/bash
-# One gpurun call: parity tests, bench (both arms), ncu launch list, ncu --set full of the hot kernels.
+# One gpurun call: parity tests, bench (both arms), ncu launch lists, ncu --set full of the hot kernels.
+# Usage: tools/gpu_round.sh [tag] [parts]   (outputs under gpurun_out/<tag>_*; parts = any of: test bench lists ncu)
+# The .ncu-rep files are summarised on the box (tools/summarize_ncu.py) and deleted: gpurun_out/ merges back only
+# below 64 MiB.
 set -x
-mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -3 gpurun_out/pytest_gpu.log
-python bench.py > gpurun_out/bench_cur.json 2> gpurun_out/bench_cur.err
-python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_cur_ref.json 2>/dev/null
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_cur.csv python bench.py --steps 3 --warmup 3 --no-extras > gpurun_out/ncu_bench.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'plan_|raster_kernel|partition_kernel' --launch-skip 10 -c 5 -f -o gpurun_out/prof_tiger_cur python tools/prof_kernels.py tiger > gpurun_out/ncu_tiger.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'blur_mma' --launch-skip 2 -c 2 -f -o gpurun_out/prof_blur_cur python tools/prof_kernels.py blur > gpurun_out/ncu_blur.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'blur_mma_a8|spread_' --launch-skip 4 -c 4 -f -o gpurun_out/prof_shadow_cur python tools/prof_kernels.py shadow > gpurun_out/ncu_shadow.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'blend_rect' --launch-skip 3 -c 1 -f -o gpurun_out/prof_blend_cur python tools/prof_kernels.py blend > gpurun_out/ncu_blend.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'draw_smooth|gradient_kernel|minify' -c 6 -f -o gpurun_out/prof_draw_cur python tools/prof_kernels.py draw > gpurun_out/ncu_draw.log 2>&1
-tail -2 gpurun_out/bench_cur.err
-head -c 1500 gpurun_out/bench_cur.json
+T=${1:-cur}
+PARTS=${2:-"test bench lists ncu"}
+O=gpurun_out
+mkdir -p $O
+NCU="ncu --clock-control none"
+FULL="$NCU --set full --import-source on -f"
+TENSOR="--metrics sm__inst_executed_pipe_tensor.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_uniform.sum,sm__pipe_tensor_subunit_cycles_active.avg.pct_of_peak_sustained_active"
+cap() {  # cap <name> <kernel regex> <skip> <count> <prof_kernels target> [extra ncu args]
+  local name=$1 rx=$2 skip=$3 cnt=$4 target=$5; shift 5
+  timeout 600 $FULL "$@" -k regex:"$rx" --launch-skip $skip -c $cnt -o $O/${T}_prof_$name python tools/prof_kernels.py $target > $O/ncu_$name.log 2>&1
+  python tools/summarize_ncu.py $O/${T}_prof_$name.ncu-rep $O/${T}_$name > /dev/null 2>&1
+  rm -f $O/${T}_prof_$name.ncu-rep
+}
+if [[ $PARTS == *test* ]]; then
+  python -m pytest tests -m gpu -x -q > $O/${T}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/${T}_pytest_gpu.log
+  tail -3 $O/${T}_pytest_gpu.log
+fi
+if [[ $PARTS == *bench* ]]; then
+  python bench.py > $O/${T}_bench.json 2> $O/${T}_bench.err
+  python bench.py --impl reference --steps 5 --warmup 1 > $O/${T}_bench_ref.json 2>/dev/null
+  tail -2 $O/${T}_bench.err
+  head -c 1500 $O/${T}_bench.json
+fi
+if [[ $PARTS == *lists* ]]; then
+  $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $O/${T}_launches_tiger.csv python bench.py --steps 3 --warmup 3 --no-extras > $O/ncu_bench.log 2>&1
+  $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $O/${T}_launches_icons.csv python tools/time_icons.py > $O/ncu_icons_l.log 2>&1
+  $NCU --metrics gpu__time_duration.sum -c 100 --csv --log-file $O/${T}_launches_blur.csv python tools/prof_kernels.py blur > $O/ncu_blur_l.log 2>&1
+fi
+if [[ $PARTS == *ncu* ]]; then
+  cap tiger 'plan_|raster_kernel|partition_kernel|count_kernel|band_' 12 9 tiger
+  cap blur_tc 'blur_tc' 1 1 blur $TENSOR
+  cap shadow 'blur_mma_a8|spread_' 4 4 shadow
+  cap blend 'blend_rect' 0 15 blend
+  cap icons 'plan_|raster_kernel|partition_kernel' 5 5 icons
+  cap draw 'draw_smooth|gradient_kernel|minify' 0 6 draw
+fi
+du -sh $O

@@ -15,8 +15,9 @@ if which in ("blend", "all"):
     dst = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 1), (n // 512, 1, 1)))
     src = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 2), (n // 512, 1, 1)))
     mask = dev.DeviceImage(n, n, a8=True).upload(np.tile(synth.coverage_mask(512, n, 3), (n // 512, 1)))
-    for mode in (0, 16, 17, 2, 8):
-        for _ in range(3):
+    modes = [int(v) for v in os.environ.get("BLEND_MODES", "0,7,3,8,12,16").split(",")]
+    for mode in modes:  # common.py ordinals: Normal 0, Overlay 7, ColorBurn 3, SoftLight 8, Hue 12, Mask 16
+        for _ in range(2):
             dev.blend_rect_masked(dst, src, mask, 0, 0, mode)
     dev.sync()
 if which in ("blur", "all"):
@@ -39,6 +40,19 @@ if which in ("tiger", "all"):
     arrays = tiger_arrays(4096)
     img = dev.DeviceImage(4096, 4096)
     cl = dev.CmdList(4096, 4096, 1, arrays)
+    for _ in range(3):
+        img.fill(0)
+        cl.run(img)
+    dev.sync()
+if which in ("icons", "all"):
+    from pixie_b200.device import FillBatch
+
+    batch = FillBatch()
+    for i in range(1024):
+        synth.icon_fills(i, 512, i, batch)
+    arrays = batch.arrays()
+    img = dev.DeviceImage(512, 512, 1024)
+    cl = dev.CmdList(512, 512, 1024, arrays)
     for _ in range(3):
         img.fill(0)
         cl.run(img)

@@ -15,6 +15,8 @@ sm__warps_active.avg.pct_of_peak_sustained_active launch__registers_per_thread l
 smsp__inst_executed.sum sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active
 sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active
 sm__inst_executed_pipe_tensor_op_hmma.avg.pct_of_peak_sustained_active sm__inst_executed_pipe_tensor.sum
+sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active sm__pipe_tensor_subunit_cycles_active.avg.pct_of_peak_sustained_active
+sm__inst_executed_pipe_uniform.sum l1tex__data_pipe_lsu_wavefronts_mem_shared.sum smsp__cycles_active.avg
 smsp__issue_active.avg.pct_of_peak_sustained_active l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum
 lts__t_sector_hit_rate.pct l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum
 l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum l1tex__t_requests_pipe_lsu_mem_global_op_st.sum
