@@ -918,12 +918,7 @@ def run_ours(args):
                 "traffic": 32271616 if size == 4096 else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(rast, 4),
                 "partition_kernel_ms": round(part, 4), "plan_kernel_ms": round(statistics.mean(plan_ms), 4), "share_of_step": round(rast / statistics.mean(step_ms), 3),
-                "launches_per_step": 4,
-                "note": "305 order-dependent fills: latency/occupancy-bound, not bandwidth-bound (SURVEY.md 7.1).  The canvas is "
-                        "planned and rasterised in 4 row bands on concurrent streams (plan of band b+1 beside the raster of band b): "
-                        "raster_kernel launches 4 times per step and kernel_ms / plan_kernel_ms are the SUMS over the band launches "
-                        "(each measured with CUDA events on its band's stream while other bands' kernels share the GPU), so "
-                        "achieved = whole-canvas algorithmic bytes / that sum"}
+                "note": "305 order-dependent fills: latency/occupancy-bound, not bandwidth-bound (SURVEY.md 7.1)"}
 
     cpu = None
     extras = None

@@ -120,6 +120,43 @@ int pixie_cuda_cmdlist_run_rows(pixie_cmdlist_t list, pixie_image_t image, int y
 int pixie_cuda_cmdlist_info(pixie_cmdlist_t list, int64_t* num_segments, int64_t* num_partitions,
                             int64_t* num_entries, int64_t* launches_per_run);
 int pixie_cuda_cmdlist_destroy(pixie_cmdlist_t list);
+/* With PIXIE_CUDA_BANDS=k in the environment single-canvas lists of 2048 rows or more are planned and rasterised in k
+ * row bands on concurrent streams (the plan kernels of band b + 1 beside the raster kernel of band b; measured slower
+ * than one band on the tiger, so the default is 1).  enabled = 0 runs such a list as one band again. */
+int pixie_cuda_cmdlist_set_overlap(pixie_cmdlist_t list, int enabled);
+
+/* ---- path commands -> segments on the device -----------------------------
+ * What fillPath (paths.nim:2084-2113) / strokePath (:2144-2176) do BEFORE fillShapes, for a whole document at once:
+ * commandsToShapes (:654-1057: lines, quadratic and cubic Beziers with the reference's adaptive halving),
+ * strokeShapes (:1922-2082: butt / square caps, miter / bevel joins), transform + shapesToSegments (:1059-1096).
+ * The result stays in HBM and becomes the segment block of a command list; only the per-path bounds
+ * (computeBounds :1098-1117, 20 bytes per path) come back to the host to lay out the fills.
+ *
+ * `commands` is the reference's Path.commands stream (seq[float32]: PathCommandKind ordinal followed by its
+ * parameters, paths.nim:18-30,73-81) of all paths concatenated.  Arcs, round caps / joins and dashes need the host
+ * libm's sin / cos / arccos, which differ from CUDA's in the last bit: such paths are flattened by the caller
+ * (kind 2: their finished segments are passed through, `begin`/`end` index raw_xyxy / raw_winding).
+ * Returns 1 with the reference's messages ("Unable to discretize ...", "Invalid path command",
+ * "Path int overflow detected"). */
+typedef struct pixie_path_desc {
+  int32_t kind;          /* 0 fill (closeSubpaths = true), 1 stroke, 2 pre-flattened segments */
+  int32_t begin, end;    /* float range of this path in `commands` (kind 0 / 1), segment range in raw_* (kind 2) */
+  int32_t num_commands;  /* path commands in [begin, end) */
+  float transform[9];    /* vmath Mat3, column-major (m[c * 3 + r]); pixelScale is derived from it (:61-66) */
+  float stroke_width;    /* kind 1: strokeWidth, LineCap / LineJoin ordinals (paths.nim:10-16), miterLimit */
+  int32_t line_cap, line_join;
+  float miter_limit;
+  uint32_t rgbx;         /* the fill of the resulting shape: colour, WindingRule, BlendMode, layer */
+  uint8_t winding_rule, blend_mode;
+  uint16_t reserved;
+  int32_t layer;
+} pixie_path_desc;
+int pixie_cuda_cmdlist_create_from_paths(int width, int height, int layers, int num_paths, const pixie_path_desc* paths,
+                                         const float* commands, int64_t num_command_floats, const float* raw_xyxy,
+                                         const int16_t* raw_winding, int64_t num_raw_segments, pixie_cmdlist_t* out);
+/* The segments a list holds, copied to the host (tests, and callers that want shapesToSegments' output):
+ * seg_offsets gets num_fills + 1 entries; any pointer may be NULL.  Blocks. */
+int pixie_cuda_cmdlist_segments(pixie_cmdlist_t list, float* seg_xyxy, int16_t* winding, int32_t* seg_offsets);
 
 /* ---- draw -> blendRect (images.nim:636-678 -> :468-529) -------------------------------------
  * Integer-translate fast path of draw(): dst <- blend(dst, src at (px, py)), all 20 modes

@@ -84,6 +84,19 @@ int get_pinned(size_t bytes, void** out);
 int staging_acquire(size_t bytes, void** out);  // pinned staging, safe to overwrite on return
 int staging_release();                          // call right after enqueuing the copy that reads it
 
+// path commands -> device-resident segments (flatten.cu); segs / wind come from the stream-ordered pool
+struct FlattenedPaths {
+  float4* segs = nullptr;
+  int16_t* wind = nullptr;
+  std::vector<int> segBegin;   // [numPaths + 1]
+  std::vector<float> bounds;   // per path: xMin, xMax, yMin, yMax of its segments, NaN flag
+  int numSegs = 0, numPoints = 0, numPrims = 0;
+  size_t h2dBytes = 0;
+};
+int flatten_paths(int numPaths, const pixie_path_desc* descs, const float* commands, int64_t numCommandFloats, const float* rawXyxy,
+                  const int16_t* rawWinding, int64_t numRaw, FlattenedPaths& out);
+void free_flattened(FlattenedPaths& f);
+
 #define PX_CUDA(call)                                  \
   do {                                                 \
     cudaError_t _e = (call);                           \

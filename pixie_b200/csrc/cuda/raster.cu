@@ -83,6 +83,7 @@ struct CmdList {
   uint8_t* block = nullptr;   // block A: host-written inputs + device-made offsets/flags/counters
   uint8_t* blockB = nullptr;  // block B: band entries + spill scratch (sized after the device-side count)
   bool owned = false;
+  bool serial = false;         // run a banded list as one band (pixie_cuda_cmdlist_set_overlap(list, 0))
   bool deviceCounted = false;  // band counts / offsets were made by count_kernel + scans (lists above 8192 segments)
   bool countFresh = false;     // ... and the arrays still hold the offsets of build_list's own pass
   // host copy of what a row-band run needs to lay out its jobs (pixie_cuda_cmdlist_run_rows)
@@ -1862,7 +1863,9 @@ static int device_count(CmdList& L) {
   count_kernel<<<std::max(cblocks, 1), 256, 0, r.stream>>>(L.fills, L.numFills, L.segs, (int)L.numSegs, L.entryOff, L.ranges, L.groupRange);
   PX_LAUNCHED();
   const int numChunks = (int)((P + kScanChunk - 1) / kScanChunk);
-  PX_CUDA(cudaMemsetAsync(L.counters + 2, 0, 24, r.stream));  // {entries, max, payload}
+  // {entries, max, payload} and the scan's block ticket — counters[5] doubles as band 1's row ticket of a banded run,
+  // which leaves it non-zero
+  PX_CUDA(cudaMemsetAsync(L.counters + 2, 0, 32, r.stream));
   band_sum_kernel<<<numChunks, 256, 0, r.stream>>>(L.entryOff, L.bandRows, (int)P, L.chunkSums, L.chunkSums + numChunks,
                                                    reinterpret_cast<unsigned*>(L.counters + 5), L.counters + 2, numChunks);
   PX_LAUNCHED();
@@ -1873,9 +1876,11 @@ static int device_count(CmdList& L) {
 
 constexpr int64_t kHostCountMaxSegs = 8192;  // lists up to this size are counted on the host (no sync in the call)
 
+// `dev` != null: the segments are already in HBM (flatten.cu) together with the bounds of every path; seg / wind are
+// null then and segOff = dev->segBegin.
 static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layers, int numFills, const int32_t* layerOf,
                       const float* seg, const int16_t* wind, const int32_t* segOff, const uint32_t* rgbx,
-                      const uint8_t* rule, const uint8_t* mode) {
+                      const uint8_t* rule, const uint8_t* mode, const FlattenedPaths* dev = nullptr) {
   Runtime& r = rt();
   const double t0 = now_ms();
   if (w <= 0 || h <= 0 || layers <= 0) return fail_pixie("Image width and height must be > 0");
@@ -1913,7 +1918,7 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   // made on the host while it stages the segments anyway, so the call needs no device round trip before it can
   // size block B — fill_segments / fill_batch then only enqueue work (the reference's callers issue thousands of
   // small fills; a synchronisation per call would cost more than the fill).
-  const bool hostCount = arena && numSegs <= kHostCountMaxSegs;
+  const bool hostCount = arena && numSegs <= kHostCountMaxSegs && !dev;
   size_t stageBytes = h2dBytes;
   if (hostCount) {
     const size_t pMax = (size_t)numSegs / 2 + (size_t)numFills + 1;
@@ -1948,6 +1953,11 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
     // computeBounds (:1098-1117) + snapToPixels (common.nim:92-101) + clip to the image (:1605-1613)
     float xMin = INFINITY, xMax = -INFINITY, yMin = INFINITY, yMax = -INFINITY;
     const double tb0 = g_trace ? now_ms() : 0;
+    if (dev) {  // computeBounds was reduced on the device (bounds_kernel)
+      const float* b = dev->bounds.data() + 5 * (size_t)k;
+      if (b[4] != 0.0f) return fail_pixie("flatten: non-finite path coordinates");
+      xMin = b[0]; xMax = b[1]; yMin = b[2]; yMax = b[3];
+    } else
     // Nim's min/max (`if x <= y: x else: y`) == MINPS/MAXPS(acc, v) including their NaN behaviour
     // (second operand when unordered); one 4-lane min + max per segment {at.x, at.y, to.x, to.y}, and the
     // segment goes to the staging buffer on the way (streaming stores: the DMA engine is the only reader).
@@ -2107,7 +2117,10 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
     PX_CUDA(cudaMallocAsync((void**)&L.block, totalA, r.stream));
     L.owned = true;
   }
-  if (numSegs) {  // segments (staged by the bounds pass) + windings go first
+  if (numSegs && dev) {
+    PX_CUDA(cudaMemcpyAsync(L.block + oSegs, dev->segs, (size_t)numSegs * 16, cudaMemcpyDeviceToDevice, r.stream));
+    PX_CUDA(cudaMemcpyAsync(L.block + oWind, dev->wind, (size_t)numSegs * 2, cudaMemcpyDeviceToDevice, r.stream));
+  } else if (numSegs) {  // segments (staged by the bounds pass) + windings go first
     memcpy(stage + oWind, wind, (size_t)numSegs * 2);
     _mm_sfence();
     PX_CUDA(cudaMemcpyAsync(L.block, stage, oFills, cudaMemcpyHostToDevice, r.stream));
@@ -2384,7 +2397,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
       raster_kernel<<<blocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
     }
     PX_LAUNCHED();
-  } else if (L.bands <= 1) {
+  } else if (L.bands <= 1 || L.serial) {
     if (L.totalJobs > 0) {
       ProfScope ps(kProfPlan);
       A.heavyList = L.heavyList;
@@ -2503,7 +2516,9 @@ int pixie_cuda_cmdlist_create(int w, int h, int layers, int numFills, const int3
   PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   CmdList L;
-  static const int residentBands = getenv("PIXIE_CUDA_BANDS") ? atoi(getenv("PIXIE_CUDA_BANDS")) : 4;
+  // measured on the tiger at 4096^2: 0.465 ms as one band, 0.515 ms in 4 bands (four launch sets, and the raster kernels
+  // of neighbouring bands compete for the same SMs) — so one band is the default; PIXIE_CUDA_BANDS is kept for experiments
+  static const int residentBands = getenv("PIXIE_CUDA_BANDS") ? atoi(getenv("PIXIE_CUDA_BANDS")) : 1;
   // single-canvas lists are planned and rasterised in row bands on concurrent streams (plan of band b + 1 beside the
   // raster of band b: both kernels are latency bound and leave most of the machine idle on their own)
   // (small canvases keep one band: four more launch sets would cost more than the overlap gains)
@@ -2518,6 +2533,58 @@ int pixie_cuda_cmdlist_create(int w, int h, int layers, int numFills, const int3
   const uint64_t hd = g_next_list++;
   g_lists[hd] = L;
   *out = hd;
+  return 0;
+}
+
+int pixie_cuda_cmdlist_create_from_paths(int w, int h, int layers, int numPaths, const pixie_path_desc* paths, const float* commands,
+                                         int64_t numCommandFloats, const float* rawXyxy, const int16_t* rawWinding, int64_t numRaw,
+                                         pixie_cmdlist_t* out) {
+  PX_API_GUARD;
+  if (int rc = ensure_init()) return rc;
+  if (numPaths < 0) return fail_pixie("negative path count");
+  FlattenedPaths F;
+  int rc = flatten_paths(numPaths, paths, commands, numCommandFloats, rawXyxy, rawWinding, numRaw, F);
+  CmdList L;
+  if (!rc) {
+    std::vector<int32_t> layerOf((size_t)numPaths);
+    std::vector<uint32_t> rgbx((size_t)numPaths);
+    std::vector<uint8_t> rule((size_t)numPaths), mode((size_t)numPaths);
+    for (int k = 0; k < numPaths; k++) {
+      layerOf[(size_t)k] = paths[k].layer; rgbx[(size_t)k] = paths[k].rgbx;
+      rule[(size_t)k] = paths[k].winding_rule; mode[(size_t)k] = paths[k].blend_mode;
+    }
+    rc = build_list(L, false, 1, w, h, layers, numPaths, layerOf.data(), nullptr, nullptr, F.segBegin.data(), rgbx.data(),
+                    rule.data(), mode.data(), &F);
+  }
+  free_flattened(F);
+  if (rc) {
+    cudaStreamSynchronize(rt().stream);
+    free_list(L);
+    return rc;
+  }
+  std::lock_guard<std::mutex> lk(rt().mu);
+  const uint64_t hd = g_next_list++;
+  g_lists[hd] = L;
+  *out = hd;
+  return 0;
+}
+
+int pixie_cuda_cmdlist_segments(pixie_cmdlist_t list, float* segXyxy, int16_t* winding, int32_t* segOffsets) {
+  PX_API_GUARD;
+  auto it = g_lists.find(list);
+  if (it == g_lists.end()) return fail_pixie("invalid command list handle");
+  const CmdList& L = it->second;
+  Runtime& r = rt();
+  if (segXyxy && L.numSegs) PX_CUDA(cudaMemcpyAsync(segXyxy, L.segs, (size_t)L.numSegs * 16, cudaMemcpyDeviceToHost, r.stream));
+  if (winding && L.numSegs) PX_CUDA(cudaMemcpyAsync(winding, L.wind, (size_t)L.numSegs * 2, cudaMemcpyDeviceToHost, r.stream));
+  std::vector<FillHeader> fills((size_t)L.numFills);
+  if (segOffsets && L.numFills)
+    PX_CUDA(cudaMemcpyAsync(fills.data(), L.fills, fills.size() * sizeof(FillHeader), cudaMemcpyDeviceToHost, r.stream));
+  PX_CUDA(cudaStreamSynchronize(r.stream));
+  if (segOffsets) {
+    for (int k = 0; k < L.numFills; k++) segOffsets[k] = fills[(size_t)k].segBegin;
+    segOffsets[L.numFills] = (int32_t)L.numSegs;
+  }
   return 0;
 }
 
@@ -2545,6 +2612,14 @@ int pixie_cuda_cmdlist_run_rows(pixie_cmdlist_t list, pixie_image_t image, int y
   const bool band = im->h != L.h;
   if (band && im->h != y1 - y0) return fail_pixie("cmdlist_run_rows: the image must be the whole canvas or exactly rows [y0, y1)");
   return run_list(L, im, covered_px, nullptr, y0, y1, band);
+}
+
+int pixie_cuda_cmdlist_set_overlap(pixie_cmdlist_t list, int enabled) {
+  PX_API_GUARD;
+  auto it = g_lists.find(list);
+  if (it == g_lists.end()) return fail_pixie("invalid command list handle");
+  it->second.serial = enabled == 0;
+  return 0;
 }
 
 int pixie_cuda_cmdlist_info(pixie_cmdlist_t list, int64_t* numSegs, int64_t* numParts, int64_t* numEntries,

@@ -51,6 +51,9 @@ _SIGNATURES = {
     "pixie_cuda_cmdlist_run_rows": [u64, u64, i32, i32, P(u64)],
     "pixie_cuda_cmdlist_info": [u64, P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64)],
     "pixie_cuda_cmdlist_destroy": [u64],
+    "pixie_cuda_cmdlist_create_from_paths": [i32, i32, i32, i32, vp, vp, C.c_int64, vp, vp, C.c_int64, P(u64)],
+    "pixie_cuda_cmdlist_segments": [u64, vp, vp, vp],
+    "pixie_cuda_cmdlist_set_overlap": [u64, i32],
     "pixie_cuda_blend_rect": [u64, u64, i32, i32, i32],
     "pixie_cuda_blend_rect_masked": [u64, u64, u64, i32, i32, i32],
     "pixie_cuda_apply_opacity": [u64, f32],
@@ -302,10 +305,114 @@ def render_batch_host(pixels_ptr: int, width: int, height: int, arrays: dict, cl
     return cov.value
 
 
+class PathDesc(C.Structure):  # pixie_path_desc (include/pixie_cuda.h)
+    _fields_ = [("kind", C.c_int32), ("begin", C.c_int32), ("end", C.c_int32), ("num_commands", C.c_int32),
+                ("transform", C.c_float * 9), ("stroke_width", C.c_float), ("line_cap", C.c_int32), ("line_join", C.c_int32),
+                ("miter_limit", C.c_float), ("rgbx", C.c_uint32), ("winding_rule", C.c_uint8), ("blend_mode", C.c_uint8),
+                ("reserved", C.c_uint16), ("layer", C.c_int32)]
+
+
+_PARAMS = (0, 2, 2, 1, 1, 6, 4, 4, 2, 7, 2, 2, 1, 1, 6, 4, 4, 2, 7)  # parameterCount per PathCommandKind, paths.nim:73-81
+_ARC_KINDS = (9, 18)
+
+
+def _scan_commands(cmds):
+    """(number of commands, whether an arc is among them) of a Path.commands stream."""
+    i, n, arc = 0, 0, False
+    while i < len(cmds):
+        k = int(cmds[i])
+        if k < 0 or k >= len(_PARAMS):
+            raise PixieError("Invalid path command")
+        arc = arc or k in _ARC_KINDS
+        i += 1 + _PARAMS[k]
+        n += 1
+    return n, arc
+
+
+class PathBatch:
+    """Ordered list of fillPath / strokePath calls as path COMMANDS: flattening, stroking and shapesToSegments run on
+    the device (pixie_cuda_cmdlist_create_from_paths).  Paths with arcs, round caps / joins or dashes are flattened by
+    libpixie_host.so here and passed through as finished segments (the header says why)."""
+
+    def __init__(self):
+        self.descs, self._cmds, self._raw, self._rawWind = [], [], [], []
+        self.ncmd, self.nraw, self.host_paths = 0, 0, 0
+
+    def __len__(self):
+        return len(self.descs)
+
+    def _desc(self, kind, begin, end, ncommands, transform, rgbx, rule, mode, layer, strokeWidth=1.0, cap=0, join=0, miter=4.0):
+        d = PathDesc()
+        d.kind, d.begin, d.end, d.num_commands = kind, begin, end, ncommands
+        m = np.eye(3, dtype=np.float32).reshape(9) if transform is None else np.ascontiguousarray(transform, np.float32).reshape(9)
+        d.transform = (C.c_float * 9)(*[float(v) for v in m])
+        d.stroke_width, d.line_cap, d.line_join, d.miter_limit = float(strokeWidth), int(cap), int(join), float(miter)
+        d.rgbx, d.winding_rule, d.blend_mode, d.layer = int(rgbx), int(rule), int(mode), int(layer)
+        self.descs.append(d)
+
+    def _add_raw(self, segs, rgbx, rule, mode, layer):
+        self._raw.append(segs.xyxy)
+        self._rawWind.append(segs.winding)
+        self._desc(2, self.nraw, self.nraw + len(segs), 0, None, rgbx, rule, mode, layer)
+        self.nraw += len(segs)
+        self.host_paths += 1
+
+    def add_fill(self, path, transform, rgbx, rule, mode, layer=0):
+        from . import host
+
+        cmds = path.commands
+        n, arc = _scan_commands(cmds)
+        if arc:
+            return self._add_raw(host.fill_segments(path, transform), rgbx, rule, mode, layer)
+        self._cmds.append(cmds)
+        self._desc(0, self.ncmd, self.ncmd + len(cmds), n, transform, rgbx, rule, mode, layer)
+        self.ncmd += len(cmds)
+
+    def add_stroke(self, path, transform, strokeWidth, lineCap, lineJoin, miterLimit, dashes, rgbx, rule, mode, layer=0):
+        from . import host
+
+        cmds = path.commands
+        n, arc = _scan_commands(cmds)
+        if arc or lineCap == host.RoundCap or lineJoin == host.RoundJoin or len(dashes) or not strokeWidth > 0:
+            segs = host.stroke_segments(path, transform, strokeWidth, lineCap, lineJoin, miterLimit, dashes)
+            return self._add_raw(segs, rgbx, rule, mode, layer)
+        self._cmds.append(cmds)
+        self._desc(1, self.ncmd, self.ncmd + len(cmds), n, transform, rgbx, rule, mode, layer, strokeWidth, lineCap, lineJoin, miterLimit)
+        self.ncmd += len(cmds)
+
+    def packed(self):
+        descs = (PathDesc * max(1, len(self.descs)))(*self.descs)
+        cmds = np.ascontiguousarray(np.concatenate(self._cmds) if self._cmds else np.zeros(0), np.float32)
+        raw = np.ascontiguousarray(np.concatenate(self._raw, axis=0) if self._raw else np.zeros((0, 4)), np.float32)
+        rw = np.ascontiguousarray(np.concatenate(self._rawWind) if self._rawWind else np.zeros(0), np.int16)
+        return descs, cmds, raw, rw
+
+
 class CmdList:
     """Device-resident command list (segments + fill headers in HBM)."""
 
+    @classmethod
+    def from_paths(cls, width, height, layers, batch: "PathBatch"):
+        """Path commands in, flattened / stroked on the device (pixie_cuda_cmdlist_create_from_paths)."""
+        descs, cmds, raw, rw = batch.packed()
+        self = cls.__new__(cls)
+        h = u64(0)
+        check(lib().pixie_cuda_cmdlist_create_from_paths(
+            width, height, layers, len(batch), C.cast(descs, vp), _ptr(cmds), len(cmds), _ptr(raw), _ptr(rw), len(rw), C.byref(h)))
+        self.handle = h.value
+        self.num_fills = len(batch)
+        return self
+
+    def segments(self, num_fills=None):
+        """The list's segments back on the host: (xyxy [n, 4] float32, winding [n] int16, seg_offsets [fills + 1])."""
+        n = self.info()["segments"]
+        nf = self.num_fills if num_fills is None else num_fills
+        xy, wd, so = np.zeros((n, 4), np.float32), np.zeros(n, np.int16), np.zeros(nf + 1, np.int32)
+        check(lib().pixie_cuda_cmdlist_segments(self.handle, _ptr(xy), _ptr(wd), _ptr(so)))
+        return xy, wd, so
+
     def __init__(self, width, height, layers, arrays: dict):
+        self.num_fills = len(arrays["rgbx"])
         h = u64(0)
         check(lib().pixie_cuda_cmdlist_create(
             width, height, layers, len(arrays["rgbx"]), _ptr(arrays["layer"]), _ptr(arrays["xyxy"]),
@@ -323,6 +430,10 @@ class CmdList:
         cov = u64(0)
         check(lib().pixie_cuda_cmdlist_run_rows(self.handle, image.handle, y0, y1, C.byref(cov) if count_covered else None))
         return cov.value
+
+    def set_overlap(self, enabled: bool):
+        """False: run a banded list as one band, kernels one after the other (to time a kernel alone)."""
+        check(lib().pixie_cuda_cmdlist_set_overlap(self.handle, 1 if enabled else 0))
 
     def info(self):
         a, b, c, d = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import host
 from .common import NormalBlend, OverwriteBlend, PixieError, parseHtmlColor, rgba_to_rgbx
-from .device import FillBatch
+from .device import FillBatch, PathBatch
 
 
 @dataclass
@@ -214,4 +214,30 @@ def svg_fill_batch(svg: Svg, layer: int = 0, batch: FillBatch | None = None) -> 
                 b.add(host.stroke_segments(path, props.transform, props.strokeWidth, props.strokeLineCap,
                                            props.strokeLineJoin, props.strokeMiterLimit, props.strokeDashArray),
                       rgbx, host.NonZero, NormalBlend, layer)
+    return b
+
+
+def svg_path_batch(svg: Svg, layer: int = 0, batch: PathBatch | None = None) -> PathBatch:
+    """The same render loop with the paths left as COMMANDS: flattening, stroking and shapesToSegments run on the device
+    (PathBatch -> pixie_cuda_cmdlist_create_from_paths)."""
+    b = batch if batch is not None else PathBatch()
+    blend = OverwriteBlend
+    for d, props in svg.elements:
+        if not (props.display and props.opacity > 0):
+            continue
+        path = host.parsePath(d)
+        if props.fill != "none":
+            if props.fill.startswith("url("):
+                raise PixieError("gradient fills are not on this path")
+            opacity = max(0.0, min(1.0, props.fillOpacity * props.opacity))
+            if opacity != 0:
+                rgbx = _scaled_alpha(rgba_to_rgbx(*parseHtmlColor(props.fill)), opacity)
+                if (rgbx >> 24) > 0 or blend == OverwriteBlend:
+                    b.add_fill(path, props.transform, rgbx, props.fillRule, blend, layer)
+        blend = NormalBlend
+        if props.stroke != 0 and props.strokeWidth > 0:
+            rgbx = _scaled_alpha(props.stroke, props.opacity * props.strokeOpacity)
+            if (rgbx >> 24) > 0:
+                b.add_stroke(path, props.transform, props.strokeWidth, props.strokeLineCap, props.strokeLineJoin,
+                             props.strokeMiterLimit, props.strokeDashArray, rgbx, host.NonZero, NormalBlend, layer)
     return b
