@@ -197,6 +197,14 @@ int pixie_cuda_magnify_by2(pixie_image_t src, int power, pixie_image_t* out);
  * Every pixel of the image is overwritten (image.unsafe[x, y] = gradientColor(t)). */
 int pixie_cuda_fill_gradient(pixie_image_t image, int kind, const float* handles_xy, int n_handles,
                              const float* stop_pos, const float* stop_rgba, int n_stops, float opacity);
+/* The composite of a non-solid fillPath / strokePath whose paint is a gradient (paths.nim:2115-2142) in one pass:
+ * `fill.fillGradient(paint at opacity 1); mask.applyOpacity(paint.opacity); fill.draw(mask, MaskBlend);
+ * image.draw(fill, blend_mode)` with the gradient evaluated inside the blend — the fill image never exists and, for
+ * NormalBlend, pixels where the mask is 0 are not touched.  mask: canvas-sized RGBX (alpha used) or A8 image holding
+ * the shape's coverage (what fillPath(mask, white) leaves).  Bit-identical to the four separate calls. */
+int pixie_cuda_fill_gradient_masked(pixie_image_t image, pixie_image_t mask, int kind, const float* handles_xy,
+                                    int n_handles, const float* stop_pos, const float* stop_rgba, int n_stops,
+                                    float opacity, int blend_mode);
 
 /* ---- blur / spread / shadow (images.nim:304-365, :700-758, :760-776) ------------------------
  * lut = gaussianKernel(radius) (internal.nim:17-34), 2*radius+1 uint16 taps, computed by the

@@ -171,7 +171,16 @@ class Image:
 
     def _composite_non_solid(self, mask: "Image", paint: Paint):
         """paths.nim:2115-2142: fill image + mask, `fill.draw(mask, MaskBlend); image.draw(fill, blendMode)`
-        fused into one pass (pixie_cuda_blend_rect_masked)."""
+        fused into one pass (pixie_cuda_blend_rect_masked); a gradient paint is evaluated inside that pass
+        (pixie_cuda_fill_gradient_masked): no fill image at all."""
+        if paint.kind in (LinearGradientPaint, RadialGradientPaint, AngularGradientPaint):
+            if len(paint.gradientStops) == 0:
+                raise PixieError("Gradient must have at least 1 color stop")
+            stops = [(float(st.position), tuple(float(v) for v in (_some_color(st.color) if isinstance(st.color, str) else st.color)))
+                     for st in paint.gradientStops]
+            dev.fill_gradient_masked(self._d, mask._d, paint.kind, [tuple(h) for h in paint.gradientHandlePositions], stops,
+                                     paint.opacity, paint.blendMode)
+            return
         fill = Image(self.width, self.height)
         if paint.kind == ImagePaint:
             dev.draw(fill._d, paint.image._d, paint.imageMat, NormalBlend)        # fill.draw(paint.image, paint.imageMat)

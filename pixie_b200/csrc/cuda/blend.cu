@@ -21,14 +21,24 @@ struct RectArgs {
 };
 
 template <int MODE>
-PXD px_t rect_op(px_t d, px_t s) {
+PXD px_t rect_op(px_t d, px_t s, const BlendTab& T) {
   // Normal / Mask rows go through the x86 row kernels (images.nim:485-520 -> sse2.nim:590-616,690-715),
   // Overwrite is a copy, everything else is blender() per pixel (images.nim:521-529).
   if (MODE == NormalBlend) return line_normal(d, s);
   if (MODE == MaskBlend) return line_mask(d, s);
   if (MODE == OverwriteBlend) return s;
+  if (mode_uses_tables(MODE)) return blend_px_tab<MODE>(d, s, T);
   return blend_px<MODE>(d, s);
 }
+
+// straight[a << 8 | c] = straight_(c, a): built once per process by the function the table replaces
+__device__ uint8_t g_straight_table[65536];
+__global__ void __launch_bounds__(256) build_straight_table_kernel() {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  g_straight_table[i] = (uint8_t)straight_(i & 255u, i >> 8);
+}
+constexpr size_t kTabSmem = 65536 + 1024 + 1024;  // straight, inv, div255
+static bool g_straight_built = false;             // per process (one GPU per process); the API lock serialises callers
 
 PXD uint4 ld16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 PXD uint4 ld16_stream(const void* p) {
@@ -47,7 +57,23 @@ PXD uint4 ld16_stream(const void* p) {
 #define PIXIE_BLEND_MINB 4
 #endif
 template <int MODE, int MASK>
-__global__ void __launch_bounds__(256, PIXIE_BLEND_MINB) blend_rect_vec4(const RectArgs a) {
+__global__ void __launch_bounds__(256, mode_uses_tables(MODE) ? 3 : PIXIE_BLEND_MINB) blend_rect_vec4(const RectArgs a) {
+  BlendTab T = {nullptr, nullptr, nullptr};
+  if (mode_uses_tables(MODE)) {  // the ALU-bound modes: tables into shared memory (66 KB, three CTAs per SM, one wave)
+    extern __shared__ __align__(16) uint8_t tab_smem[];
+    const uint4* src = reinterpret_cast<const uint4*>(g_straight_table);
+    uint4* dst = reinterpret_cast<uint4*>(tab_smem);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < 65536 / 16; i += 256) dst[i] = src[i];
+    uint32_t* inv = reinterpret_cast<uint32_t*>(tab_smem + 65536);
+    float* d255 = reinterpret_cast<float*>(tab_smem + 65536 + 1024);
+    inv[threadIdx.x] = g_inv_table.v[threadIdx.x];
+    d255[threadIdx.x] = g_blend_tables.div255[threadIdx.x];
+    __syncthreads();
+    T.straight = tab_smem;
+    T.inv = inv;
+    T.div255 = d255;
+  }
   const int g0 = a.xs >> 2;
   const int g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
   const int x = g << 2;
@@ -85,7 +111,7 @@ __global__ void __launch_bounds__(256, PIXIE_BLEND_MINB) blend_rect_vec4(const R
             const uint32_t m = (mw[r] >> (8 * k)) & 255u;
             if (m != 255u) sx = mul_div255(sx, m);
           }
-          dp[k] = rect_op<MODE>(MODE == OverwriteBlend ? 0u : dp[k], sx);
+          dp[k] = rect_op<MODE>(MODE == OverwriteBlend ? 0u : dp[k], sx, T);
         }
         *reinterpret_cast<uint4*>(a.dst + (size_t)a.dw * (yb + r) + x) = dv[r];
       }
@@ -135,7 +161,7 @@ __global__ void __launch_bounds__(256, PIXIE_BLEND_MINB) blend_rect_vec4(const R
         if (in_rect) {
           px_t sx = sp[k];
           if (MASK != 0) sx = mul_div255(sx, mv[r][k]);
-          dp[k] = rect_op<MODE>(dp[k], sx);
+          dp[k] = rect_op<MODE>(dp[k], sx, T);
         } else if (MODE == MaskBlend) {
           dp[k] = 0u;  // images.nim:501-520: MaskBlend clears everything the source does not cover
         }
@@ -158,7 +184,8 @@ __global__ void __launch_bounds__(256) blend_rect_scalar(const RectArgs a) {
       px_t s = a.src[sidx];
       if (MASK == 1) s = mul_div255(s, reinterpret_cast<const px_t*>(a.mask)[sidx] >> 24);
       else if (MASK == 2) s = mul_div255(s, a.mask[sidx]);
-      *dp = rect_op<MODE>(*dp, s);
+      const BlendTab T0 = {nullptr, nullptr, nullptr};
+      *dp = mode_uses_tables(MODE) ? blend_px<MODE>(*dp, s) : rect_op<MODE>(*dp, s, T0);
     } else if (MODE == MaskBlend) {
       *dp = 0u;
     }
@@ -170,7 +197,9 @@ static int launch_rect(const RectArgs& a) {
   Runtime& r = rt();
   const int rows = a.ye - a.ys;
   if (rows <= 0 || a.xe <= a.xs) return 0;
-  const int target_blocks = r.num_sms * 8;
+  constexpr bool TAB = mode_uses_tables(MODE);
+  // table modes: one wave of three CTAs per SM, each staging the tables once and striding over the rows
+  const int target_blocks = TAB ? r.num_sms * 3 : r.num_sms * 8;
   if ((a.dw & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dst) & 15) == 0) {
     const int groups = ((a.xe + 3) >> 2) - (a.xs >> 2);
     dim3 grid((groups + 255) / 256, 1);
@@ -179,8 +208,20 @@ static int launch_rect(const RectArgs& a) {
     int max_gy = (rows + PIXIE_BLEND_ROWS - 1) / PIXIE_BLEND_ROWS;
     if (gy > max_gy) gy = max_gy;
     grid.y = gy;
+    if (TAB) {
+      if (!g_straight_built) {
+        build_straight_table_kernel<<<256, 256, 0, r.stream>>>();
+        PX_LAUNCHED();
+        g_straight_built = true;
+      }
+      static bool configured = false;  // per instantiation
+      if (!configured) {
+        PX_CUDA(cudaFuncSetAttribute(blend_rect_vec4<MODE, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTabSmem));
+        configured = true;
+      }
+    }
     ProfScope ps(kProfBlend);
-    blend_rect_vec4<MODE, MASK><<<grid, 256, 0, r.stream>>>(a);
+    blend_rect_vec4<MODE, MASK><<<grid, 256, TAB ? kTabSmem : 0, r.stream>>>(a);
   } else {
     dim3 grid((a.xe - a.xs + 255) / 256, 1);
     int gy = target_blocks / (int)grid.x;

@@ -370,6 +370,93 @@ PXD px_t blend_px(px_t b, px_t s) {
   return mk(o[0], o[1], o[2], blend_alpha(ba, sa));
 }
 
+// ---- table forms of the seven ALU-bound modes (blend.cu stages the tables in shared memory) -----------------
+// ColorBurn / ColorDodge spend their time in to_straight's float multiply + round per channel and in integer
+// divisions by a variable (burn / dodge quotient, alpha_fix's `div a`); the five float modes in to_straight + the
+// x / 255 conversions.  straight[a << 8 | c] holds straight_(c, a) for every (a, c) — built on the device by that very
+// function, so the lookup IS the reference value; inv[d] = ceil(2^32 / d) turns floor(x / d) into one multiply-high,
+// exact whenever x * d < 2^32 (error term x * (inv[d] - 2^32 / d) / 2^32 < 1 / d, and frac(x / d) <= 1 - 1 / d).
+struct BlendTab {
+  const uint8_t* straight;  // [65536]
+  const uint32_t* inv;      // [256], inv[0] = inv[1] = 0 (d == 1 is selected around)
+  const float* div255;      // [256]
+};
+struct InvTable {
+  uint32_t v[256];
+};
+constexpr InvTable make_inv_table() {
+  InvTable t{};
+  for (uint32_t d = 2; d < 256; d++) t.v[d] = (uint32_t)((0x100000000ull + d - 1) / d);
+  return t;
+}
+__device__ const InvTable g_inv_table = make_inv_table();
+
+PXD uint32_t udiv_tab(uint32_t x, uint32_t d, const uint32_t* inv) {  // floor(x / d): 1 <= d <= 255, x * d < 2^32
+  const uint32_t q = __umulhi(x, inv[d]);
+  return d == 1u ? x : q;
+}
+PXD px_t to_straight_tab(px_t p, const uint8_t* st) {
+  const uint32_t a = pA(p);
+  const uint8_t* row = st + (a << 8);
+  return (uint32_t)row[pR(p)] | ((uint32_t)row[pG(p)] << 8) | ((uint32_t)row[pB(p)] << 16) | (a << 24);
+}
+PXD px_t alpha_fix_tab(px_t backdrop, px_t source, px_t mixed, const uint32_t* inv) {  // alpha_fix with `div a` from the table
+  const uint32_t sa = pA(source), ba = pA(backdrop);
+  const uint32_t t0 = sa * (255u - ba), t1 = sa * ba, t2 = (255u - sa) * ba;
+  const uint32_t a = sa + ba * (255u - sa) / 255u;
+  if (a == 0u) return 0u;
+  // t0 + t1 + t2 <= 65025, so every sum below is < 2^24 and sum * a < 2^32
+  const uint32_t r = t0 * pR(source) + t1 * pR(mixed) + t2 * pR(backdrop);
+  const uint32_t g = t0 * pG(source) + t1 * pG(mixed) + t2 * pG(backdrop);
+  const uint32_t b = t0 * pB(source) + t1 * pB(mixed) + t2 * pB(backdrop);
+  return mk(udiv_tab(r, a, inv) / 255u, udiv_tab(g, a, inv) / 255u, udiv_tab(b, a, inv) / 255u, a);
+}
+PXD Col to_color_tab(px_t p, const BlendTab& T) {
+  const px_t s = to_straight_tab(p, T.straight);
+  Col c = {T.div255[pR(s)], T.div255[pG(s)], T.div255[pB(s)], T.div255[pA(s)]};
+  return c;
+}
+// blend_px<MODE> for ColorBurn, ColorDodge, SoftLight, Hue, Saturation, Color, Luminosity — same values, tables in `T`
+template <int MODE>
+PXD px_t blend_px_tab(px_t b, px_t s, const BlendTab& T) {
+  if (MODE == ColorBurnBlend || MODE == ColorDodgeBlend) {
+    const px_t bd = to_straight_tab(b, T.straight), sr = to_straight_tab(s, T.straight);
+    uint32_t o[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const uint32_t bc = (bd >> (8 * c)) & 255u, sc = (sr >> (8 * c)) & 255u;
+      if (MODE == ColorBurnBlend) {
+        const uint32_t q = udiv_tab(255u * (255u - bc), sc, T.inv);  // sc == 0: inv[0] = 0, the value is not used
+        o[c] = bc == 255u ? 255u : (sc == 0u ? 0u : 255u - (min(255u, q) & 255u));
+      } else {
+        const uint32_t q = udiv_tab(255u * bc, 255u - sc, T.inv);
+        o[c] = bc == 0u ? 0u : (sc == 255u ? 255u : min(255u, q));
+      }
+    }
+    return to_premul(alpha_fix_tab(bd, sr, mk(o[0], o[1], o[2], 0u), T.inv));
+  }
+  Col cb = to_color_tab(b, T), cs = to_color_tab(s, T), m = {0.f, 0.f, 0.f, 0.f};
+  if (MODE == SoftLightBlend) {
+    m.r = (1 - 2 * cs.r) * (cb.r * cb.r) + 2 * cs.r * cb.r;
+    m.g = (1 - 2 * cs.g) * (cb.g * cb.g) + 2 * cs.g * cb.g;
+    m.b = (1 - 2 * cs.b) * (cb.b * cb.b) + 2 * cs.b * cb.b;
+  } else if (MODE == HueBlend) {
+    m = set_lum(set_sat(cs, sat(cb)), lum(cb));
+  } else if (MODE == SaturationBlend) {
+    m = set_lum(set_sat(cb, sat(cs)), lum(cb));
+  } else if (MODE == ColorBlend) {
+    m = set_lum(cs, lum(cb));
+  } else {
+    m = set_lum(cb, lum(cs));
+  }
+  return from_color(alpha_fix_f(cb, cs, m));
+}
+// Measured at 8192^2 with an A8 mask: ColorBurn 0.787 -> 0.473 ms, ColorDodge 0.754 -> 0.399 ms.  The five float modes
+// were tried too and are NOT switched over: their time is in the IEEE divisions of clip_color / set_sat / alpha_fix_f,
+// which a table cannot replace, and the 66 KB of tables cost them a resident CTA (SoftLight 0.815 -> 0.838 ms,
+// Hue 1.54 -> 1.65 ms).
+__host__ __device__ constexpr bool mode_uses_tables(int mode) { return mode == ColorBurnBlend || mode == ColorDodgeBlend; }
+
 // run-time mode -> compile-time dispatch (mode is warp-uniform at every call site)
 #define PX_DISPATCH_MODE(mode, EXPR)                                                          \
   switch (mode) {                                                                             \

@@ -468,6 +468,83 @@ __global__ void __launch_bounds__(256) gradient_kernel(const __grid_constant__ G
   for (int y = blockIdx.y; y < G.h; y += gridDim.y) G.img[(size_t)G.w * y + x] = gradient_color(G, gradient_t(G, x, y));
 }
 
+// Non-solid fillPath / strokePath with a gradient paint (paths.nim:2115-2142) in ONE pass over the canvas: the
+// reference fills a canvas-sized `fill` image with the gradient, masks it (`fill.draw(mask, MaskBlend)`) and draws it
+// (`image.draw(fill, blendMode)`).  Here the gradient colour of a pixel is evaluated where it is needed — inside the
+// blend, by the same gradient_t / gradient_color as gradient_kernel — so the fill image never exists (8 B/px less
+// traffic, one launch less) and, for NormalBlend, pixels the mask does not cover cost a mask read and nothing else:
+// the work follows the area of the shape, not of the canvas.  paint.opacity scales the mask (`mask.applyOpacity`,
+// :2138-2139) and is folded in as floor(m * o / 255).
+constexpr int GradGeneric = -1;
+__device__ __noinline__ px_t grad_blend_rt(int mode, px_t b, px_t s) {
+  px_t r = b;
+  PX_DISPATCH_MODE(mode, r = blend_px<MODE>(b, s));
+  return r;
+}
+struct GradBlendArgs {
+  GradientArgs G;       // G.img = the canvas (dst)
+  const uint8_t* mask;  // RGBX (alpha used) or A8, canvas-sized
+  int maskBpp;
+  uint32_t maskOpacity;  // 0..255; 255 = leave the mask as it is
+  int mode;
+};
+template <int MODE>
+__global__ void __launch_bounds__(256) gradient_blend_kernel(const __grid_constant__ GradBlendArgs A) {
+  const GradientArgs& G = A.G;
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (x0 >= G.w) return;
+  const int nx = min(4, G.w - x0);
+  const bool vec = nx == 4 && (G.w & 3) == 0;
+  for (int y = blockIdx.y; y < G.h; y += gridDim.y) {
+    const size_t idx = (size_t)G.w * y + x0;
+    uint32_t m[4] = {0u, 0u, 0u, 0u};
+    if (A.maskBpp == 4) {
+      const px_t* mp = reinterpret_cast<const px_t*>(A.mask) + idx;
+      if (vec) {
+        const uint4 v = *reinterpret_cast<const uint4*>(mp);
+        m[0] = v.x >> 24; m[1] = v.y >> 24; m[2] = v.z >> 24; m[3] = v.w >> 24;
+      } else {
+        for (int k = 0; k < nx; k++) m[k] = mp[k] >> 24;
+      }
+    } else {
+      const uint8_t* mp = A.mask + idx;
+      if (vec) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(mp);
+        m[0] = v & 255u; m[1] = (v >> 8) & 255u; m[2] = (v >> 16) & 255u; m[3] = v >> 24;
+      } else {
+        for (int k = 0; k < nx; k++) m[k] = mp[k];
+      }
+    }
+    if (A.maskOpacity != 255u) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) m[k] = (m[k] * A.maskOpacity) / 255u;  // mul_div255 on the alpha channel
+    }
+    // blendNormal with a transparent source leaves the backdrop alone (sse2.nim:590-616: d * 255 div 255 + 0)
+    if (MODE == NormalBlend && (m[0] | m[1] | m[2] | m[3]) == 0u) continue;
+    px_t* dp = G.img + idx;
+    uint4 dv = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&dv);
+    if (vec) dv = *reinterpret_cast<const uint4*>(dp);
+    else for (int k = 0; k < nx; k++) d[k] = dp[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (k >= nx) continue;
+      if (MODE == NormalBlend && m[k] == 0u) continue;
+      px_t sx = 0u;
+      if (m[k] != 0u) {
+        sx = gradient_color(G, gradient_t(G, x0 + k, y));
+        if (m[k] != 255u) sx = mul_div255(sx, m[k]);
+      }
+      if (MODE == NormalBlend) d[k] = line_normal(d[k], sx);   // images.nim:485-500 row kernels, as blend_rect
+      else if (MODE == MaskBlend) d[k] = line_mask(d[k], sx);
+      else if (A.mode == OverwriteBlend) d[k] = sx;
+      else d[k] = grad_blend_rt(A.mode, d[k], sx);
+    }
+    if (vec) *reinterpret_cast<uint4*>(dp) = dv;
+    else for (int k = 0; k < nx; k++) dp[k] = d[k];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host: vmath Mat3 pieces (column-major m[c*3+r]) and the draw() decision logic
 // ---------------------------------------------------------------------------------------------
@@ -794,12 +871,53 @@ int pixie_cuda_magnify_by2(pixie_image_t src, int power, pixie_image_t* out) {
   return 0;
 }
 
+static int gradient_setup(GradientArgs& G, Image* im, int kind, const float* handles, int n_handles, const float* stop_pos,
+                          const float* stop_rgba, int n_stops, float opacity);
+
 int pixie_cuda_fill_gradient(pixie_image_t image, int kind, const float* handles, int n_handles, const float* stop_pos,
                              const float* stop_rgba, int n_stops, float opacity) {
   PX_API_GUARD;
   if (int rc = ensure_init()) return rc;
   Image* im = find_image(image);
   if (!im) return 1;
+  opacity = opacity < 0.0f ? 0.0f : (opacity > 1.0f ? 1.0f : opacity);
+  if (opacity == 0.0f) return 0;
+  GradientArgs G;
+  if (int rc = gradient_setup(G, im, kind, handles, n_handles, stop_pos, stop_rgba, n_stops, opacity)) return rc;
+  gradient_kernel<<<grid_2d(im->w, im->h), 256, 0, rt().stream>>>(G);
+  PX_LAUNCHED();
+  return 0;
+}
+
+int pixie_cuda_fill_gradient_masked(pixie_image_t image, pixie_image_t maskh, int kind, const float* handles, int n_handles,
+                                    const float* stop_pos, const float* stop_rgba, int n_stops, float opacity, int blend_mode) {
+  PX_API_GUARD;
+  if (int rc = ensure_init()) return rc;
+  Image* im = find_image(image);
+  Image* mk_ = find_image(maskh);
+  if (!im || !mk_) return 1;
+  if (blend_mode < 0 || blend_mode >= NumBlendModes) return fail_pixie("invalid blend mode");
+  if (mk_->w != im->w || mk_->h != im->h || mk_->layers != 1 || (mk_->bpp != 4 && mk_->bpp != 1))
+    return fail_pixie("mask must be a single-layer RGBX or A8 image of the canvas size");
+  if (mk_->data == im->data) return fail_pixie("fill_gradient_masked: mask and image must differ");
+  opacity = opacity < 0.0f ? 0.0f : (opacity > 1.0f ? 1.0f : opacity);
+  if (opacity == 0.0f) return 0;  // paths.nim:2096-2097
+  GradBlendArgs A;
+  // the gradient itself is filled at opacity 1 (:2123-2136); paint.opacity scales the mask (:2138-2139, images.nim:261-277)
+  if (int rc = gradient_setup(A.G, im, kind, handles, n_handles, stop_pos, stop_rgba, n_stops, 1.0f)) return rc;
+  A.mask = mk_->data; A.maskBpp = mk_->bpp; A.mode = blend_mode;
+  A.maskOpacity = (uint32_t)(uint16_t)(int64_t)roundf(255 * opacity);
+  if (A.maskOpacity > 255u) return fail_pixie("opacity out of range");
+  const dim3 grid = grid_2d((im->w + 3) / 4, im->h);
+  if (blend_mode == NormalBlend) gradient_blend_kernel<NormalBlend><<<grid, 256, 0, rt().stream>>>(A);
+  else if (blend_mode == MaskBlend) gradient_blend_kernel<MaskBlend><<<grid, 256, 0, rt().stream>>>(A);
+  else gradient_blend_kernel<GradGeneric><<<grid, 256, 0, rt().stream>>>(A);
+  PX_LAUNCHED();
+  return 0;
+}
+
+static int gradient_setup(GradientArgs& G, Image* im, int kind, const float* handles, int n_handles, const float* stop_pos,
+                          const float* stop_rgba, int n_stops, float opacity) {
   if (im->bpp != 4 || im->layers != 1) return fail_pixie("fillGradient needs a single-layer RGBX image");
   if (kind < 3 || kind > 5) return fail_pixie("Paint must be a gradient");  // paints.nim:247-248
   if (kind == 3 && n_handles != 2) return fail_pixie("Linear gradient requires 2 handles");
@@ -807,9 +925,6 @@ int pixie_cuda_fill_gradient(pixie_image_t image, int kind, const float* handles
   if (kind == 5 && n_handles != 3) return fail_pixie("Angular gradient requires 2 handles");
   if (n_stops == 0) return fail_pixie("Gradient must have at least 1 color stop");
   if (n_stops < 0 || n_stops > kMaxStops) return fail_pixie("too many gradient stops (64 at most)");
-  opacity = opacity < 0.0f ? 0.0f : (opacity > 1.0f ? 1.0f : opacity);
-  if (opacity == 0.0f) return 0;
-  GradientArgs G;
   memset(&G, 0, sizeof G);
   G.img = (px_t*)im->data; G.w = im->w; G.h = im->h; G.kind = kind; G.n = n_stops; G.opacity = opacity;
   memcpy(G.pos, stop_pos, (size_t)n_stops * 4);
@@ -836,8 +951,6 @@ int pixie_cuda_fill_gradient(pixie_image_t image, int kind, const float* handles
     const float nl = vlen(ex, ey);
     G.gradientAngle = fix(atan2f(ey / nl, ex / nl));
   }
-  gradient_kernel<<<grid_2d(im->w, im->h), 256, 0, rt().stream>>>(G);
-  PX_LAUNCHED();
   return 0;
 }
 

@@ -63,6 +63,7 @@ _SIGNATURES = {
     "pixie_cuda_minify_by2": [u64, i32, P(u64)],
     "pixie_cuda_magnify_by2": [u64, i32, P(u64)],
     "pixie_cuda_fill_gradient": [u64, i32, vp, i32, vp, vp, i32, f32],
+    "pixie_cuda_fill_gradient_masked": [u64, u64, i32, vp, i32, vp, vp, i32, f32, i32],
     "pixie_cuda_blur": [u64, vp, i32, u32],
     "pixie_cuda_blur_rows": [u64, vp, i32, u32, i32, i32],
     "pixie_cuda_blur_rows_to": [u64, u64, vp, i32, u32, i32, i32],
@@ -392,9 +393,9 @@ class CmdList:
     """Device-resident command list (segments + fill headers in HBM)."""
 
     @classmethod
-    def from_paths(cls, width, height, layers, batch: "PathBatch"):
+    def from_paths(cls, width, height, layers, batch: "PathBatch", packed=None):
         """Path commands in, flattened / stroked on the device (pixie_cuda_cmdlist_create_from_paths)."""
-        descs, cmds, raw, rw = batch.packed()
+        descs, cmds, raw, rw = packed if packed is not None else batch.packed()
         self = cls.__new__(cls)
         h = u64(0)
         check(lib().pixie_cuda_cmdlist_create_from_paths(
@@ -498,6 +499,15 @@ def fill_gradient(image: DeviceImage, kind, handles, stops, opacity=1.0):
     col = np.ascontiguousarray([s[1] for s in stops], np.float32).reshape(-1)
     check(lib().pixie_cuda_fill_gradient(image.handle, kind, hx.ctypes.data, len(hx) // 2, pos.ctypes.data,
                                          col.ctypes.data, len(stops), opacity))
+
+
+def fill_gradient_masked(image: DeviceImage, mask: DeviceImage, kind, handles, stops, opacity, mode):
+    """Gradient paint composited through a coverage mask in one pass (pixie_cuda_fill_gradient_masked)."""
+    hx = np.ascontiguousarray(np.asarray(handles, np.float32).reshape(-1))
+    pos = np.ascontiguousarray([s[0] for s in stops], np.float32)
+    col = np.ascontiguousarray([s[1] for s in stops], np.float32).reshape(-1)
+    check(lib().pixie_cuda_fill_gradient_masked(image.handle, mask.handle, kind, hx.ctypes.data, len(hx) // 2, pos.ctypes.data,
+                                                col.ctypes.data, len(stops), opacity, mode))
 
 
 def blur(image: DeviceImage, lut, radius, oob=0):

@@ -318,3 +318,41 @@ def test_draw_degenerate_transforms(mat):
         return
     gb.draw(a, src, m, NormalBlend)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("kind", [3, 4, 5])
+@pytest.mark.parametrize("shape", [(256, 96), (203, 61)])
+def test_fill_gradient_masked_equals_unfused_sequence(kind, shape):
+    """pixie_cuda_fill_gradient_masked == fillGradient(opacity 1) + applyOpacity(mask) + blend_rect_masked, for every
+    blend mode, RGBX and A8 masks, paint opacities 1 / 0.6 (paths.nim:2115-2142)."""
+    from pixie_b200 import device as dev, synth
+
+    w, h = shape
+    dev.init(0)
+    rng = np.random.default_rng(kind * 100 + w)
+    dst0 = synth.random_premultiplied(h, w, 5)
+    cov = synth.coverage_mask(h, w, 6)
+    cov[:, : w // 5] = 0       # uncovered stretches (the skip path) and fully covered ones
+    cov[: h // 4, w // 2:] = 255
+    mask_rgbx = np.zeros((h, w, 4), np.uint8)
+    mask_rgbx[..., :] = cov[..., None]
+    handles = [(w * 0.2, h * 0.3), (w * 0.9, h * 0.7)] if kind == 3 else [(w * 0.5, h * 0.5), (w * 0.9, h * 0.5), (w * 0.5, h * 0.95)]
+    stops = [(0.0, (1.0, 0.2, 0.1, 1.0)), (0.35, (0.1, 0.9, 0.3, 0.4)), (1.0, (0.2, 0.1, 1.0, 0.85))]
+    for mode in range(20):
+        for opacity in (1.0, 0.6):
+            for a8 in (False, True):
+                want = dev.DeviceImage(w, h).upload(dst0)
+                fill = dev.DeviceImage(w, h)
+                dev.fill_gradient(fill, kind, handles, stops, 1.0)
+                m = dev.DeviceImage(w, h).upload(mask_rgbx)
+                if opacity != 1.0:
+                    dev.apply_opacity(m, opacity)
+                dev.blend_rect_masked(want, fill, m, 0, 0, mode)
+                got = dev.DeviceImage(w, h).upload(dst0)
+                if a8:
+                    m2 = dev.DeviceImage(w, h, a8=True).upload(np.ascontiguousarray(cov))
+                else:
+                    m2 = dev.DeviceImage(w, h).upload(mask_rgbx)
+                dev.fill_gradient_masked(got, m2, kind, handles, stops, opacity, mode)
+                a, b = got.download(), want.download()
+                assert (a == b).all(), (mode, opacity, a8, int((a != b).any(axis=-1).sum()))

@@ -116,3 +116,30 @@ def test_no_cpu_fallback_without_gpu():
         device.init(0)
     with pytest.raises(PixieError):
         device.DeviceImage(8, 8)
+
+
+def test_path_batch_packing():
+    """PathBatch (the host side of pixie_cuda_cmdlist_create_from_paths): command counts, host fallback for arcs /
+    round joins / dashes, and the ctypes struct has the header's layout (80 bytes)."""
+    import ctypes
+
+    from pixie_b200 import host
+    from pixie_b200.device import PathBatch, PathDesc, _scan_commands
+
+    assert ctypes.sizeof(PathDesc) == 80
+    p = host.parsePath("M 1 2 L 3 4 C 1 1 2 2 3 3 Q 1 1 5 5 Z")
+    assert _scan_commands(p.commands) == (5, False)
+    arc = host.parsePath("M 1 2 A 5 5 0 1 0 9 9 Z")
+    assert _scan_commands(arc.commands) == (3, True)
+    b = PathBatch()
+    b.add_fill(p, None, 0xFF0000FF, 0, 0, 0)
+    b.add_fill(arc, None, 0xFF0000FF, 0, 0, 0)
+    b.add_stroke(p, None, 2.0, host.RoundCap, host.MiterJoin, 4.0, (), 0xFF0000FF, 0, 0, 0)
+    b.add_stroke(p, None, 2.0, host.ButtCap, host.BevelJoin, 4.0, (), 0xFF0000FF, 0, 0, 1)
+    b.add_stroke(p, None, 2.0, host.ButtCap, host.BevelJoin, 4.0, (3.0, 1.0), 0xFF0000FF, 0, 0, 1)
+    assert [d.kind for d in b.descs] == [0, 2, 2, 1, 2] and b.host_paths == 3
+    descs, cmds, raw, rw = b.packed()
+    assert len(cmds) == 2 * len(p.commands) and descs[3].begin == len(p.commands) and descs[3].num_commands == 5
+    assert descs[1].begin == 0 and descs[1].end == len(host.fill_segments(arc))
+    assert raw.shape[0] == len(rw) == descs[4].end
+    assert descs[3].layer == 1 and descs[3].line_join == host.BevelJoin

@@ -1,0 +1,2 @@
+python -m pytest tests/test_gpu_blend_blur.py tests/test_gpu_baseline_sizes.py tests/test_gpu_fill.py -x -q 2>&1 | tail -5
+python tools/time_blend.py
