@@ -446,8 +446,89 @@ def extras_draw_paint(dev, peak):
     ]:
         t = timed(fn)
         draws[name] = {"ms": round(t, 4), "GB/s": round(nbytes / t / 1e6, 1), "frac_hbm": round(nbytes / t / 1e6 / peak, 3)}
+    # non-solid paint composite (paths.nim:2115-2142) through the coverage mask of an ellipse covering ~21 % of the canvas:
+    # the gradient evaluated inside the masked blend against fillGradient + blend_rect_masked
+    mask = dev.DeviceImage(n, n)
+    ell = host.newPath()
+    ell.ellipse(n / 2, n / 2, n * 0.3, n * 0.22)
+    dev.fill_segments(mask, host.fill_segments(ell), 0xFFFFFFFF, 0, 0)
+    fill = dev.DeviceImage(n, n)
+    hl, hr = [(n * 0.2, n * 0.3), (n * 0.9, n * 0.7)], [(n / 2, n / 2), (n * 0.9, n / 2), (n / 2, n * 0.95)]
+    paints = {}
+    for name, kind, handles in (("linear", 3, hl), ("radial", 4, hr), ("angular", 5, hr)):
+        def separate():
+            dev.fill_gradient(fill, kind, handles, stops, 1.0)
+            dev.blend_rect_masked(dst, fill, mask, 0, 0, 0)
+
+        t_sep = timed(separate)
+        want = dst.download_rows(n // 2 - 8, n // 2 + 8)
+        t_fused = timed(lambda: dev.fill_gradient_masked(dst, mask, kind, handles, stops, 1.0, 0))
+        same = bool(np.array_equal(want, dst.download_rows(n // 2 - 8, n // 2 + 8)))
+        paints[name] = {"fused_ms": round(t_fused, 4), "separate_passes_ms": round(t_sep, 4), "rows_equal": same}
     return {"bytes_per_px": "draw 12 (dst r+w, src r); scale 0.5: minify 5/src px + draw over the covered quarter; "
-                            "gradient 4 (write)", "ops": draws}
+                            "gradient 4 (write)", "ops": draws,
+            "gradient_paint_composite_normal": {"what": "fillPath with a gradient paint, mask given: pixie_cuda_fill_gradient_masked "
+                                                        "(gradient evaluated inside the masked blend, mask-0 pixels skipped) vs "
+                                                        "fillGradient + blend_rect_masked; ellipse covering 21 % of 8192^2",
+                                                "paints": paints}}
+
+
+def extras_flatten(dev):
+    """the tiger from path COMMANDS — flattening, stroking and shapesToSegments on the device
+    (pixie_cuda_cmdlist_create_from_paths) against libpixie_host.so (the C++ mirror of the reference's host code) +
+    pixie_cuda_cmdlist_create from its segments.  Wall clock, inputs in host memory, the list resident afterwards."""
+    from pixie_b200 import host, svg as psvg
+
+    size = 4096
+    doc = psvg.parseSvg(open(os.path.join(ROOT, "tests", "golden", "tiger.svg")).read(), size, size)
+    calls = []
+    for d, props in doc.elements:
+        if not (props.display and props.opacity > 0):
+            continue
+        path = host.parsePath(d)
+        if props.fill != "none":
+            calls.append((host.fill_segments, (path, props.transform)))
+        if props.stroke != 0 and props.strokeWidth > 0:
+            calls.append((host.stroke_segments, (path, props.transform, props.strokeWidth, props.strokeLineCap, props.strokeLineJoin,
+                                                props.strokeMiterLimit, props.strokeDashArray)))
+    tc = []
+    for it in range(4):
+        t0 = time.perf_counter()
+        for fn, a in calls:
+            fn(*a)
+        tc.append(time.perf_counter() - t0)
+    arrays = psvg.svg_fill_batch(doc).arrays()
+    pb = psvg.svg_path_batch(doc)
+    packed = pb.packed()
+    th, td = [], []
+    for it in range(6):
+        dev.sync()
+        t0 = time.perf_counter()
+        cl = dev.CmdList(size, size, 1, arrays)
+        dev.sync()
+        th.append(time.perf_counter() - t0)
+        del cl
+        t0 = time.perf_counter()
+        cl = dev.CmdList.from_paths(size, size, 1, pb, packed)
+        dev.sync()
+        td.append(time.perf_counter() - t0)
+        if it == 5:
+            xy, wd, so = cl.segments()
+            same = bool(np.array_equal(xy, arrays["xyxy"]) and np.array_equal(wd, arrays["winding"]) and
+                        np.array_equal(so, arrays["seg_offsets"]))
+        del cl
+    t_host = statistics.median(tc[1:]) + statistics.median(th[2:])
+    t_dev = statistics.median(td[2:])
+    ncmd = sum(d.num_commands for d in pb.descs)
+    return {"paths": len(pb), "commands": ncmd, "segments": int(len(arrays["winding"])), "paths_flattened_on_host": pb.host_paths,
+            "h2d_bytes": {"commands_and_headers": int(len(packed[1]) * 4 + len(pb) * 80), "segments_host_path": int(len(arrays["winding"]) * 18)},
+            "device": {"ms": round(t_dev * 1e3, 3), "call": "pixie_cuda_cmdlist_create_from_paths (H2D of the command stream, resolve / count / "
+                                                            "scan / emit / stroke / bounds kernels, 3 small readbacks, list build)"},
+            "cpu_baseline": {"kind": "port", "cores": 1, "ms": round(t_host * 1e3, 3),
+                             "flatten_ms": round(statistics.median(tc[1:]) * 1e3, 3), "cmdlist_create_ms": round(statistics.median(th[2:]) * 1e3, 3),
+                             "sample": f"{len(calls)} fill_segments / stroke_segments calls into libpixie_host.so (commandsToShapes + "
+                                       "strokeShapes + shapesToSegments as the reference's host code, 1 thread) + pixie_cuda_cmdlist_create"},
+            "speedup": round(t_host / t_dev, 1), "segments_equal_host_flattener": same}
 
 
 def icons_batch(dev, rank, world, n_icons=1024, size=512, cpu_sample=128):
@@ -934,7 +1015,8 @@ def run_ours(args):
         if not args.no_extras:
             extras = {}
             for key, fn in [("blend_8192_masked", lambda: extras_blend(dev, peak)), ("blur_shadow_16384", lambda: extras_blur_shadow(dev, peak)),
-                            ("draw_paint_8192", lambda: extras_draw_paint(dev, peak)), ("icons_512_batch", lambda: icons_batch(dev, 0, 1))]:
+                            ("draw_paint_8192", lambda: extras_draw_paint(dev, peak)), ("icons_512_batch", lambda: icons_batch(dev, 0, 1)),
+                            ("tiger_from_path_commands_4096", lambda: extras_flatten(dev))]:
                 try:  # extras never block the headline line
                     extras[key] = fn()
                 except Exception as e:

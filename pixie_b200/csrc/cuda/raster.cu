@@ -551,7 +551,12 @@ PXD int find_fill_by_job(const int* __restrict__ jobBase, int numFills, int j) {
 // crowded bands are appended to a list for plan_kernel (K2b), where the quadratic sorts get a whole warp.
 // Per-thread scratch: kLightArrays arrays of kLightMax words in shared memory, interleaved by thread.
 // ---------------------------------------------------------------------------------------------
-constexpr int kLightMax = 16;
+// 12: swept on the tiger and on the icon batch (4 / 8 / 12 / 16 -> plan 0.150 / 0.133 / 0.124 / 0.147 ms on the tiger);
+// below that too many small jobs pay a whole warp, above it the longest thread-per-job chains set the kernel's duration
+#ifndef PIXIE_LIGHT_MAX
+#define PIXIE_LIGHT_MAX 12
+#endif
+constexpr int kLightMax = PIXIE_LIGHT_MAX;
 constexpr int kVeryHeavy = 64;  // bands with more entries than this are planned first
 constexpr int kLightArrays = 5;
 constexpr int kLightThreads = 128;

@@ -14,7 +14,7 @@ dev.set_profiling(True)
 arrays = tiger_arrays(size)
 img = dev.DeviceImage(size, size)
 cl = dev.CmdList(size, size, 1, arrays)
-steps, rast = [], []
+steps, rast, plan, part = [], [], [], []
 for it in range(25):
     dev.timer_begin()
     img.fill(0)
@@ -24,8 +24,10 @@ for it in range(25):
         steps.append(t)
         try:
             rast.append(dev.profile_read(dev.PROF_RASTER))
+            plan.append(dev.profile_read(dev.PROF_PLAN))
+            part.append(dev.profile_read(dev.PROF_PARTITION))
         except Exception:
             rast.append(float('nan'))
-print("tiger %d^2 (%s): step %.4f ms (min %.4f)  raster %.4f ms" % (
-    size, os.environ.get("PIXIE_CUDA_BANDS", "8") + " bands", statistics.median(steps), min(steps),
-    statistics.median(rast)))
+print("tiger %d^2 [%s]: step %.4f ms (min %.4f)  partition %.4f  plan %.4f  raster %.4f ms" % (
+    size, os.path.basename(os.environ.get("PIXIE_CUDA_LIB", "in-tree")), statistics.median(steps), min(steps),
+    statistics.median(part) if part else float("nan"), statistics.median(plan) if plan else float("nan"), statistics.median(rast)))
