@@ -182,3 +182,133 @@ proc fillGradientCuda*(image: Image, kind: int, handles: seq[Vec2], stopPosition
     (if hx.len > 0: hx[0].addr else: nil), handles.len.cint,
     (if pos.len > 0: pos[0].addr else: nil), (if col.len > 0: col[0].addr else: nil),
     stopColors.len.cint, opacity.cfloat)
+
+# ---- paths.nim: the gradient branch of the non-solid composite (:2115-2142) in one pass ----------------
+proc pixie_cuda_fill_gradient_masked(image, mask: PixieImageT, kind: cint, handlesXy: ptr float32, nHandles: cint,
+    stopPos, stopRgba: ptr float32, nStops: cint, opacity: cfloat, blendMode: cint): cint {.importc, dynlib: lib, cdecl.}
+
+proc fillGradientMaskedCuda*(image, mask: Image, kind: int, handles: seq[Vec2], stopPositions: seq[float32],
+                             stopColors: seq[Color], opacity: float32, blendMode: BlendMode) {.raises: [PixieError].} =
+  ## `fill.fillGradient(paint at opacity 1); mask.applyOpacity(paint.opacity); fill.draw(mask, MaskBlend);
+  ## image.draw(fill, blendMode)` — `mask` is what `mask.fillPath(path, white)` left (:2112-2113).
+  var
+    hx = newSeq[float32](handles.len * 2)
+    col = newSeq[float32](stopColors.len * 4)
+    pos = stopPositions
+    hImage, hMask: PixieImageT
+  for i, p in handles:
+    hx[i * 2] = p.x
+    hx[i * 2 + 1] = p.y
+  for i, c in stopColors:
+    col[i * 4] = c.r; col[i * 4 + 1] = c.g; col[i * 4 + 2] = c.b; col[i * 4 + 3] = c.a
+  check pixie_cuda_image_create(image.width.cint, image.height.cint, hImage.addr)
+  check pixie_cuda_image_create(mask.width.cint, mask.height.cint, hMask.addr)
+  try:
+    check pixie_cuda_image_upload(hImage, cast[ptr uint8](image.data[0].addr))
+    check pixie_cuda_image_upload(hMask, cast[ptr uint8](mask.data[0].addr))
+    check pixie_cuda_fill_gradient_masked(hImage, hMask, kind.cint,
+      (if hx.len > 0: hx[0].addr else: nil), handles.len.cint,
+      (if pos.len > 0: pos[0].addr else: nil), (if col.len > 0: col[0].addr else: nil),
+      stopColors.len.cint, opacity.cfloat, blendMode.ord.cint)
+    check pixie_cuda_image_download(hImage, cast[ptr uint8](image.data[0].addr))
+  finally:
+    discard pixie_cuda_image_destroy(hImage)
+    discard pixie_cuda_image_destroy(hMask)
+
+# ---- paths.nim: fillPath / strokePath of a whole document from path COMMANDS ---------------------------
+# commandsToShapes (:654-1057), strokeShapes (:1922-2082), transform, shapesToSegments (:1059-1096) run on the device.
+type
+  PixiePathDesc* {.bycopy.} = object   # pixie_path_desc (include/pixie_cuda.h), 80 bytes
+    kind*, begin*, `end`*, numCommands*: int32
+    transform*: array[9, float32]
+    strokeWidth*: float32
+    lineCap*, lineJoin*: int32
+    miterLimit*: float32
+    rgbx*: uint32
+    windingRule*, blendMode*: uint8
+    reserved*: uint16
+    layer*: int32
+  PathBatchCuda* = object
+    descs*: seq[PixiePathDesc]
+    commands*: seq[float32]            # Path.commands of the device-flattened paths, concatenated
+    rawXyxy*: seq[float32]             # segments of the paths flattened by the Nim code (kind = 2)
+    rawWinding*: seq[int16]
+
+proc pixie_cuda_cmdlist_create_from_paths(width, height, layers, numPaths: cint, paths: ptr PixiePathDesc,
+    commands: ptr float32, numCommandFloats: int64, rawXyxy: ptr float32, rawWinding: ptr int16, numRaw: int64,
+    outList: ptr uint64): cint {.importc, dynlib: lib, cdecl.}
+proc pixie_cuda_cmdlist_run(list: uint64, image: PixieImageT, coveredPx: ptr uint64): cint {.importc, dynlib: lib, cdecl.}
+proc pixie_cuda_cmdlist_destroy(list: uint64): cint {.importc, dynlib: lib, cdecl.}
+
+const
+  parameterCounts = [0, 2, 2, 1, 1, 6, 4, 4, 2, 7, 2, 2, 1, 1, 6, 4, 4, 2, 7]   # paths.nim:73-81, by ord(PathCommandKind)
+  arcKinds = {9, 18}
+
+proc scanCommands(commands: seq[float32]): (int, bool) =
+  var i = 0
+  while i < commands.len:
+    let k = commands[i].int
+    if k in arcKinds: result[1] = true
+    i += 1 + parameterCounts[k]
+    inc result[0]
+
+proc addDesc(batch: var PathBatchCuda, kind, b, e, n: int, transform: Mat3, rgbx: ColorRGBX, rule: int, mode: BlendMode) =
+  var d = PixiePathDesc(kind: kind.int32, begin: b.int32, `end`: e.int32, numCommands: n.int32, rgbx: rgbx.asU32,
+                        windingRule: rule.uint8, blendMode: mode.ord.uint8, miterLimit: 4)
+  copyMem(d.transform[0].addr, transform.unsafeAddr, 9 * sizeof(float32))
+  batch.descs.add d
+
+proc addFill*(batch: var PathBatchCuda, commands: seq[float32], transform: Mat3, rgbx: ColorRGBX, windingRule: int,
+              blendMode: BlendMode, hostSegments: proc(): seq[(Segment, int16)]) =
+  ## `hostSegments` = the unchanged Nim code (parseSomePath + transform + shapesToSegments), called for paths with arcs
+  let (n, arc) = scanCommands(commands)
+  if arc:
+    let b = batch.rawWinding.len
+    for (s, w) in hostSegments():
+      batch.rawXyxy.add [s.at.x, s.at.y, s.to.x, s.to.y]
+      batch.rawWinding.add w
+    batch.addDesc(2, b, batch.rawWinding.len, 0, mat3(), rgbx, windingRule, blendMode)
+  else:
+    let b = batch.commands.len
+    batch.commands.add commands
+    batch.addDesc(0, b, batch.commands.len, n, transform, rgbx, windingRule, blendMode)
+
+proc addStroke*(batch: var PathBatchCuda, commands: seq[float32], transform: Mat3, strokeWidth: float32,
+                lineCap, lineJoin: int, miterLimit: float32, dashes: seq[float32], rgbx: ColorRGBX,
+                hostSegments: proc(): seq[(Segment, int16)]) =
+  let (n, arc) = scanCommands(commands)
+  if arc or lineCap == 1 or lineJoin == 1 or dashes.len > 0:   # RoundCap / RoundJoin (paths.nim:10-16), dashes
+    let b = batch.rawWinding.len
+    for (s, w) in hostSegments():
+      batch.rawXyxy.add [s.at.x, s.at.y, s.to.x, s.to.y]
+      batch.rawWinding.add w
+    batch.addDesc(2, b, batch.rawWinding.len, 0, mat3(), rgbx, 0, NormalBlend)
+  else:
+    let b = batch.commands.len
+    batch.commands.add commands
+    batch.addDesc(1, b, batch.commands.len, n, transform, rgbx, 0, NormalBlend)
+    batch.descs[^1].strokeWidth = strokeWidth
+    batch.descs[^1].lineCap = lineCap.int32
+    batch.descs[^1].lineJoin = lineJoin.int32
+    batch.descs[^1].miterLimit = miterLimit
+
+proc fillPathsCuda*(image: Image, batch: var PathBatchCuda) {.raises: [PixieError].} =
+  ## the ordered fills / strokes of `batch` over `image` (newImage(svg), svg.nim:557-608)
+  var
+    h: PixieImageT
+    list: uint64
+  check pixie_cuda_image_create(image.width.cint, image.height.cint, h.addr)
+  try:
+    check pixie_cuda_image_upload(h, cast[ptr uint8](image.data[0].addr))
+    check pixie_cuda_cmdlist_create_from_paths(image.width.cint, image.height.cint, 1, batch.descs.len.cint,
+      (if batch.descs.len > 0: batch.descs[0].addr else: nil),
+      (if batch.commands.len > 0: batch.commands[0].addr else: nil), batch.commands.len.int64,
+      (if batch.rawXyxy.len > 0: batch.rawXyxy[0].addr else: nil),
+      (if batch.rawWinding.len > 0: batch.rawWinding[0].addr else: nil), batch.rawWinding.len.int64, list.addr)
+    try:
+      check pixie_cuda_cmdlist_run(list, h, nil)
+      check pixie_cuda_image_download(h, cast[ptr uint8](image.data[0].addr))
+    finally:
+      discard pixie_cuda_cmdlist_destroy(list)
+  finally:
+    discard pixie_cuda_image_destroy(h)
