@@ -579,6 +579,28 @@ def icons_batch(dev, rank, world, n_icons=1024, size=512, cpu_sample=128):
         es.append(time.perf_counter() - t0)
         del cl2
     te = statistics.median(es[1:])
+    # the same icons from path COMMANDS: flattening + stroking on the device (round joins / caps go through the host)
+    from pixie_b200.device import PathBatch
+
+    pb = PathBatch()
+    for i in range(b0, b1):
+        synth.icon_fills(i, size, i - b0, paths=pb)
+    packed = pb.packed()
+    ep = []
+    for it in range(3):
+        img.fill(0)
+        dev.sync()
+        t0 = time.perf_counter()
+        cl3 = dev.CmdList.from_paths(size, size, b1 - b0, pb, packed)
+        cl3.run(img)
+        c3 = img.checksum()
+        ep.append(time.perf_counter() - t0)
+        del cl3
+    tp = statistics.median(ep[1:])
+    from_paths = {"ms": round(tp * 1e3, 3), "icons_per_s": round((b1 - b0) / tp), "paths": len(pb), "paths_flattened_on_host": pb.host_paths,
+                  "h2d_bytes": int(len(packed[1]) * 4 + len(pb) * 80 + len(packed[3]) * 18),
+                  "call": "pixie_cuda_cmdlist_create_from_paths + _run + _image_checksum from the icons' path commands",
+                  "checksum_equal": bool(c3 == checksum)}
     # parity + CPU baseline: the oracle renders the first `cpu_sample` icons (independent canvases: one icon per
     # thread task), the GPU's layers of the same icons must be byte-equal
     cores = _host_cores()
@@ -601,6 +623,7 @@ def icons_batch(dev, rank, world, n_icons=1024, size=512, cpu_sample=128):
                     "h2d_bytes": nseg * 18 + len(arrays["rgbx"]) * 56, "d2h_bytes": 8 + 24,
                     "call": "pixie_cuda_cmdlist_create + _run + _image_checksum from host segment arrays",
                     "checksum_equal": bool(c2 == checksum)},
+            "e2e_from_path_commands": from_paths,
             "parity_vs_oracle": _parity(len(per_icon) * size * size, bad, 0 if bad == 0 else 255),
             "cpu_baseline": {"kind": "port", "cores": cores, "icons_per_s": round(len(per_icon) / tc, 1),
                              "Mpixel/s": round(cov_cpu / tc / 1e6, 2),

@@ -27,10 +27,11 @@ def _blob(rng, cx, cy, r, knots):
     return p
 
 
-def icon_fills(index: int, size: int = 512, layer: int = 0, batch: FillBatch | None = None, seed: int = 0) -> FillBatch:
+def icon_fills(index: int, size: int = 512, layer: int = 0, batch: FillBatch | None = None, seed: int = 0, paths=None):
     """One synthetic icon: 1-8 sub-paths of rect / roundedRect / ellipse / polygon /
     closed cubic blobs / nested even-odd contours, optional strokes; seed = icon index; transparent
-    canvas, first fill OverwriteBlend then NormalBlend (svg.nim:562,590)."""
+    canvas, first fill OverwriteBlend then NormalBlend (svg.nim:562,590).  With `paths` (a device.PathBatch) the icon is
+    appended as path commands instead of host-flattened segments."""
     rng = np.random.default_rng([seed, index])
     b = batch if batch is not None else FillBatch()
     lo, hi = size / 32.0, size - size / 32.0
@@ -68,14 +69,20 @@ def icon_fills(index: int, size: int = 512, layer: int = 0, batch: FillBatch | N
         if rng.random() < 0.3:
             a = float(rng.uniform(-0.5, 0.5))
             tr = host.matmul(host.translate(cx, cy), host.matmul(host.rotate(a), host.translate(-cx, -cy)))
+        mode = OverwriteBlend if first else NormalBlend
         if rng.random() < 0.3:
             sw = float(rng.uniform(1, size * 24 / 512))
-            segs = host.stroke_segments(p, tr, sw, int(rng.integers(0, 3)), int(rng.integers(0, 3)))
-            b.add(segs, rgbx, host.NonZero, OverwriteBlend if first else NormalBlend, layer)
+            cap, join = int(rng.integers(0, 3)), int(rng.integers(0, 3))
+            if paths is not None:  # the same icon as path COMMANDS (flattened and stroked on the device)
+                paths.add_stroke(p, tr, sw, cap, join, host.defaultMiterLimit, (), rgbx, host.NonZero, mode, layer)
+            else:
+                b.add(host.stroke_segments(p, tr, sw, cap, join), rgbx, host.NonZero, mode, layer)
+        elif paths is not None:
+            paths.add_fill(p, tr, rgbx, rule, mode, layer)
         else:
-            b.add(host.fill_segments(p, tr), rgbx, rule, OverwriteBlend if first else NormalBlend, layer)
+            b.add(host.fill_segments(p, tr), rgbx, rule, mode, layer)
         first = False
-    return b
+    return b if paths is None else paths
 
 
 def random_premultiplied(h: int, w: int, seed: int) -> np.ndarray:
