@@ -1017,9 +1017,11 @@ def run_ours(args):
     achieved = alg_bytes / (rast * 1e-3) / 1e9
     roofline = {"kernel": "raster_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4),
-                # dram__bytes_read.sum + dram__bytes_write.sum of one raster_kernel launch on this workload, from the
-                # `ncu --set full` capture summarised in profiles/r01_tiger_metrics.txt (20.27 MB read + 12.00 MB written: the canvas stays in the 126 MB L2)
-                "traffic": 32271616 if size == 4096 else None, "peak_source": peak_src,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one raster_kernel launch on this workload, from the offline
+                # `ncu --set full` capture summarised in profiles/r02_tiger_metrics.txt (20.28 MB read + 11.67 MB written:
+                # the canvas stays in the 126 MB L2) — a capture, not measured by this run (traffic_source says so)
+                "traffic": 31952128 if size == 4096 else None, "traffic_source": "profiles/r02_tiger_metrics.txt (ncu capture)",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(rast, 4),
                 "partition_kernel_ms": round(part, 4), "plan_kernel_ms": round(statistics.mean(plan_ms), 4), "share_of_step": round(rast / statistics.mean(step_ms), 3),
                 "note": "305 order-dependent fills: latency/occupancy-bound, not bandwidth-bound (SURVEY.md 7.1)"}
