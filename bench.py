@@ -517,6 +517,20 @@ def extras_flatten(dev):
             same = bool(np.array_equal(xy, arrays["xyxy"]) and np.array_equal(wd, arrays["winding"]) and
                         np.array_equal(so, arrays["seg_offsets"]))
         del cl
+    # end to end, host pixels out: commands -> pixels in one call against host flattening + pixie_cuda_render_batch_host
+    pinned = dev.PinnedBuffer(size * size * 4)
+    te_dev, te_host = [], []
+    for it in range(5):
+        dev.sync()
+        t0 = time.perf_counter()
+        dev.render_paths_host(pinned.ptr, size, size, pb, packed)
+        te_dev.append(time.perf_counter() - t0)
+        if it == 4:
+            px_paths = pinned.array[:size * size * 4].copy()
+        t0 = time.perf_counter()
+        dev.render_batch_host(pinned.ptr, size, size, arrays)
+        te_host.append(time.perf_counter() - t0)
+    same_px = bool(np.array_equal(px_paths, pinned.array[:size * size * 4]))
     t_host = statistics.median(tc[1:]) + statistics.median(th[2:])
     t_dev = statistics.median(td[2:])
     ncmd = sum(d.num_commands for d in pb.descs)
@@ -528,7 +542,11 @@ def extras_flatten(dev):
                              "flatten_ms": round(statistics.median(tc[1:]) * 1e3, 3), "cmdlist_create_ms": round(statistics.median(th[2:]) * 1e3, 3),
                              "sample": f"{len(calls)} fill_segments / stroke_segments calls into libpixie_host.so (commandsToShapes + "
                                        "strokeShapes + shapesToSegments as the reference's host code, 1 thread) + pixie_cuda_cmdlist_create"},
-            "speedup": round(t_host / t_dev, 1), "segments_equal_host_flattener": same}
+            "speedup": round(t_host / t_dev, 1), "segments_equal_host_flattener": same,
+            "e2e_commands_to_host_pixels": {
+                "ms": round(statistics.median(te_dev[1:]) * 1e3, 3), "call": "pixie_cuda_render_paths_host (87 KB of commands in, 64 MiB of pinned pixels out)",
+                "host_flatten_path_ms": round((statistics.median(tc[1:]) + statistics.median(te_host[1:])) * 1e3, 3),
+                "host_flatten_path": "libpixie_host.so flattening + pixie_cuda_render_batch_host", "pixels_equal": same_px}}
 
 
 def icons_batch(dev, rank, world, n_icons=1024, size=512, cpu_sample=128):

@@ -154,6 +154,14 @@ typedef struct pixie_path_desc {
 int pixie_cuda_cmdlist_create_from_paths(int width, int height, int layers, int num_paths, const pixie_path_desc* paths,
                                          const float* commands, int64_t num_command_floats, const float* raw_xyxy,
                                          const int16_t* raw_winding, int64_t num_raw_segments, pixie_cmdlist_t* out);
+/* newImage(svg) (svg.nim:557-608) end to end from path commands: a width x height canvas (transparent when clear != 0,
+ * else initialised from `pixels`), flattening / stroking on the device, the ordered fills, the result in `pixels`
+ * (row bands on concurrent streams, each band copied out behind its raster kernel; page-locked `pixels` overlap).
+ * Every path must have layer 0.  Blocks until `pixels` is complete. */
+int pixie_cuda_render_paths_host(uint8_t* pixels, int width, int height, int clear, int num_paths,
+                                 const pixie_path_desc* paths, const float* commands, int64_t num_command_floats,
+                                 const float* raw_xyxy, const int16_t* raw_winding, int64_t num_raw_segments,
+                                 uint64_t* covered_px);
 /* The segments a list holds, copied to the host (tests, and callers that want shapesToSegments' output):
  * seg_offsets gets num_fills + 1 entries; any pointer may be NULL.  Blocks. */
 int pixie_cuda_cmdlist_segments(pixie_cmdlist_t list, float* seg_xyxy, int16_t* winding, int32_t* seg_offsets);

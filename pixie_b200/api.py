@@ -273,5 +273,7 @@ def readSvg(data: str, width=0, height=0) -> Image:
 
     s = psvg.parseSvg(data, width, height)
     img = newImage(s.width, s.height)
-    dev.fill_batch(img._d, psvg.svg_fill_batch(s).arrays())
+    # the elements stay path COMMANDS: flattening, stroking and shapesToSegments run on the device (arcs, round caps /
+    # joins and dashes are flattened by libpixie_host.so per path, see include/pixie_cuda.h)
+    dev.CmdList.from_paths(s.width, s.height, 1, psvg.svg_path_batch(s)).run(img._d)
     return img

@@ -91,6 +91,7 @@ struct CmdList {
   int maxWrapRows = 0;                          // MaskBlend fills reaching left of the canvas read jobs of later rows
   int* rowsJobBase = nullptr;                   // device [numFills + 1], made per run_rows call
   int* bandRows = nullptr;                      // device [numParts]: rows of every band (static)
+  int* rowOrder = nullptr;                      // device [h]: rows by descending work estimate, null: row order
   unsigned long long* chunkSums = nullptr;      // device [2 * chunks]: scratch of the band scans
 };
 
@@ -393,6 +394,7 @@ struct RasterArgs {
   int ticketSlot;              // counters[ticketSlot] hands out rows
   int smemCap;                 // entries whose scratch fits in shared memory
   int scratchCap;              // capacity of the global spill
+  const int* rowOrder;         // [h] rows by descending work estimate (build_list): the raster kernel's ticket order
   int tileW, tiles;            // a canvas row is rasterised in `tiles` pieces of tileW columns, one warp each
   int covBytes;                // bytes of the per-warp coverage row in shared memory
   int countCovered;
@@ -1586,8 +1588,9 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
     unsigned long long ticket = 0;
     if (lane == 0) ticket = atomicAdd(&A.counters[A.ticketSlot], 1ull);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    const unsigned long long rowOfTicket = ticket / (unsigned)A.tiles + (unsigned long long)A.rowBegin;
+    unsigned long long rowOfTicket = ticket / (unsigned)A.tiles + (unsigned long long)A.rowBegin;
     if ((long long)rowOfTicket >= A.rowEnd) break;
+    if (A.rowOrder) rowOfTicket = (unsigned long long)A.rowOrder[rowOfTicket];  // whole-canvas launches only (rowBegin = 0)
     const int tile = (int)(ticket - (ticket / (unsigned)A.tiles) * (unsigned)A.tiles);
     const unsigned t32 = (unsigned)rowOfTicket;  // layers * h < 2^31 (checked by the host)
     const int layer = (int)(t32 / H_), y = (int)(t32 - (unsigned)layer * H_);
@@ -1918,6 +1921,12 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   const size_t oLayer = off;     off = al(off + layerBegin.size() * 4);
   const size_t oJobBase = off;   off = al(off + jobBase.size() * 4);
   const size_t oBandJobs = off;  off = al(off + (L.bands > 1 ? (size_t)L.bands * jobBase.size() * 4 : 0));
+  // Longest row first (single canvases of 256..65536 rows with at least 16 fills): the raster kernel's persistent warps
+  // take (row, tile) tickets from a counter, and the rows of a drawing differ tenfold in work — handed out top to
+  // bottom, the busy middle rows of the tiger start late and the last of them run alone (12 % of the kernel's warp
+  // slots idle under ncu).  The order comes from a per-row estimate made here from the fill headers, once per list.
+  const bool lpt = layers == 1 && h >= 256 && h <= 65536 && numFills >= 16 && L.bands <= 1;
+  const size_t oRowOrder = off;  off = al(off + (lpt ? (size_t)h * 4 : 0));
   const size_t h2dBytes = off;
   // Small lists (a single fillPath, a glyph, an icon): the band counts, their scans and the packed band ranges are
   // made on the host while it stages the segments anyway, so the call needs no device round trip before it can
@@ -2140,6 +2149,30 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
       else rr[k] = make_int2(F.startY, F.pathHeight);
     }
   }
+  if (lpt) {
+    // what a raster warp spends on one (fill, row): a fixed part, the spans (about two band entries per segment and
+    // band, capped) and the covered width in 128-pixel vector steps; summed per row through a difference array
+    std::vector<long long> diff((size_t)h + 1, 0);
+    for (const FillHeader& F : fills) {
+      if (!F.active || F.numPartitions <= 0 || F.pathHeight <= F.startY) continue;
+      const long long c = 6 + std::min<long long>(64, 2ll * F.segCount / F.numPartitions) + (F.pathWidth >> 7);
+      diff[(size_t)F.startY] += c;
+      diff[(size_t)F.pathHeight] -= c;
+    }
+    std::vector<long long> cost((size_t)h);
+    long long run = 0, mx = 1;
+    for (int y = 0; y < h; y++) {
+      run += diff[(size_t)y];
+      cost[(size_t)y] = run;
+      mx = std::max(mx, run);
+    }
+    int hist[257] = {0};
+    auto bucket = [&](long long c) { return 255 - (int)(c * 255 / mx); };  // 0 = the most expensive rows
+    for (int y = 0; y < h; y++) hist[bucket(cost[(size_t)y]) + 1]++;
+    for (int b = 0; b < 256; b++) hist[b + 1] += hist[b];
+    int* order = reinterpret_cast<int*>(stage + oRowOrder);
+    for (int y = 0; y < h; y++) order[hist[bucket(cost[(size_t)y])]++] = y;
+  }
   memcpy(stage + oLayer, layerBegin.data(), layerBegin.size() * 4);
   memcpy(stage + oJobBase, jobBase.data(), jobBase.size() * 4);
   if (L.bands > 1) {  // per band: prefix over the fills of the scanlines of each path inside the band
@@ -2241,6 +2274,7 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   L.groupRange = (uint32_t*)(L.block + oGroups);
   L.counters = (unsigned long long*)(L.block + oCounters);
   L.bandRows = (int*)(L.block + oBandRows);
+  L.rowOrder = lpt ? (int*)(L.block + oRowOrder) : nullptr;
   L.chunkSums = (unsigned long long*)(L.block + oChunks);
   L.h2dBytes = h2dBytes;
 
@@ -2359,6 +2393,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
   A.rowBegin = 0; A.rowEnd = 0; A.ticketSlot = 0;
   A.scratchSlots = L.scratchSlots; A.scratchSlotCount = L.scratchSlotCount;
   A.planJobBase = L.fillJobBase; A.planY0 = 0; A.planJobs = L.totalJobs;
+  A.rowOrder = nullptr;
   static size_t configured = 0;
   if (L.smemBytes > 48 * 1024 && configured < L.smemBytes) {
     PX_CUDA(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes));
@@ -2410,6 +2445,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
       if (int rc = launch_plan_kernels(L, A, L.totalJobs, L.planBlocks, r.stream, 0)) return rc;
     }
     A.rowBegin = 0; A.rowEnd = totalRows; A.ticketSlot = 0;
+    A.rowOrder = L.bands <= 1 ? L.rowOrder : nullptr;
     {
       ProfScope ps(kProfRaster);
       raster_kernel<<<L.rasterBlocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
@@ -2572,6 +2608,46 @@ int pixie_cuda_cmdlist_create_from_paths(int w, int h, int layers, int numPaths,
   g_lists[hd] = L;
   *out = hd;
   return 0;
+}
+
+int pixie_cuda_render_paths_host(uint8_t* pixels, int width, int height, int clear, int numPaths, const pixie_path_desc* paths,
+                                 const float* commands, int64_t numCommandFloats, const float* rawXyxy, const int16_t* rawWinding,
+                                 int64_t numRaw, uint64_t* covered_px) {
+  PX_API_GUARD;
+  if (int rc = ensure_init()) return rc;
+  if (width <= 0 || height <= 0) return fail_pixie("Image width and height must be > 0");
+  if (numPaths < 0) return fail_pixie("negative path count");
+  for (int k = 0; k < numPaths; k++)
+    if (paths[k].layer != 0) return fail_pixie("render_paths_host renders one canvas (layer 0)");
+  Runtime& r = rt();
+  void* canvas;
+  const size_t bytes = (size_t)width * height * 4;
+  if (int rc = get_scratch(5, bytes, &canvas)) return rc;
+  if (clear) PX_CUDA(cudaMemsetAsync(canvas, 0, bytes, r.stream));                        // newImage(width, height)
+  else PX_CUDA(cudaMemcpyAsync(canvas, pixels, bytes, cudaMemcpyHostToDevice, r.stream));  // draw over existing pixels
+  Image im;
+  im.data = (uint8_t*)canvas; im.w = width; im.h = height; im.layers = 1; im.bpp = 4; im.owned = false;
+  FlattenedPaths F;
+  int rc = flatten_paths(numPaths, paths, commands, numCommandFloats, rawXyxy, rawWinding, numRaw, F);
+  CmdList L;
+  if (!rc) {
+    std::vector<uint32_t> rgbx((size_t)numPaths);
+    std::vector<uint8_t> rule((size_t)numPaths), mode((size_t)numPaths);
+    for (int k = 0; k < numPaths; k++) {
+      rgbx[(size_t)k] = paths[k].rgbx; rule[(size_t)k] = paths[k].winding_rule; mode[(size_t)k] = paths[k].blend_mode;
+    }
+    // row bands on concurrent streams with each band's D2H behind its raster kernel, as pixie_cuda_render_batch_host
+    rc = build_list(L, false, Runtime::kBands, width, height, 1, numPaths, nullptr, nullptr, nullptr, F.segBegin.data(), rgbx.data(),
+                    rule.data(), mode.data(), &F);
+  }
+  free_flattened(F);
+  if (!rc) {
+    if (numPaths == 0) PX_CUDA(cudaMemcpyAsync(pixels, canvas, bytes, cudaMemcpyDeviceToHost, r.stream));
+    else rc = run_list(L, &im, covered_px, pixels);
+  }
+  cudaStreamSynchronize(r.stream);
+  free_list(L);
+  return rc;
 }
 
 int pixie_cuda_cmdlist_segments(pixie_cmdlist_t list, float* segXyxy, int16_t* winding, int32_t* segOffsets) {

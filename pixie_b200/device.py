@@ -53,6 +53,7 @@ _SIGNATURES = {
     "pixie_cuda_cmdlist_destroy": [u64],
     "pixie_cuda_cmdlist_create_from_paths": [i32, i32, i32, i32, vp, vp, C.c_int64, vp, vp, C.c_int64, P(u64)],
     "pixie_cuda_cmdlist_segments": [u64, vp, vp, vp],
+    "pixie_cuda_render_paths_host": [vp, i32, i32, i32, i32, vp, vp, C.c_int64, vp, vp, C.c_int64, P(u64)],
     "pixie_cuda_cmdlist_set_overlap": [u64, i32],
     "pixie_cuda_blend_rect": [u64, u64, i32, i32, i32],
     "pixie_cuda_blend_rect_masked": [u64, u64, u64, i32, i32, i32],
@@ -387,6 +388,17 @@ class PathBatch:
         raw = np.ascontiguousarray(np.concatenate(self._raw, axis=0) if self._raw else np.zeros((0, 4)), np.float32)
         rw = np.ascontiguousarray(np.concatenate(self._rawWind) if self._rawWind else np.zeros(0), np.int16)
         return descs, cmds, raw, rw
+
+
+def render_paths_host(pixels_ptr: int, width: int, height: int, batch: "PathBatch", packed=None, clear=True, count_covered=False):
+    """pixie_cuda_render_paths_host: path commands in, flattened / stroked / rasterised on the device, pixels back to
+    host memory at `pixels_ptr` (ideally a PinnedBuffer)."""
+    descs, cmds, raw, rw = packed if packed is not None else batch.packed()
+    cov = u64(0)
+    check(lib().pixie_cuda_render_paths_host(
+        pixels_ptr, width, height, 1 if clear else 0, len(batch), C.cast(descs, vp), _ptr(cmds), len(cmds), _ptr(raw), _ptr(rw),
+        len(rw), C.byref(cov) if count_covered else None))
+    return cov.value
 
 
 class CmdList:

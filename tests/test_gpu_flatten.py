@@ -206,3 +206,42 @@ def test_errors():
     empty = dev.CmdList.from_paths(32, 32, 1, PathBatch())
     img = dev.DeviceImage(32, 32)
     assert empty.run(img, count_covered=True) == 0
+
+
+def test_render_paths_host_and_read_svg():
+    """pixie_cuda_render_paths_host (commands in, host pixels out, banded D2H) and api.readSvg give the pixels of the
+    host-flattened render."""
+    from pixie_b200 import api, device as dev
+
+    size = 2048
+    dev.init(0)
+    data = open(TIGER).read()
+    doc = psvg.parseSvg(data, size, size)
+    want_img = dev.DeviceImage(size, size)
+    cov_want = dev.CmdList(size, size, 1, psvg.svg_fill_batch(doc).arrays()).run(want_img, count_covered=True)
+    want = want_img.download()
+    pb = psvg.svg_path_batch(doc)
+    pinned = dev.PinnedBuffer(size * size * 4)
+    cov = dev.render_paths_host(pinned.ptr, size, size, pb, count_covered=True)
+    assert cov == cov_want
+    assert (pinned.array[:size * size * 4].reshape(size, size, 4) == want).all()
+    pageable = np.full((size, size, 4), 7, np.uint8)
+    dev.render_paths_host(pageable.ctypes.data, size, size, pb)
+    assert (pageable == want).all()
+    # drawing over existing pixels (clear = False): NormalBlend paths over an opaque backdrop
+    b = PathBatch()
+    tri = host.parsePath("M 100 100 L 1900 300 L 700 1800 Z")
+    b.add_fill(tri, None, 0x80402010, 0, 0, 0)
+    b.add_stroke(tri, None, 25.0, host.SquareCap, host.BevelJoin, 4.0, (), 0xFF00FF00, 0, 0, 0)
+    back = np.full((size, size, 4), 200, np.uint8)
+    back[..., 3] = 255
+    got = back.copy()
+    dev.render_paths_host(got.ctypes.data, size, size, b, clear=False)
+    ref = dev.DeviceImage(size, size).upload(back)
+    hb = FillBatch()
+    hb.add(host.fill_segments(tri, None), 0x80402010, 0, 0, 0)
+    hb.add(host.stroke_segments(tri, None, 25.0, host.SquareCap, host.BevelJoin, 4.0, ()), 0xFF00FF00, 0, 0, 0)
+    dev.fill_batch(ref, hb.arrays())
+    assert (got == ref.download()).all()
+    img = api.readSvg(data, size, size)
+    assert (img._d.download() == want).all()
