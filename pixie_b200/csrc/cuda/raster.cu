@@ -810,8 +810,15 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
   const int warpsTotal = gridDim.x * warpsPerBlock;
   // jobs plan_classify_kernel left for a whole warp: the very crowded ones from the front of the list, then the rest
   const int numFront = (int)A.heavyCount[0], numHeavy = numFront + (int)A.heavyCount[8];
+  // Jobs are handed out one at a time from a counter (heavyCount[16] = counters[32 + launch]): they differ tenfold in
+  // cost and the list starts with the most crowded ones, so whichever warp is free takes the next — a fixed stride left
+  // most warps idle while a few finished their share.
 #pragma unroll 1
-  for (int hj = blockIdx.x * warpsPerBlock + warp; hj < numHeavy; hj += warpsTotal) {
+  while (true) {
+    int hj = 0;
+    if (lane == 0) hj = (int)atomicAdd(A.heavyCount + 16, 1ull);
+    hj = __shfl_sync(0xffffffffu, hj, 0);
+    if (hj >= numHeavy) break;
     const int bj = A.heavyList[hj < numFront ? hj : A.planJobs - 1 - (hj - numFront)];
     const int f = find_fill_by_job(A.planJobBase, A.numFills, bj);
     const FillHeader* Hp = A.fills + f;
@@ -2117,7 +2124,7 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   const size_t oRanges = off;    off = al(off + std::max<size_t>(1, (size_t)numSegs) * 4);  // packed band range of each segment
   const size_t oGroups = off;    off = al(off + ((size_t)numSegs / 32 + 2) * 4);           // ... and of each group of 32
   const size_t oSlots = off;     off = al(off + (size_t)((L.scratchSlotCount + 31) / 32) * 4);
-  const size_t oCounters = off;  off = al(off + 256);           // [0] row ticket, [1] covered px, [2] entries, [3] max, [4..11] band tickets, [16..31] heavy-job counts (front / back of each launch's list)
+  const size_t oCounters = off;  off = al(off + 512);           // [32..39] plan_kernel's job tickets (one per plan launch); [0] row ticket, [1] covered px, [2] entries, [3] max, [4..11] band tickets, [16..31] heavy-job counts (front / back of each launch's list)
   // device-only scratch of the band scans (not part of what a host-counted list copies in)
   const size_t oBandRows = off;  off = al(off + std::max<size_t>(1, P) * 4);
   const size_t oChunks = off;    off = al(off + (2 * ((P + kScanChunk - 1) / kScanChunk) + 2) * 8);
@@ -2285,7 +2292,7 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   if (!hostCount) {
     if (P > 0) {
       L.numParts = numPartsTotal;
-      PX_CUDA(cudaMemsetAsync(L.counters, 0, 256, r.stream));
+      PX_CUDA(cudaMemsetAsync(L.counters, 0, 512, r.stream));
       band_rows_kernel<<<(int)((P + 255) / 256), 256, 0, r.stream>>>(L.fills, numFills, (int)P, L.bandRows);
       PX_LAUNCHED();
       if (int rc = device_count(L)) return rc;
@@ -2370,7 +2377,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
   }
   L.countFresh = false;
   r.prof_bands = 0;
-  PX_CUDA(cudaMemsetAsync(L.counters, 0, 256, r.stream));  // row tickets, covered px, heavy-job counts
+  PX_CUDA(cudaMemsetAsync(L.counters, 0, 512, r.stream));  // row tickets, covered px, heavy-job counts, plan tickets
   if (L.numParts > 0) {
     const int warps = (int)std::min<int64_t>(L.numParts, (int64_t)r.num_sms * 32);
     const int blocks = (warps + 7) / 8;
