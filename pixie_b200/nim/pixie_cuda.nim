@@ -292,6 +292,19 @@ proc addStroke*(batch: var PathBatchCuda, commands: seq[float32], transform: Mat
     batch.descs[^1].lineJoin = lineJoin.int32
     batch.descs[^1].miterLimit = miterLimit
 
+proc pixie_cuda_render_paths_host(pixels: ptr uint8, width, height, clear, numPaths: cint, paths: ptr PixiePathDesc,
+    commands: ptr float32, numCommandFloats: int64, rawXyxy: ptr float32, rawWinding: ptr int16, numRaw: int64,
+    coveredPx: ptr uint64): cint {.importc, dynlib: lib, cdecl.}
+
+proc renderPathsCuda*(image: Image, batch: var PathBatchCuda) {.raises: [PixieError].} =
+  ## the same in ONE call on host pixels: commands in, flattening / stroking / rasterising on the device, the band-wise
+  ## copy back overlapped with the rendering (pixie_cuda_render_paths_host)
+  check pixie_cuda_render_paths_host(cast[ptr uint8](image.data[0].addr), image.width.cint, image.height.cint, 0,
+    batch.descs.len.cint, (if batch.descs.len > 0: batch.descs[0].addr else: nil),
+    (if batch.commands.len > 0: batch.commands[0].addr else: nil), batch.commands.len.int64,
+    (if batch.rawXyxy.len > 0: batch.rawXyxy[0].addr else: nil),
+    (if batch.rawWinding.len > 0: batch.rawWinding[0].addr else: nil), batch.rawWinding.len.int64, nil)
+
 proc fillPathsCuda*(image: Image, batch: var PathBatchCuda) {.raises: [PixieError].} =
   ## the ordered fills / strokes of `batch` over `image` (newImage(svg), svg.nim:557-608)
   var

@@ -31,6 +31,7 @@ if [[ $PARTS == *lists* ]]; then
   $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $O/${T}_launches_tiger.csv python bench.py --steps 3 --warmup 3 --no-extras > $O/ncu_bench.log 2>&1
   $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $O/${T}_launches_icons.csv python tools/time_icons.py > $O/ncu_icons_l.log 2>&1
   $NCU --metrics gpu__time_duration.sum -c 100 --csv --log-file $O/${T}_launches_blur.csv python tools/prof_kernels.py blur > $O/ncu_blur_l.log 2>&1
+  $NCU --metrics gpu__time_duration.sum -c 200 --csv --log-file $O/${T}_launches_flatten.csv python tools/prof_kernels.py flatten > $O/ncu_flatten_l.log 2>&1
 fi
 if [[ $PARTS == *ncu* ]]; then
   cap tiger 'plan_|raster_kernel|partition_kernel|count_kernel|band_' 12 9 tiger
@@ -39,5 +40,7 @@ if [[ $PARTS == *ncu* ]]; then
   cap blend 'blend_rect' 0 15 blend
   cap icons 'plan_|raster_kernel|partition_kernel' 5 5 icons
   cap draw 'draw_smooth|gradient_kernel|minify' 0 6 draw
+  cap flatten 'resolve_kernel|count_kernel_f|shape_first|emit_kernel_f|stroke_count|stroke_emit|bounds_kernel|scan_' 22 22 flatten
+  cap paint 'gradient_blend_kernel' 1 3 paint
 fi
 du -sh $O

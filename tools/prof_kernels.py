@@ -57,6 +57,28 @@ if which in ("icons", "all"):
         img.fill(0)
         cl.run(img)
     dev.sync()
+if which in ("flatten", "all"):
+    from pixie_b200 import svg as psvg
+
+    doc = psvg.parseSvg(open(os.path.join(ROOT, "tests", "golden", "tiger.svg")).read(), 4096, 4096)
+    pb = psvg.svg_path_batch(doc)
+    packed = pb.packed()
+    for _ in range(3):
+        cl = dev.CmdList.from_paths(4096, 4096, 1, pb, packed)
+        del cl
+    dev.sync()
+if which in ("paint", "all"):
+    n = 8192
+    dst = dev.DeviceImage(n, n).upload(np.tile(synth.random_premultiplied(512, n, 1), (n // 512, 1, 1)))
+    mask = dev.DeviceImage(n, n)
+    ell = host.newPath()
+    ell.ellipse(n / 2, n / 2, n * 0.3, n * 0.22)
+    dev.fill_segments(mask, host.fill_segments(ell), 0xFFFFFFFF, 0, 0)
+    stops = [(0.0, (1, 0, 0, 1)), (0.3, (0, 1, 0, 0.5)), (1.0, (0, 0, 1, 1))]
+    for kind, handles in ((3, [(n * 0.2, n * 0.3), (n * 0.9, n * 0.7)]), (4, [(n / 2, n / 2), (n * 0.9, n / 2), (n / 2, n * 0.95)])):
+        for _ in range(2):
+            dev.fill_gradient_masked(dst, mask, kind, handles, stops, 1.0, 0)
+    dev.sync()
 if which in ("draw", "all"):
     n = 8192
     f = np.float32
