@@ -79,21 +79,39 @@ PXD bool is_quad_kind(int k) { return k == Quad || k == TQuad || k == RQuad || k
 // ---------------------------------------------------------------------------------------------
 // resolve: commands -> primitives (one thread per path)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) resolve_kernel(const DPath* __restrict__ paths, int numPaths, const float* __restrict__ cmds,
-                                                      Prim* __restrict__ prims, int* __restrict__ err) {
-  const int pi = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per path: the walk itself is sequential (lane 0), but a lone thread reading its commands from HBM pays a
+// full memory round trip per command (115 us for the tiger's 305 paths); here the warp stages the command stream in
+// shared memory 512 floats at a time and lane 0 reads from there.
+constexpr int kResolveChunk = 512;
+constexpr int kResolveWarps = 4;
+__global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(const DPath* __restrict__ paths, int numPaths, const float* __restrict__ cmdsG,
+                                                                     Prim* __restrict__ prims, int* __restrict__ err) {
+  __shared__ float sCmd[kResolveWarps][kResolveChunk + 8];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int pi = blockIdx.x * kResolveWarps + wi;
   if (pi >= numPaths) return;
   const DPath P = paths[pi];
+  float* cmds = sCmd[wi];
+  int chunkBase = P.cmdBegin;  // cmds[k] holds command float chunkBase + k
+  auto stage = [&](int from) {  // the warp loads floats [from, from + chunk + 8) of the stream (a command has <= 8 floats)
+    __syncwarp();
+    for (int k = lane; k < kResolveChunk + 8; k += 32) cmds[k] = from + k < P.cmdEnd ? cmdsG[from + k] : 0.0f;
+    chunkBase = from;
+    __syncwarp();
+  };
   int slot = P.primBase;
   const int slotEnd = P.primBase + P.primCap;
   if (P.kind == 2) {  // pre-flattened segments: one pass-through primitive
     Prim q;
     memset(&q, 0, sizeof(q));
     q.type = PrimRaw; q.path = pi; q.shapeBegin = slot; q.shapeEnd = slot + 1;
-    prims[slot++] = q;
-    for (; slot < slotEnd; slot++) { q.type = PrimNone; q.shapeBegin = slot; q.shapeEnd = slot + 1; prims[slot] = q; }
+    if (lane == 0) prims[slot] = q;
+    slot++;
+    for (; slot < slotEnd; slot++) { q.type = PrimNone; q.shapeBegin = slot; q.shapeEnd = slot + 1; if (lane == 0) prims[slot] = q; }
     return;
   }
+  // every lane walks the stream (same values, uniform control flow); lane 0 writes
+  stage(P.cmdBegin);
   const bool closeSubpaths = P.kind == 0;
   V2 start = v2(0.f, 0.f), at = v2(0.f, 0.f), prevCtrl = v2(0.f, 0.f), prevCtrl2 = v2(0.f, 0.f);
   int prevKind = Move;
@@ -102,18 +120,19 @@ __global__ void __launch_bounds__(128) resolve_kernel(const DPath* __restrict__ 
     Prim q;
     q.ax = a.x; q.ay = a.y; q.c1x = c1.x; q.c1y = c1.y; q.c2x = c2.x; q.c2y = c2.y; q.tx = to.x; q.ty = to.y;
     q.type = type; q.path = pi; q.shapeBegin = shapeBegin; q.shapeEnd = 0;
-    if (slot < slotEnd) prims[slot] = q;
+    if (lane == 0 && slot < slotEnd) prims[slot] = q;
     slot++;
   };
   auto end_shape = [&]() {
-    if (slot > shapeBegin && shapeBegin < slotEnd) prims[shapeBegin].shapeEnd = min(slot, slotEnd);
+    if (lane == 0 && slot > shapeBegin && shapeBegin < slotEnd) prims[shapeBegin].shapeEnd = min(slot, slotEnd);
     shapeBegin = slot;
   };
   int i = P.cmdBegin;
   while (i < P.cmdEnd) {
-    const int kind = (int)cmds[i];
+    if (i - chunkBase >= kResolveChunk) stage(i);  // warp-uniform: every lane tracks i
+    const int kind = (int)cmds[i - chunkBase];
     i++;
-    const float* c = cmds + i;
+    const float* c = cmds + (i - chunkBase);
     switch (kind) {
       case Move:
         // `if shape.len > 0: if closeSubpaths: addSegment(at, start)` — when the shape is still empty at == start and
@@ -178,7 +197,7 @@ __global__ void __launch_bounds__(128) resolve_kernel(const DPath* __restrict__ 
         end_shape();
         break;
       default:  // arcs are flattened on the host (kind 2); an unknown command is the reference's "Invalid path command"
-        atomicMax(err, kind == Arc || kind == RArc ? 2 : 3);
+        if (lane == 0) atomicMax(err, kind == Arc || kind == RArc ? 2 : 3);
         i = P.cmdEnd;
         break;
     }
@@ -187,10 +206,10 @@ __global__ void __launch_bounds__(128) resolve_kernel(const DPath* __restrict__ 
   }
   if (closeSubpaths) put(PrimLine, at, at, at, start);
   end_shape();
-  if (slot > slotEnd) atomicMax(err, 4);  // more primitives than the caller reserved slots for
+  if (lane == 0 && slot > slotEnd) atomicMax(err, 4);  // more primitives than the caller reserved slots for
   Prim q;
   memset(&q, 0, sizeof(q));
-  for (; slot < slotEnd; slot++) { q.type = PrimNone; q.path = pi; q.shapeBegin = slot; q.shapeEnd = slot + 1; prims[slot] = q; }
+  for (slot += lane; slot < slotEnd; slot += 32) { q.type = PrimNone; q.path = pi; q.shapeBegin = slot; q.shapeEnd = slot + 1; prims[slot] = q; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -589,18 +608,20 @@ __global__ void __launch_bounds__(128) stroke_emit_kernel(const EmitArgs A, int 
 }
 
 // per path: first segment, and computeBounds (:1098-1117) over its segments — one warp per path
-__global__ void __launch_bounds__(256) bounds_kernel(const EmitArgs A, int numPaths, int totalSegs, int* __restrict__ segBegin,
+__global__ void __launch_bounds__(128) bounds_kernel(const EmitArgs A, int numPaths, int totalSegs, int* __restrict__ segBegin,
                                                      float* __restrict__ bounds) {
-  const int pi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (pi > numPaths) return;
+  // one block per path (a path of the tiger has up to ten thousand segments: a single warp took 88 us over them)
+  __shared__ float red[4][4];
+  __shared__ int rnan[4];
+  const int pi = blockIdx.x, lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   if (pi == numPaths) {
-    if (lane == 0) segBegin[pi] = totalSegs;
+    if (threadIdx.x == 0) segBegin[pi] = totalSegs;
     return;
   }
   const int b = path_seg_begin(A, pi), e = pi + 1 < numPaths ? path_seg_begin(A, pi + 1) : totalSegs;
   float xMin = INFINITY, xMax = -INFINITY, yMin = INFINITY, yMax = -INFINITY;
   bool nan = false;
-  for (int i = b + lane; i < e; i += 32) {
+  for (int i = b + (int)threadIdx.x; i < e; i += 128) {
     const float4 s = A.segs[i];
     nan = nan || s.x != s.x || s.y != s.y || s.z != s.z || s.w != s.w;
     xMin = fminf(xMin, fminf(s.x, s.z));
@@ -617,6 +638,15 @@ __global__ void __launch_bounds__(256) bounds_kernel(const EmitArgs A, int numPa
   }
   nan = __any_sync(0xffffffffu, nan);
   if (lane == 0) {
+    red[wi][0] = xMin; red[wi][1] = xMax; red[wi][2] = yMin; red[wi][3] = yMax;
+    rnan[wi] = nan ? 1 : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 4; k++) {
+      xMin = fminf(xMin, red[k][0]); xMax = fmaxf(xMax, red[k][1]); yMin = fminf(yMin, red[k][2]); yMax = fmaxf(yMax, red[k][3]);
+      nan = nan || rnan[k] != 0;
+    }
     segBegin[pi] = b;
     bounds[5 * pi + 0] = xMin; bounds[5 * pi + 1] = xMax; bounds[5 * pi + 2] = yMin; bounds[5 * pi + 3] = yMax;
     bounds[5 * pi + 4] = nan ? 1.0f : 0.0f;
@@ -692,7 +722,36 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(int* __restrict__ data,
   if (blockIdx.x == 0 && tid == 0) data[n] = chunkSum[numChunks];
 }
 
+// arrays up to 64 K entries (the tiger's 3280 primitives, 60 000 polygon points): one block, one launch
+__global__ void __launch_bounds__(1024) scan_small_kernel(int* __restrict__ data, int n) {
+  __shared__ int sums[1024];
+  const int tid = threadIdx.x, per = (n + 1023) / 1024;
+  const int b = min(tid * per, n), e = min(b + per, n);
+  int s = 0;
+  for (int i = b; i < e; i++) s += data[i];
+  sums[tid] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int t = tid >= o ? sums[tid - o] : 0;
+    __syncthreads();
+    sums[tid] += t;
+    __syncthreads();
+  }
+  int run = sums[tid] - s;
+  for (int i = b; i < e; i++) {
+    const int c = data[i];
+    data[i] = run;
+    run += c;
+  }
+  if (tid == 1023) data[n] = sums[1023];
+}
+
 static int exclusive_scan(int* data, int n, cudaStream_t st) {
+  if (n <= 65536) {
+    scan_small_kernel<<<1, 1024, 0, st>>>(data, n);
+    PX_LAUNCHED();
+    return 0;
+  }
   const int numChunks = std::max(1, (n + kChunk - 1) / kChunk);
   int* chunkScratch = nullptr;
   PX_CUDA(cudaMallocAsync((void**)&chunkScratch, ((size_t)numChunks + 1) * 4, st));
@@ -820,7 +879,7 @@ int flatten_paths(int numPaths, const pixie_path_desc* descs, const float* comma
   int* err = (int*)(blk + oErr);
   PX_CUDA(cudaMemsetAsync(blk + oFirst, 0, totalA - oFirst, r.stream));  // first flags, error word, outputs
 
-  resolve_kernel<<<(numPaths + 127) / 128, 128, 0, r.stream>>>(dPaths, numPaths, (const float*)(blk + oCmds), dPrims, err);
+  resolve_kernel<<<(numPaths + kResolveWarps - 1) / kResolveWarps, kResolveWarps * 32, 0, r.stream>>>(dPaths, numPaths, (const float*)(blk + oCmds), dPrims, err);
   PX_LAUNCHED();
   count_kernel_f<<<(numPrims + 127) / 128, 128, 0, r.stream>>>(dPaths, dPrims, numPrims, (const int*)(blk + oRawC), cntPts, cntSeg, err);
   PX_LAUNCHED();
@@ -882,7 +941,7 @@ int flatten_paths(int numPaths, const pixie_path_desc* descs, const float* comma
   }
   int* dSegBegin = (int*)(blk + oSegBegin);
   float* dBounds = (float*)(blk + oBounds);
-  bounds_kernel<<<((numPaths + 1) * 32 + 255) / 256, 256, 0, r.stream>>>(A, numPaths, totalSegs, dSegBegin, dBounds);
+  bounds_kernel<<<numPaths + 1, 128, 0, r.stream>>>(A, numPaths, totalSegs, dSegBegin, dBounds);
   PX_LAUNCHED();
   PX_CUDA(cudaMemcpyAsync(F.segBegin.data(), dSegBegin, ((size_t)numPaths + 1) * 4, cudaMemcpyDeviceToHost, r.stream));
   PX_CUDA(cudaMemcpyAsync(F.bounds.data(), dBounds, (size_t)numPaths * 5 * 4, cudaMemcpyDeviceToHost, r.stream));
