@@ -608,8 +608,9 @@ __global__ void __launch_bounds__(128) stroke_emit_kernel(const EmitArgs A, int 
 }
 
 // per path: first segment, and computeBounds (:1098-1117) over its segments — one warp per path
-__global__ void __launch_bounds__(128) bounds_kernel(const EmitArgs A, int numPaths, int totalSegs, int* __restrict__ segBegin,
-                                                     float* __restrict__ bounds) {
+__global__ void __launch_bounds__(128) bounds_kernel(const EmitArgs A, int numPaths, int fillSegs, const int* __restrict__ strokeSegs,
+                                                     int* __restrict__ segBegin, float* __restrict__ bounds) {
+  const int totalSegs = fillSegs + (strokeSegs ? *strokeSegs : 0);  // the stroke total is still on the device
   // one block per path (a path of the tiger has up to ten thousand segments: a single warp took 88 us over them)
   __shared__ float red[4][4];
   __shared__ int rnan[4];
@@ -931,21 +932,19 @@ int flatten_paths(int numPaths, const pixie_path_desc* descs, const float* comma
     raw_copy_kernel<<<numPaths, 256, 0, r.stream>>>(A, numPaths);
     PX_LAUNCHED();
   }
-  int strokeSegs = 0;
   if (numPoints > 0) {
     stroke_emit_kernel<<<(numPoints + 127) / 128, 128, 0, r.stream>>>(A, numPoints);
     PX_LAUNCHED();
-    PX_CUDA(cudaMemcpyAsync(&strokeSegs, cnt2 + numPoints, 4, cudaMemcpyDeviceToHost, r.stream));
-    PX_CUDA(cudaStreamSynchronize(r.stream));
-    totalSegs += strokeSegs;
   }
   int* dSegBegin = (int*)(blk + oSegBegin);
   float* dBounds = (float*)(blk + oBounds);
-  bounds_kernel<<<numPaths + 1, 128, 0, r.stream>>>(A, numPaths, totalSegs, dSegBegin, dBounds);
+  bounds_kernel<<<numPaths + 1, 128, 0, r.stream>>>(A, numPaths, fillSegs, numPoints > 0 ? cnt2 + numPoints : nullptr, dSegBegin, dBounds);
   PX_LAUNCHED();
+  // one readback for the path table: first segment of every path (the last entry = the total) and the bounds
   PX_CUDA(cudaMemcpyAsync(F.segBegin.data(), dSegBegin, ((size_t)numPaths + 1) * 4, cudaMemcpyDeviceToHost, r.stream));
   PX_CUDA(cudaMemcpyAsync(F.bounds.data(), dBounds, (size_t)numPaths * 5 * 4, cudaMemcpyDeviceToHost, r.stream));
   PX_CUDA(cudaStreamSynchronize(r.stream));
+  totalSegs = F.segBegin[(size_t)numPaths];
   F.numSegs = totalSegs;
   F.numPoints = numPoints;
   F.numPrims = numPrims;
