@@ -1088,6 +1088,7 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
 // ---------------------------------------------------------------------------------------------
 // K3: raster_kernel — apply the plans to the canvas, row by row, fills in order
 // ---------------------------------------------------------------------------------------------
+constexpr int kPartCap = 128;
 struct WarpCtx {
   int mode;         // run-time blend mode (used by the GenericMode instantiation)
   px_t* row;        // canvas row of this warp
@@ -1096,6 +1097,7 @@ struct WarpCtx {
   int y;
   int lane;
   uint8_t* cov;     // coverage row in shared memory (index 0 = pixel covBase)
+  uint16_t* plist;  // kPartCap word indices: the partially covered words of the job being blended
   bool vec_ok;      // rows are 16-byte aligned
   unsigned covered; // per-lane count of pixels touched with non-zero coverage
 };
@@ -1332,34 +1334,58 @@ __device__ __noinline__ void coverage_row(WarpCtx& c, const uint2* __restrict__ 
       return v;
     };
     if (MODE == NormalBlend || MODE == OverwriteBlend) {
-      // two words per lane and step: both canvas loads are in flight before the first blend (a fill's row
-      // segment costs half as many dependent L2 round trips)
+      // Words whose four pixels are all fully covered are handled word-wise by every lane (a plain 16-byte store
+      // for opaque colours).  The others — the anti-aliased span ends, a handful per job — used to run the
+      // four-pixel blend on two or three lanes of the warp; they are listed in shared memory instead and then
+      // blended one PIXEL per lane, so the edge arithmetic fills the warp.
       const bool solid = MODE == OverwriteBlend || pA(rgbx) == 255u;
       const uint4 colour4 = make_uint4(rgbx, rgbx, rgbx, rgbx);
+      uint16_t* plist = c.plist;
+      int nPart = 0;  // warp-uniform
+      auto flush = [&]() {
+        __syncwarp();
 #pragma unroll 1
-      for (int j = word0 + lane; j < words; j += 64) {
-        const int jb = j + 32;
-        const uint32_t cva = cw[j], cvb = jb < words ? cw[jb] : 0u;
-        const int xa_ = covBase + 4 * j, xb_ = covBase + 4 * jb;
-        const bool fulla = (xa_ >= x0) && (xa_ + 4 <= x1), fullb = (xb_ >= x0) && (xb_ + 4 <= x1);
-        const bool storea = solid && cva == 0xFFFFFFFFu && fulla, storeb = solid && cvb == 0xFFFFFFFFu && fullb;
-        const bool rmwa = cva != 0u && !storea, rmwb = cvb != 0u && !storeb;
-        uint4 va = colour4, vb = colour4;
-        if (rmwa) va = *reinterpret_cast<const uint4*>(row + xa_);
-        if (rmwb) vb = *reinterpret_cast<const uint4*>(row + xb_);
-        if (cva != 0u) {
-          cw[j] = 0u;
-          if (storea) cnt += 4;  // sse2.nim:552-555, 648-651
-          else va = blend_word(cva, xa_, va);
-          *reinterpret_cast<uint4*>(row + xa_) = va;
+        for (int t = lane; t < 4 * nPart; t += 32) {
+          const int j = plist[t >> 2], x = covBase + 4 * j + (t & 3);
+          const uint32_t cvk = cov[4 * j + (t & 3)];
+          if (cvk != 0u && x >= x0 && x < x1) {
+            cnt++;
+            const px_t s_ = mul_cov_floor(rgbx, cvk);
+            row[x] = MODE == OverwriteBlend ? s_ : line_normal(row[x], s_);
+          }
         }
-        if (cvb != 0u) {
-          cw[jb] = 0u;
-          if (storeb) cnt += 4;
-          else vb = blend_word(cvb, xb_, vb);
-          *reinterpret_cast<uint4*>(row + xb_) = vb;
+        __syncwarp();
+#pragma unroll 1
+        for (int t = lane; t < nPart; t += 32) cw[plist[t]] = 0u;
+        nPart = 0;
+        __syncwarp();
+      };
+#pragma unroll 1
+      for (int j0 = word0; j0 < words; j0 += 32) {
+        const int j = j0 + lane;
+        const uint32_t cv = j < words ? cw[j] : 0u;
+        const int xw = covBase + 4 * j;
+        const bool full = cv == 0xFFFFFFFFu && (xw >= x0) && (xw + 4 <= x1);
+        if (full) {
+          cw[j] = 0u;
+          cnt += 4;
+          uint4 v = colour4;
+          if (!solid) {  // translucent colour over four fully covered pixels
+            v = *reinterpret_cast<const uint4*>(row + xw);
+            v.x = line_normal(v.x, rgbx); v.y = line_normal(v.y, rgbx);
+            v.z = line_normal(v.z, rgbx); v.w = line_normal(v.w, rgbx);
+          }
+          *reinterpret_cast<uint4*>(row + xw) = v;  // sse2.nim:552-555, 648-651
+        }
+        const bool part = cv != 0u && !full;
+        const unsigned pm = __ballot_sync(0xffffffffu, part);
+        if (pm) {
+          if (part) plist[nPart + __popc(pm & ((1u << lane) - 1u))] = (uint16_t)j;
+          nPart += __popc(pm);
+          if (nPart > kPartCap - 32) flush();
         }
       }
+      if (nPart) flush();
     } else {
 #pragma unroll 1
       for (int j = word0 + lane; j < words; j += 32) {
@@ -1609,6 +1635,7 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
     c.y = y;
     c.lane = lane;
     c.cov = cov;
+    c.plist = reinterpret_cast<uint16_t*>(cov + A.covBytes - 2 * kPartCap);
     c.vec_ok = vecGlobal;
     c.covered = 0;
     const int f0 = A.layerFillBegin[layer], f1 = A.layerFillBegin[layer + 1];
@@ -2093,7 +2120,7 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   // which shortens the ordered chain a warp walks, and a row's work runs on several warps at once
   L.tileW = w > 3072 ? 2048 : ((w + 3) & ~3);
   L.tiles = (w + L.tileW - 1) / L.tileW;
-  L.covBytes = ((L.tileW + 7) & ~3) + 4;       // coverage row of a tile, word aligned, with the covBase slack
+  L.covBytes = ((L.tileW + 7) & ~3) + 4 + 2 * kPartCap;  // coverage row of a tile, word aligned, with the covBase slack, + the partial-word list
   L.smemCap = 64;                              // entries per band planned from shared memory
   L.warpsPerBlock = 8;
   while (L.warpsPerBlock > 1 && (size_t)L.covBytes * L.warpsPerBlock > 96 * 1024) L.warpsPerBlock /= 2;
