@@ -102,6 +102,7 @@ static uint64_t g_next_list = 1;
 // device helpers
 // ---------------------------------------------------------------------------------------------
 PXD long long f2ll(float f) { return (long long)f; }          // Nim float32 -> int
+PXD int f2i_sat(float f) { return __float2int_rz(f); }         // the same, saturated to int32 (NaN -> 0 in both)
 PXD int fixed32(float f) { return __float2int_rz(f * 256.0f); }  // paths.nim:1268-1269
 PXD int fx_integer(int p) { return p / 256; }                  // :1271-1272 (truncating div)
 PXD int fx_trunc(int p) { return (p / 256) * 256; }            // :1274-1275
@@ -1179,9 +1180,9 @@ __device__ __noinline__ void fill_span(WarpCtx& c, int x0, int x1, px_t rgbx) {
 // cover pixels [trunc(min x), ceil(max x)), right edges (:1811-1847) likewise; xa / xb are the edge's x at
 // the top and the bottom of the scanline, `first` the first pixel of the edge (where the pen starts).
 template <int MODE>
-__device__ __noinline__ void edge_px(px_t* row, int mode, int y, long long xl, bool left, float em, float eb, float xa,
-                                     float xb, long long first, px_t rgbx) {
-  const int x = (int)xl;
+__device__ __noinline__ void edge_px(px_t* row, int mode, int y, int xl, bool left, float em, float eb, float xa,
+                                     float xb, int first, px_t rgbx) {
+  const int x = xl;
   float area;
   if (left) {
     const bool inverted = xa < xb;
@@ -1451,49 +1452,53 @@ __device__ __noinline__ void apply_row(WarpCtx& c, px_t rgbx, int startX, int pa
       // The partial-coverage pixels of the sorted edges and the interiors between them are pairwise
       // disjoint (that is what the two checks of the plan establish), so they can be written in any
       // order: every edge gets a lane, long edges and long interiors are handed to the whole warp.
+      // Pixel positions are kept as saturated int32 (f2i_sat): every use is clamped to the tile or compared with a
+      // pixel inside it, which gives what the reference's 64-bit values give.  Rows with up to four edges (most of
+      // them: one or two shapes' worth) spread each edge over eight lanes, one pixel per lane.
       unsigned cnt = 0;
+      const int sh = n <= 4 ? 3 : 0, per = 32 >> sh, sub = lane & ((1 << sh) - 1), slot = lane >> sh;
 #pragma unroll 1
-      for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
+      for (int base = 0; base < n; base += per) {
+        const int i = base + slot;
         float em = 0.0f, eb = 0.0f, xa = 0.0f, xb = 0.0f;
-        long long xFirst = 0, pxB = 0, pxE = 0, xEnd = 0;
+        int xFirst = 0, pxB = 0, pxE = 0, xEnd = 0;
         if (i < n) {
           const uint2 mb = pay[2 * i], ab = pay[2 * i + 1];
           em = __uint_as_float(mb.x); eb = __uint_as_float(mb.y);
           xa = __uint_as_float(ab.x); xb = __uint_as_float(ab.y);
-          xFirst = f2ll(fminf(xa, xb));
-          xEnd = f2ll(ceilf(fmaxf(xa, xb)));
-          pxB = xFirst > c.tx0 ? xFirst : c.tx0;  // inside the image and inside this warp's tile
-          pxE = xEnd < c.tx1 ? xEnd : c.tx1;
+          xFirst = f2i_sat(fminf(xa, xb));
+          xEnd = f2i_sat(ceilf(fmaxf(xa, xb)));
+          pxB = min(max(xFirst, c.tx0), c.tx1);  // inside the image and inside this warp's tile
+          pxE = min(max(xEnd, c.tx0), c.tx1);
         }
-        const bool isLeft = (lane & 1) == 0;  // base is a multiple of 32: even sorted positions are left edges
-        // interior of the pair: [ceil(left max x), trunc(right min x)) (:1849-1854); the right edge is the next lane
-        const long long rightMin = __shfl_down_sync(0xffffffffu, xFirst, 1);
+        const bool isLeft = (slot & 1) == 0;  // base is a multiple of `per`: even sorted positions are left edges
+        // interior of the pair: [ceil(left max x), trunc(right min x)) (:1849-1854); the right edge is the next slot
+        const int rightMin = __shfl_down_sync(0xffffffffu, xFirst, 1 << sh);
         int fillBegin = 0, fillEnd = 0;
-        if (i < n && isLeft) {
-          fillBegin = clampi(xEnd, c.tx0, c.tx1);
-          fillEnd = clampi(rightMin, c.tx0, c.tx1);
+        if (i < n && isLeft && sub == 0) {
+          fillBegin = pxE;
+          fillEnd = min(max(rightMin, c.tx0), c.tx1);
         }
         const bool longEdge = pxE - pxB > 6;
         if (!longEdge) {
 #pragma unroll 1
-          for (long long xl = pxB; xl < pxE; xl++) {
+          for (int xl = pxB + sub; xl < pxE; xl += 1 << sh) {
             edge_px<MODE>(row, mode, y, xl, isLeft, em, eb, xa, xb, xFirst, rgbx);
             cnt++;
           }
         }
-        unsigned todoE = __ballot_sync(0xffffffffu, longEdge);
+        unsigned todoE = __ballot_sync(0xffffffffu, longEdge && sub == 0);
 #pragma unroll 1
         while (todoE) {
           const int src = __ffs(todoE) - 1;
           todoE &= todoE - 1;
           const float sm_ = __shfl_sync(0xffffffffu, em, src), sb_ = __shfl_sync(0xffffffffu, eb, src);
           const float sa_ = __shfl_sync(0xffffffffu, xa, src), sx_ = __shfl_sync(0xffffffffu, xb, src);
-          const long long sf_ = __shfl_sync(0xffffffffu, xFirst, src);
-          const long long b_ = __shfl_sync(0xffffffffu, pxB, src), e_ = __shfl_sync(0xffffffffu, pxE, src);
+          const int sf_ = __shfl_sync(0xffffffffu, xFirst, src);
+          const int b_ = __shfl_sync(0xffffffffu, pxB, src), e_ = __shfl_sync(0xffffffffu, pxE, src);
 #pragma unroll 1
-          for (long long xl = b_ + lane; xl < e_; xl += 32) {
-            edge_px<MODE>(row, mode, y, xl, (src & 1) == 0, sm_, sb_, sa_, sx_, sf_, rgbx);
+          for (int xl = b_ + lane; xl < e_; xl += 32) {
+            edge_px<MODE>(row, mode, y, xl, ((src >> sh) & 1) == 0, sm_, sb_, sa_, sx_, sf_, rgbx);
             cnt++;
           }
         }
@@ -1527,10 +1532,10 @@ __device__ __noinline__ void apply_row(WarpCtx& c, px_t rgbx, int startX, int pa
           const float em = __uint_as_float(mb.x), eb = __uint_as_float(mb.y);
           const float xa = __uint_as_float(ab.x), xb = __uint_as_float(ab.y);
           if (side == 0) { lax = xa; lbx = xb; } else { rax = xa; rbx = xb; }
-          const long long xFirst = f2ll(fminf(xa, xb)), xEnd = f2ll(ceilf(fmaxf(xa, xb)));
-          const long long b_ = xFirst > c.tx0 ? xFirst : c.tx0, e_ = xEnd < c.tx1 ? xEnd : c.tx1;
+          const int xFirst = f2i_sat(fminf(xa, xb)), xEnd = f2i_sat(ceilf(fmaxf(xa, xb)));
+          const int b_ = min(max(xFirst, c.tx0), c.tx1), e_ = min(max(xEnd, c.tx0), c.tx1);
 #pragma unroll 1
-          for (long long xl = b_ + lane; xl < e_; xl += 32) {
+          for (int xl = b_ + lane; xl < e_; xl += 32) {
             edge_px<MODE>(row, mode, y, xl, side == 0, em, eb, xa, xb, xFirst, rgbx);
             cnt++;
           }
