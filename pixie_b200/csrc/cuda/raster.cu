@@ -1278,27 +1278,26 @@ __device__ __noinline__ void coverage_row(WarpCtx& c, const uint2* __restrict__ 
         smem_add(&cw[w], add4 & mask);
       }
     }
+    // long interiors: the owner adds its first and last (masked) word, the warp the whole words in between
+    int wA = 0, wB = 0;
+    if (isLong) {
+      wA = (i0 >> 2) + 1;
+      wB = (i1 - 1) >> 2;
+      smem_add(&cw[wA - 1], add4 & (0xFFFFFFFFu << (8 * (i0 & 3))));
+      smem_add(&cw[wB], add4 & (0xFFFFFFFFu >> (8 * (3 - ((i1 - 1) & 3)))));
+    }
     unsigned longs = __ballot_sync(0xffffffffu, isLong);
 #pragma unroll 1
     while (longs) {
       const int src = __ffs(longs) - 1;
       longs &= longs - 1;
-      const int j0 = __shfl_sync(0xffffffffu, i0, src), j1 = __shfl_sync(0xffffffffu, i1, src);
-      const int wl = (j1 - 1) >> 2;
+      const int a_ = __shfl_sync(0xffffffffu, wA, src), b_ = __shfl_sync(0xffffffffu, wB, src);
 #pragma unroll 1
-      for (int w = (j0 >> 2) + lane; w <= wl; w += 32) {
-        uint32_t mask = 0xFFFFFFFFu;
-        if (w == (j0 >> 2)) mask &= 0xFFFFFFFFu << (8 * (j0 & 3));
-        if (w == wl) mask &= 0xFFFFFFFFu >> (8 * (3 - ((j1 - 1) & 3)));
-        smem_add(&cw[w], add4 & mask);
-      }
+      for (int w = a_ + lane; w < b_; w += 32) smem_add(&cw[w], add4);
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    pxLo = min(pxLo, __shfl_xor_sync(0xffffffffu, pxLo, o));
-    pxHi = max(pxHi, __shfl_xor_sync(0xffffffffu, pxHi, o));
-  }
+  pxLo = __reduce_min_sync(0xffffffffu, pxLo);  // redux.sync
+  pxHi = __reduce_max_sync(0xffffffffu, pxHi);
   __syncwarp();
   if (MODE != MaskBlend && S == 0) return;
 
