@@ -200,10 +200,8 @@ constexpr BlendTables make_blend_tables() {
 }
 __device__ const BlendTables g_blend_tables = make_blend_tables();
 
-PXD uint32_t round_half_away_u(float v) {  // roundf() of a non-negative value below 2^23, as an integer: exact
-  uint32_t r = __float2uint_rz(v);
-  if (v - (float)r >= 0.5f) r++;
-  return r;
+PXD uint32_t round_half_away_u(float v) {  // roundf() of 0 <= v < 2^22 as an integer: floor(v + 0.5), see round_bits
+  return __float_as_uint(__fadd_rz(__fadd_rz(v, 0.5f), 8388608.0f)) - 0x4B000000u;
 }
 PXD uint32_t straight_(uint32_t c, uint32_t a) {  // internal.nim:68-74 stand-in for chroma rgba()
   if (a == 0u) return 0u;
@@ -234,17 +232,52 @@ PXD px_t alpha_fix(px_t backdrop, px_t source, px_t mixed) {  // blends.nim:18-3
 struct Col {
   float r, g, b, a;
 };
+// ---- the float blend modes' arithmetic, instruction by instruction what the reference computes, in fewer instructions:
+// * roundf(v) of 0 <= v < 2^22: floor(v + 0.5) with BOTH additions rounded toward zero — RZ(t) >= n exactly when
+//   t >= n for an integer n, so the truncated sum has the exact sum's floor; the second addition (2^23) leaves that
+//   floor in the low mantissa bits (no float -> int conversion, no compare);
+// * u / 255.0f for an integer 0 <= u <= 255: q = u * RN(1/255) corrected once with the exact FMA residual
+//   (Markstein); equal to the IEEE quotient for all 256 inputs (tests/test_chain_closed_form.py);
+// * x / d for three numerators that share d: one correctly rounded reciprocal, then per quotient the classical
+//   two-step FMA refinement, which returns the correctly rounded quotient whenever nothing leaves the normal range —
+//   denominators outside [1e-18, 1e18] (incl. 0, negatives, NaN) take the IEEE division itself.
+PXD float round_bits(float v) { return __fadd_rz(__fadd_rz(v, 0.5f), 8388608.0f); }  // 2^23 + roundf(v) for 0 <= v < 2^22
+PXD float div255f(float u) {
+  const float r = 1.0f / 255.0f;
+  const float q = u * r;
+  return __fmaf_rn(__fmaf_rn(-q, 255.0f, u), r, q);
+}
+PXD float fdiv_r(float x, float d, float r) {  // RN(x / d) given r = RN(1 / d)
+  float q = x * r;
+  q = __fmaf_rn(__fmaf_rn(-q, d, x), r, q);
+  return __fmaf_rn(__fmaf_rn(-q, d, x), r, q);
+}
+PXD void div3(float& x, float& y, float& z, float d) {  // x / d, y / d, z / d
+  if (d > 1e-18f && d < 1e18f) {
+    const float r = __frcp_rn(d);
+    x = fdiv_r(x, d, r);
+    y = fdiv_r(y, d, r);
+    z = fdiv_r(z, d, r);
+  } else {
+    x = x / d;
+    y = y / d;
+    z = z / d;
+  }
+}
+// to_color: chroma rgba() (straightAlphaTable stand-in, straight_ above) then .color (x / 255)
 PXD Col to_color(px_t p) {
-  px_t s = to_straight(p);
-  Col c = {__ldg(&g_blend_tables.div255[pR(s)]), __ldg(&g_blend_tables.div255[pG(s)]), __ldg(&g_blend_tables.div255[pB(s)]),
-           __ldg(&g_blend_tables.div255[pA(s)])};
+  const uint32_t a = pA(p);
+  const float multiplier = __ldg(&g_blend_tables.mul255[a]);  // 0 for a == 0: every channel becomes 0 as in straight_
+  Col c;
+  c.r = div255f(fminf(round_bits((float)pR(p) * multiplier) - 8388608.0f, 255.0f));
+  c.g = div255f(fminf(round_bits((float)pG(p) * multiplier) - 8388608.0f, 255.0f));
+  c.b = div255f(fminf(round_bits((float)pB(p) * multiplier) - 8388608.0f, 255.0f));
+  c.a = div255f((float)a);
   return c;
 }
 PXD uint32_t f2u8(float v) {  // roundf(v * 255) clamped to 0..255 (NaN and negatives -> 0)
-  const float x = v * 255.0f;
-  if (!(x >= 0.5f)) return 0u;
-  if (x >= 255.0f) return 255u;
-  return round_half_away_u(x);
+  const float x = fminf(fmaxf(v * 255.0f, 0.0f), 255.0f);  // fmaxf(NaN, 0) = 0
+  return __float_as_uint(round_bits(x)) & 0x1FFu;
 }
 PXD px_t from_color(Col c) { return to_premul(mk(f2u8(c.r), f2u8(c.g), f2u8(c.b), f2u8(c.a))); }
 PXD float min3f(float a, float b, float c) { return fminf(a, fminf(b, c)); }
@@ -253,14 +286,18 @@ PXD float lum(Col c) { return 0.3f * c.r + 0.59f * c.g + 0.11f * c.b; }
 PXD Col clip_color(Col c) {
   float L = lum(c), n = min3f(c.r, c.g, c.b), x = max3f(c.r, c.g, c.b);
   if (n < 0) {
-    c.r = L + (((c.r - L) * L) / (L - n));
-    c.g = L + (((c.g - L) * L) / (L - n));
-    c.b = L + (((c.b - L) * L) / (L - n));
+    float r_ = (c.r - L) * L, g_ = (c.g - L) * L, b_ = (c.b - L) * L;
+    div3(r_, g_, b_, L - n);
+    c.r = L + r_;
+    c.g = L + g_;
+    c.b = L + b_;
   }
   if (x > 1) {
-    c.r = L + (((c.r - L) * (1 - L)) / (x - L));
-    c.g = L + (((c.g - L) * (1 - L)) / (x - L));
-    c.b = L + (((c.b - L) * (1 - L)) / (x - L));
+    float r_ = (c.r - L) * (1 - L), g_ = (c.g - L) * (1 - L), b_ = (c.b - L) * (1 - L);
+    div3(r_, g_, b_, x - L);
+    c.r = L + r_;
+    c.g = L + g_;
+    c.b = L + b_;
   }
   return c;
 }
@@ -277,9 +314,10 @@ PXD Col set_sat(Col c, float s) {
   Col r = {0.f, 0.f, 0.f, c.a};
   if (satC > 0) {
     float mn = min3f(c.r, c.g, c.b);
-    r.r = (c.r - mn) * s / satC;
-    r.g = (c.g - mn) * s / satC;
-    r.b = (c.b - mn) * s / satC;
+    r.r = (c.r - mn) * s;
+    r.g = (c.g - mn) * s;
+    r.b = (c.b - mn) * s;
+    div3(r.r, r.g, r.b, satC);
   }
   return r;
 }
@@ -291,9 +329,10 @@ PXD Col alpha_fix_f(Col cb, Col cs, Col mixed) {
     return r;
   }
   float t0 = cs.a * (1 - cb.a), t1 = cs.a * cb.a, t2 = (1 - cs.a) * cb.a;
-  r.r = (t0 * cs.r + t1 * mixed.r + t2 * cb.r) / r.a;
-  r.g = (t0 * cs.g + t1 * mixed.g + t2 * cb.g) / r.a;
-  r.b = (t0 * cs.b + t1 * mixed.b + t2 * cb.b) / r.a;
+  r.r = t0 * cs.r + t1 * mixed.r + t2 * cb.r;
+  r.g = t0 * cs.g + t1 * mixed.g + t2 * cb.g;
+  r.b = t0 * cs.b + t1 * mixed.b + t2 * cb.b;
+  div3(r.r, r.g, r.b, r.a);
   return r;
 }
 
