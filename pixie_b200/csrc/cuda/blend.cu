@@ -56,8 +56,14 @@ PXD uint4 ld16_stream(const void* p) {
 #ifndef PIXIE_BLEND_MINB
 #define PIXIE_BLEND_MINB 4
 #endif
+#ifndef PIXIE_BLEND_MINB_FLOAT
+#define PIXIE_BLEND_MINB_FLOAT 4
+#endif
+#ifndef PIXIE_BLEND_MINB_PACKED
+#define PIXIE_BLEND_MINB_PACKED 3   // the two-pixel packed path wants registers (swept: 2 -> 0.472 ms, 3 -> 0.437 ms for SoftLight at 8192^2)
+#endif
 template <int MODE, int MASK>
-__global__ void __launch_bounds__(256, mode_uses_tables(MODE) ? 3 : PIXIE_BLEND_MINB) blend_rect_vec4(const RectArgs a) {
+__global__ void __launch_bounds__(256, mode_uses_tables(MODE) ? 3 : (mode_is_packed(MODE) ? PIXIE_BLEND_MINB_PACKED : (mode_is_float(MODE) ? PIXIE_BLEND_MINB_FLOAT : PIXIE_BLEND_MINB))) blend_rect_vec4(const RectArgs a) {
   BlendTab T = {nullptr, nullptr, nullptr};
   if (mode_uses_tables(MODE)) {  // the ALU-bound modes: tables into shared memory (66 KB, three CTAs per SM, one wave)
     extern __shared__ __align__(16) uint8_t tab_smem[];
@@ -104,14 +110,27 @@ __global__ void __launch_bounds__(256, mode_uses_tables(MODE) ? 3 : PIXIE_BLEND_
       for (int r = 0; r < ROWS; r++) {
         uint32_t* dp = reinterpret_cast<uint32_t*>(&dv[r]);
         const uint32_t* sp = reinterpret_cast<const uint32_t*>(&sv[r]);
+        if (mode_is_packed(MODE)) {  // two pixels per step on the packed fp32 instructions
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          px_t sx = sp[k];
-          if (MASK != 0) {
-            const uint32_t m = (mw[r] >> (8 * k)) & 255u;
-            if (m != 255u) sx = mul_div255(sx, m);
+          for (int k = 0; k < 4; k += 2) {
+            px_t s0 = sp[k], s1 = sp[k + 1];
+            if (MASK != 0) {
+              const uint32_t m0 = (mw[r] >> (8 * k)) & 255u, m1 = (mw[r] >> (8 * k + 8)) & 255u;
+              if (m0 != 255u) s0 = mul_div255(s0, m0);
+              if (m1 != 255u) s1 = mul_div255(s1, m1);
+            }
+            blend_px2_float<MODE>(dp[k], dp[k + 1], s0, s1, dp[k], dp[k + 1]);
           }
-          dp[k] = rect_op<MODE>(MODE == OverwriteBlend ? 0u : dp[k], sx, T);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            px_t sx = sp[k];
+            if (MASK != 0) {
+              const uint32_t m = (mw[r] >> (8 * k)) & 255u;
+              if (m != 255u) sx = mul_div255(sx, m);
+            }
+            dp[k] = rect_op<MODE>(MODE == OverwriteBlend ? 0u : dp[k], sx, T);
+          }
         }
         *reinterpret_cast<uint4*>(a.dst + (size_t)a.dw * (yb + r) + x) = dv[r];
       }

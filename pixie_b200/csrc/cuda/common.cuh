@@ -237,7 +237,7 @@ struct Col {
 //   t >= n for an integer n, so the truncated sum has the exact sum's floor; the second addition (2^23) leaves that
 //   floor in the low mantissa bits (no float -> int conversion, no compare);
 // * u / 255.0f for an integer 0 <= u <= 255: q = u * RN(1/255) corrected once with the exact FMA residual
-//   (Markstein); equal to the IEEE quotient for all 256 inputs (tests/test_chain_closed_form.py);
+//   (Markstein); equal to the IEEE quotient for all 256 inputs (tests/test_float_blend_identities.py);
 // * x / d for three numerators that share d: one correctly rounded reciprocal, then per quotient the classical
 //   two-step FMA refinement, which returns the correctly rounded quotient whenever nothing leaves the normal range —
 //   denominators outside [1e-18, 1e18] (incl. 0, negatives, NaN) take the IEEE division itself.
@@ -335,6 +335,198 @@ PXD Col alpha_fix_f(Col cb, Col cs, Col mixed) {
   div3(r.r, r.g, r.b, r.a);
   return r;
 }
+
+// ---- the same five modes for TWO pixels at a time on Blackwell's packed fp32 instructions (add / mul / fma .f32x2 =
+// FADD2 / FMUL2 / FFMA2: one issue slot for both pixels).  Every packed operation is the IEEE operation of its two
+// halves, so the pair function returns exactly what two calls of the scalar path return; the kernels of blend.cu use
+// it for the 16-byte groups of their fast path.
+struct F2 {
+  unsigned long long v;
+};
+PXD F2 f2(float x, float y) {  // the two halves of a 64-bit register are ordinary registers: no instruction
+  F2 r;
+  r.v = ((unsigned long long)__float_as_uint(y) << 32) | (unsigned long long)__float_as_uint(x);
+  return r;
+}
+PXD float f2lo(F2 a) { return __uint_as_float((uint32_t)a.v); }
+PXD float f2hi(F2 a) { return __uint_as_float((uint32_t)(a.v >> 32)); }
+PXD F2 splat2(float x) { return f2(x, x); }
+PXD F2 add2(F2 a, F2 b) {
+  F2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+PXD F2 add2rz(F2 a, F2 b) {
+  F2 r;
+  asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+PXD F2 mul2(F2 a, F2 b) {
+  F2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+PXD F2 fma2(F2 a, F2 b, F2 c) {
+  F2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+PXD F2 sub2(F2 a, F2 b) { return fma2(b, splat2(-1.0f), a); }  // RN(a - b): b * -1 is exact
+// A sum whose operand is a packed PRODUCT goes through two scalar additions: ptxas (CUDA 12.9) contracts
+// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under --fmad=false and despite the explicit .rn (it also folds
+// fma(a, b, -0) and fma(p, 1, c) first), which changes the last bit about once in 10^5 pixels; scalar FADDs are
+// left alone and cost no moves (the halves of a 64-bit register are ordinary registers).
+PXD F2 add2s(F2 a, F2 b) { return f2(__fadd_rn(f2lo(a), f2lo(b)), __fadd_rn(f2hi(a), f2hi(b))); }
+PXD F2 add2rzs(F2 a, float b) { return f2(__fadd_rz(f2lo(a), b), __fadd_rz(f2hi(a), b)); }
+PXD F2 sel2(bool c0, bool c1, F2 a, F2 b) { return f2(c0 ? f2lo(a) : f2lo(b), c1 ? f2hi(a) : f2hi(b)); }
+PXD F2 round_bits2(F2 v) { return add2rz(add2rzs(v, 0.5f), splat2(8388608.0f)); }  // v may be a packed product: scalar first addition
+PXD F2 div255f2(F2 u) {
+  const F2 r = splat2(1.0f / 255.0f);
+  const F2 q = mul2(u, r);
+  return fma2(fma2(q, splat2(-255.0f), u), r, q);
+}
+struct Col2 {
+  F2 r, g, b, a;
+};
+// three quotients per pixel over a shared denominator: d must be inside div3's fast range in both halves
+struct Rcp2 {
+  F2 r, nd;
+};
+PXD Rcp2 rcp2(float d0, float d1) {
+  Rcp2 q;
+  q.r = f2(__frcp_rn(d0), __frcp_rn(d1));
+  q.nd = f2(-d0, -d1);
+  return q;
+}
+PXD F2 fdiv2(F2 x, const Rcp2& k) {
+  F2 q = mul2(x, k.r);
+  q = fma2(fma2(q, k.nd, x), k.r, q);
+  return fma2(fma2(q, k.nd, x), k.r, q);
+}
+PXD bool div_fast_ok(float d) { return d > 1e-18f && d < 1e18f; }
+PXD Col2 to_color2(px_t p0, px_t p1) {
+  const F2 M = f2(__ldg(&g_blend_tables.mul255[p0 >> 24]), __ldg(&g_blend_tables.mul255[p1 >> 24]));
+  const F2 nbig = splat2(-8388608.0f);
+  Col2 c;
+  F2* out[3] = {&c.r, &c.g, &c.b};
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    // byte ch of the pixel in the mantissa of 2^23: the integer as a float after one subtraction
+    const F2 z = f2(__uint_as_float(__byte_perm(p0, 0x4B000000u, 0x7650u + ch)), __uint_as_float(__byte_perm(p1, 0x4B000000u, 0x7650u + ch)));
+    const F2 rb = add2(round_bits2(mul2(add2(z, nbig), M)), nbig);  // roundf(c * multiplier)
+    *out[ch] = div255f2(f2(fminf(f2lo(rb), 255.0f), fminf(f2hi(rb), 255.0f)));
+  }
+  const F2 za = f2(__uint_as_float(__byte_perm(p0, 0x4B000000u, 0x7653u)), __uint_as_float(__byte_perm(p1, 0x4B000000u, 0x7653u)));
+  c.a = div255f2(add2(za, nbig));
+  return c;
+}
+PXD void f2u8_2(F2 v, uint32_t& n0, uint32_t& n1) {
+  const F2 x = mul2(v, splat2(255.0f));
+  const F2 rb = round_bits2(f2(fminf(fmaxf(f2lo(x), 0.0f), 255.0f), fminf(fmaxf(f2hi(x), 0.0f), 255.0f)));
+  n0 = __float_as_uint(f2lo(rb)) & 0x1FFu;
+  n1 = __float_as_uint(f2hi(rb)) & 0x1FFu;
+}
+PXD F2 lum2(const Col2& c) { return add2s(add2s(mul2(splat2(0.3f), c.r), mul2(splat2(0.59f), c.g)), mul2(splat2(0.11f), c.b)); }
+PXD F2 min3f2(const Col2& c) { return f2(min3f(f2lo(c.r), f2lo(c.g), f2lo(c.b)), min3f(f2hi(c.r), f2hi(c.g), f2hi(c.b))); }
+PXD F2 max3f2(const Col2& c) { return f2(max3f(f2lo(c.r), f2lo(c.g), f2lo(c.b)), max3f(f2hi(c.r), f2hi(c.g), f2hi(c.b))); }
+// c + (c - L) * k / d per channel where `on`, unchanged elsewhere; false when an active half's d is outside the fast range
+PXD bool clip_step2(Col2& c, F2 L, F2 k, F2 d, bool on0, bool on1) {
+  const float d0 = on0 ? f2lo(d) : 1.0f, d1 = on1 ? f2hi(d) : 1.0f;
+  if (!(div_fast_ok(d0) && div_fast_ok(d1))) return false;
+  const Rcp2 q = rcp2(d0, d1);
+  c.r = sel2(on0, on1, add2(L, fdiv2(mul2(sub2(c.r, L), k), q)), c.r);
+  c.g = sel2(on0, on1, add2(L, fdiv2(mul2(sub2(c.g, L), k), q)), c.g);
+  c.b = sel2(on0, on1, add2(L, fdiv2(mul2(sub2(c.b, L), k), q)), c.b);
+  return true;
+}
+PXD bool clip_color2(Col2& c) {
+  const F2 L = lum2(c), n = min3f2(c), x = max3f2(c);
+  bool ok = true;
+  const bool n0 = f2lo(n) < 0, n1 = f2hi(n) < 0;
+  if (n0 || n1) ok = clip_step2(c, L, L, sub2(L, n), n0, n1);
+  const bool x0 = f2lo(x) > 1, x1 = f2hi(x) > 1;
+  if (x0 || x1) ok = clip_step2(c, L, sub2(splat2(1.0f), L), sub2(x, L), x0, x1) && ok;
+  return ok;
+}
+PXD bool set_lum2(Col2& c, F2 l) {
+  const F2 d = sub2(l, lum2(c));
+  c.r = add2(c.r, d);
+  c.g = add2(c.g, d);
+  c.b = add2(c.b, d);
+  return clip_color2(c);
+}
+PXD F2 sat2(const Col2& c) { return sub2(max3f2(c), min3f2(c)); }
+PXD bool set_sat2(Col2& c, F2 s) {
+  const F2 satC = sat2(c), mn = min3f2(c);
+  const bool on0 = f2lo(satC) > 0, on1 = f2hi(satC) > 0;
+  const float d0 = on0 ? f2lo(satC) : 1.0f, d1 = on1 ? f2hi(satC) : 1.0f;
+  if (!(div_fast_ok(d0) && div_fast_ok(d1))) return false;
+  const Rcp2 q = rcp2(d0, d1);
+  const F2 zero = splat2(0.0f);
+  c.r = sel2(on0, on1, fdiv2(mul2(sub2(c.r, mn), s), q), zero);
+  c.g = sel2(on0, on1, fdiv2(mul2(sub2(c.g, mn), s), q), zero);
+  c.b = sel2(on0, on1, fdiv2(mul2(sub2(c.b, mn), s), q), zero);
+  return true;
+}
+template <int MODE>
+PXD px_t blend_px(px_t b, px_t s);
+template <int MODE>
+PXD void blend_px2_float(px_t b0, px_t b1, px_t s0, px_t s1, px_t& o0, px_t& o1) {
+  const Col2 cb = to_color2(b0, b1), cs = to_color2(s0, s1);
+  Col2 m;
+  bool ok = true;
+  if (MODE == SoftLightBlend) {
+    const F2 one = splat2(1.0f), m2 = splat2(-2.0f);
+    m.r = add2s(mul2(fma2(cs.r, m2, one), mul2(cb.r, cb.r)), mul2(add2(cs.r, cs.r), cb.r));
+    m.g = add2s(mul2(fma2(cs.g, m2, one), mul2(cb.g, cb.g)), mul2(add2(cs.g, cs.g), cb.g));
+    m.b = add2s(mul2(fma2(cs.b, m2, one), mul2(cb.b, cb.b)), mul2(add2(cs.b, cs.b), cb.b));
+  } else if (MODE == HueBlend) {
+    m = cs;
+    ok = set_sat2(m, sat2(cb));
+    ok = set_lum2(m, lum2(cb)) && ok;
+  } else if (MODE == SaturationBlend) {
+    m = cb;
+    ok = set_sat2(m, sat2(cs));
+    ok = set_lum2(m, lum2(cb)) && ok;
+  } else if (MODE == ColorBlend) {
+    m = cs;
+    ok = set_lum2(m, lum2(cb));
+  } else {
+    m = cb;
+    ok = set_lum2(m, lum2(cs));
+  }
+  if (!ok) {  // a denominator outside the refinement's range: the scalar path, which then divides the IEEE way
+    o0 = blend_px<MODE>(b0, s0);
+    o1 = blend_px<MODE>(b1, s1);
+    return;
+  }
+  // alpha_fix_f: r.a == 0 only when both alphas are 0, then t0 = t1 = t2 = 0 and every numerator is +0: dividing by
+  // the substitute 1e-10 leaves the 0 the reference returns
+  const F2 one = splat2(1.0f);
+  const F2 omsa = sub2(one, cs.a), omba = sub2(one, cb.a);
+  const F2 ra = add2s(cs.a, mul2(cb.a, omsa));
+  const F2 t0 = mul2(cs.a, omba), t1 = mul2(cs.a, cb.a), t2 = mul2(omsa, cb.a);
+  const Rcp2 q = rcp2(fmaxf(f2lo(ra), 1e-10f), fmaxf(f2hi(ra), 1e-10f));  // 1 / 65025 <= r.a <= 2 otherwise
+  const F2 rr = fdiv2(add2s(add2s(mul2(t0, cs.r), mul2(t1, m.r)), mul2(t2, cb.r)), q);
+  const F2 rg = fdiv2(add2s(add2s(mul2(t0, cs.g), mul2(t1, m.g)), mul2(t2, cb.g)), q);
+  const F2 rbl = fdiv2(add2s(add2s(mul2(t0, cs.b), mul2(t1, m.b)), mul2(t2, cb.b)), q);
+  uint32_t r0, r1, g0, g1, bb0, bb1, a0, a1;
+  f2u8_2(rr, r0, r1);
+  f2u8_2(rg, g0, g1);
+  f2u8_2(rbl, bb0, bb1);
+  f2u8_2(ra, a0, a1);
+  o0 = to_premul(mk(r0, g0, bb0, a0));
+  o1 = to_premul(mk(r1, g1, bb1, a1));
+}
+__host__ __device__ constexpr bool mode_is_float(int mode) {
+  return mode == SoftLightBlend || mode == HueBlend || mode == SaturationBlend || mode == ColorBlend || mode == LuminosityBlend;
+}
+// which of them take the two-pixel path in blend.cu: measured at 8192^2, SoftLight gains 8 % (0.505 -> 0.463 ms); the four
+// non-separable modes do not (their per-pixel clip / saturation branches become selects over both halves)
+#ifndef PIXIE_PACKED_NONSEP
+#define PIXIE_PACKED_NONSEP 0
+#endif
+__host__ __device__ constexpr bool mode_is_packed(int mode) { return mode == SoftLightBlend || (PIXIE_PACKED_NONSEP && mode_is_float(mode)); }
 
 // blender(MODE)(backdrop, source), blends.nim:275-299 — MODE is a compile-time constant
 template <int MODE>
