@@ -17,7 +17,9 @@ for r in rows:
         cur['ci'] = {h: j for j, h in enumerate(r)}
     elif r and r[0].startswith('0x'):
         cur['rows'].append(r)
-sec = [s for s in secs if kname.split('pixie')[1][2:12].rstrip('E') in s['name'].replace('::', '')][-1] if len(secs) > 1 else secs[-1]
+short = re.search(r'pixie(\d+)([a-z_]+)', kname)
+short = short.group(2)[:int(short.group(1))] if short else kname
+sec = [s for s in secs if ('::' + short + '(') in s['name']][-1]
 ci = sec['ci']
 seq, cur_line, cur_fn = [], None, None
 for ln in open(dis_txt):
