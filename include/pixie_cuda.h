@@ -112,6 +112,10 @@ int pixie_cuda_cmdlist_create(int width, int height, int layers, int num_fills, 
                               const uint32_t* rgbx, const uint8_t* winding_rule, const uint8_t* blend_mode,
                               pixie_cmdlist_t* out);
 int pixie_cuda_cmdlist_run(pixie_cmdlist_t list, pixie_image_t image, uint64_t* covered_px);
+/* newImage(width, height) + run in one call (what `newImage(svg)` svg.nim:557-608 does before its first fill): the
+ * canvas is cleared to transparent by the raster kernel itself — every (row, tile) of the canvas is zeroed by the warp
+ * that rasterises it next — instead of by a separate pass over the canvas.  Same pixels as image_fill(0) + run. */
+int pixie_cuda_cmdlist_run_cleared(pixie_cmdlist_t list, pixie_image_t image, uint64_t* covered_px);
 /* One GPU's row band of a canvas split across GPUs: plans and rasterises only rows [y0, y1) of a
  * single-layer list.  `image` is the whole canvas (rows outside the range are left alone) or an image of exactly
  * y1 - y0 rows holding that band.  The list itself — bounds, partition boundaries (paths.nim:1172-1192), band

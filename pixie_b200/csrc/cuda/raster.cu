@@ -78,6 +78,7 @@ struct CmdList {
   uint32_t* groupRange = nullptr;  // the same per aligned group of 32 segments
   uint32_t* scratch = nullptr;  // per-warp spill area when a band has more entries than fit in smem
   unsigned long long* counters = nullptr;  // [0] row ticket, [1] covered px
+  bool clearFirst = false;  // set around one run: the raster kernel clears the canvas as it goes
   int rasterBlocks = 0, warpsPerBlock = 0, scratchWords = 0, covBytes = 0, smemCap = 0, tileW = 0, tiles = 1;
   size_t smemBytes = 0, h2dBytes = 0;
   uint8_t* block = nullptr;   // block A: host-written inputs + device-made offsets/flags/counters
@@ -393,6 +394,7 @@ struct RasterArgs {
   unsigned long long* counters;
   long long rowBegin, rowEnd;  // flattened (layer * h + y) rows this launch owns
   int ticketSlot;              // counters[ticketSlot] hands out rows
+  int clearFirst;              // every ticket zeroes its row tile before the first fill (the canvas clear rides along)
   int smemCap;                 // entries whose scratch fits in shared memory
   int scratchCap;              // capacity of the global spill
   const int* rowOrder;         // [h] rows by descending work estimate (build_list): the raster kernel's ticket order
@@ -1661,6 +1663,16 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
     c.plist = reinterpret_cast<uint16_t*>(cov + A.covBytes - 2 * kPartCap);
     c.vec_ok = vecGlobal;
     c.covered = 0;
+    if (A.clearFirst) {  // newImage(): transparent pixels, written by the warp that rasterises them next
+      if (vecGlobal) {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);  // tx0 and the width are multiples of 4 here
+#pragma unroll 4
+        for (int x = c.tx0 + 4 * lane; x < c.tx1; x += 128) *reinterpret_cast<uint4*>(c.row + x) = z;
+      } else {
+        for (int x = c.tx0 + lane; x < c.tx1; x += 32) c.row[x] = 0u;
+      }
+      __syncwarp();
+    }
     const int f0 = A.layerFillBegin[layer], f1 = A.layerFillBegin[layer + 1];
 #pragma unroll 1
     for (int fb = f0; fb < f1; fb += 32) {  // 32 fills per step: which of them touch this row?
@@ -2447,7 +2459,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
   A.countCovered = covered_px ? 1 : 0;
   A.numFills = L.numFills;
   A.fillJobBase = L.fillJobBase; A.payOff = L.payOff; A.jobs = L.jobs; A.payload = L.payload; A.totalJobs = L.totalJobs;
-  A.rowBegin = 0; A.rowEnd = 0; A.ticketSlot = 0;
+  A.rowBegin = 0; A.rowEnd = 0; A.ticketSlot = 0; A.clearFirst = L.clearFirst ? 1 : 0;
   A.scratchSlots = L.scratchSlots; A.scratchSlotCount = L.scratchSlotCount;
   A.planJobBase = L.fillJobBase; A.planY0 = 0; A.planJobs = L.totalJobs;
   A.rowOrder = nullptr;
@@ -2680,8 +2692,9 @@ int pixie_cuda_render_paths_host(uint8_t* pixels, int width, int height, int cle
   void* canvas;
   const size_t bytes = (size_t)width * height * 4;
   if (int rc = get_scratch(5, bytes, &canvas)) return rc;
-  if (clear) PX_CUDA(cudaMemsetAsync(canvas, 0, bytes, r.stream));                        // newImage(width, height)
-  else PX_CUDA(cudaMemcpyAsync(canvas, pixels, bytes, cudaMemcpyHostToDevice, r.stream));  // draw over existing pixels
+  // newImage(width, height): with paths to render, the raster kernel zeroes each row tile itself (clearFirst)
+  if (clear && numPaths == 0) PX_CUDA(cudaMemsetAsync(canvas, 0, bytes, r.stream));
+  if (!clear) PX_CUDA(cudaMemcpyAsync(canvas, pixels, bytes, cudaMemcpyHostToDevice, r.stream));  // draw over existing pixels
   Image im;
   im.data = (uint8_t*)canvas; im.w = width; im.h = height; im.layers = 1; im.bpp = 4; im.owned = false;
   FlattenedPaths F;
@@ -2699,6 +2712,7 @@ int pixie_cuda_render_paths_host(uint8_t* pixels, int width, int height, int cle
   }
   free_flattened(F);
   if (!rc) {
+    L.clearFirst = clear != 0;
     if (numPaths == 0) PX_CUDA(cudaMemcpyAsync(pixels, canvas, bytes, cudaMemcpyDeviceToHost, r.stream));
     else rc = run_list(L, &im, covered_px, pixels);
   }
@@ -2734,6 +2748,26 @@ int pixie_cuda_cmdlist_run(pixie_cmdlist_t list, pixie_image_t image, uint64_t* 
   Image* im = find_image(image);
   if (!im) return 1;
   return run_list(it->second, im, covered_px);
+}
+
+// newImage() + run in one: the canvas is cleared to transparent by the raster kernel itself — every (row, tile) ticket
+// zeroes its pixels before it applies the first fill — instead of by a separate pass over the canvas.
+int pixie_cuda_cmdlist_run_cleared(pixie_cmdlist_t list, pixie_image_t image, uint64_t* covered_px) {
+  PX_API_GUARD;
+  if (int rc = ensure_init()) return rc;
+  auto it = g_lists.find(list);
+  if (it == g_lists.end()) return fail_pixie("invalid command list handle");
+  Image* im = find_image(image);
+  if (!im) return 1;
+  CmdList& L = it->second;
+  if (L.numFills == 0) {
+    if (covered_px) *covered_px = 0;
+    return pixie_cuda_image_fill(image, 0u);
+  }
+  L.clearFirst = true;
+  const int rc = run_list(L, im, covered_px);
+  L.clearFirst = false;
+  return rc;
 }
 
 int pixie_cuda_cmdlist_run_rows(pixie_cmdlist_t list, pixie_image_t image, int y0, int y1, uint64_t* covered_px) {
@@ -2807,8 +2841,9 @@ int pixie_cuda_render_batch_host(uint8_t* pixels, int width, int height, int cle
   void* canvas;
   const size_t bytes = (size_t)width * height * 4;
   if (int rc = get_scratch(5, bytes, &canvas)) return rc;
-  if (clear) PX_CUDA(cudaMemsetAsync(canvas, 0, bytes, r.stream));                        // newImage(width, height)
-  else PX_CUDA(cudaMemcpyAsync(canvas, pixels, bytes, cudaMemcpyHostToDevice, r.stream));  // draw over existing pixels
+  // newImage(width, height): with fills to render, the raster kernel zeroes each row tile itself (clearFirst)
+  if (clear && numFills == 0) PX_CUDA(cudaMemsetAsync(canvas, 0, bytes, r.stream));
+  if (!clear) PX_CUDA(cudaMemcpyAsync(canvas, pixels, bytes, cudaMemcpyHostToDevice, r.stream));  // draw over existing pixels
   Image im;
   im.data = (uint8_t*)canvas; im.w = width; im.h = height; im.layers = 1; im.bpp = 4; im.owned = false;
   CmdList L;
@@ -2817,6 +2852,7 @@ int pixie_cuda_render_batch_host(uint8_t* pixels, int width, int height, int cle
   if (numFills == 0) {
     PX_CUDA(cudaMemcpyAsync(pixels, canvas, bytes, cudaMemcpyDeviceToHost, r.stream));
   } else {
+    L.clearFirst = clear != 0;
     rc = run_list(L, &im, covered_px, pixels);
     if (rc) return rc;
   }

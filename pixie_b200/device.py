@@ -48,6 +48,7 @@ _SIGNATURES = {
     "pixie_cuda_render_batch_host": [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, P(u64)],
     "pixie_cuda_cmdlist_create": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, P(u64)],
     "pixie_cuda_cmdlist_run": [u64, u64, P(u64)],
+    "pixie_cuda_cmdlist_run_cleared": [u64, u64, P(u64)],
     "pixie_cuda_cmdlist_run_rows": [u64, u64, i32, i32, P(u64)],
     "pixie_cuda_cmdlist_info": [u64, P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64)],
     "pixie_cuda_cmdlist_destroy": [u64],
@@ -433,9 +434,11 @@ class CmdList:
             _ptr(arrays["mode"]), C.byref(h)))
         self.handle = h.value
 
-    def run(self, image: DeviceImage, count_covered=False):
+    def run(self, image: DeviceImage, count_covered=False, clear=False):
+        """clear=True: onto a transparent canvas (newImage + fills); the raster kernel clears the canvas as it goes."""
         cov = u64(0)
-        check(lib().pixie_cuda_cmdlist_run(self.handle, image.handle, C.byref(cov) if count_covered else None))
+        fn = lib().pixie_cuda_cmdlist_run_cleared if clear else lib().pixie_cuda_cmdlist_run
+        check(fn(self.handle, image.handle, C.byref(cov) if count_covered else None))
         return cov.value
 
     def run_rows(self, image: DeviceImage, y0, y1, count_covered=False):

@@ -238,6 +238,7 @@ proc pixie_cuda_cmdlist_create_from_paths(width, height, layers, numPaths: cint,
     commands: ptr float32, numCommandFloats: int64, rawXyxy: ptr float32, rawWinding: ptr int16, numRaw: int64,
     outList: ptr uint64): cint {.importc, dynlib: lib, cdecl.}
 proc pixie_cuda_cmdlist_run(list: uint64, image: PixieImageT, coveredPx: ptr uint64): cint {.importc, dynlib: lib, cdecl.}
+proc pixie_cuda_cmdlist_run_cleared(list: uint64, image: PixieImageT, coveredPx: ptr uint64): cint {.importc, dynlib: lib, cdecl.}
 proc pixie_cuda_cmdlist_destroy(list: uint64): cint {.importc, dynlib: lib, cdecl.}
 
 const

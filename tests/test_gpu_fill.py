@@ -142,3 +142,36 @@ def test_mask_clears_left_of_canvas_wrap_into_rows_above(width, pairs):
             b.add(segs, col, rule, MaskBlend)
             b.add(segs, pack(10, 200, 30, 255), rule, NormalBlend)
             _check(b.arrays(), w, h, background=bg)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [(512, 512, 3), (333, 97, 2), (4100, 40, 1)])
+def test_run_cleared_equals_clear_then_run(size):
+    """pixie_cuda_cmdlist_run_cleared (the raster kernel zeroes each row tile before its first fill) on a DIRTY canvas
+    == image.fill(0) + run, incl. widths that are not a multiple of 4, two column tiles, several layers, MaskBlend
+    fills (which clear what they do not cover) and rows / layers no fill touches."""
+    from pixie_b200 import device as dev
+
+    w, h, layers = size
+    dev.init(0)
+    b = FillBatch()
+    for layer in range(layers):  # fills in layer order
+        if layer == 1:
+            continue  # a layer without fills: must still come out transparent
+        synth.icon_fills(7 + layer, min(w, h) if min(w, h) >= 64 else 64, layer, b)
+        if layer == 0:
+            b.add(host.fill_segments(f"M 3.5 2.5 L {w - 7.25} {h * 0.4} L {w * 0.3} {h - 3.5} z"), pack(10, 200, 30, 200), host.NonZero, NormalBlend, 0)
+    b.add(host.fill_segments(f"M -20 {h * 0.2} H {w * 0.6} V {h * 0.7} H -20 z"), pack(0, 0, 0, 180), host.NonZero, MaskBlend, layers - 1)
+    arrays = b.arrays()
+    dirty = np.stack([synth.random_premultiplied(h, w, 40 + k) for k in range(layers)]) if layers > 1 else synth.random_premultiplied(h, w, 40)
+    a = dev.DeviceImage(w, h, layers).upload(dirty)
+    ref = dev.DeviceImage(w, h, layers).upload(dirty)
+    cl = dev.CmdList(w, h, layers, arrays)
+    ca = cl.run(a, count_covered=True, clear=True)
+    ref.fill(0)
+    cb = cl.run(ref, count_covered=True)
+    assert ca == cb
+    got, want = a.download(), ref.download()
+    assert np.array_equal(got, want)
+    ow, _ = oracle_render_batch(arrays, w, h, layers=layers)
+    assert diff_report(got.reshape(layers, h, w, 4)[0], ow[0])[0] == 0
