@@ -1628,6 +1628,9 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
   const bool vecGlobal = (A.w & 3) == 0 && (reinterpret_cast<uintptr_t>(A.canvas) & 15) == 0;
   const unsigned H_ = (unsigned)A.h;
 
+#ifdef PIXIE_RASTER_TIMING
+  const long long kern0_ = clock64();
+#endif
   unsigned covered = 0;
   const unsigned long long nTickets = (unsigned long long)(A.rowEnd > A.rowBegin ? A.rowEnd - A.rowBegin : 0) * (unsigned)A.tiles;
   while (true) {
@@ -1635,6 +1638,9 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
     if (lane == 0) ticket = atomicAdd(&A.counters[A.ticketSlot], 1ull);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
     if (ticket >= nTickets) break;
+#ifdef PIXIE_RASTER_TIMING
+    const long long tk0_ = clock64();
+#endif
     // ticket -> (row, tile) without a 64-bit division (75 instructions per ticket, 7 % of an icon batch's kernel)
     unsigned long long rowRel = ticket;
     int tile = 0;
@@ -1733,7 +1739,21 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
       }
     }
     covered += c.covered;
+#ifdef PIXIE_RASTER_TIMING  // tools/build_variant.sh tk pixie_b200/csrc/cuda/raster.cu -DPIXIE_RASTER_TIMING
+    if (lane == 0) {
+      const unsigned long long dt = (unsigned long long)(clock64() - tk0_);
+      atomicMax(&A.counters[40], dt);
+      atomicAdd(&A.counters[41], dt);
+      atomicAdd(&A.counters[42], 1ull);
+      if (dt > 100000ull) atomicAdd(&A.counters[43], 1ull);
+      if (dt > 50000ull) atomicAdd(&A.counters[44], 1ull);
+      if (dt > 20000ull) atomicAdd(&A.counters[45], 1ull);
+    }
+#endif
   }
+#ifdef PIXIE_RASTER_TIMING
+  if (lane == 0) atomicMax(&A.counters[46], (unsigned long long)(clock64() - kern0_));
+#endif
   if (A.countCovered) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) covered += __shfl_xor_sync(0xffffffffu, covered, o);
@@ -2520,6 +2540,15 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
       raster_kernel<<<L.rasterBlocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
     }
     PX_LAUNCHED();
+#ifdef PIXIE_RASTER_TIMING  // per-ticket durations: the kernel cannot end before its longest (row, tile) ticket does
+    {
+      unsigned long long hc[64];
+      cudaMemcpyAsync(hc, L.counters, 512, cudaMemcpyDeviceToHost, r.stream);
+      cudaStreamSynchronize(r.stream);
+      fprintf(stderr, "[raster tickets] n %llu  mean %.0f cycles  max %llu  >100k %llu  >50k %llu  >20k %llu  longest warp lifetime %llu cycles\n", hc[42],
+              hc[42] ? (double)hc[41] / (double)hc[42] : 0.0, hc[40], hc[43], hc[44], hc[45], hc[46]);
+    }
+#endif
     if (host_pixels)
       PX_CUDA(cudaMemcpyAsync(host_pixels, im->data, (size_t)totalRows * L.w * 4, cudaMemcpyDeviceToHost, r.stream));
   } else {
