@@ -366,8 +366,11 @@ __global__ void __launch_bounds__(256) partition_kernel(const FillHeader* __rest
 struct JobHdr {
   int kind;    // PlanKind
   int n;       // Trapezoids: edges (even); Coverage / Spans: spans
-  int pa, pb;  // Aligned: the span [pa, pb)
+  int pa, pb;  // Aligned: the span [pa, pb); the other kinds: the pixels [pa, pb) the plan can touch (its edges / spans),
+               // so that a raster warp whose columns they miss skips the job (MaskBlend fills clear and are never skipped)
 };
+PXD int extent_lo(int lo, float xa, float xb) { return min(lo, __float2int_rz(fminf(xa, xb))); }          // trapezoid edge pixels
+PXD int extent_hi(int hi, float xa, float xb) { return max(hi, __float2int_rz(ceilf(fmaxf(xa, xb)))); }  // [trunc(min x), ceil(max x))
 
 struct RasterArgs {
   px_t* canvas;
@@ -696,13 +699,18 @@ __global__ void __launch_bounds__(kLightThreads) plan_light_kernel(const RasterA
     if (ok) {
       hdr.kind = PlanTrapezoids;
       hdr.n = nsel;
+      int lo = INT_MAX, hi = INT_MIN;
 #pragma unroll 1
       for (int i = 0; i < nsel; i++) {
         const int es = (int)at(4, i);
         const Entry* e = ent + at(0, es);
         pay[2 * i] = make_uint2(__float_as_uint(e->m), __float_as_uint(e->b));
         pay[2 * i + 1] = make_uint2(__float_as_uint(atf(1, es)), __float_as_uint(atf(2, es)));
+        lo = extent_lo(lo, atf(1, es), atf(2, es));
+        hi = extent_hi(hi, atf(1, es), atf(2, es));
       }
+      hdr.pa = lo;
+      hdr.pb = hi;
       A.jobs[job] = hdr;
       return;
     }
@@ -718,7 +726,7 @@ __global__ void __launch_bounds__(kLightThreads) plan_light_kernel(const RasterA
   const float offset = 1.0f / (float)quality;
   const float initialOffset = offset / 2.0f + (float)(0.0001 * 3.141592653589793238462643383279502884);
   hdr.kind = aa ? PlanCoverage : PlanSpans;
-  int S = 0;
+  int S = 0, extLo = INT_MAX, extHi = INT_MIN;
   if (nsel > 0) {
     float yLine = (float)y + initialOffset - offset;
 #pragma unroll 1
@@ -764,6 +772,8 @@ __global__ void __launch_bounds__(kLightThreads) plan_light_kernel(const RasterA
               }
             }
             pay[S++] = make_uint2((uint32_t)prevAt, (uint32_t)hat);
+            extLo = min(extLo, fx_integer(prevAt));
+            extHi = max(extHi, fx_integer(hat) + 1);
           }
           prevAt = hat;
         }
@@ -773,6 +783,8 @@ __global__ void __launch_bounds__(kLightThreads) plan_light_kernel(const RasterA
     }
   }
   hdr.n = S;
+  hdr.pa = extLo;
+  hdr.pb = extHi;
   A.jobs[job] = hdr;
 }
 
@@ -954,13 +966,18 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
       if (ok) {  // payload: per sorted edge {m, b} {x at the top, x at the bottom of the scanline}
         hdr.kind = PlanTrapezoids;
         hdr.n = nsel;
+        int lo = INT_MAX, hi = INT_MIN;
 #pragma unroll 1
         for (int i = lane; i < nsel; i += 32) {
           const int es = order[i];
           const Entry e = ent[sel[es]];
           pay[2 * i] = make_uint2(__float_as_uint(e.m), __float_as_uint(e.b));
           pay[2 * i + 1] = make_uint2(__float_as_uint(tax[es]), __float_as_uint(tbx[es]));
+          lo = extent_lo(lo, tax[es], tbx[es]);
+          hi = extent_hi(hi, tax[es], tbx[es]);
         }
+        hdr.pa = __reduce_min_sync(0xffffffffu, lo);
+        hdr.pb = __reduce_max_sync(0xffffffffu, hi);
         if (lane == 0) A.jobs[job] = hdr;
         continue;
       }
@@ -1079,12 +1096,18 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
       const int n4 = __shfl_sync(0xffffffffu, ns, 4);
       const int pre1 = n0, pre2 = pre1 + n1, pre3 = pre2 + n2, pre4 = pre3 + n3, S = pre4 + n4;
       hdr.n = S;
+      int lo = INT_MAX, hi = INT_MIN;
 #pragma unroll 1
       for (int g = lane; g < S; g += 32) {  // payload: the spans of all lines, {begin, end} in 24.8 fixed point
         const int m = (g >= pre1) + (g >= pre2) + (g >= pre3) + (g >= pre4);
         const int k = g - (m == 0 ? 0 : m == 1 ? pre1 : m == 2 ? pre2 : m == 3 ? pre3 : pre4);
-        pay[g] = make_uint2((uint32_t)sAt[m * n + k], (uint32_t)sW[m * n + k]);
+        const int b_ = sAt[m * n + k], e_ = sW[m * n + k];
+        pay[g] = make_uint2((uint32_t)b_, (uint32_t)e_);
+        lo = min(lo, fx_integer(b_));
+        hi = max(hi, fx_integer(e_) + 1);
       }
+      hdr.pa = __reduce_min_sync(0xffffffffu, lo);
+      hdr.pb = __reduce_max_sync(0xffffffffu, hi);
     }
     if (lane == 0) A.jobs[job] = hdr;
   }
@@ -1701,9 +1724,13 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
           if (act && y >= sY && y < pH) {
             const JobHdr hd = A.jobs[A.fillJobBase[fl] + (y - sY)];
             kind = hd.kind; n = hd.n; pa = hd.pa; pb = hd.pb;
+            // the plan's pixels [pa, pb) miss this warp's columns, or there is no plan: nothing to do here
+            if (bmode != MaskBlend && (kind < PlanAligned || pb <= c.tx0 || pa >= c.tx1)) act = false;
             pay = job_payload(A, Hp, y, nullptr);
             wrapRows = Hp->wrapRows;
             rowsBelow = pH - 1 - y;
+          } else if (bmode != MaskBlend) {
+            act = false;
           }
         }
       }
