@@ -79,6 +79,7 @@ struct CmdList {
   uint32_t* scratch = nullptr;  // per-warp spill area when a band has more entries than fit in smem
   unsigned long long* counters = nullptr;  // [0] row ticket, [1] covered px
   bool clearFirst = false;  // set around one run: the raster kernel clears the canvas as it goes
+  int subShift = 0;         // see RasterArgs
   int rasterBlocks = 0, warpsPerBlock = 0, scratchWords = 0, covBytes = 0, smemCap = 0, tileW = 0, tiles = 1;
   size_t smemBytes = 0, h2dBytes = 0;
   uint8_t* block = nullptr;   // block A: host-written inputs + device-made offsets/flags/counters
@@ -398,6 +399,7 @@ struct RasterArgs {
   long long rowBegin, rowEnd;  // flattened (layer * h + y) rows this launch owns
   int ticketSlot;              // counters[ticketSlot] hands out rows
   int clearFirst;              // every ticket zeroes its row tile before the first fill (the canvas clear rides along)
+  int subShift;                // rowOrder lists: a tile is handed out in 1 << subShift pieces; rowOrder[i] >> 28 = how many of them the row uses (as a shift)
   int smemCap;                 // entries whose scratch fits in shared memory
   int scratchCap;              // capacity of the global spill
   const int* rowOrder;         // [h] rows by descending work estimate (build_list): the raster kernel's ticket order
@@ -1121,6 +1123,7 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
 // K3: raster_kernel — apply the plans to the canvas, row by row, fills in order
 // ---------------------------------------------------------------------------------------------
 constexpr int kPartCap = 128;
+constexpr int kMaxSubShift = 3;  // a tile of a busy row in up to 8 pieces
 struct WarpCtx {
   int mode;         // run-time blend mode (used by the GenericMode instantiation)
   px_t* row;        // canvas row of this warp
@@ -1642,6 +1645,9 @@ PXD const uint2* job_payload(const RasterArgs& A, const FillHeader* Hp, int y, i
   return A.payload + ((size_t)A.payOff[gp] + (size_t)(y - (startY + p * ph)) * (size_t)eCnt) * kPaySlots;
 }
 
+// CUT: rows are handed out in pieces (RasterArgs::subShift > 0); a separate instantiation, so that lists without cut
+// rows (icon batches, row bands) run the kernel without the extra state
+template <bool CUT>
 __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1655,7 +1661,9 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
   const long long kern0_ = clock64();
 #endif
   unsigned covered = 0;
-  const unsigned long long nTickets = (unsigned long long)(A.rowEnd > A.rowBegin ? A.rowEnd - A.rowBegin : 0) * (unsigned)A.tiles;
+  const int subShift = CUT ? A.subShift : 0, pieceW = A.tileW >> subShift;
+  const unsigned per = (unsigned)A.tiles << subShift;
+  const unsigned long long nTickets = (unsigned long long)(A.rowEnd > A.rowBegin ? A.rowEnd - A.rowBegin : 0) * per;
   while (true) {
     unsigned long long ticket = 0;
     if (lane == 0) ticket = atomicAdd(&A.counters[A.ticketSlot], 1ull);
@@ -1664,28 +1672,47 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterArgs A) {
 #ifdef PIXIE_RASTER_TIMING
     const long long tk0_ = clock64();
 #endif
-    // ticket -> (row, tile) without a 64-bit division (75 instructions per ticket, 7 % of an icon batch's kernel)
-    unsigned long long rowRel = ticket;
-    int tile = 0;
-    if (A.tiles != 1) {
-      if ((ticket >> 32) == 0ull) {
-        const unsigned q = (unsigned)ticket / (unsigned)A.tiles;
-        rowRel = q;
-        tile = (int)((unsigned)ticket - q * (unsigned)A.tiles);
-      } else {
-        rowRel = ticket / (unsigned)A.tiles;
-        tile = (int)(ticket - rowRel * (unsigned)A.tiles);
+    unsigned long long rowOfTicket;
+    int tx0_, txW_;
+    if (!CUT) {
+      // ticket -> (row, tile) without a 64-bit division (75 instructions per ticket, 7 % of an icon batch's kernel)
+      unsigned long long rowRel = ticket;
+      int tile = 0;
+      if (A.tiles != 1) {
+        if ((ticket >> 32) == 0ull) {
+          const unsigned q = (unsigned)ticket / (unsigned)A.tiles;
+          rowRel = q;
+          tile = (int)((unsigned)ticket - q * (unsigned)A.tiles);
+        } else {
+          rowRel = ticket / (unsigned)A.tiles;
+          tile = (int)(ticket - rowRel * (unsigned)A.tiles);
+        }
       }
+      rowOfTicket = rowRel + (unsigned long long)A.rowBegin;
+      if (A.rowOrder) rowOfTicket = (unsigned long long)((unsigned)A.rowOrder[rowOfTicket] & 0x0FFFFFFFu);  // whole-canvas launches only (rowBegin = 0)
+      tx0_ = tile * A.tileW;
+      txW_ = A.tileW;
+    } else {
+      // A row is handed out in `per` pieces of pieceW columns; a row that is cut less finely (most rows: the cut
+      // exists for the few busiest ones, whose single warp would otherwise outlast the rest of the kernel) is
+      // rasterised by the ticket of the first piece of each group and the other tickets of the group return at once.
+      const unsigned q = (unsigned)ticket / per;  // cut lists are single canvases: tickets fit 32 bits
+      const unsigned sub = (unsigned)ticket - q * per;
+      const unsigned ro = (unsigned)A.rowOrder[q];
+      rowOfTicket = ro & 0x0FFFFFFFu;
+      const int group = subShift - (int)(ro >> 28);  // log2 of the pieces this ticket covers
+      if (sub & ((1u << group) - 1u)) continue;
+      tx0_ = (int)sub * pieceW;
+      if (tx0_ >= A.w) continue;
+      txW_ = pieceW << group;
     }
-    unsigned long long rowOfTicket = rowRel + (unsigned long long)A.rowBegin;
-    if (A.rowOrder) rowOfTicket = (unsigned long long)A.rowOrder[rowOfTicket];  // whole-canvas launches only (rowBegin = 0)
     const unsigned t32 = (unsigned)rowOfTicket;  // layers * h < 2^31 (checked by the host)
     const int layer = t32 < H_ ? 0 : (int)(t32 / H_), y = (int)(t32 - (unsigned)layer * H_);
     WarpCtx c;
     c.row = A.canvas + (size_t)t32 * (size_t)A.w;
     c.w = A.w;
-    c.tx0 = tile * A.tileW;
-    c.tx1 = min(c.tx0 + A.tileW, A.w);
+    c.tx0 = tx0_;
+    c.tx1 = min(tx0_ + txW_, A.w);
     c.y = y;
     c.lane = lane;
     c.cov = cov;
@@ -2213,9 +2240,11 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   static size_t occSmem = ~(size_t)0;  // occupancy of the two kernels, looked up once per coverage-row size
   static int occRaster = 1, occPlan = 1;
   if (occSmem != L.smemBytes) {
-    if (L.smemBytes > 48 * 1024)
-      PX_CUDA(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes));
-    PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occRaster, raster_kernel, L.warpsPerBlock * 32, L.smemBytes));
+    if (L.smemBytes > 48 * 1024) {
+      PX_CUDA(cudaFuncSetAttribute(raster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes));
+      PX_CUDA(cudaFuncSetAttribute(raster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes));
+    }
+    PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occRaster, raster_kernel<false>, L.warpsPerBlock * 32, L.smemBytes));
     PX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occPlan, plan_kernel, 256, L.planSmem));
     occSmem = L.smemBytes;
   }
@@ -2286,8 +2315,29 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
     auto bucket = [&](long long c) { return 255 - (int)(c * 255 / mx); };  // 0 = the most expensive rows
     for (int y = 0; y < h; y++) hist[bucket(cost[(size_t)y]) + 1]++;
     for (int b = 0; b < 256; b++) hist[b + 1] += hist[b];
+    // How finely a row is cut: the kernel cannot end before its longest ticket does, and on the tiger the busiest
+    // half-row took as long as the whole kernel (358 k of 375 k cycles; the mean ticket 119 k).  A row whose ticket
+    // is estimated above cutPct % of an even share of the work is cut in two, four, eight; pieces repeat the per-ticket
+    // scan of the fills, so cutting everything is slower (jobs that miss a piece cost it nothing: JobHdr::pa / pb).
+    long long total = 0;
+    for (int y = 0; y < h; y++) total += cost[(size_t)y];
+    const long long even = std::max<long long>(1, total / std::max(1, r.num_sms * 24));
+    int maxShift = 0;
+    while (maxShift < kMaxSubShift && (L.tileW >> (maxShift + 1)) >= 256 && (L.tileW % (8 << maxShift)) == 0) maxShift++;
+    std::vector<uint8_t> shiftOf((size_t)h, 0);
+    // swept on the tiger (PIXIE_CUDA_CUT = percent): 4096^2 raster 0.195 ms uncut, 0.183 at 80, 0.189 at 90, 0.22 at 40;
+    // 2048^2 0.166 uncut (before the jobs carried their extents), 0.131 at 90, 0.142 at 80; 8192^2 unchanged
+    static const long long cutPct = getenv("PIXIE_CUDA_CUT") ? atoll(getenv("PIXIE_CUDA_CUT")) : 85;
+    int used = 0;
+    for (int y = 0; y < h; y++) {
+      int s_ = 0;
+      while (s_ < maxShift && cost[(size_t)y] / L.tiles > (even << s_) * cutPct / 100) s_++;
+      shiftOf[(size_t)y] = (uint8_t)s_;
+      used = std::max(used, s_);
+    }
+    L.subShift = used;
     int* order = reinterpret_cast<int*>(stage + oRowOrder);
-    for (int y = 0; y < h; y++) order[hist[bucket(cost[(size_t)y])]++] = y;
+    for (int y = 0; y < h; y++) order[hist[bucket(cost[(size_t)y])]++] = y | ((int)shiftOf[(size_t)y] << 28);
   }
   memcpy(stage + oLayer, layerBegin.data(), layerBegin.size() * 4);
   memcpy(stage + oJobBase, jobBase.data(), jobBase.size() * 4);
@@ -2506,13 +2556,14 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
   A.countCovered = covered_px ? 1 : 0;
   A.numFills = L.numFills;
   A.fillJobBase = L.fillJobBase; A.payOff = L.payOff; A.jobs = L.jobs; A.payload = L.payload; A.totalJobs = L.totalJobs;
-  A.rowBegin = 0; A.rowEnd = 0; A.ticketSlot = 0; A.clearFirst = L.clearFirst ? 1 : 0;
+  A.rowBegin = 0; A.rowEnd = 0; A.ticketSlot = 0; A.clearFirst = L.clearFirst ? 1 : 0; A.subShift = 0;
   A.scratchSlots = L.scratchSlots; A.scratchSlotCount = L.scratchSlotCount;
   A.planJobBase = L.fillJobBase; A.planY0 = 0; A.planJobs = L.totalJobs;
   A.rowOrder = nullptr;
   static size_t configured = 0;
   if (L.smemBytes > 48 * 1024 && configured < L.smemBytes) {
-    PX_CUDA(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes));
+    PX_CUDA(cudaFuncSetAttribute(raster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes));
+    PX_CUDA(cudaFuncSetAttribute(raster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes));
     configured = L.smemBytes;
   }
   const long long totalRows = (long long)L.layers * L.h;
@@ -2550,7 +2601,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
                                                                      L.rasterBlocks));
     {
       ProfScope ps(kProfRaster);
-      raster_kernel<<<blocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
+      raster_kernel<false><<<blocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
     }
     PX_LAUNCHED();
   } else if (L.bands <= 1 || L.serial) {
@@ -2562,9 +2613,11 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
     }
     A.rowBegin = 0; A.rowEnd = totalRows; A.ticketSlot = 0;
     A.rowOrder = L.bands <= 1 ? L.rowOrder : nullptr;
+    A.subShift = A.rowOrder ? L.subShift : 0;
     {
       ProfScope ps(kProfRaster);
-      raster_kernel<<<L.rasterBlocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
+      if (A.subShift > 0) raster_kernel<true><<<L.rasterBlocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
+      else raster_kernel<false><<<L.rasterBlocks, L.warpsPerBlock * 32, L.smemBytes, r.stream>>>(A);
     }
     PX_LAUNCHED();
 #ifdef PIXIE_RASTER_TIMING  // per-ticket durations: the kernel cannot end before its longest (row, tile) ticket does
@@ -2631,7 +2684,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
       if (B.rowEnd <= B.rowBegin) return 0;
       const int blocks = (int)std::max<long long>(1, std::min<long long>(((B.rowEnd - B.rowBegin) * L.tiles + L.warpsPerBlock - 1) / L.warpsPerBlock,
                                                                        L.rasterBlocks));
-      raster_kernel<<<blocks, L.warpsPerBlock * 32, L.smemBytes, r.band_stream[b]>>>(B);
+      raster_kernel<false><<<blocks, L.warpsPerBlock * 32, L.smemBytes, r.band_stream[b]>>>(B);
       PX_LAUNCHED();
       if (prof) PX_CUDA(cudaEventRecord(r.band_prof[b][3], r.band_stream[b]));
       if (g_trace) PX_CUDA(cudaEventRecord(tev[2 + 3 * b], r.band_stream[b]));
