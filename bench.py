@@ -1034,13 +1034,18 @@ def run_ours(args):
     roofline = {"kernel": "raster_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4),
                 # dram__bytes_read.sum + dram__bytes_write.sum of one raster_kernel launch on this workload, from the offline
-                # `ncu --set full` capture summarised in profiles/r02_tiger_metrics.txt (20.28 MB read + 11.67 MB written:
+                # `ncu --set full` capture summarised in profiles/r02_tiger_metrics.txt (19.94 MB read + 14.69 MB written:
                 # the canvas stays in the 126 MB L2) — a capture, not measured by this run (traffic_source says so)
-                "traffic": 31952128 if size == 4096 else None, "traffic_source": "profiles/r02_tiger_metrics.txt (ncu capture)",
+                "traffic": 34633472 if size == 4096 else None, "traffic_source": "profiles/r02_tiger_metrics.txt (ncu capture)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(rast, 4),
                 "partition_kernel_ms": round(part, 4), "plan_kernel_ms": round(statistics.mean(plan_ms), 4), "share_of_step": round(rast / statistics.mean(step_ms), 3),
-                "note": "305 order-dependent fills: latency/occupancy-bound, not bandwidth-bound (SURVEY.md 7.1)"}
+                # since round 2 the launch also clears the canvas (pixie_cuda_cmdlist_run_cleared: every row tile is zeroed by the
+                # warp that rasterises it): 4 B per canvas pixel that `achieved` (SURVEY.md 8(d)'s per-unit figure) does not count
+                "clear_bytes_per_launch": 4 * size * size,
+                "achieved_incl_clear": round((alg_bytes + 4 * size * size) / (rast * 1e-3) / 1e9, 1),
+                "note": "305 order-dependent fills: the kernel ends with its longest (row, tile) ticket — latency-bound, not "
+                        "bandwidth-bound (SURVEY.md 7.1; per-ticket cycle counters: DESIGN.md 8)"}
 
     cpu = None
     extras = None

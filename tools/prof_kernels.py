@@ -41,8 +41,7 @@ if which in ("tiger", "all"):
     img = dev.DeviceImage(4096, 4096)
     cl = dev.CmdList(4096, 4096, 1, arrays)
     for _ in range(3):
-        img.fill(0)
-        cl.run(img)
+        cl.run(img, clear=True)  # as the bench step: the raster kernel clears the canvas
     dev.sync()
 if which in ("icons", "all"):
     from pixie_b200.device import FillBatch
