@@ -1,2 +1,4 @@
 #!/bin/bash
-for c in 50 70 85 100 120 150; do echo "cut $c"; export PIXIE_CUDA_CUT=$c; PIXIE_CUDA_LIB=build/pixie_cuda_tk.so python tools/time_tiger.py 2>&1 | tail -2 | head -1; TIGER_CLEAR=1 python tools/time_tiger.py;  TIGER_CLEAR=1 python tools/time_tiger.py 2048; TIGER_CLEAR=1 python tools/time_tiger.py 8192; done
+timeout 900 python -m pytest tests/test_gpu_fill.py tests/test_gpu_tiger.py tests/test_gpu_fuzz.py tests/test_gpu_goldens.py tests/test_gpu_api.py tests/test_gpu_flatten.py tests/test_gpu_boundary.py -x -q 2>&1 | tail -2
+for i in 1 2; do PIXIE_CUDA_LIB=build/pixie_cuda_base.so python tools/time_icons.py | tail -1; python tools/time_icons.py | tail -1; done
+for s in 2048 4096 8192; do PIXIE_CUDA_LIB=build/pixie_cuda_base.so TIGER_CLEAR=1 python tools/time_tiger.py $s; TIGER_CLEAR=1 python tools/time_tiger.py $s; done
