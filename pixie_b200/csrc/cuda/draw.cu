@@ -394,11 +394,14 @@ struct GradientArgs {
   float gradientAngle;  // angular
   float pos[kMaxStops];
   float col[kMaxStops][4];
+  // RN(1 / (pos[i + 1] - pos[i])) where that difference is inside fdiv_r's range (common.cuh), else 0: the division of
+  // the interpolation parameter then costs one multiply and two FMA refinement steps instead of an IEEE division
+  float rstep[kMaxStops];
 };
 PXD uint32_t quant_f(float v) {  // chroma Color channel -> uint8: floor(v * 255 + 0.5) clamped to 0..255, NaN -> 0
-  const float r = v * 255.0f + 0.5f;
-  if (!(r >= 1.0f)) return 0u;
-  return r >= 255.0f ? 255u : (uint32_t)__float2int_rd(r);
+  // branch-free: clamp first (fmaxf(NaN, 0) = 0; floor is monotone), then floor through a round-down addition of 2^23
+  const float r = fminf(fmaxf(v * 255.0f + 0.5f, 0.0f), 255.0f);
+  return __float_as_uint(__fadd_rd(r, 8388608.0f)) & 0x1FFu;
 }
 PXD float fix_angle(float a) {
   const float pi = (float)3.141592653589793238462643383279502884, tau = (float)(2 * 3.141592653589793238462643383279502884);
@@ -418,7 +421,8 @@ PXD px_t gradient_color(const GradientArgs& G, float t) {  // :68-94
   } else if (index + 1 >= G.n) {
     r = G.col[index][0]; g = G.col[index][1]; b = G.col[index][2]; a = G.col[index][3];
   } else {
-    const float v = (t - G.pos[index]) / (G.pos[index + 1] - G.pos[index]);
+    const float vn = t - G.pos[index], vd = G.pos[index + 1] - G.pos[index], vr = G.rstep[index];
+    const float v = vr != 0.0f ? fdiv_r(vn, vd, vr) : vn / vd;
     const float iv = 1.0f - v;
     r = G.col[index][0] * iv + G.col[index + 1][0] * v;
     g = G.col[index][1] * iv + G.col[index + 1][1] * v;
@@ -441,7 +445,9 @@ PXD float gradient_t(const GradientArgs& G, int x, int y) {
     else if (G.h0x == G.h1x) qx = 0.0f;
     const float ddx = G.h1x - G.h0x, ddy = G.h1y - G.h0y;
     const float det = ddx * ddx + ddy * ddy;
-    return (ddy * (qy - G.h0y) + ddx * (qx - G.h0x)) / det;
+    const float num = ddy * (qy - G.h0y) + ddx * (qx - G.h0x);
+    // det is the same for every pixel: its reciprocal is hoisted out of the pixel loops by the compiler
+    return div_fast_ok(det) ? fdiv_r(num, det, __frcp_rn(det)) : num / det;
   }
   if (G.kind == 4) {
     const float vx = (float)x, vy = (float)y;
@@ -929,6 +935,11 @@ static int gradient_setup(GradientArgs& G, Image* im, int kind, const float* han
   G.img = (px_t*)im->data; G.w = im->w; G.h = im->h; G.kind = kind; G.n = n_stops; G.opacity = opacity;
   memcpy(G.pos, stop_pos, (size_t)n_stops * 4);
   memcpy(G.col, stop_rgba, (size_t)n_stops * 16);
+  for (int i = 0; i + 1 < n_stops; i++) {
+    volatile float d = G.pos[i + 1] - G.pos[i];  // one IEEE subtraction, as the kernel's
+    const float dd = d;
+    G.rstep[i] = (dd > 1e-18f && dd < 1e18f) ? 1.0f / dd : 0.0f;
+  }
   G.h0x = handles[0]; G.h0y = handles[1]; G.h1x = handles[2]; G.h1y = handles[3];
   const float pi = (float)3.141592653589793238462643383279502884, tau = (float)(2 * 3.141592653589793238462643383279502884);
   auto fix = [&](float a) {

@@ -1,3 +1,6 @@
 #!/bin/bash
-for so in pixie_b200/pixie_cuda.so build/pixie_cuda_a3.so build/pixie_cuda_a4.so build/pixie_cuda_a6.so; do echo $so; PIXIE_CUDA_LIB=$so timeout 120 python tools/time_blend.py 3,6 2>&1 | tail -2; done
-PIXIE_CUDA_LIB=build/pixie_cuda_a4.so timeout 600 python -m pytest tests/test_gpu_blend_blur.py -x -q -k blend 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_draw.py tests/test_gpu_goldens.py tests/test_gpu_api.py -x -q 2>&1 | tail -2
+PIXIE_CUDA_LIB=build/pixie_cuda_base.so timeout 200 python tools/time_paint.py 2>&1 | tail -6
+timeout 200 python tools/time_paint.py 2>&1 | tail -6
+PIXIE_CUDA_LIB=build/pixie_cuda_base.so timeout 200 python tools/time_draw.py 2>&1 | grep -i grad
+timeout 200 python tools/time_draw.py 2>&1 | grep -i grad
