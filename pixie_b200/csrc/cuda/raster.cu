@@ -67,6 +67,8 @@ struct CmdList {
   int* bandJobBase = nullptr;              // [bands][numFills + 1] job prefix of each band
   int bandJobs[Runtime::kBands] = {};
   int* heavyList = nullptr;                // [totalJobs] jobs left for plan_kernel, one region per plan launch
+  int* splitArrive = nullptr;              // [totalJobs] see RasterArgs
+  int* monsterList = nullptr;              // [totalJobs] see RasterArgs
   unsigned* scratchSlots = nullptr;        // bitmap: spill-scratch block slots in use
   int scratchSlotCount = 0;
   size_t planSmem = 0;
@@ -386,6 +388,8 @@ struct RasterArgs {
   const int* fillJobBase;      // [numFills + 1] first job of each fill; job = fillJobBase[f] + (y - startY)
   const int* planJobBase;      // [numFills + 1] the same restricted to the rows [planY0, planY1) of this plan launch
   int planY0, planJobs;        // jobs of this plan launch (whole list: planJobBase = fillJobBase, planY0 = 0)
+  int* monsterList;            // jobs whose scanline is planned by one warp per sample line (plan_classify_kernel), count in heavyCount[24]
+  int* splitArrive;            // [totalJobs], zero between runs: sample lines of a split job that have been planned (atomicInc wraps it back to 0)
   int* heavyList;              // jobs of crowded bands (> kLightMax entries), compacted by plan_light_kernel for
   unsigned long long* heavyCount;  // plan_kernel; one list region + counter per plan launch
   unsigned* scratchSlots;      // bitmap of the spill-scratch block slots in use (plan launches of several row
@@ -566,8 +570,12 @@ PXD int find_fill_by_job(const int* __restrict__ jobBase, int numFills, int j) {
 #ifndef PIXIE_LIGHT_MAX
 #define PIXIE_LIGHT_MAX 12
 #endif
+#ifndef PIXIE_SPLIT_MIN
+#define PIXIE_SPLIT_MIN 128
+#endif
 constexpr int kLightMax = PIXIE_LIGHT_MAX;
 constexpr int kVeryHeavy = 64;  // bands with more entries than this are planned first
+constexpr int kSplitLines = PIXIE_SPLIT_MIN;  // ... and above this many, one warp per SAMPLE LINE plans the scanline (plan_kernel)
 constexpr int kLightArrays = 5;
 constexpr int kLightThreads = 128;
 
@@ -586,11 +594,19 @@ __global__ void __launch_bounds__(256) plan_classify_kernel(const RasterArgs A) 
   // The list is filled from both ends: jobs of very crowded bands (their sorts and walks are the longest single
   // pieces of work of the whole launch) from the front, so that plan_kernel starts them first, the rest from the
   // back.  One atomic per warp and class: the jobs of a warp take consecutive slots.
-  const bool heavy = eCnt > kLightMax, very = eCnt > kVeryHeavy;
+  const bool mon = eCnt > kSplitLines && (A.flags[gp] & 3u) == 1u;  // anti-aliased, not the two-spanning-segments case
+  const bool heavy = eCnt > kLightMax && !mon, very = eCnt > kVeryHeavy;
   const int lane = threadIdx.x & 31;
   const unsigned act = __activemask();
   const unsigned balV = __ballot_sync(act, heavy && very), balH = __ballot_sync(act, heavy && !very);
-  if (heavy && very) {
+  const unsigned balM = __ballot_sync(act, mon);
+  if (mon) {
+    const int leader = __ffs(balM) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(A.heavyCount + 24, (unsigned long long)__popc(balM));
+    base = __shfl_sync(balM, base, leader);
+    A.monsterList[base + __popc(balM & ((1u << lane) - 1u))] = bj;
+  } else if (heavy && very) {
     const int leader = __ffs(balV) - 1;
     unsigned long long base = 0;
     if (lane == leader) base = atomicAdd(A.heavyCount, (unsigned long long)__popc(balV));
@@ -605,7 +621,22 @@ __global__ void __launch_bounds__(256) plan_classify_kernel(const RasterArgs A) 
   }
 }
 
+PXD unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void plan_light_impl(const RasterArgs& A);
 __global__ void __launch_bounds__(kLightThreads) plan_light_kernel(const RasterArgs A) {
+#ifdef PIXIE_RASTER_TIMING
+  if ((threadIdx.x & 31) == 0) atomicMax(&A.counters[52], ~gtime());
+#endif
+  plan_light_impl(A);
+#ifdef PIXIE_RASTER_TIMING
+  if ((threadIdx.x & 31) == 0) atomicMax(&A.counters[53], gtime());
+#endif
+}
+__device__ __forceinline__ void plan_light_impl(const RasterArgs& A) {
   __shared__ uint32_t lsm[kLightArrays * kLightMax * kLightThreads];
   const int tid = threadIdx.x;
   auto at = [&](int arr, int i) -> uint32_t& { return lsm[(arr * kLightMax + i) * kLightThreads + tid]; };
@@ -801,6 +832,9 @@ __global__ void __launch_bounds__(kLightThreads) plan_light_kernel(const RasterA
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+#ifdef PIXIE_RASTER_TIMING
+  if ((threadIdx.x & 31) == 0) atomicMax(&A.counters[50], ~gtime());
+#endif
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warpsPerBlock = blockDim.x >> 5;
   uint32_t* sscr = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * A.smemCap * kScratchArrays;
@@ -826,7 +860,12 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
   const float wf = (float)W;
   const int warpsTotal = gridDim.x * warpsPerBlock;
   // jobs plan_classify_kernel left for a whole warp: the very crowded ones from the front of the list, then the rest
-  const int numFront = (int)A.heavyCount[0], numHeavy = numFront + (int)A.heavyCount[8];
+  const int numFront = (int)A.heavyCount[0], numHeavy = numFront + (int)A.heavyCount[8], numMon = (int)A.heavyCount[24];
+  // Splitting pays when a few such scanlines would otherwise outlast the rest of the launch (the tiger: 362 of 93 k jobs);
+  // when there are thousands of them (an icon batch: 6 400) the launch is bound by its total work and they are planned
+  // whole like the others, first.
+  const bool doSplit = 5 * numMon <= 2 * warpsTotal;
+  const int monTickets = doSplit ? 5 * numMon : numMon;
   // Jobs are handed out one at a time from a counter (heavyCount[16] = counters[32 + launch]): they differ tenfold in
   // cost and the list starts with the most crowded ones, so whichever warp is free takes the next — a fixed stride left
   // most warps idle while a few finished their share.
@@ -835,8 +874,21 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
     int hj = 0;
     if (lane == 0) hj = (int)atomicAdd(A.heavyCount + 16, 1ull);
     hj = __shfl_sync(0xffffffffu, hj, 0);
-    if (hj >= numHeavy) break;
-    const int bj = A.heavyList[hj < numFront ? hj : A.planJobs - 1 - (hj - numFront)];
+    // The scanlines plan_classify_kernel put on the monster list are handed out five tickets per job, one per sample
+    // line: a scanline with hundreds of band entries is the longest single piece of work of the launch and its five
+    // lines are independent until their spans are concatenated.
+    if (hj >= numHeavy + monTickets) break;
+    int splitLine = 0;
+    int bj;
+    const bool isMon = doSplit && hj < monTickets;
+    if (hj < monTickets) {
+      const int idx = doSplit ? hj / 5 : hj;
+      splitLine = doSplit ? hj - idx * 5 : 0;
+      bj = A.monsterList[idx];
+    } else {
+      const int h2 = hj - monTickets;
+      bj = A.heavyList[h2 < numFront ? h2 : A.planJobs - 1 - (h2 - numFront)];
+    }
     const int f = find_fill_by_job(A.planJobBase, A.numFills, bj);
     const FillHeader* Hp = A.fills + f;
     const int startY = Hp->startY, rule = Hp->rule;
@@ -895,6 +947,10 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
       }
     }
     __syncwarp();
+    // one warp per sample line: anti-aliased scanlines that go through computeCoverage with the bitonic sort
+    const bool modeB = allSpan && (nsel % 2) == 0;
+    const bool split = isMon && !modeB && nsel > kBitonicMin && nsel <= kBitonicMax && scr != sscr;
+    if (!split && splitLine != 0) continue;  // planned whole by the line-0 ticket
 
     if (allSpan && (nsel % 2) == 0) {  // mode B (:1691-1872)
       float* tax = reinterpret_cast<float*>(scr + 2 * cap);
@@ -1006,6 +1062,87 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
     int* lineHits = sW + T;                            // [quality]
     constexpr int kNoHit = INT_MAX;
     hdr.kind = aa ? PlanCoverage : PlanSpans;
+    if (split) {
+      const int m = splitLine;
+      int P = 2 * kBitonicMin;
+      while (P < n) P <<= 1;
+      uint2* key = reinterpret_cast<uint2*>(sscr);
+      float yLine = (float)y + initialOffset - offset;
+#pragma unroll 1
+      for (int k = 0; k <= m; k++) yLine += offset;  // the reference accumulates yLine line by line (:1362-1371)
+#pragma unroll 1
+      for (int s_ = lane; s_ < P; s_ += 32) {
+        int at = kNoHit;
+        if (s_ < n) {
+          const Entry e = ent[selC[s_]];
+          if (e.ay <= yLine && e.by >= yLine) {
+            float x = e.m == 0.0f ? e.b : (yLine - e.b) / e.m;
+            x = (x != x) ? wf : (x < wf ? x : wf);  // min(x, width.float32)
+            at = fixed32(x);
+          }
+        }
+        key[s_] = make_uint2((uint32_t)s_, (uint32_t)at ^ 0x80000000u);  // kNoHit -> 0xFFFFFFFF sorts last
+      }
+      __syncwarp();
+      warp_bitonic_sort(key, P, lane);
+      int cnt = 0;
+#pragma unroll 1
+      for (int base = 0; base < n; base += 32) {
+        const int r_ = base + lane;
+        const uint2 kv = r_ < n ? key[r_] : make_uint2(0u, 0xFFFFFFFFu);
+        const bool hit = kv.y != 0xFFFFFFFFu;
+        if (hit) {
+          sAt[r_] = (int)(kv.y ^ 0x80000000u);
+          sW[r_] = ent[selC[kv.x]].winding;
+        }
+        cnt += __popc(__ballot_sync(0xffffffffu, hit));
+      }
+      __syncwarp();
+      int ns = 0;
+      if (lane == 0) ns = walk_spans(sAt, sW, cnt, rule, sAt, sW);
+      ns = __shfl_sync(0xffffffffu, ns, 0);
+      uint2* lp = pay + (size_t)m * (size_t)eCnt;
+#pragma unroll 1
+      for (int g = lane; g < ns; g += 32) lp[g] = make_uint2((uint32_t)sAt[g], (uint32_t)sW[g]);
+      if (lane == 0) lp[eCnt - 1] = make_uint2((uint32_t)ns, 0u);
+      __threadfence();
+      __syncwarp();
+      unsigned old = 0;
+      if (lane == 0) old = atomicInc(reinterpret_cast<unsigned*>(A.splitArrive + job), (unsigned)(quality - 1));
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old != (unsigned)(quality - 1)) continue;  // other lines of the scanline are still being planned
+      __threadfence();
+      int cntOf[5], S = 0;
+#pragma unroll
+      for (int q = 0; q < 5; q++) cntOf[q] = (int)__ldcg(reinterpret_cast<const unsigned*>(&pay[(size_t)q * eCnt + eCnt - 1].x));
+      int lo = INT_MAX, hi = INT_MIN;
+#pragma unroll 1
+      for (int q = 0; q < 5; q++) {
+        const uint2* srcp = pay + (size_t)q * (size_t)eCnt;
+#pragma unroll 1
+        for (int base = 0; base < cntOf[q]; base += 32) {
+          const int g = base + lane;
+          uint2 v = make_uint2(0u, 0u);
+          if (g < cntOf[q]) {
+            v.x = __ldcg(&srcp[g].x);
+            v.y = __ldcg(&srcp[g].y);
+          }
+          __syncwarp();
+          if (g < cntOf[q]) {
+            pay[S + g] = v;
+            lo = min(lo, fx_integer((int)v.x));
+            hi = max(hi, fx_integer((int)v.y) + 1);
+          }
+          __syncwarp();
+        }
+        S += cntOf[q];
+      }
+      hdr.n = S;
+      hdr.pa = __reduce_min_sync(0xffffffffu, lo);
+      hdr.pb = __reduce_max_sync(0xffffffffu, hi);
+      if (lane == 0) A.jobs[job] = hdr;
+      continue;
+    }
     if (n > 0) {
       if (n > kBitonicMin && n <= kBitonicMax && scr != sscr) {
         // crowded scanline: line after line, hits keyed {x, entry position} through the bitonic sort; the keys
@@ -1113,6 +1250,9 @@ __global__ void __launch_bounds__(256) plan_kernel(const RasterArgs A) {
     }
     if (lane == 0) A.jobs[job] = hdr;
   }
+#ifdef PIXIE_RASTER_TIMING
+  if ((threadIdx.x & 31) == 0) atomicMax(&A.counters[51], gtime());
+#endif
   if (A.gscratch) {
     __syncthreads();
     if (threadIdx.x == 0) atomicAnd(A.scratchSlots + (s_slot >> 5), ~(1u << (s_slot & 31)));
@@ -2251,7 +2391,11 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   const int blocksPerSm = std::max(1, occRaster), planPerSm = std::max(1, occPlan);
   long long wantBlocks = (totalRows * L.tiles + L.warpsPerBlock - 1) / L.warpsPerBlock;
   L.rasterBlocks = (int)std::max<long long>(1, std::min<long long>(wantBlocks, (long long)r.num_sms * blocksPerSm));
-  L.planBlocks = (int)std::max<long long>(1, std::min<long long>((jobsTotal + 7) / 8, (long long)r.num_sms * planPerSm));
+  // plan_kernel takes three blocks per SM, not the four its registers allow: the rest of the register file is
+  // plan_light_kernel's, which runs beside it (launch_plan_kernels)
+  static const int planCap = getenv("PIXIE_CUDA_PLAN_PER_SM") ? atoi(getenv("PIXIE_CUDA_PLAN_PER_SM")) : 3;
+  const int planRes = planCap > 0 ? std::min(planCap, planPerSm) : planPerSm;
+  L.planBlocks = (int)std::max<long long>(1, std::min<long long>((jobsTotal + 7) / 8, (long long)r.num_sms * planRes));
   L.scratchSlotCount = r.num_sms * planPerSm;
 
   // device-made part of block A: band counts, entry offsets, flags and counters
@@ -2473,7 +2617,7 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   const size_t jobsBytes = al(std::max<size_t>(1, (size_t)L.totalJobs) * sizeof(JobHdr));
   const size_t payBytes = al(std::max<size_t>(1, (size_t)meta[2]) * kPaySlots * sizeof(uint2));
   const size_t heavyBytes = al(std::max<size_t>(1, (size_t)L.totalJobs) * sizeof(int));
-  const size_t totalB = entriesBytes + jobsBytes + payBytes + heavyBytes + al((size_t)L.scratchSlotCount * 8 * L.scratchWords * 4);
+  const size_t totalB = entriesBytes + jobsBytes + payBytes + 3 * heavyBytes + al((size_t)L.scratchSlotCount * 8 * L.scratchWords * 4);
   if (arena) {
     void* blk;
     if (int rc = get_scratch(4, totalB, &blk)) return rc;
@@ -2485,7 +2629,10 @@ static int build_list(CmdList& L, bool arena, int bands, int w, int h, int layer
   L.jobs = (JobHdr*)(L.blockB + entriesBytes);
   L.payload = (uint2*)(L.blockB + entriesBytes + jobsBytes);
   L.heavyList = (int*)(L.blockB + entriesBytes + jobsBytes + payBytes);
-  L.scratch = L.scratchWords ? (uint32_t*)(L.blockB + entriesBytes + jobsBytes + payBytes + heavyBytes) : nullptr;
+  L.splitArrive = (int*)(L.blockB + entriesBytes + jobsBytes + payBytes + heavyBytes);
+  PX_CUDA(cudaMemsetAsync(L.splitArrive, 0, heavyBytes, r.stream));
+  L.monsterList = (int*)(L.blockB + entriesBytes + jobsBytes + payBytes + 2 * heavyBytes);
+  L.scratch = L.scratchWords ? (uint32_t*)(L.blockB + entriesBytes + jobsBytes + payBytes + 3 * heavyBytes) : nullptr;
   if (g_trace)
     fprintf(stderr, "[pixie_cuda] build_list: host plan %.3f ms (bounds %.3f), stage + device count/scan + readback %.3f ms "
             "(%zu B staged, blocks %zu + %zu B, %lld entries, max %d per band)\n",
@@ -2504,6 +2651,15 @@ static int launch_plan_kernels(const CmdList& L, const RasterArgs& A, int jobs, 
     PX_CUDA(cudaEventCreateWithFlags(&r.aux_join[auxIndex], cudaEventDisableTiming));
   }
   cudaStream_t aux = r.aux_stream[auxIndex];
+  static bool carve = false;
+  if (!carve && !getenv("PIXIE_CUDA_NO_CARVE")) {
+    // the two plan kernels are meant to share the SMs: with the shared-memory / L1 split the driver picks for the first
+    // of them alone, the blocks of the second do not fit until the first ones leave (measured: plan_light_kernel started
+    // 40 us after plan_kernel, when its blocks began to exit)
+    PX_CUDA(cudaFuncSetAttribute(plan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    PX_CUDA(cudaFuncSetAttribute(plan_light_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    carve = true;
+  }
   plan_classify_kernel<<<(jobs + 255) / 256, 256, 0, st>>>(A);
   PX_LAUNCHED();
   PX_CUDA(cudaEventRecord(r.aux_fork[auxIndex], st));
@@ -2556,6 +2712,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
   A.countCovered = covered_px ? 1 : 0;
   A.numFills = L.numFills;
   A.fillJobBase = L.fillJobBase; A.payOff = L.payOff; A.jobs = L.jobs; A.payload = L.payload; A.totalJobs = L.totalJobs;
+  A.splitArrive = L.splitArrive;
   A.rowBegin = 0; A.rowEnd = 0; A.ticketSlot = 0; A.clearFirst = L.clearFirst ? 1 : 0; A.subShift = 0;
   A.scratchSlots = L.scratchSlots; A.scratchSlotCount = L.scratchSlotCount;
   A.planJobBase = L.fillJobBase; A.planY0 = 0; A.planJobs = L.totalJobs;
@@ -2591,6 +2748,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
       ProfScope ps(kProfPlan);
       A.planJobBase = L.rowsJobBase; A.planY0 = rowY0; A.planJobs = run;
       A.heavyList = L.heavyList;
+      A.monsterList = L.monsterList;
       A.heavyCount = L.counters + 16;
       const int blocks = std::max(1, std::min((run + 7) / 8, L.planBlocks));
       if (int rc = launch_plan_kernels(L, A, run, blocks, r.stream, 0)) return rc;
@@ -2608,6 +2766,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
     if (L.totalJobs > 0) {
       ProfScope ps(kProfPlan);
       A.heavyList = L.heavyList;
+      A.monsterList = L.monsterList;
       A.heavyCount = L.counters + 16;
       if (int rc = launch_plan_kernels(L, A, L.totalJobs, L.planBlocks, r.stream, 0)) return rc;
     }
@@ -2625,6 +2784,8 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
       unsigned long long hc[64];
       cudaMemcpyAsync(hc, L.counters, 512, cudaMemcpyDeviceToHost, r.stream);
       cudaStreamSynchronize(r.stream);
+      fprintf(stderr, "[plan kernels, ns] heavy: start 0 end %llu | light: start %lld end %lld\n", hc[51] - ~hc[50], (long long)(~hc[52] - ~hc[50]),
+              (long long)(hc[53] - ~hc[50]));
       fprintf(stderr, "[raster tickets] n %llu  mean %.0f cycles  max %llu  >100k %llu  >50k %llu  >20k %llu  longest warp lifetime %llu cycles\n", hc[42],
               hc[42] ? (double)hc[41] / (double)hc[42] : 0.0, hc[40], hc[43], hc[44], hc[45], hc[46]);
     }
@@ -2667,6 +2828,7 @@ static int run_list(CmdList& L, Image* im, uint64_t* covered_px, uint8_t* host_p
       int before = 0;
       for (int bb = 0; bb < b; bb++) before += L.bandJobs[bb];
       B.heavyList = L.heavyList + before;
+      B.monsterList = L.monsterList + before;
       B.heavyCount = L.counters + 16 + b;
       const int blocks = std::max(1, std::min((L.bandJobs[b] + 7) / 8, L.planBlocks));
       if (int rc = launch_plan_kernels(L, B, L.bandJobs[b], blocks, r.band_stream[b], 1 + b)) return rc;
