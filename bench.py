@@ -1034,9 +1034,10 @@ def run_ours(args):
     roofline = {"kernel": "raster_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4),
                 # dram__bytes_read.sum + dram__bytes_write.sum of one raster_kernel launch on this workload, from the offline
-                # `ncu --set full` capture summarised in profiles/r02_tiger_metrics.txt (19.94 MB read + 14.69 MB written:
-                # the canvas stays in the 126 MB L2) — a capture, not measured by this run (traffic_source says so)
-                "traffic": 34633472 if size == 4096 else None, "traffic_source": "profiles/r02_tiger_metrics.txt (ncu capture)",
+                # `ncu --set full` capture summarised in profiles/r02_tiger_metrics.txt (18.07 MB read + 34.84 MB written, the
+                # latter incl. what reaches DRAM of the 64 MiB the launch clears: the canvas stays in the 126 MB L2) — a
+                # capture, not measured by this run (traffic_source says so)
+                "traffic": 52912896 if size == 4096 else None, "traffic_source": "profiles/r02_tiger_metrics.txt (ncu capture)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(rast, 4),
                 "partition_kernel_ms": round(part, 4), "plan_kernel_ms": round(statistics.mean(plan_ms), 4), "share_of_step": round(rast / statistics.mean(step_ms), 3),
