@@ -19,7 +19,7 @@ for r in rows:
         cur['rows'].append(r)
 short = re.search(r'pixie(\d+)([a-z_]+)', kname)
 short = short.group(2)[:int(short.group(1))] if short else kname
-sec = [s for s in secs if ('::' + short + '(') in s['name']][-1]
+sec = [s for s in secs if ('::' + short + '(') in s['name'] or ('::' + short + '<') in s['name']][-1]
 ci = sec['ci']
 seq, cur_line, cur_fn = [], None, None
 for ln in open(dis_txt):
